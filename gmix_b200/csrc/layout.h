@@ -1,0 +1,133 @@
+// Host-side sizing of one stream arena (the global-memory workspace a CTA reuses across the
+// streams it processes) and of the host-precomputed libm tables. Pure C++ (no CUDA): used by the
+// C-ABI library and by the CPU emulation tests.
+#ifndef GMIX_B200_LAYOUT_H_
+#define GMIX_B200_LAYOUT_H_
+#include <math.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "stream_kernel.cuh"
+
+namespace gmx {
+
+inline uint64_t AlignUp(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+// max_len = longest stream (in uncompressed bytes) the arena must hold.
+inline ArenaLayout MakeLayout(uint64_t max_len) {
+  static const IndirectSpec ind[NIND] = {GMX_INDIRECT_SPECS};
+  static const IHSpec ih[NIH] = {GMX_IH_SPECS};
+  static const MatchSpec mt[NMATCH] = {GMX_MATCH_SPECS};
+  static const MixerSpec mx[NMIX] = {GMX_MIXER_SPECS};
+  ArenaLayout L;
+  memset(&L, 0, sizeof(L));
+  uint64_t off = 0;
+  auto take = [&](uint64_t bytes) { uint64_t o = off; off = AlignUp(off + bytes, 256); return o; };
+  for (int k = 0; k < NIND; ++k) {
+    L.ind_size[k] = (1u << ind[k].log2) * 256 + 1;  // indirect.cpp:15-19
+    L.ind_tab[k] = take(((uint64_t)L.ind_size[k] + 1) / 2 * 4);
+  }
+  L.ind_pred = take((uint64_t)NIND * 512 * 4);
+  for (int k = 0; k < NMATCH; ++k) L.match_tab[k] = take((4ull << mt[k].log2));
+  L.match_pred = take(NMATCH * 256 * 4);
+  L.match_cnt = take(NMATCH * 256 * 4);
+  L.history_cap = max_len + 8;
+  L.history = take(L.history_cap);
+  for (int k = 0; k < NIH; ++k) L.ih_tab[k] = take(4ull << ih[k].log2);
+  // Weight-set pool: a mixer can create at most one set per distinct gate context it ever sees:
+  // min(table size, bytes + 1) for byte-level contexts, min(table size, bits + 1) otherwise.
+  uint64_t sets = 1;
+  for (int m = 0; m < NMIX; ++m) {
+    L.mix_dir[m] = take(4ull << mx[m].log2);
+    const uint64_t t = 1ull << mx[m].log2;
+    const bool bit_level = mx[m].ctx == C_SLPR || mx[m].ctx == C_LBPR || mx[m].ctx == C_BIT_CONTEXT || mx[m].ctx == C_LONGEST;
+    const uint64_t seen = bit_level ? 8 * max_len + 1 : max_len + 1;
+    sets += t < seen ? t : seen;
+  }
+  L.mix_pool_sets = (uint32_t)sets;
+  L.mix_set_stride = 116;  // 2 header words + up to 114 weights, 16-byte multiple
+  L.mix_pool = take(sets * L.mix_set_stride * 4);
+  const uint64_t wsz = 3ull * L_ROW * L_CELLS * 4;
+  L.l_w = take(wsz); L.l_m = take(wsz); L.l_v = take(wsz);
+  L.l_gb = take(8 * 3 * L_CELLS * 4);
+  L.l_wout = take((uint64_t)L_HORIZON * L_HID * L_NOUT * 4);
+  L.l_lin = take((uint64_t)L_HORIZON * (L_NIN + 1) * 4);
+  L.l_out = take((uint64_t)L_HORIZON * L_NOUT * 4);
+  L.l_gstate = take(3ull * L_HORIZON * L_CELLS * 4);
+  L.l_norm = take(3ull * L_HORIZON * L_CELLS * 4);
+  L.l_ivar = take(3ull * L_HORIZON * 4);
+  L.l_tanh = take((uint64_t)L_HORIZON * L_CELLS * 4);
+  L.l_ig = take((uint64_t)L_HORIZON * L_CELLS * 4);
+  L.l_last = take((uint64_t)L_HORIZON * L_CELLS * 4);
+  L.l_errh = take(3ull * L_HORIZON * L_CELLS * 4);
+  L.p_state = take(sizeof(PpmdState));
+  L.p_text_cap = (uint32_t)(max_len + 64);
+  L.p_text = take(AlignUp(L.p_text_cap, 4));
+  uint64_t units = AlignUp(96 * max_len + (256u << 10), 48);  // ~19 B/byte on text
+  const uint64_t units_max = 800ull << 20;                   // must stay below half of the virtual units area
+  if (units > units_max) units = units_max / 48 * 48;
+  L.p_units_cap = (uint32_t)units;
+  L.p_units = take(units);
+  L.total = off;
+  return L;
+}
+
+// decay[s] = (float)(0.9 / pow(0.0000001 * s + 0.8, 0.8)) — mixer.cpp:111, a function of the mixer's
+// global step counter only; evaluated with the HOST libm exactly as the reference does.
+inline void FillDecayTable(std::vector<float>& t, uint64_t n) {
+  const uint64_t old = t.size();
+  if (n <= old) return;
+  t.resize(n);
+  for (uint64_t s = old; s < n; ++s) {
+    unsigned long long steps = s;
+    float decay = 0.9 / pow(0.0000001 * steps + 0.8, 0.8);
+    t[s] = decay;
+  }
+}
+
+// Adam scalars per update step t = 1..3000 (lstm-layer.cpp:12-34): alpha, 1 - beta1^t, 1 - beta2^t,
+// with the reference's exact expression types (powf below the limit, double pow at the limit).
+inline void FillAdamTable(std::vector<float>& t) {
+  t.assign(4 * (L_UPDATE_LIMIT + 1), 0.0f);
+  const float beta1 = 0.025, beta2 = 0.9999;
+  const float learning_rate = 0.03;
+  const unsigned long long update_limit = L_UPDATE_LIMIT;
+  for (unsigned long long steps = 1; steps <= update_limit; ++steps) {
+    float tt = steps;
+    float alpha, d1, d2;
+    if (tt < update_limit) {
+      alpha = learning_rate * 0.1f / sqrtf(5e-5f * tt + 1.0f);
+      d1 = (float)(1.0f - powf(beta1, tt));
+      d2 = (float)(1.0f - powf(beta2, tt));
+    } else {
+      alpha = learning_rate * 0.1f / sqrtf(5e-5f * update_limit + 1.0f);
+      d1 = (float)(1.0f - pow((double)beta1, (double)update_limit));
+      d2 = (float)(1.0f - pow((double)beta2, (double)update_limit));
+    }
+    t[4 * steps + 0] = alpha; t[4 * steps + 1] = d1; t[4 * steps + 2] = d2;
+  }
+}
+
+// Initial LSTM gate weights (lstm-layer.cpp:176-195): srand(0xDEADBEEF) (predictor.cpp:18), then
+// per cell i, per column j, one glibc rand() draw for each of the three gates in turn; forget-gate
+// bias column = 1. Stored transposed: out[(g * L_ROW + j) * L_CELLS + i].
+inline void FillLstmInit(std::vector<float>& out) {
+  out.assign(3ull * L_ROW * L_CELLS, 0.0f);
+  srand(0xDEADBEEF);
+  float val = sqrtf(6.0f / float(256 + 256));
+  float low = -val;
+  float range = 2 * val;
+  for (int i = 0; i < L_CELLS; ++i) {
+    for (int j = 0; j < L_ROW; ++j) {
+      for (int g = 0; g < 3; ++g) {
+        float r = static_cast<float>(rand()) / static_cast<float>(RAND_MAX);
+        out[((size_t)g * L_ROW + j) * L_CELLS + i] = low + r * range;
+      }
+    }
+    out[((size_t)0 * L_ROW + (L_ROW - 1)) * L_CELLS + i] = 1;
+  }
+}
+
+}  // namespace gmx
+#endif

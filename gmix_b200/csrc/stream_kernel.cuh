@@ -1,0 +1,1033 @@
+// One CTA per stream: the complete gmix bit step (reference src/predictor.cpp:360-387 and every
+// Model::Predict/Learn it calls) plus the binary arithmetic coder (src/coder/*.cpp), for
+// compress and decompress. Persistent CTAs pull stream ids from an atomic queue and reuse their
+// arena (global-memory workspace) across streams.
+//
+// Exactness rules: every fp32 operation goes through
+// gmx::f_* (single IEEE rounding, never contracted), every dot product is accumulated by ONE
+// thread in the reference's index order, libm calls go through gmx::gm_* (dmath.cuh). Parallelism
+// inside a stream is only across independent quantities (the 41 Indirect models, the 24 layer-0
+// mixers, the 150 LSTM gate rows, the 2697 mixer weights, ...).
+//
+// The file is plain CUDA C++ that also compiles for the host under tests/emu/cuda_emu.h (a fiber
+// based SIMT emulator used by the CPU test-suite to debug the kernel logic without a GPU). The
+// shipped library only contains the nvcc build.
+#ifndef GMIX_B200_STREAM_KERNEL_CUH_
+#define GMIX_B200_STREAM_KERNEL_CUH_
+#include <stdint.h>
+
+#include "dmath.cuh"
+#include "ppmd.cuh"
+#include "spec.cuh"
+
+namespace gmx {
+
+enum : uint32_t {
+  GMX_OK = 0,
+  GMX_ERR_PPMD_ARENA = 1,    // backed part of the PPMd heap exhausted
+  GMX_ERR_MIXER_POOL = 2,    // mixer weight-set pool exhausted
+  GMX_ERR_OUTPUT_CAP = 3,    // output slice too small
+  GMX_ERR_MATCH_RANGE = 4,   // Match pointer outside history (reference would throw, match.cpp:55)
+  GMX_ERR_HISTORY_CAP = 5,
+  GMX_ERR_BAD_HEADER = 6,
+};
+
+enum : int { WSTRIDE = 117 };  // smem stride of one staged mixer weight set (odd: conflict-free lanes)
+
+// Byte offsets (from the arena base) of every per-stream table. Filled by the host (layout.h).
+struct ArenaLayout {
+  uint64_t ind_tab[NIND];     // u16 {ns | rm<<8} per slot, (2^log2*256+1) slots (indirect.cpp:15-19)
+  uint32_t ind_size[NIND];
+  uint64_t ind_pred;          // float [NIND][2][256]
+  uint64_t match_tab[NMATCH]; // u32 history pointers (5-byte pointers in the reference, match.cpp:48-49)
+  uint64_t match_pred;        // float [NMATCH][256]
+  uint64_t match_cnt;         // int   [NMATCH][256]
+  uint64_t history; uint64_t history_cap;
+  uint64_t ih_tab[NIH];       // u32
+  uint64_t mix_dir[NMIX];     // u32 pool id per gate context (0 = no weight set yet)
+  uint64_t mix_pool; uint32_t mix_pool_sets; uint32_t mix_set_stride;  // floats per set record
+  // LSTM
+  uint64_t l_w, l_m, l_v;     // float [3][L_ROW][L_CELLS] (row-major by input column: coalesced over cells)
+  uint64_t l_gb;              // float [8][3][L_CELLS]: gamma, beta, gamma_m, gamma_v, beta_m, beta_v, gamma_u, beta_u
+  uint64_t l_wout;            // float [L_HORIZON][L_HID][L_NOUT]
+  uint64_t l_lin;             // float [L_HORIZON][L_NIN + 1]
+  uint64_t l_out;             // float [L_HORIZON][L_NOUT]
+  uint64_t l_gstate, l_norm;  // float [3][L_HORIZON][L_CELLS]
+  uint64_t l_ivar;            // float [3][L_HORIZON]
+  uint64_t l_tanh, l_ig, l_last;  // float [L_HORIZON][L_CELLS]
+  uint64_t l_errh;            // float [3][L_HORIZON][L_CELLS]
+  // PPMd
+  uint64_t p_state; uint64_t p_text; uint64_t p_units; uint32_t p_text_cap; uint32_t p_units_cap;
+  uint64_t total;             // arena bytes
+};
+
+struct StreamParams {
+  const uint8_t* in; const uint64_t* in_off;     // n_streams + 1 offsets
+  uint8_t* out; const uint64_t* out_off;         // n_streams + 1 offsets (capacity slices)
+  uint64_t* out_len; uint32_t* status;           // per stream
+  uint32_t n_streams; uint32_t* queue;           // atomic stream counter
+  uint8_t* arenas; uint64_t arena_stride;
+  const ArenaLayout* layout;
+  const float* lstm_init;    // [3][L_ROW][L_CELLS] initial gate weights (host glibc rand(), lstm-layer.cpp:176-195)
+  const float* decay;        // decay[s] = (float)(0.9 / pow(1e-7*s + 0.8, 0.8)) (mixer.cpp:111), host libm
+  uint32_t decay_len;
+  const float* adam;         // [L_UPDATE_LIMIT + 1][4]: alpha, 1-b1^t, 1-b2^t (lstm-layer.cpp:16-33), host libm
+  uint64_t* bit_trace;       // optional: {f32 prob, u32 p16} per bit of stream 0 (debug/parity), or null
+  float* pred_trace;         // optional: 90 predictions + 3 mask words + 33 mixer outs per bit of stream 0
+};
+
+// ---- device constant tables --------------------------------------------------------------------
+#if defined(__CUDACC__)
+#define GMX_CONST_TABLE static __device__ const
+#else
+#define GMX_CONST_TABLE static const
+#endif
+GMX_CONST_TABLE IndirectSpec kInd[NIND] = {GMX_INDIRECT_SPECS};
+GMX_CONST_TABLE SkipSpec kSkip[20] = {GMX_SKIP_SPECS};
+GMX_CONST_TABLE IntervalSpec kInterval[9] = {GMX_INTERVAL_SPECS};
+GMX_CONST_TABLE IHSpec kIH[NIH] = {GMX_IH_SPECS};
+GMX_CONST_TABLE MatchSpec kMatch[NMATCH] = {GMX_MATCH_SPECS};
+GMX_CONST_TABLE MixerSpec kMixer[NMIX] = {GMX_MIXER_SPECS};
+GMX_CONST_TABLE uint8_t kNonstationary[512] = {
+#include "nonstationary.inc"
+};
+
+// ---- per-stream state staged in shared memory ---------------------------------------------------
+struct StreamSmem {
+  // blackboard (ShortTermMemory)
+  float preds[NPRED + 2];
+  uint8_t act[NPRED + 6];
+  uint32_t ctx[C_COUNT + 2];
+  float l0_out[NL0], l1_out[NL1], final_out, prob;
+  float ppm[256], lprob[256];          // byte distributions of PPMd and LSTM
+  float node_ppm[256], node_lstm[256]; // Logit(p) of every node of the binary interval search
+  uint8_t nflag_ppm[256], nflag_lstm[256];  // bit0: denom != 0, bit1: p != 0.5
+  uint32_t sqp[256];
+  uint8_t ring[1000];
+  uint32_t ring_pos;
+  int32_t new_bit, recent_bits, bb, first_prediction, analysis;
+  uint32_t error;
+  uint32_t steps;                      // Mixer::steps_ (identical for all 33 mixers)
+  // mixers
+  float w[NMIX * WSTRIDE];
+  uint32_t set_steps[NMIX], max_steps[NMIX], set_idx[NMIX], set_pool[NMIX], new_idx[NMIX];
+  uint8_t swap[NMIX + 3], shrink[NMIX + 3];
+  float upd[NMIX];
+  uint32_t pool_next;
+  // indirect
+  uint32_t ind_base[NIND], ind_slot[NIND];
+  uint16_t ind_state[NIND + 1];
+  // match
+  uint32_t m_cur[NMATCH]; uint8_t m_byte[NMATCH], m_bitpos[NMATCH], m_len[NMATCH];
+  uint32_t hist_len;
+  // indirect hash
+  uint64_t ih_outer[NIH]; uint32_t ih_hash[NIH];
+  // LSTM
+  float l_in[L_NIN + 1];
+  float l_hidden[L_HID + 1], l_state[L_CELLS], l_state_err[L_CELLS], l_stored_err[L_CELLS], l_hidden_err[L_CELLS];
+  float l_gate[3][L_CELLS], l_gerr[3][L_CELLS];
+  float l_red[16];
+  float l_err256[256];
+  uint8_t l_hist[L_HORIZON], l_symin[L_HORIZON];
+  uint32_t l_epoch, l_update_steps, l_old_input;
+  // coder
+  uint32_t x1, x2, x;
+  uint64_t out_pos, out_cap, in_pos, in_len;
+};
+
+struct Arena {
+  uint8_t* base;
+  const ArenaLayout* L;
+  template <typename T> GMX_DEV T* at(uint64_t off) const { return (T*)(base + off); }
+};
+
+// ---- small helpers -----------------------------------------------------------------------------
+GMX_DEV inline uint32_t Rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+GMX_DEV inline uint32_t MurmurMix(uint32_t h, uint32_t k) {
+  k *= 0xcc9e2d51u; k = Rotl32(k, 15); k *= 0x1b873593u;
+  h ^= k; h = Rotl32(h, 13); return h * 5 + 0xe6546b64u;
+}
+GMX_DEV inline uint32_t MurmurFinal(uint32_t h, uint32_t len) {
+  h ^= len; h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16; return h;
+}
+// MurmurHash3_x86_32 of a little-endian u64 / u32, seed 0xDEADBEEF (murmur-hash.cpp:94-146).
+GMX_DEV inline uint32_t Murmur64(uint64_t v) {
+  uint32_t h = 0xDEADBEEFu;
+  h = MurmurMix(h, (uint32_t)v); h = MurmurMix(h, (uint32_t)(v >> 32));
+  return MurmurFinal(h, 8);
+}
+GMX_DEV inline uint32_t Murmur32(uint32_t v) { return MurmurFinal(MurmurMix(0xDEADBEEFu, v), 4); }
+
+GMX_DEV inline uint32_t RecentByte(const StreamSmem& s, int ago) {  // short-term-memory.cpp:215-219
+  int pos = (int)s.ring_pos - ago;
+  if (pos < 0) pos += 1000;
+  return s.ring[pos];
+}
+GMX_DEV inline int MixerNW(int m) { return m < NL0 ? NPRED + m : m < NL0 + NL1 ? NL0 + (m - NL0) + 1 : NL0 + NL1 + 1; }
+
+GMX_DEV inline void BlockSync() { __syncthreads(); }
+
+// ---- stream start ------------------------------------------------------------------------------
+template <int NT>
+GMX_DEV void FillWords(uint32_t* p, uint64_t nwords, uint32_t v, int tid) {
+  for (uint64_t i = tid; i < nwords; i += NT) p[i] = v;
+}
+
+template <int NT>
+GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, int tid) {
+  const ArenaLayout& L = *A.L;
+  for (int k = 0; k < NIND; ++k) FillWords<NT>(A.at<uint32_t>(L.ind_tab[k]), ((uint64_t)L.ind_size[k] + 1) / 2, 0x00FF00FFu, tid);
+  FillWords<NT>(A.at<uint32_t>(L.ind_pred), NIND * 512, 0u, tid);
+  for (int k = 0; k < NMATCH; ++k) FillWords<NT>(A.at<uint32_t>(L.match_tab[k]), 1ull << kMatch[k].log2, 0u, tid);
+  for (int i = tid; i < NMATCH * 256; i += NT) {
+    A.at<float>(L.match_pred)[i] = (float)(0.5 + ((double)(i & 255) + 0.5) / 512);  // match.cpp:19-21
+    A.at<int>(L.match_cnt)[i] = 1;
+  }
+  for (int k = 0; k < NIH; ++k) FillWords<NT>(A.at<uint32_t>(L.ih_tab[k]), 1ull << kIH[k].log2, 0u, tid);
+  for (int m = 0; m < NMIX; ++m) FillWords<NT>(A.at<uint32_t>(L.mix_dir[m]), 1ull << kMixer[m].log2, 0u, tid);
+  // LSTM (lstm.cpp:8-43, lstm-layer.cpp:36-54,156-196)
+  for (int i = tid; i < 3 * L_ROW * L_CELLS; i += NT) {
+    A.at<float>(L.l_w)[i] = P.lstm_init[i];
+    A.at<float>(L.l_m)[i] = 0.0f;
+    A.at<float>(L.l_v)[i] = 0.0f;
+  }
+  for (int i = tid; i < 8 * 3 * L_CELLS; i += NT) A.at<float>(L.l_gb)[i] = i < 3 * L_CELLS ? 1.0f : 0.0f;
+  FillWords<NT>(A.at<uint32_t>(L.l_wout), L_HID * L_NOUT, 0u, tid);  // epoch slot 0; others are written before read
+  for (int e = tid; e < L_HORIZON; e += NT) A.at<float>(L.l_lin)[e * (L_NIN + 1) + L_NIN - 1] = 1.0f;
+  // PPMd heap must start zeroed (mod_ppmd.cpp relies on fresh pages)
+  FillWords<NT>(A.at<uint32_t>(L.p_text), (L.p_text_cap + 3) / 4, 0u, tid);
+  FillWords<NT>(A.at<uint32_t>(L.p_units), L.p_units_cap / 4, 0u, tid);
+  // shared state
+  for (int i = tid; i < NPRED + 2; i += NT) s.preds[i] = 0.0f;
+  for (int i = tid; i < NPRED + 6; i += NT) s.act[i] = 0;
+  for (int i = tid; i < C_COUNT + 2; i += NT) s.ctx[i] = 0;
+  for (int i = tid; i < NL0; i += NT) s.l0_out[i] = 0.0f;
+  for (int i = tid; i < NL1; i += NT) s.l1_out[i] = 0.0f;
+  for (int i = tid; i < 256; i += NT) { s.ppm[i] = (float)(1.0 / 256); s.lprob[i] = (float)(1.0 / 256); }
+  for (int i = tid; i < 1000; i += NT) s.ring[i] = 0;
+  for (int i = tid; i < NMIX * WSTRIDE; i += NT) s.w[i] = 0.0f;
+  for (int i = tid; i < NMIX; i += NT) {
+    s.set_steps[i] = 0; s.max_steps[i] = 1; s.set_idx[i] = 0xFFFFFFFFu; s.set_pool[i] = 0; s.swap[i] = 0; s.shrink[i] = 0;
+  }
+  for (int i = tid; i < NMATCH; i += NT) { s.m_cur[i] = 0; s.m_byte[i] = 0; s.m_bitpos[i] = 128; s.m_len[i] = 0; }
+  for (int i = tid; i < NIH; i += NT) { s.ih_outer[i] = 0; s.ih_hash[i] = 0; }
+  for (int i = tid; i < L_HID + 1; i += NT) s.l_hidden[i] = i == L_HID - 1 ? 1.0f : 0.0f;
+  for (int i = tid; i < L_CELLS; i += NT) { s.l_state[i] = 0; s.l_state_err[i] = 0; s.l_stored_err[i] = 0; s.l_hidden_err[i] = 0; }
+  for (int i = tid; i < L_HORIZON; i += NT) { s.l_hist[i] = 0; s.l_symin[i] = 0; }
+  if (tid == 0) {
+    s.final_out = 0; s.prob = 0.5f; s.ring_pos = 0; s.new_bit = 0; s.recent_bits = 1; s.bb = 0;
+    s.first_prediction = 1; s.error = 0; s.steps = 0; s.pool_next = 1; s.hist_len = 0;
+    s.l_epoch = 0; s.l_update_steps = 0; s.l_old_input = 0; s.l_in[L_NIN] = 0;
+    s.x1 = 0; s.x2 = 0xffffffffu; s.x = 0;
+  }
+  BlockSync();
+  if (tid == 0) {
+    Ppmd pm{A.at<PpmdState>(L.p_state), A.at<uint8_t>(L.p_text), A.at<uint8_t>(L.p_units), L.p_text_cap, L.p_units_cap, s.sqp};
+    pm.Init();
+  }
+  BlockSync();
+}
+
+// ---- LSTM forward at a byte boundary (Lstm::Predict lstm.cpp:91-122, LstmLayer::ForwardPass
+// lstm-layer.cpp:198-241). Precondition: s.ppm holds the normalised PPMd distribution. --------------
+template <int NT>
+GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, int tid) {
+  const ArenaLayout& L = *A.L;
+  const uint32_t e = s.l_epoch;
+  const uint32_t sym = s.ctx[C_LAST_BYTE];
+  float* lin_e = A.at<float>(L.l_lin) + e * (L_NIN + 1);
+  // layer_input[e] = [ppm 256 | hidden 50 | 1]  (SetInput lstm.cpp:45-50, copy :94-96)
+  for (int i = tid; i < L_NIN; i += NT) {
+    const float v = i < 256 ? s.ppm[i] : i < 306 ? s.l_hidden[i - 256] : 1.0f;
+    s.l_in[i] = v;
+    lin_e[i] = v;
+  }
+  if (tid < L_CELLS) A.at<float>(L.l_last)[e * L_CELLS + tid] = s.l_state[tid];  // last_state_[epoch] = state_
+  BlockSync();
+  // gate pre-activations: f = w[sym]; f += in[j] * w[256 + j], j ascending (lstm-layer.cpp:227-232)
+  for (int t = tid; t < 3 * L_CELLS; t += NT) {
+    const int g = t / L_CELLS, i = t - g * L_CELLS;
+    const float* w = A.at<float>(L.l_w) + (size_t)g * L_ROW * L_CELLS + i;
+    float f = w[(size_t)sym * L_CELLS];
+    const float* wd = w + (size_t)L_NOUT * L_CELLS;
+#pragma unroll 4
+    for (int j = 0; j < L_NIN; ++j) f = f_add(f, f_mul(s.l_in[j], wd[(size_t)j * L_CELLS]));
+    s.l_gate[g][i] = f;
+  }
+  BlockSync();
+  // ivar = 1 / sqrt(sum(norm^2)/cells + 1e-5): _Expr::sum() runs descending (lstm-layer.cpp:233-236)
+  if (tid < 3) {
+    const float* nrm = s.l_gate[tid];
+    float acc = f_mul(nrm[L_CELLS - 1], nrm[L_CELLS - 1]);
+    for (int i = L_CELLS - 2; i >= 0; --i) acc = f_add(acc, f_mul(nrm[i], nrm[i]));
+    const float ivar = f_div(1.0f, f_sqrt(f_add(f_div(acc, (float)L_CELLS), 1e-5f)));
+    s.l_red[tid] = ivar;
+    A.at<float>(L.l_ivar)[tid * L_HORIZON + e] = ivar;
+  }
+  BlockSync();
+  for (int t = tid; t < 3 * L_CELLS; t += NT) {
+    const int g = t / L_CELLS, i = t - g * L_CELLS;
+    const float* gb = A.at<float>(L.l_gb);
+    const float nrm = f_mul(s.l_gate[g][i], s.l_red[g]);
+    A.at<float>(L.l_norm)[((size_t)g * L_HORIZON + e) * L_CELLS + i] = nrm;
+    float st = f_add(f_mul(nrm, gb[g * L_CELLS + i]), gb[(3 + g) * L_CELLS + i]);  // norm*gamma + beta
+    st = g == 1 ? gm_tanhf(st) : Logistic(st);  // lstm-layer.cpp:205-211
+    s.l_gate[g][i] = st;
+    A.at<float>(L.l_gstate)[((size_t)g * L_HORIZON + e) * L_CELLS + i] = st;
+  }
+  BlockSync();
+  if (tid < L_CELLS) {  // lstm-layer.cpp:212-217
+    const int i = tid;
+    const float F = s.l_gate[0][i], I = s.l_gate[1][i], O = s.l_gate[2][i];
+    const float ig = f_sub(1.0f, F);
+    float st = f_mul(s.l_state[i], F);
+    st = f_add(st, f_mul(I, ig));
+    const float th = gm_tanhf(st);
+    s.l_state[i] = st;
+    s.l_hidden[i] = f_mul(O, th);
+    A.at<float>(L.l_ig)[e * L_CELLS + i] = ig;
+    A.at<float>(L.l_tanh)[e * L_CELLS + i] = th;
+  }
+  BlockSync();
+  // output layer: sum_j hidden[j] * Wout[e][i][j], j ascending, hidden[50] = 1 (lstm.cpp:105-113)
+  const float* wo = A.at<float>(L.l_wout) + (size_t)e * L_HID * L_NOUT;
+  float mx = 0.0f;
+  for (int i = tid; i < L_NOUT; i += NT) {
+    float acc = 0.0f;
+#pragma unroll 3
+    for (int j = 0; j < L_HID; ++j) acc = f_add(acc, f_mul(s.l_hidden[j], wo[j * L_NOUT + i]));
+    s.l_err256[i] = acc;
+    mx = acc > mx ? acc : mx;
+  }
+  // max over all outputs, seeded with 0 (max is order independent)
+  for (int o = 16; o > 0; o >>= 1) { const float v = __shfl_xor_sync(0xffffffffu, mx, o); mx = v > mx ? v : mx; }
+  if ((tid & 31) == 0) s.l_red[4 + (tid >> 5)] = mx;
+  BlockSync();
+  mx = 0.0f;
+  for (int wi = 0; wi < NT / 32; ++wi) { const float v = s.l_red[4 + wi]; mx = v > mx ? v : mx; }
+  for (int i = tid; i < L_NOUT; i += NT) s.lprob[i] = gm_expf(f_sub(s.l_err256[i], mx));
+  BlockSync();
+  if (tid == 0) {  // valarray::sum(): ascending, seeded with element 0 (lstm.cpp:118)
+    float acc = s.lprob[0];
+    for (int i = 1; i < L_NOUT; ++i) acc = f_add(acc, s.lprob[i]);
+    s.l_red[3] = acc;
+  }
+  BlockSync();
+  const float denom = s.l_red[3];
+  for (int i = tid; i < L_NOUT; i += NT) {
+    const float v = f_div(s.lprob[i], denom);
+    s.lprob[i] = v;
+    A.at<float>(L.l_out)[e * L_NOUT + i] = v;
+  }
+  if (tid == 0) s.l_epoch = e + 1 == L_HORIZON ? 0 : e + 1;
+  BlockSync();
+}
+
+// Truncated BPTT over the 100 stored steps + Adam (Lstm::Perceive lstm.cpp:57-79,
+// LstmLayer::BackwardPass lstm-layer.cpp:252-354). Weight gradients are accumulated per weight in
+// the reference's epoch order (99 -> 0) by the thread that owns the weight, then Adam is applied.
+template <int NT>
+GMX_DEV void LstmBptt(StreamSmem& s, const Arena& A, const StreamParams& P, int tid) {
+  const ArenaLayout& L = *A.L;
+  float* gb = A.at<float>(L.l_gb);
+  const float* W = A.at<float>(L.l_w);
+  float* errh = A.at<float>(L.l_errh);
+  for (int ep = L_HORIZON - 1; ep >= 0; --ep) {
+    const float* out_e = A.at<float>(L.l_out) + ep * L_NOUT;
+    for (int i = tid; i < L_NOUT; i += NT)
+      s.l_err256[i] = (uint32_t)i == s.l_hist[ep] ? f_sub(out_e[i], 1.0f) : out_e[i];
+    BlockSync();
+    if (tid < L_CELLS) {
+      // hidden_error[j] += Wout[ep][i][j] * err_i, i ascending; hidden_error is 0 on entry (lstm.cpp:60-70)
+      const float* wo = A.at<float>(L.l_wout) + ((size_t)ep * L_HID + tid) * L_NOUT;
+      float he = s.l_hidden_err[tid];
+#pragma unroll 4
+      for (int i = 0; i < L_NOUT; ++i) he = f_add(he, f_mul(wo[i], s.l_err256[i]));
+      // LstmLayer::BackwardPass lstm-layer.cpp:256-281
+      const int i = tid;
+      float stored = ep == L_HORIZON - 1 ? he : f_add(s.l_stored_err[i], he);
+      float se = ep == L_HORIZON - 1 ? 0.0f : s.l_state_err[i];
+      const float th = A.at<float>(L.l_tanh)[ep * L_CELLS + i];
+      const float ig = A.at<float>(L.l_ig)[ep * L_CELLS + i];
+      const float ls = A.at<float>(L.l_last)[ep * L_CELLS + i];
+      const float F = A.at<float>(L.l_gstate)[((size_t)0 * L_HORIZON + ep) * L_CELLS + i];
+      const float I = A.at<float>(L.l_gstate)[((size_t)1 * L_HORIZON + ep) * L_CELLS + i];
+      const float O = A.at<float>(L.l_gstate)[((size_t)2 * L_HORIZON + ep) * L_CELLS + i];
+      s.l_gerr[2][i] = f_mul(f_mul(f_mul(th, stored), O), f_sub(1.0f, O));
+      se = f_add(se, f_mul(f_mul(stored, O), f_sub(1.0f, f_mul(th, th))));
+      s.l_gerr[1][i] = f_mul(f_mul(se, ig), f_sub(1.0f, f_mul(I, I)));
+      s.l_gerr[0][i] = f_mul(f_mul(f_mul(f_sub(ls, I), se), F), ig);
+      s.l_hidden_err[i] = 0.0f;
+      if (ep > 0) { se = f_mul(se, F); stored = 0.0f; }
+      s.l_state_err[i] = se;
+      s.l_stored_err[i] = stored;
+    }
+    if (tid == 0 && ep == 0 && s.l_update_steps < (uint32_t)L_UPDATE_LIMIT) s.l_update_steps++;
+    BlockSync();
+    // per gate (lstm-layer.cpp:313-318): beta_u += err; gamma_u += err*norm; err *= gamma*ivar
+    for (int t = tid; t < 3 * L_CELLS; t += NT) {
+      const int g = t / L_CELLS, i = t - g * L_CELLS;
+      const float err = s.l_gerr[g][i];
+      const float nrm = A.at<float>(L.l_norm)[((size_t)g * L_HORIZON + ep) * L_CELLS + i];
+      const float gu = ep == L_HORIZON - 1 ? 0.0f : gb[(6 * 3 + g) * L_CELLS + i];
+      const float bu = ep == L_HORIZON - 1 ? 0.0f : gb[(7 * 3 + g) * L_CELLS + i];
+      gb[(7 * 3 + g) * L_CELLS + i] = f_add(bu, err);
+      gb[(6 * 3 + g) * L_CELLS + i] = f_add(gu, f_mul(err, nrm));
+      s.l_gerr[g][i] = f_mul(err, f_mul(gb[g * L_CELLS + i], A.at<float>(L.l_ivar)[g * L_HORIZON + ep]));
+    }
+    BlockSync();
+    // err -= (sum(err*norm)/cells) * norm; the sum is an _Expr::sum(): descending (lstm-layer.cpp:319-321)
+    float newerr[(3 * L_CELLS + NT - 1) / NT];
+    {
+      int q = 0;
+      for (int t = tid; t < 3 * L_CELLS; t += NT, ++q) {
+        const int g = t / L_CELLS, i = t - g * L_CELLS;
+        const float* nrm = A.at<float>(L.l_norm) + ((size_t)g * L_HORIZON + ep) * L_CELLS;
+        float acc = f_mul(s.l_gerr[g][L_CELLS - 1], nrm[L_CELLS - 1]);
+        for (int k = L_CELLS - 2; k >= 0; --k) acc = f_add(acc, f_mul(s.l_gerr[g][k], nrm[k]));
+        acc = f_div(acc, (float)L_CELLS);
+        newerr[q] = f_sub(s.l_gerr[g][i], f_mul(acc, nrm[i]));
+      }
+    }
+    BlockSync();
+    {
+      int q = 0;
+      for (int t = tid; t < 3 * L_CELLS; t += NT, ++q) {
+        const int g = t / L_CELLS, i = t - g * L_CELLS;
+        s.l_gerr[g][i] = newerr[q];
+        errh[((size_t)g * L_HORIZON + ep) * L_CELLS + i] = newerr[q];
+      }
+    }
+    BlockSync();
+    if (tid < L_CELLS) {
+      const int i = tid;
+      float stored = s.l_stored_err[i];
+      if (ep > 0) {  // stored_error[i] += sum_j err[j] * W[j][512 + i], gates in order (lstm-layer.cpp:331-339)
+        for (int g = 0; g < 3; ++g) {
+          const float* wr = W + ((size_t)g * L_ROW + 512 + i) * L_CELLS;
+          float f = 0.0f;
+          for (int j = 0; j < L_CELLS; ++j) f = f_add(f, f_mul(s.l_gerr[g][j], wr[j]));
+          stored = f_add(stored, f);
+        }
+      }
+      // ClipGradients(+-10) on state_error, stored_error, hidden_error(=0) (lstm-layer.cpp:243-250,292-294)
+      float se = s.l_state_err[i];
+      se = se < -10.0f ? -10.0f : se > 10.0f ? 10.0f : se;
+      stored = stored < -10.0f ? -10.0f : stored > 10.0f ? 10.0f : stored;
+      s.l_state_err[i] = se;
+      s.l_stored_err[i] = stored;
+    }
+    BlockSync();
+  }
+  // Weight gradients + Adam (lstm-layer.cpp:340-353, :12-34), one weight per thread at a time.
+  const float* ad = P.adam + 4 * s.l_update_steps;
+  const float alpha = ad[0], d1 = ad[1], d2 = ad[2];
+  const float beta1 = (float)0.025, beta2 = (float)0.9999, eps = 1e-6f;
+  const float omb1 = f_sub(1.0f, beta1), omb2 = f_sub(1.0f, beta2);
+  float* Wm = A.at<float>(L.l_w);
+  float* M = A.at<float>(L.l_m);
+  float* V = A.at<float>(L.l_v);
+  const float* lin = A.at<float>(L.l_lin);
+  for (int f = tid; f < 3 * L_ROW * L_CELLS; f += NT) {
+    const int g = f / (L_ROW * L_CELLS);
+    const int r = (f / L_CELLS) % L_ROW;
+    const int i = f % L_CELLS;
+    const float* eh = errh + (size_t)g * L_HORIZON * L_CELLS + i;
+    float grad = 0.0f;
+    if (r < L_NOUT) {
+      for (int ep = L_HORIZON - 1; ep >= 0; --ep)
+        if (s.l_symin[ep] == r) grad = f_add(grad, eh[ep * L_CELLS]);
+    } else {
+      const float* x = lin + (r - L_NOUT);
+#pragma unroll 4
+      for (int ep = L_HORIZON - 1; ep >= 0; --ep) grad = f_add(grad, f_mul(eh[ep * L_CELLS], x[ep * (L_NIN + 1)]));
+    }
+    float m = f_mul(M[f], beta1);
+    m = f_add(m, f_mul(omb1, grad));
+    float v = f_mul(V[f], beta2);
+    v = f_add(v, f_mul(f_mul(omb2, grad), grad));
+    M[f] = m; V[f] = v;
+    Wm[f] = f_sub(Wm[f], f_mul(alpha, f_div(f_div(m, d1), f_sqrt(f_add(f_div(v, d2), eps)))));
+  }
+  for (int t = tid; t < 2 * 3 * L_CELLS; t += NT) {  // gamma then beta (lstm-layer.cpp:349-352)
+    const int which = t / (3 * L_CELLS), k = t - which * 3 * L_CELLS;  // k = g*CELLS + i
+    float* w = gb + (which == 0 ? 0 : 3) * L_CELLS + k;
+    float* pm = gb + ((which == 0 ? 2 : 4) * 3) * L_CELLS + k;
+    float* pv = gb + ((which == 0 ? 3 : 5) * 3) * L_CELLS + k;
+    const float grad = gb[((which == 0 ? 6 : 7) * 3) * L_CELLS + k];
+    float m = f_mul(*pm, beta1);
+    m = f_add(m, f_mul(omb1, grad));
+    float v = f_mul(*pv, beta2);
+    v = f_add(v, f_mul(f_mul(omb2, grad), grad));
+    *pm = m; *pv = v;
+    *w = f_sub(*w, f_mul(alpha, f_div(f_div(m, d1), f_sqrt(f_add(f_div(v, d2), eps)))));
+  }
+  BlockSync();
+}
+
+// Lstm::Perceive (lstm.cpp:52-89) on the 8th bit of a byte.
+template <int NT>
+GMX_DEV void LstmPerceive(StreamSmem& s, const Arena& A, const StreamParams& P, uint32_t byte, int tid) {
+  const ArenaLayout& L = *A.L;
+  const uint32_t cur = s.l_epoch;
+  const uint32_t last = cur == 0 ? L_HORIZON - 1 : cur - 1;
+  if (tid == 0) { s.l_old_input = s.l_hist[last]; s.l_hist[last] = (uint8_t)byte; }
+  BlockSync();
+  if (cur == 0) {
+    // input symbol of epoch ep = byte perceived before it (lstm.cpp:71-74)
+    for (int ep = tid; ep < L_HORIZON; ep += NT) s.l_symin[ep] = ep == 0 ? (uint8_t)s.l_old_input : s.l_hist[ep - 1];
+    BlockSync();
+    LstmBptt<NT>(s, A, P, tid);
+  }
+  // output layer: copy the previous epoch's layer, then one SGD step (lstm.cpp:81-88)
+  const float* wl = A.at<float>(L.l_wout) + (size_t)last * L_HID * L_NOUT;
+  float* wc = A.at<float>(L.l_wout) + (size_t)cur * L_HID * L_NOUT;
+  const float lr = (float)0.03;
+  for (int i = tid; i < L_NOUT; i += NT) {
+    const float err = (uint32_t)i == byte ? f_sub(s.lprob[i], 1.0f) : s.lprob[i];
+    const float le = f_mul(lr, err);
+#pragma unroll 3
+    for (int j = 0; j < L_HID; ++j) wc[j * L_NOUT + i] = f_sub(wl[j * L_NOUT + i], f_mul(le, s.l_hidden[j]));
+  }
+  BlockSync();
+}
+
+// Binary interval search node tables (ModPPMD::Predict mod_ppmd.cpp:1662-1681, LstmModel::Predict
+// lstm-model.cpp:36-47): node = recent_bits (1..255) covers [bot, top]; num = sum(mid+1..top) from
+// 0.0f ascending, denom continues from num over bot..mid. All 255 nodes are evaluated at the byte
+// boundary so the per-bit step is a lookup.
+GMX_DEV inline void IntervalNode(const float* probs, int node, float* val, uint8_t* flag) {
+  int level = 31 - __clz(node);
+  const int width = 256 >> level;
+  const int bot = (node - (1 << level)) * width;
+  const int top = bot + width - 1;
+  const int mid = bot + ((top - bot) / 2);
+  float num = 0.0f;
+  for (int i = mid + 1; i <= top; ++i) num = f_add(num, probs[i]);
+  float denom = num;
+  for (int i = bot; i <= mid; ++i) denom = f_add(denom, probs[i]);
+  if (denom != 0.0f) {
+    const float p = f_div(num, denom);
+    *val = Logit(p);
+    *flag = (uint8_t)(1 | (p == 0.5f ? 0 : 2));
+  } else {
+    *val = 0.0f;
+    *flag = 0;
+  }
+}
+
+// ---- everything that only happens when a new byte has been perceived (recent_bits == 1) ----------
+template <int NT>
+GMX_DEV void ByteBoundary(StreamSmem& s, const Arena& A, const StreamParams& P, int tid) {
+  const ArenaLayout& L = *A.L;
+  const uint32_t last_byte = s.ctx[C_LAST_BYTE];
+  // (1) contexts: intervals, hashed skip contexts, indirect-hash tables; PPMd on its own thread.
+  if (tid < 9) {  // IntervalContext::Predict interval-context.cpp:17-23
+    const IntervalSpec sp = kInterval[tid];
+    s.ctx[C_IV0 + tid] = sp.mask & ((s.ctx[C_IV0 + tid] << sp.shift) + (last_byte >> sp.div_log2));
+  } else if (tid >= 32 && tid < 52) {  // SkipContext::Predict skip-context.cpp:9-19
+    const SkipSpec sp = kSkip[tid - 32];
+    uint64_t c = 0;
+    for (int k = 0; k < sp.n; ++k) c = (c << 8) + RecentByte(s, sp.b[k]);
+    const int id = tid - 32;
+    s.ctx[id < 5 ? C_H2 + id : C_SK0 + (id - 5)] = Murmur64(c);
+  } else if (tid >= 64 && tid < 64 + NIH) {  // IndirectHash::Predict indirect-hash.cpp:16-31
+    const int k = tid - 64;
+    const IHSpec sp = kIH[k];
+    uint32_t* tab = A.at<uint32_t>(L.ih_tab[k]);
+    const uint32_t mask = (1u << sp.log2) - 1;
+    const uint64_t inner_mod = 1ull << (8 * (sp.inner_order - 1)), outer_mod = 1ull << (8 * (sp.outer_order - 1));
+    uint32_t* slot = tab + (s.ih_hash[k] & mask);
+    *slot = (uint32_t)((((uint64_t)*slot % inner_mod) << 8) + last_byte);
+    const uint64_t oc = ((s.ih_outer[k] % outer_mod) << 8) + last_byte;
+    s.ih_outer[k] = oc;
+    const uint32_t oh = Murmur64(oc);
+    s.ih_hash[k] = oh;
+    s.ctx[C_IH0 + k] = Murmur32(tab[oh & mask]);
+  } else if (tid == NT - 1) {  // ModPPMD::Predict byte part, mod_ppmd.cpp:1651-1654
+    Ppmd pm{A.at<PpmdState>(L.p_state), A.at<uint8_t>(L.p_text), A.at<uint8_t>(L.p_units), L.p_text_cap, L.p_units_cap, s.sqp};
+    pm.UpdateByte(last_byte);
+    if (!pm.S->error) pm.PrepareByte();
+    if (pm.S->error) s.error = GMX_ERR_PPMD_ARENA;
+  }
+  BlockSync();
+  // (2) ppm_predictions = max(sqp, 1) / sum, valarray::sum() ascending (mod_ppmd.cpp:1655-1661)
+  for (int i = tid; i < 256; i += NT) { float v = (float)s.sqp[i]; if (v < 1.0f) v = 1.0f; s.ppm[i] = v; }
+  // Indirect row bases ((ctx << 8) % M, so that slot = (base + bit_context) % M) and L2 prefetch of
+  // the 255-slot row every table will touch during this byte.
+  if (tid >= 80 && tid < 80 + NIND) {  // (the row keyed by lstm_prediction_context is redone below)
+    const int k = tid - 80;
+    const uint32_t M = L.ind_size[k];
+    const uint32_t base = (s.ctx[kInd[k].ctx] << 8) % M;
+    s.ind_base[k] = base;
+  }
+  BlockSync();
+  if (tid == 0) {
+    float acc = s.ppm[0];
+    for (int i = 1; i < 256; ++i) acc = f_add(acc, s.ppm[i]);
+    s.l_red[3] = acc;
+  } else {
+    // prefetch: 41 tables x 5 lines of 128 B cover the 510-byte row
+    for (int t = tid - 1; t < NIND * 5; t += NT - 1) {
+      const int k = t / 5, ln = t - k * 5;
+      const uint32_t M = L.ind_size[k];
+      uint32_t slot = s.ind_base[k] + ln * 64;
+      if (slot >= M) slot -= M;
+#if defined(__CUDA_ARCH__)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(A.at<uint16_t>(L.ind_tab[k]) + slot));
+#endif
+    }
+  }
+  BlockSync();
+  {
+    const float sum = s.l_red[3];
+    for (int i = tid; i < 256; i += NT) s.ppm[i] = f_div(s.ppm[i], sum);
+  }
+  BlockSync();
+  // (3) LSTM forward (LstmModel::Predict byte part, lstm-model.cpp:19-34)
+  LstmForward<NT>(s, A, tid);
+  // lstm_prediction_context = first index of the maximum, strict > from 0 (lstm-model.cpp:26-33)
+  {
+    float bv = 0.0f; int bi = 0;
+    for (int i = tid; i < 256; i += NT) if (s.lprob[i] > bv) { bv = s.lprob[i]; bi = i; }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((tid & 31) == 0) { s.l_red[4 + (tid >> 5)] = bv; s.l_err256[tid >> 5] = (float)bi; }
+  }
+  // (4) interval-search node tables for both byte models
+  for (int n = tid + 1; n < 256; n += NT) {
+    IntervalNode(s.ppm, n, &s.node_ppm[n], &s.nflag_ppm[n]);
+    const int n2 = 256 - n;
+    IntervalNode(s.lprob, n2, &s.node_lstm[n2], &s.nflag_lstm[n2]);
+  }
+  BlockSync();
+  if (tid == 0) {
+    float bv = 0.0f; int bi = 0;
+    for (int wi = 0; wi < NT / 32; ++wi) {
+      const float ov = s.l_red[4 + wi]; const int oi = (int)s.l_err256[wi];
+      if (ov > bv || (ov == bv && ov > 0.0f && oi < bi)) { bv = ov; bi = oi; }
+    }
+    s.ctx[C_LSTM] = bv > 0.0f ? bi : 0;
+    for (int k = 0; k < NIND; ++k)
+      if (kInd[k].ctx == C_LSTM) s.ind_base[k] = (s.ctx[C_LSTM] << 8) % L.ind_size[k];
+  }
+  BlockSync();
+}
+
+// ---- Predictor::Predict (predictor.cpp:360-376) --------------------------------------------------
+template <int NT>
+GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, int tid) {
+  const ArenaLayout& L = *A.L;
+  if (tid == 0) {  // BasicContexts::Predict basic-contexts.cpp:21-40
+    if (s.first_prediction) {
+      s.first_prediction = 0;
+    } else {
+      int rb = s.recent_bits * 2 + s.new_bit;
+      if (rb >= 256) {  // ByteUpdate basic-contexts.cpp:5-19
+        const uint32_t lb = rb - 256;
+        s.ctx[C_LAST_BYTE] = lb;
+        uint32_t rp = s.ring_pos + 1;
+        if (rp == 1000) rp = 0;
+        s.ring_pos = rp;
+        s.ring[rp] = (uint8_t)lb;
+        for (int i = 1; i < 10; ++i) s.ctx[C_RB1 + i - 1] = RecentByte(s, i);
+        rb = 1;
+      }
+      s.recent_bits = rb;
+      s.ctx[C_BIT_CONTEXT] = rb - 1;
+      s.ctx[C_LBPR] = (s.ctx[C_LAST_BYTE] << 8) + (rb - 1);
+      s.ctx[C_SLPR] = (s.ctx[C_RB1] << 8) + (rb - 1);
+    }
+    s.bb = s.recent_bits == 1;
+  }
+  BlockSync();
+  if (s.bb) ByteBoundary<NT>(s, A, P, tid);
+  const uint32_t bitctx = s.ctx[C_BIT_CONTEXT];
+  const bool zero_inactive = s.analysis != 0;  // predictor.cpp:362-365
+  if (tid < NIND) {  // Indirect::Predict indirect.cpp:28-45
+    const int k = tid;
+    const uint32_t M = L.ind_size[k];
+    uint32_t slot = s.ind_base[k] + bitctx;
+    if (slot >= M) slot -= M;
+    const uint32_t e = A.at<uint16_t>(L.ind_tab[k])[slot];
+    s.ind_slot[k] = slot;
+    s.ind_state[k] = (uint16_t)e;
+    const uint32_t ns = e & 0xff, rm = e >> 8;
+    const float* pr = A.at<float>(L.ind_pred) + k * 512;
+    const int pi = kInd[k].pred;
+    if (ns != 255) { const float p = pr[ns]; s.preds[pi] = p; s.act[pi] = p != 0.0f; }
+    else { s.act[pi] = 0; if (zero_inactive) s.preds[pi] = 0.0f; }
+    if (rm != 0) { const float p = pr[256 + rm]; s.preds[pi + 1] = p; s.act[pi + 1] = p != 0.0f; }
+    else { s.act[pi + 1] = 0; if (zero_inactive) s.preds[pi + 1] = 0.0f; }
+  } else if (tid >= 64 && tid < 64 + NMATCH) {  // Match::Predict match.cpp:25-74
+    const int k = tid - 64;
+    uint32_t len = s.m_len[k];
+    const uint32_t cb = s.m_byte[k];
+    uint32_t bp = s.m_bitpos[k];
+    const int hit = s.new_bit == ((cb & bp) != 0);
+    if (hit) { if (len < 255) ++len; } else len = 0;
+    bp >>= 1;
+    uint32_t cbyte = cb;
+    if (s.bb) {
+      uint32_t cm = s.m_cur[k];
+      if (s.hist_len != 0 && cm == s.hist_len - 1) len = 0;
+      if (len < 8) cm = A.at<uint32_t>(L.match_tab[k])[s.ctx[kMatch[k].ctx] & ((1u << kMatch[k].log2) - 1)];
+      else ++cm;
+      if (s.hist_len != 0) {
+        if (cm >= s.hist_len) { s.error = GMX_ERR_MATCH_RANGE; cm = 0; }
+        cbyte = A.at<uint8_t>(L.history)[cm];
+      }
+      s.m_cur[k] = cm;
+      bp = 128;
+    }
+    s.m_len[k] = (uint8_t)len; s.m_byte[k] = (uint8_t)cbyte; s.m_bitpos[k] = (uint8_t)bp;
+    const int pi = P_MATCH0 + k;
+    if (len > 2) {
+      const float mp = A.at<float>(L.match_pred)[k * 256 + len];
+      const float p = (cbyte & bp) ? mp : f_sub(1.0f, mp);
+      s.preds[pi] = Logit(p);
+      s.act[pi] = p != 0.5f;
+    } else {
+      s.act[pi] = 0;
+      if (zero_inactive) s.preds[pi] = 0.0f;
+    }
+  } else if (tid == 96 || tid == 97) {  // per-bit part of ModPPMD / LstmModel::Predict
+    const int which = tid - 96;
+    const int node = s.recent_bits;
+    const uint8_t fl = which ? s.nflag_lstm[node] : s.nflag_ppm[node];
+    if (fl & 1) { s.preds[which] = which ? s.node_lstm[node] : s.node_ppm[node]; s.act[which] = (fl >> 1) & 1; }
+    else { s.act[which] = 0; if (zero_inactive) s.preds[which] = 0.0f; }
+  }
+  BlockSync();
+  // Mixer gate selection (mixer.cpp:29-37): which weight set does each mixer need for this bit?
+  if (tid < NMIX) {
+    const int m = tid;
+    uint32_t c;
+    if (kMixer[m].ctx == C_LONGEST) {  // longest_match = max(match_length / 32) (match.cpp:71-73)
+      c = 0;
+      for (int k = 0; k < NMATCH; ++k) { const uint32_t v = s.m_len[k] >> 5; c = v > c ? v : c; }
+    } else {
+      c = s.ctx[kMixer[m].ctx];
+    }
+    const uint32_t idx = c & ((1u << kMixer[m].log2) - 1);
+    s.new_idx[m] = idx;
+    s.swap[m] = idx != s.set_idx[m];
+  }
+  if (tid == 40) {
+    uint32_t c = 0;
+    for (int k = 0; k < NMATCH; ++k) { const uint32_t v = s.m_len[k] >> 5; c = v > c ? v : c; }
+    s.ctx[C_LONGEST] = c;
+  }
+  BlockSync();
+  // Swap staged weight sets: write the old one back, fetch the new one (zero weights == no set yet:
+  // the dot product of zeros is +0, exactly the reference's "data == nullptr" output).
+  for (int m = tid >> 5; m < NMIX; m += NT / 32) {
+    if (!s.swap[m]) continue;
+    const int lane = tid & 31;
+    const int nw = MixerNW(m);
+    float* pool = A.at<float>(L.mix_pool);
+    const uint32_t stride = L.mix_set_stride;
+    const uint32_t old = s.set_pool[m];
+    const uint32_t nidx = s.new_idx[m];
+    const uint32_t nid = A.at<uint32_t>(L.mix_dir[m])[nidx];
+    const uint32_t old_steps = s.set_steps[m];
+    __syncwarp();  // every lane has read the staging state before lane 0 rewrites it
+    if (old) {
+      float* rec = pool + (size_t)old * stride;
+      for (int i = lane; i < nw; i += 32) rec[2 + i] = s.w[m * WSTRIDE + i];
+      if (lane == 0) ((uint32_t*)rec)[0] = old_steps;
+    }
+    if (nid) {
+      const float* rec = pool + (size_t)nid * stride;
+      for (int i = lane; i < nw; i += 32) s.w[m * WSTRIDE + i] = rec[2 + i];
+      if (lane == 0) s.set_steps[m] = ((const uint32_t*)rec)[0];
+    } else {
+      for (int i = lane; i < nw; i += 32) s.w[m * WSTRIDE + i] = 0.0f;
+      if (lane == 0) s.set_steps[m] = 0;
+    }
+    if (lane == 0) { s.set_pool[m] = nid; s.set_idx[m] = nidx; }
+  }
+  BlockSync();
+  // Mixer::Predict (mixer.cpp:51-106): warp 0, one lane per neuron, sequential sums, the serial
+  // same-layer chain is resolved by warp shuffles in neuron order.
+  if (tid < 32) {
+    const int lane = tid;
+    const float* w = s.w + (lane < NL0 ? lane : 0) * WSTRIDE;
+    float acc = 0.0f;
+    for (int i = 0; i < NPRED; ++i)
+      if (s.act[i]) acc = f_add(acc, f_mul(s.preds[i], w[i]));
+    for (int j = 0; j < NL0 - 1; ++j) {
+      const float oj = __shfl_sync(0xffffffffu, acc, j);
+      if (lane > j && lane < NL0) acc = f_add(acc, f_mul(oj, w[NPRED + j]));
+    }
+    if (lane < NL0) s.l0_out[lane] = acc;
+    __syncwarp();
+    const float skip = s.preds[P_LSTM];
+    const float* w1 = s.w + (NL0 + (lane < NL1 ? lane : 0)) * WSTRIDE;
+    acc = 0.0f;
+    for (int i = 0; i < NL0; ++i) acc = f_add(acc, f_mul(s.l0_out[i], w1[i]));
+    // a layer-1 output is complete (skip connection added last, weights[num_layer0 + output_index],
+    // mixer.cpp:77-83) before the next layer-1 neuron reads it
+    for (int j = 0; j < NL1; ++j) {
+      if (lane == j) acc = f_add(acc, f_mul(skip, w1[NL0 + j]));
+      if (j < NL1 - 1) {
+        const float oj = __shfl_sync(0xffffffffu, acc, j);
+        if (lane > j && lane < NL1) acc = f_add(acc, f_mul(oj, w1[NL0 + j]));
+      }
+    }
+    if (lane < NL1) s.l1_out[lane] = acc;
+    __syncwarp();
+    if (lane == 0) {
+      const float* w2 = s.w + (NL0 + NL1) * WSTRIDE;
+      float p = 0.0f;
+      for (int i = 0; i < NL0; ++i) p = f_add(p, f_mul(s.l0_out[i], w2[i]));
+      for (int i = 0; i < NL1; ++i) p = f_add(p, f_mul(s.l1_out[i], w2[NL0 + i]));
+      p = f_add(p, f_mul(skip, w2[NL0 + NL1]));
+      s.final_out = p;
+      float prob = Logistic(p);
+      const float eps = (float)0.0001;
+      const float hi = f_sub(1.0f, eps);
+      if (prob < eps) prob = eps; else if (prob > hi) prob = hi;
+      s.prob = prob;
+    }
+  }
+  BlockSync();
+}
+
+// ---- Predictor::Learn (predictor.cpp:383-387) ----------------------------------------------------
+template <int NT>
+GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int tid) {
+  const ArenaLayout& L = *A.L;
+  const int bit = s.new_bit;
+  const float fbit = (float)bit;
+  const int cur = s.recent_bits * 2 + bit;
+  const bool byte_done = cur >= 256;
+  const uint32_t longest = s.ctx[C_LONGEST];
+  // history length after BasicContexts::Learn (basic-contexts.cpp:42-54)
+  const uint32_t hist_after = s.hist_len + ((byte_done && longest < 2) ? 1u : 0u);
+  if (tid < NMIX) {  // Mixer::Learn scalars (mixer.cpp:108-127)
+    const int m = tid;
+    if (s.set_pool[m] == 0) {  // FindOrCreateMixerData mixer.cpp:39-49
+      const uint32_t id = atomicAdd(&s.pool_next, 1u);
+      if (id >= L.mix_pool_sets) { s.error = GMX_ERR_MIXER_POOL; }
+      else { s.set_pool[m] = id; A.at<uint32_t>(L.mix_dir[m])[s.set_idx[m]] = id; }
+    }
+    const uint32_t st = s.steps < P.decay_len ? s.steps : P.decay_len - 1;
+    float decay = P.decay[st];
+    const uint32_t dsteps = s.set_steps[m];
+    uint32_t mx = s.max_steps[m];
+    decay = (float)d_mul((double)decay, d_sub(1.5, d_div((double)dsteps, (double)mx)));
+    const float out = m < NL0 ? s.l0_out[m] : m < NL0 + NL1 ? s.l1_out[m - NL0] : s.final_out;
+    const float p = Logistic(out);
+    s.upd[m] = f_mul(f_mul(decay, kMixer[m].lr), f_sub(p, fbit));
+    const uint32_t nsteps = dsteps + 1;
+    s.set_steps[m] = nsteps;
+    if (nsteps > mx) s.max_steps[m] = nsteps;
+    s.shrink[m] = (nsteps & 1023u) == 0;
+  } else if (tid >= 64 && tid < 64 + NIND) {  // Indirect::Learn indirect.cpp:47-70
+    const int k = tid - 64;
+    const float lr = kInd[k].slow_lr ? f_div(1.0f, 200.0f) : (float)0.02;
+    float* pr = A.at<float>(L.ind_pred) + k * 512;
+    const uint32_t e = s.ind_state[k];
+    uint32_t ns = e & 0xff;
+    const uint32_t rm = e >> 8;
+    if (ns == 255) ns = 0;
+    const float a = pr[ns];
+    pr[ns] = f_add(a, f_mul(f_sub(fbit, Logistic(a)), lr));
+    const float b = pr[256 + rm];
+    pr[256 + rm] = f_add(b, f_mul(f_sub(fbit, Logistic(b)), lr));
+    // RunMap::Next run-map.cpp:3-21
+    uint32_t nrm;
+    if (bit == 0) nrm = rm < 127 ? rm + 1 : rm >= 128 ? 1 : rm;
+    else nrm = rm < 128 ? 128 : rm < 255 ? rm + 1 : rm;
+    A.at<uint16_t>(L.ind_tab[k])[s.ind_slot[k]] = (uint16_t)(kNonstationary[ns * 2 + bit] | (nrm << 8));
+  } else if (tid >= 40 && tid < 40 + NMATCH) {  // Match::Learn match.cpp:76-109
+    const int k = tid - 40;
+    const uint32_t len = s.m_len[k];
+    if (len > 2) {
+      const int hit = bit == ((s.m_byte[k] & s.m_bitpos[k]) != 0);
+      int* cnt = A.at<int>(L.match_cnt) + k * 256 + len;
+      float* mp = A.at<float>(L.match_pred) + k * 256 + len;
+      float rate = (float)(1.0 / 400);
+      const int c = *cnt;
+      if (c < 400) { *cnt = c + 1; rate = (float)d_div(1.0, (double)(c + 1)); }
+      const float v = *mp;
+      *mp = f_add(v, f_mul(f_sub((float)hit, v), rate));
+    }
+    if (s.recent_bits >= 128 && longest < 2)
+      A.at<uint32_t>(L.match_tab[k])[s.ctx[kMatch[k].ctx] & ((1u << kMatch[k].log2) - 1)] = hist_after - 1;
+  } else if (tid == 48 && byte_done && longest < 2) {
+    if (s.hist_len >= L.history_cap) s.error = GMX_ERR_HISTORY_CAP;
+    else A.at<uint8_t>(L.history)[s.hist_len] = (uint8_t)cur;
+  }
+  BlockSync();
+  // Mixer weight updates (mixer.cpp:128-175): w -= update * x over exactly the inputs used by
+  // Predict, then the (1 - 3e-6) shrink every 1024 steps of the set.
+  for (int f = tid; f < NMIX * WSTRIDE; f += NT) {
+    const int m = f / WSTRIDE, i = f - m * WSTRIDE;
+    float x; bool use;
+    if (m < NL0) {
+      if (i < NPRED) { use = s.act[i] != 0; x = s.preds[i]; }
+      else { use = i < NPRED + m; x = s.l0_out[i < NPRED + NL0 ? i - NPRED : 0]; }
+    } else if (m < NL0 + NL1) {
+      const int o = m - NL0;
+      if (i < NL0) { use = true; x = s.l0_out[i]; }
+      else if (i < NL0 + o) { use = true; x = s.l1_out[i - NL0]; }
+      else { use = i == NL0 + o; x = s.preds[P_LSTM]; }
+    } else {
+      if (i < NL0) { use = true; x = s.l0_out[i]; }
+      else if (i < NL0 + NL1) { use = true; x = s.l1_out[i - NL0]; }
+      else { use = i == NL0 + NL1; x = s.preds[P_LSTM]; }
+    }
+    if (i >= MixerNW(m)) continue;
+    float w = s.w[f];
+    if (use) w = f_sub(w, f_mul(s.upd[m], x));
+    if (s.shrink[m]) w = f_mul(w, f_sub(1.0f, 3.0e-6f));
+    s.w[f] = w;
+  }
+  if (tid == 0) { s.steps++; s.hist_len = hist_after; }
+  BlockSync();
+  if (byte_done) LstmPerceive<NT>(s, A, P, (uint32_t)(cur - 256), tid);  // LstmModel::Learn lstm-model.cpp:50-59
+}
+
+// ---- coder (encoder.cpp:8-34, decoder.cpp:3-39) ---------------------------------------------------
+GMX_DEV inline uint32_t Discretize(float p) { return (uint32_t)f_add(1.0f, f_mul(65534.0f, p)); }
+
+GMX_DEV inline void PutByte(StreamSmem& s, uint8_t* out, uint32_t b) {
+  if (s.out_pos < s.out_cap) out[s.out_pos] = (uint8_t)b; else s.error = GMX_ERR_OUTPUT_CAP;
+  s.out_pos++;
+}
+GMX_DEV inline uint32_t GetByte(StreamSmem& s, const uint8_t* in) {  // Decoder::ReadByte: 0 past the end
+  const uint32_t b = s.in_pos < s.in_len ? in[s.in_pos] : 0u;
+  s.in_pos++;
+  return b;
+}
+
+GMX_DEV inline void Trace(StreamSmem& s, const StreamParams& P, uint64_t bit_index) {
+  if (P.bit_trace) {
+    const uint32_t p16 = Discretize(s.prob);
+    P.bit_trace[bit_index] = (uint64_t)f2u(s.prob) | ((uint64_t)p16 << 32);
+  }
+  if (P.pred_trace) {
+    float* t = P.pred_trace + bit_index * 126;
+    for (int i = 0; i < NPRED; ++i) t[i] = s.preds[i];
+    uint32_t mask[3] = {0, 0, 0};
+    for (int i = 0; i < NPRED; ++i) if (s.act[i]) mask[i >> 5] |= 1u << (i & 31);
+    for (int i = 0; i < 3; ++i) t[NPRED + i] = u2f(mask[i]);
+    for (int i = 0; i < NL0; ++i) t[93 + i] = s.l0_out[i];
+    for (int i = 0; i < NL1; ++i) t[117 + i] = s.l1_out[i];
+    t[125] = s.final_out;
+  }
+}
+
+// runner_utils::Compress (runner-utils.cpp:43-67) incl. the 5-byte header of RunCompression (:109).
+template <int NT>
+GMX_DEV void CompressStream(StreamSmem& s, const Arena& A, const StreamParams& P, uint32_t sid, int tid) {
+  const uint8_t* in = P.in + P.in_off[sid];
+  const uint64_t n = P.in_off[sid + 1] - P.in_off[sid];
+  uint8_t* out = P.out + P.out_off[sid];
+  InitStream<NT>(s, A, P, tid);
+  if (tid == 0) {
+    s.out_pos = 0; s.out_cap = P.out_off[sid + 1] - P.out_off[sid];
+    s.analysis = (8 * n / 1000) > 0;  // EnableAnalysis(8*n/1000) -> predictions zeroed every bit
+    for (int i = 4; i >= 0; --i) PutByte(s, out, (uint32_t)(n >> (8 * i)) & 0xff);
+  }
+  BlockSync();
+  const bool tracing = sid == 0;
+  for (uint64_t pos = 0; pos < n; ++pos) {
+    const uint32_t c = in[pos];
+    for (int j = 7; j >= 0; --j) {
+      const int bit = (c >> j) & 1;
+      PredictBit<NT>(s, A, P, tid);
+      if (tid == 0) {
+        if (tracing) Trace(s, P, pos * 8 + (7 - j));
+        const uint32_t p16 = Discretize(s.prob);
+        const uint32_t r = s.x2 - s.x1;
+        const uint32_t xmid = s.x1 + (r >> 16) * p16 + (((r & 0xffff) * p16) >> 16);
+        if (bit) s.x2 = xmid; else s.x1 = xmid + 1;
+        while (((s.x1 ^ s.x2) & 0xff000000u) == 0) { PutByte(s, out, s.x2 >> 24); s.x1 <<= 8; s.x2 = (s.x2 << 8) + 255; }
+        s.new_bit = bit;
+      }
+      BlockSync();
+      LearnBit<NT>(s, A, P, tid);
+      if (s.error) break;
+    }
+    if (s.error) break;
+  }
+  BlockSync();
+  if (tid == 0) {
+    while (((s.x1 ^ s.x2) & 0xff000000u) == 0) { PutByte(s, out, s.x2 >> 24); s.x1 <<= 8; s.x2 = (s.x2 << 8) + 255; }
+    PutByte(s, out, s.x2 >> 24);
+    P.out_len[sid] = s.out_pos;
+    P.status[sid] = s.error;
+  }
+  BlockSync();
+}
+
+// runner_utils::Decompress (runner-utils.cpp:69-86) + ReadHeader (:29-36). Analysis is never on.
+template <int NT>
+GMX_DEV void DecompressStream(StreamSmem& s, const Arena& A, const StreamParams& P, uint32_t sid, int tid) {
+  const uint8_t* in = P.in + P.in_off[sid];
+  uint8_t* out = P.out + P.out_off[sid];
+  InitStream<NT>(s, A, P, tid);
+  if (tid == 0) {
+    s.in_pos = 0; s.in_len = P.in_off[sid + 1] - P.in_off[sid];
+    s.out_pos = 0; s.out_cap = P.out_off[sid + 1] - P.out_off[sid];
+    s.analysis = 0;
+    uint64_t len = 0;
+    for (int i = 0; i <= 4; ++i) len = (len << 8) + GetByte(s, in);
+    if (s.in_len < 5 || len > s.out_cap) { s.error = s.in_len < 5 ? GMX_ERR_BAD_HEADER : GMX_ERR_OUTPUT_CAP; len = 0; }
+    s.out_cap = len;  // number of bytes to produce
+    for (int i = 0; i < 4; ++i) s.x = (s.x << 8) + (GetByte(s, in) & 0xff);
+  }
+  BlockSync();
+  const uint64_t n = s.out_cap;
+  for (uint64_t pos = 0; pos < n; ++pos) {
+    for (int j = 7; j >= 0; --j) {
+      PredictBit<NT>(s, A, P, tid);
+      if (tid == 0) {  // Decoder::Decode decoder.cpp:19-39
+        const uint32_t p16 = Discretize(s.prob);
+        const uint32_t r = s.x2 - s.x1;
+        const uint32_t xmid = s.x1 + (r >> 16) * p16 + (((r & 0xffff) * p16) >> 16);
+        int bit = 0;
+        if (s.x <= xmid) { bit = 1; s.x2 = xmid; } else s.x1 = xmid + 1;
+        s.new_bit = bit;
+        while (((s.x1 ^ s.x2) & 0xff000000u) == 0) { s.x1 <<= 8; s.x2 = (s.x2 << 8) + 255; s.x = (s.x << 8) + GetByte(s, in); }
+        if (j == 0) out[pos] = (uint8_t)((s.recent_bits * 2 + bit) & 0xff);
+      }
+      BlockSync();
+      LearnBit<NT>(s, A, P, tid);
+      if (s.error) break;
+    }
+    if (s.error) break;
+  }
+  BlockSync();
+  if (tid == 0) { P.out_len[sid] = s.error ? 0 : n; P.status[sid] = s.error; }
+  BlockSync();
+}
+
+// ---- kernel entry: persistent CTAs, one stream at a time, ids from an atomic queue ---------------
+enum : int { MODE_COMPRESS = 0, MODE_DECOMPRESS = 1 };
+
+template <int NT, int MODE>
+__global__ void __launch_bounds__(NT) StreamKernel(StreamParams P) {
+  __shared__ StreamSmem s;
+  __shared__ uint32_t next_stream;
+  const int tid = (int)threadIdx.x;
+  Arena A{P.arenas + (uint64_t)blockIdx.x * P.arena_stride, P.layout};
+  for (;;) {
+    if (tid == 0) next_stream = atomicAdd(P.queue, 1u);
+    BlockSync();
+    const uint32_t sid = next_stream;
+    BlockSync();
+    if (sid >= P.n_streams) break;
+    if (MODE == MODE_COMPRESS) CompressStream<NT>(s, A, P, sid, tid);
+    else DecompressStream<NT>(s, A, P, sid, tid);
+  }
+}
+
+}  // namespace gmx
+#endif  // GMIX_B200_STREAM_KERNEL_CUH_

@@ -559,3 +559,13 @@ int gmo_decompress(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, ui
 }
 
 }  // extern "C"
+
+// Debug accessor (tests only): copies the weight vector of mixer `m` for gate-context index `idx`;
+// returns the number of weights, or -1 if that set does not exist yet. *steps gets MixerData::steps.
+extern "C" int gmo_debug_mixer_set(gmo_predictor* p, int m, uint32_t idx, float* out, uint64_t* steps) {
+  MixerSet* d = p->mixers[m].table[idx % p->mixers[m].table_size];
+  if (!d) return -1;
+  memcpy(out, d->w.data(), d->w.size() * sizeof(float));
+  if (steps) *steps = d->steps;
+  return (int)d->w.size();
+}
