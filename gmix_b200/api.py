@@ -1,0 +1,186 @@
+"""ctypes binding of include/gmix_b200.h plus a small host-side mirror of the reference's runner
+interface (reference src/runner/runner-utils.h:24-40: RunCompression / RunDecompression), batched
+over independent streams."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_LIB = None
+
+
+class GmixError(RuntimeError):
+    pass
+
+
+def library_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libgmix_b200.so")
+
+
+def load_library():
+    """Load libgmix_b200.so or fail loudly — there is no CPU path behind this package."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise GmixError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(gmix_b200 has no CPU fallback)")
+    lib = C.CDLL(path)
+    u8p, u64p, u32p, f32p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_float)
+    lib.gmx_version.restype = C.c_char_p
+    lib.gmx_global_error.restype = C.c_char_p
+    lib.gmx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.gmx_destroy.argtypes = [C.c_void_p]
+    lib.gmx_last_error.argtypes = [C.c_void_p]
+    lib.gmx_last_error.restype = C.c_char_p
+    lib.gmx_set_cuda_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.gmx_configure.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32]
+    lib.gmx_compress_bound.argtypes = [C.c_uint64]
+    lib.gmx_compress_bound.restype = C.c_uint64
+    batch = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gmx_compress_batch.argtypes = batch
+    lib.gmx_decompress_batch.argtypes = batch
+    lib.gmx_compress_batch_device.argtypes = batch + [C.c_uint64]
+    lib.gmx_decompress_batch_device.argtypes = batch + [C.c_uint64]
+    lib.gmx_compress_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, u64p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gmx_resident_streams.argtypes = [C.c_void_p]
+    lib.gmx_resident_streams.restype = C.c_uint32
+    lib.gmx_arena_bytes.argtypes = [C.c_void_p]
+    lib.gmx_arena_bytes.restype = C.c_uint64
+    lib.gmx_kernel_launches.argtypes = [C.c_void_p]
+    lib.gmx_kernel_launches.restype = C.c_uint64
+    lib.gmx_last_kernel_ms.argtypes = [C.c_void_p]
+    lib.gmx_last_kernel_ms.restype = C.c_double
+    lib.gmx_device_sm_count.argtypes = [C.c_void_p]
+    lib.gmx_selftest_math.argtypes = [C.c_void_p, C.c_uint32, u64p, u32p]
+    _LIB = lib
+    return lib
+
+
+def compress_bound(n):
+    return int(load_library().gmx_compress_bound(n))
+
+
+def _pack(streams):
+    """list of bytes-like -> (uint8 array, uint64 offsets)."""
+    lens = [len(s) for s in streams]
+    off = np.zeros(len(streams) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    buf = np.frombuffer(b"".join(bytes(s) for s in streams), dtype=np.uint8).copy() if sum(lens) else np.zeros(1, np.uint8)
+    return buf, off
+
+
+class Context:
+    """One GPU. Mirrors the reference runner at batch granularity: compress_batch(streams) returns, for
+    every stream, exactly the bytes `gmix -c` writes for it (5-byte big-endian length + coder bytes)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.gmx_create(device, C.byref(h))
+        if rc != 0:
+            raise GmixError(f"gmx_create({device}) failed ({rc}): {self.lib.gmx_global_error().decode()}")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gmx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise GmixError(f"{what} failed ({rc}): {self.lib.gmx_last_error(self.h).decode()}")
+
+    def set_cuda_stream(self, stream_ptr):
+        self._check(self.lib.gmx_set_cuda_stream(self.h, C.c_void_p(stream_ptr)), "gmx_set_cuda_stream")
+
+    def configure(self, max_stream_len, max_resident=0):
+        self._check(self.lib.gmx_configure(self.h, max_stream_len, max_resident), "gmx_configure")
+
+    # ---- host-buffer API (the call a user makes) ----
+    def _run_host(self, fn, what, streams, caps):
+        n = len(streams)
+        if n == 0:
+            return []
+        buf, off = _pack(streams)
+        ooff = np.zeros(n + 1, dtype=np.uint64)
+        np.cumsum(np.asarray(caps, dtype=np.uint64), out=ooff[1:])
+        out = np.zeros(int(ooff[-1]) + 1, dtype=np.uint8)
+        out_len = np.zeros(n, dtype=np.uint64)
+        status = np.zeros(n, dtype=np.uint32)
+        rc = fn(self.h, buf.ctypes.data, off.ctypes.data, n, out.ctypes.data, ooff.ctypes.data, out_len.ctypes.data, status.ctypes.data)
+        self.last_status = status
+        self._check(rc, what)
+        return [out[int(ooff[i]):int(ooff[i]) + int(out_len[i])].tobytes() for i in range(n)]
+
+    def compress_batch(self, streams):
+        return self._run_host(self.lib.gmx_compress_batch, "gmx_compress_batch", streams, [compress_bound(len(s)) for s in streams])
+
+    def decompress_batch(self, streams):
+        caps = [int.from_bytes(bytes(s[:5]), "big") + 8 if len(s) >= 5 else 8 for s in streams]
+        return self._run_host(self.lib.gmx_decompress_batch, "gmx_decompress_batch", streams, caps)
+
+    def compress(self, data):
+        return self.compress_batch([data])[0]
+
+    def decompress(self, data):
+        return self.decompress_batch([data])[0]
+
+    def compress_trace(self, data, blackboard=False):
+        """Single stream; returns (compressed bytes, probs[8n] float32, p16[8n] uint32, blackboard or None)."""
+        n = len(data)
+        src = np.frombuffer(bytes(data), dtype=np.uint8).copy() if n else np.zeros(1, np.uint8)
+        cap = compress_bound(n)
+        out = np.zeros(cap, dtype=np.uint8)
+        out_len = C.c_uint64(0)
+        probs = np.zeros(max(8 * n, 1), dtype=np.float32)
+        p16 = np.zeros(max(8 * n, 1), dtype=np.uint32)
+        bb = np.zeros((max(8 * n, 1), 126), dtype=np.float32) if blackboard else None
+        rc = self.lib.gmx_compress_trace(self.h, src.ctypes.data, n, out.ctypes.data, cap, C.byref(out_len), probs.ctypes.data,
+                                         p16.ctypes.data, bb.ctypes.data if blackboard else None)
+        self._check(rc, "gmx_compress_trace")
+        return out[:out_len.value].tobytes(), probs[:8 * n], p16[:8 * n], bb
+
+    # ---- device-pointer API (inputs already resident in HBM) ----
+    def compress_batch_device(self, d_in, d_in_off, n, d_out, d_out_off, d_out_len, d_status, max_stream_len):
+        self._check(self.lib.gmx_compress_batch_device(self.h, d_in, d_in_off, n, d_out, d_out_off, d_out_len, d_status, max_stream_len),
+                    "gmx_compress_batch_device")
+
+    def decompress_batch_device(self, d_in, d_in_off, n, d_out, d_out_off, d_out_len, d_status, max_stream_len):
+        self._check(self.lib.gmx_decompress_batch_device(self.h, d_in, d_in_off, n, d_out, d_out_off, d_out_len, d_status, max_stream_len),
+                    "gmx_decompress_batch_device")
+
+    # ---- introspection ----
+    @property
+    def resident_streams(self):
+        return int(self.lib.gmx_resident_streams(self.h))
+
+    @property
+    def arena_bytes(self):
+        return int(self.lib.gmx_arena_bytes(self.h))
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.gmx_kernel_launches(self.h))
+
+    @property
+    def last_kernel_ms(self):
+        return float(self.lib.gmx_last_kernel_ms(self.h))
+
+    @property
+    def sm_count(self):
+        return int(self.lib.gmx_device_sm_count(self.h))
+
+    def selftest_math(self, stride=1):
+        mism = (C.c_uint64 * 3)()
+        first = (C.c_uint32 * 3)()
+        self._check(self.lib.gmx_selftest_math(self.h, stride, mism, first), "gmx_selftest_math")
+        return {name: (int(mism[i]), int(first[i])) for i, name in enumerate(("expf", "logf", "tanhf"))}

@@ -1,0 +1,388 @@
+// libgmix_b200.so — host side of the C ABI declared in include/gmix_b200.h.
+// Owns device memory (stream arenas, libm tables), launches the sm_100a stream kernels
+// (stream_kernel.cuh) and the device-math self test. No CPU fallback exists.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/gmix_b200.h"
+#include "layout.h"
+#include "stream_kernel.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+std::string g_global_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace
+
+struct gmx_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string error;
+  // arenas
+  uint64_t cfg_max_len = 0;
+  uint32_t n_arenas = 0;
+  gmx::ArenaLayout layout;
+  uint8_t* d_arenas = nullptr;
+  gmx::ArenaLayout* d_layout = nullptr;
+  float* d_lstm_init = nullptr;
+  float* d_adam = nullptr;
+  float* d_decay = nullptr;
+  uint32_t decay_len = 0;
+  uint32_t* d_queue = nullptr;
+  std::vector<float> h_decay;
+  // staging buffers of the host-pointer entry points
+  DevBuf b_in, b_out, b_in_off, b_out_off, b_out_len, b_status, b_trace, b_ptrace;
+  uint32_t last_grid = 0;
+  uint64_t launches = 0;
+  double last_ms = 0;
+};
+
+namespace {
+
+int Fail(gmx_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->error = buf; else g_global_error = buf;
+  return code;
+}
+
+#define GMX_CUDA(c, expr)                                                                          \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess) return Fail((c), GMX_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+int Reserve(gmx_ctx* c, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap && b.p) return 0;
+  if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+  size_t want = bytes < 256 ? 256 : bytes;
+  GMX_CUDA(c, cudaMalloc(&b.p, want));
+  b.cap = want;
+  return 0;
+}
+
+void FreeArenas(gmx_ctx* c) {
+  if (c->d_arenas) cudaFree(c->d_arenas);
+  c->d_arenas = nullptr;
+  c->n_arenas = 0;
+  c->cfg_max_len = 0;
+}
+
+template <int MODE>
+int Launch(gmx_ctx* c, const gmx::StreamParams& P, uint32_t grid) {
+  GMX_CUDA(c, cudaMemsetAsync(c->d_queue, 0, sizeof(uint32_t), c->stream));
+  GMX_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+  gmx::StreamKernel<kThreads, MODE><<<grid, kThreads, 0, c->stream>>>(P);
+  GMX_CUDA(c, cudaGetLastError());
+  GMX_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+  GMX_CUDA(c, cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  GMX_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->last_ms = ms;
+  c->last_grid = grid;
+  c->launches += 1;
+  return 0;
+}
+
+int RunDevice(gmx_ctx* c, int mode, const uint8_t* d_in, const uint64_t* d_in_off, uint32_t n, uint8_t* d_out,
+              const uint64_t* d_out_off, uint64_t* d_out_len, uint32_t* d_status, uint64_t max_len,
+              uint64_t* d_bit_trace, float* d_pred_trace) {
+  if (!c) return GMX_E_ARG;
+  if (n == 0) return 0;
+  if (!d_in || !d_in_off || !d_out || !d_out_off || !d_out_len || !d_status) return Fail(c, GMX_E_ARG, "null pointer argument");
+  GMX_CUDA(c, cudaSetDevice(c->device));
+  if (max_len > c->cfg_max_len || c->n_arenas == 0) {
+    int rc = gmx_configure(c, max_len, 0);
+    if (rc) return rc;
+  }
+  gmx::StreamParams P;
+  memset(&P, 0, sizeof(P));
+  P.in = d_in; P.in_off = d_in_off; P.out = d_out; P.out_off = d_out_off; P.out_len = d_out_len; P.status = d_status;
+  P.n_streams = n; P.queue = c->d_queue;
+  P.arenas = c->d_arenas; P.arena_stride = c->layout.total; P.layout = c->d_layout;
+  P.lstm_init = c->d_lstm_init; P.decay = c->d_decay; P.decay_len = c->decay_len; P.adam = c->d_adam;
+  P.bit_trace = d_bit_trace; P.pred_trace = d_pred_trace;
+  const uint32_t grid = n < c->n_arenas ? n : c->n_arenas;
+  return mode == gmx::MODE_COMPRESS ? Launch<gmx::MODE_COMPRESS>(c, P, grid) : Launch<gmx::MODE_DECOMPRESS>(c, P, grid);
+}
+
+int RunHost(gmx_ctx* c, int mode, const uint8_t* in, const uint64_t* in_off, uint32_t n, uint8_t* out,
+            const uint64_t* out_off, uint64_t* out_len, uint32_t* status, uint64_t* h_bit_trace, float* h_pred_trace) {
+  if (!c) return GMX_E_ARG;
+  if (n == 0) return 0;
+  if (!in || !in_off || !out || !out_off || !out_len || !status) return Fail(c, GMX_E_ARG, "null pointer argument");
+  GMX_CUDA(c, cudaSetDevice(c->device));
+  const uint64_t in_total = in_off[n] - in_off[0], out_total = out_off[n] - out_off[0];
+  uint64_t max_len = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (in_off[i + 1] < in_off[i] || out_off[i + 1] < out_off[i]) return Fail(c, GMX_E_ARG, "offsets must be non-decreasing");
+    uint64_t len;
+    if (mode == gmx::MODE_COMPRESS) len = in_off[i + 1] - in_off[i];
+    else {  // uncompressed length from the 5-byte big-endian header (runner-utils.cpp:29-36)
+      len = 0;
+      const uint64_t avail = in_off[i + 1] - in_off[i];
+      for (uint64_t k = 0; k < 5 && k < avail; ++k) len = (len << 8) + in[in_off[i] + k];
+      const uint64_t cap = out_off[i + 1] - out_off[i];
+      if (len > cap) len = cap;  // the kernel reports GMX_S_OUTPUT_CAP for this stream
+    }
+    if (len > max_len) max_len = len;
+  }
+  // rebase offsets to 0 for the device copies
+  std::vector<uint64_t> io(n + 1), oo(n + 1);
+  for (uint32_t i = 0; i <= n; ++i) { io[i] = in_off[i] - in_off[0]; oo[i] = out_off[i] - out_off[0]; }
+  int rc;
+  if ((rc = Reserve(c, c->b_in, in_total + 16))) return rc;
+  if ((rc = Reserve(c, c->b_out, out_total + 16))) return rc;
+  if ((rc = Reserve(c, c->b_in_off, (n + 1) * 8))) return rc;
+  if ((rc = Reserve(c, c->b_out_off, (n + 1) * 8))) return rc;
+  if ((rc = Reserve(c, c->b_out_len, (size_t)n * 8))) return rc;
+  if ((rc = Reserve(c, c->b_status, (size_t)n * 4))) return rc;
+  uint64_t* d_bt = nullptr;
+  float* d_pt = nullptr;
+  const uint64_t nbits0 = (in_off[1] - in_off[0]) * 8;
+  if (h_bit_trace) { if ((rc = Reserve(c, c->b_trace, nbits0 * 8 + 8))) return rc; d_bt = (uint64_t*)c->b_trace.p; }
+  if (h_pred_trace) { if ((rc = Reserve(c, c->b_ptrace, nbits0 * 126 * 4 + 8))) return rc; d_pt = (float*)c->b_ptrace.p; }
+  GMX_CUDA(c, cudaMemcpyAsync(c->b_in.p, in + in_off[0], in_total, cudaMemcpyHostToDevice, c->stream));
+  GMX_CUDA(c, cudaMemcpyAsync(c->b_in_off.p, io.data(), (n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  GMX_CUDA(c, cudaMemcpyAsync(c->b_out_off.p, oo.data(), (n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  GMX_CUDA(c, cudaMemsetAsync(c->b_out_len.p, 0, (size_t)n * 8, c->stream));
+  GMX_CUDA(c, cudaMemsetAsync(c->b_status.p, 0xff, (size_t)n * 4, c->stream));
+  rc = RunDevice(c, mode, (const uint8_t*)c->b_in.p, (const uint64_t*)c->b_in_off.p, n, (uint8_t*)c->b_out.p,
+                 (const uint64_t*)c->b_out_off.p, (uint64_t*)c->b_out_len.p, (uint32_t*)c->b_status.p, max_len, d_bt, d_pt);
+  if (rc) return rc;
+  GMX_CUDA(c, cudaMemcpyAsync(out + out_off[0], c->b_out.p, out_total, cudaMemcpyDeviceToHost, c->stream));
+  GMX_CUDA(c, cudaMemcpyAsync(out_len, c->b_out_len.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+  GMX_CUDA(c, cudaMemcpyAsync(status, c->b_status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (h_bit_trace) GMX_CUDA(c, cudaMemcpyAsync(h_bit_trace, d_bt, nbits0 * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (h_pred_trace) GMX_CUDA(c, cudaMemcpyAsync(h_pred_trace, d_pt, nbits0 * 126 * 4, cudaMemcpyDeviceToHost, c->stream));
+  GMX_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (uint32_t i = 0; i < n; ++i)
+    if (status[i] != 0) return Fail(c, GMX_E_STREAM, "stream %u failed with status %u", i, status[i]);
+  return 0;
+}
+
+// ---- device math self test ----------------------------------------------------------------------
+__global__ void MathSweepKernel(uint32_t first, uint32_t stride, uint32_t count, float* e, float* l, float* t) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const float x = gmx::u2f(first + i * stride);
+  e[i] = gmx::gm_expf(x);
+  t[i] = gmx::gm_tanhf(x);
+  const uint32_t u = first + i * stride;
+  l[i] = (u >= 0x00800000u && u < 0x7f800000u) ? gmx::gm_logf(x) : 0.0f;
+}
+
+bool SameFloat(float a, float b) {
+  if (a != a && b != b) return true;
+  uint32_t x, y;
+  memcpy(&x, &a, 4); memcpy(&y, &b, 4);
+  return x == y;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gmx_version(void) { return "gmix_b200 0.1 (sm_100a)"; }
+const char* gmx_global_error(void) { return g_global_error.c_str(); }
+
+int gmx_create(int device, gmx_ctx** out) {
+  if (!out) return GMX_E_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return Fail(nullptr, GMX_E_NODEVICE, "no CUDA device available (%s); gmix_b200 has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= count) return Fail(nullptr, GMX_E_ARG, "device %d out of range (%d devices)", device, count);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return Fail(nullptr, GMX_E_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10) return Fail(nullptr, GMX_E_NODEVICE, "device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+  gmx_ctx* c = new gmx_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
+      cudaMalloc(&c->d_queue, 256) != cudaSuccess || cudaMalloc(&c->d_layout, sizeof(gmx::ArenaLayout)) != cudaSuccess) {
+    Fail(nullptr, GMX_E_CUDA, "CUDA initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete c;
+    return GMX_E_CUDA;
+  }
+  c->stream = c->own_stream;
+  std::vector<float> linit, adam;
+  gmx::FillLstmInit(linit);
+  gmx::FillAdamTable(adam);
+  if (cudaMalloc(&c->d_lstm_init, linit.size() * 4) != cudaSuccess || cudaMalloc(&c->d_adam, adam.size() * 4) != cudaSuccess ||
+      cudaMemcpy(c->d_lstm_init, linit.data(), linit.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(c->d_adam, adam.data(), adam.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+    Fail(nullptr, GMX_E_CUDA, "table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    gmx_destroy(c);
+    return GMX_E_CUDA;
+  }
+  *out = c;
+  return 0;
+}
+
+void gmx_destroy(gmx_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  FreeArenas(c);
+  for (DevBuf* b : {&c->b_in, &c->b_out, &c->b_in_off, &c->b_out_off, &c->b_out_len, &c->b_status, &c->b_trace, &c->b_ptrace})
+    if (b->p) cudaFree(b->p);
+  if (c->d_layout) cudaFree(c->d_layout);
+  if (c->d_lstm_init) cudaFree(c->d_lstm_init);
+  if (c->d_adam) cudaFree(c->d_adam);
+  if (c->d_decay) cudaFree(c->d_decay);
+  if (c->d_queue) cudaFree(c->d_queue);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+const char* gmx_last_error(const gmx_ctx* c) { return c ? c->error.c_str() : g_global_error.c_str(); }
+
+int gmx_set_cuda_stream(gmx_ctx* c, void* s) {
+  if (!c) return GMX_E_ARG;
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return 0;
+}
+
+int gmx_configure(gmx_ctx* c, uint64_t max_stream_len, uint32_t max_resident) {
+  if (!c) return GMX_E_ARG;
+  GMX_CUDA(c, cudaSetDevice(c->device));
+  if (max_stream_len >= (1ull << 31)) return Fail(c, GMX_E_ARG, "streams of 2 GiB or more are not supported");
+  FreeArenas(c);
+  c->layout = gmx::MakeLayout(max_stream_len);
+  // decay table: one entry per bit step (mixer.cpp:111)
+  const uint64_t need = max_stream_len * 8 + 16;
+  if (need > c->decay_len) {
+    gmx::FillDecayTable(c->h_decay, need);
+    if (c->d_decay) cudaFree(c->d_decay);
+    c->d_decay = nullptr;
+    GMX_CUDA(c, cudaMalloc(&c->d_decay, c->h_decay.size() * 4));
+    GMX_CUDA(c, cudaMemcpy(c->d_decay, c->h_decay.data(), c->h_decay.size() * 4, cudaMemcpyHostToDevice));
+    c->decay_len = (uint32_t)c->h_decay.size();
+  }
+  int per_sm = 0;
+  GMX_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gmx::StreamKernel<kThreads, gmx::MODE_COMPRESS>, kThreads, 0));
+  if (per_sm < 1) per_sm = 1;
+  uint64_t want = (uint64_t)per_sm * c->sm_count;
+  if (max_resident && max_resident < want) want = max_resident;
+  size_t free_b = 0, total_b = 0;
+  GMX_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+  const uint64_t usable = free_b > (2ull << 30) ? free_b - (2ull << 30) : 0;  // leave 2 GiB for I/O buffers
+  const uint64_t fit = usable / c->layout.total;
+  if (fit == 0) return Fail(c, GMX_E_NOMEM, "one stream arena needs %llu MiB but only %llu MiB are free",
+                            (unsigned long long)(c->layout.total >> 20), (unsigned long long)(free_b >> 20));
+  if (fit < want) want = fit;
+  GMX_CUDA(c, cudaMalloc(&c->d_arenas, want * c->layout.total));
+  GMX_CUDA(c, cudaMemcpy(c->d_layout, &c->layout, sizeof(c->layout), cudaMemcpyHostToDevice));
+  c->n_arenas = (uint32_t)want;
+  c->cfg_max_len = max_stream_len;
+  return 0;
+}
+
+uint64_t gmx_compress_bound(uint64_t n) { return n + n / 16 + 64; }
+
+int gmx_compress_batch(gmx_ctx* c, const uint8_t* in, const uint64_t* in_off, uint32_t n, uint8_t* out,
+                       const uint64_t* out_off, uint64_t* out_len, uint32_t* status) {
+  return RunHost(c, gmx::MODE_COMPRESS, in, in_off, n, out, out_off, out_len, status, nullptr, nullptr);
+}
+int gmx_decompress_batch(gmx_ctx* c, const uint8_t* in, const uint64_t* in_off, uint32_t n, uint8_t* out,
+                         const uint64_t* out_off, uint64_t* out_len, uint32_t* status) {
+  return RunHost(c, gmx::MODE_DECOMPRESS, in, in_off, n, out, out_off, out_len, status, nullptr, nullptr);
+}
+int gmx_compress_batch_device(gmx_ctx* c, const uint8_t* d_in, const uint64_t* d_in_off, uint32_t n, uint8_t* d_out,
+                              const uint64_t* d_out_off, uint64_t* d_out_len, uint32_t* d_status, uint64_t max_len) {
+  return RunDevice(c, gmx::MODE_COMPRESS, d_in, d_in_off, n, d_out, d_out_off, d_out_len, d_status, max_len, nullptr, nullptr);
+}
+int gmx_decompress_batch_device(gmx_ctx* c, const uint8_t* d_in, const uint64_t* d_in_off, uint32_t n, uint8_t* d_out,
+                                const uint64_t* d_out_off, uint64_t* d_out_len, uint32_t* d_status, uint64_t max_len) {
+  return RunDevice(c, gmx::MODE_DECOMPRESS, d_in, d_in_off, n, d_out, d_out_off, d_out_len, d_status, max_len, nullptr, nullptr);
+}
+
+int gmx_compress_trace(gmx_ctx* c, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_len,
+                       float* probs, uint32_t* p16, float* blackboard) {
+  if (!c || !probs || !p16) return GMX_E_ARG;
+  std::vector<uint64_t> bt(n * 8 + 1);
+  const uint64_t io[2] = {0, n}, oo[2] = {0, cap};
+  uint32_t status = 0;
+  int rc = RunHost(c, gmx::MODE_COMPRESS, in, io, 1, out, oo, out_len, &status, bt.data(), blackboard);
+  if (rc) return rc;
+  for (uint64_t i = 0; i < n * 8; ++i) {
+    const uint32_t lo = (uint32_t)bt[i];
+    memcpy(&probs[i], &lo, 4);
+    p16[i] = (uint32_t)(bt[i] >> 32);
+  }
+  return 0;
+}
+
+uint32_t gmx_resident_streams(const gmx_ctx* c) { return c ? c->last_grid : 0; }
+uint64_t gmx_arena_bytes(const gmx_ctx* c) { return c ? c->layout.total : 0; }
+uint64_t gmx_kernel_launches(const gmx_ctx* c) { return c ? c->launches : 0; }
+double gmx_last_kernel_ms(const gmx_ctx* c) { return c ? c->last_ms : 0; }
+int gmx_device_sm_count(const gmx_ctx* c) { return c ? c->sm_count : 0; }
+
+int gmx_selftest_math(gmx_ctx* c, uint32_t stride, uint64_t mismatches[3], uint32_t first_bad[3]) {
+  if (!c || !mismatches || !first_bad || stride == 0) return GMX_E_ARG;
+  GMX_CUDA(c, cudaSetDevice(c->device));
+  const uint32_t chunk = 1u << 24;
+  float *d[3] = {nullptr, nullptr, nullptr};
+  for (int k = 0; k < 3; ++k) GMX_CUDA(c, cudaMalloc(&d[k], (size_t)chunk * 4));
+  std::vector<float> h[3];
+  for (int k = 0; k < 3; ++k) h[k].resize(chunk);
+  std::atomic<uint64_t> bad[3];
+  std::atomic<uint32_t> first[3];
+  for (int k = 0; k < 3; ++k) { bad[k] = 0; first[k] = 0xffffffffu; }
+  const uint64_t total = ((1ull << 32) + stride - 1) / stride;
+  unsigned nt = std::thread::hardware_concurrency();
+  if (nt == 0) nt = 4;
+  if (nt > 64) nt = 64;
+  for (uint64_t done = 0; done < total; done += chunk) {
+    const uint32_t count = (uint32_t)((total - done) < chunk ? (total - done) : chunk);
+    const uint32_t first_u = (uint32_t)(done * stride);
+    MathSweepKernel<<<(count + 255) / 256, 256, 0, c->stream>>>(first_u, stride, count, d[0], d[1], d[2]);
+    GMX_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    for (int k = 0; k < 3; ++k) GMX_CUDA(c, cudaMemcpyAsync(h[k].data(), d[k], (size_t)count * 4, cudaMemcpyDeviceToHost, c->stream));
+    GMX_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) th.emplace_back([&, t] {
+      for (uint32_t i = t; i < count; i += nt) {
+        const uint32_t u = first_u + i * stride;
+        float x;
+        memcpy(&x, &u, 4);
+        if (!SameFloat(h[0][i], expf(x))) { bad[0]++; uint32_t f = first[0]; while (u < f && !first[0].compare_exchange_weak(f, u)) {} }
+        if (u >= 0x00800000u && u < 0x7f800000u && !SameFloat(h[1][i], logf(x))) { bad[1]++; uint32_t f = first[1]; while (u < f && !first[1].compare_exchange_weak(f, u)) {} }
+        if (!SameFloat(h[2][i], tanhf(x))) { bad[2]++; uint32_t f = first[2]; while (u < f && !first[2].compare_exchange_weak(f, u)) {} }
+      }
+    });
+    for (auto& x : th) x.join();
+  }
+  for (int k = 0; k < 3; ++k) { cudaFree(d[k]); mismatches[k] = bad[k]; first_bad[k] = first[k]; }
+  return 0;
+}
+
+}  // extern "C"

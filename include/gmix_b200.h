@@ -1,0 +1,107 @@
+/* gmix_b200 — C ABI of the B200-native gmix per-bit path (libgmix_b200.so).
+ *
+ * This is the drop-in boundary: plain C, plain pointers and sizes, no CUDA or torch types. The
+ * reference has no FFI of its own (it is one C++ program); what it exposes for this path is the
+ * Predictor class and the runner entry points, so each entry point below cites the reference
+ * interface it replaces (paths relative to the reference's src/):
+ *
+ *   gmx_compress_batch / _device    runner_utils::RunCompression + Compress   runner/runner-utils.cpp:43-67,88-121
+ *   gmx_decompress_batch / _device  runner_utils::RunDecompression + Decompress runner/runner-utils.cpp:69-86,123-156
+ *                                   (coder: coder/encoder.cpp:8-34, coder/decoder.cpp:3-39;
+ *                                    per bit: Predictor::Predict/Perceive/Learn predictor.cpp:360-387)
+ *   gmx_compress_trace              same loop, additionally exporting what Predictor::Predict returns per bit
+ *
+ * A per-bit host<->device call is a non-starter (2.1e9 bit steps in the 4096 x 64 KiB config), so
+ * the ABI is stream-batch granular: n independent streams, each compressed from scratch exactly
+ * like one `gmix -c` process would, one CTA per stream. Stream framing is the reference's:
+ * 5-byte big-endian length, then the arithmetic-coder bytes.
+ *
+ * Conventions: return 0 on success, negative gmx error code otherwise (never throws); the caller
+ * owns every buffer passed in; the library owns its device memory; a gmx_ctx is bound to one GPU
+ * and must be used from one host thread at a time (one ctx per GPU for multi-GPU). There is NO CPU
+ * fallback: without a usable CUDA device gmx_create fails.
+ */
+#ifndef GMIX_B200_H_
+#define GMIX_B200_H_
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gmx_ctx gmx_ctx;
+
+enum {
+  GMX_E_OK = 0,
+  GMX_E_CUDA = -1,        /* CUDA runtime error, see gmx_last_error */
+  GMX_E_ARG = -2,         /* invalid argument */
+  GMX_E_NOMEM = -3,       /* not enough device memory for even one stream arena */
+  GMX_E_STREAM = -4,      /* at least one stream failed; per-stream codes in status[] */
+  GMX_E_NODEVICE = -5     /* no CUDA device / wrong architecture */
+};
+
+/* Per-stream status codes written to status[] (0 = ok). */
+enum {
+  GMX_S_OK = 0, GMX_S_PPMD_ARENA = 1, GMX_S_MIXER_POOL = 2, GMX_S_OUTPUT_CAP = 3,
+  GMX_S_MATCH_RANGE = 4, GMX_S_HISTORY_CAP = 5, GMX_S_BAD_HEADER = 6
+};
+
+const char* gmx_version(void);
+/* Library-level error text for failures that happen before a ctx exists. */
+const char* gmx_global_error(void);
+
+int gmx_create(int device, gmx_ctx** out);
+void gmx_destroy(gmx_ctx* ctx);
+const char* gmx_last_error(const gmx_ctx* ctx);
+
+/* Launch kernels on an existing CUDA stream (cudaStream_t passed as void*), e.g. torch's current
+ * stream, so the caller can bracket calls with its own CUDA events. NULL = the ctx's own stream. */
+int gmx_set_cuda_stream(gmx_ctx* ctx, void* cuda_stream);
+
+/* Size the per-CTA stream arenas: max_stream_len = longest uncompressed stream in bytes,
+ * max_resident = upper bound on concurrently resident streams (0 = as many as fit, at most one
+ * wave of co-resident CTAs). Called implicitly by the batch calls when needed. */
+int gmx_configure(gmx_ctx* ctx, uint64_t max_stream_len, uint32_t max_resident);
+
+/* Worst-case compressed size of an n-byte stream (header + coder bytes). */
+uint64_t gmx_compress_bound(uint64_t n);
+
+/* Compress n_streams independent streams. Stream i is in[in_off[i] .. in_off[i+1]); its output goes
+ * to out[out_off[i] ..] with capacity out_off[i+1]-out_off[i]; out_len[i] receives its length and
+ * status[i] its per-stream code. Host-pointer variant: copies in, runs, copies out. */
+int gmx_compress_batch(gmx_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uint32_t n_streams,
+                       uint8_t* out, const uint64_t* out_off, uint64_t* out_len, uint32_t* status);
+int gmx_decompress_batch(gmx_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uint32_t n_streams,
+                         uint8_t* out, const uint64_t* out_off, uint64_t* out_len, uint32_t* status);
+/* Device-pointer variants: every pointer is a device pointer on the ctx's GPU; max_stream_len is the
+ * longest uncompressed stream (for arena sizing). Enqueued on the ctx stream and synchronised
+ * before returning. */
+int gmx_compress_batch_device(gmx_ctx* ctx, const uint8_t* d_in, const uint64_t* d_in_off, uint32_t n_streams,
+                              uint8_t* d_out, const uint64_t* d_out_off, uint64_t* d_out_len, uint32_t* d_status,
+                              uint64_t max_stream_len);
+int gmx_decompress_batch_device(gmx_ctx* ctx, const uint8_t* d_in, const uint64_t* d_in_off, uint32_t n_streams,
+                                uint8_t* d_out, const uint64_t* d_out_off, uint64_t* d_out_len, uint32_t* d_status,
+                                uint64_t max_stream_len);
+
+/* Single-stream compress that also returns, per input bit, what Predictor::Predict returned
+ * (probs[8n]) and the coder's 16-bit probability (p16[8n]); blackboard[8n*126] (optional, may be
+ * NULL) receives the 90 stretched predictions, 3 active-mask words and 24+8+1 mixer outputs. */
+int gmx_compress_trace(gmx_ctx* ctx, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_len,
+                       float* probs, uint32_t* p16, float* blackboard);
+
+/* Introspection for benchmarks. */
+uint32_t gmx_resident_streams(const gmx_ctx* ctx);   /* CTAs (= arenas) the last launch used */
+uint64_t gmx_arena_bytes(const gmx_ctx* ctx);        /* bytes of one stream arena */
+uint64_t gmx_kernel_launches(const gmx_ctx* ctx);    /* kernels launched by this ctx so far */
+double gmx_last_kernel_ms(const gmx_ctx* ctx);       /* device time of the last stream kernel (CUDA events) */
+int gmx_device_sm_count(const gmx_ctx* ctx);
+
+/* Exhaustive check of the device expf/logf/tanhf against the host libm: inputs are the bit
+ * patterns 0, stride, 2*stride, ... < 2^32 (logf: positive normals only). mismatches[3] and
+ * first_bad[3] are indexed expf, logf, tanhf. */
+int gmx_selftest_math(gmx_ctx* ctx, uint32_t stride, uint64_t mismatches[3], uint32_t first_bad[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMIX_B200_H_ */
