@@ -53,6 +53,8 @@ def load_library():
     lib.gmx_last_kernel_ms.argtypes = [C.c_void_p]
     lib.gmx_last_kernel_ms.restype = C.c_double
     lib.gmx_device_sm_count.argtypes = [C.c_void_p]
+    lib.gmx_set_profile.argtypes = [C.c_void_p, C.c_int]
+    lib.gmx_get_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     lib.gmx_selftest_math.argtypes = [C.c_void_p, C.c_uint32, u64p, u32p]
     _LIB = lib
     return lib
@@ -178,6 +180,19 @@ class Context:
     @property
     def sm_count(self):
         return int(self.lib.gmx_device_sm_count(self.h))
+
+    PROFILE_SLOTS = ("byte_ctx+ppmd", "ppm_norm", "lstm_fwd", "nodes", "lookups", "mix_swap", "mix_predict", "coder",
+                     "learn_scalars", "mix_update", "lstm_out_step", "bptt_epochs", "bptt_grads", "init", "bit_misc", "-")
+
+    def set_profile(self, on=True):
+        self._check(self.lib.gmx_set_profile(self.h, int(on)), "gmx_set_profile")
+
+    def get_profile(self, max_streams=1):
+        buf = np.zeros((max_streams, 16), dtype=np.uint64)
+        n = self.lib.gmx_get_profile(self.h, buf.ctypes.data, max_streams)
+        if n < 0:
+            self._check(n, "gmx_get_profile")
+        return buf[:n]
 
     def selftest_math(self, stride=1):
         mism = (C.c_uint64 * 3)()

@@ -6,12 +6,12 @@ import sys
 ROOT = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(ROOT, "csrc")
 LIB = os.path.join(ROOT, "lib", "libgmix_b200.so")
-SOURCES = ["gmix_b200.cu"]
-DEPS = ["gmix_b200.cu", "stream_kernel.cuh", "ppmd.cuh", "dmath.cuh", "spec.cuh", "layout.h", "nonstationary.inc",
+SOURCES = ["host.cu", "kernel_compress.cu", "kernel_decompress.cu"]
+DEPS = ["host.cu", "kernel_compress.cu", "kernel_decompress.cu", "kernels.h", "stream_kernel.cuh", "ppmd.cuh", "dmath.cuh", "spec.cuh", "layout.h", "nonstationary.inc",
         os.path.join("..", "..", "include", "gmix_b200.h")]
 
 NVCC_FLAGS = [
-    "-std=c++17", "-shared", "-O3", "-lineinfo",
+    "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
     # exactness: no FMA contraction on the device, none on the host either
     "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off",
@@ -30,8 +30,29 @@ def build_library(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    objdir = os.path.join(ROOT, "lib", "obj")
+    os.makedirs(objdir, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = ["-Xptxas", "-v"] if verbose else []
+    procs, objs = [], []
+    for src in SOURCES:  # the translation units compile in parallel (each stream kernel takes ptxas > 1 min)
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
+        print("[gmix_b200] " + " ".join(cmd), file=sys.stderr)
+        log = open(obj + ".log", "w")
+        procs.append((subprocess.Popen(cmd, stdout=log, stderr=subprocess.STDOUT), obj, log))
+    failed = False
+    for p, obj, log in procs:
+        rc = p.wait()
+        log.close()
+        out = open(obj + ".log").read()
+        if rc != 0 or verbose:
+            print(out, file=sys.stderr)
+        failed |= rc != 0
+    if failed:
+        raise RuntimeError("nvcc failed")
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
     print("[gmix_b200] " + " ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True)
     return LIB

@@ -13,12 +13,10 @@
 #include <vector>
 
 #include "../../include/gmix_b200.h"
+#include "kernels.h"
 #include "layout.h"
-#include "stream_kernel.cuh"
 
 namespace {
-
-constexpr int kThreads = 256;
 
 std::string g_global_error;
 
@@ -49,7 +47,9 @@ struct gmx_ctx {
   uint32_t* d_queue = nullptr;
   std::vector<float> h_decay;
   // staging buffers of the host-pointer entry points
-  DevBuf b_in, b_out, b_in_off, b_out_off, b_out_len, b_status, b_trace, b_ptrace;
+  DevBuf b_in, b_out, b_in_off, b_out_off, b_out_len, b_status, b_trace, b_ptrace, b_prof;
+  bool profile = false;
+  uint32_t prof_streams = 0;
   uint32_t last_grid = 0;
   uint64_t launches = 0;
   double last_ms = 0;
@@ -89,12 +89,10 @@ void FreeArenas(gmx_ctx* c) {
   c->cfg_max_len = 0;
 }
 
-template <int MODE>
-int Launch(gmx_ctx* c, const gmx::StreamParams& P, uint32_t grid) {
+int Launch(gmx_ctx* c, int mode, const gmx::StreamParams& P, uint32_t grid) {
   GMX_CUDA(c, cudaMemsetAsync(c->d_queue, 0, sizeof(uint32_t), c->stream));
   GMX_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-  gmx::StreamKernel<kThreads, MODE><<<grid, kThreads, 0, c->stream>>>(P);
-  GMX_CUDA(c, cudaGetLastError());
+  GMX_CUDA(c, mode == gmx::MODE_COMPRESS ? gmx::LaunchCompress(P, grid, c->stream) : gmx::LaunchDecompress(P, grid, c->stream));
   GMX_CUDA(c, cudaEventRecord(c->ev1, c->stream));
   GMX_CUDA(c, cudaStreamSynchronize(c->stream));
   float ms = 0;
@@ -124,7 +122,14 @@ int RunDevice(gmx_ctx* c, int mode, const uint8_t* d_in, const uint64_t* d_in_of
   P.lstm_init = c->d_lstm_init; P.decay = c->d_decay; P.decay_len = c->decay_len; P.adam = c->d_adam;
   P.bit_trace = d_bit_trace; P.pred_trace = d_pred_trace;
   const uint32_t grid = n < c->n_arenas ? n : c->n_arenas;
-  return mode == gmx::MODE_COMPRESS ? Launch<gmx::MODE_COMPRESS>(c, P, grid) : Launch<gmx::MODE_DECOMPRESS>(c, P, grid);
+  if (c->profile) {
+    int rc = Reserve(c, c->b_prof, (size_t)n * gmx::GMX_PROF_SLOTS * 8);
+    if (rc) return rc;
+    GMX_CUDA(c, cudaMemsetAsync(c->b_prof.p, 0, (size_t)n * gmx::GMX_PROF_SLOTS * 8, c->stream));
+    P.prof = (unsigned long long*)c->b_prof.p;
+    c->prof_streams = n;
+  }
+  return Launch(c, mode, P, grid);
 }
 
 int RunHost(gmx_ctx* c, int mode, const uint8_t* in, const uint64_t* in_off, uint32_t n, uint8_t* out,
@@ -248,7 +253,7 @@ void gmx_destroy(gmx_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   FreeArenas(c);
-  for (DevBuf* b : {&c->b_in, &c->b_out, &c->b_in_off, &c->b_out_off, &c->b_out_len, &c->b_status, &c->b_trace, &c->b_ptrace})
+  for (DevBuf* b : {&c->b_in, &c->b_out, &c->b_in_off, &c->b_out_off, &c->b_out_len, &c->b_status, &c->b_trace, &c->b_ptrace, &c->b_prof})
     if (b->p) cudaFree(b->p);
   if (c->d_layout) cudaFree(c->d_layout);
   if (c->d_lstm_init) cudaFree(c->d_lstm_init);
@@ -286,7 +291,7 @@ int gmx_configure(gmx_ctx* c, uint64_t max_stream_len, uint32_t max_resident) {
     c->decay_len = (uint32_t)c->h_decay.size();
   }
   int per_sm = 0;
-  GMX_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gmx::StreamKernel<kThreads, gmx::MODE_COMPRESS>, kThreads, 0));
+  GMX_CUDA(c, gmx::OccupancyCompress(&per_sm));
   if (per_sm < 1) per_sm = 1;
   uint64_t want = (uint64_t)per_sm * c->sm_count;
   if (max_resident && max_resident < want) want = max_resident;
@@ -337,6 +342,19 @@ int gmx_compress_trace(gmx_ctx* c, const uint8_t* in, uint64_t n, uint8_t* out, 
     p16[i] = (uint32_t)(bt[i] >> 32);
   }
   return 0;
+}
+
+int gmx_set_profile(gmx_ctx* c, int on) {
+  if (!c) return GMX_E_ARG;
+  c->profile = on != 0;
+  return 0;
+}
+int gmx_get_profile(gmx_ctx* c, uint64_t* out, uint32_t max_streams) {
+  if (!c || !out) return GMX_E_ARG;
+  const uint32_t n = c->prof_streams < max_streams ? c->prof_streams : max_streams;
+  if (n == 0 || !c->b_prof.p) return 0;
+  GMX_CUDA(c, cudaMemcpy(out, c->b_prof.p, (size_t)n * gmx::GMX_PROF_SLOTS * 8, cudaMemcpyDeviceToHost));
+  return (int)n;
 }
 
 uint32_t gmx_resident_streams(const gmx_ctx* c) { return c ? c->last_grid : 0; }

@@ -32,7 +32,24 @@ enum : uint32_t {
   GMX_ERR_BAD_HEADER = 6,
 };
 
-enum : int { WSTRIDE = 117 };  // smem stride of one staged mixer weight set (odd: conflict-free lanes)
+enum : int { WSTRIDE = 117 };
+enum : int { GMX_PROF_SLOTS = 16 };
+// Phase slots: 0 byte contexts+PPMd, 1 ppm normalise, 2 LSTM forward, 3 interval nodes, 4 indirect/match
+// lookups, 5 mixer set swap, 6 mixer predict, 7 coder, 8 learn scalars+indirect, 9 mixer weight update,
+// 10 LSTM output-layer step, 11 BPTT epochs, 12 BPTT weight grads+Adam, 13 stream init, 14 bit bookkeeping.
+#if defined(__CUDA_ARCH__)
+#define GMX_CLOCK() clock64()
+#else
+#define GMX_CLOCK() 0ll
+#endif
+#define GMX_PROF(slot)                                                        \
+  do {                                                                        \
+    if (P.prof && tid == 0) {                                                 \
+      const long long t_ = GMX_CLOCK();                                       \
+      s.prof[slot] += (unsigned long long)(t_ - s.prof_t);                    \
+      s.prof_t = t_;                                                          \
+    }                                                                         \
+  } while (0)  // smem stride of one staged mixer weight set (odd: conflict-free lanes)
 
 // Byte offsets (from the arena base) of every per-stream table. Filled by the host (layout.h).
 struct ArenaLayout {
@@ -74,6 +91,7 @@ struct StreamParams {
   const float* adam;         // [L_UPDATE_LIMIT + 1][4]: alpha, 1-b1^t, 1-b2^t (lstm-layer.cpp:16-33), host libm
   uint64_t* bit_trace;       // optional: {f32 prob, u32 p16} per bit of stream 0 (debug/parity), or null
   float* pred_trace;         // optional: 90 predictions + 3 mask words + 33 mixer outs per bit of stream 0
+  unsigned long long* prof;  // optional: GMX_PROF_SLOTS cycle counters per stream (phase breakdown), or null
 };
 
 // ---- device constant tables --------------------------------------------------------------------
@@ -133,6 +151,9 @@ struct StreamSmem {
   // coder
   uint32_t x1, x2, x;
   uint64_t out_pos, out_cap, in_pos, in_len;
+  // phase profiler (lap timer driven by thread 0)
+  unsigned long long prof[GMX_PROF_SLOTS];
+  long long prof_t;
 };
 
 struct Arena {
@@ -176,6 +197,7 @@ GMX_DEV void FillWords(uint32_t* p, uint64_t nwords, uint32_t v, int tid) {
 template <int NT>
 GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, int tid) {
   const ArenaLayout& L = *A.L;
+  if (tid == 0) s.prof_t = GMX_CLOCK();
   for (int k = 0; k < NIND; ++k) FillWords<NT>(A.at<uint32_t>(L.ind_tab[k]), ((uint64_t)L.ind_size[k] + 1) / 2, 0x00FF00FFu, tid);
   FillWords<NT>(A.at<uint32_t>(L.ind_pred), NIND * 512, 0u, tid);
   for (int k = 0; k < NMATCH; ++k) FillWords<NT>(A.at<uint32_t>(L.match_tab[k]), 1ull << kMatch[k].log2, 0u, tid);
@@ -219,6 +241,7 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
     s.first_prediction = 1; s.error = 0; s.steps = 0; s.pool_next = 1; s.hist_len = 0;
     s.l_epoch = 0; s.l_update_steps = 0; s.l_old_input = 0; s.l_in[L_NIN] = 0;
     s.x1 = 0; s.x2 = 0xffffffffu; s.x = 0;
+    for (int i = 0; i < GMX_PROF_SLOTS; ++i) s.prof[i] = 0;
   }
   BlockSync();
   if (tid == 0) {
@@ -226,12 +249,13 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
     pm.Init();
   }
   BlockSync();
+  GMX_PROF(13);
 }
 
 // ---- LSTM forward at a byte boundary (Lstm::Predict lstm.cpp:91-122, LstmLayer::ForwardPass
 // lstm-layer.cpp:198-241). Precondition: s.ppm holds the normalised PPMd distribution. --------------
 template <int NT>
-GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, int tid) {
+GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, int tid) {
   const ArenaLayout& L = *A.L;
   const uint32_t e = s.l_epoch;
   const uint32_t sym = s.ctx[C_LAST_BYTE];
@@ -419,6 +443,7 @@ GMX_DEV void LstmBptt(StreamSmem& s, const Arena& A, const StreamParams& P, int 
     }
     BlockSync();
   }
+  GMX_PROF(11);
   // Weight gradients + Adam (lstm-layer.cpp:340-353, :12-34), one weight per thread at a time.
   const float* ad = P.adam + 4 * s.l_update_steps;
   const float alpha = ad[0], d1 = ad[1], d2 = ad[2];
@@ -463,6 +488,7 @@ GMX_DEV void LstmBptt(StreamSmem& s, const Arena& A, const StreamParams& P, int 
     *w = f_sub(*w, f_mul(alpha, f_div(f_div(m, d1), f_sqrt(f_add(f_div(v, d2), eps)))));
   }
   BlockSync();
+  GMX_PROF(12);
 }
 
 // Lstm::Perceive (lstm.cpp:52-89) on the 8th bit of a byte.
@@ -490,6 +516,7 @@ GMX_DEV void LstmPerceive(StreamSmem& s, const Arena& A, const StreamParams& P, 
     for (int j = 0; j < L_HID; ++j) wc[j * L_NOUT + i] = f_sub(wl[j * L_NOUT + i], f_mul(le, s.l_hidden[j]));
   }
   BlockSync();
+  GMX_PROF(10);
 }
 
 // Binary interval search node tables (ModPPMD::Predict mod_ppmd.cpp:1662-1681, LstmModel::Predict
@@ -551,6 +578,7 @@ GMX_DEV void ByteBoundary(StreamSmem& s, const Arena& A, const StreamParams& P, 
     if (pm.S->error) s.error = GMX_ERR_PPMD_ARENA;
   }
   BlockSync();
+  GMX_PROF(0);
   // (2) ppm_predictions = max(sqp, 1) / sum, valarray::sum() ascending (mod_ppmd.cpp:1655-1661)
   for (int i = tid; i < 256; i += NT) { float v = (float)s.sqp[i]; if (v < 1.0f) v = 1.0f; s.ppm[i] = v; }
   // Indirect row bases ((ctx << 8) % M, so that slot = (base + bit_context) % M) and L2 prefetch of
@@ -585,7 +613,9 @@ GMX_DEV void ByteBoundary(StreamSmem& s, const Arena& A, const StreamParams& P, 
   }
   BlockSync();
   // (3) LSTM forward (LstmModel::Predict byte part, lstm-model.cpp:19-34)
-  LstmForward<NT>(s, A, tid);
+  GMX_PROF(1);
+  LstmForward<NT>(s, A, P, tid);
+  GMX_PROF(2);
   // lstm_prediction_context = first index of the maximum, strict > from 0 (lstm-model.cpp:26-33)
   {
     float bv = 0.0f; int bi = 0;
@@ -615,6 +645,7 @@ GMX_DEV void ByteBoundary(StreamSmem& s, const Arena& A, const StreamParams& P, 
       if (kInd[k].ctx == C_LSTM) s.ind_base[k] = (s.ctx[C_LSTM] << 8) % L.ind_size[k];
   }
   BlockSync();
+  GMX_PROF(3);
 }
 
 // ---- Predictor::Predict (predictor.cpp:360-376) --------------------------------------------------
@@ -644,6 +675,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     s.bb = s.recent_bits == 1;
   }
   BlockSync();
+  GMX_PROF(14);
   if (s.bb) ByteBoundary<NT>(s, A, P, tid);
   const uint32_t bitctx = s.ctx[C_BIT_CONTEXT];
   const bool zero_inactive = s.analysis != 0;  // predictor.cpp:362-365
@@ -702,6 +734,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     else { s.act[which] = 0; if (zero_inactive) s.preds[which] = 0.0f; }
   }
   BlockSync();
+  GMX_PROF(4);
   // Mixer gate selection (mixer.cpp:29-37): which weight set does each mixer need for this bit?
   if (tid < NMIX) {
     const int m = tid;
@@ -751,6 +784,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     if (lane == 0) { s.set_pool[m] = nid; s.set_idx[m] = nidx; }
   }
   BlockSync();
+  GMX_PROF(5);
   // Mixer::Predict (mixer.cpp:51-106): warp 0, one lane per neuron, sequential sums, the serial
   // same-layer chain is resolved by warp shuffles in neuron order.
   if (tid < 32) {
@@ -795,6 +829,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     }
   }
   BlockSync();
+  GMX_PROF(6);
 }
 
 // ---- Predictor::Learn (predictor.cpp:383-387) ----------------------------------------------------
@@ -864,6 +899,7 @@ GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int 
     else A.at<uint8_t>(L.history)[s.hist_len] = (uint8_t)cur;
   }
   BlockSync();
+  GMX_PROF(8);
   // Mixer weight updates (mixer.cpp:128-175): w -= update * x over exactly the inputs used by
   // Predict, then the (1 - 3e-6) shrink every 1024 steps of the set.
   for (int f = tid; f < NMIX * WSTRIDE; f += NT) {
@@ -890,6 +926,7 @@ GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int 
   }
   if (tid == 0) { s.steps++; s.hist_len = hist_after; }
   BlockSync();
+  GMX_PROF(9);
   if (byte_done) LstmPerceive<NT>(s, A, P, (uint32_t)(cur - 256), tid);  // LstmModel::Learn lstm-model.cpp:50-59
 }
 
@@ -952,6 +989,7 @@ GMX_DEV void CompressStream(StreamSmem& s, const Arena& A, const StreamParams& P
         s.new_bit = bit;
       }
       BlockSync();
+      GMX_PROF(7);
       LearnBit<NT>(s, A, P, tid);
       if (s.error) break;
     }
@@ -963,6 +1001,7 @@ GMX_DEV void CompressStream(StreamSmem& s, const Arena& A, const StreamParams& P
     PutByte(s, out, s.x2 >> 24);
     P.out_len[sid] = s.out_pos;
     P.status[sid] = s.error;
+    if (P.prof) for (int i = 0; i < GMX_PROF_SLOTS; ++i) P.prof[(size_t)sid * GMX_PROF_SLOTS + i] = s.prof[i];
   }
   BlockSync();
 }
@@ -999,13 +1038,17 @@ GMX_DEV void DecompressStream(StreamSmem& s, const Arena& A, const StreamParams&
         if (j == 0) out[pos] = (uint8_t)((s.recent_bits * 2 + bit) & 0xff);
       }
       BlockSync();
+      GMX_PROF(7);
       LearnBit<NT>(s, A, P, tid);
       if (s.error) break;
     }
     if (s.error) break;
   }
   BlockSync();
-  if (tid == 0) { P.out_len[sid] = s.error ? 0 : n; P.status[sid] = s.error; }
+  if (tid == 0) {
+    P.out_len[sid] = s.error ? 0 : n; P.status[sid] = s.error;
+    if (P.prof) for (int i = 0; i < GMX_PROF_SLOTS; ++i) P.prof[(size_t)sid * GMX_PROF_SLOTS + i] = s.prof[i];
+  }
   BlockSync();
 }
 
