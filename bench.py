@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Benchmark of the gmix per-bit path on B200 (BASELINE.json metric: aggregate compress MB/s).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU code, all host cores
+
+Workload = BASELINE.json configs[1]: independent 64 KiB synthetic-text chunks (gmix_b200/synth.py,
+SURVEY.md section 8d), every chunk compressed from scratch as its own stream, one CTA per stream.
+A *step* is one pass of the hot path over one batch of `--chunks` chunks per GPU (default: 4096, the
+whole configs[1] set; smaller batches are named in config.chunks_per_step). Weak scaling: every
+rank compresses its own `--chunks` chunks (chunk ids are disjoint across ranks), no collective on the
+data path; after every step one NCCL all_gather collects {compressed size, FNV-1a checksum} per stream.
+
+JSON line keys follow the driver contract; `value` is device-resident throughput (inputs already in
+HBM), `e2e` is the same metric through the host-pointer C-ABI call (pinned host buffers, H2D and D2H
+inside the timed region). `roofline` is the HBM roofline of the stream kernel with SURVEY.md 8(d)'s
+algorithmic bytes (4.29e5 B of model-state traffic per input byte).
+"""
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_INPUT_BYTE = 4.29e5   # SURVEY.md section 8(d); derivation in DESIGN.md
+METRIC = "aggregate compress MB/s"
+UNIT = "MB/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chunks", type=int, default=int(os.environ.get("GMIX_BENCH_CHUNKS", "296")), help="chunks per GPU per step")
+    ap.add_argument("--chunk-bytes", type=int, default=65536)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--verify", type=int, default=1, help="streams per rank checked by a GPU decompress round trip after timing")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        exe = shutil.which("nvidia-smi")
+        if not exe:
+            return
+        self.proc = subprocess.Popen([exe, "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        mhz, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                mhz.append(float(r[0]))
+                mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(mhz) if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(mhz)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def chunk_ids(rank, step, per_step, total_set=4096):
+    """Chunk ids of this rank for one step: disjoint across ranks, walking the configs[1] set."""
+    base = (step * per_step) % max(total_set, per_step)
+    return [rank * max(total_set, per_step) + base + i for i in range(per_step)]
+
+
+_CHUNK_CACHE = {}
+
+
+def make_chunks(ids, size):
+    from gmix_b200 import synth
+    out = []
+    for i in ids:
+        if (i, size) not in _CHUNK_CACHE:
+            _CHUNK_CACHE[(i, size)] = synth.synthetic_text_chunk(i, size)
+        out.append(_CHUNK_CACHE[(i, size)])
+    return out
+
+
+def fnv1a(b):
+    h = 0xcbf29ce484222325
+    for x in b:
+        h = ((h ^ x) * 0x100000001b3) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation, one `gmix -c` process per host core
+def reference_binary():
+    p = os.path.join(ROOT, "oracle", "_ref", "gmix")
+    if os.path.exists(p):
+        return p, "reference"
+    p2 = os.path.join(ROOT, "oracle", "_build", "gmix_oracle")
+    if not os.path.exists(p2):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True, capture_output=True)
+    return p2, "port"
+
+
+def cpu_wave(binary, chunks, workdir, cores):
+    """Compress `chunks` with one process per core (at most `cores` at a time); returns wall seconds."""
+    paths = []
+    for i, c in enumerate(chunks):
+        p = os.path.join(workdir, f"c{i}.in")
+        with open(p, "wb") as f:
+            f.write(c)
+        paths.append(p)
+    t0 = time.perf_counter()
+    running, nxt = [], 0
+    while nxt < len(paths) or running:
+        while nxt < len(paths) and len(running) < cores:
+            running.append(subprocess.Popen([binary, "-c", paths[nxt], paths[nxt] + ".gmix"], stdout=subprocess.DEVNULL,
+                                            stderr=subprocess.DEVNULL, cwd=workdir))
+            nxt += 1
+        for p in list(running):
+            if p.poll() is not None:
+                if p.returncode != 0:
+                    raise RuntimeError(f"{binary} exited with {p.returncode}")
+                running.remove(p)
+        time.sleep(0.005)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(sample_bytes, cores=None):
+    """Bounded sample: one wave of `cores` streams of `sample_bytes` (prefixes of configs[1] chunks)."""
+    binary, kind = reference_binary()
+    cores = cores or os.cpu_count() or 1
+    chunks = make_chunks(list(range(cores)), sample_bytes)
+    with tempfile.TemporaryDirectory(prefix="gmix_cpu_") as wd:
+        os.makedirs(os.path.join(wd, "analysis"), exist_ok=True)
+        dt = cpu_wave(binary, chunks, wd, cores)
+    return {"value": cores * sample_bytes / dt / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{cores} streams x first {sample_bytes} B of configs[1] chunks, one `gmix -c` process per core, "
+                      f"{dt:.1f} s wall incl. process start-up"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    binary, kind = reference_binary()
+    cores = os.cpu_count() or 1
+    # a step = one wave of one stream per core; bounded sample: the first 16 KiB of each chunk
+    sample = min(args.chunk_bytes, 16384)
+    times = []
+    with tempfile.TemporaryDirectory(prefix="gmix_ref_") as wd:
+        os.makedirs(os.path.join(wd, "analysis"), exist_ok=True)
+        for step in range(args.warmup + args.steps):
+            chunks = make_chunks(chunk_ids(0, step, cores), sample)
+            dt = cpu_wave(binary, chunks, wd, cores)
+            if step >= args.warmup:
+                times.append(dt)
+    total = sum(times)
+    value = args.steps * cores * sample / total / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32+u8 (bit-exact integer/fp32 model state)", "data": "synthetic",
+        "config": {"workload": "configs[1]: independent 64 KiB synthetic-text chunks compressed from scratch",
+                   "chunk_bytes": args.chunk_bytes, "chunks_per_step": cores,
+                   "sample": f"first {sample} B of each chunk, one stream per host core per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{cores} streams x first {sample} B per step, one `gmix -c` process per core (strict -O2 build)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import gmix_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; gmix_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = gmix_b200.Context(local)
+    stream = torch.cuda.current_stream()
+    ctx.set_cuda_stream(stream.cuda_stream)
+    n, size = args.chunks, args.chunk_bytes
+    ctx.configure(size, 0)
+    cap = gmix_b200.compress_bound(size)
+    in_off = torch.arange(n + 1, dtype=torch.int64) * size
+    out_off = torch.arange(n + 1, dtype=torch.int64) * cap
+    d_in_off, d_out_off = in_off.to(dev), out_off.to(dev)
+    d_out = torch.zeros(n * cap + 16, dtype=torch.uint8, device=dev)
+    d_len = torch.zeros(n, dtype=torch.int64, device=dev)
+    d_status = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_sum = torch.zeros(n, dtype=torch.int64, device=dev)
+    gathered = [torch.zeros(2 * n, dtype=torch.int64, device=dev) for _ in range(world)] if world > 1 else None
+    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step_inputs(step):
+        data = b"".join(make_chunks(chunk_ids(rank, step, n), size))
+        return torch.frombuffer(bytearray(data), dtype=torch.uint8)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    kernel_ms, launches0 = [], ctx.kernel_launches
+
+    def device_step(d_in):
+        ctx.compress_batch_device(d_in.data_ptr(), d_in_off.data_ptr(), n, d_out.data_ptr(), d_out_off.data_ptr(),
+                                  d_len.data_ptr(), d_status.data_ptr(), size)
+        kernel_ms.append(ctx.last_kernel_ms)
+        ctx.checksum_device(d_out.data_ptr(), d_out_off.data_ptr(), d_len.data_ptr(), n, d_sum.data_ptr())
+        if world > 1:
+            dist.all_gather(gathered, torch.cat([d_len, d_sum]))
+
+    # ---- device-resident measurement --------------------------------------------------------------
+    total_steps = args.warmup + args.steps
+    inputs = [step_inputs(s).to(dev) for s in range(total_steps)]
+    for s in range(args.warmup):
+        device_step(inputs[s])
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    kernel_ms.clear()
+    launches_before = ctx.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for s in range(args.warmup, total_steps):
+        l2_flush.fill_(s & 0xff)          # flush L2 between timed steps (the arenas alone exceed L2 as well)
+        device_step(inputs[s])
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    gpu_launches = ctx.kernel_launches - launches_before
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    kms = torch.tensor([sum(kernel_ms) / max(len(kernel_ms), 1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kms, op=dist.ReduceOp.MAX)
+    ms_total, kernel_ms_avg = float(ms.item()), float(kms.item())
+    bad = int((d_status != 0).sum().item())
+    if bad:
+        raise SystemExit(f"bench.py: {bad} streams failed on rank {rank}: {d_status[d_status != 0][:8].tolist()}")
+    comp_bytes = int(d_len.sum().item())
+    value = world * n * size * args.steps / (ms_total / 1e3) / 1e6
+
+    # ---- parity spot check outside the timed region: GPU decompress of the last step's streams ------
+    if args.verify:
+        k = min(args.verify, n)
+        lens = d_len[:k].cpu().tolist()
+        comp = [bytes(d_out[i * cap:i * cap + lens[i]].cpu().numpy()) for i in range(k)]
+        ctx.set_cuda_stream(0)
+        back = ctx.decompress_batch(comp)
+        ctx.set_cuda_stream(stream.cuda_stream)
+        want = make_chunks(chunk_ids(rank, total_steps - 1, n)[:k], size)
+        assert back == want, "GPU decompress of a GPU-compressed stream does not reproduce the input"
+
+    # ---- end-to-end measurement through the host-pointer C ABI ---------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_in = [step_inputs(s).pin_memory() for s in range(total_steps)]
+        h_out = torch.zeros(n * cap + 16, dtype=torch.uint8).pin_memory()
+        h_len = torch.zeros(n, dtype=torch.int64).pin_memory()
+        h_status = torch.zeros(n, dtype=torch.int32).pin_memory()
+        np_in_off, np_out_off = in_off.numpy(), out_off.numpy()
+
+        def host_step(s):
+            rc = ctx.lib.gmx_compress_batch(ctx.h, h_in[s].data_ptr(), np_in_off.ctypes.data, n, h_out.data_ptr(),
+                                            np_out_off.ctypes.data, h_len.data_ptr(), h_status.data_ptr())
+            ctx._check(rc, "gmx_compress_batch")
+            return int(h_len.sum().item())           # the step's result is read on the host
+
+        e2e_steps = max(1, min(args.steps, 2))
+        host_step(0)
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(args.warmup, args.warmup + e2e_steps):
+            host_step(s)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n * size * e2e_steps / float(dt.item()) / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": n * size + 2 * 8 * (n + 1), "d2h_bytes_per_step": n * cap + 12 * n,
+               "steps": e2e_steps, "timing": "host wall clock around gmx_compress_batch (pinned buffers), max over ranks"}
+
+    if rank == 0:
+        pk, pk_kind = peaks()
+        achieved = n * size * ALGO_BYTES_PER_INPUT_BYTE / (kernel_ms_avg / 1e3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32+u8 (bit-exact integer/fp32 model state)", "data": "synthetic",
+            "config": {"workload": "configs[1]: independent 64 KiB synthetic-text chunks compressed from scratch, one CTA per stream",
+                       "chunk_bytes": size, "chunks_per_step": n, "chunks_per_step_all_gpus": n * world,
+                       "resident_streams_per_gpu": ctx.resident_streams, "arena_mib_per_stream": ctx.arena_bytes >> 20,
+                       "l2": "256 MiB flush write between timed steps; per-stream arenas exceed L2",
+                       "parallelism": f"streams sharded over {world} GPU(s), all_gather of sizes+checksums per step"},
+            "bits_per_byte": 8.0 * comp_bytes / (n * size),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_kind": pk_kind,
+                         "kernel": "gmx::StreamKernel<256, MODE_COMPRESS>", "kernel_ms": kernel_ms_avg,
+                         "algorithmic_bytes_per_input_byte": ALGO_BYTES_PER_INPUT_BYTE},
+            "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(min(size, 8192))
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

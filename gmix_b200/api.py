@@ -43,6 +43,7 @@ def load_library():
     lib.gmx_decompress_batch.argtypes = batch
     lib.gmx_compress_batch_device.argtypes = batch + [C.c_uint64]
     lib.gmx_decompress_batch_device.argtypes = batch + [C.c_uint64]
+    lib.gmx_checksum_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     lib.gmx_compress_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, u64p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gmx_resident_streams.argtypes = [C.c_void_p]
     lib.gmx_resident_streams.restype = C.c_uint32
@@ -159,6 +160,9 @@ class Context:
     def decompress_batch_device(self, d_in, d_in_off, n, d_out, d_out_off, d_out_len, d_status, max_stream_len):
         self._check(self.lib.gmx_decompress_batch_device(self.h, d_in, d_in_off, n, d_out, d_out_off, d_out_len, d_status, max_stream_len),
                     "gmx_decompress_batch_device")
+
+    def checksum_device(self, d_data, d_off, d_len, n, d_sum):
+        self._check(self.lib.gmx_checksum_device(self.h, d_data, d_off, d_len, n, d_sum), "gmx_checksum_device")
 
     # ---- introspection ----
     @property

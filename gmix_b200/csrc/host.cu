@@ -198,6 +198,16 @@ __global__ void MathSweepKernel(uint32_t first, uint32_t stride, uint32_t count,
   l[i] = (u >= 0x00800000u && u < 0x7f800000u) ? gmx::gm_logf(x) : 0.0f;
 }
 
+// FNV-1a 64 of every stream's output slice; one thread per stream (slices are tens of KB).
+__global__ void ChecksumKernel(const uint8_t* data, const uint64_t* off, const uint64_t* len, uint32_t n, uint64_t* sum) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* p = data + off[i];
+  uint64_t h = 0xcbf29ce484222325ull;
+  for (uint64_t k = 0, e = len[i]; k < e; ++k) h = (h ^ p[k]) * 0x100000001b3ull;
+  sum[i] = h;
+}
+
 bool SameFloat(float a, float b) {
   if (a != a && b != b) return true;
   uint32_t x, y;
@@ -326,6 +336,17 @@ int gmx_compress_batch_device(gmx_ctx* c, const uint8_t* d_in, const uint64_t* d
 int gmx_decompress_batch_device(gmx_ctx* c, const uint8_t* d_in, const uint64_t* d_in_off, uint32_t n, uint8_t* d_out,
                                 const uint64_t* d_out_off, uint64_t* d_out_len, uint32_t* d_status, uint64_t max_len) {
   return RunDevice(c, gmx::MODE_DECOMPRESS, d_in, d_in_off, n, d_out, d_out_off, d_out_len, d_status, max_len, nullptr, nullptr);
+}
+
+int gmx_checksum_device(gmx_ctx* c, const uint8_t* d_data, const uint64_t* d_off, const uint64_t* d_len, uint32_t n, uint64_t* d_sum) {
+  if (!c) return GMX_E_ARG;
+  if (n == 0) return 0;
+  if (!d_data || !d_off || !d_len || !d_sum) return Fail(c, GMX_E_ARG, "null pointer argument");
+  GMX_CUDA(c, cudaSetDevice(c->device));
+  ChecksumKernel<<<(n + 63) / 64, 64, 0, c->stream>>>(d_data, d_off, d_len, n, d_sum);
+  GMX_CUDA(c, cudaGetLastError());
+  c->launches += 1;
+  return 0;
 }
 
 int gmx_compress_trace(gmx_ctx* c, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_len,

@@ -83,6 +83,12 @@ int gmx_decompress_batch_device(gmx_ctx* ctx, const uint8_t* d_in, const uint64_
                                 uint8_t* d_out, const uint64_t* d_out_off, uint64_t* d_out_len, uint32_t* d_status,
                                 uint64_t max_stream_len);
 
+/* FNV-1a 64 checksum of every stream slice d_data[d_off[i] .. d_off[i]+d_len[i]) into d_sum[i] (device
+ * pointers; enqueued on the ctx stream, not synchronised). Used to gather {size, checksum} per stream
+ * across GPUs without moving the payload. */
+int gmx_checksum_device(gmx_ctx* ctx, const uint8_t* d_data, const uint64_t* d_off, const uint64_t* d_len,
+                        uint32_t n_streams, uint64_t* d_sum);
+
 /* Single-stream compress that also returns, per input bit, what Predictor::Predict returned
  * (probs[8n]) and the coder's 16-bit probability (p16[8n]); blackboard[8n*126] (optional, may be
  * NULL) receives the 90 stretched predictions, 3 active-mask words and 24+8+1 mixer outputs. */
