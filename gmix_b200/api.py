@@ -49,6 +49,8 @@ def load_library():
     lib.gmx_resident_streams.restype = C.c_uint32
     lib.gmx_arena_bytes.argtypes = [C.c_void_p]
     lib.gmx_arena_bytes.restype = C.c_uint64
+    lib.gmx_retried_streams.argtypes = [C.c_void_p]
+    lib.gmx_retried_streams.restype = C.c_uint64
     lib.gmx_kernel_launches.argtypes = [C.c_void_p]
     lib.gmx_kernel_launches.restype = C.c_uint64
     lib.gmx_last_kernel_ms.argtypes = [C.c_void_p]
@@ -56,6 +58,7 @@ def load_library():
     lib.gmx_device_sm_count.argtypes = [C.c_void_p]
     lib.gmx_set_profile.argtypes = [C.c_void_p, C.c_int]
     lib.gmx_get_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.gmx_get_usage.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     lib.gmx_selftest_math.argtypes = [C.c_void_p, C.c_uint32, u64p, u32p]
     _LIB = lib
     return lib
@@ -174,6 +177,10 @@ class Context:
         return int(self.lib.gmx_arena_bytes(self.h))
 
     @property
+    def retried_streams(self):
+        return int(self.lib.gmx_retried_streams(self.h))
+
+    @property
     def kernel_launches(self):
         return int(self.lib.gmx_kernel_launches(self.h))
 
@@ -196,6 +203,14 @@ class Context:
         n = self.lib.gmx_get_profile(self.h, buf.ctypes.data, max_streams)
         if n < 0:
             self._check(n, "gmx_get_profile")
+        return buf[:n]
+
+    def get_usage(self, max_streams):
+        """[n, 4] uint32: sparse-table entries, mixer weight sets, PPMd unit bytes, history bytes per stream."""
+        buf = np.zeros((max_streams, 4), dtype=np.uint32)
+        n = self.lib.gmx_get_usage(self.h, buf.ctypes.data, max_streams)
+        if n < 0:
+            self._check(n, "gmx_get_usage")
         return buf[:n]
 
     def selftest_math(self, stride=1):

@@ -34,12 +34,19 @@ struct gmx_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string error;
-  // arenas
+  // arenas: `layout`/`d_arenas` is the normal class every stream is first run in; `roomy` is the
+  // worst-case-sized class, allocated on demand for the streams that overflowed a normal arena
   uint64_t cfg_max_len = 0;
+  uint32_t cfg_max_resident = 0;
   uint32_t n_arenas = 0;
   gmx::ArenaLayout layout;
   uint8_t* d_arenas = nullptr;
   gmx::ArenaLayout* d_layout = nullptr;
+  uint32_t n_roomy = 0;
+  gmx::ArenaLayout roomy_layout;
+  uint8_t* d_roomy = nullptr;
+  gmx::ArenaLayout* d_roomy_layout = nullptr;
+  uint64_t retried_streams = 0;
   float* d_lstm_init = nullptr;
   float* d_adam = nullptr;
   float* d_decay = nullptr;
@@ -47,9 +54,10 @@ struct gmx_ctx {
   uint32_t* d_queue = nullptr;
   std::vector<float> h_decay;
   // staging buffers of the host-pointer entry points
-  DevBuf b_in, b_out, b_in_off, b_out_off, b_out_len, b_status, b_trace, b_ptrace, b_prof;
+  DevBuf b_in, b_out, b_in_off, b_out_off, b_out_len, b_status, b_trace, b_ptrace, b_prof, b_ids, b_usage;
   bool profile = false;
   uint32_t prof_streams = 0;
+  uint32_t usage_streams = 0;
   uint32_t last_grid = 0;
   uint64_t launches = 0;
   double last_ms = 0;
@@ -84,9 +92,16 @@ int Reserve(gmx_ctx* c, DevBuf& b, size_t bytes) {
 
 void FreeArenas(gmx_ctx* c) {
   if (c->d_arenas) cudaFree(c->d_arenas);
+  if (c->d_roomy) cudaFree(c->d_roomy);
   c->d_arenas = nullptr;
+  c->d_roomy = nullptr;
   c->n_arenas = 0;
+  c->n_roomy = 0;
   c->cfg_max_len = 0;
+}
+
+bool Retryable(uint32_t st) {
+  return st == gmx::GMX_ERR_PPMD_ARENA || st == gmx::GMX_ERR_MIXER_POOL || st == gmx::GMX_ERR_SPARSE_FULL;
 }
 
 int Launch(gmx_ctx* c, int mode, const gmx::StreamParams& P, uint32_t grid) {
@@ -97,10 +112,42 @@ int Launch(gmx_ctx* c, int mode, const gmx::StreamParams& P, uint32_t grid) {
   GMX_CUDA(c, cudaStreamSynchronize(c->stream));
   float ms = 0;
   GMX_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-  c->last_ms = ms;
-  c->last_grid = grid;
+  c->last_ms += ms;
   c->launches += 1;
   return 0;
+}
+
+// Streams whose normal arena overflowed (incompressible data touches far more table slots and gate
+// contexts than text) are re-run from scratch in worst-case-sized arenas.
+int RetryInRoomyArenas(gmx_ctx* c, int mode, gmx::StreamParams P, uint32_t n, uint32_t* d_status) {
+  std::vector<uint32_t> st(n), ids;
+  GMX_CUDA(c, cudaMemcpyAsync(st.data(), d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  GMX_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (uint32_t i = 0; i < n; ++i) if (Retryable(st[i])) ids.push_back(i);
+  if (ids.empty()) return 0;
+  if (!c->d_roomy) {
+    c->roomy_layout = gmx::MakeLayout(c->cfg_max_len, true);
+    size_t free_b = 0, total_b = 0;
+    GMX_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t usable = free_b > (1ull << 30) ? free_b - (1ull << 30) : 0;
+    uint64_t want = ids.size() < c->n_arenas ? ids.size() : c->n_arenas;
+    if (usable / c->roomy_layout.total < want) want = usable / c->roomy_layout.total;
+    if (want == 0) return Fail(c, GMX_E_NOMEM, "%zu streams overflowed their arena and no worst-case arena (%llu MiB) fits",
+                               ids.size(), (unsigned long long)(c->roomy_layout.total >> 20));
+    GMX_CUDA(c, cudaMalloc(&c->d_roomy, want * c->roomy_layout.total));
+    if (!c->d_roomy_layout) GMX_CUDA(c, cudaMalloc(&c->d_roomy_layout, sizeof(gmx::ArenaLayout)));
+    GMX_CUDA(c, cudaMemcpy(c->d_roomy_layout, &c->roomy_layout, sizeof(gmx::ArenaLayout), cudaMemcpyHostToDevice));
+    c->n_roomy = (uint32_t)want;
+  }
+  int rc = Reserve(c, c->b_ids, ids.size() * 4);
+  if (rc) return rc;
+  GMX_CUDA(c, cudaMemcpyAsync(c->b_ids.p, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  P.ids = (const uint32_t*)c->b_ids.p;
+  P.n_streams = (uint32_t)ids.size();
+  P.arenas = c->d_roomy; P.arena_stride = c->roomy_layout.total; P.layout = c->d_roomy_layout;
+  P.bit_trace = nullptr; P.pred_trace = nullptr;  // traces belong to stream 0 of the first launch
+  c->retried_streams += ids.size();
+  return Launch(c, mode, P, P.n_streams < c->n_roomy ? P.n_streams : c->n_roomy);
 }
 
 int RunDevice(gmx_ctx* c, int mode, const uint8_t* d_in, const uint64_t* d_in_off, uint32_t n, uint8_t* d_out,
@@ -111,7 +158,7 @@ int RunDevice(gmx_ctx* c, int mode, const uint8_t* d_in, const uint64_t* d_in_of
   if (!d_in || !d_in_off || !d_out || !d_out_off || !d_out_len || !d_status) return Fail(c, GMX_E_ARG, "null pointer argument");
   GMX_CUDA(c, cudaSetDevice(c->device));
   if (max_len > c->cfg_max_len || c->n_arenas == 0) {
-    int rc = gmx_configure(c, max_len, 0);
+    int rc = gmx_configure(c, max_len, c->cfg_max_resident);
     if (rc) return rc;
   }
   gmx::StreamParams P;
@@ -122,6 +169,12 @@ int RunDevice(gmx_ctx* c, int mode, const uint8_t* d_in, const uint64_t* d_in_of
   P.lstm_init = c->d_lstm_init; P.decay = c->d_decay; P.decay_len = c->decay_len; P.adam = c->d_adam;
   P.bit_trace = d_bit_trace; P.pred_trace = d_pred_trace;
   const uint32_t grid = n < c->n_arenas ? n : c->n_arenas;
+  {
+    int rc = Reserve(c, c->b_usage, (size_t)n * 16);
+    if (rc) return rc;
+    P.usage = (uint32_t*)c->b_usage.p;
+    c->usage_streams = n;
+  }
   if (c->profile) {
     int rc = Reserve(c, c->b_prof, (size_t)n * gmx::GMX_PROF_SLOTS * 8);
     if (rc) return rc;
@@ -129,7 +182,11 @@ int RunDevice(gmx_ctx* c, int mode, const uint8_t* d_in, const uint64_t* d_in_of
     P.prof = (unsigned long long*)c->b_prof.p;
     c->prof_streams = n;
   }
-  return Launch(c, mode, P, grid);
+  c->last_ms = 0;
+  c->last_grid = grid;
+  int rc = Launch(c, mode, P, grid);
+  if (rc) return rc;
+  return RetryInRoomyArenas(c, mode, P, n, d_status);
 }
 
 int RunHost(gmx_ctx* c, int mode, const uint8_t* in, const uint64_t* in_off, uint32_t n, uint8_t* out,
@@ -263,9 +320,10 @@ void gmx_destroy(gmx_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   FreeArenas(c);
-  for (DevBuf* b : {&c->b_in, &c->b_out, &c->b_in_off, &c->b_out_off, &c->b_out_len, &c->b_status, &c->b_trace, &c->b_ptrace, &c->b_prof})
+  for (DevBuf* b : {&c->b_in, &c->b_out, &c->b_in_off, &c->b_out_off, &c->b_out_len, &c->b_status, &c->b_trace, &c->b_ptrace, &c->b_prof, &c->b_ids, &c->b_usage})
     if (b->p) cudaFree(b->p);
   if (c->d_layout) cudaFree(c->d_layout);
+  if (c->d_roomy_layout) cudaFree(c->d_roomy_layout);
   if (c->d_lstm_init) cudaFree(c->d_lstm_init);
   if (c->d_adam) cudaFree(c->d_adam);
   if (c->d_decay) cudaFree(c->d_decay);
@@ -316,6 +374,7 @@ int gmx_configure(gmx_ctx* c, uint64_t max_stream_len, uint32_t max_resident) {
   GMX_CUDA(c, cudaMemcpy(c->d_layout, &c->layout, sizeof(c->layout), cudaMemcpyHostToDevice));
   c->n_arenas = (uint32_t)want;
   c->cfg_max_len = max_stream_len;
+  c->cfg_max_resident = max_resident;
   return 0;
 }
 
@@ -378,8 +437,17 @@ int gmx_get_profile(gmx_ctx* c, uint64_t* out, uint32_t max_streams) {
   return (int)n;
 }
 
+int gmx_get_usage(gmx_ctx* c, uint32_t* out, uint32_t max_streams) {
+  if (!c || !out) return GMX_E_ARG;
+  const uint32_t n = c->usage_streams < max_streams ? c->usage_streams : max_streams;
+  if (n == 0 || !c->b_usage.p) return 0;
+  GMX_CUDA(c, cudaMemcpy(out, c->b_usage.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
+  return (int)n;
+}
+
 uint32_t gmx_resident_streams(const gmx_ctx* c) { return c ? c->last_grid : 0; }
 uint64_t gmx_arena_bytes(const gmx_ctx* c) { return c ? c->layout.total : 0; }
+uint64_t gmx_retried_streams(const gmx_ctx* c) { return c ? c->retried_streams : 0; }
 uint64_t gmx_kernel_launches(const gmx_ctx* c) { return c ? c->launches : 0; }
 double gmx_last_kernel_ms(const gmx_ctx* c) { return c ? c->last_ms : 0; }
 int gmx_device_sm_count(const gmx_ctx* c) { return c ? c->sm_count : 0; }

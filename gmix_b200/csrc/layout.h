@@ -14,8 +14,13 @@ namespace gmx {
 
 inline uint64_t AlignUp(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
+inline uint64_t Pow2Ceil(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
+
 // max_len = longest stream (in uncompressed bytes) the arena must hold.
-inline ArenaLayout MakeLayout(uint64_t max_len) {
+// roomy = false: the shared sparse map and the mixer weight-set pool are sized for what text-like data
+// touches (a stream that needs more ends with GMX_ERR_SPARSE_FULL / GMX_ERR_MIXER_POOL and the host
+// re-runs it in a roomy arena); roomy = true: both are sized for the worst case of max_len bytes.
+inline ArenaLayout MakeLayout(uint64_t max_len, bool roomy = false) {
   static const IndirectSpec ind[NIND] = {GMX_INDIRECT_SPECS};
   static const IHSpec ih[NIH] = {GMX_IH_SPECS};
   static const MatchSpec mt[NMATCH] = {GMX_MATCH_SPECS};
@@ -24,17 +29,52 @@ inline ArenaLayout MakeLayout(uint64_t max_len) {
   memset(&L, 0, sizeof(L));
   uint64_t off = 0;
   auto take = [&](uint64_t bytes) { uint64_t o = off; off = AlignUp(off + bytes, 256); return o; };
+  // Which big tables go into the shared sparse map? Worst-case entry count vs their dense size.
+  uint64_t worst = 64, dense_bytes = 0;
+  uint32_t next_sid = 1;
   for (int k = 0; k < NIND; ++k) {
     L.ind_size[k] = (1u << ind[k].log2) * 256 + 1;  // indirect.cpp:15-19
-    L.ind_tab[k] = take(((uint64_t)L.ind_size[k] + 1) / 2 * 4);
+    if (ind[k].log2 >= 15) {
+      L.ind_sid[k] = (uint8_t)next_sid++;
+      worst += 8 * max_len < L.ind_size[k] ? 8 * max_len : L.ind_size[k];  // one new slot per bit at most
+      dense_bytes += ((uint64_t)L.ind_size[k] + 1) / 2 * 4;
+    }
   }
+  for (int k = 0; k < NMATCH; ++k)
+    if (mt[k].log2 >= 21) {
+      L.match_sid[k] = (uint8_t)next_sid++;
+      worst += max_len < (1ull << mt[k].log2) ? max_len : (1ull << mt[k].log2);  // one store per byte
+      dense_bytes += 4ull << mt[k].log2;
+    }
+  for (int k = 0; k < NIH; ++k)
+    if (ih[k].log2 >= 24) {
+      L.ih_sid[k] = (uint8_t)next_sid++;
+      worst += max_len + 1 < (1ull << ih[k].log2) ? max_len + 1 : (1ull << ih[k].log2);
+      dense_bytes += 4ull << ih[k].log2;
+    }
+  uint64_t cap = Pow2Ceil(roomy ? worst * 4 / 3 + 64 : 80 * max_len + (256u << 10));
+  const uint64_t cap_worst = Pow2Ceil(worst * 4 / 3 + 64);
+  if (cap > cap_worst) cap = cap_worst;
+  if (cap * 8 >= dense_bytes || cap > (1ull << 31)) {  // long streams: the dense tables are smaller
+    for (int k = 0; k < NIND; ++k) L.ind_sid[k] = 0;
+    for (int k = 0; k < NMATCH; ++k) L.match_sid[k] = 0;
+    for (int k = 0; k < NIH; ++k) L.ih_sid[k] = 0;
+  } else {
+    L.sparse_mask = (uint32_t)(cap - 1);
+    L.sparse_limit = (uint32_t)(cap / 4 * 3);
+    L.sparse = take(cap * 8);
+  }
+  for (int k = 0; k < NIND; ++k)
+    if (!L.ind_sid[k]) L.ind_tab[k] = take(((uint64_t)L.ind_size[k] + 1) / 2 * 4);
   L.ind_pred = take((uint64_t)NIND * 512 * 4);
-  for (int k = 0; k < NMATCH; ++k) L.match_tab[k] = take((4ull << mt[k].log2));
+  for (int k = 0; k < NMATCH; ++k)
+    if (!L.match_sid[k]) L.match_tab[k] = take((4ull << mt[k].log2));
   L.match_pred = take(NMATCH * 256 * 4);
   L.match_cnt = take(NMATCH * 256 * 4);
   L.history_cap = max_len + 8;
   L.history = take(L.history_cap);
-  for (int k = 0; k < NIH; ++k) L.ih_tab[k] = take(4ull << ih[k].log2);
+  for (int k = 0; k < NIH; ++k)
+    if (!L.ih_sid[k]) L.ih_tab[k] = take(4ull << ih[k].log2);
   // Weight-set pool: a mixer can create at most one set per distinct gate context it ever sees:
   // min(table size, bytes + 1) for byte-level contexts, min(table size, bits + 1) otherwise.
   uint64_t sets = 1;
@@ -44,6 +84,10 @@ inline ArenaLayout MakeLayout(uint64_t max_len) {
     const bool bit_level = mx[m].ctx == C_SLPR || mx[m].ctx == C_LBPR || mx[m].ctx == C_BIT_CONTEXT || mx[m].ctx == C_LONGEST;
     const uint64_t seen = bit_level ? 8 * max_len + 1 : max_len + 1;
     sets += t < seen ? t : seen;
+  }
+  if (!roomy) {  // text creates ~0.35 sets per byte
+    const uint64_t typical = 8192 + max_len * 3 / 4;
+    if (typical < sets) sets = typical;
   }
   L.mix_pool_sets = (uint32_t)sets;
   L.mix_set_stride = 116;  // 2 header words + up to 114 weights, 16-byte multiple
@@ -64,7 +108,7 @@ inline ArenaLayout MakeLayout(uint64_t max_len) {
   L.p_state = take(sizeof(PpmdState));
   L.p_text_cap = (uint32_t)(max_len + 64);
   L.p_text = take(AlignUp(L.p_text_cap, 4));
-  uint64_t units = AlignUp(96 * max_len + (256u << 10), 48);  // ~19 B/byte on text
+  uint64_t units = AlignUp((roomy ? 400 : 96) * max_len + (256u << 10), 48);  // ~19 B/byte on text
   const uint64_t units_max = 800ull << 20;                   // must stay below half of the virtual units area
   if (units > units_max) units = units_max / 48 * 48;
   L.p_units_cap = (uint32_t)units;

@@ -30,6 +30,7 @@ enum : uint32_t {
   GMX_ERR_MATCH_RANGE = 4,   // Match pointer outside history (reference would throw, match.cpp:55)
   GMX_ERR_HISTORY_CAP = 5,
   GMX_ERR_BAD_HEADER = 6,
+  GMX_ERR_SPARSE_FULL = 7,   // shared sparse table over its load limit (host retries with a roomier arena)
 };
 
 enum : int { WSTRIDE = 117 };
@@ -53,6 +54,12 @@ enum : int { GMX_PROF_SLOTS = 16 };
 
 // Byte offsets (from the arena base) of every per-stream table. Filled by the host (layout.h).
 struct ArenaLayout {
+  // Big tables (Indirect 2^15/2^16, Match 2^21/2^24, IndirectHash 2^24) can live in ONE shared sparse
+  // open-addressing map instead of dense arrays: sid = table id inside the map (1..63), 0 = dense.
+  uint64_t sparse;            // u64 entries {key:31 = sid<<25 | index, value:32}; 0 = empty
+  uint32_t sparse_mask;       // capacity - 1 (power of two), 0 = no sparse map
+  uint32_t sparse_limit;      // maximum number of entries (load limit)
+  uint8_t ind_sid[NIND], match_sid[NMATCH], ih_sid[NIH];
   uint64_t ind_tab[NIND];     // u16 {ns | rm<<8} per slot, (2^log2*256+1) slots (indirect.cpp:15-19)
   uint32_t ind_size[NIND];
   uint64_t ind_pred;          // float [NIND][2][256]
@@ -83,6 +90,7 @@ struct StreamParams {
   uint8_t* out; const uint64_t* out_off;         // n_streams + 1 offsets (capacity slices)
   uint64_t* out_len; uint32_t* status;           // per stream
   uint32_t n_streams; uint32_t* queue;           // atomic stream counter
+  const uint32_t* ids;                           // optional: queue position -> stream id (retry launches), or null
   uint8_t* arenas; uint64_t arena_stride;
   const ArenaLayout* layout;
   const float* lstm_init;    // [3][L_ROW][L_CELLS] initial gate weights (host glibc rand(), lstm-layer.cpp:176-195)
@@ -91,6 +99,7 @@ struct StreamParams {
   const float* adam;         // [L_UPDATE_LIMIT + 1][4]: alpha, 1-b1^t, 1-b2^t (lstm-layer.cpp:16-33), host libm
   uint64_t* bit_trace;       // optional: {f32 prob, u32 p16} per bit of stream 0 (debug/parity), or null
   float* pred_trace;         // optional: 90 predictions + 3 mask words + 33 mixer outs per bit of stream 0
+  uint32_t* usage;           // optional: per stream {sparse entries, mixer sets, PPMd unit bytes, history bytes}, or null
   unsigned long long* prof;  // optional: GMX_PROF_SLOTS cycle counters per stream (phase breakdown), or null
 };
 
@@ -128,13 +137,17 @@ struct StreamSmem {
   uint32_t steps;                      // Mixer::steps_ (identical for all 33 mixers)
   // mixers
   float w[NMIX * WSTRIDE];
-  uint32_t set_steps[NMIX], max_steps[NMIX], set_idx[NMIX], set_pool[NMIX], new_idx[NMIX];
-  uint8_t swap[NMIX + 3], shrink[NMIX + 3];
+  uint32_t set_steps[NMIX], max_steps[NMIX], set_idx[NMIX], set_pool[NMIX];
+  uint32_t swap_old[NMIX], swap_new[NMIX], nswap;   // queued set swaps of this bit
+  uint8_t swap_m[NMIX + 3], shrink[NMIX + 3];
+  float act_x[NPRED + 2]; uint8_t act_idx[NPRED + 2]; uint32_t act_n;  // compacted active predictions
   float upd[NMIX];
   uint32_t pool_next;
   // indirect
-  uint32_t ind_base[NIND], ind_slot[NIND];
+  uint32_t ind_base[NIND], ind_slot[NIND];   // ind_slot: dense slot, or position in the sparse map
   uint16_t ind_state[NIND + 1];
+  uint8_t ind_found[NIND + 3];               // sparse tables: entry exists at ind_slot
+  uint32_t sparse_used;
   // match
   uint32_t m_cur[NMATCH]; uint8_t m_byte[NMATCH], m_bitpos[NMATCH], m_len[NMATCH];
   uint32_t hist_len;
@@ -156,10 +169,13 @@ struct StreamSmem {
   long long prof_t;
 };
 
+struct SparseMap { unsigned long long* tab; uint32_t mask; };
+
 struct Arena {
   uint8_t* base;
   const ArenaLayout* L;
   template <typename T> GMX_DEV T* at(uint64_t off) const { return (T*)(base + off); }
+  GMX_DEV SparseMap map() const { return SparseMap{(unsigned long long*)(base + L->sparse), L->sparse_mask}; }
 };
 
 // ---- small helpers -----------------------------------------------------------------------------
@@ -178,6 +194,45 @@ GMX_DEV inline uint32_t Murmur64(uint64_t v) {
   return MurmurFinal(h, 8);
 }
 GMX_DEV inline uint32_t Murmur32(uint32_t v) { return MurmurFinal(MurmurMix(0xDEADBEEFu, v), 4); }
+
+// ---- shared sparse map (exact: keyed by table id + full index, linear probing, never deletes) ----
+GMX_DEV inline uint32_t SparseKey(uint32_t sid, uint32_t index) { return (sid << 25) | index; }
+GMX_DEV inline uint32_t SparseHash(uint32_t k) {
+  k ^= k >> 16; k *= 0x85ebca6bu; k ^= k >> 13; k *= 0xc2b2ae35u; k ^= k >> 16; return k;
+}
+// Returns the position of `key`, or of the first empty slot of its probe sequence; *entry = slot content
+// (0 when absent).
+GMX_DEV inline uint32_t SparseFind(const SparseMap& M, uint32_t key, unsigned long long* entry) {
+  uint32_t pos = SparseHash(key) & M.mask;
+  for (;;) {
+    const unsigned long long e = M.tab[pos];
+    if (e == 0ull || (uint32_t)(e >> 32) == key) { *entry = e; return pos; }
+    pos = (pos + 1) & M.mask;
+  }
+}
+// Store `value` for `key`. pos/found come from a SparseFind of the same key; other threads may have
+// inserted OTHER keys since (never this one: every table is owned by one thread per phase).
+GMX_DEV inline void SparsePut(const SparseMap& M, uint32_t* used, uint32_t limit, uint32_t* error, uint32_t key,
+                              uint32_t pos, bool found, uint32_t value) {
+  const unsigned long long e = ((unsigned long long)key << 32) | value;
+  if (found) { M.tab[pos] = e; return; }
+  if (atomicAdd(used, 1u) >= limit) { *error = GMX_ERR_SPARSE_FULL; return; }
+  for (;;) {
+    const unsigned long long old = atomicCAS(&M.tab[pos], 0ull, e);
+    if (old == 0ull) return;
+    pos = (pos + 1) & M.mask;
+  }
+}
+GMX_DEV inline uint32_t SparseGet(const SparseMap& M, uint32_t key) {  // value, 0 when absent
+  unsigned long long e;
+  SparseFind(M, key, &e);
+  return (uint32_t)e;
+}
+GMX_DEV inline void SparseSet(const SparseMap& M, uint32_t* used, uint32_t limit, uint32_t* error, uint32_t key, uint32_t value) {
+  unsigned long long e;
+  const uint32_t pos = SparseFind(M, key, &e);
+  SparsePut(M, used, limit, error, key, pos, e != 0ull, value);
+}
 
 GMX_DEV inline uint32_t RecentByte(const StreamSmem& s, int ago) {  // short-term-memory.cpp:215-219
   int pos = (int)s.ring_pos - ago;
@@ -198,14 +253,22 @@ template <int NT>
 GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, int tid) {
   const ArenaLayout& L = *A.L;
   if (tid == 0) s.prof_t = GMX_CLOCK();
-  for (int k = 0; k < NIND; ++k) FillWords<NT>(A.at<uint32_t>(L.ind_tab[k]), ((uint64_t)L.ind_size[k] + 1) / 2, 0x00FF00FFu, tid);
+  for (int k = 0; k < NIND; ++k)
+    if (!L.ind_sid[k]) FillWords<NT>(A.at<uint32_t>(L.ind_tab[k]), ((uint64_t)L.ind_size[k] + 1) / 2, 0x00FF00FFu, tid);
+  if (L.sparse_mask) {
+    uint4* z = A.at<uint4>(L.sparse);
+    const uint64_t n16 = ((uint64_t)L.sparse_mask + 1) / 2;
+    for (uint64_t i = tid; i < n16; i += NT) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
   FillWords<NT>(A.at<uint32_t>(L.ind_pred), NIND * 512, 0u, tid);
-  for (int k = 0; k < NMATCH; ++k) FillWords<NT>(A.at<uint32_t>(L.match_tab[k]), 1ull << kMatch[k].log2, 0u, tid);
+  for (int k = 0; k < NMATCH; ++k)
+    if (!L.match_sid[k]) FillWords<NT>(A.at<uint32_t>(L.match_tab[k]), 1ull << kMatch[k].log2, 0u, tid);
   for (int i = tid; i < NMATCH * 256; i += NT) {
     A.at<float>(L.match_pred)[i] = (float)(0.5 + ((double)(i & 255) + 0.5) / 512);  // match.cpp:19-21
     A.at<int>(L.match_cnt)[i] = 1;
   }
-  for (int k = 0; k < NIH; ++k) FillWords<NT>(A.at<uint32_t>(L.ih_tab[k]), 1ull << kIH[k].log2, 0u, tid);
+  for (int k = 0; k < NIH; ++k)
+    if (!L.ih_sid[k]) FillWords<NT>(A.at<uint32_t>(L.ih_tab[k]), 1ull << kIH[k].log2, 0u, tid);
   for (int m = 0; m < NMIX; ++m) FillWords<NT>(A.at<uint32_t>(L.mix_dir[m]), 1ull << kMixer[m].log2, 0u, tid);
   // LSTM (lstm.cpp:8-43, lstm-layer.cpp:36-54,156-196)
   for (int i = tid; i < 3 * L_ROW * L_CELLS; i += NT) {
@@ -229,7 +292,7 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
   for (int i = tid; i < 1000; i += NT) s.ring[i] = 0;
   for (int i = tid; i < NMIX * WSTRIDE; i += NT) s.w[i] = 0.0f;
   for (int i = tid; i < NMIX; i += NT) {
-    s.set_steps[i] = 0; s.max_steps[i] = 1; s.set_idx[i] = 0xFFFFFFFFu; s.set_pool[i] = 0; s.swap[i] = 0; s.shrink[i] = 0;
+    s.set_steps[i] = 0; s.max_steps[i] = 1; s.set_idx[i] = 0xFFFFFFFFu; s.set_pool[i] = 0; s.shrink[i] = 0;
   }
   for (int i = tid; i < NMATCH; i += NT) { s.m_cur[i] = 0; s.m_byte[i] = 0; s.m_bitpos[i] = 128; s.m_len[i] = 0; }
   for (int i = tid; i < NIH; i += NT) { s.ih_outer[i] = 0; s.ih_hash[i] = 0; }
@@ -238,7 +301,7 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
   for (int i = tid; i < L_HORIZON; i += NT) { s.l_hist[i] = 0; s.l_symin[i] = 0; }
   if (tid == 0) {
     s.final_out = 0; s.prob = 0.5f; s.ring_pos = 0; s.new_bit = 0; s.recent_bits = 1; s.bb = 0;
-    s.first_prediction = 1; s.error = 0; s.steps = 0; s.pool_next = 1; s.hist_len = 0;
+    s.first_prediction = 1; s.error = 0; s.steps = 0; s.pool_next = 1; s.hist_len = 0; s.sparse_used = 0; s.nswap = 0; s.act_n = 0;
     s.l_epoch = 0; s.l_update_steps = 0; s.l_old_input = 0; s.l_in[L_NIN] = 0;
     s.x1 = 0; s.x2 = 0xffffffffu; s.x = 0;
     for (int i = 0; i < GMX_PROF_SLOTS; ++i) s.prof[i] = 0;
@@ -561,16 +624,27 @@ GMX_DEV void ByteBoundary(StreamSmem& s, const Arena& A, const StreamParams& P, 
   } else if (tid >= 64 && tid < 64 + NIH) {  // IndirectHash::Predict indirect-hash.cpp:16-31
     const int k = tid - 64;
     const IHSpec sp = kIH[k];
-    uint32_t* tab = A.at<uint32_t>(L.ih_tab[k]);
     const uint32_t mask = (1u << sp.log2) - 1;
     const uint64_t inner_mod = 1ull << (8 * (sp.inner_order - 1)), outer_mod = 1ull << (8 * (sp.outer_order - 1));
-    uint32_t* slot = tab + (s.ih_hash[k] & mask);
-    *slot = (uint32_t)((((uint64_t)*slot % inner_mod) << 8) + last_byte);
     const uint64_t oc = ((s.ih_outer[k] % outer_mod) << 8) + last_byte;
     s.ih_outer[k] = oc;
     const uint32_t oh = Murmur64(oc);
+    const uint32_t sid = L.ih_sid[k];
+    if (sid) {
+      const SparseMap M = A.map();
+      const uint32_t key = SparseKey(sid, s.ih_hash[k] & mask);
+      unsigned long long e;
+      const uint32_t pos = SparseFind(M, key, &e);
+      SparsePut(M, &s.sparse_used, L.sparse_limit, &s.error, key, pos, e != 0ull,
+                (uint32_t)((((uint64_t)(uint32_t)e % inner_mod) << 8) + last_byte));
+      s.ctx[C_IH0 + k] = Murmur32(SparseGet(M, SparseKey(sid, oh & mask)));
+    } else {
+      uint32_t* tab = A.at<uint32_t>(L.ih_tab[k]);
+      uint32_t* slot = tab + (s.ih_hash[k] & mask);
+      *slot = (uint32_t)((((uint64_t)*slot % inner_mod) << 8) + last_byte);
+      s.ctx[C_IH0 + k] = Murmur32(tab[oh & mask]);
+    }
     s.ih_hash[k] = oh;
-    s.ctx[C_IH0 + k] = Murmur32(tab[oh & mask]);
   } else if (tid == NT - 1) {  // ModPPMD::Predict byte part, mod_ppmd.cpp:1651-1654
     Ppmd pm{A.at<PpmdState>(L.p_state), A.at<uint8_t>(L.p_text), A.at<uint8_t>(L.p_units), L.p_text_cap, L.p_units_cap, s.sqp};
     pm.UpdateByte(last_byte);
@@ -598,6 +672,7 @@ GMX_DEV void ByteBoundary(StreamSmem& s, const Arena& A, const StreamParams& P, 
     // prefetch: 41 tables x 5 lines of 128 B cover the 510-byte row
     for (int t = tid - 1; t < NIND * 5; t += NT - 1) {
       const int k = t / 5, ln = t - k * 5;
+      if (L.ind_sid[k]) continue;
       const uint32_t M = L.ind_size[k];
       uint32_t slot = s.ind_base[k] + ln * 64;
       if (slot >= M) slot -= M;
@@ -684,7 +759,16 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     const uint32_t M = L.ind_size[k];
     uint32_t slot = s.ind_base[k] + bitctx;
     if (slot >= M) slot -= M;
-    const uint32_t e = A.at<uint16_t>(L.ind_tab[k])[slot];
+    uint32_t e;
+    const uint32_t sid = L.ind_sid[k];
+    if (sid) {  // absent == never written == {ns 255, rm 0}
+      unsigned long long ent;
+      slot = SparseFind(A.map(), SparseKey(sid, slot), &ent);
+      e = ent ? (uint32_t)ent & 0xffffu : 0x00ffu;
+      s.ind_found[k] = ent != 0ull;
+    } else {
+      e = A.at<uint16_t>(L.ind_tab[k])[slot];
+    }
     s.ind_slot[k] = slot;
     s.ind_state[k] = (uint16_t)e;
     const uint32_t ns = e & 0xff, rm = e >> 8;
@@ -706,8 +790,10 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     if (s.bb) {
       uint32_t cm = s.m_cur[k];
       if (s.hist_len != 0 && cm == s.hist_len - 1) len = 0;
-      if (len < 8) cm = A.at<uint32_t>(L.match_tab[k])[s.ctx[kMatch[k].ctx] & ((1u << kMatch[k].log2) - 1)];
-      else ++cm;
+      if (len < 8) {
+        const uint32_t idx = s.ctx[kMatch[k].ctx] & ((1u << kMatch[k].log2) - 1);
+        cm = L.match_sid[k] ? SparseGet(A.map(), SparseKey(L.match_sid[k], idx)) : A.at<uint32_t>(L.match_tab[k])[idx];
+      } else ++cm;
       if (s.hist_len != 0) {
         if (cm >= s.hist_len) { s.error = GMX_ERR_MATCH_RANGE; cm = 0; }
         cbyte = A.at<uint8_t>(L.history)[cm];
@@ -746,42 +832,60 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
       c = s.ctx[kMixer[m].ctx];
     }
     const uint32_t idx = c & ((1u << kMixer[m].log2) - 1);
-    s.new_idx[m] = idx;
-    s.swap[m] = idx != s.set_idx[m];
-  }
-  if (tid == 40) {
+    if (idx != s.set_idx[m]) {  // queue the swap: old set goes back to the pool, new one (if any) is staged
+      const uint32_t q = atomicAdd(&s.nswap, 1u);
+      s.swap_m[q] = (uint8_t)m;
+      s.swap_old[q] = s.set_pool[m];
+      s.swap_new[q] = A.at<uint32_t>(L.mix_dir[m])[idx];
+      s.set_idx[m] = idx;
+    }
+  } else if (tid == 40) {
     uint32_t c = 0;
     for (int k = 0; k < NMATCH; ++k) { const uint32_t v = s.m_len[k] >> 5; c = v > c ? v : c; }
     s.ctx[C_LONGEST] = c;
+  } else if (tid >= 64 && tid < 96) {
+    // ascending list of the active predictions: Mixer::Predict sums exactly these, in index order
+    const int lane = tid - 64;
+    uint32_t base = 0;
+    for (int r = 0; r < 3; ++r) {
+      const int i = r * 32 + lane;
+      const bool on = i < NPRED && s.act[i] != 0;
+      const uint32_t mask = __ballot_sync(0xffffffffu, on);
+      if (on) {
+        const uint32_t pos = base + __popc(mask & ((1u << lane) - 1u));
+        s.act_idx[pos] = (uint8_t)i;
+        s.act_x[pos] = s.preds[i];
+      }
+      base += __popc(mask);
+    }
+    if (lane == 0) s.act_n = base;
   }
   BlockSync();
-  // Swap staged weight sets: write the old one back, fetch the new one (zero weights == no set yet:
-  // the dot product of zeros is +0, exactly the reference's "data == nullptr" output).
-  for (int m = tid >> 5; m < NMIX; m += NT / 32) {
-    if (!s.swap[m]) continue;
-    const int lane = tid & 31;
-    const int nw = MixerNW(m);
+  // Swap staged weight sets, one queued mixer per round, one weight per thread: first all write-backs,
+  // then all fetches (zero weights == no set yet: the dot product of zeros is +0, exactly the
+  // reference's "data == nullptr" output).
+  {
+    const uint32_t nswap = s.nswap;
     float* pool = A.at<float>(L.mix_pool);
     const uint32_t stride = L.mix_set_stride;
-    const uint32_t old = s.set_pool[m];
-    const uint32_t nidx = s.new_idx[m];
-    const uint32_t nid = A.at<uint32_t>(L.mix_dir[m])[nidx];
-    const uint32_t old_steps = s.set_steps[m];
-    __syncwarp();  // every lane has read the staging state before lane 0 rewrites it
-    if (old) {
-      float* rec = pool + (size_t)old * stride;
-      for (int i = lane; i < nw; i += 32) rec[2 + i] = s.w[m * WSTRIDE + i];
-      if (lane == 0) ((uint32_t*)rec)[0] = old_steps;
+    for (uint32_t r = 0; r < nswap; ++r) {
+      const int m = s.swap_m[r];
+      const uint32_t old = s.swap_old[r];
+      if (old && tid < MixerNW(m) + 1) {
+        float* rec = pool + (size_t)old * stride;
+        if (tid == 0) ((uint32_t*)rec)[0] = s.set_steps[m]; else rec[1 + tid] = s.w[m * WSTRIDE + tid - 1];
+      }
     }
-    if (nid) {
-      const float* rec = pool + (size_t)nid * stride;
-      for (int i = lane; i < nw; i += 32) s.w[m * WSTRIDE + i] = rec[2 + i];
-      if (lane == 0) s.set_steps[m] = ((const uint32_t*)rec)[0];
-    } else {
-      for (int i = lane; i < nw; i += 32) s.w[m * WSTRIDE + i] = 0.0f;
-      if (lane == 0) s.set_steps[m] = 0;
+#pragma unroll 4
+    for (uint32_t r = 0; r < nswap; ++r) {
+      const int m = s.swap_m[r];
+      const uint32_t nid = s.swap_new[r];
+      if (tid < MixerNW(m) + 1) {
+        const float* rec = pool + (size_t)nid * stride;
+        if (tid == 0) { s.set_steps[m] = nid ? ((const uint32_t*)rec)[0] : 0u; s.set_pool[m] = nid; }
+        else s.w[m * WSTRIDE + tid - 1] = nid ? rec[1 + tid] : 0.0f;
+      }
     }
-    if (lane == 0) { s.set_pool[m] = nid; s.set_idx[m] = nidx; }
   }
   BlockSync();
   GMX_PROF(5);
@@ -789,10 +893,12 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
   // same-layer chain is resolved by warp shuffles in neuron order.
   if (tid < 32) {
     const int lane = tid;
+    if (lane == 0) s.nswap = 0;
     const float* w = s.w + (lane < NL0 ? lane : 0) * WSTRIDE;
     float acc = 0.0f;
-    for (int i = 0; i < NPRED; ++i)
-      if (s.act[i]) acc = f_add(acc, f_mul(s.preds[i], w[i]));
+    const int na = (int)s.act_n;
+#pragma unroll 8
+    for (int c = 0; c < na; ++c) acc = f_add(acc, f_mul(s.act_x[c], w[s.act_idx[c]]));
     for (int j = 0; j < NL0 - 1; ++j) {
       const float oj = __shfl_sync(0xffffffffu, acc, j);
       if (lane > j && lane < NL0) acc = f_add(acc, f_mul(oj, w[NPRED + j]));
@@ -802,6 +908,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     const float skip = s.preds[P_LSTM];
     const float* w1 = s.w + (NL0 + (lane < NL1 ? lane : 0)) * WSTRIDE;
     acc = 0.0f;
+#pragma unroll
     for (int i = 0; i < NL0; ++i) acc = f_add(acc, f_mul(s.l0_out[i], w1[i]));
     // a layer-1 output is complete (skip connection added last, weights[num_layer0 + output_index],
     // mixer.cpp:77-83) before the next layer-1 neuron reads it
@@ -817,7 +924,9 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     if (lane == 0) {
       const float* w2 = s.w + (NL0 + NL1) * WSTRIDE;
       float p = 0.0f;
+#pragma unroll
       for (int i = 0; i < NL0; ++i) p = f_add(p, f_mul(s.l0_out[i], w2[i]));
+#pragma unroll
       for (int i = 0; i < NL1; ++i) p = f_add(p, f_mul(s.l1_out[i], w2[NL0 + i]));
       p = f_add(p, f_mul(skip, w2[NL0 + NL1]));
       s.final_out = p;
@@ -878,7 +987,15 @@ GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int 
     uint32_t nrm;
     if (bit == 0) nrm = rm < 127 ? rm + 1 : rm >= 128 ? 1 : rm;
     else nrm = rm < 128 ? 128 : rm < 255 ? rm + 1 : rm;
-    A.at<uint16_t>(L.ind_tab[k])[s.ind_slot[k]] = (uint16_t)(kNonstationary[ns * 2 + bit] | (nrm << 8));
+    const uint32_t nst = kNonstationary[ns * 2 + bit] | (nrm << 8);
+    const uint32_t sid = L.ind_sid[k];
+    if (sid) {
+      uint32_t slot = s.ind_base[k] + s.ctx[C_BIT_CONTEXT];
+      if (slot >= L.ind_size[k]) slot -= L.ind_size[k];
+      SparsePut(A.map(), &s.sparse_used, L.sparse_limit, &s.error, SparseKey(sid, slot), s.ind_slot[k], s.ind_found[k] != 0, nst);
+    } else {
+      A.at<uint16_t>(L.ind_tab[k])[s.ind_slot[k]] = (uint16_t)nst;
+    }
   } else if (tid >= 40 && tid < 40 + NMATCH) {  // Match::Learn match.cpp:76-109
     const int k = tid - 40;
     const uint32_t len = s.m_len[k];
@@ -892,8 +1009,11 @@ GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int 
       const float v = *mp;
       *mp = f_add(v, f_mul(f_sub((float)hit, v), rate));
     }
-    if (s.recent_bits >= 128 && longest < 2)
-      A.at<uint32_t>(L.match_tab[k])[s.ctx[kMatch[k].ctx] & ((1u << kMatch[k].log2) - 1)] = hist_after - 1;
+    if (s.recent_bits >= 128 && longest < 2) {
+      const uint32_t idx = s.ctx[kMatch[k].ctx] & ((1u << kMatch[k].log2) - 1);
+      if (L.match_sid[k]) SparseSet(A.map(), &s.sparse_used, L.sparse_limit, &s.error, SparseKey(L.match_sid[k], idx), hist_after - 1);
+      else A.at<uint32_t>(L.match_tab[k])[idx] = hist_after - 1;
+    }
   } else if (tid == 48 && byte_done && longest < 2) {
     if (s.hist_len >= L.history_cap) s.error = GMX_ERR_HISTORY_CAP;
     else A.at<uint8_t>(L.history)[s.hist_len] = (uint8_t)cur;
@@ -902,27 +1022,28 @@ GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int 
   GMX_PROF(8);
   // Mixer weight updates (mixer.cpp:128-175): w -= update * x over exactly the inputs used by
   // Predict, then the (1 - 3e-6) shrink every 1024 steps of the set.
-  for (int f = tid; f < NMIX * WSTRIDE; f += NT) {
-    const int m = f / WSTRIDE, i = f - m * WSTRIDE;
-    float x; bool use;
-    if (m < NL0) {
-      if (i < NPRED) { use = s.act[i] != 0; x = s.preds[i]; }
-      else { use = i < NPRED + m; x = s.l0_out[i < NPRED + NL0 ? i - NPRED : 0]; }
-    } else if (m < NL0 + NL1) {
-      const int o = m - NL0;
-      if (i < NL0) { use = true; x = s.l0_out[i]; }
-      else if (i < NL0 + o) { use = true; x = s.l1_out[i - NL0]; }
-      else { use = i == NL0 + o; x = s.preds[P_LSTM]; }
-    } else {
-      if (i < NL0) { use = true; x = s.l0_out[i]; }
-      else if (i < NL0 + NL1) { use = true; x = s.l1_out[i - NL0]; }
-      else { use = i == NL0 + NL1; x = s.preds[P_LSTM]; }
+  for (int m = tid >> 5; m < NMIX; m += NT / 32) {
+    const int lane = tid & 31;
+    const int nw = MixerNW(m);
+    const float upd = s.upd[m];
+    const bool shrink = s.shrink[m] != 0;
+    float* w = s.w + m * WSTRIDE;
+    for (int i = lane; i < nw; i += 32) {
+      float x; bool use;
+      if (m < NL0) {
+        if (i < NPRED) { use = s.act[i] != 0; x = s.preds[i]; }
+        else { use = true; x = s.l0_out[i - NPRED]; }
+      } else {
+        const int nin = m < NL0 + NL1 ? NL0 + (m - NL0) : NL0 + NL1;  // inputs before the skip connection
+        if (i < NL0) { use = true; x = s.l0_out[i]; }
+        else if (i < nin) { use = true; x = s.l1_out[i - NL0]; }
+        else { use = true; x = s.preds[P_LSTM]; }
+      }
+      float v = w[i];
+      if (use) v = f_sub(v, f_mul(upd, x));
+      if (shrink) v = f_mul(v, f_sub(1.0f, 3.0e-6f));
+      w[i] = v;
     }
-    if (i >= MixerNW(m)) continue;
-    float w = s.w[f];
-    if (use) w = f_sub(w, f_mul(s.upd[m], x));
-    if (s.shrink[m]) w = f_mul(w, f_sub(1.0f, 3.0e-6f));
-    s.w[f] = w;
   }
   if (tid == 0) { s.steps++; s.hist_len = hist_after; }
   BlockSync();
@@ -958,6 +1079,14 @@ GMX_DEV inline void Trace(StreamSmem& s, const StreamParams& P, uint64_t bit_ind
     for (int i = 0; i < NL1; ++i) t[117 + i] = s.l1_out[i];
     t[125] = s.final_out;
   }
+}
+
+GMX_DEV inline void WriteUsage(const StreamSmem& s, const Arena& A, const StreamParams& P, uint32_t sid) {
+  if (!P.usage) return;
+  const PpmdState* ps = A.at<PpmdState>(A.L->p_state);
+  uint32_t* u = P.usage + 4 * (size_t)sid;
+  u[0] = s.sparse_used; u[1] = s.pool_next;
+  u[2] = (ps->lo_unit - PPMD_UNITS_START) + (PPMD_HEAP_END - ps->hi_unit); u[3] = s.hist_len;
 }
 
 // runner_utils::Compress (runner-utils.cpp:43-67) incl. the 5-byte header of RunCompression (:109).
@@ -1001,6 +1130,7 @@ GMX_DEV void CompressStream(StreamSmem& s, const Arena& A, const StreamParams& P
     PutByte(s, out, s.x2 >> 24);
     P.out_len[sid] = s.out_pos;
     P.status[sid] = s.error;
+    WriteUsage(s, A, P, sid);
     if (P.prof) for (int i = 0; i < GMX_PROF_SLOTS; ++i) P.prof[(size_t)sid * GMX_PROF_SLOTS + i] = s.prof[i];
   }
   BlockSync();
@@ -1047,6 +1177,7 @@ GMX_DEV void DecompressStream(StreamSmem& s, const Arena& A, const StreamParams&
   BlockSync();
   if (tid == 0) {
     P.out_len[sid] = s.error ? 0 : n; P.status[sid] = s.error;
+    WriteUsage(s, A, P, sid);
     if (P.prof) for (int i = 0; i < GMX_PROF_SLOTS; ++i) P.prof[(size_t)sid * GMX_PROF_SLOTS + i] = s.prof[i];
   }
   BlockSync();
@@ -1055,8 +1186,8 @@ GMX_DEV void DecompressStream(StreamSmem& s, const Arena& A, const StreamParams&
 // ---- kernel entry: persistent CTAs, one stream at a time, ids from an atomic queue ---------------
 enum : int { MODE_COMPRESS = 0, MODE_DECOMPRESS = 1 };
 
-template <int NT, int MODE>
-__global__ void __launch_bounds__(NT) StreamKernel(StreamParams P) {
+template <int NT, int MODE, int MINB>
+__global__ void __launch_bounds__(NT, MINB) StreamKernel(StreamParams P) {
   __shared__ StreamSmem s;
   __shared__ uint32_t next_stream;
   const int tid = (int)threadIdx.x;
@@ -1064,9 +1195,10 @@ __global__ void __launch_bounds__(NT) StreamKernel(StreamParams P) {
   for (;;) {
     if (tid == 0) next_stream = atomicAdd(P.queue, 1u);
     BlockSync();
-    const uint32_t sid = next_stream;
+    const uint32_t q = next_stream;
     BlockSync();
-    if (sid >= P.n_streams) break;
+    if (q >= P.n_streams) break;
+    const uint32_t sid = P.ids ? P.ids[q] : q;
     if (MODE == MODE_COMPRESS) CompressStream<NT>(s, A, P, sid, tid);
     else DecompressStream<NT>(s, A, P, sid, tid);
   }

@@ -43,7 +43,7 @@ enum {
 /* Per-stream status codes written to status[] (0 = ok). */
 enum {
   GMX_S_OK = 0, GMX_S_PPMD_ARENA = 1, GMX_S_MIXER_POOL = 2, GMX_S_OUTPUT_CAP = 3,
-  GMX_S_MATCH_RANGE = 4, GMX_S_HISTORY_CAP = 5, GMX_S_BAD_HEADER = 6
+  GMX_S_MATCH_RANGE = 4, GMX_S_HISTORY_CAP = 5, GMX_S_BAD_HEADER = 6, GMX_S_SPARSE_FULL = 7
 };
 
 const char* gmx_version(void);
@@ -60,7 +60,10 @@ int gmx_set_cuda_stream(gmx_ctx* ctx, void* cuda_stream);
 
 /* Size the per-CTA stream arenas: max_stream_len = longest uncompressed stream in bytes,
  * max_resident = upper bound on concurrently resident streams (0 = as many as fit, at most one
- * wave of co-resident CTAs). Called implicitly by the batch calls when needed. */
+ * wave of co-resident CTAs). Called implicitly by the batch calls when needed.
+ * Arenas are sized for what text-like data touches; a stream that needs more (incompressible data)
+ * is transparently re-run from scratch in a worst-case-sized arena by the same batch call, so
+ * statuses 1, 2 and 7 only surface when even that does not fit the GPU. */
 int gmx_configure(gmx_ctx* ctx, uint64_t max_stream_len, uint32_t max_resident);
 
 /* Worst-case compressed size of an n-byte stream (header + coder bytes). */
@@ -98,6 +101,7 @@ int gmx_compress_trace(gmx_ctx* ctx, const uint8_t* in, uint64_t n, uint8_t* out
 /* Introspection for benchmarks. */
 uint32_t gmx_resident_streams(const gmx_ctx* ctx);   /* CTAs (= arenas) the last launch used */
 uint64_t gmx_arena_bytes(const gmx_ctx* ctx);        /* bytes of one stream arena */
+uint64_t gmx_retried_streams(const gmx_ctx* ctx);    /* streams re-run in a worst-case arena so far (see gmx_configure) */
 uint64_t gmx_kernel_launches(const gmx_ctx* ctx);    /* kernels launched by this ctx so far */
 double gmx_last_kernel_ms(const gmx_ctx* ctx);       /* device time of the last stream kernel (CUDA events) */
 int gmx_device_sm_count(const gmx_ctx* ctx);
@@ -107,6 +111,10 @@ int gmx_device_sm_count(const gmx_ctx* ctx);
  * last launch and returns the number of streams copied. */
 int gmx_set_profile(gmx_ctx* ctx, int on);
 int gmx_get_profile(gmx_ctx* ctx, uint64_t* out, uint32_t max_streams);
+
+/* Arena usage of the streams of the last batch call: 4 words per stream {entries in the shared sparse
+ * table, mixer weight sets, PPMd unit bytes, Match history bytes}; returns the number of streams copied. */
+int gmx_get_usage(gmx_ctx* ctx, uint32_t* out, uint32_t max_streams);
 
 /* Exhaustive check of the device expf/logf/tanhf against the host libm: inputs are the bit
  * patterns 0, stride, 2*stride, ... < 2^32 (logf: positive normals only). mismatches[3] and
