@@ -206,8 +206,9 @@ class Context:
         return buf[:n]
 
     def get_usage(self, max_streams):
-        """[n, 4] uint32: sparse-table entries, mixer weight sets, PPMd unit bytes, history bytes per stream."""
-        buf = np.zeros((max_streams, 4), dtype=np.uint32)
+        """[n, 8] uint32: sparse-table entries, mixer weight sets, PPMd unit bytes, history bytes, SM id,
+        start us, end us, 0 per stream."""
+        buf = np.zeros((max_streams, 8), dtype=np.uint32)
         n = self.lib.gmx_get_usage(self.h, buf.ctypes.data, max_streams)
         if n < 0:
             self._check(n, "gmx_get_usage")

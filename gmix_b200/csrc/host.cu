@@ -170,7 +170,7 @@ int RunDevice(gmx_ctx* c, int mode, const uint8_t* d_in, const uint64_t* d_in_of
   P.bit_trace = d_bit_trace; P.pred_trace = d_pred_trace;
   const uint32_t grid = n < c->n_arenas ? n : c->n_arenas;
   {
-    int rc = Reserve(c, c->b_usage, (size_t)n * 16);
+    int rc = Reserve(c, c->b_usage, (size_t)n * 32);
     if (rc) return rc;
     P.usage = (uint32_t*)c->b_usage.p;
     c->usage_streams = n;
@@ -441,7 +441,7 @@ int gmx_get_usage(gmx_ctx* c, uint32_t* out, uint32_t max_streams) {
   if (!c || !out) return GMX_E_ARG;
   const uint32_t n = c->usage_streams < max_streams ? c->usage_streams : max_streams;
   if (n == 0 || !c->b_usage.p) return 0;
-  GMX_CUDA(c, cudaMemcpy(out, c->b_usage.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
+  GMX_CUDA(c, cudaMemcpy(out, c->b_usage.p, (size_t)n * 32, cudaMemcpyDeviceToHost));
   return (int)n;
 }
 

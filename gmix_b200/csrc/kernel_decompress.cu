@@ -1,6 +1,10 @@
 #include "kernels.h"
 namespace gmx {
 cudaError_t LaunchDecompress(const StreamParams& P, unsigned grid, cudaStream_t st) {
+  // all of the SM's unified L1/shared memory as shared memory, so that kStreamMinBlocks CTAs are co-resident
+  static const cudaError_t carve = cudaFuncSetAttribute(StreamKernel<kStreamThreads, MODE_DECOMPRESS, kStreamMinBlocks>,
+                                                        cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (carve != cudaSuccess) return carve;
   StreamKernel<kStreamThreads, MODE_DECOMPRESS, kStreamMinBlocks><<<grid, kStreamThreads, 0, st>>>(P);
   return cudaGetLastError();
 }

@@ -1,4 +1,5 @@
-// Order-20 PPMd byte model for one stream, run by ONE thread of the stream's CTA.
+// Order-20 PPMd byte model for one stream, run by ONE WARP of the stream's CTA: scalar control on
+// lane 0, the scans over a context's symbol statistics one state per lane.
 //
 // Behaviour follows the reference's ModPPMD (src/models/mod_ppmd.cpp; line cites below refer to
 // that file): same 12-byte units, same free lists, same SEE / binary-context estimators, same
@@ -40,7 +41,6 @@ struct PpmdState {
   uint32_t text_ptr, units_start, lo_unit, hi_unit;
   int32_t order_fall, bsumm, run_length, init_rl, num_masked, prev_success;
   uint32_t found_state, max_context, esc_count;
-  uint32_t cum;  // running ConvertSQ coefficient while PrepareByte walks the suffix chain
   uint32_t error;
   uint32_t char_mask[256];
   uint16_t bin_summ[25][64];
@@ -55,6 +55,7 @@ struct Ppmd {
   uint8_t* units;
   uint32_t text_cap, units_cap;
   uint32_t* sqp;  // out: 256 symbol pseudo-probabilities (:1187)
+  int lane;       // lane of the calling thread in the PPMd warp (UpdateByte / PrepareByte are warp-collective)
 
   // ---- virtual heap -> backed memory -------------------------------------------------------
   GMX_DEV uint8_t* At(uint32_t v) const {
@@ -218,7 +219,7 @@ struct Ppmd {
       S->see2[i][k].count = 7;
     }
     S->dummy_see2.summ = 0; S->dummy_see2.shift = 0; S->dummy_see2.count = 0;
-    S->found_state = 0; S->bsumm = 0; S->num_masked = 0; S->cum = 0;
+    S->found_state = 0; S->bsumm = 0; S->num_masked = 0;
   }
 
   GMX_DEV void See2Update(PpmdSee2* s) const {  // :478-493
@@ -492,11 +493,11 @@ struct Ppmd {
     const int i = S->ns2bs[NumStats(Suffix(q))] + S->prev_success + (int)Flags(q) + ((S->run_length >> 26) & 0x20);
     return &S->bin_summ[S->qtable[Freq(rs) - 1]][i];
   }
-  GMX_DEV PpmdSee2* See2For(uint32_t q, int cnum, int* see_freq) const {  // :1116-1124 / :1270-1278
+  GMX_DEV PpmdSee2* See2For(uint32_t q, int cnum, int num_masked, int* see_freq) const {  // :1116-1124 / :1270-1278
     if (cnum != 0xFF) {
       PpmdSee2* s = S->see2[S->qtable[cnum + 3] - 4];
       s += ((int)SummFreq(q) > 10 * (cnum + 1));
-      s += 2 * (2 * cnum < (int)NumStats(Suffix(q)) + S->num_masked) + (int)Flags(q);
+      s += 2 * (2 * cnum < (int)NumStats(Suffix(q)) + num_masked) + (int)Flags(q);
       *see_freq = (s->summ >> s->shift) + 1;
       return s;
     }
@@ -504,142 +505,174 @@ struct Ppmd {
     return &S->dummy_see2;
   }
 
+  // ---- warp-collective entry points --------------------------------------------------------
+  // UpdateByte / PrepareByte are called by ALL 32 lanes of one warp with identical arguments. Control
+  // flow is uniform (every lane reads the same scalars), the per-symbol scans over a context's
+  // statistics run one state per lane, and everything that writes scalar state runs on lane 0
+  // between two __syncwarp()s (GMX_L0). Only order-independent reductions cross lanes (integer
+  // sums, first-hit ballots), so the result is identical to the serial code of the reference.
+#define GMX_L0(...) do { __syncwarp(); if (lane == 0) { __VA_ARGS__; } __syncwarp(); } while (0)
+
+  GMX_DEV int WarpSum(int v) const {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
+  // index of the first of the n states at p whose symbol is sym, or -1
+  GMX_DEV int FindSym(uint32_t p, int n, uint32_t sym) const {
+    for (int base = 0; base < n; base += 32) {
+      const int k = base + lane;
+      const bool hit = k < n && Sym(p + 6 * k) == sym;
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m) return base + __ffs((int)m) - 1;
+    }
+    return -1;
+  }
+
   // ppmd_UpdateByte :1351-1382 — code byte `c`, update the model.
   GMX_DEV void UpdateByte(uint32_t c) const {
     uint32_t minc = S->max_context;
     if (NumStats(minc)) {  // processSymbol1<0> :1049-1098
-      uint32_t p = Stats(minc);
+      const uint32_t p0 = Stats(minc);
       const int cnum = (int)NumStats(minc);
-      S->prev_success = 0;
-      if (Sym(p) == c) {
-        SetFreq(p, Freq(p) + 4); SetSummFreq(minc, SummFreq(minc) + 4);
+      const int i = FindSym(p0, cnum + 1, c);
+      if (i >= 0) {
+        GMX_L0(
+          S->prev_success = 0;
+          uint32_t p = p0 + 6 * i;
+          SetFreq(p, Freq(p) + 4); SetSummFreq(minc, SummFreq(minc) + 4);
+          if (i > 0 && Freq(p) > Freq(p - 6)) { SwapState(p, p - 6); p -= 6; }
+          S->found_state = p;
+          if (Freq(p) > PPMD_MAX_FREQ) S->found_state = Rescale(minc, S->order_fall, p));
       } else {
-        int i; bool hit = false;
-        for (i = 1; i <= cnum; i++) if (Sym(p + 6 * i) == c) { hit = true; break; }
-        if (hit) {
-          const uint32_t pi = p + 6 * i;
-          SetFreq(pi, Freq(pi) + 4); SetSummFreq(minc, SummFreq(minc) + 4);
-          if (Freq(pi) > Freq(pi - 6)) { SwapState(pi, pi - 6); p = pi - 6; } else p = pi;
-        } else {
-          S->num_masked = cnum;
-          const uint32_t ec = S->esc_count;
-          for (i = 0; i <= cnum; i++) S->char_mask[Sym(p + 6 * i)] = ec;
-          p = 0;
-        }
+        const uint32_t ec = S->esc_count;
+        for (int k = lane; k <= cnum; k += 32) S->char_mask[Sym(p0 + 6 * k)] = ec;
+        GMX_L0(S->prev_success = 0; S->num_masked = cnum; S->found_state = 0);
       }
-      S->found_state = p;
-      if (p && Freq(p) > PPMD_MAX_FREQ) S->found_state = Rescale(minc, S->order_fall, p);
     } else {  // processBinSymbol<0> :1023-1046
-      const uint32_t rs = OneState(minc);
-      uint16_t* bs = BinSummFor(minc);
-      S->bsumm = *bs;
-      *bs = (uint16_t)(*bs - ((S->bsumm + 64) >> PPMD_PERIOD_BITS));
-      if (Sym(rs) != c) {
-        S->char_mask[Sym(rs)] = S->esc_count; S->num_masked = 0; S->prev_success = 0; S->found_state = 0;
-      } else {
-        *bs = (uint16_t)(*bs + PPMD_INTERVAL);
-        SetFreq(rs, Freq(rs) + (Freq(rs) < 196));
-        S->run_length++; S->prev_success = 1; S->found_state = rs;
-      }
+      GMX_L0(
+        const uint32_t rs = OneState(minc);
+        uint16_t* bs = BinSummFor(minc);
+        S->bsumm = *bs;
+        *bs = (uint16_t)(*bs - ((S->bsumm + 64) >> PPMD_PERIOD_BITS));
+        if (Sym(rs) != c) {
+          S->char_mask[Sym(rs)] = S->esc_count; S->num_masked = 0; S->prev_success = 0; S->found_state = 0;
+        } else {
+          *bs = (uint16_t)(*bs + PPMD_INTERVAL);
+          SetFreq(rs, Freq(rs) + (Freq(rs) < 196));
+          S->run_length++; S->prev_success = 1; S->found_state = rs;
+        });
     }
     while (!S->found_state) {
-      do { S->order_fall++; minc = Suffix(minc); } while ((int)NumStats(minc) == S->num_masked);
+      int climbed = 0;
+      const int nm = S->num_masked;
+      do { climbed++; minc = Suffix(minc); } while ((int)NumStats(minc) == nm);
       // processSymbol2<0> :1104-1170
-      uint32_t p = Stats(minc);
+      const uint32_t p = Stats(minc);
       const int cnum = (int)NumStats(minc);
-      int see_freq;
-      PpmdSee2* see = See2For(minc, cnum, &see_freq);
-      int low = 0, hit_i = -1;
       const uint32_t ec = S->esc_count;
-      for (int i = 0; i <= cnum; i++) {
-        const uint32_t s = Sym(p + 6 * i);
-        if (S->char_mask[s] != ec) {
-          S->char_mask[s] = ec;
-          low += (int)Freq(p + 6 * i);
-          if (s == c) hit_i = i;
+      int low = 0, hit_i = -1;
+      for (int base = 0; base <= cnum; base += 32) {
+        const int k = base + lane;
+        bool hit = false;
+        if (k <= cnum) {
+          const uint32_t sy = Sym(p + 6 * k);
+          if (S->char_mask[sy] != ec) {
+            S->char_mask[sy] = ec;
+            low += (int)Freq(p + 6 * k);
+            hit = sy == c;
+          }
         }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (m) hit_i = base + __ffs((int)m) - 1;
       }
-      const int total = see_freq + low;
-      if (hit_i >= 0) {
-        p += 6 * hit_i;
-        if (see_freq > 2) see->summ = (uint16_t)(see->summ - see_freq);
-        See2Update(see);
-        S->found_state = p;
-        SetFreq(p, Freq(p) + 4); SetSummFreq(minc, SummFreq(minc) + 4);
-        if (Freq(p) > PPMD_MAX_FREQ) S->found_state = Rescale(minc, S->order_fall, p);
-        S->run_length = S->init_rl;
-        S->esc_count++;
-      } else {
-        S->num_masked = cnum;
-        see->summ = (uint16_t)(see->summ + (total - see_freq));
-      }
+      low = WarpSum(low);
+      GMX_L0(
+        S->order_fall += climbed;
+        int see_freq;
+        PpmdSee2* see = See2For(minc, cnum, S->num_masked, &see_freq);
+        const int total = see_freq + low;
+        if (hit_i >= 0) {
+          const uint32_t ph = p + 6 * hit_i;
+          if (see_freq > 2) see->summ = (uint16_t)(see->summ - see_freq);
+          See2Update(see);
+          S->found_state = ph;
+          SetFreq(ph, Freq(ph) + 4); SetSummFreq(minc, SummFreq(minc) + 4);
+          if (Freq(ph) > PPMD_MAX_FREQ) S->found_state = Rescale(minc, S->order_fall, ph);
+          S->run_length = S->init_rl;
+          S->esc_count++;
+        } else {
+          S->num_masked = cnum;
+          see->summ = (uint16_t)(see->summ + (total - see_freq));
+        });
     }
-    if (S->order_fall != 0 || Succ(S->found_state) < S->units_start) UpdateModel(minc);
-    else S->max_context = Succ(S->found_state);
+    GMX_L0(
+      if (S->order_fall != 0 || Succ(S->found_state) < S->units_start) UpdateModel(minc);
+      else S->max_context = Succ(S->found_state));
   }
 
-  // One SQ entry folded straight into ConvertSQ :1192-1209.
-  GMX_DEV void Emit(uint32_t sym, uint32_t freq, uint32_t total) const {
-    const uint32_t prob = (uint32_t)(((uint64_t)S->cum * freq) / total);
-    if (sym < 256) sqp[sym] = prob + 1; else S->cum = prob;
-  }
+  // ConvertSQ :1192-1209 for one symbol: cum * freq / total (+1 for a symbol, the new cum for an escape)
+  GMX_DEV static uint32_t Scale(uint32_t cum, uint32_t freq, uint32_t total) { return (uint32_t)(((uint64_t)cum * freq) / total); }
 
   // ppmd_PrepareByte :1322-1349 with the *_T walkers :1222-1297: full next-byte distribution.
+  // (OrderFall is incremented and restored by the reference and read by nothing in between.)
   GMX_DEV void PrepareByte() const {
-    S->num_masked = 0;
-    const int saved_order_fall = S->order_fall;
-    S->cum = 0xFFFFFF00u;
-    for (int i = 0; i < 256; i++) sqp[i] = 0;
+    uint32_t cum = 0xFFFFFF00u;
+    for (int i = lane; i < 256; i += 32) sqp[i] = 0;
     uint32_t minc = S->max_context;
     const uint32_t ec = S->esc_count;
+    int nm;
+    __syncwarp();
     if (NumStats(minc)) {  // processSymbol1_T
       const uint32_t p = Stats(minc);
       const int cnum = (int)NumStats(minc);
       const uint32_t total = SummFreq(minc);
-      uint32_t low = 0;
-      for (int i = 0; i <= cnum; i++) {
-        const uint32_t f = Freq(p + 6 * i), s = Sym(p + 6 * i);
-        Emit(s, f, total);
-        low += f;
-        S->char_mask[s] = ec;
+      int low = 0;
+      for (int k = lane; k <= cnum; k += 32) {
+        const uint32_t f = Freq(p + 6 * k), sy = Sym(p + 6 * k);
+        sqp[sy] = Scale(cum, f, total) + 1;
+        low += (int)f;
+        S->char_mask[sy] = ec;
       }
-      S->num_masked = cnum;
-      Emit(256, (total - low) & 0xffff, total);
+      low = WarpSum(low);
+      nm = cnum;
+      cum = Scale(cum, (total - (uint32_t)low) & 0xffff, total);
     } else {  // processBinSymbol_T
       const uint32_t rs = OneState(minc);
-      S->bsumm = *BinSummFor(minc);
-      Emit(Sym(rs), (uint32_t)(S->bsumm + S->bsumm) & 0xffff, PPMD_SCALE);
-      Emit(256, (uint32_t)(PPMD_SCALE - S->bsumm - S->bsumm) & 0xffff, PPMD_SCALE);
-      S->char_mask[Sym(rs)] = ec;
-      S->num_masked = 0;
+      const int bsv = *BinSummFor(minc);
+      const uint32_t sy = Sym(rs);
+      GMX_L0(S->bsumm = bsv; sqp[sy] = Scale(cum, (uint32_t)(bsv + bsv) & 0xffff, PPMD_SCALE) + 1; S->char_mask[sy] = ec);
+      cum = Scale(cum, (uint32_t)(PPMD_SCALE - bsv - bsv) & 0xffff, PPMD_SCALE);
+      nm = 0;
     }
+    __syncwarp();
     for (;;) {
       bool root = false;
       do {
         if (!Suffix(minc)) { root = true; break; }
-        S->order_fall++;
         minc = Suffix(minc);
-      } while ((int)NumStats(minc) == S->num_masked);
+      } while ((int)NumStats(minc) == nm);
       if (root) break;
       // processSymbol2_T
       const uint32_t p = Stats(minc);
       const int cnum = (int)NumStats(minc);
       int see_freq;
-      See2For(minc, cnum, &see_freq);
-      uint32_t low = 0;
-      for (int i = 0; i <= cnum; i++) if (S->char_mask[Sym(p + 6 * i)] != ec) low += Freq(p + 6 * i);
-      const uint32_t total = ((uint32_t)see_freq + low) & 0xffff;
-      for (int i = 0; i <= cnum; i++) {
-        const uint32_t s = Sym(p + 6 * i);
-        if (S->char_mask[s] != ec) { Emit(s, Freq(p + 6 * i), total); S->char_mask[s] = ec; }
+      See2For(minc, cnum, nm, &see_freq);
+      int low = 0;
+      for (int k = lane; k <= cnum; k += 32)
+        if (S->char_mask[Sym(p + 6 * k)] != ec) low += (int)Freq(p + 6 * k);
+      low = WarpSum(low);
+      const uint32_t total = ((uint32_t)see_freq + (uint32_t)low) & 0xffff;
+      for (int k = lane; k <= cnum; k += 32) {
+        const uint32_t sy = Sym(p + 6 * k);
+        if (S->char_mask[sy] != ec) { sqp[sy] = Scale(cum, Freq(p + 6 * k), total) + 1; S->char_mask[sy] = ec; }
       }
-      Emit(256, (uint32_t)see_freq & 0xffff, total);
-      S->num_masked = cnum;
+      cum = Scale(cum, (uint32_t)see_freq & 0xffff, total);
+      nm = cnum;
+      __syncwarp();
     }
-    S->esc_count++;
-    S->num_masked = 0;
-    S->order_fall = saved_order_fall;
+    GMX_L0(S->esc_count++; S->num_masked = 0);
   }
+#undef GMX_L0
 };
 
 }  // namespace gmx

@@ -99,7 +99,8 @@ struct StreamParams {
   const float* adam;         // [L_UPDATE_LIMIT + 1][4]: alpha, 1-b1^t, 1-b2^t (lstm-layer.cpp:16-33), host libm
   uint64_t* bit_trace;       // optional: {f32 prob, u32 p16} per bit of stream 0 (debug/parity), or null
   float* pred_trace;         // optional: 90 predictions + 3 mask words + 33 mixer outs per bit of stream 0
-  uint32_t* usage;           // optional: per stream {sparse entries, mixer sets, PPMd unit bytes, history bytes}, or null
+  uint32_t* usage;           // optional: 8 words per stream {sparse entries, mixer sets, PPMd unit bytes, history bytes,
+                             // SM id, start us, end us (globaltimer, low 32 bits), 0}, or null
   unsigned long long* prof;  // optional: GMX_PROF_SLOTS cycle counters per stream (phase breakdown), or null
 };
 
@@ -148,6 +149,7 @@ struct StreamSmem {
   uint16_t ind_state[NIND + 1];
   uint8_t ind_found[NIND + 3];               // sparse tables: entry exists at ind_slot
   uint32_t sparse_used;
+  uint32_t t_start_us;
   // match
   uint32_t m_cur[NMATCH]; uint8_t m_byte[NMATCH], m_bitpos[NMATCH], m_len[NMATCH];
   uint32_t hist_len;
@@ -242,6 +244,24 @@ GMX_DEV inline uint32_t RecentByte(const StreamSmem& s, int ago) {  // short-ter
 GMX_DEV inline int MixerNW(int m) { return m < NL0 ? NPRED + m : m < NL0 + NL1 ? NL0 + (m - NL0) + 1 : NL0 + NL1 + 1; }
 
 GMX_DEV inline void BlockSync() { __syncthreads(); }
+GMX_DEV inline unsigned long long GlobalTimerNs() {
+#if defined(__CUDA_ARCH__)
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+#else
+  return 0ull;
+#endif
+}
+GMX_DEV inline uint32_t SmId() {
+#if defined(__CUDA_ARCH__)
+  uint32_t v;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
+  return v;
+#else
+  return 0u;
+#endif
+}
 
 // ---- stream start ------------------------------------------------------------------------------
 template <int NT>
@@ -252,7 +272,7 @@ GMX_DEV void FillWords(uint32_t* p, uint64_t nwords, uint32_t v, int tid) {
 template <int NT>
 GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, int tid) {
   const ArenaLayout& L = *A.L;
-  if (tid == 0) s.prof_t = GMX_CLOCK();
+  if (tid == 0) { s.prof_t = GMX_CLOCK(); s.t_start_us = (uint32_t)(GlobalTimerNs() / 1000ull); }
   for (int k = 0; k < NIND; ++k)
     if (!L.ind_sid[k]) FillWords<NT>(A.at<uint32_t>(L.ind_tab[k]), ((uint64_t)L.ind_size[k] + 1) / 2, 0x00FF00FFu, tid);
   if (L.sparse_mask) {
@@ -308,7 +328,7 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
   }
   BlockSync();
   if (tid == 0) {
-    Ppmd pm{A.at<PpmdState>(L.p_state), A.at<uint8_t>(L.p_text), A.at<uint8_t>(L.p_units), L.p_text_cap, L.p_units_cap, s.sqp};
+    Ppmd pm{A.at<PpmdState>(L.p_state), A.at<uint8_t>(L.p_text), A.at<uint8_t>(L.p_units), L.p_text_cap, L.p_units_cap, s.sqp, 0};
     pm.Init();
   }
   BlockSync();
@@ -507,7 +527,8 @@ GMX_DEV void LstmBptt(StreamSmem& s, const Arena& A, const StreamParams& P, int 
     BlockSync();
   }
   GMX_PROF(11);
-  // Weight gradients + Adam (lstm-layer.cpp:340-353, :12-34), one weight per thread at a time.
+  // Weight gradients + Adam (lstm-layer.cpp:340-353, :12-34). Every gradient is accumulated by one
+  // thread in the reference's epoch order (99 -> 0).
   const float* ad = P.adam + 4 * s.l_update_steps;
   const float alpha = ad[0], d1 = ad[1], d2 = ad[2];
   const float beta1 = (float)0.025, beta2 = (float)0.9999, eps = 1e-6f;
@@ -516,26 +537,57 @@ GMX_DEV void LstmBptt(StreamSmem& s, const Arena& A, const StreamParams& P, int 
   float* M = A.at<float>(L.l_m);
   float* V = A.at<float>(L.l_v);
   const float* lin = A.at<float>(L.l_lin);
-  for (int f = tid; f < 3 * L_ROW * L_CELLS; f += NT) {
-    const int g = f / (L_ROW * L_CELLS);
-    const int r = (f / L_CELLS) % L_ROW;
-    const int i = f % L_CELLS;
-    const float* eh = errh + (size_t)g * L_HORIZON * L_CELLS + i;
-    float grad = 0.0f;
-    if (r < L_NOUT) {
-      for (int ep = L_HORIZON - 1; ep >= 0; --ep)
-        if (s.l_symin[ep] == r) grad = f_add(grad, eh[ep * L_CELLS]);
-    } else {
-      const float* x = lin + (r - L_NOUT);
-#pragma unroll 4
-      for (int ep = L_HORIZON - 1; ep >= 0; --ep) grad = f_add(grad, f_mul(eh[ep * L_CELLS], x[ep * (L_NIN + 1)]));
-    }
+  auto adam = [&](size_t f, float grad) {
     float m = f_mul(M[f], beta1);
     m = f_add(m, f_mul(omb1, grad));
     float v = f_mul(V[f], beta2);
     v = f_add(v, f_mul(f_mul(omb2, grad), grad));
     M[f] = m; V[f] = v;
     Wm[f] = f_sub(Wm[f], f_mul(alpha, f_div(f_div(m, d1), f_sqrt(f_add(f_div(v, d2), eps)))));
+  };
+  // (a) one-hot rows: row r only receives err of the epochs whose input symbol was r. Per-symbol epoch
+  // lists (descending) are threaded through the scratch buffer.
+  uint8_t* head = (uint8_t*)s.l_err256;          // [256] first (largest) epoch of a symbol, 0xFF = none
+  uint8_t* nxt = head + 256;                     // [100] next smaller epoch with the same symbol
+  for (int i = tid; i < 256; i += NT) head[i] = 0xFF;
+  BlockSync();
+  if (tid == 0)
+    for (int ep = 0; ep < L_HORIZON; ++ep) { const int sy = s.l_symin[ep]; nxt[ep] = head[sy]; head[sy] = (uint8_t)ep; }
+  BlockSync();
+  for (int q = tid; q < 3 * L_NOUT * L_CELLS; q += NT) {
+    const int g = q / (L_NOUT * L_CELLS), rem = q - g * (L_NOUT * L_CELLS);
+    const int r = rem / L_CELLS, i = rem - r * L_CELLS;
+    const float* eh = errh + (size_t)g * L_HORIZON * L_CELLS + i;
+    float grad = 0.0f;
+    for (int ep = head[r]; ep != 0xFF; ep = nxt[ep]) grad = f_add(grad, eh[ep * L_CELLS]);
+    adam(((size_t)g * L_ROW + r) * L_CELLS + i, grad);
+  }
+  // (b) dense rows: grad[r][i] = sum_ep err[ep][i] * in[ep][r] as a register-tiled product, 4 rows x 2
+  // cells per thread (one 16-byte and one 8-byte load feed 8 multiply-adds).
+  constexpr int RG = (L_NIN + 3) / 4, IP = L_CELLS / 2;
+  for (int id = tid; id < 3 * RG * IP; id += NT) {
+    const int ip = id % IP, rg = (id / IP) % RG, g = id / (IP * RG);
+    const float2* e2 = (const float2*)(errh + (size_t)g * L_HORIZON * L_CELLS + 2 * ip);
+    const float4* x4 = (const float4*)(lin + 4 * rg);
+    float a[4][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}, {0.0f, 0.0f}, {0.0f, 0.0f}};
+#pragma unroll 2
+    for (int ep = L_HORIZON - 1; ep >= 0; --ep) {
+      const float2 e = e2[ep * (L_CELLS / 2)];
+      const float4 x = x4[ep * ((L_NIN + 1) / 4)];
+      a[0][0] = f_add(a[0][0], f_mul(e.x, x.x)); a[0][1] = f_add(a[0][1], f_mul(e.y, x.x));
+      a[1][0] = f_add(a[1][0], f_mul(e.x, x.y)); a[1][1] = f_add(a[1][1], f_mul(e.y, x.y));
+      a[2][0] = f_add(a[2][0], f_mul(e.x, x.z)); a[2][1] = f_add(a[2][1], f_mul(e.y, x.z));
+      a[3][0] = f_add(a[3][0], f_mul(e.x, x.w)); a[3][1] = f_add(a[3][1], f_mul(e.y, x.w));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int rr = 4 * rg + k;
+      if (rr < L_NIN) {
+        const size_t f = ((size_t)g * L_ROW + L_NOUT + rr) * L_CELLS + 2 * ip;
+        adam(f, a[k][0]);
+        adam(f + 1, a[k][1]);
+      }
+    }
   }
   for (int t = tid; t < 2 * 3 * L_CELLS; t += NT) {  // gamma then beta (lstm-layer.cpp:349-352)
     const int which = t / (3 * L_CELLS), k = t - which * 3 * L_CELLS;  // k = g*CELLS + i
@@ -645,8 +697,8 @@ GMX_DEV void ByteBoundary(StreamSmem& s, const Arena& A, const StreamParams& P, 
       s.ctx[C_IH0 + k] = Murmur32(tab[oh & mask]);
     }
     s.ih_hash[k] = oh;
-  } else if (tid == NT - 1) {  // ModPPMD::Predict byte part, mod_ppmd.cpp:1651-1654
-    Ppmd pm{A.at<PpmdState>(L.p_state), A.at<uint8_t>(L.p_text), A.at<uint8_t>(L.p_units), L.p_text_cap, L.p_units_cap, s.sqp};
+  } else if (tid >= NT - 32) {  // ModPPMD::Predict byte part, mod_ppmd.cpp:1651-1654 (the last warp, collectively)
+    Ppmd pm{A.at<PpmdState>(L.p_state), A.at<uint8_t>(L.p_text), A.at<uint8_t>(L.p_units), L.p_text_cap, L.p_units_cap, s.sqp, tid - (NT - 32)};
     pm.UpdateByte(last_byte);
     if (!pm.S->error) pm.PrepareByte();
     if (pm.S->error) s.error = GMX_ERR_PPMD_ARENA;
@@ -1084,9 +1136,10 @@ GMX_DEV inline void Trace(StreamSmem& s, const StreamParams& P, uint64_t bit_ind
 GMX_DEV inline void WriteUsage(const StreamSmem& s, const Arena& A, const StreamParams& P, uint32_t sid) {
   if (!P.usage) return;
   const PpmdState* ps = A.at<PpmdState>(A.L->p_state);
-  uint32_t* u = P.usage + 4 * (size_t)sid;
+  uint32_t* u = P.usage + 8 * (size_t)sid;
   u[0] = s.sparse_used; u[1] = s.pool_next;
   u[2] = (ps->lo_unit - PPMD_UNITS_START) + (PPMD_HEAP_END - ps->hi_unit); u[3] = s.hist_len;
+  u[4] = SmId(); u[5] = s.t_start_us; u[6] = (uint32_t)(GlobalTimerNs() / 1000ull); u[7] = 0;
 }
 
 // runner_utils::Compress (runner-utils.cpp:43-67) incl. the 5-byte header of RunCompression (:109).

@@ -112,8 +112,9 @@ int gmx_device_sm_count(const gmx_ctx* ctx);
 int gmx_set_profile(gmx_ctx* ctx, int on);
 int gmx_get_profile(gmx_ctx* ctx, uint64_t* out, uint32_t max_streams);
 
-/* Arena usage of the streams of the last batch call: 4 words per stream {entries in the shared sparse
- * table, mixer weight sets, PPMd unit bytes, Match history bytes}; returns the number of streams copied. */
+/* Per-stream counters of the last batch call: 8 words per stream {entries in the shared sparse table,
+ * mixer weight sets, PPMd unit bytes, Match history bytes, SM id, start and end time in us (device
+ * globaltimer, low 32 bits), 0}; returns the number of streams copied. */
 int gmx_get_usage(gmx_ctx* ctx, uint32_t* out, uint32_t max_streams);
 
 /* Exhaustive check of the device expf/logf/tanhf against the host libm: inputs are the bit

@@ -171,12 +171,15 @@ inline unsigned __ballot_sync(unsigned, int pred) {
   for (int l = 0; l < 32; ++l) m |= (cuda_emu::Shfl(pred ? 1u : 0u, (unsigned)l) & 1u) << l;
   return m;
 }
+inline int __ffs(int x) { return x == 0 ? 0 : __builtin_ctz((unsigned)x) + 1; }
 inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 template <typename T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 template <typename T> inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
 template <typename T> inline T atomicCAS(T* p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
 struct uint4 { unsigned x, y, z, w; };
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
 inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 
 #endif  // GMIX_TESTS_CUDA_EMU_H_

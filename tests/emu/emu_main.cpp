@@ -49,7 +49,7 @@ retry:
   P.n_streams = 1; P.queue = &queue;
   P.arenas = (uint8_t*)(((uintptr_t)arena.data() + 255) & ~(uintptr_t)255); P.arena_stride = L.total; P.layout = &L;
   P.lstm_init = linit.data(); P.decay = decay.data(); P.decay_len = (uint32_t)decay.size(); P.adam = adam.data();
-  uint32_t usage[4] = {0, 0, 0, 0};
+  uint32_t usage[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   P.usage = usage;
   P.bit_trace = bit_trace.empty() ? nullptr : bit_trace.data();
   P.pred_trace = pred_trace.empty() ? nullptr : pred_trace.data();
