@@ -6,8 +6,8 @@ import sys
 ROOT = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(ROOT, "csrc")
 LIB = os.path.join(ROOT, "lib", "libgmix_b200.so")
-SOURCES = ["host.cu", "kernel_compress.cu", "kernel_decompress.cu"]
-DEPS = ["host.cu", "kernel_compress.cu", "kernel_decompress.cu", "kernels.h", "stream_kernel.cuh", "ppmd.cuh", "dmath.cuh", "spec.cuh", "layout.h", "nonstationary.inc",
+SOURCES = ["host.cu", "kernel_compress.cu", "kernel_decompress.cu", "kernel_compress_prof.cu"]
+DEPS = ["host.cu", "kernel_compress.cu", "kernel_decompress.cu", "kernel_compress_prof.cu", "kernels.h", "stream_kernel.cuh", "ppmd.cuh", "dmath.cuh", "spec.cuh", "layout.h", "nonstationary.inc",
         os.path.join("..", "..", "include", "gmix_b200.h")]
 
 NVCC_FLAGS = [

@@ -25,8 +25,12 @@
 
 #if defined(__CUDACC__)
 #define GMX_HD __host__ __device__ __forceinline__
+// The libm bodies are called from a dozen sites of the stream kernel; one out-of-line copy each keeps
+// the per-bit path's code small (it is instruction-cache bound).
+#define GMX_HD_OUTLINE static __host__ __device__ __noinline__
 #else
 #define GMX_HD inline
+#define GMX_HD_OUTLINE inline
 #endif
 
 namespace gmx {
@@ -176,7 +180,7 @@ GMX_HD double LogT(int i) {
 }  // namespace tables
 
 // glibc 2.39 expf, FMA variant.
-GMX_HD float gm_expf(float x) {
+GMX_HD_OUTLINE float gm_expf(float x) {
   const uint32_t ux = f2u(x);
   const uint32_t abstop = (ux >> 20) & 0x7ff;
   if (abstop >= 0x42b) {  // |x| >= 88 or non-finite
@@ -204,7 +208,7 @@ GMX_HD float gm_expf(float x) {
 
 // glibc 2.39 logf, FMA variant, positive normal arguments only: every
 // call site clamps its argument first (Sigmoid::Logit, sigmoid.cpp:7-12 => x in [1e-4, 1e4]).
-GMX_HD float gm_logf(float x) {
+GMX_HD_OUTLINE float gm_logf(float x) {
   const uint32_t ix = f2u(x);
   if (ix == 0x3f800000u) return 0.0f;
   const double Ln2 = 0x1.62e42fefa39efp-1;
@@ -297,7 +301,7 @@ GMX_HD float gm_expm1f(float x) {
 }
 
 // fdlibm tanhf as shipped in glibc (s_tanhf.c).
-GMX_HD float gm_tanhf(float x) {
+GMX_HD_OUTLINE float gm_tanhf(float x) {
   const float one = 1.0f, two = 2.0f, tiny = 1.0e-30f;
   const uint32_t jx = f2u(x);
   const uint32_t ix = jx & 0x7fffffffu;

@@ -107,7 +107,8 @@ bool Retryable(uint32_t st) {
 int Launch(gmx_ctx* c, int mode, const gmx::StreamParams& P, uint32_t grid) {
   GMX_CUDA(c, cudaMemsetAsync(c->d_queue, 0, sizeof(uint32_t), c->stream));
   GMX_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-  GMX_CUDA(c, mode == gmx::MODE_COMPRESS ? gmx::LaunchCompress(P, grid, c->stream) : gmx::LaunchDecompress(P, grid, c->stream));
+  GMX_CUDA(c, mode == gmx::MODE_COMPRESS ? (P.prof ? gmx::LaunchCompressProf(P, grid, c->stream) : gmx::LaunchCompress(P, grid, c->stream))
+                                         : gmx::LaunchDecompress(P, grid, c->stream));
   GMX_CUDA(c, cudaEventRecord(c->ev1, c->stream));
   GMX_CUDA(c, cudaStreamSynchronize(c->stream));
   float ms = 0;

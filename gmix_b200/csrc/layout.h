@@ -105,6 +105,7 @@ inline ArenaLayout MakeLayout(uint64_t max_len, bool roomy = false) {
   L.l_ig = take((uint64_t)L_HORIZON * L_CELLS * 4);
   L.l_last = take((uint64_t)L_HORIZON * L_CELLS * 4);
   L.l_errh = take(3ull * L_HORIZON * L_CELLS * 4);
+  L.l_wt = take(3ull * L_CELLS * L_CELLS * 4);
   L.p_state = take(sizeof(PpmdState));
   L.p_text_cap = (uint32_t)(max_len + 64);
   L.p_text = take(AlignUp(L.p_text_cap, 4));

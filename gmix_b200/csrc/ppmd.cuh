@@ -20,8 +20,10 @@
 
 #if defined(__CUDACC__)
 #define GMX_DEV __device__
+#define GMX_NOINLINE __noinline__
 #else
 #define GMX_DEV
+#define GMX_NOINLINE
 #endif
 
 namespace gmx {
@@ -59,9 +61,11 @@ struct Ppmd {
 
   // ---- virtual heap -> backed memory -------------------------------------------------------
   GMX_DEV uint8_t* At(uint32_t v) const {
-    if (v < PPMD_UNITS_START) return text + v;
-    if (v >= PPMD_HEAP_END - units_cap) return units + (units_cap - (PPMD_HEAP_END - v));
-    return units + (v - PPMD_UNITS_START);
+    // one base select + one add (this is inlined at every heap access)
+    const long long lo = (long long)(units - text) - (long long)PPMD_UNITS_START;
+    const long long hi = (long long)(units - text) + (long long)units_cap - (long long)PPMD_HEAP_END;
+    const long long off = v < PPMD_UNITS_START ? 0ll : (v >= PPMD_HEAP_END - units_cap ? hi : lo);
+    return text + (off + (long long)v);
   }
   GMX_DEV uint32_t R8(uint32_t v) const { return *At(v); }
   GMX_DEV void W8(uint32_t v, uint32_t x) const { *At(v) = (uint8_t)x; }
@@ -172,7 +176,7 @@ struct Ppmd {
   }
 
   // ---- model start: PPMD_STARTUP :375-400 + StartModelRare :659-713 ---------------------------
-  GMX_DEV void Init() const {
+  GMX_DEV GMX_NOINLINE void Init() const {
     int i, k, m, step;
     for (i = 0, k = 1; i < 4; i++, k += 1) S->indx2units[i] = (uint8_t)k;
     for (k++; i < 8; i++, k += 2) S->indx2units[i] = (uint8_t)k;
@@ -233,7 +237,7 @@ struct Ppmd {
   }
 
   // rescale :498-566
-  GMX_DEV uint32_t Rescale(uint32_t q, int order_fall, uint32_t fs) const {
+  GMX_DEV GMX_NOINLINE uint32_t Rescale(uint32_t q, int order_fall, uint32_t fs) const {
     SetFlags(q, Flags(q) & 0x14);
     const uint32_t p1 = Stats(q);
     uint32_t t0 = R16(fs), t1 = R16(fs + 2), t2 = R16(fs + 4);
@@ -301,7 +305,7 @@ struct Ppmd {
 
   // CreateSuccessors :888-969 (`p` = state of the coded symbol in suffix(pc), or 0). Returns 0 on
   // arena exhaustion.
-  GMX_DEV uint32_t CreateSuccessors(bool skip, uint32_t p, uint32_t pc) const {
+  GMX_DEV GMX_NOINLINE uint32_t CreateSuccessors(bool skip, uint32_t p, uint32_t pc) const {
     uint32_t ps[PPMD_MAX_ORDER + 4];
     int n = 0;
     uint32_t sym = Sym(S->found_state);
@@ -360,7 +364,7 @@ struct Ppmd {
     return pc;
   }
 
-  GMX_DEV uint32_t ReduceOrder(uint32_t p, uint32_t pc) const {  // :971-1018
+  GMX_DEV GMX_NOINLINE uint32_t ReduceOrder(uint32_t p, uint32_t pc) const {  // :971-1018
     const uint32_t pc1 = pc;
     SetSucc(S->found_state, S->text_ptr);
     const uint32_t sym = Sym(S->found_state);
@@ -402,7 +406,7 @@ struct Ppmd {
     return Succ(p);
   }
 
-  GMX_DEV void UpdateModel(uint32_t minc) const {  // :759-886
+  GMX_DEV GMX_NOINLINE void UpdateModel(uint32_t minc) const {  // :759-886
     const uint32_t fs = S->found_state;
     const uint32_t fsym = Sym(fs);
     const uint32_t ffreq = Freq(fs);

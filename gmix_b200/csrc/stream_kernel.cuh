@@ -33,7 +33,10 @@ enum : uint32_t {
   GMX_ERR_SPARSE_FULL = 7,   // shared sparse table over its load limit (host retries with a roomier arena)
 };
 
-enum : int { WSTRIDE = 117 };
+// Shared-memory staging of the 33 selected weight sets: layer-0 sets (<= 113 weights) at stride 132 words,
+// layer-1/final sets (<= 33 weights) at stride 36 words. Both strides are 16-byte multiples (float4
+// loads) and = 4 mod 32 banks, which makes lane-per-neuron float4 reads conflict free.
+enum : int { WSTRIDE0 = 132, WSTRIDE1 = 36, WTOTAL = 24 * WSTRIDE0 + 9 * WSTRIDE1 };
 enum : int { GMX_PROF_SLOTS = 16 };
 // Phase slots: 0 byte contexts+PPMd, 1 ppm normalise, 2 LSTM forward, 3 interval nodes, 4 indirect/match
 // lookups, 5 mixer set swap, 6 mixer predict, 7 coder, 8 learn scalars+indirect, 9 mixer weight update,
@@ -45,7 +48,7 @@ enum : int { GMX_PROF_SLOTS = 16 };
 #endif
 #define GMX_PROF(slot)                                                        \
   do {                                                                        \
-    if (P.prof && tid == 0) {                                                 \
+    if (PROF && tid == 0) {                                                   \
       const long long t_ = GMX_CLOCK();                                       \
       s.prof[slot] += (unsigned long long)(t_ - s.prof_t);                    \
       s.prof_t = t_;                                                          \
@@ -80,6 +83,7 @@ struct ArenaLayout {
   uint64_t l_ivar;            // float [3][L_HORIZON]
   uint64_t l_tanh, l_ig, l_last;  // float [L_HORIZON][L_CELLS]
   uint64_t l_errh;            // float [3][L_HORIZON][L_CELLS]
+  uint64_t l_wt;              // float [3][L_CELLS][L_CELLS] transposed recurrent weights (BPTT scratch)
   // PPMd
   uint64_t p_state; uint64_t p_text; uint64_t p_units; uint32_t p_text_cap; uint32_t p_units_cap;
   uint64_t total;             // arena bytes
@@ -120,28 +124,37 @@ GMX_CONST_TABLE uint8_t kNonstationary[512] = {
 #include "nonstationary.inc"
 };
 
+// Read-only per launch: the arena layout and the model-graph tables, staged in shared memory because
+// every lane indexes them with its own model number on the per-bit path.
+struct StreamTables {
+  ArenaLayout L;
+  IndirectSpec ind[NIND]; SkipSpec skip[20]; IntervalSpec interval[9]; IHSpec ih[NIH]; MatchSpec match[NMATCH];
+  MixerSpec mixer[NMIX];
+  uint8_t nonstationary[512];
+};
+
 // ---- per-stream state staged in shared memory ---------------------------------------------------
 struct StreamSmem {
+  StreamTables T;
   // blackboard (ShortTermMemory)
   float preds[NPRED + 2];
   uint8_t act[NPRED + 6];
   uint32_t ctx[C_COUNT + 2];
-  float l0_out[NL0], l1_out[NL1], final_out, prob;
+  alignas(16) float l0_out[NL0]; float l1_out[NL1], final_out, prob;   // l0_out | l1_out contiguous (final mixer input)
   float ppm[256], lprob[256];          // byte distributions of PPMd and LSTM
   float node_ppm[256], node_lstm[256]; // Logit(p) of every node of the binary interval search
   uint8_t nflag_ppm[256], nflag_lstm[256];  // bit0: denom != 0, bit1: p != 0.5
-  uint32_t sqp[256];
   uint8_t ring[1000];
   uint32_t ring_pos;
   int32_t new_bit, recent_bits, bb, first_prediction, analysis;
   uint32_t error;
   uint32_t steps;                      // Mixer::steps_ (identical for all 33 mixers)
   // mixers
-  float w[NMIX * WSTRIDE];
+  alignas(16) float w[WTOTAL];
+  alignas(16) float xe[NPRED + 2];          // predictions with the inactive ones zeroed (mixer layer-0 input)
   uint32_t set_steps[NMIX], max_steps[NMIX], set_idx[NMIX], set_pool[NMIX];
   uint32_t swap_old[NMIX], swap_new[NMIX], nswap;   // queued set swaps of this bit
   uint8_t swap_m[NMIX + 3], shrink[NMIX + 3];
-  float act_x[NPRED + 2]; uint8_t act_idx[NPRED + 2]; uint32_t act_n;  // compacted active predictions
   float upd[NMIX];
   uint32_t pool_next;
   // indirect
@@ -156,11 +169,13 @@ struct StreamSmem {
   // indirect hash
   uint64_t ih_outer[NIH]; uint32_t ih_hash[NIH];
   // LSTM
-  float l_in[L_NIN + 1];
   float l_hidden[L_HID + 1], l_state[L_CELLS], l_state_err[L_CELLS], l_stored_err[L_CELLS], l_hidden_err[L_CELLS];
   float l_gate[3][L_CELLS], l_gerr[3][L_CELLS];
   float l_red[16];
-  float l_err256[256];
+  union alignas(16) {            // never live at the same time:
+    uint32_t sqp[256];           //   PPMd symbol pseudo-probabilities (byte boundary, before the LSTM forward pass)
+    float l_err256[256];         //   LSTM scratch (forward pass, Perceive, BPTT)
+  };
   uint8_t l_hist[L_HORIZON], l_symin[L_HORIZON];
   uint32_t l_epoch, l_update_steps, l_old_input;
   // coder
@@ -241,9 +256,17 @@ GMX_DEV inline uint32_t RecentByte(const StreamSmem& s, int ago) {  // short-ter
   if (pos < 0) pos += 1000;
   return s.ring[pos];
 }
+GMX_DEV inline int WOff(int m) { return m < NL0 ? m * WSTRIDE0 : NL0 * WSTRIDE0 + (m - NL0) * WSTRIDE1; }
 GMX_DEV inline int MixerNW(int m) { return m < NL0 ? NPRED + m : m < NL0 + NL1 ? NL0 + (m - NL0) + 1 : NL0 + NL1 + 1; }
 
 GMX_DEV inline void BlockSync() { __syncthreads(); }
+GMX_DEV inline void PrefetchL2(const void* p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
 GMX_DEV inline unsigned long long GlobalTimerNs() {
 #if defined(__CUDA_ARCH__)
   unsigned long long t;
@@ -263,13 +286,18 @@ GMX_DEV inline uint32_t SmId() {
 #endif
 }
 
+// L2 prefetch of `bytes` bytes at p, cooperatively by the `nthr` threads numbered t = 0..nthr-1.
+GMX_DEV inline void PrefetchRange(const void* p, uint32_t bytes, int t, int nthr) {
+  for (uint32_t o = (uint32_t)t * 128u; o < bytes; o += (uint32_t)nthr * 128u) PrefetchL2((const char*)p + o);
+}
+
 // ---- stream start ------------------------------------------------------------------------------
 template <int NT>
 GMX_DEV void FillWords(uint32_t* p, uint64_t nwords, uint32_t v, int tid) {
   for (uint64_t i = tid; i < nwords; i += NT) p[i] = v;
 }
 
-template <int NT>
+template <int NT, bool PROF>
 GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, int tid) {
   const ArenaLayout& L = *A.L;
   if (tid == 0) { s.prof_t = GMX_CLOCK(); s.t_start_us = (uint32_t)(GlobalTimerNs() / 1000ull); }
@@ -282,14 +310,14 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
   }
   FillWords<NT>(A.at<uint32_t>(L.ind_pred), NIND * 512, 0u, tid);
   for (int k = 0; k < NMATCH; ++k)
-    if (!L.match_sid[k]) FillWords<NT>(A.at<uint32_t>(L.match_tab[k]), 1ull << kMatch[k].log2, 0u, tid);
+    if (!L.match_sid[k]) FillWords<NT>(A.at<uint32_t>(L.match_tab[k]), 1ull << s.T.match[k].log2, 0u, tid);
   for (int i = tid; i < NMATCH * 256; i += NT) {
     A.at<float>(L.match_pred)[i] = (float)(0.5 + ((double)(i & 255) + 0.5) / 512);  // match.cpp:19-21
     A.at<int>(L.match_cnt)[i] = 1;
   }
   for (int k = 0; k < NIH; ++k)
-    if (!L.ih_sid[k]) FillWords<NT>(A.at<uint32_t>(L.ih_tab[k]), 1ull << kIH[k].log2, 0u, tid);
-  for (int m = 0; m < NMIX; ++m) FillWords<NT>(A.at<uint32_t>(L.mix_dir[m]), 1ull << kMixer[m].log2, 0u, tid);
+    if (!L.ih_sid[k]) FillWords<NT>(A.at<uint32_t>(L.ih_tab[k]), 1ull << s.T.ih[k].log2, 0u, tid);
+  for (int m = 0; m < NMIX; ++m) FillWords<NT>(A.at<uint32_t>(L.mix_dir[m]), 1ull << s.T.mixer[m].log2, 0u, tid);
   // LSTM (lstm.cpp:8-43, lstm-layer.cpp:36-54,156-196)
   for (int i = tid; i < 3 * L_ROW * L_CELLS; i += NT) {
     A.at<float>(L.l_w)[i] = P.lstm_init[i];
@@ -310,7 +338,8 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
   for (int i = tid; i < NL1; i += NT) s.l1_out[i] = 0.0f;
   for (int i = tid; i < 256; i += NT) { s.ppm[i] = (float)(1.0 / 256); s.lprob[i] = (float)(1.0 / 256); }
   for (int i = tid; i < 1000; i += NT) s.ring[i] = 0;
-  for (int i = tid; i < NMIX * WSTRIDE; i += NT) s.w[i] = 0.0f;
+  for (int i = tid; i < WTOTAL; i += NT) s.w[i] = 0.0f;
+  for (int i = tid; i < NPRED + 2; i += NT) s.xe[i] = 0.0f;
   for (int i = tid; i < NMIX; i += NT) {
     s.set_steps[i] = 0; s.max_steps[i] = 1; s.set_idx[i] = 0xFFFFFFFFu; s.set_pool[i] = 0; s.shrink[i] = 0;
   }
@@ -321,8 +350,8 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
   for (int i = tid; i < L_HORIZON; i += NT) { s.l_hist[i] = 0; s.l_symin[i] = 0; }
   if (tid == 0) {
     s.final_out = 0; s.prob = 0.5f; s.ring_pos = 0; s.new_bit = 0; s.recent_bits = 1; s.bb = 0;
-    s.first_prediction = 1; s.error = 0; s.steps = 0; s.pool_next = 1; s.hist_len = 0; s.sparse_used = 0; s.nswap = 0; s.act_n = 0;
-    s.l_epoch = 0; s.l_update_steps = 0; s.l_old_input = 0; s.l_in[L_NIN] = 0;
+    s.first_prediction = 1; s.error = 0; s.steps = 0; s.pool_next = 1; s.hist_len = 0; s.sparse_used = 0; s.nswap = 0;
+    s.l_epoch = 0; s.l_update_steps = 0; s.l_old_input = 0;
     s.x1 = 0; s.x2 = 0xffffffffu; s.x = 0;
     for (int i = 0; i < GMX_PROF_SLOTS; ++i) s.prof[i] = 0;
   }
@@ -346,20 +375,36 @@ GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, i
   // layer_input[e] = [ppm 256 | hidden 50 | 1]  (SetInput lstm.cpp:45-50, copy :94-96)
   for (int i = tid; i < L_NIN; i += NT) {
     const float v = i < 256 ? s.ppm[i] : i < 306 ? s.l_hidden[i - 256] : 1.0f;
-    s.l_in[i] = v;
     lin_e[i] = v;
   }
   if (tid < L_CELLS) A.at<float>(L.l_last)[e * L_CELLS + tid] = s.l_state[tid];  // last_state_[epoch] = state_
   BlockSync();
-  // gate pre-activations: f = w[sym]; f += in[j] * w[256 + j], j ascending (lstm-layer.cpp:227-232)
-  for (int t = tid; t < 3 * L_CELLS; t += NT) {
-    const int g = t / L_CELLS, i = t - g * L_CELLS;
-    const float* w = A.at<float>(L.l_w) + (size_t)g * L_ROW * L_CELLS + i;
-    float f = w[(size_t)sym * L_CELLS];
-    const float* wd = w + (size_t)L_NOUT * L_CELLS;
-#pragma unroll 4
-    for (int j = 0; j < L_NIN; ++j) f = f_add(f, f_mul(s.l_in[j], wd[(size_t)j * L_CELLS]));
-    s.l_gate[g][i] = f;
+  // gate pre-activations: f = w[sym]; f += in[j] * w[256 + j], j ascending (lstm-layer.cpp:227-232).
+  // 150 rows on 75 threads, two independent sequential sums per thread (twice the loads in flight).
+  if (tid < 3 * L_CELLS / 2) {
+    const int t0 = tid, t1 = tid + 3 * L_CELLS / 2;
+    const int g0 = t0 / L_CELLS, i0 = t0 - g0 * L_CELLS, g1 = t1 / L_CELLS, i1 = t1 - g1 * L_CELLS;
+    const float* w0 = A.at<float>(L.l_w) + (size_t)g0 * L_ROW * L_CELLS + i0;
+    const float* w1 = A.at<float>(L.l_w) + (size_t)g1 * L_ROW * L_CELLS + i1;
+    float f0 = w0[(size_t)sym * L_CELLS], f1 = w1[(size_t)sym * L_CELLS];
+    w0 += (size_t)L_NOUT * L_CELLS; w1 += (size_t)L_NOUT * L_CELLS;
+#pragma unroll 8
+    for (int j = 0; j < L_NOUT; ++j) {              // layer input = [ppm 256 | hidden 50 | 1]
+      const float x = s.ppm[j];
+      f0 = f_add(f0, f_mul(x, w0[(size_t)j * L_CELLS]));
+      f1 = f_add(f1, f_mul(x, w1[(size_t)j * L_CELLS]));
+    }
+    w0 += (size_t)L_NOUT * L_CELLS; w1 += (size_t)L_NOUT * L_CELLS;
+#pragma unroll 10
+    for (int j = 0; j < L_CELLS; ++j) {
+      const float x = s.l_hidden[j];
+      f0 = f_add(f0, f_mul(x, w0[(size_t)j * L_CELLS]));
+      f1 = f_add(f1, f_mul(x, w1[(size_t)j * L_CELLS]));
+    }
+    f0 = f_add(f0, f_mul(1.0f, w0[(size_t)L_CELLS * L_CELLS]));
+    f1 = f_add(f1, f_mul(1.0f, w1[(size_t)L_CELLS * L_CELLS]));
+    s.l_gate[g0][i0] = f0;
+    s.l_gate[g1][i1] = f1;
   }
   BlockSync();
   // ivar = 1 / sqrt(sum(norm^2)/cells + 1e-5): _Expr::sum() runs descending (lstm-layer.cpp:233-236)
@@ -401,7 +446,7 @@ GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, i
   float mx = 0.0f;
   for (int i = tid; i < L_NOUT; i += NT) {
     float acc = 0.0f;
-#pragma unroll 3
+#pragma unroll 17
     for (int j = 0; j < L_HID; ++j) acc = f_add(acc, f_mul(s.l_hidden[j], wo[j * L_NOUT + i]));
     s.l_err256[i] = acc;
     mx = acc > mx ? acc : mx;
@@ -433,13 +478,23 @@ GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, i
 // Truncated BPTT over the 100 stored steps + Adam (Lstm::Perceive lstm.cpp:57-79,
 // LstmLayer::BackwardPass lstm-layer.cpp:252-354). Weight gradients are accumulated per weight in
 // the reference's epoch order (99 -> 0) by the thread that owns the weight, then Adam is applied.
-template <int NT>
+template <int NT, bool PROF>
 GMX_DEV void LstmBptt(StreamSmem& s, const Arena& A, const StreamParams& P, int tid) {
   const ArenaLayout& L = *A.L;
   float* gb = A.at<float>(L.l_gb);
   const float* W = A.at<float>(L.l_w);
   float* errh = A.at<float>(L.l_errh);
+  // recurrent weights W[cell j][512 + i], snapshot transposed so that lanes (= i) read them coalesced
+  // (the reference snapshots the same block into transpose_ at the first epoch, lstm-layer.cpp:300-311)
+  float* Wt = A.at<float>(L.l_wt);
+  for (int q = tid; q < 3 * L_CELLS * L_CELLS; q += NT) {
+    const int g = q / (L_CELLS * L_CELLS), rem = q - g * (L_CELLS * L_CELLS);
+    const int j = rem / L_CELLS, i = rem - j * L_CELLS;
+    Wt[q] = W[((size_t)g * L_ROW + 512 + i) * L_CELLS + j];
+  }
+  BlockSync();
   for (int ep = L_HORIZON - 1; ep >= 0; --ep) {
+    if (ep > 0) PrefetchRange(A.at<float>(L.l_wout) + (size_t)(ep - 1) * L_HID * L_NOUT, L_HID * L_NOUT * 4, tid, NT);
     const float* out_e = A.at<float>(L.l_out) + ep * L_NOUT;
     for (int i = tid; i < L_NOUT; i += NT)
       s.l_err256[i] = (uint32_t)i == s.l_hist[ep] ? f_sub(out_e[i], 1.0f) : out_e[i];
@@ -448,8 +503,14 @@ GMX_DEV void LstmBptt(StreamSmem& s, const Arena& A, const StreamParams& P, int 
       // hidden_error[j] += Wout[ep][i][j] * err_i, i ascending; hidden_error is 0 on entry (lstm.cpp:60-70)
       const float* wo = A.at<float>(L.l_wout) + ((size_t)ep * L_HID + tid) * L_NOUT;
       float he = s.l_hidden_err[tid];
+      const float4* wo4 = (const float4*)wo;
+      const float4* er4 = (const float4*)s.l_err256;
 #pragma unroll 4
-      for (int i = 0; i < L_NOUT; ++i) he = f_add(he, f_mul(wo[i], s.l_err256[i]));
+      for (int i = 0; i < L_NOUT / 4; ++i) {
+        const float4 w = wo4[i], e = er4[i];
+        he = f_add(he, f_mul(w.x, e.x)); he = f_add(he, f_mul(w.y, e.y));
+        he = f_add(he, f_mul(w.z, e.z)); he = f_add(he, f_mul(w.w, e.w));
+      }
       // LstmLayer::BackwardPass lstm-layer.cpp:256-281
       const int i = tid;
       float stored = ep == L_HORIZON - 1 ? he : f_add(s.l_stored_err[i], he);
@@ -483,27 +544,23 @@ GMX_DEV void LstmBptt(StreamSmem& s, const Arena& A, const StreamParams& P, int 
       s.l_gerr[g][i] = f_mul(err, f_mul(gb[g * L_CELLS + i], A.at<float>(L.l_ivar)[g * L_HORIZON + ep]));
     }
     BlockSync();
-    // err -= (sum(err*norm)/cells) * norm; the sum is an _Expr::sum(): descending (lstm-layer.cpp:319-321)
-    float newerr[(3 * L_CELLS + NT - 1) / NT];
-    {
-      int q = 0;
-      for (int t = tid; t < 3 * L_CELLS; t += NT, ++q) {
-        const int g = t / L_CELLS, i = t - g * L_CELLS;
-        const float* nrm = A.at<float>(L.l_norm) + ((size_t)g * L_HORIZON + ep) * L_CELLS;
-        float acc = f_mul(s.l_gerr[g][L_CELLS - 1], nrm[L_CELLS - 1]);
-        for (int k = L_CELLS - 2; k >= 0; --k) acc = f_add(acc, f_mul(s.l_gerr[g][k], nrm[k]));
-        acc = f_div(acc, (float)L_CELLS);
-        newerr[q] = f_sub(s.l_gerr[g][i], f_mul(acc, nrm[i]));
-      }
+    // err -= (sum(err*norm)/cells) * norm; the sum is an _Expr::sum(): descending (lstm-layer.cpp:319-321).
+    // One lane per gate forms the sum (it is the same for every cell of the gate).
+    if (tid < 3) {
+      const int g = tid;
+      const float* nrm = A.at<float>(L.l_norm) + ((size_t)g * L_HORIZON + ep) * L_CELLS;
+      float acc = f_mul(s.l_gerr[g][L_CELLS - 1], nrm[L_CELLS - 1]);
+#pragma unroll 7
+      for (int k = L_CELLS - 2; k >= 0; --k) acc = f_add(acc, f_mul(s.l_gerr[g][k], nrm[k]));
+      s.l_red[8 + g] = f_div(acc, (float)L_CELLS);
     }
     BlockSync();
-    {
-      int q = 0;
-      for (int t = tid; t < 3 * L_CELLS; t += NT, ++q) {
-        const int g = t / L_CELLS, i = t - g * L_CELLS;
-        s.l_gerr[g][i] = newerr[q];
-        errh[((size_t)g * L_HORIZON + ep) * L_CELLS + i] = newerr[q];
-      }
+    for (int t = tid; t < 3 * L_CELLS; t += NT) {
+      const int g = t / L_CELLS, i = t - g * L_CELLS;
+      const float nrm = A.at<float>(L.l_norm)[((size_t)g * L_HORIZON + ep) * L_CELLS + i];
+      const float ne = f_sub(s.l_gerr[g][i], f_mul(s.l_red[8 + g], nrm));
+      s.l_gerr[g][i] = ne;
+      errh[((size_t)g * L_HORIZON + ep) * L_CELLS + i] = ne;
     }
     BlockSync();
     if (tid < L_CELLS) {
@@ -511,9 +568,10 @@ GMX_DEV void LstmBptt(StreamSmem& s, const Arena& A, const StreamParams& P, int 
       float stored = s.l_stored_err[i];
       if (ep > 0) {  // stored_error[i] += sum_j err[j] * W[j][512 + i], gates in order (lstm-layer.cpp:331-339)
         for (int g = 0; g < 3; ++g) {
-          const float* wr = W + ((size_t)g * L_ROW + 512 + i) * L_CELLS;
+          const float* wt = Wt + (size_t)g * L_CELLS * L_CELLS + i;
           float f = 0.0f;
-          for (int j = 0; j < L_CELLS; ++j) f = f_add(f, f_mul(s.l_gerr[g][j], wr[j]));
+#pragma unroll 10
+          for (int j = 0; j < L_CELLS; ++j) f = f_add(f, f_mul(s.l_gerr[g][j], wt[j * L_CELLS]));
           stored = f_add(stored, f);
         }
       }
@@ -552,6 +610,7 @@ GMX_DEV void LstmBptt(StreamSmem& s, const Arena& A, const StreamParams& P, int 
   for (int i = tid; i < 256; i += NT) head[i] = 0xFF;
   BlockSync();
   if (tid == 0)
+#pragma unroll 1
     for (int ep = 0; ep < L_HORIZON; ++ep) { const int sy = s.l_symin[ep]; nxt[ep] = head[sy]; head[sy] = (uint8_t)ep; }
   BlockSync();
   for (int q = tid; q < 3 * L_NOUT * L_CELLS; q += NT) {
@@ -607,7 +666,7 @@ GMX_DEV void LstmBptt(StreamSmem& s, const Arena& A, const StreamParams& P, int 
 }
 
 // Lstm::Perceive (lstm.cpp:52-89) on the 8th bit of a byte.
-template <int NT>
+template <int NT, bool PROF>
 GMX_DEV void LstmPerceive(StreamSmem& s, const Arena& A, const StreamParams& P, uint32_t byte, int tid) {
   const ArenaLayout& L = *A.L;
   const uint32_t cur = s.l_epoch;
@@ -618,7 +677,7 @@ GMX_DEV void LstmPerceive(StreamSmem& s, const Arena& A, const StreamParams& P, 
     // input symbol of epoch ep = byte perceived before it (lstm.cpp:71-74)
     for (int ep = tid; ep < L_HORIZON; ep += NT) s.l_symin[ep] = ep == 0 ? (uint8_t)s.l_old_input : s.l_hist[ep - 1];
     BlockSync();
-    LstmBptt<NT>(s, A, P, tid);
+    LstmBptt<NT, PROF>(s, A, P, tid);
   }
   // output layer: copy the previous epoch's layer, then one SGD step (lstm.cpp:81-88)
   const float* wl = A.at<float>(L.l_wout) + (size_t)last * L_HID * L_NOUT;
@@ -627,7 +686,7 @@ GMX_DEV void LstmPerceive(StreamSmem& s, const Arena& A, const StreamParams& P, 
   for (int i = tid; i < L_NOUT; i += NT) {
     const float err = (uint32_t)i == byte ? f_sub(s.lprob[i], 1.0f) : s.lprob[i];
     const float le = f_mul(lr, err);
-#pragma unroll 3
+#pragma unroll 17
     for (int j = 0; j < L_HID; ++j) wc[j * L_NOUT + i] = f_sub(wl[j * L_NOUT + i], f_mul(le, s.l_hidden[j]));
   }
   BlockSync();
@@ -638,7 +697,7 @@ GMX_DEV void LstmPerceive(StreamSmem& s, const Arena& A, const StreamParams& P, 
 // lstm-model.cpp:36-47): node = recent_bits (1..255) covers [bot, top]; num = sum(mid+1..top) from
 // 0.0f ascending, denom continues from num over bot..mid. All 255 nodes are evaluated at the byte
 // boundary so the per-bit step is a lookup.
-GMX_DEV inline void IntervalNode(const float* probs, int node, float* val, uint8_t* flag) {
+static GMX_DEV GMX_NOINLINE void IntervalNode(const float* probs, int node, float* val, uint8_t* flag) {
   int level = 31 - __clz(node);
   const int width = 256 >> level;
   const int bot = (node - (1 << level)) * width;
@@ -658,24 +717,57 @@ GMX_DEV inline void IntervalNode(const float* probs, int node, float* val, uint8
   }
 }
 
+// L2 prefetch of the pool record a mixer's gate will select. which = 0: with the contexts as they are now
+// (byte-level gates, called at the byte boundary before the swap); which = 1/2: the bit-level gates'
+// contexts after the next bit turns out 0/1 (called one bit ahead).
+GMX_DEV inline void PrefetchMixerSet(const StreamSmem& s, const Arena& A, int m, int which) {
+  const ArenaLayout& L = *A.L;
+  const int cid = s.T.mixer[m].ctx;
+  const bool bit_level = cid == C_SLPR || cid == C_LBPR || cid == C_BIT_CONTEXT;
+  uint32_t c;
+  if (which == 0) {
+    if (bit_level || cid == C_LONGEST || cid == C_ZERO || cid == C_LSTM) return;
+    c = s.ctx[cid];
+  } else {
+    const uint32_t bc = s.ctx[C_BIT_CONTEXT];
+    if (!bit_level || bc >= 127) return;
+    const uint32_t nbc = 2 * bc + which;  // bit_context after the next bit
+    c = cid == C_BIT_CONTEXT ? nbc : cid == C_LBPR ? (s.ctx[C_LAST_BYTE] << 8) + nbc : (s.ctx[C_RB1] << 8) + nbc;
+  }
+  const uint32_t nid = A.at<uint32_t>(L.mix_dir[m])[c & ((1u << s.T.mixer[m].log2) - 1)];
+  if (nid) {
+    const float* rec = A.at<float>(L.mix_pool) + (size_t)nid * L.mix_set_stride;
+    const int bytes = (MixerNW(m) + 2) * 4;
+    for (int o = 0; o < bytes; o += 128) PrefetchL2((const char*)rec + o);
+  }
+}
+
 // ---- everything that only happens when a new byte has been perceived (recent_bits == 1) ----------
-template <int NT>
+template <int NT, bool PROF>
 GMX_DEV void ByteBoundary(StreamSmem& s, const Arena& A, const StreamParams& P, int tid) {
   const ArenaLayout& L = *A.L;
   const uint32_t last_byte = s.ctx[C_LAST_BYTE];
+  // (0) the LSTM forward pass streams 184 KB of gate weights and the 52 KB output layer of this epoch
+  // slot from HBM: start them towards L2 now, they are needed after the PPMd update.
+  if (tid < NT - 32) {
+    const float* W = A.at<float>(L.l_w);
+    for (int g = 0; g < 3; ++g)
+      PrefetchRange(W + ((size_t)g * L_ROW + L_NOUT) * L_CELLS, L_NIN * L_CELLS * 4, tid, NT - 32);
+    PrefetchRange(A.at<float>(L.l_wout) + (size_t)s.l_epoch * L_HID * L_NOUT, L_HID * L_NOUT * 4, tid, NT - 32);
+  }
   // (1) contexts: intervals, hashed skip contexts, indirect-hash tables; PPMd on its own thread.
   if (tid < 9) {  // IntervalContext::Predict interval-context.cpp:17-23
-    const IntervalSpec sp = kInterval[tid];
+    const IntervalSpec sp = s.T.interval[tid];
     s.ctx[C_IV0 + tid] = sp.mask & ((s.ctx[C_IV0 + tid] << sp.shift) + (last_byte >> sp.div_log2));
   } else if (tid >= 32 && tid < 52) {  // SkipContext::Predict skip-context.cpp:9-19
-    const SkipSpec sp = kSkip[tid - 32];
+    const SkipSpec sp = s.T.skip[tid - 32];
     uint64_t c = 0;
     for (int k = 0; k < sp.n; ++k) c = (c << 8) + RecentByte(s, sp.b[k]);
     const int id = tid - 32;
     s.ctx[id < 5 ? C_H2 + id : C_SK0 + (id - 5)] = Murmur64(c);
   } else if (tid >= 64 && tid < 64 + NIH) {  // IndirectHash::Predict indirect-hash.cpp:16-31
     const int k = tid - 64;
-    const IHSpec sp = kIH[k];
+    const IHSpec sp = s.T.ih[k];
     const uint32_t mask = (1u << sp.log2) - 1;
     const uint64_t inner_mod = 1ull << (8 * (sp.inner_order - 1)), outer_mod = 1ull << (8 * (sp.outer_order - 1));
     const uint64_t oc = ((s.ih_outer[k] % outer_mod) << 8) + last_byte;
@@ -712,7 +804,7 @@ GMX_DEV void ByteBoundary(StreamSmem& s, const Arena& A, const StreamParams& P, 
   if (tid >= 80 && tid < 80 + NIND) {  // (the row keyed by lstm_prediction_context is redone below)
     const int k = tid - 80;
     const uint32_t M = L.ind_size[k];
-    const uint32_t base = (s.ctx[kInd[k].ctx] << 8) % M;
+    const uint32_t base = (s.ctx[s.T.ind[k].ctx] << 8) % M;
     s.ind_base[k] = base;
   }
   BlockSync();
@@ -724,14 +816,17 @@ GMX_DEV void ByteBoundary(StreamSmem& s, const Arena& A, const StreamParams& P, 
     // prefetch: 41 tables x 5 lines of 128 B cover the 510-byte row
     for (int t = tid - 1; t < NIND * 5; t += NT - 1) {
       const int k = t / 5, ln = t - k * 5;
-      if (L.ind_sid[k]) continue;
+      if (L.ind_sid[k]) {  // sparse: the probe start of the row's first slot (bit_context 0)
+        if (ln == 0) PrefetchL2(A.map().tab + (SparseHash(SparseKey(L.ind_sid[k], s.ind_base[k])) & L.sparse_mask));
+        continue;
+      }
       const uint32_t M = L.ind_size[k];
       uint32_t slot = s.ind_base[k] + ln * 64;
       if (slot >= M) slot -= M;
-#if defined(__CUDA_ARCH__)
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(A.at<uint16_t>(L.ind_tab[k]) + slot));
-#endif
+      PrefetchL2(A.at<uint16_t>(L.ind_tab[k]) + slot);
     }
+    // weight sets the byte-level gates will select at this boundary: bring their pool records to L2
+    if (tid >= 64 && tid < 64 + NMIX) PrefetchMixerSet(s, A, tid - 64, 0);
   }
   BlockSync();
   {
@@ -769,14 +864,14 @@ GMX_DEV void ByteBoundary(StreamSmem& s, const Arena& A, const StreamParams& P, 
     }
     s.ctx[C_LSTM] = bv > 0.0f ? bi : 0;
     for (int k = 0; k < NIND; ++k)
-      if (kInd[k].ctx == C_LSTM) s.ind_base[k] = (s.ctx[C_LSTM] << 8) % L.ind_size[k];
+      if (s.T.ind[k].ctx == C_LSTM) s.ind_base[k] = (s.ctx[C_LSTM] << 8) % L.ind_size[k];
   }
   BlockSync();
   GMX_PROF(3);
 }
 
 // ---- Predictor::Predict (predictor.cpp:360-376) --------------------------------------------------
-template <int NT>
+template <int NT, bool PROF>
 GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, int tid) {
   const ArenaLayout& L = *A.L;
   if (tid == 0) {  // BasicContexts::Predict basic-contexts.cpp:21-40
@@ -803,7 +898,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
   }
   BlockSync();
   GMX_PROF(14);
-  if (s.bb) ByteBoundary<NT>(s, A, P, tid);
+  if (s.bb) ByteBoundary<NT, PROF>(s, A, P, tid);
   const uint32_t bitctx = s.ctx[C_BIT_CONTEXT];
   const bool zero_inactive = s.analysis != 0;  // predictor.cpp:362-365
   if (tid < NIND) {  // Indirect::Predict indirect.cpp:28-45
@@ -823,9 +918,17 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     }
     s.ind_slot[k] = slot;
     s.ind_state[k] = (uint16_t)e;
+    if (sid && bitctx < 127) {  // both slots the next bit can select: start their probes' sectors towards L2
+      uint32_t nslot = s.ind_base[k] + 2 * bitctx + 1;
+      if (nslot >= M) nslot -= M;
+      const SparseMap Mp = A.map();
+      PrefetchL2(Mp.tab + (SparseHash(SparseKey(sid, nslot)) & Mp.mask));
+      if (++nslot >= M) nslot -= M;
+      PrefetchL2(Mp.tab + (SparseHash(SparseKey(sid, nslot)) & Mp.mask));
+    }
     const uint32_t ns = e & 0xff, rm = e >> 8;
     const float* pr = A.at<float>(L.ind_pred) + k * 512;
-    const int pi = kInd[k].pred;
+    const int pi = s.T.ind[k].pred;
     if (ns != 255) { const float p = pr[ns]; s.preds[pi] = p; s.act[pi] = p != 0.0f; }
     else { s.act[pi] = 0; if (zero_inactive) s.preds[pi] = 0.0f; }
     if (rm != 0) { const float p = pr[256 + rm]; s.preds[pi + 1] = p; s.act[pi + 1] = p != 0.0f; }
@@ -843,7 +946,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
       uint32_t cm = s.m_cur[k];
       if (s.hist_len != 0 && cm == s.hist_len - 1) len = 0;
       if (len < 8) {
-        const uint32_t idx = s.ctx[kMatch[k].ctx] & ((1u << kMatch[k].log2) - 1);
+        const uint32_t idx = s.ctx[s.T.match[k].ctx] & ((1u << s.T.match[k].log2) - 1);
         cm = L.match_sid[k] ? SparseGet(A.map(), SparseKey(L.match_sid[k], idx)) : A.at<uint32_t>(L.match_tab[k])[idx];
       } else ++cm;
       if (s.hist_len != 0) {
@@ -864,6 +967,10 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
       s.act[pi] = 0;
       if (zero_inactive) s.preds[pi] = 0.0f;
     }
+  } else if (tid >= 98 && s.recent_bits >= 128) {
+    // last bit of the byte: Lstm::Perceive will copy + update the output layer of the epoch slot just used
+    const uint32_t last = s.l_epoch == 0 ? L_HORIZON - 1 : s.l_epoch - 1;
+    PrefetchRange(A.at<float>(L.l_wout) + (size_t)last * L_HID * L_NOUT, L_HID * L_NOUT * 4, tid - 98, NT - 98);
   } else if (tid == 96 || tid == 97) {  // per-bit part of ModPPMD / LstmModel::Predict
     const int which = tid - 96;
     const int node = s.recent_bits;
@@ -877,13 +984,14 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
   if (tid < NMIX) {
     const int m = tid;
     uint32_t c;
-    if (kMixer[m].ctx == C_LONGEST) {  // longest_match = max(match_length / 32) (match.cpp:71-73)
+    if (s.T.mixer[m].ctx == C_LONGEST) {  // longest_match = max(match_length / 32) (match.cpp:71-73)
       c = 0;
+#pragma unroll 1
       for (int k = 0; k < NMATCH; ++k) { const uint32_t v = s.m_len[k] >> 5; c = v > c ? v : c; }
     } else {
-      c = s.ctx[kMixer[m].ctx];
+      c = s.ctx[s.T.mixer[m].ctx];
     }
-    const uint32_t idx = c & ((1u << kMixer[m].log2) - 1);
+    const uint32_t idx = c & ((1u << s.T.mixer[m].log2) - 1);
     if (idx != s.set_idx[m]) {  // queue the swap: old set goes back to the pool, new one (if any) is staged
       const uint32_t q = atomicAdd(&s.nswap, 1u);
       s.swap_m[q] = (uint8_t)m;
@@ -895,22 +1003,13 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     uint32_t c = 0;
     for (int k = 0; k < NMATCH; ++k) { const uint32_t v = s.m_len[k] >> 5; c = v > c ? v : c; }
     s.ctx[C_LONGEST] = c;
+  } else if (tid >= 96 && tid < 128) {
+    // the weight sets the bit-level gates can select for the NEXT bit (both values of the bit)
+    for (int j = tid - 96; j < 2 * NMIX; j += 32) PrefetchMixerSet(s, A, j >> 1, 1 + (j & 1));
   } else if (tid >= 64 && tid < 96) {
-    // ascending list of the active predictions: Mixer::Predict sums exactly these, in index order
-    const int lane = tid - 64;
-    uint32_t base = 0;
-    for (int r = 0; r < 3; ++r) {
-      const int i = r * 32 + lane;
-      const bool on = i < NPRED && s.act[i] != 0;
-      const uint32_t mask = __ballot_sync(0xffffffffu, on);
-      if (on) {
-        const uint32_t pos = base + __popc(mask & ((1u << lane) - 1u));
-        s.act_idx[pos] = (uint8_t)i;
-        s.act_x[pos] = s.preds[i];
-      }
-      base += __popc(mask);
-    }
-    if (lane == 0) s.act_n = base;
+    // layer-0 input vector: the active predictions, inactive ones as +0 (Mixer::Predict sums the active ones
+    // in index order; a +-0 product leaves the running sum unchanged, the sum itself is never -0)
+    for (int i = tid - 64; i < NPRED; i += 32) s.xe[i] = s.act[i] ? s.preds[i] : 0.0f;
   }
   BlockSync();
   // Swap staged weight sets, one queued mixer per round, one weight per thread: first all write-backs,
@@ -920,22 +1019,23 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     const uint32_t nswap = s.nswap;
     float* pool = A.at<float>(L.mix_pool);
     const uint32_t stride = L.mix_set_stride;
+#pragma unroll 1
     for (uint32_t r = 0; r < nswap; ++r) {
       const int m = s.swap_m[r];
       const uint32_t old = s.swap_old[r];
       if (old && tid < MixerNW(m) + 1) {
         float* rec = pool + (size_t)old * stride;
-        if (tid == 0) ((uint32_t*)rec)[0] = s.set_steps[m]; else rec[1 + tid] = s.w[m * WSTRIDE + tid - 1];
+        if (tid == 0) ((uint32_t*)rec)[0] = s.set_steps[m]; else rec[1 + tid] = s.w[WOff(m) + tid - 1];
       }
     }
-#pragma unroll 4
+#pragma unroll 1
     for (uint32_t r = 0; r < nswap; ++r) {
       const int m = s.swap_m[r];
       const uint32_t nid = s.swap_new[r];
       if (tid < MixerNW(m) + 1) {
         const float* rec = pool + (size_t)nid * stride;
         if (tid == 0) { s.set_steps[m] = nid ? ((const uint32_t*)rec)[0] : 0u; s.set_pool[m] = nid; }
-        else s.w[m * WSTRIDE + tid - 1] = nid ? rec[1 + tid] : 0.0f;
+        else s.w[WOff(m) + tid - 1] = nid ? rec[1 + tid] : 0.0f;
       }
     }
   }
@@ -946,11 +1046,21 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
   if (tid < 32) {
     const int lane = tid;
     if (lane == 0) s.nswap = 0;
-    const float* w = s.w + (lane < NL0 ? lane : 0) * WSTRIDE;
+    const float* w = s.w + (lane < NL0 ? lane : 0) * WSTRIDE0;
     float acc = 0.0f;
-    const int na = (int)s.act_n;
-#pragma unroll 8
-    for (int c = 0; c < na; ++c) acc = f_add(acc, f_mul(s.act_x[c], w[s.act_idx[c]]));
+    {
+      const float4* x4 = (const float4*)s.xe;
+      const float4* w4 = (const float4*)w;
+#pragma unroll 1
+      for (int q = 0; q < NPRED / 4; ++q) {
+        const float4 x = x4[q], v = w4[q];
+        acc = f_add(acc, f_mul(x.x, v.x)); acc = f_add(acc, f_mul(x.y, v.y));
+        acc = f_add(acc, f_mul(x.z, v.z)); acc = f_add(acc, f_mul(x.w, v.w));
+      }
+#pragma unroll
+      for (int i = NPRED / 4 * 4; i < NPRED; ++i) acc = f_add(acc, f_mul(s.xe[i], w[i]));
+    }
+#pragma unroll 1
     for (int j = 0; j < NL0 - 1; ++j) {
       const float oj = __shfl_sync(0xffffffffu, acc, j);
       if (lane > j && lane < NL0) acc = f_add(acc, f_mul(oj, w[NPRED + j]));
@@ -958,12 +1068,21 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     if (lane < NL0) s.l0_out[lane] = acc;
     __syncwarp();
     const float skip = s.preds[P_LSTM];
-    const float* w1 = s.w + (NL0 + (lane < NL1 ? lane : 0)) * WSTRIDE;
+    const float* w1 = s.w + NL0 * WSTRIDE0 + (lane < NL1 ? lane : 0) * WSTRIDE1;
     acc = 0.0f;
-#pragma unroll
-    for (int i = 0; i < NL0; ++i) acc = f_add(acc, f_mul(s.l0_out[i], w1[i]));
+    {
+      const float4* x4 = (const float4*)s.l0_out;
+      const float4* w4 = (const float4*)w1;
+#pragma unroll 1
+      for (int q = 0; q < NL0 / 4; ++q) {
+        const float4 x = x4[q], v = w4[q];
+        acc = f_add(acc, f_mul(x.x, v.x)); acc = f_add(acc, f_mul(x.y, v.y));
+        acc = f_add(acc, f_mul(x.z, v.z)); acc = f_add(acc, f_mul(x.w, v.w));
+      }
+    }
     // a layer-1 output is complete (skip connection added last, weights[num_layer0 + output_index],
     // mixer.cpp:77-83) before the next layer-1 neuron reads it
+#pragma unroll 1
     for (int j = 0; j < NL1; ++j) {
       if (lane == j) acc = f_add(acc, f_mul(skip, w1[NL0 + j]));
       if (j < NL1 - 1) {
@@ -974,12 +1093,16 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     if (lane < NL1) s.l1_out[lane] = acc;
     __syncwarp();
     if (lane == 0) {
-      const float* w2 = s.w + (NL0 + NL1) * WSTRIDE;
+      const float* w2 = s.w + NL0 * WSTRIDE0 + NL1 * WSTRIDE1;
       float p = 0.0f;
-#pragma unroll
-      for (int i = 0; i < NL0; ++i) p = f_add(p, f_mul(s.l0_out[i], w2[i]));
-#pragma unroll
-      for (int i = 0; i < NL1; ++i) p = f_add(p, f_mul(s.l1_out[i], w2[NL0 + i]));
+      const float4* x4 = (const float4*)s.l0_out;   // l0_out[24] then l1_out[8]
+      const float4* w4 = (const float4*)w2;
+#pragma unroll 1
+      for (int q = 0; q < (NL0 + NL1) / 4; ++q) {
+        const float4 x = x4[q], v = w4[q];
+        p = f_add(p, f_mul(x.x, v.x)); p = f_add(p, f_mul(x.y, v.y));
+        p = f_add(p, f_mul(x.z, v.z)); p = f_add(p, f_mul(x.w, v.w));
+      }
       p = f_add(p, f_mul(skip, w2[NL0 + NL1]));
       s.final_out = p;
       float prob = Logistic(p);
@@ -994,7 +1117,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
 }
 
 // ---- Predictor::Learn (predictor.cpp:383-387) ----------------------------------------------------
-template <int NT>
+template <int NT, bool PROF>
 GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int tid) {
   const ArenaLayout& L = *A.L;
   const int bit = s.new_bit;
@@ -1018,14 +1141,14 @@ GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int 
     decay = (float)d_mul((double)decay, d_sub(1.5, d_div((double)dsteps, (double)mx)));
     const float out = m < NL0 ? s.l0_out[m] : m < NL0 + NL1 ? s.l1_out[m - NL0] : s.final_out;
     const float p = Logistic(out);
-    s.upd[m] = f_mul(f_mul(decay, kMixer[m].lr), f_sub(p, fbit));
+    s.upd[m] = f_mul(f_mul(decay, s.T.mixer[m].lr), f_sub(p, fbit));
     const uint32_t nsteps = dsteps + 1;
     s.set_steps[m] = nsteps;
     if (nsteps > mx) s.max_steps[m] = nsteps;
     s.shrink[m] = (nsteps & 1023u) == 0;
   } else if (tid >= 64 && tid < 64 + NIND) {  // Indirect::Learn indirect.cpp:47-70
     const int k = tid - 64;
-    const float lr = kInd[k].slow_lr ? f_div(1.0f, 200.0f) : (float)0.02;
+    const float lr = s.T.ind[k].slow_lr ? f_div(1.0f, 200.0f) : (float)0.02;
     float* pr = A.at<float>(L.ind_pred) + k * 512;
     const uint32_t e = s.ind_state[k];
     uint32_t ns = e & 0xff;
@@ -1039,7 +1162,7 @@ GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int 
     uint32_t nrm;
     if (bit == 0) nrm = rm < 127 ? rm + 1 : rm >= 128 ? 1 : rm;
     else nrm = rm < 128 ? 128 : rm < 255 ? rm + 1 : rm;
-    const uint32_t nst = kNonstationary[ns * 2 + bit] | (nrm << 8);
+    const uint32_t nst = s.T.nonstationary[ns * 2 + bit] | (nrm << 8);
     const uint32_t sid = L.ind_sid[k];
     if (sid) {
       uint32_t slot = s.ind_base[k] + s.ctx[C_BIT_CONTEXT];
@@ -1062,7 +1185,7 @@ GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int 
       *mp = f_add(v, f_mul(f_sub((float)hit, v), rate));
     }
     if (s.recent_bits >= 128 && longest < 2) {
-      const uint32_t idx = s.ctx[kMatch[k].ctx] & ((1u << kMatch[k].log2) - 1);
+      const uint32_t idx = s.ctx[s.T.match[k].ctx] & ((1u << s.T.match[k].log2) - 1);
       if (L.match_sid[k]) SparseSet(A.map(), &s.sparse_used, L.sparse_limit, &s.error, SparseKey(L.match_sid[k], idx), hist_after - 1);
       else A.at<uint32_t>(L.match_tab[k])[idx] = hist_after - 1;
     }
@@ -1074,12 +1197,14 @@ GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int 
   GMX_PROF(8);
   // Mixer weight updates (mixer.cpp:128-175): w -= update * x over exactly the inputs used by
   // Predict, then the (1 - 3e-6) shrink every 1024 steps of the set.
+#pragma unroll 1
   for (int m = tid >> 5; m < NMIX; m += NT / 32) {
     const int lane = tid & 31;
     const int nw = MixerNW(m);
     const float upd = s.upd[m];
     const bool shrink = s.shrink[m] != 0;
-    float* w = s.w + m * WSTRIDE;
+    float* w = s.w + WOff(m);
+#pragma unroll 1
     for (int i = lane; i < nw; i += 32) {
       float x; bool use;
       if (m < NL0) {
@@ -1100,7 +1225,7 @@ GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int 
   if (tid == 0) { s.steps++; s.hist_len = hist_after; }
   BlockSync();
   GMX_PROF(9);
-  if (byte_done) LstmPerceive<NT>(s, A, P, (uint32_t)(cur - 256), tid);  // LstmModel::Learn lstm-model.cpp:50-59
+  if (byte_done) LstmPerceive<NT, PROF>(s, A, P, (uint32_t)(cur - 256), tid);  // LstmModel::Learn lstm-model.cpp:50-59
 }
 
 // ---- coder (encoder.cpp:8-34, decoder.cpp:3-39) ---------------------------------------------------
@@ -1116,7 +1241,7 @@ GMX_DEV inline uint32_t GetByte(StreamSmem& s, const uint8_t* in) {  // Decoder:
   return b;
 }
 
-GMX_DEV inline void Trace(StreamSmem& s, const StreamParams& P, uint64_t bit_index) {
+static GMX_DEV GMX_NOINLINE void Trace(StreamSmem& s, const StreamParams& P, uint64_t bit_index) {
   if (P.bit_trace) {
     const uint32_t p16 = Discretize(s.prob);
     P.bit_trace[bit_index] = (uint64_t)f2u(s.prob) | ((uint64_t)p16 << 32);
@@ -1143,12 +1268,12 @@ GMX_DEV inline void WriteUsage(const StreamSmem& s, const Arena& A, const Stream
 }
 
 // runner_utils::Compress (runner-utils.cpp:43-67) incl. the 5-byte header of RunCompression (:109).
-template <int NT>
+template <int NT, bool PROF>
 GMX_DEV void CompressStream(StreamSmem& s, const Arena& A, const StreamParams& P, uint32_t sid, int tid) {
   const uint8_t* in = P.in + P.in_off[sid];
   const uint64_t n = P.in_off[sid + 1] - P.in_off[sid];
   uint8_t* out = P.out + P.out_off[sid];
-  InitStream<NT>(s, A, P, tid);
+  InitStream<NT, PROF>(s, A, P, tid);
   if (tid == 0) {
     s.out_pos = 0; s.out_cap = P.out_off[sid + 1] - P.out_off[sid];
     s.analysis = (8 * n / 1000) > 0;  // EnableAnalysis(8*n/1000) -> predictions zeroed every bit
@@ -1156,11 +1281,13 @@ GMX_DEV void CompressStream(StreamSmem& s, const Arena& A, const StreamParams& P
   }
   BlockSync();
   const bool tracing = sid == 0;
+#pragma unroll 1
   for (uint64_t pos = 0; pos < n; ++pos) {
     const uint32_t c = in[pos];
+#pragma unroll 1
     for (int j = 7; j >= 0; --j) {
       const int bit = (c >> j) & 1;
-      PredictBit<NT>(s, A, P, tid);
+      PredictBit<NT, PROF>(s, A, P, tid);
       if (tid == 0) {
         if (tracing) Trace(s, P, pos * 8 + (7 - j));
         const uint32_t p16 = Discretize(s.prob);
@@ -1172,7 +1299,7 @@ GMX_DEV void CompressStream(StreamSmem& s, const Arena& A, const StreamParams& P
       }
       BlockSync();
       GMX_PROF(7);
-      LearnBit<NT>(s, A, P, tid);
+      LearnBit<NT, PROF>(s, A, P, tid);
       if (s.error) break;
     }
     if (s.error) break;
@@ -1184,17 +1311,17 @@ GMX_DEV void CompressStream(StreamSmem& s, const Arena& A, const StreamParams& P
     P.out_len[sid] = s.out_pos;
     P.status[sid] = s.error;
     WriteUsage(s, A, P, sid);
-    if (P.prof) for (int i = 0; i < GMX_PROF_SLOTS; ++i) P.prof[(size_t)sid * GMX_PROF_SLOTS + i] = s.prof[i];
+    if (PROF && P.prof) for (int i = 0; i < GMX_PROF_SLOTS; ++i) P.prof[(size_t)sid * GMX_PROF_SLOTS + i] = s.prof[i];
   }
   BlockSync();
 }
 
 // runner_utils::Decompress (runner-utils.cpp:69-86) + ReadHeader (:29-36). Analysis is never on.
-template <int NT>
+template <int NT, bool PROF>
 GMX_DEV void DecompressStream(StreamSmem& s, const Arena& A, const StreamParams& P, uint32_t sid, int tid) {
   const uint8_t* in = P.in + P.in_off[sid];
   uint8_t* out = P.out + P.out_off[sid];
-  InitStream<NT>(s, A, P, tid);
+  InitStream<NT, PROF>(s, A, P, tid);
   if (tid == 0) {
     s.in_pos = 0; s.in_len = P.in_off[sid + 1] - P.in_off[sid];
     s.out_pos = 0; s.out_cap = P.out_off[sid + 1] - P.out_off[sid];
@@ -1207,9 +1334,11 @@ GMX_DEV void DecompressStream(StreamSmem& s, const Arena& A, const StreamParams&
   }
   BlockSync();
   const uint64_t n = s.out_cap;
+#pragma unroll 1
   for (uint64_t pos = 0; pos < n; ++pos) {
+#pragma unroll 1
     for (int j = 7; j >= 0; --j) {
-      PredictBit<NT>(s, A, P, tid);
+      PredictBit<NT, PROF>(s, A, P, tid);
       if (tid == 0) {  // Decoder::Decode decoder.cpp:19-39
         const uint32_t p16 = Discretize(s.prob);
         const uint32_t r = s.x2 - s.x1;
@@ -1222,7 +1351,7 @@ GMX_DEV void DecompressStream(StreamSmem& s, const Arena& A, const StreamParams&
       }
       BlockSync();
       GMX_PROF(7);
-      LearnBit<NT>(s, A, P, tid);
+      LearnBit<NT, PROF>(s, A, P, tid);
       if (s.error) break;
     }
     if (s.error) break;
@@ -1231,7 +1360,7 @@ GMX_DEV void DecompressStream(StreamSmem& s, const Arena& A, const StreamParams&
   if (tid == 0) {
     P.out_len[sid] = s.error ? 0 : n; P.status[sid] = s.error;
     WriteUsage(s, A, P, sid);
-    if (P.prof) for (int i = 0; i < GMX_PROF_SLOTS; ++i) P.prof[(size_t)sid * GMX_PROF_SLOTS + i] = s.prof[i];
+    if (PROF && P.prof) for (int i = 0; i < GMX_PROF_SLOTS; ++i) P.prof[(size_t)sid * GMX_PROF_SLOTS + i] = s.prof[i];
   }
   BlockSync();
 }
@@ -1239,12 +1368,25 @@ GMX_DEV void DecompressStream(StreamSmem& s, const Arena& A, const StreamParams&
 // ---- kernel entry: persistent CTAs, one stream at a time, ids from an atomic queue ---------------
 enum : int { MODE_COMPRESS = 0, MODE_DECOMPRESS = 1 };
 
-template <int NT, int MODE, int MINB>
+template <int NT, int MODE, int MINB, bool PROF>
 __global__ void __launch_bounds__(NT, MINB) StreamKernel(StreamParams P) {
   __shared__ StreamSmem s;
   __shared__ uint32_t next_stream;
   const int tid = (int)threadIdx.x;
-  Arena A{P.arenas + (uint64_t)blockIdx.x * P.arena_stride, P.layout};
+  {
+    const uint32_t* src = (const uint32_t*)P.layout;
+    uint32_t* dst = (uint32_t*)&s.T.L;
+    for (int i = tid; i < (int)(sizeof(ArenaLayout) / 4); i += NT) dst[i] = src[i];
+    for (int i = tid; i < NIND; i += NT) s.T.ind[i] = kInd[i];
+    for (int i = tid; i < 20; i += NT) s.T.skip[i] = kSkip[i];
+    for (int i = tid; i < 9; i += NT) s.T.interval[i] = kInterval[i];
+    for (int i = tid; i < NIH; i += NT) s.T.ih[i] = kIH[i];
+    for (int i = tid; i < NMATCH; i += NT) s.T.match[i] = kMatch[i];
+    for (int i = tid; i < NMIX; i += NT) s.T.mixer[i] = kMixer[i];
+    for (int i = tid; i < 512; i += NT) s.T.nonstationary[i] = kNonstationary[i];
+  }
+  BlockSync();
+  Arena A{P.arenas + (uint64_t)blockIdx.x * P.arena_stride, &s.T.L};
   for (;;) {
     if (tid == 0) next_stream = atomicAdd(P.queue, 1u);
     BlockSync();
@@ -1252,8 +1394,8 @@ __global__ void __launch_bounds__(NT, MINB) StreamKernel(StreamParams P) {
     BlockSync();
     if (q >= P.n_streams) break;
     const uint32_t sid = P.ids ? P.ids[q] : q;
-    if (MODE == MODE_COMPRESS) CompressStream<NT>(s, A, P, sid, tid);
-    else DecompressStream<NT>(s, A, P, sid, tid);
+    if (MODE == MODE_COMPRESS) CompressStream<NT, PROF>(s, A, P, sid, tid);
+    else DecompressStream<NT, PROF>(s, A, P, sid, tid);
   }
 }
 

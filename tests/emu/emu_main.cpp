@@ -54,8 +54,8 @@ retry:
   P.bit_trace = bit_trace.empty() ? nullptr : bit_trace.data();
   P.pred_trace = pred_trace.empty() ? nullptr : pred_trace.data();
   cuda_emu::RunBlock(EMU_NT, 0, 1, [&] {
-    if (comp) gmx::StreamKernel<EMU_NT, gmx::MODE_COMPRESS, 1>(P);
-    else gmx::StreamKernel<EMU_NT, gmx::MODE_DECOMPRESS, 1>(P);
+    if (comp) gmx::StreamKernel<EMU_NT, gmx::MODE_COMPRESS, 1, false>(P);
+    else gmx::StreamKernel<EMU_NT, gmx::MODE_DECOMPRESS, 1, false>(P);
   });
   if (!roomy && (status[0] == gmx::GMX_ERR_PPMD_ARENA || status[0] == gmx::GMX_ERR_MIXER_POOL || status[0] == gmx::GMX_ERR_SPARSE_FULL)) {
     fprintf(stderr, "status %u: retrying in a roomy arena (as the host library does)\n", status[0]);
