@@ -58,6 +58,12 @@ def load_library():
     lib.gmx_device_sm_count.argtypes = [C.c_void_p]
     lib.gmx_set_profile.argtypes = [C.c_void_p, C.c_int]
     lib.gmx_get_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.gmx_pred_new.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+    lib.gmx_pred_free.argtypes = [C.c_void_p]
+    lib.gmx_pred_enable_analysis.argtypes = [C.c_void_p, C.c_int]
+    lib.gmx_pred_predict.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    lib.gmx_pred_perceive.argtypes = [C.c_void_p, C.c_int]
+    lib.gmx_pred_learn.argtypes = [C.c_void_p]
     lib.gmx_get_usage.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     lib.gmx_selftest_math.argtypes = [C.c_void_p, C.c_uint32, u64p, u32p]
     _LIB = lib
@@ -75,6 +81,35 @@ def _pack(streams):
     np.cumsum(lens, out=off[1:])
     buf = np.frombuffer(b"".join(bytes(s) for s in streams), dtype=np.uint8).copy() if sum(lens) else np.zeros(1, np.uint8)
     return buf, off
+
+
+class Predictor:
+    """One stream stepped bit by bit: the reference's Predictor interface (src/predictor.h:20-38)."""
+
+    def __init__(self, ctx, max_stream_len):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx._check(ctx.lib.gmx_pred_new(ctx.h, max_stream_len, C.byref(h)), "gmx_pred_new")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.gmx_pred_free(self.h)
+            self.h = None
+
+    def enable_analysis(self, on=True):
+        self.ctx._check(self.ctx.lib.gmx_pred_enable_analysis(self.h, int(on)), "gmx_pred_enable_analysis")
+
+    def predict(self):
+        p = C.c_float()
+        self.ctx._check(self.ctx.lib.gmx_pred_predict(self.h, C.byref(p)), "gmx_pred_predict")
+        return p.value
+
+    def perceive(self, bit):
+        self.ctx._check(self.ctx.lib.gmx_pred_perceive(self.h, int(bit)), "gmx_pred_perceive")
+
+    def learn(self):
+        self.ctx._check(self.ctx.lib.gmx_pred_learn(self.h), "gmx_pred_learn")
 
 
 class Context:

@@ -6,9 +6,10 @@ import sys
 ROOT = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(ROOT, "csrc")
 LIB = os.path.join(ROOT, "lib", "libgmix_b200.so")
-SOURCES = ["host.cu", "kernel_compress.cu", "kernel_decompress.cu", "kernel_compress_prof.cu"]
-DEPS = ["host.cu", "kernel_compress.cu", "kernel_decompress.cu", "kernel_compress_prof.cu", "kernels.h", "stream_kernel.cuh", "ppmd.cuh", "dmath.cuh", "spec.cuh", "layout.h", "nonstationary.inc",
-        os.path.join("..", "..", "include", "gmix_b200.h")]
+SOURCES = ["host.cu", "kernel_compress.cu", "kernel_decompress.cu", "kernel_compress_prof.cu", "kernel_step.cu"]
+DEPS = ["host.cu", "kernel_compress.cu", "kernel_decompress.cu", "kernel_compress_prof.cu", "kernel_step.cu", "kernels.h", "stream_kernel.cuh", "ppmd.cuh", "dmath.cuh", "spec.cuh", "layout.h", "nonstationary.inc",
+        os.path.join("..", "..", "include", "gmix_b200.h"), os.path.join("..", "host", "runner.cpp"), os.path.join("..", "host", "predictor.h"),
+        os.path.join("..", "host", "coder.h")]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
@@ -28,6 +29,8 @@ def _stale():
 def build_library(force=False, verbose=False):
     """Compile the CUDA library if it is missing or older than its sources. Returns the .so path."""
     if not force and not _stale():
+        if not os.path.exists(os.path.join(os.path.dirname(LIB), "gmixb200")):
+            build_host_tools()
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     objdir = os.path.join(ROOT, "lib", "obj")
@@ -55,7 +58,18 @@ def build_library(force=False, verbose=False):
     cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
     print("[gmix_b200] " + " ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True)
+    build_host_tools()
     return LIB
+
+
+def build_host_tools():
+    """C++ host layer above the C ABI: the gmixb200 runner (reference CLI mirror) and the profiler driver."""
+    libdir = os.path.dirname(LIB)
+    cxx = os.environ.get("CXX", "g++")
+    for src, exe in ((os.path.join(ROOT, "host", "runner.cpp"), "gmixb200"), (os.path.join(ROOT, "..", "scripts", "ncu_case.cpp"), "ncu_case")):
+        cmd = [cxx, "-std=c++17", "-O2", "-ffp-contract=off", "-o", os.path.join(libdir, exe), src, "-L" + libdir, "-lgmix_b200", "-Wl,-rpath,$ORIGIN"]
+        print("[gmix_b200] " + " ".join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True)
 
 
 if __name__ == "__main__":

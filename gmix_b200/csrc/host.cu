@@ -63,6 +63,19 @@ struct gmx_ctx {
   double last_ms = 0;
 };
 
+// One stream stepped bit by bit (the Predictor facade). Owns a worst-case-sized arena.
+struct gmx_pred {
+  gmx_ctx* ctx = nullptr;
+  gmx::ArenaLayout layout;
+  uint8_t* d_arena = nullptr;
+  gmx::ArenaLayout* d_layout = nullptr;
+  uint32_t* d_state = nullptr;
+  float* d_prob = nullptr;       // {prob, status}
+  int pending_bit = -1;
+  int analysis = 0;
+  uint64_t bits = 0, max_bits = 0;
+};
+
 namespace {
 
 int Fail(gmx_ctx* c, int code, const char* fmt, ...) {
@@ -87,6 +100,19 @@ int Reserve(gmx_ctx* c, DevBuf& b, size_t bytes) {
   size_t want = bytes < 256 ? 256 : bytes;
   GMX_CUDA(c, cudaMalloc(&b.p, want));
   b.cap = want;
+  return 0;
+}
+
+// decay table: one entry per bit step (mixer.cpp:111), shared by all streams of the ctx
+int EnsureDecay(gmx_ctx* c, uint64_t max_stream_len) {
+  const uint64_t need = max_stream_len * 8 + 16;
+  if (need <= c->decay_len) return 0;
+  gmx::FillDecayTable(c->h_decay, need);
+  if (c->d_decay) cudaFree(c->d_decay);
+  c->d_decay = nullptr;
+  GMX_CUDA(c, cudaMalloc(&c->d_decay, c->h_decay.size() * 4));
+  GMX_CUDA(c, cudaMemcpy(c->d_decay, c->h_decay.data(), c->h_decay.size() * 4, cudaMemcpyHostToDevice));
+  c->decay_len = (uint32_t)c->h_decay.size();
   return 0;
 }
 
@@ -349,15 +375,9 @@ int gmx_configure(gmx_ctx* c, uint64_t max_stream_len, uint32_t max_resident) {
   if (max_stream_len >= (1ull << 31)) return Fail(c, GMX_E_ARG, "streams of 2 GiB or more are not supported");
   FreeArenas(c);
   c->layout = gmx::MakeLayout(max_stream_len);
-  // decay table: one entry per bit step (mixer.cpp:111)
-  const uint64_t need = max_stream_len * 8 + 16;
-  if (need > c->decay_len) {
-    gmx::FillDecayTable(c->h_decay, need);
-    if (c->d_decay) cudaFree(c->d_decay);
-    c->d_decay = nullptr;
-    GMX_CUDA(c, cudaMalloc(&c->d_decay, c->h_decay.size() * 4));
-    GMX_CUDA(c, cudaMemcpy(c->d_decay, c->h_decay.data(), c->h_decay.size() * 4, cudaMemcpyHostToDevice));
-    c->decay_len = (uint32_t)c->h_decay.size();
+  {
+    int rc = EnsureDecay(c, max_stream_len);
+    if (rc) return rc;
   }
   int per_sm = 0;
   GMX_CUDA(c, gmx::OccupancyCompress(&per_sm));
@@ -444,6 +464,82 @@ int gmx_get_usage(gmx_ctx* c, uint32_t* out, uint32_t max_streams) {
   if (n == 0 || !c->b_usage.p) return 0;
   GMX_CUDA(c, cudaMemcpy(out, c->b_usage.p, (size_t)n * 32, cudaMemcpyDeviceToHost));
   return (int)n;
+}
+
+// ---- Predictor facade (reference src/predictor.h:20-38) -------------------------------------------
+static int PredStep(gmx_pred* p, int op, float* prob) {
+  gmx_ctx* c = p->ctx;
+  GMX_CUDA(c, cudaSetDevice(c->device));
+  gmx::StepParams Q;
+  memset(&Q, 0, sizeof(Q));
+  Q.P.arenas = p->d_arena; Q.P.arena_stride = p->layout.total; Q.P.layout = p->d_layout;
+  Q.P.lstm_init = c->d_lstm_init; Q.P.decay = c->d_decay; Q.P.decay_len = c->decay_len; Q.P.adam = c->d_adam;
+  Q.state = p->d_state; Q.op = op; Q.has_bit = p->pending_bit >= 0; Q.bit = p->pending_bit > 0; Q.analysis = p->analysis;
+  Q.prob_out = p->d_prob; Q.status_out = (uint32_t*)(p->d_prob + 1);
+  GMX_CUDA(c, gmx::LaunchStep(Q, c->stream));
+  c->launches += 1;
+  p->pending_bit = -1;
+  float host[2];
+  GMX_CUDA(c, cudaMemcpyAsync(host, p->d_prob, 8, cudaMemcpyDeviceToHost, c->stream));
+  GMX_CUDA(c, cudaStreamSynchronize(c->stream));
+  uint32_t st;
+  memcpy(&st, &host[1], 4);
+  if (st != 0) return Fail(c, GMX_E_STREAM, "predictor stream failed with status %u", st);
+  if (prob) *prob = host[0];
+  return 0;
+}
+
+int gmx_pred_new(gmx_ctx* c, uint64_t max_stream_len, gmx_pred** out) {
+  if (!c || !out) return GMX_E_ARG;
+  *out = nullptr;
+  GMX_CUDA(c, cudaSetDevice(c->device));
+  if (max_stream_len == 0 || max_stream_len >= (1ull << 31)) return Fail(c, GMX_E_ARG, "max_stream_len out of range");
+  int rc = EnsureDecay(c, max_stream_len);
+  if (rc) return rc;
+  gmx_pred* p = new gmx_pred();
+  p->ctx = c;
+  p->layout = gmx::MakeLayout(max_stream_len, true);
+  p->max_bits = max_stream_len * 8;
+  if (cudaMalloc(&p->d_arena, p->layout.total) != cudaSuccess || cudaMalloc(&p->d_layout, sizeof(gmx::ArenaLayout)) != cudaSuccess ||
+      cudaMalloc(&p->d_state, gmx::StepStateBytes()) != cudaSuccess || cudaMalloc(&p->d_prob, 8) != cudaSuccess ||
+      cudaMemcpy(p->d_layout, &p->layout, sizeof(gmx::ArenaLayout), cudaMemcpyHostToDevice) != cudaSuccess) {
+    gmx_pred_free(p);
+    return Fail(c, GMX_E_NOMEM, "cannot allocate a %llu MiB predictor arena: %s", (unsigned long long)(p->layout.total >> 20),
+                cudaGetErrorString(cudaGetLastError()));
+  }
+  rc = PredStep(p, gmx::STEP_INIT, nullptr);
+  if (rc) { gmx_pred_free(p); return rc; }
+  *out = p;
+  return 0;
+}
+void gmx_pred_free(gmx_pred* p) {
+  if (!p) return;
+  cudaSetDevice(p->ctx->device);
+  if (p->d_arena) cudaFree(p->d_arena);
+  if (p->d_layout) cudaFree(p->d_layout);
+  if (p->d_state) cudaFree(p->d_state);
+  if (p->d_prob) cudaFree(p->d_prob);
+  delete p;
+}
+int gmx_pred_enable_analysis(gmx_pred* p, int on) {
+  if (!p) return GMX_E_ARG;
+  p->analysis = on != 0;
+  return 0;
+}
+int gmx_pred_predict(gmx_pred* p, float* prob) {
+  if (!p || !prob) return GMX_E_ARG;
+  if (p->bits >= p->max_bits) return Fail(p->ctx, GMX_E_ARG, "predictor was created for %llu bits", (unsigned long long)p->max_bits);
+  return PredStep(p, gmx::STEP_PREDICT, prob);
+}
+int gmx_pred_perceive(gmx_pred* p, int bit) {
+  if (!p) return GMX_E_ARG;
+  p->pending_bit = bit != 0;
+  p->bits++;
+  return 0;
+}
+int gmx_pred_learn(gmx_pred* p) {
+  if (!p) return GMX_E_ARG;
+  return PredStep(p, gmx::STEP_LEARN, nullptr);
 }
 
 uint32_t gmx_resident_streams(const gmx_ctx* c) { return c ? c->last_grid : 0; }

@@ -144,7 +144,7 @@ struct StreamSmem {
   float ppm[256], lprob[256];          // byte distributions of PPMd and LSTM
   float node_ppm[256], node_lstm[256]; // Logit(p) of every node of the binary interval search
   uint8_t nflag_ppm[256], nflag_lstm[256];  // bit0: denom != 0, bit1: p != 0.5
-  uint8_t ring[1000];
+  uint8_t ring[32];            // last bytes (the reference keeps 1000, short-term-memory.h:23; only 10 are ever read)
   uint32_t ring_pos;
   int32_t new_bit, recent_bits, bb, first_prediction, analysis;
   uint32_t error;
@@ -252,9 +252,7 @@ GMX_DEV inline void SparseSet(const SparseMap& M, uint32_t* used, uint32_t limit
 }
 
 GMX_DEV inline uint32_t RecentByte(const StreamSmem& s, int ago) {  // short-term-memory.cpp:215-219
-  int pos = (int)s.ring_pos - ago;
-  if (pos < 0) pos += 1000;
-  return s.ring[pos];
+  return s.ring[(s.ring_pos - (uint32_t)ago) & 31u];
 }
 GMX_DEV inline int WOff(int m) { return m < NL0 ? m * WSTRIDE0 : NL0 * WSTRIDE0 + (m - NL0) * WSTRIDE1; }
 GMX_DEV inline int MixerNW(int m) { return m < NL0 ? NPRED + m : m < NL0 + NL1 ? NL0 + (m - NL0) + 1 : NL0 + NL1 + 1; }
@@ -337,7 +335,7 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
   for (int i = tid; i < NL0; i += NT) s.l0_out[i] = 0.0f;
   for (int i = tid; i < NL1; i += NT) s.l1_out[i] = 0.0f;
   for (int i = tid; i < 256; i += NT) { s.ppm[i] = (float)(1.0 / 256); s.lprob[i] = (float)(1.0 / 256); }
-  for (int i = tid; i < 1000; i += NT) s.ring[i] = 0;
+  for (int i = tid; i < 32; i += NT) s.ring[i] = 0;
   for (int i = tid; i < WTOTAL; i += NT) s.w[i] = 0.0f;
   for (int i = tid; i < NPRED + 2; i += NT) s.xe[i] = 0.0f;
   for (int i = tid; i < NMIX; i += NT) {
@@ -372,6 +370,14 @@ GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, i
   const uint32_t e = s.l_epoch;
   const uint32_t sym = s.ctx[C_LAST_BYTE];
   float* lin_e = A.at<float>(L.l_lin) + e * (L_NIN + 1);
+  // The pass streams 184 KB of gate weights and then the 52 KB output layer of this epoch slot from HBM.
+  // Request them all now (a few thousand cycles ahead of use: long enough to cover the HBM latency,
+  // short enough that the lines are still in L2 when the dot products reach them).
+  {
+    const float* W = A.at<float>(L.l_w);
+    for (int g = 0; g < 3; ++g) PrefetchRange(W + ((size_t)g * L_ROW + L_NOUT) * L_CELLS, L_NIN * L_CELLS * 4, tid, NT);
+    PrefetchRange(A.at<float>(L.l_wout) + (size_t)e * L_HID * L_NOUT, L_HID * L_NOUT * 4, tid, NT);
+  }
   // layer_input[e] = [ppm 256 | hidden 50 | 1]  (SetInput lstm.cpp:45-50, copy :94-96)
   for (int i = tid; i < L_NIN; i += NT) {
     const float v = i < 256 ? s.ppm[i] : i < 306 ? s.l_hidden[i - 256] : 1.0f;
@@ -747,14 +753,6 @@ template <int NT, bool PROF>
 GMX_DEV void ByteBoundary(StreamSmem& s, const Arena& A, const StreamParams& P, int tid) {
   const ArenaLayout& L = *A.L;
   const uint32_t last_byte = s.ctx[C_LAST_BYTE];
-  // (0) the LSTM forward pass streams 184 KB of gate weights and the 52 KB output layer of this epoch
-  // slot from HBM: start them towards L2 now, they are needed after the PPMd update.
-  if (tid < NT - 32) {
-    const float* W = A.at<float>(L.l_w);
-    for (int g = 0; g < 3; ++g)
-      PrefetchRange(W + ((size_t)g * L_ROW + L_NOUT) * L_CELLS, L_NIN * L_CELLS * 4, tid, NT - 32);
-    PrefetchRange(A.at<float>(L.l_wout) + (size_t)s.l_epoch * L_HID * L_NOUT, L_HID * L_NOUT * 4, tid, NT - 32);
-  }
   // (1) contexts: intervals, hashed skip contexts, indirect-hash tables; PPMd on its own thread.
   if (tid < 9) {  // IntervalContext::Predict interval-context.cpp:17-23
     const IntervalSpec sp = s.T.interval[tid];
@@ -882,8 +880,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
       if (rb >= 256) {  // ByteUpdate basic-contexts.cpp:5-19
         const uint32_t lb = rb - 256;
         s.ctx[C_LAST_BYTE] = lb;
-        uint32_t rp = s.ring_pos + 1;
-        if (rp == 1000) rp = 0;
+        const uint32_t rp = (s.ring_pos + 1) & 31u;
         s.ring_pos = rp;
         s.ring[rp] = (uint8_t)lb;
         for (int i = 1; i < 10; ++i) s.ctx[C_RB1 + i - 1] = RecentByte(s, i);
@@ -1365,6 +1362,22 @@ GMX_DEV void DecompressStream(StreamSmem& s, const Arena& A, const StreamParams&
   BlockSync();
 }
 
+// Copies the launch's read-only tables into shared memory (StreamTables).
+template <int NT>
+GMX_DEV void StageTables(StreamSmem& s, const StreamParams& P, int tid) {
+  const uint32_t* src = (const uint32_t*)P.layout;
+  uint32_t* dst = (uint32_t*)&s.T.L;
+  for (int i = tid; i < (int)(sizeof(ArenaLayout) / 4); i += NT) dst[i] = src[i];
+  for (int i = tid; i < NIND; i += NT) s.T.ind[i] = kInd[i];
+  for (int i = tid; i < 20; i += NT) s.T.skip[i] = kSkip[i];
+  for (int i = tid; i < 9; i += NT) s.T.interval[i] = kInterval[i];
+  for (int i = tid; i < NIH; i += NT) s.T.ih[i] = kIH[i];
+  for (int i = tid; i < NMATCH; i += NT) s.T.match[i] = kMatch[i];
+  for (int i = tid; i < NMIX; i += NT) s.T.mixer[i] = kMixer[i];
+  for (int i = tid; i < 512; i += NT) s.T.nonstationary[i] = kNonstationary[i];
+  BlockSync();
+}
+
 // ---- kernel entry: persistent CTAs, one stream at a time, ids from an atomic queue ---------------
 enum : int { MODE_COMPRESS = 0, MODE_DECOMPRESS = 1 };
 
@@ -1373,19 +1386,7 @@ __global__ void __launch_bounds__(NT, MINB) StreamKernel(StreamParams P) {
   __shared__ StreamSmem s;
   __shared__ uint32_t next_stream;
   const int tid = (int)threadIdx.x;
-  {
-    const uint32_t* src = (const uint32_t*)P.layout;
-    uint32_t* dst = (uint32_t*)&s.T.L;
-    for (int i = tid; i < (int)(sizeof(ArenaLayout) / 4); i += NT) dst[i] = src[i];
-    for (int i = tid; i < NIND; i += NT) s.T.ind[i] = kInd[i];
-    for (int i = tid; i < 20; i += NT) s.T.skip[i] = kSkip[i];
-    for (int i = tid; i < 9; i += NT) s.T.interval[i] = kInterval[i];
-    for (int i = tid; i < NIH; i += NT) s.T.ih[i] = kIH[i];
-    for (int i = tid; i < NMATCH; i += NT) s.T.match[i] = kMatch[i];
-    for (int i = tid; i < NMIX; i += NT) s.T.mixer[i] = kMixer[i];
-    for (int i = tid; i < 512; i += NT) s.T.nonstationary[i] = kNonstationary[i];
-  }
-  BlockSync();
+  StageTables<NT>(s, P, tid);
   Arena A{P.arenas + (uint64_t)blockIdx.x * P.arena_stride, &s.T.L};
   for (;;) {
     if (tid == 0) next_stream = atomicAdd(P.queue, 1u);
@@ -1397,6 +1398,48 @@ __global__ void __launch_bounds__(NT, MINB) StreamKernel(StreamParams P) {
     if (MODE == MODE_COMPRESS) CompressStream<NT, PROF>(s, A, P, sid, tid);
     else DecompressStream<NT, PROF>(s, A, P, sid, tid);
   }
+}
+
+// ---- single-stream stepping (the Predictor facade: reference src/predictor.h:20-38) ---------------
+// One launch per Predict() / Learn() call of ONE stream; the shared-memory state of the stream is
+// parked in global memory between launches. Perceive(bit) travels with the next launch.
+enum : int { STEP_INIT = 0, STEP_PREDICT = 1, STEP_LEARN = 2 };
+struct StepParams {
+  StreamParams P;          // arenas/layout/tables of the one stream (n_streams, in/out unused)
+  uint32_t* state;         // sizeof(StreamSmem) bytes
+  int op, has_bit, bit, analysis;
+  float* prob_out;         // STEP_PREDICT: what Predictor::Predict() returns
+  uint32_t* status_out;    // stream error code after the step
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT) StepKernel(StepParams Q) {
+  __shared__ StreamSmem s;
+  const int tid = (int)threadIdx.x;
+  uint32_t* sw = (uint32_t*)&s;
+  constexpr int kWords = (int)(sizeof(StreamSmem) / 4);
+  if (Q.op == STEP_INIT) {
+    StageTables<NT>(s, Q.P, tid);
+    Arena A{Q.P.arenas, &s.T.L};
+    InitStream<NT, false>(s, A, Q.P, tid);
+    if (tid == 0) s.analysis = Q.analysis;
+  } else {
+    for (int i = tid; i < kWords; i += NT) sw[i] = Q.state[i];
+    BlockSync();
+    Arena A{Q.P.arenas, &s.T.L};
+    if (tid == 0 && Q.has_bit) s.new_bit = Q.bit;   // Predictor::Perceive predictor.cpp:378-381
+    if (tid == 0 && Q.analysis >= 0) s.analysis = Q.analysis;
+    BlockSync();
+    if (Q.op == STEP_PREDICT) {
+      PredictBit<NT, false>(s, A, Q.P, tid);
+      if (tid == 0) *Q.prob_out = s.prob;
+    } else {
+      LearnBit<NT, false>(s, A, Q.P, tid);
+    }
+  }
+  BlockSync();
+  for (int i = tid; i < kWords; i += NT) Q.state[i] = sw[i];
+  if (tid == 0) *Q.status_out = s.error;
 }
 
 }  // namespace gmx

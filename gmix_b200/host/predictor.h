@@ -1,0 +1,56 @@
+// Host-side mirror of the reference's `class Predictor` (reference src/predictor.h:13-38) on top of
+// the C ABI (include/gmix_b200.h). Same call contract: Predict() -> Perceive(bit) -> Learn(); Learn() is
+// optional once training is over (generation). Every call is a kernel launch on the GPU that owns the
+// stream; bulk work should use gmx_compress_batch / gmx_decompress_batch instead.
+#ifndef GMIX_B200_HOST_PREDICTOR_H_
+#define GMIX_B200_HOST_PREDICTOR_H_
+#include <stdexcept>
+#include <string>
+
+#include "../../include/gmix_b200.h"
+
+namespace gmixb {
+
+class Gpu {  // one gmx_ctx per GPU
+ public:
+  explicit Gpu(int device = 0) {
+    if (gmx_create(device, &ctx_) != 0) throw std::runtime_error(std::string("gmx_create: ") + gmx_global_error());
+  }
+  ~Gpu() { gmx_destroy(ctx_); }
+  Gpu(const Gpu&) = delete;
+  Gpu& operator=(const Gpu&) = delete;
+  gmx_ctx* ctx() const { return ctx_; }
+
+ private:
+  gmx_ctx* ctx_ = nullptr;
+};
+
+class Predictor {
+ public:
+  // max_stream_len: upper bound on the bytes this predictor will see (sizes its device arena).
+  Predictor(Gpu& gpu, unsigned long long max_stream_len) : gpu_(gpu) {
+    if (gmx_pred_new(gpu.ctx(), max_stream_len, &p_) != 0) throw std::runtime_error(gmx_last_error(gpu.ctx()));
+  }
+  ~Predictor() { gmx_pred_free(p_); }
+  Predictor(const Predictor&) = delete;
+  Predictor& operator=(const Predictor&) = delete;
+
+  // Probability that the next bit is 1 (reference predictor.cpp:360-376).
+  float Predict() {
+    float p = 0.5f;
+    Check(gmx_pred_predict(p_, &p));
+    return p;
+  }
+  void Perceive(int bit) { Check(gmx_pred_perceive(p_, bit)); }   // predictor.cpp:378-381
+  void Learn() { Check(gmx_pred_learn(p_)); }                       // predictor.cpp:383-387
+  // Only the path-visible effect of EnableAnalysis (predictions zeroed each Predict, predictor.cpp:362-365).
+  void EnableAnalysis(int sample_frequency) { Check(gmx_pred_enable_analysis(p_, sample_frequency > 0)); }
+
+ private:
+  void Check(int rc) { if (rc != 0) throw std::runtime_error(gmx_last_error(gpu_.ctx())); }
+  Gpu& gpu_;
+  gmx_pred* p_ = nullptr;
+};
+
+}  // namespace gmixb
+#endif

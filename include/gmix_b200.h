@@ -98,6 +98,21 @@ int gmx_checksum_device(gmx_ctx* ctx, const uint8_t* d_data, const uint64_t* d_o
 int gmx_compress_trace(gmx_ctx* ctx, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_len,
                        float* probs, uint32_t* p16, float* blackboard);
 
+/* ---- Predictor facade: one stream stepped bit by bit -------------------------------------------
+ * Mirrors `class Predictor` (reference src/predictor.h:20-38): Predict() -> Perceive(bit) -> Learn(), Learn
+ * optional (generation). Every Predict/Learn is one kernel launch plus a device->host read, so this is
+ * the compatibility / debugging path, not the fast one (use the batch calls). The stream arena is
+ * worst-case sized for max_stream_len bytes. gmx_pred_enable_analysis mirrors the one path-visible
+ * effect of Predictor::EnableAnalysis (predictor.cpp:362-365, predictions zeroed each Predict), which
+ * runner_utils::Compress turns on for inputs of 125 bytes or more (runner-utils.cpp:47). */
+typedef struct gmx_pred gmx_pred;
+int gmx_pred_new(gmx_ctx* ctx, uint64_t max_stream_len, gmx_pred** out);
+void gmx_pred_free(gmx_pred* pred);
+int gmx_pred_enable_analysis(gmx_pred* pred, int on);
+int gmx_pred_predict(gmx_pred* pred, float* prob);
+int gmx_pred_perceive(gmx_pred* pred, int bit);
+int gmx_pred_learn(gmx_pred* pred);
+
 /* Introspection for benchmarks. */
 uint32_t gmx_resident_streams(const gmx_ctx* ctx);   /* CTAs (= arenas) the last launch used */
 uint64_t gmx_arena_bytes(const gmx_ctx* ctx);        /* bytes of one stream arena */
