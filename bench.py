@@ -105,22 +105,39 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------------
 def chunk_ids(rank, step, per_step, total_set=4096):
-    """Chunk ids of this rank for one step: disjoint across ranks, walking the configs[1] set."""
-    base = (step * per_step) % max(total_set, per_step)
-    return [rank * max(total_set, per_step) + base + i for i in range(per_step)]
+    """Chunk ids of this rank for one step: every rank owns its own 4096-chunk set (disjoint ids) and successive
+    steps walk through it (wrapping around)."""
+    span = max(total_set, per_step)
+    return [rank * span + (step * per_step + i) % span for i in range(per_step)]
 
 
 _CHUNK_CACHE = {}
 
 
-def make_chunks(ids, size):
+def _gen_chunk(args):
     from gmix_b200 import synth
-    out = []
-    for i in ids:
-        if (i, size) not in _CHUNK_CACHE:
-            _CHUNK_CACHE[(i, size)] = synth.synthetic_text_chunk(i, size)
-        out.append(_CHUNK_CACHE[(i, size)])
-    return out
+    return synth.synthetic_text_chunk(*args)
+
+
+def pregenerate(ids, size, procs):
+    """Generate the synthetic chunks with a process pool (pure-Python generator, ~26 ms per 64 KiB chunk).
+    Must run before CUDA is initialised in this process (fork)."""
+    todo = sorted({i for i in ids if (i, size) not in _CHUNK_CACHE})
+    if not todo:
+        return
+    if procs > 1 and len(todo) >= 64:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(procs) as pool:
+            for i, c in zip(todo, pool.map(_gen_chunk, [(i, size) for i in todo], chunksize=16)):
+                _CHUNK_CACHE[(i, size)] = c
+    else:
+        for i in todo:
+            _CHUNK_CACHE[(i, size)] = _gen_chunk((i, size))
+
+
+def make_chunks(ids, size):
+    pregenerate(ids, size, 1)
+    return [_CHUNK_CACHE[(i, size)] for i in ids]
 
 
 def fnv1a(b):
@@ -214,6 +231,10 @@ def run_reference(args):
 
 # ---------------------------------------------------------------------------------------------------
 def run_ours(args):
+    world0 = int(os.environ.get("WORLD_SIZE", "1"))
+    rank0 = int(os.environ.get("RANK", "0"))
+    all_ids = [i for st in range(args.warmup + args.steps) for i in chunk_ids(rank0, st, args.chunks)]
+    pregenerate(all_ids, args.chunk_bytes, max(1, min(32, (os.cpu_count() or 1) // world0)))
     import numpy as np
     import torch
     import torch.distributed as dist

@@ -107,13 +107,26 @@ inline ArenaLayout MakeLayout(uint64_t max_len, bool roomy = false) {
   L.l_errh = take(3ull * L_HORIZON * L_CELLS * 4);
   L.l_wt = take(3ull * L_CELLS * L_CELLS * 4);
   L.p_state = take(sizeof(PpmdState));
-  L.p_text_cap = (uint32_t)(max_len + 64);
-  L.p_text = take(AlignUp(L.p_text_cap, 4));
-  uint64_t units = AlignUp((roomy ? 400 : 96) * max_len + (256u << 10), 48);  // ~19 B/byte on text
-  const uint64_t units_max = 800ull << 20;                   // must stay below half of the virtual units area
-  if (units > units_max) units = units_max / 48 * 48;
-  L.p_units_cap = (uint32_t)units;
-  L.p_units = take(units);
+  // PPMd heap window (ppmd.cuh): smallest 2^k whose unit window (2^k - units_start mod 2^k) holds the
+  // units this stream can need (~19 B/byte on text; 400 B/byte worst-case sizing)
+  // and whose bottom holds the text area.
+  {
+    const uint64_t want_units = (roomy ? 400 : 90) * max_len + (256u << 10);
+    const uint64_t want_text = max_len + 64;
+    uint64_t P = 1ull << 20;
+    for (;; P <<= 1) {
+      const uint64_t text_room = PPMD_UNITS_START % P, units_room = P - text_room;
+      if ((text_room >= want_text && units_room >= want_units) || P >= (1ull << 30)) break;
+    }
+    const uint64_t text_room = PPMD_UNITS_START % P, units_room = P - text_room;
+    L.p_mask = (uint32_t)(P - 1);
+    L.p_text_cap = (uint32_t)(want_text < text_room ? want_text : text_room);
+    uint64_t units = units_room / 48 * 48;
+    const uint64_t units_max = 800ull << 20;   // must stay below half of the virtual units area
+    if (units > units_max) units = units_max / 48 * 48;
+    L.p_units_cap = (uint32_t)units;
+    L.p_heap = take(P);
+  }
   L.total = off;
   return L;
 }

@@ -4,14 +4,18 @@
 // Behaviour follows the reference's ModPPMD (src/models/mod_ppmd.cpp; line cites below refer to
 // that file): same 12-byte units, same free lists, same SEE / binary-context estimators, same
 // 32-bit *virtual* heap offsets (0 .. 2000 MiB) because offset comparisons against `units_start`
-// are semantic. Only three parts of that virtual heap are ever backed:
-//   text area   [0, text_cap)                       -> `text`
-//   low units   [units_start, units_start + x)      -> `units[0 .. x)`
-//   high units  [heap_end - y, heap_end)            -> `units[units_cap - y .. units_cap)`
-// with x + y <= units_cap. The reference's out-of-memory machinery (AllocUnitsRare/GlueFreeBlocks
+// are semantic. Only three parts of that virtual heap are ever touched:
+//   text area   [0, text_cap)                    grows up
+//   low units   [units_start, units_start + x)   grows up
+//   high units  [heap_end - y, heap_end)         grows down
+// They are backed by ONE window of 2^k bytes addressed as heap[v & (2^k - 1)]: heap_end = 2000 MiB is
+// a multiple of 2^k (k <= 24), so the high units end at the top of the window, the low units start
+// at units_start mod 2^k, and the text sits at the bottom; the three never meet as long as
+// text_cap <= units_start mod 2^k and x + y <= units_cap = 2^k - units_start mod 2^k (layout.h picks k).
+// The reference's out-of-memory machinery (AllocUnitsRare/GlueFreeBlocks
 // :158-228, RestoreModelRare/cutOff :568-755, Expand/PrepareTextArea :299-348) only runs when the
 // 2000 MiB heap is exhausted (> ~90 MB of input); here exhausting the *backed* part raises
-// GMX_ERR_PPMD_ARENA for the stream instead (the host sizes the arena from the stream length).
+// GMX_ERR_PPMD_ARENA for the stream instead (the host re-runs it with a larger window).
 #ifndef GMIX_B200_PPMD_CUH_
 #define GMIX_B200_PPMD_CUH_
 #include <stdint.h>
@@ -53,20 +57,14 @@ struct PpmdState {
 
 struct Ppmd {
   PpmdState* S;
-  uint8_t* text;
-  uint8_t* units;
+  uint8_t* heap;               // backing window of 2^k bytes: byte v of the virtual heap lives at heap[v & mask]
+  uint32_t mask;
   uint32_t text_cap, units_cap;
   uint32_t* sqp;  // out: 256 symbol pseudo-probabilities (:1187)
   int lane;       // lane of the calling thread in the PPMd warp (UpdateByte / PrepareByte are warp-collective)
 
   // ---- virtual heap -> backed memory -------------------------------------------------------
-  GMX_DEV uint8_t* At(uint32_t v) const {
-    // one base select + one add (this is inlined at every heap access)
-    const long long lo = (long long)(units - text) - (long long)PPMD_UNITS_START;
-    const long long hi = (long long)(units - text) + (long long)units_cap - (long long)PPMD_HEAP_END;
-    const long long off = v < PPMD_UNITS_START ? 0ll : (v >= PPMD_HEAP_END - units_cap ? hi : lo);
-    return text + (off + (long long)v);
-  }
+  GMX_DEV uint8_t* At(uint32_t v) const { return heap + (v & mask); }
   GMX_DEV uint32_t R8(uint32_t v) const { return *At(v); }
   GMX_DEV void W8(uint32_t v, uint32_t x) const { *At(v) = (uint8_t)x; }
   GMX_DEV uint32_t R16(uint32_t v) const { return *(const uint16_t*)At(v); }

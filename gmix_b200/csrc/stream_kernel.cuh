@@ -85,7 +85,7 @@ struct ArenaLayout {
   uint64_t l_errh;            // float [3][L_HORIZON][L_CELLS]
   uint64_t l_wt;              // float [3][L_CELLS][L_CELLS] transposed recurrent weights (BPTT scratch)
   // PPMd
-  uint64_t p_state; uint64_t p_text; uint64_t p_units; uint32_t p_text_cap; uint32_t p_units_cap;
+  uint64_t p_state; uint64_t p_heap; uint32_t p_mask; uint32_t p_text_cap; uint32_t p_units_cap;  // see ppmd.cuh
   uint64_t total;             // arena bytes
 };
 
@@ -137,8 +137,8 @@ struct StreamTables {
 struct StreamSmem {
   StreamTables T;
   // blackboard (ShortTermMemory)
-  float preds[NPRED + 2];
-  uint8_t act[NPRED + 6];
+  alignas(16) float preds[NPRED + 2];
+  alignas(4) uint8_t act[NPRED + 6];
   uint32_t ctx[C_COUNT + 2];
   alignas(16) float l0_out[NL0]; float l1_out[NL1], final_out, prob;   // l0_out | l1_out contiguous (final mixer input)
   float ppm[256], lprob[256];          // byte distributions of PPMd and LSTM
@@ -258,6 +258,20 @@ GMX_DEV inline int WOff(int m) { return m < NL0 ? m * WSTRIDE0 : NL0 * WSTRIDE0 
 GMX_DEV inline int MixerNW(int m) { return m < NL0 ? NPRED + m : m < NL0 + NL1 ? NL0 + (m - NL0) + 1 : NL0 + NL1 + 1; }
 
 GMX_DEV inline void BlockSync() { __syncthreads(); }
+// 4-byte asynchronous global -> shared copy (LDGSTS): no register round trip, so many can be in flight.
+GMX_DEV inline void CpAsync4(void* smem_dst, const void* gmem_src) {
+#if defined(__CUDA_ARCH__)
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+#else
+  *(uint32_t*)smem_dst = *(const uint32_t*)gmem_src;
+#endif
+}
+GMX_DEV inline void CpAsyncWaitAll() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
 GMX_DEV inline void PrefetchL2(const void* p) {
 #if defined(__CUDA_ARCH__)
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -326,8 +340,11 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
   FillWords<NT>(A.at<uint32_t>(L.l_wout), L_HID * L_NOUT, 0u, tid);  // epoch slot 0; others are written before read
   for (int e = tid; e < L_HORIZON; e += NT) A.at<float>(L.l_lin)[e * (L_NIN + 1) + L_NIN - 1] = 1.0f;
   // PPMd heap must start zeroed (mod_ppmd.cpp relies on fresh pages)
-  FillWords<NT>(A.at<uint32_t>(L.p_text), (L.p_text_cap + 3) / 4, 0u, tid);
-  FillWords<NT>(A.at<uint32_t>(L.p_units), L.p_units_cap / 4, 0u, tid);
+  {
+    uint4* z = A.at<uint4>(L.p_heap);
+    const uint64_t n16 = ((uint64_t)L.p_mask + 1) / 16;
+    for (uint64_t i = tid; i < n16; i += NT) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
   // shared state
   for (int i = tid; i < NPRED + 2; i += NT) s.preds[i] = 0.0f;
   for (int i = tid; i < NPRED + 6; i += NT) s.act[i] = 0;
@@ -355,7 +372,7 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
   }
   BlockSync();
   if (tid == 0) {
-    Ppmd pm{A.at<PpmdState>(L.p_state), A.at<uint8_t>(L.p_text), A.at<uint8_t>(L.p_units), L.p_text_cap, L.p_units_cap, s.sqp, 0};
+    Ppmd pm{A.at<PpmdState>(L.p_state), A.at<uint8_t>(L.p_heap), L.p_mask, L.p_text_cap, L.p_units_cap, s.sqp, 0};
     pm.Init();
   }
   BlockSync();
@@ -450,12 +467,18 @@ GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, i
   // output layer: sum_j hidden[j] * Wout[e][i][j], j ascending, hidden[50] = 1 (lstm.cpp:105-113)
   const float* wo = A.at<float>(L.l_wout) + (size_t)e * L_HID * L_NOUT;
   float mx = 0.0f;
-  for (int i = tid; i < L_NOUT; i += NT) {
-    float acc = 0.0f;
+  if (tid < L_NOUT / 4) {  // 4 adjacent outputs per thread: one 16-byte load feeds 4 sequential sums
+    const float4* wo4 = (const float4*)wo + tid;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
 #pragma unroll 17
-    for (int j = 0; j < L_HID; ++j) acc = f_add(acc, f_mul(s.l_hidden[j], wo[j * L_NOUT + i]));
-    s.l_err256[i] = acc;
-    mx = acc > mx ? acc : mx;
+    for (int j = 0; j < L_HID; ++j) {
+      const float h = s.l_hidden[j];
+      const float4 w = wo4[j * (L_NOUT / 4)];
+      a0 = f_add(a0, f_mul(h, w.x)); a1 = f_add(a1, f_mul(h, w.y));
+      a2 = f_add(a2, f_mul(h, w.z)); a3 = f_add(a3, f_mul(h, w.w));
+    }
+    s.l_err256[4 * tid + 0] = a0; s.l_err256[4 * tid + 1] = a1; s.l_err256[4 * tid + 2] = a2; s.l_err256[4 * tid + 3] = a3;
+    mx = a0 > mx ? a0 : mx; mx = a1 > mx ? a1 : mx; mx = a2 > mx ? a2 : mx; mx = a3 > mx ? a3 : mx;
   }
   // max over all outputs, seeded with 0 (max is order independent)
   for (int o = 16; o > 0; o >>= 1) { const float v = __shfl_xor_sync(0xffffffffu, mx, o); mx = v > mx ? v : mx; }
@@ -689,11 +712,27 @@ GMX_DEV void LstmPerceive(StreamSmem& s, const Arena& A, const StreamParams& P, 
   const float* wl = A.at<float>(L.l_wout) + (size_t)last * L_HID * L_NOUT;
   float* wc = A.at<float>(L.l_wout) + (size_t)cur * L_HID * L_NOUT;
   const float lr = (float)0.03;
-  for (int i = tid; i < L_NOUT; i += NT) {
-    const float err = (uint32_t)i == byte ? f_sub(s.lprob[i], 1.0f) : s.lprob[i];
-    const float le = f_mul(lr, err);
-#pragma unroll 17
-    for (int j = 0; j < L_HID; ++j) wc[j * L_NOUT + i] = f_sub(wl[j * L_NOUT + i], f_mul(le, s.l_hidden[j]));
+  {
+    const int q = tid & (L_NOUT / 4 - 1), half = tid / (L_NOUT / 4);   // outputs 4q..4q+3, rows of half `half`
+    float le[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t i = 4 * q + k;
+      const float err = i == byte ? f_sub(s.lprob[i], 1.0f) : s.lprob[i];
+      le[k] = f_mul(lr, err);
+    }
+    const float4* wl4 = (const float4*)wl + q;
+    float4* wc4 = (float4*)wc + q;
+    const int j0 = half * ((L_HID + NT / (L_NOUT / 4) - 1) / (NT / (L_NOUT / 4)));
+    const int j1 = j0 + (L_HID + NT / (L_NOUT / 4) - 1) / (NT / (L_NOUT / 4)) < L_HID ? j0 + (L_HID + NT / (L_NOUT / 4) - 1) / (NT / (L_NOUT / 4)) : L_HID;
+#pragma unroll 13
+    for (int j = j0; j < j1; ++j) {
+      const float h = s.l_hidden[j];
+      float4 w = wl4[j * (L_NOUT / 4)];
+      w.x = f_sub(w.x, f_mul(le[0], h)); w.y = f_sub(w.y, f_mul(le[1], h));
+      w.z = f_sub(w.z, f_mul(le[2], h)); w.w = f_sub(w.w, f_mul(le[3], h));
+      wc4[j * (L_NOUT / 4)] = w;
+    }
   }
   BlockSync();
   GMX_PROF(10);
@@ -788,7 +827,7 @@ GMX_DEV void ByteBoundary(StreamSmem& s, const Arena& A, const StreamParams& P, 
     }
     s.ih_hash[k] = oh;
   } else if (tid >= NT - 32) {  // ModPPMD::Predict byte part, mod_ppmd.cpp:1651-1654 (the last warp, collectively)
-    Ppmd pm{A.at<PpmdState>(L.p_state), A.at<uint8_t>(L.p_text), A.at<uint8_t>(L.p_units), L.p_text_cap, L.p_units_cap, s.sqp, tid - (NT - 32)};
+    Ppmd pm{A.at<PpmdState>(L.p_state), A.at<uint8_t>(L.p_heap), L.p_mask, L.p_text_cap, L.p_units_cap, s.sqp, tid - (NT - 32)};
     pm.UpdateByte(last_byte);
     if (!pm.S->error) pm.PrepareByte();
     if (pm.S->error) s.error = GMX_ERR_PPMD_ARENA;
@@ -1026,15 +1065,17 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
       }
     }
 #pragma unroll 1
-    for (uint32_t r = 0; r < nswap; ++r) {
+    for (uint32_t r = 0; r < nswap; ++r) {   // asynchronous copies: all queued sets are in flight together
       const int m = s.swap_m[r];
       const uint32_t nid = s.swap_new[r];
       if (tid < MixerNW(m) + 1) {
+        uint32_t* dst = tid == 0 ? &s.set_steps[m] : (uint32_t*)&s.w[WOff(m) + tid - 1];
         const float* rec = pool + (size_t)nid * stride;
-        if (tid == 0) { s.set_steps[m] = nid ? ((const uint32_t*)rec)[0] : 0u; s.set_pool[m] = nid; }
-        else s.w[WOff(m) + tid - 1] = nid ? rec[1 + tid] : 0.0f;
+        if (nid) CpAsync4(dst, tid == 0 ? rec : rec + 1 + tid); else *dst = 0u;
+        if (tid == 0) s.set_pool[m] = nid;
       }
     }
+    CpAsyncWaitAll();
   }
   BlockSync();
   GMX_PROF(5);
@@ -1048,7 +1089,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     {
       const float4* x4 = (const float4*)s.xe;
       const float4* w4 = (const float4*)w;
-#pragma unroll 1
+#pragma unroll 2
       for (int q = 0; q < NPRED / 4; ++q) {
         const float4 x = x4[q], v = w4[q];
         acc = f_add(acc, f_mul(x.x, v.x)); acc = f_add(acc, f_mul(x.y, v.y));
@@ -1057,10 +1098,17 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
 #pragma unroll
       for (int i = NPRED / 4 * 4; i < NPRED; ++i) acc = f_add(acc, f_mul(s.xe[i], w[i]));
     }
-#pragma unroll 1
-    for (int j = 0; j < NL0 - 1; ++j) {
-      const float oj = __shfl_sync(0xffffffffu, acc, j);
-      if (lane > j && lane < NL0) acc = f_add(acc, f_mul(oj, w[NPRED + j]));
+    {
+      // serial chain of the layer: neuron j's finished output feeds every later neuron (mixer.cpp:60-70).
+      // The 23 chain weights sit in registers so that one step is shuffle -> mul -> add.
+      float cw[NL0 - 1];
+#pragma unroll
+      for (int j = 0; j < NL0 - 1; ++j) cw[j] = w[NPRED + j];
+#pragma unroll
+      for (int j = 0; j < NL0 - 1; ++j) {
+        const float oj = __shfl_sync(0xffffffffu, acc, j);
+        if (lane > j && lane < NL0) acc = f_add(acc, f_mul(oj, cw[j]));
+      }
     }
     if (lane < NL0) s.l0_out[lane] = acc;
     __syncwarp();
@@ -1200,22 +1248,36 @@ GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int 
     const int nw = MixerNW(m);
     const float upd = s.upd[m];
     const bool shrink = s.shrink[m] != 0;
+    const float keep = f_sub(1.0f, 3.0e-6f);
     float* w = s.w + WOff(m);
+    int first = 0;
+    if (m < NL0) {  // inputs 0..87 = predictions, four per lane
+      first = NPRED / 4 * 4;
+      if (lane < NPRED / 4) {
+        float4 v = ((float4*)w)[lane];
+        const float4 x = ((const float4*)s.preds)[lane];
+        const uint32_t on = ((const uint32_t*)s.act)[lane];
+        if (on & 0x000000ffu) v.x = f_sub(v.x, f_mul(upd, x.x));
+        if (on & 0x0000ff00u) v.y = f_sub(v.y, f_mul(upd, x.y));
+        if (on & 0x00ff0000u) v.z = f_sub(v.z, f_mul(upd, x.z));
+        if (on & 0xff000000u) v.w = f_sub(v.w, f_mul(upd, x.w));
+        if (shrink) { v.x = f_mul(v.x, keep); v.y = f_mul(v.y, keep); v.z = f_mul(v.z, keep); v.w = f_mul(v.w, keep); }
+        ((float4*)w)[lane] = v;
+      }
+    }
 #pragma unroll 1
-    for (int i = lane; i < nw; i += 32) {
-      float x; bool use;
+    for (int i = first + lane; i < nw; i += 32) {
+      float x; bool use = true;
       if (m < NL0) {
         if (i < NPRED) { use = s.act[i] != 0; x = s.preds[i]; }
-        else { use = true; x = s.l0_out[i - NPRED]; }
+        else x = s.l0_out[i - NPRED];
       } else {
         const int nin = m < NL0 + NL1 ? NL0 + (m - NL0) : NL0 + NL1;  // inputs before the skip connection
-        if (i < NL0) { use = true; x = s.l0_out[i]; }
-        else if (i < nin) { use = true; x = s.l1_out[i - NL0]; }
-        else { use = true; x = s.preds[P_LSTM]; }
+        x = i < NL0 ? s.l0_out[i] : i < nin ? s.l1_out[i - NL0] : s.preds[P_LSTM];
       }
       float v = w[i];
       if (use) v = f_sub(v, f_mul(upd, x));
-      if (shrink) v = f_mul(v, f_sub(1.0f, 3.0e-6f));
+      if (shrink) v = f_mul(v, keep);
       w[i] = v;
     }
   }

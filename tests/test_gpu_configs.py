@@ -1,0 +1,54 @@
+"""GPU parity at the shapes BASELINE.json names (scaled where the CPU oracle would take hours):
+config 1 (dictionary/english.dic as one stream: known answers of the canonical reference build),
+configs 2/3 (independent synthetic-text chunks: oracle sample + lossless round trip of every stream)."""
+import hashlib
+import json
+import os
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+DIC = open(os.path.join(ROOT, "tests", "data", "english.dic"), "rb").read()
+KNOWN = json.load(open(os.path.join(HERE, "golden", "known_answers.json")))
+
+
+def test_config1_english_dic_known_answers_and_roundtrip(gpu_ctx):
+    """Reference (strict build) compresses english.dic to 109 490 B, md5 5ea62ac4...; prefixes likewise."""
+    names = ["english_dic_full", "english_dic_64k", "english_dic_16k"]
+    streams = [DIC[:KNOWN[k]["input_bytes"]] for k in names]
+    assert len(streams[0]) == len(DIC) == 411996
+    comp = gpu_ctx.compress_batch(streams)
+    for k, c in zip(names, comp):
+        assert len(c) == KNOWN[k]["output_bytes"], k
+        assert hashlib.md5(c).hexdigest() == KNOWN[k]["md5"], k
+    back = gpu_ctx.decompress_batch(comp)
+    assert back == streams
+
+
+def test_config2_synthetic_chunks_oracle_sample_and_roundtrip(gpu_ctx, oracle):
+    from gmix_b200 import synth
+    n, size = 300, 8192
+    streams = [synth.synthetic_text_chunk(i, size) for i in range(n)]
+    comp = gpu_ctx.compress_batch(streams)
+    for i in (0, 137, 299):                               # seeded sample against the CPU oracle
+        assert comp[i] == oracle.compress(streams[i]), f"chunk {i} differs from the oracle"
+    assert all(c[:5] == size.to_bytes(5, "big") for c in comp)
+    back = gpu_ctx.decompress_batch(comp)                 # config 3: every stream decodes losslessly
+    assert back == streams
+    assert gpu_ctx.retried_streams == 0                   # text fits the normal arenas
+
+
+def test_incompressible_streams_take_the_roomy_retry_path(gpu_ctx, oracle):
+    import numpy as np
+    rng = np.random.RandomState(7)
+    streams = [rng.randint(0, 256, 3000, dtype=np.uint8).tobytes(), DIC[2000:5000], rng.randint(0, 256, 2500, dtype=np.uint8).tobytes()]
+    gpu_ctx.configure(3000, 0)
+    before = gpu_ctx.retried_streams
+    comp = gpu_ctx.compress_batch(streams)
+    assert gpu_ctx.retried_streams > before                # random bytes overflow the text-sized sparse map
+    for s, c in zip(streams, comp):
+        assert c == oracle.compress(s)
+    assert gpu_ctx.decompress_batch(comp) == streams

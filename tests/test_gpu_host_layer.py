@@ -37,20 +37,31 @@ def test_predictor_facade_matches_oracle_per_bit(gpu_ctx, oracle):
     assert [_discretize(p) for p in got] == op16.tolist()
 
 
-def test_predictor_without_learn_keeps_predicting(gpu_ctx):
-    """Generation-style use (reference runner-utils.cpp:198-215): Perceive + Predict without Learn."""
+def test_predictor_without_learn_matches_oracle(gpu_ctx, oracle):
+    """Generation-style use (reference runner-utils.cpp:187-215): learn over a prompt, then Perceive + Predict
+    without Learn. Compared bit for bit with the oracle's Predictor facade driven the same way."""
     import gmix_b200
-    pred = gmix_b200.Predictor(gpu_ctx, 64)
-    probs = []
-    for k in range(24):
-        p = pred.predict()
-        assert np.float32(0.0001) <= np.float32(p) <= np.float32(1.0) - np.float32(0.0001)   # predictor.cpp:369-375 clamp
-        probs.append(p)
-        pred.perceive(k & 1)
-        if k < 8:
-            pred.learn()
+    prompt = open(os.path.join(GOLD, "text1k.in"), "rb").read()[:120]
+    tail_bits = [1, 0, 0, 1, 1, 1, 0, 1, 0, 0, 1, 0, 1, 1, 0, 0, 0, 1, 1, 0, 1, 0, 1, 1]
+    lib = oracle.lib
+    o = lib.gmo_new()
+    pred = gmix_b200.Predictor(gpu_ctx, 256)
+    got, want = [], []
+    for byte in prompt:
+        for j in range(7, -1, -1):
+            bit = (byte >> j) & 1
+            got.append(pred.predict()); want.append(lib.gmo_predict(o))
+            pred.perceive(bit); lib.gmo_perceive(o, bit)
+            pred.learn(); lib.gmo_learn(o)
+    for bit in tail_bits:                      # learning disabled
+        got.append(pred.predict()); want.append(lib.gmo_predict(o))
+        pred.perceive(bit); lib.gmo_perceive(o, bit)
     pred.close()
-    assert len(set(probs)) > 1
+    lib.gmo_free(o)
+    got, want = np.asarray(got, dtype=np.float32), np.asarray(want, dtype=np.float32)
+    bad = np.nonzero(got.view(np.uint32) != want.view(np.uint32))[0]
+    assert bad.size == 0, f"first differing bit {bad[0]} ({'prompt' if bad[0] < 960 else 'no-learn tail'})"
+    assert len(set(got[960:].tolist())) > 1
 
 
 @pytest.mark.parametrize("name", ["text1k", "one_byte", "empty"])
