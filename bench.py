@@ -7,7 +7,7 @@
 Workload = BASELINE.json configs[1]: independent 64 KiB synthetic-text chunks (gmix_b200/synth.py,
 SURVEY.md section 8d), every chunk compressed from scratch as its own stream, one CTA per stream.
 A *step* is one pass of the hot path over one batch of `--chunks` chunks per GPU. The default batch is
-one full wave of resident streams (7 CTAs x 148 SMs = 1036 chunks = 67.9 MB of input), so that a default
+one full wave of resident streams (8 CTAs x 148 SMs = 1184 chunks = 77.6 MB of input), so that a default
 run (3 warm-up + 2 timed steps + 2 end-to-end steps) finishes within minutes; successive steps walk
 through the 4096-chunk set of configs[1] (`--chunks 4096` runs the whole set in one step). Weak scaling: every
 rank compresses its own `--chunks` chunks (chunk ids are disjoint across ranks), no collective on the
@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--chunks", type=int, default=int(os.environ.get("GMIX_BENCH_CHUNKS", "1036")), help="chunks per GPU per step")
+    ap.add_argument("--chunks", type=int, default=int(os.environ.get("GMIX_BENCH_CHUNKS", "1184")), help="chunks per GPU per step")
     ap.add_argument("--chunk-bytes", type=int, default=65536)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -372,7 +372,7 @@ def run_ours(args):
             "bits_per_byte": 8.0 * comp_bytes / (n * size),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_kind": pk_kind,
-                         "kernel": "gmx::StreamKernel<128, MODE_COMPRESS, 7, false>", "kernel_ms": kernel_ms_avg,
+                         "kernel": "gmx::StreamKernel<128, MODE_COMPRESS, 8, false>", "kernel_ms": kernel_ms_avg,
                          "algorithmic_bytes_per_input_byte": ALGO_BYTES_PER_INPUT_BYTE},
             "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
         }
