@@ -228,13 +228,14 @@ class Context:
         return int(self.lib.gmx_device_sm_count(self.h))
 
     PROFILE_SLOTS = ("byte_ctx+ppmd", "ppm_norm", "lstm_fwd", "nodes", "lookups", "mix_swap", "mix_predict", "coder",
-                     "learn_scalars", "mix_update", "lstm_out_step", "bptt_epochs", "bptt_grads", "init", "bit_misc", "-")
+                     "learn_scalars", "mix_update", "lstm_out_step", "bptt_epochs", "bptt_grads", "init", "bit_misc", "-",
+                     "gate_select", "l0_dot", "l0_chain", "l1", "final", "-", "-", "-")
 
     def set_profile(self, on=True):
         self._check(self.lib.gmx_set_profile(self.h, int(on)), "gmx_set_profile")
 
     def get_profile(self, max_streams=1):
-        buf = np.zeros((max_streams, 16), dtype=np.uint64)
+        buf = np.zeros((max_streams, len(self.PROFILE_SLOTS)), dtype=np.uint64)
         n = self.lib.gmx_get_profile(self.h, buf.ctypes.data, max_streams)
         if n < 0:
             self._check(n, "gmx_get_profile")

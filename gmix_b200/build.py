@@ -37,6 +37,7 @@ def build_library(force=False, verbose=False):
     os.makedirs(objdir, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = ["-Xptxas", "-v"] if verbose else []
+    extra += os.environ.get("GMX_NVCC_EXTRA", "").split()
     procs, objs = [], []
     for src in SOURCES:  # the translation units compile in parallel (each stream kernel takes ptxas > 1 min)
         obj = os.path.join(objdir, src.replace(".cu", ".o"))

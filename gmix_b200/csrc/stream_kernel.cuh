@@ -37,10 +37,12 @@ enum : uint32_t {
 // layer-1/final sets (<= 33 weights) at stride 36 words. Both strides are 16-byte multiples (float4
 // loads) and = 4 mod 32 banks, which makes lane-per-neuron float4 reads conflict free.
 enum : int { WSTRIDE0 = 132, WSTRIDE1 = 36, WTOTAL = 24 * WSTRIDE0 + 9 * WSTRIDE1 };
-enum : int { GMX_PROF_SLOTS = 16 };
+enum : int { GMX_PROF_SLOTS = 24 };
 // Phase slots: 0 byte contexts+PPMd, 1 ppm normalise, 2 LSTM forward, 3 interval nodes, 4 indirect/match
 // lookups, 5 mixer set swap, 6 mixer predict, 7 coder, 8 learn scalars+indirect, 9 mixer weight update,
-// 10 LSTM output-layer step, 11 BPTT epochs, 12 BPTT weight grads+Adam, 13 stream init, 14 bit bookkeeping.
+// 10 LSTM output-layer step, 11 BPTT epochs, 12 BPTT weight grads+Adam, 13 stream init, 14 bit bookkeeping,
+// 16 gate selection, 17 layer-0 dot products, 18 layer-0 chain, 19 layer 1, 20 final neuron (6 = what is left
+// of the predict phase: the barrier).
 #if defined(__CUDA_ARCH__)
 #define GMX_CLOCK() clock64()
 #else
@@ -177,7 +179,7 @@ struct StreamSmem {
     float l_err256[256];         //   LSTM scratch (forward pass, Perceive, BPTT)
   };
   uint8_t l_hist[L_HORIZON], l_symin[L_HORIZON];
-  uint32_t l_epoch, l_update_steps, l_old_input;
+  uint32_t l_epoch, l_update_steps, l_old_input, l_fused;
   // coder
   uint32_t x1, x2, x;
   uint64_t out_pos, out_cap, in_pos, in_len;
@@ -298,6 +300,34 @@ GMX_DEV inline uint32_t SmId() {
 #endif
 }
 
+// Cache-policy helpers. The LSTM gate weights (184 KB per stream) are re-read every byte and are the
+// only large per-stream data worth keeping in the 126 MB L2; the output-layer copies (52 KB read + 52 KB
+// written per byte out of a 5.2 MB ring) are pure streaming traffic and are marked evict-first.
+GMX_DEV inline void PrefetchL2Keep(const void* p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+GMX_DEV inline float4 LoadStream4(const float4* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldcs(p);
+#else
+  return *p;
+#endif
+}
+GMX_DEV inline void StoreStream4(float4* p, float4 v) {
+#if defined(__CUDA_ARCH__)
+  __stcs(p, v);
+#else
+  *p = v;
+#endif
+}
+GMX_DEV inline void PrefetchRangeKeep(const void* p, uint32_t bytes, int t, int nthr) {
+  for (uint32_t o = (uint32_t)t * 128u; o < bytes; o += (uint32_t)nthr * 128u) PrefetchL2Keep((const char*)p + o);
+}
+
 // L2 prefetch of `bytes` bytes at p, cooperatively by the `nthr` threads numbered t = 0..nthr-1.
 GMX_DEV inline void PrefetchRange(const void* p, uint32_t bytes, int t, int nthr) {
   for (uint32_t o = (uint32_t)t * 128u; o < bytes; o += (uint32_t)nthr * 128u) PrefetchL2((const char*)p + o);
@@ -366,7 +396,7 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
   if (tid == 0) {
     s.final_out = 0; s.prob = 0.5f; s.ring_pos = 0; s.new_bit = 0; s.recent_bits = 1; s.bb = 0;
     s.first_prediction = 1; s.error = 0; s.steps = 0; s.pool_next = 1; s.hist_len = 0; s.sparse_used = 0; s.nswap = 0;
-    s.l_epoch = 0; s.l_update_steps = 0; s.l_old_input = 0;
+    s.l_epoch = 0; s.l_update_steps = 0; s.l_old_input = 0; s.l_fused = 0;
     s.x1 = 0; s.x2 = 0xffffffffu; s.x = 0;
     for (int i = 0; i < GMX_PROF_SLOTS; ++i) s.prof[i] = 0;
   }
@@ -379,10 +409,42 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
   GMX_PROF(13);
 }
 
+// Output layer of the next epoch slot: copy of the slot just used plus one SGD step (Lstm::Perceive
+// lstm.cpp:81-88). `byte` is the symbol that followed the forward pass of slot `last`.
+template <int NT>
+GMX_DEV void LstmOutputStep(StreamSmem& s, const Arena& A, uint32_t last, uint32_t cur, uint32_t byte, int tid) {
+  const ArenaLayout& L = *A.L;
+  const float* wl = A.at<float>(L.l_wout) + (size_t)last * L_HID * L_NOUT;
+  float* wc = A.at<float>(L.l_wout) + (size_t)cur * L_HID * L_NOUT;
+  const float lr = (float)0.03;
+  {
+    const int q = tid & (L_NOUT / 4 - 1), half = tid / (L_NOUT / 4);   // outputs 4q..4q+3, rows of half `half`
+    float le[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t i = 4 * q + k;
+      const float err = i == byte ? f_sub(s.lprob[i], 1.0f) : s.lprob[i];
+      le[k] = f_mul(lr, err);
+    }
+    const float4* wl4 = (const float4*)wl + q;
+    float4* wc4 = (float4*)wc + q;
+    const int j0 = half * ((L_HID + NT / (L_NOUT / 4) - 1) / (NT / (L_NOUT / 4)));
+    const int j1 = j0 + (L_HID + NT / (L_NOUT / 4) - 1) / (NT / (L_NOUT / 4)) < L_HID ? j0 + (L_HID + NT / (L_NOUT / 4) - 1) / (NT / (L_NOUT / 4)) : L_HID;
+#pragma unroll 13
+    for (int j = j0; j < j1; ++j) {
+      const float h = s.l_hidden[j];
+      float4 w = LoadStream4(wl4 + j * (L_NOUT / 4));
+      w.x = f_sub(w.x, f_mul(le[0], h)); w.y = f_sub(w.y, f_mul(le[1], h));
+      w.z = f_sub(w.z, f_mul(le[2], h)); w.w = f_sub(w.w, f_mul(le[3], h));
+      StoreStream4(wc4 + j * (L_NOUT / 4), w);
+    }
+  }
+}
+
 // ---- LSTM forward at a byte boundary (Lstm::Predict lstm.cpp:91-122, LstmLayer::ForwardPass
 // lstm-layer.cpp:198-241). Precondition: s.ppm holds the normalised PPMd distribution. --------------
 template <int NT>
-GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, int tid) {
+GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, int known_byte, int tid) {
   const ArenaLayout& L = *A.L;
   const uint32_t e = s.l_epoch;
   const uint32_t sym = s.ctx[C_LAST_BYTE];
@@ -392,8 +454,10 @@ GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, i
   // short enough that the lines are still in L2 when the dot products reach them).
   {
     const float* W = A.at<float>(L.l_w);
-    for (int g = 0; g < 3; ++g) PrefetchRange(W + ((size_t)g * L_ROW + L_NOUT) * L_CELLS, L_NIN * L_CELLS * 4, tid, NT);
+#if !defined(GMX_NO_LSTM_PREFETCH)
+    for (int g = 0; g < 3; ++g) PrefetchRangeKeep(W + ((size_t)g * L_ROW + L_NOUT) * L_CELLS, L_NIN * L_CELLS * 4, tid, NT);
     PrefetchRange(A.at<float>(L.l_wout) + (size_t)e * L_HID * L_NOUT, L_HID * L_NOUT * 4, tid, NT);
+#endif
   }
   // layer_input[e] = [ppm 256 | hidden 50 | 1]  (SetInput lstm.cpp:45-50, copy :94-96)
   for (int i = tid; i < L_NIN; i += NT) {
@@ -500,8 +564,17 @@ GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, i
     s.lprob[i] = v;
     A.at<float>(L.l_out)[e * L_NOUT + i] = v;
   }
-  if (tid == 0) s.l_epoch = e + 1 == L_HORIZON ? 0 : e + 1;
+  if (tid == 0) { s.l_epoch = e + 1 == L_HORIZON ? 0 : e + 1; s.l_fused = known_byte >= 0 && e + 1 < L_HORIZON; }
   BlockSync();
+  // Compress knows the byte this distribution is about to code, so the output-layer step that
+  // Lstm::Perceive performs after the byte (same operands: these probabilities, this hidden state, the
+  // layer of slot e) can run now, while slot e is still in L2 from the dot products above: one HBM read of
+  // the 52 KB layer per byte instead of two. Not in the last slot: there Perceive runs BPTT over all 100
+  // stored layers before it overwrites slot 0.
+  if (known_byte >= 0 && e + 1 < L_HORIZON) {
+    LstmOutputStep<NT>(s, A, e, e + 1, (uint32_t)known_byte, tid);
+    BlockSync();
+  }
 }
 
 // Truncated BPTT over the 100 stored steps + Adam (Lstm::Perceive lstm.cpp:57-79,
@@ -536,7 +609,7 @@ GMX_DEV void LstmBptt(StreamSmem& s, const Arena& A, const StreamParams& P, int 
       const float4* er4 = (const float4*)s.l_err256;
 #pragma unroll 4
       for (int i = 0; i < L_NOUT / 4; ++i) {
-        const float4 w = wo4[i], e = er4[i];
+        const float4 w = LoadStream4(wo4 + i), e = er4[i];
         he = f_add(he, f_mul(w.x, e.x)); he = f_add(he, f_mul(w.y, e.y));
         he = f_add(he, f_mul(w.z, e.z)); he = f_add(he, f_mul(w.w, e.w));
       }
@@ -708,32 +781,7 @@ GMX_DEV void LstmPerceive(StreamSmem& s, const Arena& A, const StreamParams& P, 
     BlockSync();
     LstmBptt<NT, PROF>(s, A, P, tid);
   }
-  // output layer: copy the previous epoch's layer, then one SGD step (lstm.cpp:81-88)
-  const float* wl = A.at<float>(L.l_wout) + (size_t)last * L_HID * L_NOUT;
-  float* wc = A.at<float>(L.l_wout) + (size_t)cur * L_HID * L_NOUT;
-  const float lr = (float)0.03;
-  {
-    const int q = tid & (L_NOUT / 4 - 1), half = tid / (L_NOUT / 4);   // outputs 4q..4q+3, rows of half `half`
-    float le[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t i = 4 * q + k;
-      const float err = i == byte ? f_sub(s.lprob[i], 1.0f) : s.lprob[i];
-      le[k] = f_mul(lr, err);
-    }
-    const float4* wl4 = (const float4*)wl + q;
-    float4* wc4 = (float4*)wc + q;
-    const int j0 = half * ((L_HID + NT / (L_NOUT / 4) - 1) / (NT / (L_NOUT / 4)));
-    const int j1 = j0 + (L_HID + NT / (L_NOUT / 4) - 1) / (NT / (L_NOUT / 4)) < L_HID ? j0 + (L_HID + NT / (L_NOUT / 4) - 1) / (NT / (L_NOUT / 4)) : L_HID;
-#pragma unroll 13
-    for (int j = j0; j < j1; ++j) {
-      const float h = s.l_hidden[j];
-      float4 w = wl4[j * (L_NOUT / 4)];
-      w.x = f_sub(w.x, f_mul(le[0], h)); w.y = f_sub(w.y, f_mul(le[1], h));
-      w.z = f_sub(w.z, f_mul(le[2], h)); w.w = f_sub(w.w, f_mul(le[3], h));
-      wc4[j * (L_NOUT / 4)] = w;
-    }
-  }
+  if (!s.l_fused) LstmOutputStep<NT>(s, A, last, cur, byte, tid);
   BlockSync();
   GMX_PROF(10);
 }
@@ -789,7 +837,7 @@ GMX_DEV inline void PrefetchMixerSet(const StreamSmem& s, const Arena& A, int m,
 
 // ---- everything that only happens when a new byte has been perceived (recent_bits == 1) ----------
 template <int NT, bool PROF>
-GMX_DEV void ByteBoundary(StreamSmem& s, const Arena& A, const StreamParams& P, int tid) {
+GMX_DEV void ByteBoundary(StreamSmem& s, const Arena& A, const StreamParams& P, int known_byte, int tid) {
   const ArenaLayout& L = *A.L;
   const uint32_t last_byte = s.ctx[C_LAST_BYTE];
   // (1) contexts: intervals, hashed skip contexts, indirect-hash tables; PPMd on its own thread.
@@ -873,7 +921,7 @@ GMX_DEV void ByteBoundary(StreamSmem& s, const Arena& A, const StreamParams& P, 
   BlockSync();
   // (3) LSTM forward (LstmModel::Predict byte part, lstm-model.cpp:19-34)
   GMX_PROF(1);
-  LstmForward<NT>(s, A, P, tid);
+  LstmForward<NT>(s, A, P, known_byte, tid);
   GMX_PROF(2);
   // lstm_prediction_context = first index of the maximum, strict > from 0 (lstm-model.cpp:26-33)
   {
@@ -909,7 +957,8 @@ GMX_DEV void ByteBoundary(StreamSmem& s, const Arena& A, const StreamParams& P, 
 
 // ---- Predictor::Predict (predictor.cpp:360-376) --------------------------------------------------
 template <int NT, bool PROF>
-GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, int tid) {
+// known_byte: the byte whose bits are being predicted if the caller knows it (compress), else -1.
+GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, int known_byte, int tid) {
   const ArenaLayout& L = *A.L;
   if (tid == 0) {  // BasicContexts::Predict basic-contexts.cpp:21-40
     if (s.first_prediction) {
@@ -934,7 +983,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
   }
   BlockSync();
   GMX_PROF(14);
-  if (s.bb) ByteBoundary<NT, PROF>(s, A, P, tid);
+  if (s.bb) ByteBoundary<NT, PROF>(s, A, P, known_byte, tid);
   const uint32_t bitctx = s.ctx[C_BIT_CONTEXT];
   const bool zero_inactive = s.analysis != 0;  // predictor.cpp:362-365
   if (tid < NIND) {  // Indirect::Predict indirect.cpp:28-45
@@ -1048,6 +1097,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     for (int i = tid - 64; i < NPRED; i += 32) s.xe[i] = s.act[i] ? s.preds[i] : 0.0f;
   }
   BlockSync();
+  GMX_PROF(16);
   // Swap staged weight sets, one queued mixer per round, one weight per thread: first all write-backs,
   // then all fetches (zero weights == no set yet: the dot product of zeros is +0, exactly the
   // reference's "data == nullptr" output).
@@ -1098,6 +1148,8 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
 #pragma unroll
       for (int i = NPRED / 4 * 4; i < NPRED; ++i) acc = f_add(acc, f_mul(s.xe[i], w[i]));
     }
+    GMX_PROF(17);
+    __syncwarp();   // converged warp: the shuffles below take their fast path
     {
       // serial chain of the layer: neuron j's finished output feeds every later neuron (mixer.cpp:60-70).
       // The 23 chain weights sit in registers so that one step is shuffle -> mul -> add.
@@ -1112,6 +1164,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     }
     if (lane < NL0) s.l0_out[lane] = acc;
     __syncwarp();
+    GMX_PROF(18);
     const float skip = s.preds[P_LSTM];
     const float* w1 = s.w + NL0 * WSTRIDE0 + (lane < NL1 ? lane : 0) * WSTRIDE1;
     acc = 0.0f;
@@ -1125,6 +1178,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
         acc = f_add(acc, f_mul(x.z, v.z)); acc = f_add(acc, f_mul(x.w, v.w));
       }
     }
+    __syncwarp();
     // a layer-1 output is complete (skip connection added last, weights[num_layer0 + output_index],
     // mixer.cpp:77-83) before the next layer-1 neuron reads it
 #pragma unroll 1
@@ -1137,6 +1191,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     }
     if (lane < NL1) s.l1_out[lane] = acc;
     __syncwarp();
+    GMX_PROF(19);
     if (lane == 0) {
       const float* w2 = s.w + NL0 * WSTRIDE0 + NL1 * WSTRIDE1;
       float p = 0.0f;
@@ -1156,6 +1211,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
       if (prob < eps) prob = eps; else if (prob > hi) prob = hi;
       s.prob = prob;
     }
+    GMX_PROF(20);
   }
   BlockSync();
   GMX_PROF(6);
@@ -1346,7 +1402,7 @@ GMX_DEV void CompressStream(StreamSmem& s, const Arena& A, const StreamParams& P
 #pragma unroll 1
     for (int j = 7; j >= 0; --j) {
       const int bit = (c >> j) & 1;
-      PredictBit<NT, PROF>(s, A, P, tid);
+      PredictBit<NT, PROF>(s, A, P, (int)c, tid);
       if (tid == 0) {
         if (tracing) Trace(s, P, pos * 8 + (7 - j));
         const uint32_t p16 = Discretize(s.prob);
@@ -1397,7 +1453,7 @@ GMX_DEV void DecompressStream(StreamSmem& s, const Arena& A, const StreamParams&
   for (uint64_t pos = 0; pos < n; ++pos) {
 #pragma unroll 1
     for (int j = 7; j >= 0; --j) {
-      PredictBit<NT, PROF>(s, A, P, tid);
+      PredictBit<NT, PROF>(s, A, P, -1, tid);
       if (tid == 0) {  // Decoder::Decode decoder.cpp:19-39
         const uint32_t p16 = Discretize(s.prob);
         const uint32_t r = s.x2 - s.x1;
@@ -1493,7 +1549,7 @@ __global__ void __launch_bounds__(NT) StepKernel(StepParams Q) {
     if (tid == 0 && Q.analysis >= 0) s.analysis = Q.analysis;
     BlockSync();
     if (Q.op == STEP_PREDICT) {
-      PredictBit<NT, false>(s, A, Q.P, tid);
+      PredictBit<NT, false>(s, A, Q.P, -1, tid);
       if (tid == 0) *Q.prob_out = s.prob;
     } else {
       LearnBit<NT, false>(s, A, Q.P, tid);

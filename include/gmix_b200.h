@@ -121,8 +121,8 @@ uint64_t gmx_kernel_launches(const gmx_ctx* ctx);    /* kernels launched by this
 double gmx_last_kernel_ms(const gmx_ctx* ctx);       /* device time of the last stream kernel (CUDA events) */
 int gmx_device_sm_count(const gmx_ctx* ctx);
 
-/* Phase profiler: when on, every stream accumulates 16 cycle counters (slots documented in
- * gmix_b200/csrc/stream_kernel.cuh); gmx_get_profile copies up to max_streams x 16 counters of the
+/* Phase profiler: when on, every stream accumulates 24 cycle counters (slots documented in
+ * gmix_b200/csrc/stream_kernel.cuh); gmx_get_profile copies up to max_streams x 24 counters of the
  * last launch and returns the number of streams copied. */
 int gmx_set_profile(gmx_ctx* ctx, int on);
 int gmx_get_profile(gmx_ctx* ctx, uint64_t* out, uint32_t max_streams);
