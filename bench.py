@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--chunk-bytes", type=int, default=65536)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-decompress", action="store_true", help="skip the configs[2] leg (GPU decompress of the last step's streams)")
     ap.add_argument("--verify", type=int, default=1, help="streams per rank checked by a GPU decompress round trip after timing")
     return ap.parse_args()
 
@@ -328,6 +329,36 @@ def run_ours(args):
         want = make_chunks(chunk_ids(rank, total_steps - 1, n)[:k], size)
         assert back == want, "GPU decompress of a GPU-compressed stream does not reproduce the input"
 
+    # ---- configs[2]: GPU decompress of every stream of the last step, device resident, checked ---------
+    decomp = None
+    if not args.no_decompress:
+        d_back = torch.zeros(n * size + 16, dtype=torch.uint8, device=dev)
+        d_back_len = torch.zeros(n, dtype=torch.int64, device=dev)
+        d_back_off = in_off.to(dev)                     # capacity = the original stream length
+        # the compressed streams sit at out_off[i] with length d_len[i]; decompress reads in_off[i+1]-in_off[i]
+        # bytes per stream, so pack them contiguously first
+        lens = d_len.clone()
+        pack_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        pack_off[1:] = torch.cumsum(lens, 0)
+        idx = torch.arange(int(pack_off[-1].item()), device=dev)
+        which = torch.searchsorted(pack_off[1:], idx, right=True)
+        d_pack = d_out[out_off.to(dev)[which] + (idx - pack_off[which])]
+        barrier()
+        dv0, dv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dv0.record(stream)
+        ctx.decompress_batch_device(d_pack.data_ptr(), pack_off.data_ptr(), n, d_back.data_ptr(), d_back_off.data_ptr(),
+                                    d_back_len.data_ptr(), d_status.data_ptr(), size)
+        dv1.record(stream)
+        barrier()
+        dms = torch.tensor([dv0.elapsed_time(dv1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dms, op=dist.ReduceOp.MAX)
+        lossless = bool(torch.equal(d_back[:n * size], inputs[total_steps - 1][:n * size])) and int((d_status != 0).sum().item()) == 0
+        if not lossless:
+            raise SystemExit(f"bench.py: GPU decompress of the GPU-compressed streams is not lossless on rank {rank}")
+        decomp = {"value": world * n * size / (float(dms.item()) / 1e3) / 1e6, "unit": UNIT, "lossless_streams": n * world,
+                  "workload": "configs[2]: decompression of the same chunk set, every stream compared with its input"}
+
     # ---- end-to-end measurement through the host-pointer C ABI ---------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -374,7 +405,7 @@ def run_ours(args):
                          "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_kind": pk_kind,
                          "kernel": "gmx::StreamKernel<128, MODE_COMPRESS, 8, false>", "kernel_ms": kernel_ms_avg,
                          "algorithmic_bytes_per_input_byte": ALGO_BYTES_PER_INPUT_BYTE},
-            "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
+            "e2e": e2e, "decompress": decomp, "retried_streams": ctx.retried_streams, "gpu_launches": gpu_launches, "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(min(size, 8192))

@@ -93,7 +93,7 @@ inline ArenaLayout MakeLayout(uint64_t max_len, bool roomy = false) {
     if (typical < sets) sets = typical;
   }
   L.mix_pool_sets = (uint32_t)sets;
-  L.mix_set_stride = 116;  // 2 header words + up to 114 weights, 16-byte multiple
+  L.mix_set_stride = 120;  // 4 header words {steps, 0, 0, 0} + up to 116 weight slots (29 float4), 16-byte multiple
   L.mix_pool = take(sets * L.mix_set_stride * 4);
   const uint64_t wsz = 3ull * L_ROW * L_CELLS * 4;
   L.l_w = take(wsz); L.l_m = take(wsz); L.l_v = take(wsz);

@@ -140,7 +140,7 @@ struct StreamSmem {
   StreamTables T;
   // blackboard (ShortTermMemory)
   alignas(16) float preds[NPRED + 2];
-  alignas(4) uint8_t act[NPRED + 6];
+  alignas(4) uint8_t act[NPRED + NL0 + 2];   // prediction i is active; entries 90.. (layer-0 outputs) are always 1
   uint32_t ctx[C_COUNT + 2];
   alignas(16) float l0_out[NL0]; float l1_out[NL1], final_out, prob;   // l0_out | l1_out contiguous (final mixer input)
   float ppm[256], lprob[256];          // byte distributions of PPMd and LSTM
@@ -153,7 +153,7 @@ struct StreamSmem {
   uint32_t steps;                      // Mixer::steps_ (identical for all 33 mixers)
   // mixers
   alignas(16) float w[WTOTAL];
-  alignas(16) float xe[NPRED + 2];          // predictions with the inactive ones zeroed (mixer layer-0 input)
+  alignas(16) float xe[NPRED + NL0 + 2];    // layer-0 input vector: predictions (inactive ones zeroed) | layer-0 outputs
   uint32_t set_steps[NMIX], max_steps[NMIX], set_idx[NMIX], set_pool[NMIX];
   uint32_t swap_old[NMIX], swap_new[NMIX], nswap;   // queued set swaps of this bit
   uint8_t swap_m[NMIX + 3], shrink[NMIX + 3];
@@ -269,6 +269,14 @@ GMX_DEV inline void CpAsync4(void* smem_dst, const void* gmem_src) {
   *(uint32_t*)smem_dst = *(const uint32_t*)gmem_src;
 #endif
 }
+GMX_DEV inline void CpAsync16(void* smem_dst, const void* gmem_src) {   // both 16-byte aligned
+#if defined(__CUDA_ARCH__)
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+#else
+  memcpy(smem_dst, gmem_src, 16);
+#endif
+}
 GMX_DEV inline void CpAsyncWaitAll() {
 #if defined(__CUDA_ARCH__)
   asm volatile("cp.async.wait_all;" ::: "memory");
@@ -377,14 +385,14 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
   }
   // shared state
   for (int i = tid; i < NPRED + 2; i += NT) s.preds[i] = 0.0f;
-  for (int i = tid; i < NPRED + 6; i += NT) s.act[i] = 0;
+  for (int i = tid; i < NPRED + NL0 + 2; i += NT) s.act[i] = i >= NPRED;
   for (int i = tid; i < C_COUNT + 2; i += NT) s.ctx[i] = 0;
   for (int i = tid; i < NL0; i += NT) s.l0_out[i] = 0.0f;
   for (int i = tid; i < NL1; i += NT) s.l1_out[i] = 0.0f;
   for (int i = tid; i < 256; i += NT) { s.ppm[i] = (float)(1.0 / 256); s.lprob[i] = (float)(1.0 / 256); }
   for (int i = tid; i < 32; i += NT) s.ring[i] = 0;
   for (int i = tid; i < WTOTAL; i += NT) s.w[i] = 0.0f;
-  for (int i = tid; i < NPRED + 2; i += NT) s.xe[i] = 0.0f;
+  for (int i = tid; i < NPRED + NL0 + 2; i += NT) s.xe[i] = 0.0f;
   for (int i = tid; i < NMIX; i += NT) {
     s.set_steps[i] = 0; s.max_steps[i] = 1; s.set_idx[i] = 0xFFFFFFFFu; s.set_pool[i] = 0; s.shrink[i] = 0;
   }
@@ -830,7 +838,7 @@ GMX_DEV inline void PrefetchMixerSet(const StreamSmem& s, const Arena& A, int m,
   const uint32_t nid = A.at<uint32_t>(L.mix_dir[m])[c & ((1u << s.T.mixer[m].log2) - 1)];
   if (nid) {
     const float* rec = A.at<float>(L.mix_pool) + (size_t)nid * L.mix_set_stride;
-    const int bytes = (MixerNW(m) + 2) * 4;
+    const int bytes = (MixerNW(m) + 4) * 4;
     for (int o = 0; o < bytes; o += 128) PrefetchL2((const char*)rec + o);
   }
 }
@@ -1102,27 +1110,36 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
   // then all fetches (zero weights == no set yet: the dot product of zeros is +0, exactly the
   // reference's "data == nullptr" output).
   {
+    // Pool record = {steps, 0, 0, 0 | weights...}: header and weights are 16-byte aligned, a set moves as
+    // at most 29 float4. One warp per queued set, one float4 per lane.
     const uint32_t nswap = s.nswap;
-    float* pool = A.at<float>(L.mix_pool);
-    const uint32_t stride = L.mix_set_stride;
+    float4* pool = A.at<float4>(L.mix_pool);
+    const uint32_t stride4 = L.mix_set_stride / 4;
+    const int lane = tid & 31;
 #pragma unroll 1
-    for (uint32_t r = 0; r < nswap; ++r) {
+    for (uint32_t r = tid >> 5; r < nswap; r += NT / 32) {
       const int m = s.swap_m[r];
       const uint32_t old = s.swap_old[r];
-      if (old && tid < MixerNW(m) + 1) {
-        float* rec = pool + (size_t)old * stride;
-        if (tid == 0) ((uint32_t*)rec)[0] = s.set_steps[m]; else rec[1 + tid] = s.w[WOff(m) + tid - 1];
+      if (old && lane <= (MixerNW(m) + 3) / 4) {
+        float4* rec = pool + (size_t)old * stride4;
+        if (lane == 0) rec[0] = make_float4(u2f(s.set_steps[m]), 0.0f, 0.0f, 0.0f);
+        else rec[lane] = ((const float4*)(s.w + WOff(m)))[lane - 1];
       }
     }
+    __syncwarp();   // the same warp re-reads swap_* and overwrites the staged sets below
 #pragma unroll 1
-    for (uint32_t r = 0; r < nswap; ++r) {   // asynchronous copies: all queued sets are in flight together
+    for (uint32_t r = tid >> 5; r < nswap; r += NT / 32) {   // asynchronous copies: all queued sets in flight together
       const int m = s.swap_m[r];
       const uint32_t nid = s.swap_new[r];
-      if (tid < MixerNW(m) + 1) {
-        uint32_t* dst = tid == 0 ? &s.set_steps[m] : (uint32_t*)&s.w[WOff(m) + tid - 1];
-        const float* rec = pool + (size_t)nid * stride;
-        if (nid) CpAsync4(dst, tid == 0 ? rec : rec + 1 + tid); else *dst = 0u;
-        if (tid == 0) s.set_pool[m] = nid;
+      if (lane <= (MixerNW(m) + 3) / 4) {
+        const float4* rec = pool + (size_t)nid * stride4;
+        if (lane == 0) {
+          if (nid) CpAsync4(&s.set_steps[m], rec); else s.set_steps[m] = 0u;
+          s.set_pool[m] = nid;
+        } else {
+          float4* dst = (float4*)(s.w + WOff(m)) + (lane - 1);
+          if (nid) CpAsync16(dst, rec + lane); else *dst = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
       }
     }
     CpAsyncWaitAll();
@@ -1162,7 +1179,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
         if (lane > j && lane < NL0) acc = f_add(acc, f_mul(oj, cw[j]));
       }
     }
-    if (lane < NL0) s.l0_out[lane] = acc;
+    if (lane < NL0) { s.l0_out[lane] = acc; s.xe[NPRED + lane] = acc; }
     __syncwarp();
     GMX_PROF(18);
     const float skip = s.preds[P_LSTM];
@@ -1306,35 +1323,33 @@ GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int 
     const bool shrink = s.shrink[m] != 0;
     const float keep = f_sub(1.0f, 3.0e-6f);
     float* w = s.w + WOff(m);
-    int first = 0;
-    if (m < NL0) {  // inputs 0..87 = predictions, four per lane
-      first = NPRED / 4 * 4;
-      if (lane < NPRED / 4) {
+    if (m < NL0) {
+      // Layer 0: inputs = [90 predictions | outputs of the earlier layer-0 neurons] = s.xe[0 .. nw) (inactive
+      // predictions are +0 there and are skipped through the `use` bytes); one float4 per lane covers them all.
+      const int left = nw - 4 * lane;   // inputs of this lane's quad that exist
+      if (left > 0) {
         float4 v = ((float4*)w)[lane];
-        const float4 x = ((const float4*)s.preds)[lane];
-        const uint32_t on = ((const uint32_t*)s.act)[lane];
+        const float4 x = ((const float4*)s.xe)[lane];
+        uint32_t on = ((const uint32_t*)s.act)[lane];
+        if (left < 4) on &= 0x00ffffffu >> (8 * (3 - left));
         if (on & 0x000000ffu) v.x = f_sub(v.x, f_mul(upd, x.x));
         if (on & 0x0000ff00u) v.y = f_sub(v.y, f_mul(upd, x.y));
         if (on & 0x00ff0000u) v.z = f_sub(v.z, f_mul(upd, x.z));
         if (on & 0xff000000u) v.w = f_sub(v.w, f_mul(upd, x.w));
-        if (shrink) { v.x = f_mul(v.x, keep); v.y = f_mul(v.y, keep); v.z = f_mul(v.z, keep); v.w = f_mul(v.w, keep); }
+        if (shrink) {   // applies to every weight of the set (mixer.cpp:170-174), used or not; pad lanes hold 0
+          v.x = f_mul(v.x, keep); v.y = f_mul(v.y, keep); v.z = f_mul(v.z, keep); v.w = f_mul(v.w, keep);
+        }
         ((float4*)w)[lane] = v;
       }
-    }
+    } else {
+      const int nin = m < NL0 + NL1 ? NL0 + (m - NL0) : NL0 + NL1;  // inputs before the skip connection
 #pragma unroll 1
-    for (int i = first + lane; i < nw; i += 32) {
-      float x; bool use = true;
-      if (m < NL0) {
-        if (i < NPRED) { use = s.act[i] != 0; x = s.preds[i]; }
-        else x = s.l0_out[i - NPRED];
-      } else {
-        const int nin = m < NL0 + NL1 ? NL0 + (m - NL0) : NL0 + NL1;  // inputs before the skip connection
-        x = i < NL0 ? s.l0_out[i] : i < nin ? s.l1_out[i - NL0] : s.preds[P_LSTM];
+      for (int i = lane; i < nw; i += 32) {
+        const float x = i < NL0 ? s.l0_out[i] : i < nin ? s.l1_out[i - NL0] : s.preds[P_LSTM];
+        float v = f_sub(w[i], f_mul(upd, x));
+        if (shrink) v = f_mul(v, keep);
+        w[i] = v;
       }
-      float v = w[i];
-      if (use) v = f_sub(v, f_mul(upd, x));
-      if (shrink) v = f_mul(v, keep);
-      w[i] = v;
     }
   }
   if (tid == 0) { s.steps++; s.hist_len = hist_after; }

@@ -180,6 +180,7 @@ template <typename T> inline T atomicCAS(T* p, T cmp, T v) { T o = *p; if (o == 
 struct uint4 { unsigned x, y, z, w; };
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 
 #endif  // GMIX_TESTS_CUDA_EMU_H_
