@@ -16,11 +16,19 @@ inline uint64_t AlignUp(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
 inline uint64_t Pow2Ceil(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
 
+// What a stream that starts from a checkpoint already occupies (checkpoint.h: Count): added on top of what
+// max_len new bytes can need.
+struct Preload {
+  uint64_t sparse_entries = 0, mixer_sets = 0, ppmd_unit_bytes = 0, ppmd_text_bytes = 0, history_bytes = 0, steps = 0;
+};
+
 // max_len = longest stream (in uncompressed bytes) the arena must hold.
 // roomy = false: the shared sparse map and the mixer weight-set pool are sized for what text-like data
 // touches (a stream that needs more ends with GMX_ERR_SPARSE_FULL / GMX_ERR_MIXER_POOL and the host
 // re-runs it in a roomy arena); roomy = true: both are sized for the worst case of max_len bytes.
-inline ArenaLayout MakeLayout(uint64_t max_len, bool roomy = false) {
+inline ArenaLayout MakeLayout(uint64_t max_len, bool roomy = false, const Preload* pre = nullptr) {
+  const Preload none;
+  if (!pre) pre = &none;
   static const IndirectSpec ind[NIND] = {GMX_INDIRECT_SPECS};
   static const IHSpec ih[NIH] = {GMX_IH_SPECS};
   static const MatchSpec mt[NMATCH] = {GMX_MATCH_SPECS};
@@ -30,7 +38,7 @@ inline ArenaLayout MakeLayout(uint64_t max_len, bool roomy = false) {
   uint64_t off = 0;
   auto take = [&](uint64_t bytes) { uint64_t o = off; off = AlignUp(off + bytes, 256); return o; };
   // Which big tables go into the shared sparse map? Worst-case entry count vs their dense size.
-  uint64_t worst = 64, dense_bytes = 0;
+  uint64_t worst = 64 + pre->sparse_entries, dense_bytes = 0;
   uint32_t next_sid = 1;
   for (int k = 0; k < NIND; ++k) {
     L.ind_size[k] = (1u << ind[k].log2) * 256 + 1;  // indirect.cpp:15-19
@@ -55,7 +63,7 @@ inline ArenaLayout MakeLayout(uint64_t max_len, bool roomy = false) {
   // Text touches ~5.2e5 * (len / 4096)^0.72 slots (measured on the synthetic-text chunks: 517 K at 4 KiB,
   // 1.45 M at 16 KiB, 3.6 M at 64 KiB); 35 % head room on top, load limit 3/4.
   const double typical = 5.2e5 * pow((double)(max_len > 4096 ? max_len : 4096) / 4096.0, 0.72) * 1.35;
-  uint64_t cap = Pow2Ceil(roomy ? worst * 4 / 3 + 64 : (uint64_t)(typical * 4.0 / 3.0) + 64);
+  uint64_t cap = Pow2Ceil(roomy ? worst * 4 / 3 + 64 : (uint64_t)(typical * 4.0 / 3.0) + pre->sparse_entries * 4 / 3 + 64);
   const uint64_t cap_worst = Pow2Ceil(worst * 4 / 3 + 64);
   if (cap > cap_worst) cap = cap_worst;
   if (cap * 8 >= dense_bytes || cap > (1ull << 31)) {  // long streams: the dense tables are smaller
@@ -74,13 +82,13 @@ inline ArenaLayout MakeLayout(uint64_t max_len, bool roomy = false) {
     if (!L.match_sid[k]) L.match_tab[k] = take((4ull << mt[k].log2));
   L.match_pred = take(NMATCH * 256 * 4);
   L.match_cnt = take(NMATCH * 256 * 4);
-  L.history_cap = max_len + 8;
+  L.history_cap = max_len + 8 + pre->history_bytes;
   L.history = take(L.history_cap);
   for (int k = 0; k < NIH; ++k)
     if (!L.ih_sid[k]) L.ih_tab[k] = take(4ull << ih[k].log2);
   // Weight-set pool: a mixer can create at most one set per distinct gate context it ever sees:
   // min(table size, bytes + 1) for byte-level contexts, min(table size, bits + 1) otherwise.
-  uint64_t sets = 1;
+  uint64_t sets = 1 + pre->mixer_sets;
   for (int m = 0; m < NMIX; ++m) {
     L.mix_dir[m] = take(4ull << mx[m].log2);
     const uint64_t t = 1ull << mx[m].log2;
@@ -89,7 +97,7 @@ inline ArenaLayout MakeLayout(uint64_t max_len, bool roomy = false) {
     sets += t < seen ? t : seen;
   }
   if (!roomy) {  // text creates ~0.35 sets per byte
-    const uint64_t typical = 8192 + max_len * 3 / 4;
+    const uint64_t typical = 8192 + max_len * 3 / 4 + pre->mixer_sets;
     if (typical < sets) sets = typical;
   }
   L.mix_pool_sets = (uint32_t)sets;
@@ -114,8 +122,8 @@ inline ArenaLayout MakeLayout(uint64_t max_len, bool roomy = false) {
   // units this stream can need (~19 B/byte on text; 400 B/byte worst-case sizing)
   // and whose bottom holds the text area.
   {
-    const uint64_t want_units = (roomy ? 400 : 90) * max_len + (256u << 10);
-    const uint64_t want_text = max_len + 64;
+    const uint64_t want_units = (roomy ? 400 : 90) * max_len + (256u << 10) + pre->ppmd_unit_bytes;
+    const uint64_t want_text = max_len + 64 + pre->ppmd_text_bytes;
     uint64_t P = 1ull << 20;
     for (;; P <<= 1) {
       const uint64_t text_room = PPMD_UNITS_START % P, units_room = P - text_room;

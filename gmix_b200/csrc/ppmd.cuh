@@ -24,9 +24,11 @@
 
 #if defined(__CUDACC__)
 #define GMX_DEV __device__
+#define GMX_HD __host__ __device__
 #define GMX_NOINLINE __noinline__
 #else
 #define GMX_DEV
+#define GMX_HD
 #define GMX_NOINLINE
 #endif
 
@@ -54,6 +56,22 @@ struct PpmdState {
   PpmdSee2 dummy_see2;
   uint8_t indx2units[PPMD_N_INDEXES], units2indx[128], ns2bs[256], qtable[260];
 };
+
+// Constant lookup tables of the model (PPMD_STARTUP :375-400); also filled by the host when a checkpoint
+// is turned into an arena image (checkpoint.h).
+GMX_HD inline void PpmdFillTables(PpmdState* S) {
+  int i, k, m, step;
+  for (i = 0, k = 1; i < 4; i++, k += 1) S->indx2units[i] = (uint8_t)k;
+  for (k++; i < 8; i++, k += 2) S->indx2units[i] = (uint8_t)k;
+  for (k++; i < 12; i++, k += 3) S->indx2units[i] = (uint8_t)k;
+  for (k++; i < (int)PPMD_N_INDEXES; i++, k += 4) S->indx2units[i] = (uint8_t)k;
+  for (k = 0, i = 0; k < 128; k++) { i += S->indx2units[i] < k + 1; S->units2indx[k] = (uint8_t)i; }
+  S->ns2bs[0] = 0; S->ns2bs[1] = 2; S->ns2bs[2] = 2;
+  for (i = 3; i < 29; i++) S->ns2bs[i] = 4;
+  for (i = 29; i < 256; i++) S->ns2bs[i] = 6;
+  for (i = 0; i < 5; i++) S->qtable[i] = (uint8_t)i;
+  for (m = i = 5, k = step = 1; i < 260; i++) { S->qtable[i] = (uint8_t)m; if (!--k) { k = ++step; m++; } }
+}
 
 struct Ppmd {
   PpmdState* S;
@@ -175,17 +193,8 @@ struct Ppmd {
 
   // ---- model start: PPMD_STARTUP :375-400 + StartModelRare :659-713 ---------------------------
   GMX_DEV GMX_NOINLINE void Init() const {
-    int i, k, m, step;
-    for (i = 0, k = 1; i < 4; i++, k += 1) S->indx2units[i] = (uint8_t)k;
-    for (k++; i < 8; i++, k += 2) S->indx2units[i] = (uint8_t)k;
-    for (k++; i < 12; i++, k += 3) S->indx2units[i] = (uint8_t)k;
-    for (k++; i < (int)PPMD_N_INDEXES; i++, k += 4) S->indx2units[i] = (uint8_t)k;
-    for (k = 0, i = 0; k < 128; k++) { i += S->indx2units[i] < k + 1; S->units2indx[k] = (uint8_t)i; }
-    S->ns2bs[0] = 0; S->ns2bs[1] = 2; S->ns2bs[2] = 2;
-    for (i = 3; i < 29; i++) S->ns2bs[i] = 4;
-    for (i = 29; i < 256; i++) S->ns2bs[i] = 6;
-    for (i = 0; i < 5; i++) S->qtable[i] = (uint8_t)i;
-    for (m = i = 5, k = step = 1; i < 260; i++) { S->qtable[i] = (uint8_t)m; if (!--k) { k = ++step; m++; } }
+    int i, k;
+    PpmdFillTables(S);
     for (i = 0; i < 256; i++) S->char_mask[i] = 0;
     S->esc_count = 1;
     S->order_fall = PPMD_MAX_ORDER;

@@ -108,6 +108,14 @@ struct StreamParams {
   uint32_t* usage;           // optional: 8 words per stream {sparse entries, mixer sets, PPMd unit bytes, history bytes,
                              // SM id, start us, end us (globaltimer, low 32 bits), 0}, or null
   unsigned long long* prof;  // optional: GMX_PROF_SLOTS cycle counters per stream (phase breakdown), or null
+  // Start every stream from a parked stream (a loaded checkpoint: Predictor::ReadCheckpoint predictor.cpp:406-420)
+  // instead of from scratch: arena image of layout->total bytes + StreamSmem image. null = from scratch.
+  const uint8_t* tmpl_arena; const uint32_t* tmpl_state;
+  uint32_t* final_state;     // optional: the stream's StreamSmem is parked here at its end (n_streams x sizeof(StreamSmem)), or null
+  int32_t analysis;          // -1: what the reference runner does for this mode; 0/1: forced (Predictor::EnableAnalysis)
+  // generation (runner_utils::RunGeneration runner-utils.cpp:158-221): `in` holds the prompts, out[sid * gen_bytes ..] the samples
+  uint32_t gen_bytes; float temperature;
+  const float* rand_u; uint64_t rand_stride;   // rand()/RAND_MAX draws, one per generated bit; stream sid reads rand_u[sid * rand_stride + k]
 };
 
 // ---- device constant tables --------------------------------------------------------------------
@@ -351,6 +359,24 @@ template <int NT, bool PROF>
 GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, int tid) {
   const ArenaLayout& L = *A.L;
   if (tid == 0) { s.prof_t = GMX_CLOCK(); s.t_start_us = (uint32_t)(GlobalTimerNs() / 1000ull); }
+  if (P.tmpl_arena) {   // clone of a parked stream: arena image, then everything of StreamSmem behind the launch tables
+    const uint4* src = (const uint4*)P.tmpl_arena;
+    uint4* dst = (uint4*)A.base;
+    const uint64_t n16 = L.total / 16;
+    for (uint64_t i = tid; i < n16; i += NT) dst[i] = src[i];
+    constexpr int kFirst = (int)(sizeof(StreamTables) / 4), kWords = (int)(sizeof(StreamSmem) / 4);
+    uint32_t* sw = (uint32_t*)&s;
+    for (int i = kFirst + tid; i < kWords; i += NT) sw[i] = P.tmpl_state[i];
+    BlockSync();
+    if (tid == 0) {
+      s.error = 0; s.nswap = 0; s.x1 = 0; s.x2 = 0xffffffffu; s.x = 0;
+      for (int i = 0; i < GMX_PROF_SLOTS; ++i) s.prof[i] = 0;
+      s.prof_t = GMX_CLOCK(); s.t_start_us = (uint32_t)(GlobalTimerNs() / 1000ull);
+    }
+    BlockSync();
+    GMX_PROF(13);
+    return;
+  }
   for (int k = 0; k < NIND; ++k)
     if (!L.ind_sid[k]) FillWords<NT>(A.at<uint32_t>(L.ind_tab[k]), ((uint64_t)L.ind_size[k] + 1) / 2, 0x00FF00FFu, tid);
   if (L.sparse_mask) {
@@ -377,6 +403,7 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
   for (int i = tid; i < 8 * 3 * L_CELLS; i += NT) A.at<float>(L.l_gb)[i] = i < 3 * L_CELLS ? 1.0f : 0.0f;
   FillWords<NT>(A.at<uint32_t>(L.l_wout), L_HID * L_NOUT, 0u, tid);  // epoch slot 0; others are written before read
   for (int e = tid; e < L_HORIZON; e += NT) A.at<float>(L.l_lin)[e * (L_NIN + 1) + L_NIN - 1] = 1.0f;
+  for (int i = tid; i < L_HORIZON * L_NOUT; i += NT) A.at<float>(L.l_out)[i] = (float)(1.0 / L_NOUT);  // lstm.cpp:19 (only a checkpoint ever shows it)
   // PPMd heap must start zeroed (mod_ppmd.cpp relies on fresh pages)
   {
     uint4* z = A.at<uint4>(L.p_heap);
@@ -1397,6 +1424,17 @@ GMX_DEV inline void WriteUsage(const StreamSmem& s, const Arena& A, const Stream
   u[4] = SmId(); u[5] = s.t_start_us; u[6] = (uint32_t)(GlobalTimerNs() / 1000ull); u[7] = 0;
 }
 
+// Parks the stream's shared-memory state in global memory (with the arena it is the whole stream: what
+// Predictor::WriteCheckpoint serialises, checkpoint.h FromArena).
+template <int NT>
+GMX_DEV void ParkState(const StreamSmem& s, const StreamParams& P, uint32_t sid, int tid) {
+  if (!P.final_state) return;
+  constexpr int kWords = (int)(sizeof(StreamSmem) / 4);
+  uint32_t* dst = P.final_state + (size_t)sid * kWords;
+  const uint32_t* sw = (const uint32_t*)&s;
+  for (int i = tid; i < kWords; i += NT) dst[i] = sw[i];
+}
+
 // runner_utils::Compress (runner-utils.cpp:43-67) incl. the 5-byte header of RunCompression (:109).
 template <int NT, bool PROF>
 GMX_DEV void CompressStream(StreamSmem& s, const Arena& A, const StreamParams& P, uint32_t sid, int tid) {
@@ -1406,7 +1444,7 @@ GMX_DEV void CompressStream(StreamSmem& s, const Arena& A, const StreamParams& P
   InitStream<NT, PROF>(s, A, P, tid);
   if (tid == 0) {
     s.out_pos = 0; s.out_cap = P.out_off[sid + 1] - P.out_off[sid];
-    s.analysis = (8 * n / 1000) > 0;  // EnableAnalysis(8*n/1000) -> predictions zeroed every bit
+    s.analysis = P.analysis >= 0 ? P.analysis : (8 * n / 1000) > 0;  // EnableAnalysis(8*n/1000) -> predictions zeroed every bit
     for (int i = 4; i >= 0; --i) PutByte(s, out, (uint32_t)(n >> (8 * i)) & 0xff);
   }
   BlockSync();
@@ -1444,6 +1482,8 @@ GMX_DEV void CompressStream(StreamSmem& s, const Arena& A, const StreamParams& P
     if (PROF && P.prof) for (int i = 0; i < GMX_PROF_SLOTS; ++i) P.prof[(size_t)sid * GMX_PROF_SLOTS + i] = s.prof[i];
   }
   BlockSync();
+  ParkState<NT>(s, P, sid, tid);
+  BlockSync();
 }
 
 // runner_utils::Decompress (runner-utils.cpp:69-86) + ReadHeader (:29-36). Analysis is never on.
@@ -1455,7 +1495,7 @@ GMX_DEV void DecompressStream(StreamSmem& s, const Arena& A, const StreamParams&
   if (tid == 0) {
     s.in_pos = 0; s.in_len = P.in_off[sid + 1] - P.in_off[sid];
     s.out_pos = 0; s.out_cap = P.out_off[sid + 1] - P.out_off[sid];
-    s.analysis = 0;
+    s.analysis = P.analysis >= 0 ? P.analysis : 0;
     uint64_t len = 0;
     for (int i = 0; i <= 4; ++i) len = (len << 8) + GetByte(s, in);
     if (s.in_len < 5 || len > s.out_cap) { s.error = s.in_len < 5 ? GMX_ERR_BAD_HEADER : GMX_ERR_OUTPUT_CAP; len = 0; }
@@ -1493,6 +1533,60 @@ GMX_DEV void DecompressStream(StreamSmem& s, const Arena& A, const StreamParams&
     if (PROF && P.prof) for (int i = 0; i < GMX_PROF_SLOTS; ++i) P.prof[(size_t)sid * GMX_PROF_SLOTS + i] = s.prof[i];
   }
   BlockSync();
+  ParkState<NT>(s, P, sid, tid);
+  BlockSync();
+}
+
+// runner_utils::RunGeneration (runner-utils.cpp:158-221): the prompt (all but its last byte) is consumed WITH
+// learning, then gen_bytes bytes are sampled bit by bit without Learn: prob = Logistic(Logit(prob) / temperature),
+// bit = r < prob with r the next rand()/RAND_MAX draw, Perceive(bit), Predict().
+template <int NT, bool PROF>
+GMX_DEV void GenerateStream(StreamSmem& s, const Arena& A, const StreamParams& P, uint32_t sid, int tid) {
+  const uint8_t* in = P.in + P.in_off[sid];
+  const uint64_t n = P.in_off[sid + 1] - P.in_off[sid];
+  uint8_t* out = P.out + (size_t)sid * P.gen_bytes;
+  const float* ru = P.rand_u + (size_t)sid * P.rand_stride;
+  InitStream<NT, PROF>(s, A, P, tid);
+  if (tid == 0) s.analysis = P.analysis >= 0 ? P.analysis : (8 * (uint64_t)P.gen_bytes / 1000) > 0;   // :177
+  BlockSync();
+#pragma unroll 1
+  for (uint64_t pos = 0; pos + 1 < n; ++pos) {   // :187-194
+    const uint32_t c = in[pos];
+#pragma unroll 1
+    for (int j = 7; j >= 0; --j) {
+      PredictBit<NT, PROF>(s, A, P, -1, tid);
+      if (tid == 0) s.new_bit = (c >> j) & 1;
+      BlockSync();
+      LearnBit<NT, PROF>(s, A, P, tid);
+      if (s.error) break;
+    }
+    if (s.error) break;
+  }
+  if (!s.error) {
+    PredictBit<NT, PROF>(s, A, P, -1, tid);   // :198
+#pragma unroll 1
+    for (uint32_t i = 0; i < P.gen_bytes && !s.error; ++i) {
+#pragma unroll 1
+      for (int j = 0; j < 8; ++j) {
+        if (tid == 0) {
+          const float r = ru[(size_t)i * 8 + j];
+          const float prob = Logistic(f_div(Logit(s.prob), P.temperature));
+          s.new_bit = r < prob ? 1 : 0;
+          if (j == 7) out[i] = (uint8_t)((s.recent_bits * 2 + s.new_bit) & 0xff);
+        }
+        BlockSync();
+        PredictBit<NT, PROF>(s, A, P, -1, tid);
+      }
+    }
+  }
+  BlockSync();
+  if (tid == 0) {
+    P.out_len[sid] = s.error ? 0 : P.gen_bytes; P.status[sid] = s.error;
+    WriteUsage(s, A, P, sid);
+  }
+  BlockSync();
+  ParkState<NT>(s, P, sid, tid);
+  BlockSync();
 }
 
 // Copies the launch's read-only tables into shared memory (StreamTables).
@@ -1512,7 +1606,7 @@ GMX_DEV void StageTables(StreamSmem& s, const StreamParams& P, int tid) {
 }
 
 // ---- kernel entry: persistent CTAs, one stream at a time, ids from an atomic queue ---------------
-enum : int { MODE_COMPRESS = 0, MODE_DECOMPRESS = 1 };
+enum : int { MODE_COMPRESS = 0, MODE_DECOMPRESS = 1, MODE_GENERATE = 2 };
 
 template <int NT, int MODE, int MINB, bool PROF>
 __global__ void __launch_bounds__(NT, MINB) StreamKernel(StreamParams P) {
@@ -1529,7 +1623,8 @@ __global__ void __launch_bounds__(NT, MINB) StreamKernel(StreamParams P) {
     if (q >= P.n_streams) break;
     const uint32_t sid = P.ids ? P.ids[q] : q;
     if (MODE == MODE_COMPRESS) CompressStream<NT, PROF>(s, A, P, sid, tid);
-    else DecompressStream<NT, PROF>(s, A, P, sid, tid);
+    else if (MODE == MODE_DECOMPRESS) DecompressStream<NT, PROF>(s, A, P, sid, tid);
+    else GenerateStream<NT, PROF>(s, A, P, sid, tid);
   }
 }
 

@@ -1,72 +1,183 @@
 // TEST-ONLY: runs the product's CUDA stream kernel under the CPU SIMT emulator (cuda_emu.h) on one
 // stream, so kernel logic can be checked against the oracle without a GPU.
 //   emu_main compress|decompress <in> <out> [bit_trace_out] [pred_trace_out]
+//   emu_main train    <in> <ckpt_prefix> [from_ckpt_prefix]   Predict/Perceive/Learn over <in> (analysis off), then the
+//                                                             stream is written as <ckpt_prefix>.short/.long (checkpoint.h)
+//   emu_main resume   <ckpt_prefix> <in> <out> [bit_trace_out]   `gmix -c <ckpt> <in> <out>`: compress starting from a checkpoint
+//   emu_main expand   <ckpt_prefix> <in> <out>                   `gmix -d <ckpt> <in> <out>`
+//   emu_main generate <ckpt_prefix> <prompt> <out> <size> <temperature>   `gmix -g ...` (sampling draws from this host's rand())
+//   emu_main recode   <ckpt_prefix> <out_prefix>                 Parse then Serialize (must reproduce the files byte for byte)
 #include "cuda_emu.h"
 
 #include <stdio.h>
+#include <string>
 #include <vector>
 
-#include "../../gmix_b200/csrc/layout.h"
+#include "../../gmix_b200/csrc/checkpoint.h"
 
 #ifndef EMU_NT
 #define EMU_NT 128
 #endif
 
-static std::vector<uint8_t> ReadAll(const char* path) {
-  FILE* f = fopen(path, "rb");
-  if (!f) { fprintf(stderr, "cannot open %s\n", path); exit(2); }
-  std::vector<uint8_t> v; int c;
-  while ((c = fgetc(f)) != EOF) v.push_back((uint8_t)c);
+static std::vector<uint8_t> ReadAll(const std::string& path) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) { fprintf(stderr, "cannot open %s\n", path.c_str()); exit(2); }
+  std::vector<uint8_t> v;
+  uint8_t buf[1 << 16];
+  size_t n;
+  while ((n = fread(buf, 1, sizeof(buf), f)) > 0) v.insert(v.end(), buf, buf + n);
   fclose(f);
   return v;
 }
+static void WriteAll(const std::string& path, const void* p, size_t n) {
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) { fprintf(stderr, "cannot write %s\n", path.c_str()); exit(2); }
+  fwrite(p, 1, n, f);
+  fclose(f);
+}
 
-int main(int argc, char** argv) {
-  if (argc < 4) { fprintf(stderr, "usage: emu_main compress|decompress <in> <out> [bit_trace] [pred_trace]\n"); return 2; }
-  const bool comp = argv[1][0] == 'c';
-  std::vector<uint8_t> in = ReadAll(argv[2]);
-  uint64_t raw_len = in.size();
-  if (!comp) { raw_len = 0; for (int i = 0; i < 5 && i < (int)in.size(); ++i) raw_len = (raw_len << 8) + in[i]; }
+struct Run {
+  gmx::ArenaLayout L;
+  std::vector<uint8_t> arena, tmpl_arena;
+  std::vector<uint32_t> tmpl_state, final_state;
+  std::vector<float> decay, adam, linit;
+  uint32_t usage[8];
+  uint32_t status;
+};
+
+// mode: gmx::MODE_*; ckpt: optional parsed checkpoint to start from; new_bytes: bytes the stream will add.
+static int Execute(Run& R, int mode, const gmx::ckpt::Image* ckpt, uint64_t new_bytes, gmx::StreamParams& P, bool want_final) {
   const bool force_roomy = getenv("EMU_ROOMY") != nullptr;
   bool roomy = force_roomy;
+  gmx::Preload pre;
+  if (ckpt) pre = gmx::ckpt::Count(*ckpt);
 retry:
-  gmx::ArenaLayout L = gmx::MakeLayout(raw_len, roomy);
-  std::vector<uint8_t> arena(L.total + 256);
-  std::vector<float> decay, adam, linit;
-  gmx::FillDecayTable(decay, raw_len * 8 + 16);
-  gmx::FillAdamTable(adam);
-  gmx::FillLstmInit(linit);
-  std::vector<uint8_t> out(comp ? raw_len + raw_len / 8 + 64 : raw_len + 8);
-  uint64_t in_off[2] = {0, in.size()}, out_off[2] = {0, out.size()}, out_len[1] = {0};
-  uint32_t status[1] = {0};
+  R.L = gmx::MakeLayout(new_bytes, roomy, ckpt ? &pre : nullptr);
+  R.arena.assign(R.L.total + 256, 0);
+  gmx::FillDecayTable(R.decay, pre.steps + new_bytes * 8 + 16);
+  gmx::FillAdamTable(R.adam);
+  gmx::FillLstmInit(R.linit);
   static uint32_t queue;
   queue = 0;
-  std::vector<uint64_t> bit_trace(argc > 4 ? raw_len * 8 : 0);
-  std::vector<float> pred_trace(argc > 5 ? raw_len * 8 * 126 : 0);
-  gmx::StreamParams P;
-  memset(&P, 0, sizeof(P));
-  P.in = in.data(); P.in_off = in_off; P.out = out.data(); P.out_off = out_off; P.out_len = out_len; P.status = status;
   P.n_streams = 1; P.queue = &queue;
-  P.arenas = (uint8_t*)(((uintptr_t)arena.data() + 255) & ~(uintptr_t)255); P.arena_stride = L.total; P.layout = &L;
-  P.lstm_init = linit.data(); P.decay = decay.data(); P.decay_len = (uint32_t)decay.size(); P.adam = adam.data();
-  uint32_t usage[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  P.usage = usage;
-  P.bit_trace = bit_trace.empty() ? nullptr : bit_trace.data();
-  P.pred_trace = pred_trace.empty() ? nullptr : pred_trace.data();
+  P.arenas = (uint8_t*)(((uintptr_t)R.arena.data() + 255) & ~(uintptr_t)255); P.arena_stride = R.L.total; P.layout = &R.L;
+  P.lstm_init = R.linit.data(); P.decay = R.decay.data(); P.decay_len = (uint32_t)R.decay.size(); P.adam = R.adam.data();
+  memset(R.usage, 0, sizeof(R.usage));
+  P.usage = R.usage;
+  R.status = 0;
+  P.status = &R.status;
+  if (ckpt) {
+    R.tmpl_arena.assign(R.L.total + 256, 0);
+    R.tmpl_state.assign(sizeof(gmx::StreamSmem) / 4 + 4, 0);
+    uint8_t* ta = (uint8_t*)(((uintptr_t)R.tmpl_arena.data() + 255) & ~(uintptr_t)255);
+    std::string err;
+    if (!gmx::ckpt::ToArena(*ckpt, R.L, ta, (gmx::StreamSmem*)R.tmpl_state.data(), &err)) {
+      if (!roomy) { fprintf(stderr, "%s: retrying with a roomy layout\n", err.c_str()); roomy = true; goto retry; }
+      fprintf(stderr, "ToArena: %s\n", err.c_str());
+      return 1;
+    }
+    P.tmpl_arena = ta; P.tmpl_state = R.tmpl_state.data();
+  }
+  if (want_final) { R.final_state.assign(sizeof(gmx::StreamSmem) / 4 + 4, 0); P.final_state = R.final_state.data(); }
   cuda_emu::RunBlock(EMU_NT, 0, 1, [&] {
-    if (comp) gmx::StreamKernel<EMU_NT, gmx::MODE_COMPRESS, 1, false>(P);
-    else gmx::StreamKernel<EMU_NT, gmx::MODE_DECOMPRESS, 1, false>(P);
+    if (mode == gmx::MODE_COMPRESS) gmx::StreamKernel<EMU_NT, gmx::MODE_COMPRESS, 1, false>(P);
+    else if (mode == gmx::MODE_DECOMPRESS) gmx::StreamKernel<EMU_NT, gmx::MODE_DECOMPRESS, 1, false>(P);
+    else gmx::StreamKernel<EMU_NT, gmx::MODE_GENERATE, 1, false>(P);
   });
-  if (!roomy && (status[0] == gmx::GMX_ERR_PPMD_ARENA || status[0] == gmx::GMX_ERR_MIXER_POOL || status[0] == gmx::GMX_ERR_SPARSE_FULL)) {
-    fprintf(stderr, "status %u: retrying in a roomy arena (as the host library does)\n", status[0]);
+  if (!roomy && (R.status == gmx::GMX_ERR_PPMD_ARENA || R.status == gmx::GMX_ERR_MIXER_POOL || R.status == gmx::GMX_ERR_SPARSE_FULL)) {
+    fprintf(stderr, "status %u: retrying in a roomy arena (as the host library does)\n", R.status);
     roomy = true;
     goto retry;
   }
-  if (status[0]) { fprintf(stderr, "stream status %u\n", status[0]); return 1; }
+  if (R.status) { fprintf(stderr, "stream status %u\n", R.status); return 1; }
   fprintf(stderr, "arena %llu KiB; sparse %u of %u (cap %u); mixer sets %u of %u; ppmd units %u of %u B; history %u\n",
-          (unsigned long long)(L.total >> 10), usage[0], L.sparse_limit, L.sparse_mask ? L.sparse_mask + 1 : 0, usage[1], L.mix_pool_sets,
-          usage[2], L.p_units_cap, usage[3]);
-  FILE* f = fopen(argv[3], "wb"); fwrite(out.data(), 1, out_len[0], f); fclose(f);
+          (unsigned long long)(R.L.total >> 10), R.usage[0], R.L.sparse_limit, R.L.sparse_mask ? R.L.sparse_mask + 1 : 0, R.usage[1], R.L.mix_pool_sets,
+          R.usage[2], R.L.p_units_cap, R.usage[3]);
+  return 0;
+}
+
+static bool LoadCkpt(const std::string& prefix, gmx::ckpt::Image* im) {
+  std::vector<uint8_t> sh = ReadAll(prefix + ".short"), lo = ReadAll(prefix + ".long");
+  std::string err;
+  if (!gmx::ckpt::Parse(sh.data(), sh.size(), lo.data(), lo.size(), im, &err)) { fprintf(stderr, "Parse: %s\n", err.c_str()); return false; }
+  return true;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 4) { fprintf(stderr, "usage: see the header of tests/emu/emu_main.cpp\n"); return 2; }
+  const std::string mode = argv[1];
+  Run R;
+  gmx::StreamParams P;
+  memset(&P, 0, sizeof(P));
+  P.analysis = -1;
+  uint64_t in_off[2], out_off[2], out_len[1] = {0};
+  P.in_off = in_off; P.out_off = out_off; P.out_len = out_len;
+
+  if (mode == "recode") {
+    gmx::ckpt::Image im;
+    if (!LoadCkpt(argv[2], &im)) return 1;
+    std::vector<uint8_t> sh, lo;
+    gmx::ckpt::Serialize(im, &sh, &lo);
+    WriteAll(std::string(argv[3]) + ".short", sh.data(), sh.size());
+    WriteAll(std::string(argv[3]) + ".long", lo.data(), lo.size());
+    return 0;
+  }
+  if (mode == "train") {
+    std::vector<uint8_t> in = ReadAll(argv[2]);
+    gmx::ckpt::Image from;
+    const bool has_from = argc > 4;
+    if (has_from && !LoadCkpt(argv[4], &from)) return 1;
+    std::vector<uint8_t> out(in.size() + in.size() / 8 + 64);
+    in_off[0] = 0; in_off[1] = in.size(); out_off[0] = 0; out_off[1] = out.size();
+    P.in = in.data(); P.out = out.data(); P.analysis = 0;
+    if (Execute(R, gmx::MODE_COMPRESS, has_from ? &from : nullptr, in.size(), P, true)) return 1;
+    gmx::ckpt::Image im;
+    std::string err;
+    if (!gmx::ckpt::FromArena(R.L, P.arenas, *(const gmx::StreamSmem*)R.final_state.data(), &im, &err)) { fprintf(stderr, "FromArena: %s\n", err.c_str()); return 1; }
+    std::vector<uint8_t> sh, lo;
+    gmx::ckpt::Serialize(im, &sh, &lo);
+    WriteAll(std::string(argv[3]) + ".short", sh.data(), sh.size());
+    WriteAll(std::string(argv[3]) + ".long", lo.data(), lo.size());
+    return 0;
+  }
+  if (mode == "generate") {
+    if (argc < 7) return 2;
+    gmx::ckpt::Image im;
+    if (!LoadCkpt(argv[2], &im)) return 1;
+    std::vector<uint8_t> prompt = ReadAll(argv[3]);
+    if (prompt.empty()) { fprintf(stderr, "empty prompt\n"); return 2; }
+    const uint32_t size = (uint32_t)atoi(argv[5]);
+    float temperature = (float)atof(argv[6]);
+    if (temperature < 0.001) temperature = 0.001;   // runner-utils.cpp:170
+    // what `gmix -g` draws: srand(0xDEADBEEF) by the Predictor constructor, 3*50*563 draws by the LSTM init, then sampling
+    std::vector<float> unused;
+    gmx::FillLstmInit(unused);
+    std::vector<float> ru((size_t)size * 8);
+    for (auto& r : ru) r = static_cast<float>(rand()) / static_cast<float>(RAND_MAX);
+    std::vector<uint8_t> out(size + 8);
+    in_off[0] = 0; in_off[1] = prompt.size(); out_off[0] = 0; out_off[1] = out.size();
+    P.in = prompt.data(); P.out = out.data(); P.gen_bytes = size; P.temperature = temperature; P.rand_u = ru.data(); P.rand_stride = 0;
+    if (Execute(R, gmx::MODE_GENERATE, &im, prompt.size() + size, P, false)) return 1;
+    WriteAll(argv[4], out.data(), size);
+    return 0;
+  }
+
+  const bool resume = mode == "resume" || mode == "expand";
+  gmx::ckpt::Image im;
+  if (resume) { if (!LoadCkpt(argv[2], &im)) return 1; argv += 1; argc -= 1; }
+  const bool comp = mode == "compress" || mode == "resume";
+  std::vector<uint8_t> in = ReadAll(argv[2]);
+  uint64_t raw_len = in.size();
+  if (!comp) { raw_len = 0; for (int i = 0; i < 5 && i < (int)in.size(); ++i) raw_len = (raw_len << 8) + in[i]; }
+  std::vector<uint8_t> out(comp ? raw_len + raw_len / 8 + 64 : raw_len + 8);
+  in_off[0] = 0; in_off[1] = in.size(); out_off[0] = 0; out_off[1] = out.size();
+  std::vector<uint64_t> bit_trace(argc > 4 ? raw_len * 8 : 0);
+  std::vector<float> pred_trace(argc > 5 ? raw_len * 8 * 126 : 0);
+  P.in = in.data(); P.out = out.data();
+  P.bit_trace = bit_trace.empty() ? nullptr : bit_trace.data();
+  P.pred_trace = pred_trace.empty() ? nullptr : pred_trace.data();
+  if (Execute(R, comp ? gmx::MODE_COMPRESS : gmx::MODE_DECOMPRESS, resume ? &im : nullptr, raw_len, P, false)) return 1;
+  WriteAll(argv[3], out.data(), out_len[0]);
   if (argc > 4) {  // same record format as ref_driver trace level 1/2
     FILE* t = fopen(argv[4], "wb");
     for (size_t i = 0; i < bit_trace.size(); ++i) {
