@@ -4,4 +4,4 @@ The package is a thin host-side mirror of the reference's runner interface over 
 include/gmix_b200.h (libgmix_b200.so). There is no CPU fallback: importing works anywhere, but every
 compute entry point needs the CUDA library and a B200.
 """
-from .api import Context, GmixError, Predictor, compress_bound, library_path, load_library  # noqa: F401
+from .api import Context, GmixError, Model, Predictor, compress_bound, library_path, load_library, reference_rand_u  # noqa: F401

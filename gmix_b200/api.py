@@ -65,6 +65,24 @@ def load_library():
     lib.gmx_pred_perceive.argtypes = [C.c_void_p, C.c_int]
     lib.gmx_pred_learn.argtypes = [C.c_void_p]
     lib.gmx_get_usage.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.gmx_model_load.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]
+    lib.gmx_model_free.argtypes = [C.c_void_p]
+    lib.gmx_model_arena_bytes.argtypes = [C.c_void_p]
+    lib.gmx_model_arena_bytes.restype = C.c_uint64
+    lib.gmx_model_trained_bytes.argtypes = [C.c_void_p]
+    lib.gmx_model_trained_bytes.restype = C.c_uint64
+    lib.gmx_compress_batch_from.argtypes = [C.c_void_p, C.c_void_p] + batch[1:]
+    lib.gmx_decompress_batch_from.argtypes = [C.c_void_p, C.c_void_p] + batch[1:]
+    lib.gmx_generate_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p,
+                                       C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.gmx_generate_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p,
+                                              C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.gmx_reference_rand_u.argtypes = [C.c_void_p, C.c_uint64]
+    lib.gmx_reference_rand_u.restype = None
+    blobs = [C.POINTER(C.c_void_p), u64p, C.POINTER(C.c_void_p), u64p]
+    lib.gmx_train_checkpoint.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64] + blobs
+    lib.gmx_pred_write_checkpoint.argtypes = [C.c_void_p] + blobs
+    lib.gmx_pred_read_checkpoint.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
     lib.gmx_selftest_math.argtypes = [C.c_void_p, C.c_uint32, u64p, u32p]
     _LIB = lib
     return lib
@@ -81,6 +99,51 @@ def _pack(streams):
     np.cumsum(lens, out=off[1:])
     buf = np.frombuffer(b"".join(bytes(s) for s in streams), dtype=np.uint8).copy() if sum(lens) else np.zeros(1, np.uint8)
     return buf, off
+
+
+def reference_rand_u(n):
+    """The n draws rand()/RAND_MAX one `gmix -g` process uses for sampling (after the Predictor constructor)."""
+    out = np.zeros(max(n, 1), dtype=np.float32)
+    load_library().gmx_reference_rand_u(out.ctypes.data, n)
+    return out[:n]
+
+
+def _blobs(fn, *args):
+    sp, lp = C.c_void_p(), C.c_void_p()
+    sl, ll = C.c_uint64(0), C.c_uint64(0)
+    rc = fn(*args, C.byref(sp), C.byref(sl), C.byref(lp), C.byref(ll))
+    if rc != 0:
+        return rc, None, None
+    return 0, C.string_at(sp.value, sl.value), C.string_at(lp.value, ll.value)
+
+
+class Model:
+    """A loaded checkpoint (reference Predictor::ReadCheckpoint, predictor.cpp:406-420): `.short` + `.long` bytes as the
+    reference writes them, parked on the GPU; batch calls start every stream as a clone of it."""
+
+    def __init__(self, ctx, short_blob, long_blob, max_new_bytes, roomy=False):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx._check(ctx.lib.gmx_model_load(ctx.h, short_blob, len(short_blob), long_blob, len(long_blob), max_new_bytes, int(roomy), C.byref(h)),
+                   "gmx_model_load")
+        self.h = h
+
+    @classmethod
+    def from_files(cls, ctx, prefix, max_new_bytes, roomy=False):
+        return cls(ctx, open(prefix + ".short", "rb").read(), open(prefix + ".long", "rb").read(), max_new_bytes, roomy)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.gmx_model_free(self.h)
+            self.h = None
+
+    @property
+    def arena_bytes(self):
+        return int(self.ctx.lib.gmx_model_arena_bytes(self.h))
+
+    @property
+    def trained_bytes(self):
+        return int(self.ctx.lib.gmx_model_trained_bytes(self.h))
 
 
 class Predictor:
@@ -110,6 +173,16 @@ class Predictor:
 
     def learn(self):
         self.ctx._check(self.ctx.lib.gmx_pred_learn(self.h), "gmx_pred_learn")
+
+    def write_checkpoint(self):
+        """Predictor::WriteCheckpoint: returns (.short bytes, .long bytes)."""
+        rc, sh, lo = _blobs(self.ctx.lib.gmx_pred_write_checkpoint, self.h)
+        self.ctx._check(rc, "gmx_pred_write_checkpoint")
+        return sh, lo
+
+    def read_checkpoint(self, short_blob, long_blob):
+        self.ctx._check(self.ctx.lib.gmx_pred_read_checkpoint(self.h, short_blob, len(short_blob), long_blob, len(long_blob)),
+                        "gmx_pred_read_checkpoint")
 
 
 class Context:
@@ -147,10 +220,13 @@ class Context:
         self._check(self.lib.gmx_configure(self.h, max_stream_len, max_resident), "gmx_configure")
 
     # ---- host-buffer API (the call a user makes) ----
-    def _run_host(self, fn, what, streams, caps):
+    def _run_host(self, fn, what, streams, caps, model=None):
         n = len(streams)
         if n == 0:
             return []
+        if model is not None:
+            plain = fn
+            fn = lambda h, *a: plain(h, model.h, *a)
         buf, off = _pack(streams)
         ooff = np.zeros(n + 1, dtype=np.uint64)
         np.cumsum(np.asarray(caps, dtype=np.uint64), out=ooff[1:])
@@ -168,6 +244,39 @@ class Context:
     def decompress_batch(self, streams):
         caps = [int.from_bytes(bytes(s[:5]), "big") + 8 if len(s) >= 5 else 8 for s in streams]
         return self._run_host(self.lib.gmx_decompress_batch, "gmx_decompress_batch", streams, caps)
+
+    def compress_batch_from(self, model, streams):
+        """`gmix -c <ckpt> in out` for every stream."""
+        return self._run_host(self.lib.gmx_compress_batch_from, "gmx_compress_batch_from", streams, [compress_bound(len(s)) for s in streams], model)
+
+    def decompress_batch_from(self, model, streams):
+        caps = [int.from_bytes(bytes(s[:5]), "big") + 8 if len(s) >= 5 else 8 for s in streams]
+        return self._run_host(self.lib.gmx_decompress_batch_from, "gmx_decompress_batch_from", streams, caps, model)
+
+    def generate_batch(self, model, prompts, out_bytes, temperature=1.0, rand_u=None, rand_stride=0):
+        """`gmix -g <ckpt> prompt out out_bytes temperature` for every prompt; rand_u defaults to the reference's draws,
+        shared by all prompts (what separate gmix processes do)."""
+        n = len(prompts)
+        if n == 0:
+            return []
+        if rand_u is None:
+            rand_u = reference_rand_u(out_bytes * 8)
+        rand_u = np.ascontiguousarray(rand_u, dtype=np.float32)
+        buf, off = _pack(prompts)
+        out = np.zeros(n * out_bytes + 1, dtype=np.uint8)
+        status = np.zeros(n, dtype=np.uint32)
+        rc = self.lib.gmx_generate_batch(self.h, model.h, buf.ctypes.data, off.ctypes.data, n, out_bytes, temperature, rand_u.ctypes.data,
+                                         rand_stride, out.ctypes.data, status.ctypes.data)
+        self.last_status = status
+        self._check(rc, "gmx_generate_batch")
+        return [out[i * out_bytes:(i + 1) * out_bytes].tobytes() for i in range(n)]
+
+    def train_checkpoint(self, data, model=None):
+        """Predict/Perceive/Learn over data, then Predictor::WriteCheckpoint: returns (.short bytes, .long bytes)."""
+        src = np.frombuffer(bytes(data), dtype=np.uint8).copy() if len(data) else np.zeros(1, np.uint8)
+        rc, sh, lo = _blobs(self.lib.gmx_train_checkpoint, self.h, model.h if model is not None else None, src.ctypes.data, len(data))
+        self._check(rc, "gmx_train_checkpoint")
+        return sh, lo
 
     def compress(self, data):
         return self.compress_batch([data])[0]

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/gmix_b200.h"
+#include "checkpoint.h"
 #include "kernels.h"
 #include "layout.h"
 
@@ -38,6 +39,8 @@ struct gmx_ctx {
   // worst-case-sized class, allocated on demand for the streams that overflowed a normal arena
   uint64_t cfg_max_len = 0;
   uint32_t cfg_max_resident = 0;
+  const gmx_model* cfg_model = nullptr;   // arenas currently use this model's layout (streams start from its checkpoint)
+  std::vector<uint8_t> ck_short, ck_long; // last checkpoint written through this ctx (gmx_train_checkpoint, gmx_pred_write_checkpoint)
   uint32_t n_arenas = 0;
   gmx::ArenaLayout layout;
   uint8_t* d_arenas = nullptr;
@@ -54,13 +57,33 @@ struct gmx_ctx {
   uint32_t* d_queue = nullptr;
   std::vector<float> h_decay;
   // staging buffers of the host-pointer entry points
-  DevBuf b_in, b_out, b_in_off, b_out_off, b_out_len, b_status, b_trace, b_ptrace, b_prof, b_ids, b_usage;
+  DevBuf b_in, b_out, b_in_off, b_out_off, b_out_len, b_status, b_trace, b_ptrace, b_prof, b_ids, b_usage, b_rand, b_final;
   bool profile = false;
   uint32_t prof_streams = 0;
   uint32_t usage_streams = 0;
   uint32_t last_grid = 0;
   uint64_t launches = 0;
   double last_ms = 0;
+};
+
+// A loaded checkpoint (Predictor::ReadCheckpoint predictor.cpp:406-420): one parked stream on the device
+// (arena image + StreamSmem image) that batch calls clone into every stream arena. Read-only after load.
+struct gmx_model {
+  gmx_ctx* ctx = nullptr;
+  gmx::ArenaLayout layout;
+  gmx::Preload pre;
+  uint64_t max_new_bytes = 0;
+  uint8_t* d_arena = nullptr;
+  uint32_t* d_state = nullptr;
+};
+
+// Per-call options of RunDevice beyond the stream slices.
+struct RunOpts {
+  const gmx_model* model = nullptr;
+  int analysis = -1;
+  uint32_t* d_final_state = nullptr;
+  uint32_t gen_bytes = 0; float temperature = 1.0f; const float* d_rand_u = nullptr; uint64_t rand_stride = 0;
+  uint64_t* d_bit_trace = nullptr; float* d_pred_trace = nullptr;
 };
 
 // One stream stepped bit by bit (the Predictor facade). Owns a worst-case-sized arena.
@@ -124,6 +147,7 @@ void FreeArenas(gmx_ctx* c) {
   c->n_arenas = 0;
   c->n_roomy = 0;
   c->cfg_max_len = 0;
+  c->cfg_model = nullptr;
 }
 
 bool Retryable(uint32_t st) {
@@ -134,7 +158,7 @@ int Launch(gmx_ctx* c, int mode, const gmx::StreamParams& P, uint32_t grid) {
   GMX_CUDA(c, cudaMemsetAsync(c->d_queue, 0, sizeof(uint32_t), c->stream));
   GMX_CUDA(c, cudaEventRecord(c->ev0, c->stream));
   GMX_CUDA(c, mode == gmx::MODE_COMPRESS ? (P.prof ? gmx::LaunchCompressProf(P, grid, c->stream) : gmx::LaunchCompress(P, grid, c->stream))
-                                         : gmx::LaunchDecompress(P, grid, c->stream));
+              : mode == gmx::MODE_DECOMPRESS ? gmx::LaunchDecompress(P, grid, c->stream) : gmx::LaunchGenerate(P, grid, c->stream));
   GMX_CUDA(c, cudaEventRecord(c->ev1, c->stream));
   GMX_CUDA(c, cudaStreamSynchronize(c->stream));
   float ms = 0;
@@ -153,6 +177,7 @@ int RetryInRoomyArenas(gmx_ctx* c, int mode, gmx::StreamParams P, uint32_t n, ui
   for (uint32_t i = 0; i < n; ++i) if (Retryable(st[i])) ids.push_back(i);
   if (ids.empty()) return 0;
   if (!c->d_roomy) {
+    if (c->cfg_model) return Fail(c, GMX_E_STREAM, "%zu streams overflowed the arena sized by gmx_model_load (reload the model with a larger max_new_bytes)", ids.size());
     c->roomy_layout = gmx::MakeLayout(c->cfg_max_len, true);
     size_t free_b = 0, total_b = 0;
     GMX_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
@@ -177,15 +202,47 @@ int RetryInRoomyArenas(gmx_ctx* c, int mode, gmx::StreamParams P, uint32_t n, ui
   return Launch(c, mode, P, P.n_streams < c->n_roomy ? P.n_streams : c->n_roomy);
 }
 
+// Arenas sized by a loaded model's layout (every stream is a clone of the model's parked stream).
+int ConfigureForModel(gmx_ctx* c, const gmx_model* m) {
+  if (c->cfg_model == m && c->n_arenas) return 0;
+  const uint32_t max_resident = c->cfg_max_resident;
+  FreeArenas(c);
+  c->layout = m->layout;
+  int rc = EnsureDecay(c, m->pre.steps / 8 + m->max_new_bytes + 2);
+  if (rc) return rc;
+  int per_sm = 0;
+  GMX_CUDA(c, gmx::OccupancyCompress(&per_sm));
+  if (per_sm < 1) per_sm = 1;
+  uint64_t want = (uint64_t)per_sm * c->sm_count;
+  if (max_resident && max_resident < want) want = max_resident;
+  size_t free_b = 0, total_b = 0;
+  GMX_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+  const uint64_t usable = free_b > (2ull << 30) ? free_b - (2ull << 30) : 0;
+  const uint64_t fit = usable / c->layout.total;
+  if (fit == 0) return Fail(c, GMX_E_NOMEM, "one stream arena of this model needs %llu MiB but only %llu MiB are free",
+                            (unsigned long long)(c->layout.total >> 20), (unsigned long long)(free_b >> 20));
+  if (fit < want) want = fit;
+  GMX_CUDA(c, cudaMalloc(&c->d_arenas, want * c->layout.total));
+  GMX_CUDA(c, cudaMemcpy(c->d_layout, &c->layout, sizeof(c->layout), cudaMemcpyHostToDevice));
+  c->n_arenas = (uint32_t)want;
+  c->cfg_model = m;
+  return 0;
+}
+
 int RunDevice(gmx_ctx* c, int mode, const uint8_t* d_in, const uint64_t* d_in_off, uint32_t n, uint8_t* d_out,
-              const uint64_t* d_out_off, uint64_t* d_out_len, uint32_t* d_status, uint64_t max_len,
-              uint64_t* d_bit_trace, float* d_pred_trace) {
+              const uint64_t* d_out_off, uint64_t* d_out_len, uint32_t* d_status, uint64_t max_len, const RunOpts& o) {
   if (!c) return GMX_E_ARG;
   if (n == 0) return 0;
-  if (!d_in || !d_in_off || !d_out || !d_out_off || !d_out_len || !d_status) return Fail(c, GMX_E_ARG, "null pointer argument");
+  if (!d_in || !d_in_off || !d_out || !d_out_len || !d_status || (mode != gmx::MODE_GENERATE && !d_out_off)) return Fail(c, GMX_E_ARG, "null pointer argument");
   GMX_CUDA(c, cudaSetDevice(c->device));
-  if (max_len > c->cfg_max_len || c->n_arenas == 0) {
-    int rc = gmx_configure(c, max_len, c->cfg_max_resident);
+  if (o.model) {
+    if (o.model->ctx != c) return Fail(c, GMX_E_ARG, "model belongs to another context");
+    if (max_len > o.model->max_new_bytes) return Fail(c, GMX_E_ARG, "stream of %llu bytes exceeds the max_new_bytes (%llu) the model was loaded with",
+                                                       (unsigned long long)max_len, (unsigned long long)o.model->max_new_bytes);
+    int rc = ConfigureForModel(c, o.model);
+    if (rc) return rc;
+  } else if (max_len > c->cfg_max_len || c->n_arenas == 0 || c->cfg_model) {
+    int rc = gmx_configure(c, max_len > c->cfg_max_len || c->cfg_model ? max_len : c->cfg_max_len, c->cfg_max_resident);
     if (rc) return rc;
   }
   gmx::StreamParams P;
@@ -194,7 +251,10 @@ int RunDevice(gmx_ctx* c, int mode, const uint8_t* d_in, const uint64_t* d_in_of
   P.n_streams = n; P.queue = c->d_queue;
   P.arenas = c->d_arenas; P.arena_stride = c->layout.total; P.layout = c->d_layout;
   P.lstm_init = c->d_lstm_init; P.decay = c->d_decay; P.decay_len = c->decay_len; P.adam = c->d_adam;
-  P.bit_trace = d_bit_trace; P.pred_trace = d_pred_trace;
+  P.bit_trace = o.d_bit_trace; P.pred_trace = o.d_pred_trace;
+  P.analysis = o.analysis; P.final_state = o.d_final_state;
+  P.gen_bytes = o.gen_bytes; P.temperature = o.temperature; P.rand_u = o.d_rand_u; P.rand_stride = o.rand_stride;
+  if (o.model) { P.tmpl_arena = o.model->d_arena; P.tmpl_state = o.model->d_state; }
   const uint32_t grid = n < c->n_arenas ? n : c->n_arenas;
   {
     int rc = Reserve(c, c->b_usage, (size_t)n * 32);
@@ -202,7 +262,7 @@ int RunDevice(gmx_ctx* c, int mode, const uint8_t* d_in, const uint64_t* d_in_of
     P.usage = (uint32_t*)c->b_usage.p;
     c->usage_streams = n;
   }
-  if (c->profile) {
+  if (c->profile && mode == gmx::MODE_COMPRESS) {
     int rc = Reserve(c, c->b_prof, (size_t)n * gmx::GMX_PROF_SLOTS * 8);
     if (rc) return rc;
     GMX_CUDA(c, cudaMemsetAsync(c->b_prof.p, 0, (size_t)n * gmx::GMX_PROF_SLOTS * 8, c->stream));
@@ -213,11 +273,13 @@ int RunDevice(gmx_ctx* c, int mode, const uint8_t* d_in, const uint64_t* d_in_of
   c->last_grid = grid;
   int rc = Launch(c, mode, P, grid);
   if (rc) return rc;
+  if (o.d_final_state) return 0;   // the parked state belongs to the arena the stream ran in: no re-run elsewhere
   return RetryInRoomyArenas(c, mode, P, n, d_status);
 }
 
 int RunHost(gmx_ctx* c, int mode, const uint8_t* in, const uint64_t* in_off, uint32_t n, uint8_t* out,
-            const uint64_t* out_off, uint64_t* out_len, uint32_t* status, uint64_t* h_bit_trace, float* h_pred_trace) {
+            const uint64_t* out_off, uint64_t* out_len, uint32_t* status, uint64_t* h_bit_trace, float* h_pred_trace,
+            RunOpts o = RunOpts()) {
   if (!c) return GMX_E_ARG;
   if (n == 0) return 0;
   if (!in || !in_off || !out || !out_off || !out_len || !status) return Fail(c, GMX_E_ARG, "null pointer argument");
@@ -257,8 +319,9 @@ int RunHost(gmx_ctx* c, int mode, const uint8_t* in, const uint64_t* in_off, uin
   GMX_CUDA(c, cudaMemcpyAsync(c->b_out_off.p, oo.data(), (n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
   GMX_CUDA(c, cudaMemsetAsync(c->b_out_len.p, 0, (size_t)n * 8, c->stream));
   GMX_CUDA(c, cudaMemsetAsync(c->b_status.p, 0xff, (size_t)n * 4, c->stream));
+  o.d_bit_trace = d_bt; o.d_pred_trace = d_pt;
   rc = RunDevice(c, mode, (const uint8_t*)c->b_in.p, (const uint64_t*)c->b_in_off.p, n, (uint8_t*)c->b_out.p,
-                 (const uint64_t*)c->b_out_off.p, (uint64_t*)c->b_out_len.p, (uint32_t*)c->b_status.p, max_len, d_bt, d_pt);
+                 (const uint64_t*)c->b_out_off.p, (uint64_t*)c->b_out_len.p, (uint32_t*)c->b_status.p, max_len, o);
   if (rc) return rc;
   GMX_CUDA(c, cudaMemcpyAsync(out + out_off[0], c->b_out.p, out_total, cudaMemcpyDeviceToHost, c->stream));
   GMX_CUDA(c, cudaMemcpyAsync(out_len, c->b_out_len.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -347,7 +410,7 @@ void gmx_destroy(gmx_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   FreeArenas(c);
-  for (DevBuf* b : {&c->b_in, &c->b_out, &c->b_in_off, &c->b_out_off, &c->b_out_len, &c->b_status, &c->b_trace, &c->b_ptrace, &c->b_prof, &c->b_ids, &c->b_usage})
+  for (DevBuf* b : {&c->b_in, &c->b_out, &c->b_in_off, &c->b_out_off, &c->b_out_len, &c->b_status, &c->b_trace, &c->b_ptrace, &c->b_prof, &c->b_ids, &c->b_usage, &c->b_rand, &c->b_final})
     if (b->p) cudaFree(b->p);
   if (c->d_layout) cudaFree(c->d_layout);
   if (c->d_roomy_layout) cudaFree(c->d_roomy_layout);
@@ -411,11 +474,162 @@ int gmx_decompress_batch(gmx_ctx* c, const uint8_t* in, const uint64_t* in_off, 
 }
 int gmx_compress_batch_device(gmx_ctx* c, const uint8_t* d_in, const uint64_t* d_in_off, uint32_t n, uint8_t* d_out,
                               const uint64_t* d_out_off, uint64_t* d_out_len, uint32_t* d_status, uint64_t max_len) {
-  return RunDevice(c, gmx::MODE_COMPRESS, d_in, d_in_off, n, d_out, d_out_off, d_out_len, d_status, max_len, nullptr, nullptr);
+  return RunDevice(c, gmx::MODE_COMPRESS, d_in, d_in_off, n, d_out, d_out_off, d_out_len, d_status, max_len, RunOpts());
 }
 int gmx_decompress_batch_device(gmx_ctx* c, const uint8_t* d_in, const uint64_t* d_in_off, uint32_t n, uint8_t* d_out,
                                 const uint64_t* d_out_off, uint64_t* d_out_len, uint32_t* d_status, uint64_t max_len) {
-  return RunDevice(c, gmx::MODE_DECOMPRESS, d_in, d_in_off, n, d_out, d_out_off, d_out_len, d_status, max_len, nullptr, nullptr);
+  return RunDevice(c, gmx::MODE_DECOMPRESS, d_in, d_in_off, n, d_out, d_out_off, d_out_len, d_status, max_len, RunOpts());
+}
+
+// ---- checkpoints and generation ---------------------------------------------------------------------
+int gmx_model_load(gmx_ctx* c, const void* short_blob, uint64_t short_len, const void* long_blob, uint64_t long_len,
+                   uint64_t max_new_bytes, int roomy, gmx_model** out) {
+  if (!c || !out || !short_blob || !long_blob) return GMX_E_ARG;
+  *out = nullptr;
+  GMX_CUDA(c, cudaSetDevice(c->device));
+  if (max_new_bytes >= (1ull << 31)) return Fail(c, GMX_E_ARG, "max_new_bytes out of range");
+  gmx::ckpt::Image im;
+  std::string err;
+  if (!gmx::ckpt::Parse(short_blob, short_len, long_blob, long_len, &im, &err)) return Fail(c, GMX_E_ARG, "checkpoint: %s", err.c_str());
+  gmx_model* m = new gmx_model();
+  m->ctx = c;
+  m->pre = gmx::ckpt::Count(im);
+  m->max_new_bytes = max_new_bytes;
+  std::vector<uint8_t> arena;
+  std::vector<uint32_t> state(sizeof(gmx::StreamSmem) / 4 + 4);
+  bool ok = false;
+  for (int attempt = roomy ? 1 : 0; attempt < 2 && !ok; ++attempt) {   // typical sizing first, worst case if the checkpoint does not fit it
+    m->layout = gmx::MakeLayout(max_new_bytes, attempt == 1, &m->pre);
+    arena.assign(m->layout.total, 0);
+    ok = gmx::ckpt::ToArena(im, m->layout, arena.data(), (gmx::StreamSmem*)state.data(), &err);
+  }
+  if (!ok) { delete m; return Fail(c, GMX_E_ARG, "checkpoint: %s", err.c_str()); }
+  if (cudaMalloc(&m->d_arena, m->layout.total) != cudaSuccess || cudaMalloc(&m->d_state, sizeof(gmx::StreamSmem)) != cudaSuccess ||
+      cudaMemcpy(m->d_arena, arena.data(), m->layout.total, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(m->d_state, state.data(), sizeof(gmx::StreamSmem), cudaMemcpyHostToDevice) != cudaSuccess) {
+    const char* what = cudaGetErrorString(cudaGetLastError());
+    gmx_model_free(m);
+    return Fail(c, GMX_E_NOMEM, "cannot place a %llu MiB model on the device: %s", (unsigned long long)(m->layout.total >> 20), what);
+  }
+  *out = m;
+  return 0;
+}
+
+void gmx_model_free(gmx_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->ctx->device);
+  if (m->ctx->cfg_model == m) FreeArenas(m->ctx);
+  if (m->d_arena) cudaFree(m->d_arena);
+  if (m->d_state) cudaFree(m->d_state);
+  delete m;
+}
+
+uint64_t gmx_model_arena_bytes(const gmx_model* m) { return m ? m->layout.total : 0; }
+uint64_t gmx_model_trained_bytes(const gmx_model* m) { return m ? m->pre.steps / 8 : 0; }
+
+int gmx_compress_batch_from(gmx_ctx* c, const gmx_model* model, const uint8_t* in, const uint64_t* in_off, uint32_t n, uint8_t* out,
+                            const uint64_t* out_off, uint64_t* out_len, uint32_t* status) {
+  RunOpts o; o.model = model;
+  return RunHost(c, gmx::MODE_COMPRESS, in, in_off, n, out, out_off, out_len, status, nullptr, nullptr, o);
+}
+int gmx_decompress_batch_from(gmx_ctx* c, const gmx_model* model, const uint8_t* in, const uint64_t* in_off, uint32_t n, uint8_t* out,
+                              const uint64_t* out_off, uint64_t* out_len, uint32_t* status) {
+  RunOpts o; o.model = model;
+  return RunHost(c, gmx::MODE_DECOMPRESS, in, in_off, n, out, out_off, out_len, status, nullptr, nullptr, o);
+}
+
+int gmx_generate_batch_device(gmx_ctx* c, const gmx_model* model, const uint8_t* d_prompts, const uint64_t* d_prompt_off, uint32_t n,
+                              uint32_t out_bytes, float temperature, const float* d_rand_u, uint64_t rand_stride, uint8_t* d_out,
+                              uint64_t* d_out_len, uint32_t* d_status, uint64_t max_prompt_len) {
+  if (!c || !model) return GMX_E_ARG;
+  if (!d_rand_u) return Fail(c, GMX_E_ARG, "null pointer argument");
+  RunOpts o; o.model = model; o.gen_bytes = out_bytes; o.d_rand_u = d_rand_u; o.rand_stride = rand_stride;
+  o.temperature = temperature < (float)0.001 ? (float)0.001 : temperature;   // runner-utils.cpp:170
+  return RunDevice(c, gmx::MODE_GENERATE, d_prompts, d_prompt_off, n, d_out, nullptr, d_out_len, d_status, max_prompt_len + out_bytes, o);
+}
+
+int gmx_generate_batch(gmx_ctx* c, const gmx_model* model, const uint8_t* prompts, const uint64_t* prompt_off, uint32_t n,
+                       uint32_t out_bytes, float temperature, const float* rand_u, uint64_t rand_stride, uint8_t* out, uint32_t* status) {
+  if (!c || !model) return GMX_E_ARG;
+  if (n == 0) return 0;
+  if (!prompts || !prompt_off || !rand_u || !out || !status) return Fail(c, GMX_E_ARG, "null pointer argument");
+  GMX_CUDA(c, cudaSetDevice(c->device));
+  uint64_t max_len = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (prompt_off[i + 1] <= prompt_off[i]) return Fail(c, GMX_E_ARG, "prompt %u is empty (the reference needs at least one byte)", i);
+    max_len = std::max(max_len, prompt_off[i + 1] - prompt_off[i]);
+  }
+  std::vector<uint64_t> po(n + 1);
+  for (uint32_t i = 0; i <= n; ++i) po[i] = prompt_off[i] - prompt_off[0];
+  const uint64_t in_total = po[n], out_total = (uint64_t)n * out_bytes;
+  const uint64_t n_rand = (rand_stride ? (uint64_t)(n - 1) * rand_stride : 0) + (uint64_t)out_bytes * 8;
+  int rc;
+  if ((rc = Reserve(c, c->b_in, in_total + 16))) return rc;
+  if ((rc = Reserve(c, c->b_out, out_total + 16))) return rc;
+  if ((rc = Reserve(c, c->b_in_off, (n + 1) * 8))) return rc;
+  if ((rc = Reserve(c, c->b_out_len, (size_t)n * 8))) return rc;
+  if ((rc = Reserve(c, c->b_status, (size_t)n * 4))) return rc;
+  if ((rc = Reserve(c, c->b_rand, n_rand * 4 + 16))) return rc;
+  GMX_CUDA(c, cudaMemcpyAsync(c->b_in.p, prompts + prompt_off[0], in_total, cudaMemcpyHostToDevice, c->stream));
+  GMX_CUDA(c, cudaMemcpyAsync(c->b_in_off.p, po.data(), (n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  GMX_CUDA(c, cudaMemcpyAsync(c->b_rand.p, rand_u, n_rand * 4, cudaMemcpyHostToDevice, c->stream));
+  GMX_CUDA(c, cudaMemsetAsync(c->b_status.p, 0xff, (size_t)n * 4, c->stream));
+  rc = gmx_generate_batch_device(c, model, (const uint8_t*)c->b_in.p, (const uint64_t*)c->b_in_off.p, n, out_bytes, temperature,
+                                 (const float*)c->b_rand.p, rand_stride, (uint8_t*)c->b_out.p, (uint64_t*)c->b_out_len.p,
+                                 (uint32_t*)c->b_status.p, max_len);
+  if (rc) return rc;
+  GMX_CUDA(c, cudaMemcpyAsync(out, c->b_out.p, out_total, cudaMemcpyDeviceToHost, c->stream));
+  GMX_CUDA(c, cudaMemcpyAsync(status, c->b_status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  GMX_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (uint32_t i = 0; i < n; ++i)
+    if (status[i] != 0) return Fail(c, GMX_E_STREAM, "stream %u failed with status %u", i, status[i]);
+  return 0;
+}
+
+void gmx_reference_rand_u(float* out, uint64_t n) {
+  // what `gmix -g` draws: Predictor() seeds srand(0xDEADBEEF) (predictor.cpp:18), the LSTM initialisation takes
+  // 3*50*563 draws (lstm-layer.cpp:176-195), sampling continues that sequence (runner-utils.cpp:18-20,203)
+  std::vector<float> skip;
+  gmx::FillLstmInit(skip);
+  for (uint64_t i = 0; i < n; ++i) out[i] = static_cast<float>(rand()) / static_cast<float>(RAND_MAX);
+}
+
+namespace {
+// arena + parked state of stream `slot` of the ctx arenas -> reference checkpoint bytes in c->ck_short / c->ck_long
+int SerializeParked(gmx_ctx* c, const gmx::ArenaLayout& L, const uint8_t* d_arena, const uint32_t* d_state) {
+  std::vector<uint8_t> arena(L.total);
+  std::vector<uint32_t> state(sizeof(gmx::StreamSmem) / 4 + 4);
+  GMX_CUDA(c, cudaMemcpy(arena.data(), d_arena, L.total, cudaMemcpyDeviceToHost));
+  GMX_CUDA(c, cudaMemcpy(state.data(), d_state, sizeof(gmx::StreamSmem), cudaMemcpyDeviceToHost));
+  gmx::ckpt::Image im;
+  std::string err;
+  if (!gmx::ckpt::FromArena(L, arena.data(), *(const gmx::StreamSmem*)state.data(), &im, &err)) return Fail(c, GMX_E_ARG, "checkpoint: %s", err.c_str());
+  gmx::ckpt::Serialize(im, &c->ck_short, &c->ck_long);
+  return 0;
+}
+}  // namespace
+
+int gmx_train_checkpoint(gmx_ctx* c, const gmx_model* from, const uint8_t* data, uint64_t n, const void** short_blob,
+                         uint64_t* short_len, const void** long_blob, uint64_t* long_len) {
+  if (!c || !short_blob || !short_len || !long_blob || !long_len || (!data && n)) return GMX_E_ARG;
+  GMX_CUDA(c, cudaSetDevice(c->device));
+  int rc;
+  if ((rc = Reserve(c, c->b_final, sizeof(gmx::StreamSmem)))) return rc;
+  std::vector<uint8_t> out(gmx_compress_bound(n));
+  const uint64_t io[2] = {0, n}, oo[2] = {0, out.size()};
+  uint64_t out_len = 0;
+  uint32_t status = 0;
+  const uint8_t dummy = 0;
+  RunOpts o; o.model = from; o.analysis = 0; o.d_final_state = (uint32_t*)c->b_final.p;
+  const uint32_t keep_resident = c->cfg_max_resident;
+  rc = RunHost(c, gmx::MODE_COMPRESS, n ? data : &dummy, io, 1, out.data(), oo, &out_len, &status, nullptr, nullptr, o);
+  (void)keep_resident;
+  if (rc) return rc;
+  rc = SerializeParked(c, c->layout, c->d_arenas, (const uint32_t*)c->b_final.p);   // one stream: it ran in arena 0
+  if (rc) return rc;
+  *short_blob = c->ck_short.data(); *short_len = c->ck_short.size();
+  *long_blob = c->ck_long.data(); *long_len = c->ck_long.size();
+  return 0;
 }
 
 int gmx_checksum_device(gmx_ctx* c, const uint8_t* d_data, const uint64_t* d_off, const uint64_t* d_len, uint32_t n, uint64_t* d_sum) {
@@ -540,6 +754,43 @@ int gmx_pred_perceive(gmx_pred* p, int bit) {
 int gmx_pred_learn(gmx_pred* p) {
   if (!p) return GMX_E_ARG;
   return PredStep(p, gmx::STEP_LEARN, nullptr);
+}
+
+int gmx_pred_write_checkpoint(gmx_pred* p, const void** short_blob, uint64_t* short_len, const void** long_blob, uint64_t* long_len) {
+  if (!p || !short_blob || !short_len || !long_blob || !long_len) return GMX_E_ARG;
+  gmx_ctx* c = p->ctx;
+  GMX_CUDA(c, cudaSetDevice(c->device));
+  if (p->pending_bit >= 0) {   // Perceive travels with the next launch: apply it to the parked state first
+    GMX_CUDA(c, cudaMemcpy((uint8_t*)p->d_state + offsetof(gmx::StreamSmem, new_bit), &p->pending_bit, 4, cudaMemcpyHostToDevice));
+  }
+  int rc = SerializeParked(c, p->layout, p->d_arena, p->d_state);
+  if (rc) return rc;
+  *short_blob = c->ck_short.data(); *short_len = c->ck_short.size();
+  *long_blob = c->ck_long.data(); *long_len = c->ck_long.size();
+  return 0;
+}
+
+int gmx_pred_read_checkpoint(gmx_pred* p, const void* short_blob, uint64_t short_len, const void* long_blob, uint64_t long_len) {
+  if (!p || !short_blob || !long_blob) return GMX_E_ARG;
+  gmx_ctx* c = p->ctx;
+  GMX_CUDA(c, cudaSetDevice(c->device));
+  gmx::ckpt::Image im;
+  std::string err;
+  if (!gmx::ckpt::Parse(short_blob, short_len, long_blob, long_len, &im, &err)) return Fail(c, GMX_E_ARG, "checkpoint: %s", err.c_str());
+  // the predictor's arena was sized (worst case) for max_stream_len bytes from scratch; the checkpoint must fit it
+  std::vector<uint8_t> arena(p->layout.total);
+  std::vector<uint32_t> state(sizeof(gmx::StreamSmem) / 4 + 4);
+  if (!gmx::ckpt::ToArena(im, p->layout, arena.data(), (gmx::StreamSmem*)state.data(), &err))
+    return Fail(c, GMX_E_ARG, "checkpoint does not fit this predictor (create it with a larger max_stream_len): %s", err.c_str());
+  const uint64_t trained_bits = im.mixer[0].steps;
+  int rc = EnsureDecay(c, trained_bits / 8 + p->max_bits / 8 + 2);
+  if (rc) return rc;
+  ((gmx::StreamSmem*)state.data())->analysis = p->analysis;
+  GMX_CUDA(c, cudaMemcpy(p->d_arena, arena.data(), p->layout.total, cudaMemcpyHostToDevice));
+  GMX_CUDA(c, cudaMemcpy(p->d_state, state.data(), sizeof(gmx::StreamSmem), cudaMemcpyHostToDevice));
+  p->pending_bit = -1;
+  p->bits = 0;
+  return 0;
 }
 
 uint32_t gmx_resident_streams(const gmx_ctx* c) { return c ? c->last_grid : 0; }

@@ -12,6 +12,7 @@ constexpr int kStreamMinBlocks = 8;   // resident CTAs per SM the register budge
 cudaError_t LaunchCompress(const StreamParams& P, unsigned grid, cudaStream_t st);
 cudaError_t LaunchCompressProf(const StreamParams& P, unsigned grid, cudaStream_t st);
 cudaError_t LaunchDecompress(const StreamParams& P, unsigned grid, cudaStream_t st);
+cudaError_t LaunchGenerate(const StreamParams& P, unsigned grid, cudaStream_t st);
 cudaError_t LaunchStep(const StepParams& Q, cudaStream_t st);
 unsigned StepStateBytes();
 cudaError_t OccupancyCompress(int* blocks_per_sm);

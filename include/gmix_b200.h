@@ -10,6 +10,10 @@
  *                                   (coder: coder/encoder.cpp:8-34, coder/decoder.cpp:3-39;
  *                                    per bit: Predictor::Predict/Perceive/Learn predictor.cpp:360-387)
  *   gmx_compress_trace              same loop, additionally exporting what Predictor::Predict returns per bit
+ *   gmx_model_load, gmx_*_from      Predictor::ReadCheckpoint predictor.cpp:406-420 (+ `gmix -c/-d <ckpt>` runner-utils.cpp:110-116)
+ *   gmx_generate_batch / _device    runner_utils::RunGeneration runner/runner-utils.cpp:158-221
+ *   gmx_train_checkpoint,           Predictor::WriteCheckpoint predictor.cpp:389-404
+ *   gmx_pred_write/read_checkpoint
  *
  * A per-bit host<->device call is a non-starter (2.1e9 bit steps in the 4096 x 64 KiB config), so
  * the ABI is stream-batch granular: n independent streams, each compressed from scratch exactly
@@ -86,6 +90,47 @@ int gmx_decompress_batch_device(gmx_ctx* ctx, const uint8_t* d_in, const uint64_
                                 uint8_t* d_out, const uint64_t* d_out_off, uint64_t* d_out_len, uint32_t* d_status,
                                 uint64_t max_stream_len);
 
+/* ---- Checkpoints (reference src/memory: `<path>.short` + `<path>.long`) and generation --------------------
+ * gmx_model_load replaces Predictor::ReadCheckpoint (predictor.cpp:406-420): it parses the two files exactly as the
+ * reference writes them (every Model::WriteToDisk in construction order + ShortTermMemory::WriteToDisk
+ * memory/short-term-memory.cpp:3-59; LongTermMemory::WriteToDisk memory/long-term-memory.cpp:6-108) and parks the
+ * resulting stream on the device. The *_from calls then start every stream as a clone of it: `gmix -c <ckpt> in out`,
+ * `gmix -d <ckpt> in out` (runner-utils.cpp:88-156). max_new_bytes bounds the bytes any stream adds on top (stream
+ * length, or prompt + generated bytes); roomy != 0 sizes the tables for worst-case instead of text-like data.
+ * Only byte-boundary checkpoints exist in practice (the reference writes them after whole files) and only those load. */
+typedef struct gmx_model gmx_model;
+int gmx_model_load(gmx_ctx* ctx, const void* short_blob, uint64_t short_len, const void* long_blob, uint64_t long_len,
+                   uint64_t max_new_bytes, int roomy, gmx_model** out);
+void gmx_model_free(gmx_model* model);
+uint64_t gmx_model_arena_bytes(const gmx_model* model);     /* bytes of one stream arena cloned from this model */
+uint64_t gmx_model_trained_bytes(const gmx_model* model);   /* bytes the checkpoint had learned (Mixer::steps_ / 8) */
+int gmx_compress_batch_from(gmx_ctx* ctx, const gmx_model* model, const uint8_t* in, const uint64_t* in_off, uint32_t n_streams,
+                            uint8_t* out, const uint64_t* out_off, uint64_t* out_len, uint32_t* status);
+int gmx_decompress_batch_from(gmx_ctx* ctx, const gmx_model* model, const uint8_t* in, const uint64_t* in_off, uint32_t n_streams,
+                              uint8_t* out, const uint64_t* out_off, uint64_t* out_len, uint32_t* status);
+
+/* runner_utils::RunGeneration (runner-utils.cpp:158-221) for n prompts at once, one CTA per prompt: prompt i =
+ * prompts[prompt_off[i] .. prompt_off[i+1]) is consumed WITH learning except its last byte, then out_bytes bytes are
+ * sampled without Learn into out[i * out_bytes ..]. rand_u holds the rand()/RAND_MAX draws, one per generated bit;
+ * stream i reads rand_u[i * rand_stride + k] (rand_stride 0: all streams share one sequence, which is what n separate
+ * `gmix -g` processes do). temperature is clamped to >= 0.001 as the reference does. */
+int gmx_generate_batch(gmx_ctx* ctx, const gmx_model* model, const uint8_t* prompts, const uint64_t* prompt_off, uint32_t n,
+                       uint32_t out_bytes, float temperature, const float* rand_u, uint64_t rand_stride, uint8_t* out,
+                       uint32_t* status);
+int gmx_generate_batch_device(gmx_ctx* ctx, const gmx_model* model, const uint8_t* d_prompts, const uint64_t* d_prompt_off, uint32_t n,
+                              uint32_t out_bytes, float temperature, const float* d_rand_u, uint64_t rand_stride, uint8_t* d_out,
+                              uint64_t* d_out_len, uint32_t* d_status, uint64_t max_prompt_len);
+/* The draws one `gmix -g` process makes for sampling: srand(0xDEADBEEF) (predictor.cpp:18), 84450 draws consumed by
+ * the LSTM initialisation (lstm-layer.cpp:176-195), then n x rand()/RAND_MAX. Uses and reseeds the host libc rand(). */
+void gmx_reference_rand_u(float* out, uint64_t n);
+
+/* Predict/Perceive/Learn over data[0..n) (analysis off, as RunTraining and a plain Predictor loop do), starting from
+ * `from` or from scratch, then Predictor::WriteCheckpoint (predictor.cpp:389-404): *short_blob / *long_blob point at
+ * library-owned buffers valid until the next call on ctx. The `.long` bytes equal the reference's; `.short` differs
+ * only in fields the reference rebuilds before reading (gmix_b200/csrc/checkpoint.h). */
+int gmx_train_checkpoint(gmx_ctx* ctx, const gmx_model* from, const uint8_t* data, uint64_t n, const void** short_blob,
+                         uint64_t* short_len, const void** long_blob, uint64_t* long_len);
+
 /* FNV-1a 64 checksum of every stream slice d_data[d_off[i] .. d_off[i]+d_len[i]) into d_sum[i] (device
  * pointers; enqueued on the ctx stream, not synchronised). Used to gather {size, checksum} per stream
  * across GPUs without moving the payload. */
@@ -112,6 +157,10 @@ int gmx_pred_enable_analysis(gmx_pred* pred, int on);
 int gmx_pred_predict(gmx_pred* pred, float* prob);
 int gmx_pred_perceive(gmx_pred* pred, int bit);
 int gmx_pred_learn(gmx_pred* pred);
+
+/* Predictor::WriteCheckpoint / ReadCheckpoint (predictor.cpp:389-420) of the stepped stream, at a byte boundary. */
+int gmx_pred_write_checkpoint(gmx_pred* pred, const void** short_blob, uint64_t* short_len, const void** long_blob, uint64_t* long_len);
+int gmx_pred_read_checkpoint(gmx_pred* pred, const void* short_blob, uint64_t short_len, const void* long_blob, uint64_t long_len);
 
 /* Introspection for benchmarks. */
 uint32_t gmx_resident_streams(const gmx_ctx* ctx);   /* CTAs (= arenas) the last launch used */

@@ -1,0 +1,42 @@
+"""CPU: the committed checkpoint fixtures (written by the UNMODIFIED reference, tests/golden/make_golden_ckpt.py) drive
+the product's kernel source under the SIMT emulator: load, continue compressing, generate. Unlike
+test_checkpoint_emu.py this needs no reference build, so it also pins the format on machines without /root/reference."""
+import gzip
+import os
+import subprocess
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+
+
+@pytest.fixture(scope="module")
+def work(tmp_path_factory):
+    d = tmp_path_factory.mktemp("ckptgold")
+    exe = str(d / "emu_main")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-w", "-o", exe, os.path.join(HERE, "emu", "emu_main.cpp")], check=True)
+    for ext in (".short", ".long"):
+        (d / ("ckpt600" + ext)).write_bytes(gzip.open(os.path.join(GOLD, "ckpt600" + ext + ".gz")).read())
+    (d / "b.in").write_bytes(open(os.path.join(GOLD, "text1k.in"), "rb").read()[600:])
+    return d, exe
+
+
+def test_fixture_checkpoint_resumes_to_the_reference_stream(work):
+    d, exe = work
+    subprocess.run([exe, "resume", str(d / "ckpt600"), str(d / "b.in"), str(d / "b.gmix")], check=True, stderr=subprocess.DEVNULL)
+    assert (d / "b.gmix").read_bytes() == open(os.path.join(GOLD, "ckpt600_b.gmix"), "rb").read()
+
+
+def test_fixture_checkpoint_recodes_to_itself(work):
+    d, exe = work
+    subprocess.run([exe, "recode", str(d / "ckpt600"), str(d / "rec")], check=True, stderr=subprocess.DEVNULL)
+    assert (d / "rec.short").read_bytes() == (d / "ckpt600.short").read_bytes()
+    assert (d / "rec.long").read_bytes() == (d / "ckpt600.long").read_bytes()
+
+
+def test_fixture_generation(work):
+    d, exe = work
+    subprocess.run([exe, "generate", str(d / "ckpt600"), os.path.join(GOLD, "ckpt600_prompt.txt"), str(d / "gen.out"), "40", "0.5"],
+                   check=True, stderr=subprocess.DEVNULL)
+    assert (d / "gen.out").read_bytes() == open(os.path.join(GOLD, "ckpt600_gen_40_0.5.out"), "rb").read()

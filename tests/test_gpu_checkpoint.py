@@ -1,0 +1,90 @@
+"""GPU: checkpoints in the reference's format and batched generation, through the C ABI, against fixtures produced by
+the UNMODIFIED reference (tests/golden/make_golden_ckpt.py): a reference-written checkpoint loads unchanged and
+`gmix -c/-d <ckpt>` / `gmix -g` reproduce the reference's bytes; the checkpoint the GPU writes has the reference's
+`.long` bytes and a `.short` that differs only in documented scratch fields; the Predictor facade reads and writes
+the same files."""
+import gzip
+import os
+
+import pytest
+
+import ckpt_layout
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+TEXT = open(os.path.join(GOLD, "text1k.in"), "rb").read()
+A, B = TEXT[:600], TEXT[600:]
+PROMPT = open(os.path.join(GOLD, "ckpt600_prompt.txt"), "rb").read()
+
+
+@pytest.fixture(scope="module")
+def ckpt():
+    return gzip.open(os.path.join(GOLD, "ckpt600.short.gz")).read(), gzip.open(os.path.join(GOLD, "ckpt600.long.gz")).read()
+
+
+@pytest.fixture()
+def model(gpu_ctx, ckpt):
+    import gmix_b200
+    m = gmix_b200.Model(gpu_ctx, ckpt[0], ckpt[1], max_new_bytes=2048)
+    yield m
+    m.close()
+
+
+def test_reference_checkpoint_loads_and_compress_decompress_continue_identically(gpu_ctx, model):
+    assert model.trained_bytes == 600
+    want = open(os.path.join(GOLD, "ckpt600_b.gmix"), "rb").read()
+    streams = [B, B[:100], B, b""]
+    comp = gpu_ctx.compress_batch_from(model, streams)
+    assert comp[0] == want and comp[2] == want          # every stream is an independent clone of the checkpoint
+    assert gpu_ctx.decompress_batch_from(model, comp) == streams
+    # and the context still serves from-scratch streams afterwards
+    assert gpu_ctx.compress_batch([TEXT]) == [open(os.path.join(GOLD, "text1k.gmix"), "rb").read()]
+
+
+@pytest.mark.parametrize("size,temp", [(48, 1.0), (40, 0.5)])
+def test_batched_generation_samples_the_reference_bytes(gpu_ctx, model, size, temp):
+    want = open(os.path.join(GOLD, f"ckpt600_gen_{size}_{temp}.out"), "rb").read()
+    prompts = [PROMPT] * 5 + [PROMPT[:9] + b"\n"]
+    out = gpu_ctx.generate_batch(model, prompts, size, temp)
+    assert all(o == want for o in out[:5])
+    assert len(out[5]) == size and out[5] != want        # another prompt, another continuation
+    # learning is off while sampling, so the same call again gives the same bytes (LongTermMemory untouched, tester.cpp:358-366)
+    assert gpu_ctx.generate_batch(model, prompts[:2], size, temp) == out[:2]
+
+
+def test_written_checkpoint_matches_the_reference_files(gpu_ctx, ckpt):
+    sh, lo = gpu_ctx.train_checkpoint(A)
+    assert lo == ckpt[1]
+    diff = ckpt_layout.differing_sections(sh, ckpt[0])
+    assert set(diff) <= ckpt_layout.SCRATCH, [x for x in diff if x not in ckpt_layout.SCRATCH]
+    # training continues from a checkpoint: A then B equals A+B in one go
+    import gmix_b200
+    m = gmix_b200.Model(gpu_ctx, sh, lo, max_new_bytes=len(B))
+    sh2, lo2 = gpu_ctx.train_checkpoint(B, m)
+    m.close()
+    sh3, lo3 = gpu_ctx.train_checkpoint(TEXT)
+    assert lo2 == lo3
+    assert set(ckpt_layout.differing_sections(sh2, sh3)) <= ckpt_layout.SCRATCH
+
+
+def test_predictor_facade_reads_and_writes_checkpoints(gpu_ctx, ckpt):
+    import gmix_b200
+    import numpy as np
+    p16 = np.fromfile(os.path.join(GOLD, "text1k.p16"), dtype=np.uint16)   # the reference's whole-stream run
+    p = gmix_b200.Predictor(gpu_ctx, 4096)
+    p.enable_analysis(True)                               # what `gmix -c <ckpt>` does for this length (runner-utils.cpp:47)
+    p.read_checkpoint(*ckpt)                              # Predictor::ReadCheckpoint
+    got = []
+    for byte in TEXT[600:640]:
+        for j in range(7, -1, -1):
+            got.append(int(1 + 65534 * np.float32(p.predict())))
+            p.perceive((byte >> j) & 1)
+            p.learn()
+    assert got == [int(x) for x in p16[600 * 8:640 * 8]]
+    sh, lo = p.write_checkpoint()                         # Predictor::WriteCheckpoint
+    p.close()
+    sh_ref, lo_ref = gpu_ctx.train_checkpoint(TEXT[:640])
+    assert lo == lo_ref
+    assert set(ckpt_layout.differing_sections(sh, sh_ref)) <= ckpt_layout.SCRATCH
