@@ -4,8 +4,11 @@
 // stream; bulk work should use gmx_compress_batch / gmx_decompress_batch instead.
 #ifndef GMIX_B200_HOST_PREDICTOR_H_
 #define GMIX_B200_HOST_PREDICTOR_H_
+#include <fstream>
+#include <iterator>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "../../include/gmix_b200.h"
 
@@ -45,6 +48,28 @@ class Predictor {
   void Learn() { Check(gmx_pred_learn(p_)); }                       // predictor.cpp:383-387
   // Only the path-visible effect of EnableAnalysis (predictions zeroed each Predict, predictor.cpp:362-365).
   void EnableAnalysis(int sample_frequency) { Check(gmx_pred_enable_analysis(p_, sample_frequency > 0)); }
+  // `path`.short + `path`.long in the reference's format (predictor.cpp:389-420); like the reference, a file that
+  // cannot be opened is silently ignored. Call at a byte boundary (after Learn() of a byte's last bit).
+  void WriteCheckpoint(const std::string& path) {
+    const void *sp, *lp;
+    uint64_t sl, ll;
+    Check(gmx_pred_write_checkpoint(p_, &sp, &sl, &lp, &ll));
+    std::ofstream fs(path + ".short", std::ios::out | std::ios::binary);
+    if (!fs.is_open()) return;
+    std::ofstream fl(path + ".long", std::ios::out | std::ios::binary);
+    if (!fl.is_open()) return;
+    fs.write((const char*)sp, (std::streamsize)sl);
+    fl.write((const char*)lp, (std::streamsize)ll);
+  }
+  void ReadCheckpoint(const std::string& path) {
+    std::ifstream fs(path + ".short", std::ios::in | std::ios::binary);
+    if (!fs.is_open()) return;
+    std::ifstream fl(path + ".long", std::ios::in | std::ios::binary);
+    if (!fl.is_open()) return;
+    const std::vector<char> s((std::istreambuf_iterator<char>(fs)), std::istreambuf_iterator<char>());
+    const std::vector<char> l((std::istreambuf_iterator<char>(fl)), std::istreambuf_iterator<char>());
+    Check(gmx_pred_read_checkpoint(p_, s.data(), s.size(), l.data(), l.size()));
+  }
 
  private:
   void Check(int rc) { if (rc != 0) throw std::runtime_error(gmx_last_error(gpu_.ctx())); }

@@ -1,20 +1,24 @@
 // gmixb200 — command-line runner over libgmix_b200.so, mirroring the reference CLI (reference
 // src/runner/runner.cpp:14-104, src/runner/runner-utils.cpp:88-156):
 //
-//   gmixb200 -c input output        compress, one stream; bytes identical to `gmix -c` (strict build)
-//   gmixb200 -d input output        decompress a stream written by either program
+//   gmixb200 -c [ckpt] input output   compress, one stream; bytes identical to `gmix -c` (strict build)
+//   gmixb200 -d [ckpt] input output   decompress a stream written by either program
+//   gmixb200 -g ckpt prompt output size temperature    generate, bytes identical to `gmix -g` (runner-utils.cpp:158-221)
+//   gmixb200 -t [ckpt] train test     Predict/Perceive/Learn over `train`, write data/trained_checkpoint.{short,long}
+//                                     (the reference's format) and report the cross entropy of `test` under the trained
+//                                     model (runner-utils.cpp:223-322 without the periodic test passes)
 //   gmixb200 -C bytes input output  split input into chunks of `bytes`, compress them as independent
 //                                   streams in one GPU batch (container: "GMXB", u32 count, u64 sizes[], streams)
 //   gmixb200 -D input output        inverse of -C
 //   gmixb200 -p input output        compress one stream through the Predictor facade + host coder
 //                                   (Predict/Perceive/Learn per bit; slow, for checking the drop-in interface)
-//
-// Not implemented on the GPU path yet: the optional checkpoint argument, -g and -t.
+// `ckpt` is a checkpoint prefix: <ckpt>.short + <ckpt>.long, written by the reference or by this program.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
 
+#include <filesystem>
 #include <fstream>
 #include <iterator>
 #include <string>
@@ -28,11 +32,12 @@ namespace {
 
 int Help() {
   printf("gmixb200 (B200 build of the gmix per-bit path)\n"
-         "Compress:    gmixb200 -c input output\n"
-         "Decompress:  gmixb200 -d input output\n"
+         "Compress:    gmixb200 -c [checkpoint_path] input output\n"
+         "Decompress:  gmixb200 -d [checkpoint_path] input output\n"
+         "Generate:    gmixb200 -g checkpoint_path prompt output output_size temperature\n"
+         "Train:       gmixb200 -t [checkpoint_path] training_file test_file\n"
          "Chunked:     gmixb200 -C chunk_bytes input output   /   gmixb200 -D input output\n"
-         "Via facade:  gmixb200 -p input output\n"
-         "Checkpoints, -g (generate) and -t (train) are not available on the GPU path yet.\n");
+         "Via facade:  gmixb200 -p input output\n");
   return -1;
 }
 
@@ -54,8 +59,18 @@ struct Batch {
   std::vector<uint64_t> out_off, out_len;
 };
 
-// n streams in[in_off[i]..in_off[i+1]) -> Batch, through the C ABI.
-bool RunBatch(gmx_ctx* ctx, bool compress, const std::vector<uint8_t>& in, const std::vector<uint64_t>& in_off, Batch* b) {
+// Predictor::ReadCheckpoint for the batch calls: <prefix>.short/.long -> device-resident model.
+gmx_model* LoadModel(gmx_ctx* ctx, const std::string& prefix, uint64_t max_new_bytes) {
+  std::vector<uint8_t> sh, lo;
+  if (!ReadFile(prefix + ".short", &sh) || !ReadFile(prefix + ".long", &lo)) { printf("Error opening: %s.short/.long\n", prefix.c_str()); return nullptr; }
+  gmx_model* m = nullptr;
+  if (gmx_model_load(ctx, sh.data(), sh.size(), lo.data(), lo.size(), max_new_bytes, 0, &m) != 0) { printf("%s\n", gmx_last_error(ctx)); return nullptr; }
+  return m;
+}
+
+// n streams in[in_off[i]..in_off[i+1]) -> Batch, through the C ABI; model != null: every stream starts from it.
+bool RunBatch(gmx_ctx* ctx, bool compress, const std::vector<uint8_t>& in, const std::vector<uint64_t>& in_off, Batch* b,
+              const gmx_model* model = nullptr) {
   const uint32_t n = (uint32_t)in_off.size() - 1;
   b->out_off.assign(n + 1, 0);
   for (uint32_t i = 0; i < n; ++i) {
@@ -73,8 +88,11 @@ bool RunBatch(gmx_ctx* ctx, bool compress, const std::vector<uint8_t>& in, const
   std::vector<uint32_t> status(n, 0);
   static const uint8_t kNone = 0;
   const uint8_t* src = in.empty() ? &kNone : in.data();
-  const int rc = compress ? gmx_compress_batch(ctx, src, in_off.data(), n, b->out.data(), b->out_off.data(), b->out_len.data(), status.data())
-                          : gmx_decompress_batch(ctx, src, in_off.data(), n, b->out.data(), b->out_off.data(), b->out_len.data(), status.data());
+  int rc;
+  if (model) rc = compress ? gmx_compress_batch_from(ctx, model, src, in_off.data(), n, b->out.data(), b->out_off.data(), b->out_len.data(), status.data())
+                           : gmx_decompress_batch_from(ctx, model, src, in_off.data(), n, b->out.data(), b->out_off.data(), b->out_len.data(), status.data());
+  else rc = compress ? gmx_compress_batch(ctx, src, in_off.data(), n, b->out.data(), b->out_off.data(), b->out_len.data(), status.data())
+                     : gmx_decompress_batch(ctx, src, in_off.data(), n, b->out.data(), b->out_off.data(), b->out_len.data(), status.data());
   if (rc != 0) { printf("%s\n", gmx_last_error(ctx)); return false; }
   return true;
 }
@@ -98,16 +116,88 @@ bool CompressViaPredictor(const std::vector<uint8_t>& in, std::vector<uint8_t>* 
   return true;
 }
 
+uint64_t HeaderLength(const std::vector<uint8_t>& in) {  // ReadHeader runner-utils.cpp:29-36
+  uint64_t n = 0;
+  for (size_t k = 0; k < 5 && k < in.size(); ++k) n = (n << 8) + in[k];
+  return n;
+}
+
+// RunGeneration (runner-utils.cpp:158-221) for one prompt.
+int Generate(int argc, char* argv[]) {
+  if (argc != 7) { printf("Wrong number of arguments.\n"); return Help(); }
+  std::vector<uint8_t> prompt;
+  if (!ReadFile(argv[3], &prompt) || prompt.empty()) { printf("Can not open: %s\n", argv[3]); return Help(); }
+  const int size = std::stoi(argv[5]);
+  const float temperature = std::stof(argv[6]);
+  if (size < 0) return Help();
+  const clock_t start = clock();
+  gmixb::Gpu gpu(0);
+  gmx_model* m = LoadModel(gpu.ctx(), argv[2], prompt.size() + (uint64_t)size);
+  if (!m) return -1;
+  std::vector<float> rand_u((size_t)size * 8 + 1);
+  gmx_reference_rand_u(rand_u.data(), (uint64_t)size * 8);
+  std::vector<uint8_t> out((size_t)size + 1);
+  const uint64_t off[2] = {0, prompt.size()};
+  uint32_t status = 0;
+  const int rc = size ? gmx_generate_batch(gpu.ctx(), m, prompt.data(), off, 1, (uint32_t)size, temperature, rand_u.data(), 0, out.data(), &status) : 0;
+  if (rc != 0) printf("%s\n", gmx_last_error(gpu.ctx()));
+  gmx_model_free(m);
+  if (rc != 0) return -1;
+  if (!WriteFile(argv[4], out.data(), (size_t)size)) { printf("Can not open: %s\n", argv[4]); return Help(); }
+  printf("generation: 100%%\n%1.2f s.\n", ((double)clock() - start) / CLOCKS_PER_SEC);
+  return 0;
+}
+
+// RunTraining (runner-utils.cpp:223-322): learn the training file, write data/trained_checkpoint, score the test file.
+int Train(int argc, char* argv[]) {
+  if (argc != 4 && argc != 5) { printf("Wrong number of arguments.\n"); return Help(); }
+  const std::string ckpt = argc == 5 ? argv[2] : "", train_path = argv[argc - 2], test_path = argv[argc - 1];
+  std::vector<uint8_t> train, test;
+  if (!ReadFile(train_path, &train)) { printf("Can not open: %s\n", train_path.c_str()); return Help(); }
+  if (!ReadFile(test_path, &test)) { printf("Can not open: %s\n", test_path.c_str()); return Help(); }
+  const clock_t start = clock();
+  gmixb::Gpu gpu(0);
+  gmx_model* from = nullptr;
+  if (!ckpt.empty() && !(from = LoadModel(gpu.ctx(), ckpt, train.size()))) return -1;
+  const void *sp, *lp;
+  uint64_t sl, ll;
+  int rc = gmx_train_checkpoint(gpu.ctx(), from, train.data(), train.size(), &sp, &sl, &lp, &ll);
+  if (from) gmx_model_free(from);
+  if (rc != 0) { printf("%s\n", gmx_last_error(gpu.ctx())); return -1; }
+  std::filesystem::create_directory("data");
+  if (!WriteFile("data/trained_checkpoint.short", (const uint8_t*)sp, sl) || !WriteFile("data/trained_checkpoint.long", (const uint8_t*)lp, ll)) {
+    printf("Can not write data/trained_checkpoint\n");
+    return -1;
+  }
+  gmx_model* trained = nullptr;
+  if (gmx_model_load(gpu.ctx(), sp, sl, lp, ll, test.size(), 0, &trained) != 0) { printf("%s\n", gmx_last_error(gpu.ctx())); return -1; }
+  Batch b;
+  const bool ok = RunBatch(gpu.ctx(), true, test, {0, test.size()}, &b, trained);
+  gmx_model_free(trained);
+  if (!ok) return -1;
+  printf("trained on %zu bytes -> data/trained_checkpoint (.short %llu B, .long %llu B)\n", train.size(), (unsigned long long)sl, (unsigned long long)ll);
+  printf("test cross entropy: %.4f\n", test.empty() ? 0.0 : 8.0 * (double)(b.out_len[0] - 5) / test.size());
+  printf("%1.2f s.\n", ((double)clock() - start) / CLOCKS_PER_SEC);
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char* argv[]) {
   if (argc < 4 || strlen(argv[1]) != 2 || argv[1][0] != '-') return Help();
   const char mode = argv[1][1];
-  if (mode == 'g' || mode == 't') { printf("-%c is not available on the GPU path yet.\n", mode); return Help(); }
-  if ((mode == 'c' || mode == 'd') && argc == 5) { printf("Checkpoints are not available on the GPU path yet.\n"); return Help(); }
+  try {
+    if (mode == 'g') return Generate(argc, argv);
+    if (mode == 't') return Train(argc, argv);
+  } catch (const std::exception& e) {
+    printf("%s\n", e.what());
+    return -1;
+  }
   const bool chunked_c = mode == 'C';
-  if ((chunked_c && argc != 5) || (!chunked_c && argc != 4) || !strchr("cdCDp", mode)) return Help();
-  const std::string input_path = argv[chunked_c ? 3 : 2], output_path = argv[chunked_c ? 4 : 3];
+  const bool with_ckpt = (mode == 'c' || mode == 'd') && argc == 5;
+  if ((chunked_c && argc != 5) || (!chunked_c && !with_ckpt && argc != 4) || !strchr("cdCDp", mode)) return Help();
+  const std::string checkpoint_path = with_ckpt ? argv[2] : "";
+  const std::string input_path = argv[chunked_c || with_ckpt ? 3 : 2], output_path = argv[chunked_c || with_ckpt ? 4 : 3];
   std::vector<uint8_t> in;
   if (!ReadFile(input_path, &in)) { printf("Error opening: %s\n", input_path.c_str()); return Help(); }
   const clock_t start = clock();
@@ -139,7 +229,11 @@ int main(int argc, char* argv[]) {
         src = &payload;
       }
       Batch b;
-      if (!RunBatch(gpu.ctx(), mode == 'c' || mode == 'C', *src, in_off, &b)) return -1;
+      gmx_model* model = nullptr;
+      if (with_ckpt && !(model = LoadModel(gpu.ctx(), checkpoint_path, mode == 'c' ? in.size() : HeaderLength(in)))) return -1;
+      const bool ok = RunBatch(gpu.ctx(), mode == 'c' || mode == 'C', *src, in_off, &b, model);
+      if (model) gmx_model_free(model);
+      if (!ok) return -1;
       const uint32_t n = (uint32_t)in_off.size() - 1;
       if (mode == 'C') {
         result.assign({'G', 'M', 'X', 'B'});

@@ -84,3 +84,29 @@ def test_runner_chunked_roundtrip_and_facade_mode(tmp_path):
     out = str(tmp_path / "p.gmix")
     subprocess.run([RUNNER, "-p", os.path.join(GOLD, "short124.in"), out], check=True)
     assert open(out, "rb").read() == open(os.path.join(GOLD, "short124.gmix"), "rb").read()
+
+
+def test_runner_checkpoint_generate_and_train_cli(tmp_path):
+    """The reference CLI shapes with a checkpoint (runner.cpp:14-104): -c/-d <ckpt>, -g, -t; fixtures written by the
+    unmodified reference (tests/golden/make_golden_ckpt.py)."""
+    import gzip
+    import ckpt_layout
+    d = tmp_path
+    ck = str(d / "ckpt600")
+    short_ref = gzip.open(os.path.join(GOLD, "ckpt600.short.gz")).read()
+    long_ref = gzip.open(os.path.join(GOLD, "ckpt600.long.gz")).read()
+    open(ck + ".short", "wb").write(short_ref)
+    open(ck + ".long", "wb").write(long_ref)
+    text = open(os.path.join(GOLD, "text1k.in"), "rb").read()
+    (d / "a.in").write_bytes(text[:600])
+    (d / "b.in").write_bytes(text[600:])
+    subprocess.run([RUNNER, "-c", ck, str(d / "b.in"), str(d / "b.gmix")], check=True)
+    assert (d / "b.gmix").read_bytes() == open(os.path.join(GOLD, "ckpt600_b.gmix"), "rb").read()
+    subprocess.run([RUNNER, "-d", ck, str(d / "b.gmix"), str(d / "b.back")], check=True)
+    assert (d / "b.back").read_bytes() == text[600:]
+    subprocess.run([RUNNER, "-g", ck, os.path.join(GOLD, "ckpt600_prompt.txt"), str(d / "gen.out"), "48", "1.0"], check=True)
+    assert (d / "gen.out").read_bytes() == open(os.path.join(GOLD, "ckpt600_gen_48_1.0.out"), "rb").read()
+    subprocess.run([RUNNER, "-t", str(d / "a.in"), str(d / "b.in")], check=True, cwd=str(d))
+    assert (d / "data" / "trained_checkpoint.long").read_bytes() == long_ref
+    diff = ckpt_layout.differing_sections((d / "data" / "trained_checkpoint.short").read_bytes(), short_ref)
+    assert set(diff) <= ckpt_layout.SCRATCH, diff
