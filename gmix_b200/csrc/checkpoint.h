@@ -541,7 +541,7 @@ inline bool ToArena(const Image& im, const ArenaLayout& L, uint8_t* arena, Strea
       const auto& n = im.nl[g];
       for (int i = 0; i < L_CELLS; ++i)
         for (int j = 0; j < L_ROW; ++j) {
-          const size_t dst = ((size_t)g * L_ROW + j) * L_CELLS + i, src = (size_t)i * L_ROW + j;
+          const size_t dst = LstmW(g, j, i), src = (size_t)i * L_ROW + j;
           W[dst] = im.wgate[(size_t)g * L_CELLS * L_ROW + src]; M[dst] = n.m[src]; V[dst] = n.v[src];
         }
       const float* q8[8] = {n.gamma, n.beta, n.gamma_m, n.gamma_v, n.beta_m, n.beta_v, n.gamma_u, n.beta_u};
@@ -685,7 +685,7 @@ inline bool FromArena(const ArenaLayout& L, const uint8_t* arena, const StreamSm
       n.state.resize(hc); n.update.assign(wsz, 0.0f); n.m.resize(wsz); n.v.resize(wsz); n.transpose.resize((size_t)kTr * L_CELLS); n.norm.resize(hc);
       for (int i = 0; i < L_CELLS; ++i)
         for (int j = 0; j < L_ROW; ++j) {
-          const size_t src = ((size_t)g * L_ROW + j) * L_CELLS + i, dst = (size_t)i * L_ROW + j;
+          const size_t src = LstmW(g, j, i), dst = (size_t)i * L_ROW + j;
           im.wgate[g * wsz + dst] = W[src]; n.m[dst] = M[src]; n.v[dst] = V[src];
         }
       float* q8[8] = {n.gamma, n.beta, n.gamma_m, n.gamma_v, n.beta_m, n.beta_v, n.gamma_u, n.beta_u};

@@ -103,7 +103,7 @@ inline ArenaLayout MakeLayout(uint64_t max_len, bool roomy = false, const Preloa
   L.mix_pool_sets = (uint32_t)sets;
   L.mix_set_stride = 120;  // 4 header words {steps, 0, 0, 0} + up to 116 weight slots (29 float4), 16-byte multiple
   L.mix_pool = take(sets * L.mix_set_stride * 4);
-  const uint64_t wsz = 3ull * L_ROW * L_CELLS * 4;
+  const uint64_t wsz = (uint64_t)L_WSIZE * 4;
   L.l_w = take(wsz); L.l_m = take(wsz); L.l_v = take(wsz);
   L.l_gb = take(8 * 3 * L_CELLS * 4);
   L.l_wout = take((uint64_t)L_HORIZON * L_HID * L_NOUT * 4);
@@ -180,9 +180,9 @@ inline void FillAdamTable(std::vector<float>& t) {
 
 // Initial LSTM gate weights (lstm-layer.cpp:176-195): srand(0xDEADBEEF) (predictor.cpp:18), then
 // per cell i, per column j, one glibc rand() draw for each of the three gates in turn; forget-gate
-// bias column = 1. Stored transposed: out[(g * L_ROW + j) * L_CELLS + i].
+// bias column = 1. Stored in the device layout: out[LstmW(g, j, i)] (spec.cuh).
 inline void FillLstmInit(std::vector<float>& out) {
-  out.assign(3ull * L_ROW * L_CELLS, 0.0f);
+  out.assign((size_t)L_WSIZE, 0.0f);
   srand(0xDEADBEEF);
   float val = sqrtf(6.0f / float(256 + 256));
   float low = -val;
@@ -191,10 +191,10 @@ inline void FillLstmInit(std::vector<float>& out) {
     for (int j = 0; j < L_ROW; ++j) {
       for (int g = 0; g < 3; ++g) {
         float r = static_cast<float>(rand()) / static_cast<float>(RAND_MAX);
-        out[((size_t)g * L_ROW + j) * L_CELLS + i] = low + r * range;
+        out[LstmW(g, j, i)] = low + r * range;
       }
     }
-    out[((size_t)0 * L_ROW + (L_ROW - 1)) * L_CELLS + i] = 1;
+    out[LstmW(0, L_ROW - 1, i)] = 1;
   }
 }
 

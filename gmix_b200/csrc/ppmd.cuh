@@ -195,6 +195,7 @@ struct Ppmd {
   GMX_DEV GMX_NOINLINE void Init() const {
     int i, k;
     PpmdFillTables(S);
+#pragma unroll 1
     for (i = 0; i < 256; i++) S->char_mask[i] = 0;
     S->esc_count = 1;
     S->order_fall = PPMD_MAX_ORDER;
@@ -213,10 +214,12 @@ struct Ppmd {
     SetFlags(mc, 0);
     SetSuffix(mc, 0);
     S->prev_success = 0;
+#pragma unroll 1
     for (i = 0; i < 256; i++) { SetSym(st + 6 * i, i); SetFreq(st + 6 * i, 1); SetSucc(st + 6 * i, 0); }
     const int esc_coef[12] = {16, -10, 1, 51, 14, 89, 23, 35, 64, 26, -42, 43};  // :35-36
     uint8_t i2f[25];
     for (k = i = 0; i < 25; i2f[i++] = (uint8_t)(k + 1)) while (S->qtable[k] == i) k++;
+#pragma unroll 1
     for (k = 0; k < 64; k++) {
       int s = 0;
       for (i = 0; i < 6; i++) s += esc_coef[2 * i + ((k >> i) & 1)];
@@ -224,7 +227,10 @@ struct Ppmd {
       s *= 128;
       for (i = 0; i < 25; i++) S->bin_summ[i][k] = (uint16_t)(PPMD_BIN_SCALE - s / i2f[i]);
     }
-    for (i = 0; i < 23; i++) for (k = 0; k < 32; k++) {
+#pragma unroll 1
+    for (i = 0; i < 23; i++)
+#pragma unroll 1
+      for (k = 0; k < 32; k++) {
       S->see2[i][k].shift = PPMD_PERIOD_BITS - 4;
       S->see2[i][k].summ = (uint16_t)((8 * i + 5) << (PPMD_PERIOD_BITS - 4));
       S->see2[i][k].count = 7;

@@ -81,6 +81,15 @@ constexpr int MixerWeights(int m) { return m < NL0 ? NPRED + m : m < NL0 + NL1 ?
 
 // LSTM dimensions (lstm-model.cpp:7).
 enum : int { L_CELLS = 50, L_HORIZON = 100, L_NIN = 307, L_ROW = 563, L_NOUT = 256, L_HID = 51, L_UPDATE_LIMIT = 3000 };
+// Gate weights and their Adam moments are stored as [3 gates][L_ROWQ quads of input columns][L_CELLS][4]: the four
+// consecutive input columns of one cell are one float4 and cells are adjacent, so the forward pass (one gate row per
+// thread, lanes = cells) moves 512 contiguous bytes per warp load and keeps 4x the bytes in flight of scalar loads.
+// Column 563 is padding (always 0).
+enum : int { L_ROWQ = (L_ROW + 3) / 4, L_WSIZE = 3 * L_ROWQ * L_CELLS * 4 };
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+constexpr inline unsigned LstmW(int g, int j, int i) { return (unsigned)(((g * L_ROWQ + (j >> 2)) * L_CELLS + i) * 4 + (j & 3)); }
 
 }  // namespace gmx
 #endif

@@ -76,7 +76,7 @@ struct ArenaLayout {
   uint64_t mix_dir[NMIX];     // u32 pool id per gate context (0 = no weight set yet)
   uint64_t mix_pool; uint32_t mix_pool_sets; uint32_t mix_set_stride;  // floats per set record
   // LSTM
-  uint64_t l_w, l_m, l_v;     // float [3][L_ROW][L_CELLS] (row-major by input column: coalesced over cells)
+  uint64_t l_w, l_m, l_v;     // float [3][L_ROWQ][L_CELLS][4], element (gate, column, cell) at LstmW() (spec.cuh)
   uint64_t l_gb;              // float [8][3][L_CELLS]: gamma, beta, gamma_m, gamma_v, beta_m, beta_v, gamma_u, beta_u
   uint64_t l_wout;            // float [L_HORIZON][L_HID][L_NOUT]
   uint64_t l_lin;             // float [L_HORIZON][L_NIN + 1]
@@ -99,7 +99,7 @@ struct StreamParams {
   const uint32_t* ids;                           // optional: queue position -> stream id (retry launches), or null
   uint8_t* arenas; uint64_t arena_stride;
   const ArenaLayout* layout;
-  const float* lstm_init;    // [3][L_ROW][L_CELLS] initial gate weights (host glibc rand(), lstm-layer.cpp:176-195)
+  const float* lstm_init;    // [L_WSIZE] initial gate weights in the arena layout (host glibc rand(), lstm-layer.cpp:176-195)
   const float* decay;        // decay[s] = (float)(0.9 / pow(1e-7*s + 0.8, 0.8)) (mixer.cpp:111), host libm
   uint32_t decay_len;
   const float* adam;         // [L_UPDATE_LIMIT + 1][4]: alpha, 1-b1^t, 1-b2^t (lstm-layer.cpp:16-33), host libm
@@ -151,7 +151,7 @@ struct StreamSmem {
   alignas(4) uint8_t act[NPRED + NL0 + 2];   // prediction i is active; entries 90.. (layer-0 outputs) are always 1
   uint32_t ctx[C_COUNT + 2];
   alignas(16) float l0_out[NL0]; float l1_out[NL1], final_out, prob;   // l0_out | l1_out contiguous (final mixer input)
-  float ppm[256], lprob[256];          // byte distributions of PPMd and LSTM
+  alignas(16) float ppm[256], lprob[256];   // byte distributions of PPMd and LSTM
   float node_ppm[256], node_lstm[256]; // Logit(p) of every node of the binary interval search
   uint8_t nflag_ppm[256], nflag_lstm[256];  // bit0: denom != 0, bit1: p != 0.5
   uint8_t ring[32];            // last bytes (the reference keeps 1000, short-term-memory.h:23; only 10 are ever read)
@@ -179,7 +179,7 @@ struct StreamSmem {
   // indirect hash
   uint64_t ih_outer[NIH]; uint32_t ih_hash[NIH];
   // LSTM
-  float l_hidden[L_HID + 1], l_state[L_CELLS], l_state_err[L_CELLS], l_stored_err[L_CELLS], l_hidden_err[L_CELLS];
+  alignas(16) float l_hidden[L_HID + 1]; float l_state[L_CELLS], l_state_err[L_CELLS], l_stored_err[L_CELLS], l_hidden_err[L_CELLS];
   float l_gate[3][L_CELLS], l_gerr[3][L_CELLS];
   float l_red[16];
   union alignas(16) {            // never live at the same time:
@@ -395,7 +395,7 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
     if (!L.ih_sid[k]) FillWords<NT>(A.at<uint32_t>(L.ih_tab[k]), 1ull << s.T.ih[k].log2, 0u, tid);
   for (int m = 0; m < NMIX; ++m) FillWords<NT>(A.at<uint32_t>(L.mix_dir[m]), 1ull << s.T.mixer[m].log2, 0u, tid);
   // LSTM (lstm.cpp:8-43, lstm-layer.cpp:36-54,156-196)
-  for (int i = tid; i < 3 * L_ROW * L_CELLS; i += NT) {
+  for (int i = tid; i < L_WSIZE; i += NT) {
     A.at<float>(L.l_w)[i] = P.lstm_init[i];
     A.at<float>(L.l_m)[i] = 0.0f;
     A.at<float>(L.l_v)[i] = 0.0f;
@@ -490,7 +490,7 @@ GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, i
   {
     const float* W = A.at<float>(L.l_w);
 #if !defined(GMX_NO_LSTM_PREFETCH)
-    for (int g = 0; g < 3; ++g) PrefetchRangeKeep(W + ((size_t)g * L_ROW + L_NOUT) * L_CELLS, L_NIN * L_CELLS * 4, tid, NT);
+    for (int g = 0; g < 3; ++g) PrefetchRangeKeep(W + LstmW(g, L_NOUT, 0), (L_ROWQ - L_NOUT / 4) * L_CELLS * 16, tid, NT);
     PrefetchRange(A.at<float>(L.l_wout) + (size_t)e * L_HID * L_NOUT, L_HID * L_NOUT * 4, tid, NT);
 #endif
   }
@@ -506,25 +506,37 @@ GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, i
   if (tid < 3 * L_CELLS / 2) {
     const int t0 = tid, t1 = tid + 3 * L_CELLS / 2;
     const int g0 = t0 / L_CELLS, i0 = t0 - g0 * L_CELLS, g1 = t1 / L_CELLS, i1 = t1 - g1 * L_CELLS;
-    const float* w0 = A.at<float>(L.l_w) + (size_t)g0 * L_ROW * L_CELLS + i0;
-    const float* w1 = A.at<float>(L.l_w) + (size_t)g1 * L_ROW * L_CELLS + i1;
-    float f0 = w0[(size_t)sym * L_CELLS], f1 = w1[(size_t)sym * L_CELLS];
-    w0 += (size_t)L_NOUT * L_CELLS; w1 += (size_t)L_NOUT * L_CELLS;
-#pragma unroll 8
-    for (int j = 0; j < L_NOUT; ++j) {              // layer input = [ppm 256 | hidden 50 | 1]
-      const float x = s.ppm[j];
-      f0 = f_add(f0, f_mul(x, w0[(size_t)j * L_CELLS]));
-      f1 = f_add(f1, f_mul(x, w1[(size_t)j * L_CELLS]));
+    const float* W = A.at<float>(L.l_w);
+    float f0 = W[LstmW(g0, (int)sym, i0)], f1 = W[LstmW(g1, (int)sym, i1)];
+    // quad q of this row = input columns 4q..4q+3 = one 16-byte load
+    const float4* w0 = (const float4*)W + ((size_t)g0 * L_ROWQ + L_NOUT / 4) * L_CELLS + i0;
+    const float4* w1 = (const float4*)W + ((size_t)g1 * L_ROWQ + L_NOUT / 4) * L_CELLS + i1;
+    const float4* x4 = (const float4*)s.ppm;
+#pragma unroll 2
+    for (int q = 0; q < L_NOUT / 4; ++q) {           // layer input = [ppm 256 | hidden 50 | 1]
+      const float4 x = x4[q], a = w0[q * L_CELLS], b = w1[q * L_CELLS];
+      f0 = f_add(f0, f_mul(x.x, a.x)); f1 = f_add(f1, f_mul(x.x, b.x));
+      f0 = f_add(f0, f_mul(x.y, a.y)); f1 = f_add(f1, f_mul(x.y, b.y));
+      f0 = f_add(f0, f_mul(x.z, a.z)); f1 = f_add(f1, f_mul(x.z, b.z));
+      f0 = f_add(f0, f_mul(x.w, a.w)); f1 = f_add(f1, f_mul(x.w, b.w));
     }
-    w0 += (size_t)L_NOUT * L_CELLS; w1 += (size_t)L_NOUT * L_CELLS;
-#pragma unroll 10
-    for (int j = 0; j < L_CELLS; ++j) {
-      const float x = s.l_hidden[j];
-      f0 = f_add(f0, f_mul(x, w0[(size_t)j * L_CELLS]));
-      f1 = f_add(f1, f_mul(x, w1[(size_t)j * L_CELLS]));
+    w0 += (L_NOUT / 4) * L_CELLS; w1 += (L_NOUT / 4) * L_CELLS;
+    x4 = (const float4*)s.l_hidden;
+#pragma unroll 2
+    for (int q = 0; q < L_CELLS / 4; ++q) {          // hidden 0..47
+      const float4 x = x4[q], a = w0[q * L_CELLS], b = w1[q * L_CELLS];
+      f0 = f_add(f0, f_mul(x.x, a.x)); f1 = f_add(f1, f_mul(x.x, b.x));
+      f0 = f_add(f0, f_mul(x.y, a.y)); f1 = f_add(f1, f_mul(x.y, b.y));
+      f0 = f_add(f0, f_mul(x.z, a.z)); f1 = f_add(f1, f_mul(x.z, b.z));
+      f0 = f_add(f0, f_mul(x.w, a.w)); f1 = f_add(f1, f_mul(x.w, b.w));
     }
-    f0 = f_add(f0, f_mul(1.0f, w0[(size_t)L_CELLS * L_CELLS]));
-    f1 = f_add(f1, f_mul(1.0f, w1[(size_t)L_CELLS * L_CELLS]));
+    {                                                // hidden 48, 49 and the bias input (1.0); the fourth column is padding
+      const float4 a = w0[(L_CELLS / 4) * L_CELLS], b = w1[(L_CELLS / 4) * L_CELLS];
+      const float h48 = s.l_hidden[L_CELLS - 2], h49 = s.l_hidden[L_CELLS - 1];
+      f0 = f_add(f0, f_mul(h48, a.x)); f1 = f_add(f1, f_mul(h48, b.x));
+      f0 = f_add(f0, f_mul(h49, a.y)); f1 = f_add(f1, f_mul(h49, b.y));
+      f0 = f_add(f0, f_mul(1.0f, a.z)); f1 = f_add(f1, f_mul(1.0f, b.z));
+    }
     s.l_gate[g0][i0] = f0;
     s.l_gate[g1][i1] = f1;
   }
@@ -627,7 +639,7 @@ GMX_DEV void LstmBptt(StreamSmem& s, const Arena& A, const StreamParams& P, int 
   for (int q = tid; q < 3 * L_CELLS * L_CELLS; q += NT) {
     const int g = q / (L_CELLS * L_CELLS), rem = q - g * (L_CELLS * L_CELLS);
     const int j = rem / L_CELLS, i = rem - j * L_CELLS;
-    Wt[q] = W[((size_t)g * L_ROW + 512 + i) * L_CELLS + j];
+    Wt[q] = W[LstmW(g, 512 + i, j)];
   }
   BlockSync();
   for (int ep = L_HORIZON - 1; ep >= 0; --ep) {
@@ -732,16 +744,16 @@ GMX_DEV void LstmBptt(StreamSmem& s, const Arena& A, const StreamParams& P, int 
   float* M = A.at<float>(L.l_m);
   float* V = A.at<float>(L.l_v);
   const float* lin = A.at<float>(L.l_lin);
-  auto adam = [&](size_t f, float grad) {
-    float m = f_mul(M[f], beta1);
-    m = f_add(m, f_mul(omb1, grad));
-    float v = f_mul(V[f], beta2);
-    v = f_add(v, f_mul(f_mul(omb2, grad), grad));
-    M[f] = m; V[f] = v;
-    Wm[f] = f_sub(Wm[f], f_mul(alpha, f_div(f_div(m, d1), f_sqrt(f_add(f_div(v, d2), eps)))));
+  // one Adam step of one weight (lstm-layer.cpp:12-34)
+  auto adam1 = [&](float& w, float& m, float& v, float grad) {
+    m = f_add(f_mul(m, beta1), f_mul(omb1, grad));
+    v = f_add(f_mul(v, beta2), f_mul(f_mul(omb2, grad), grad));
+    w = f_sub(w, f_mul(alpha, f_div(f_div(m, d1), f_sqrt(f_add(f_div(v, d2), eps)))));
   };
+  float4* W4 = (float4*)Wm; float4* M4 = (float4*)M; float4* V4 = (float4*)V;
   // (a) one-hot rows: row r only receives err of the epochs whose input symbol was r. Per-symbol epoch
-  // lists (descending) are threaded through the scratch buffer.
+  // lists (descending) are threaded through the scratch buffer. One thread updates the four rows of a quad
+  // for one cell = one float4 of W, m and v.
   uint8_t* head = (uint8_t*)s.l_err256;          // [256] first (largest) epoch of a symbol, 0xFF = none
   uint8_t* nxt = head + 256;                     // [100] next smaller epoch with the same symbol
   for (int i = tid; i < 256; i += NT) head[i] = 0xFF;
@@ -750,17 +762,27 @@ GMX_DEV void LstmBptt(StreamSmem& s, const Arena& A, const StreamParams& P, int 
 #pragma unroll 1
     for (int ep = 0; ep < L_HORIZON; ++ep) { const int sy = s.l_symin[ep]; nxt[ep] = head[sy]; head[sy] = (uint8_t)ep; }
   BlockSync();
-  for (int q = tid; q < 3 * L_NOUT * L_CELLS; q += NT) {
-    const int g = q / (L_NOUT * L_CELLS), rem = q - g * (L_NOUT * L_CELLS);
-    const int r = rem / L_CELLS, i = rem - r * L_CELLS;
+#pragma unroll 1
+  for (int q = tid; q < 3 * (L_NOUT / 4) * L_CELLS; q += NT) {
+    const int g = q / ((L_NOUT / 4) * L_CELLS), rem = q - g * ((L_NOUT / 4) * L_CELLS);
+    const int rq = rem / L_CELLS, i = rem - rq * L_CELLS;
     const float* eh = errh + (size_t)g * L_HORIZON * L_CELLS + i;
-    float grad = 0.0f;
-    for (int ep = head[r]; ep != 0xFF; ep = nxt[ep]) grad = f_add(grad, eh[ep * L_CELLS]);
-    adam(((size_t)g * L_ROW + r) * L_CELLS + i, grad);
+    float grad[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float gsum = 0.0f;
+      for (int ep = head[4 * rq + k]; ep != 0xFF; ep = nxt[ep]) gsum = f_add(gsum, eh[ep * L_CELLS]);
+      grad[k] = gsum;
+    }
+    const size_t f4 = ((size_t)g * L_ROWQ + rq) * L_CELLS + i;
+    float4 w = W4[f4], m = M4[f4], v = V4[f4];
+    adam1(w.x, m.x, v.x, grad[0]); adam1(w.y, m.y, v.y, grad[1]); adam1(w.z, m.z, v.z, grad[2]); adam1(w.w, m.w, v.w, grad[3]);
+    W4[f4] = w; M4[f4] = m; V4[f4] = v;
   }
-  // (b) dense rows: grad[r][i] = sum_ep err[ep][i] * in[ep][r] as a register-tiled product, 4 rows x 2
-  // cells per thread (one 16-byte and one 8-byte load feed 8 multiply-adds).
+  // (b) dense rows: grad[r][i] = sum_ep err[ep][i] * in[ep][r] as a register-tiled product, 4 rows (one quad) x 2
+  // cells per thread (one 16-byte and one 8-byte load feed 8 multiply-adds), then two float4 Adam updates.
   constexpr int RG = (L_NIN + 3) / 4, IP = L_CELLS / 2;
+#pragma unroll 1
   for (int id = tid; id < 3 * RG * IP; id += NT) {
     const int ip = id % IP, rg = (id / IP) % RG, g = id / (IP * RG);
     const float2* e2 = (const float2*)(errh + (size_t)g * L_HORIZON * L_CELLS + 2 * ip);
@@ -775,14 +797,14 @@ GMX_DEV void LstmBptt(StreamSmem& s, const Arena& A, const StreamParams& P, int 
       a[2][0] = f_add(a[2][0], f_mul(e.x, x.z)); a[2][1] = f_add(a[2][1], f_mul(e.y, x.z));
       a[3][0] = f_add(a[3][0], f_mul(e.x, x.w)); a[3][1] = f_add(a[3][1], f_mul(e.y, x.w));
     }
+    const bool pad = 4 * rg + 3 >= L_NIN;   // the last quad's fourth column does not exist (stays 0)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int rr = 4 * rg + k;
-      if (rr < L_NIN) {
-        const size_t f = ((size_t)g * L_ROW + L_NOUT + rr) * L_CELLS + 2 * ip;
-        adam(f, a[k][0]);
-        adam(f + 1, a[k][1]);
-      }
+    for (int c = 0; c < 2; ++c) {
+      const size_t f4 = ((size_t)g * L_ROWQ + L_NOUT / 4 + rg) * L_CELLS + 2 * ip + c;
+      float4 w = W4[f4], m = M4[f4], v = V4[f4];
+      adam1(w.x, m.x, v.x, a[0][c]); adam1(w.y, m.y, v.y, a[1][c]); adam1(w.z, m.z, v.z, a[2][c]);
+      if (!pad) adam1(w.w, m.w, v.w, a[3][c]);
+      W4[f4] = w; M4[f4] = m; V4[f4] = v;
     }
   }
   for (int t = tid; t < 2 * 3 * L_CELLS; t += NT) {  // gamma then beta (lstm-layer.cpp:349-352)
@@ -1196,6 +1218,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     __syncwarp();   // converged warp: the shuffles below take their fast path
     {
       // serial chain of the layer: neuron j's finished output feeds every later neuron (mixer.cpp:60-70).
+#if defined(GMX_CHAIN_UNROLLED)
       // The 23 chain weights sit in registers so that one step is shuffle -> mul -> add.
       float cw[NL0 - 1];
 #pragma unroll
@@ -1205,6 +1228,18 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
         const float oj = __shfl_sync(0xffffffffu, acc, j);
         if (lane > j && lane < NL0) acc = f_add(acc, f_mul(oj, cw[j]));
       }
+#else
+      // Rolled (a handful of instructions that stay in the instruction cache); the chain weight of the next step is
+      // loaded from shared memory while the current step's shuffle is in flight.
+      float c = w[NPRED];
+#pragma unroll 1
+      for (int j = 0; j < NL0 - 1; ++j) {
+        const float cn = w[NPRED + j + 1];   // j = 22 reads the pad word behind the set: never used
+        const float oj = __shfl_sync(0xffffffffu, acc, j);
+        if (lane > j && lane < NL0) acc = f_add(acc, f_mul(oj, c));
+        c = cn;
+      }
+#endif
     }
     if (lane < NL0) { s.l0_out[lane] = acc; s.xe[NPRED + lane] = acc; }
     __syncwarp();

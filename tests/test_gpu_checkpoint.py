@@ -87,4 +87,6 @@ def test_predictor_facade_reads_and_writes_checkpoints(gpu_ctx, ckpt):
     p.close()
     sh_ref, lo_ref = gpu_ctx.train_checkpoint(TEXT[:640])
     assert lo == lo_ref
-    assert set(ckpt_layout.differing_sections(sh, sh_ref)) <= ckpt_layout.SCRATCH
+    # the facade ran with analysis on (inactive predictions are zeroed each Predict, predictor.cpp:362-365), the
+    # training pass with analysis off (they keep their last value): ShortTermMemory::predictions legitimately differs
+    assert set(ckpt_layout.differing_sections(sh, sh_ref)) <= ckpt_layout.SCRATCH | {"stm.predictions"}
