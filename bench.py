@@ -33,6 +33,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALGO_BYTES_PER_INPUT_BYTE = 4.29e5   # SURVEY.md section 8(d); derivation in DESIGN.md
+
+
+def ncu_traffic_per_input_byte():
+    """dram__bytes_read.sum + dram__bytes_write.sum per input byte from the committed `ncu` capture of the stream kernel
+    (profiles/traffic.json, written from the raw page of the capture named there), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    t = json.load(open(p))
+    return (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["input_bytes"], t["capture"]
 METRIC = "aggregate compress MB/s"
 UNIT = "MB/s"
 
@@ -49,6 +59,13 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-decompress", action="store_true", help="skip the configs[2] leg (GPU decompress of the last step's streams)")
     ap.add_argument("--verify", type=int, default=1, help="streams per rank checked by a GPU decompress round trip after timing")
+    ap.add_argument("--no-generate", action="store_true", help="skip the configs[3] leg (batched generation from a checkpoint)")
+    ap.add_argument("--gen-train-bytes", type=int, default=65536, help="bytes of the enwik-shaped corpus the generation checkpoint is trained on")
+    ap.add_argument("--gen-prompts", type=int, default=0, help="prompts per GPU for the generation leg (0 = one wave of resident streams)")
+    ap.add_argument("--gen-bytes", type=int, default=1024)
+    ap.add_argument("--workload", default="chunks", choices=["chunks", "enwik"],
+                    help="chunks = configs[1] (default, the metric's configuration); enwik = configs[4]: --chunks streams of --chunk-bytes "
+                         "bytes cut from the enwik-shaped corpus (100 x 1000000 in BASELINE.json)")
     return ap.parse_args()
 
 
@@ -115,9 +132,20 @@ def chunk_ids(rank, step, per_step, total_set=4096):
 _CHUNK_CACHE = {}
 
 
+_WORKLOAD = "chunks"
+_CORPUS = {}
+
+
 def _gen_chunk(args):
     from gmix_b200 import synth
-    return synth.synthetic_text_chunk(*args)
+    i, size = args
+    if _WORKLOAD == "enwik":       # stream i = bytes [i*size, (i+1)*size) of the enwik-shaped corpus
+        need = (i + 1) * size
+        have = _CORPUS.get("data", b"")
+        if len(have) < need:
+            _CORPUS["data"] = have = synth.enwik_shaped_corpus(max(need, _CORPUS.get("want", 0)))
+        return have[i * size:(i + 1) * size]
+    return synth.synthetic_text_chunk(i, size)
 
 
 def pregenerate(ids, size, procs):
@@ -232,10 +260,16 @@ def run_reference(args):
 
 # ---------------------------------------------------------------------------------------------------
 def run_ours(args):
+    global _WORKLOAD
     world0 = int(os.environ.get("WORLD_SIZE", "1"))
     rank0 = int(os.environ.get("RANK", "0"))
-    all_ids = [i for st in range(args.warmup + args.steps) for i in chunk_ids(rank0, st, args.chunks)]
-    pregenerate(all_ids, args.chunk_bytes, max(1, min(32, (os.cpu_count() or 1) // world0)))
+    _WORKLOAD = args.workload
+    all_ids = [i for st in range(args.warmup + args.steps) for i in chunk_ids(rank0, st, args.chunks, 4096 if args.workload == "chunks" else args.chunks)]
+    if args.workload == "enwik":   # one sequential generator: build the corpus once, then slice
+        _CORPUS["want"] = (max(all_ids) + 1) * args.chunk_bytes
+        pregenerate(all_ids, args.chunk_bytes, 1)
+    else:
+        pregenerate(all_ids, args.chunk_bytes, max(1, min(32, (os.cpu_count() or 1) // world0)))
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -267,8 +301,10 @@ def run_ours(args):
     gathered = [torch.zeros(2 * n, dtype=torch.int64, device=dev) for _ in range(world)] if world > 1 else None
     l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    total_set = 4096 if args.workload == "chunks" else n      # enwik: rank r owns streams [r*n, (r+1)*n) of one corpus, every step
+
     def step_inputs(step):
-        data = b"".join(make_chunks(chunk_ids(rank, step, n), size))
+        data = b"".join(make_chunks(chunk_ids(rank, step, n, total_set), size))
         return torch.frombuffer(bytearray(data), dtype=torch.uint8)
 
     def barrier():
@@ -326,7 +362,7 @@ def run_ours(args):
         ctx.set_cuda_stream(0)
         back = ctx.decompress_batch(comp)
         ctx.set_cuda_stream(stream.cuda_stream)
-        want = make_chunks(chunk_ids(rank, total_steps - 1, n)[:k], size)
+        want = make_chunks(chunk_ids(rank, total_steps - 1, n, total_set)[:k], size)
         assert back == want, "GPU decompress of a GPU-compressed stream does not reproduce the input"
 
     # ---- configs[2]: GPU decompress of every stream of the last step, device resident, checked ---------
@@ -358,6 +394,41 @@ def run_ours(args):
             raise SystemExit(f"bench.py: GPU decompress of the GPU-compressed streams is not lossless on rank {rank}")
         decomp = {"value": world * n * size / (float(dms.item()) / 1e3) / 1e6, "unit": UNIT, "lossless_streams": n * world,
                   "workload": "configs[2]: decompression of the same chunk set, every stream compared with its input"}
+
+    # ---- configs[3]: batched generation from a checkpoint, learning disabled while sampling ------------------
+    generate = None
+    if not args.no_generate and args.workload == "chunks":
+        from gmix_b200 import synth
+        ctx.set_cuda_stream(0)
+        npr = args.gen_prompts or ctx.resident_streams
+        T, G = args.gen_train_bytes, args.gen_bytes
+        corpus = synth.enwik_shaped_corpus(T + 4096 * npr + 64)
+        t0 = time.perf_counter()
+        ck_short, ck_long = ctx.train_checkpoint(corpus[:T])            # Predict/Perceive/Learn + Predictor::WriteCheckpoint on the GPU
+        train_s = time.perf_counter() - t0
+        model = gmix_b200.Model(ctx, ck_short, ck_long, max_new_bytes=64 + G)
+        prompts = [corpus[T + 4096 * k:T + 4096 * k + 64] for k in range(npr)]
+        prompts[1] = prompts[0]                                          # same prompt, same draws -> must give the same bytes
+        ctx.generate_batch(model, prompts[:8], 16)                       # warm-up (allocates the model-sized arenas)
+        barrier()
+        t0 = time.perf_counter()
+        out = ctx.generate_batch(model, prompts, G, 1.0)
+        barrier()
+        gen_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        gen_kernel_ms = ctx.last_kernel_ms
+        if world > 1:
+            dist.all_reduce(gen_s, op=dist.ReduceOp.MAX)
+        if out[0] != out[1] or len(set(out)) < max(2, npr // 2) or any(len(o) != G for o in out):
+            raise SystemExit("bench.py: generation is not deterministic per prompt / not prompt dependent")
+        generate = {"value": world * npr * G / float(gen_s.item()), "unit": "generated bytes/s", "prompts": npr * world, "prompt_bytes": 64,
+                    "bytes_per_prompt": G, "temperature": 1.0, "kernel_ms": gen_kernel_ms,
+                    "checkpoint": f"written on the GPU after {T} B of the enwik-shaped corpus ({train_s:.1f} s), reference format "
+                                  f"(.short {len(ck_short)} B, .long {len(ck_long)} B), loaded back through gmx_model_load",
+                    "arena_mib_per_stream": model.arena_bytes >> 20,
+                    "workload": "configs[3] at reduced scale: one wave of prompts, checkpoint trained on 64 KiB instead of 1 MB; host buffers, "
+                                "H2D of prompts + draws and D2H of samples inside the timed region"}
+        model.close()
+        ctx.set_cuda_stream(stream.cuda_stream)
 
     # ---- end-to-end measurement through the host-pointer C ABI ---------------------------------------
     e2e = None
@@ -391,21 +462,25 @@ def run_ours(args):
     if rank == 0:
         pk, pk_kind = peaks()
         achieved = n * size * ALGO_BYTES_PER_INPUT_BYTE / (kernel_ms_avg / 1e3) / 1e9
+        tpb, tsrc = ncu_traffic_per_input_byte()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32+u8 (bit-exact integer/fp32 model state)", "data": "synthetic",
-            "config": {"workload": "configs[1]: independent 64 KiB synthetic-text chunks compressed from scratch, one CTA per stream",
+            "config": {"workload": "configs[1]: independent 64 KiB synthetic-text chunks compressed from scratch, one CTA per stream" if args.workload == "chunks"
+                       else "configs[4]: enwik-shaped corpus cut into independent streams, sharded over the GPUs, NCCL gather of sizes+checksums",
                        "chunk_bytes": size, "chunks_per_step": n, "chunks_per_step_all_gpus": n * world,
                        "resident_streams_per_gpu": ctx.resident_streams, "arena_mib_per_stream": ctx.arena_bytes >> 20,
                        "l2": "256 MiB flush write between timed steps; per-stream arenas exceed L2",
                        "parallelism": f"streams sharded over {world} GPU(s), all_gather of sizes+checksums per step"},
             "bits_per_byte": 8.0 * comp_bytes / (n * size),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_kind": pk_kind,
+                         "frac": achieved / pk["hbm_gbs"], "traffic": tpb * n * size if tpb else None,
+                         "traffic_source": f"{tpb:.0f} B of DRAM traffic per input byte in {tsrc}, scaled to this launch's input bytes" if tpb else None,
+                         "peak_kind": pk_kind,
                          "kernel": "gmx::StreamKernel<128, MODE_COMPRESS, 8, false>", "kernel_ms": kernel_ms_avg,
                          "algorithmic_bytes_per_input_byte": ALGO_BYTES_PER_INPUT_BYTE},
-            "e2e": e2e, "decompress": decomp, "retried_streams": ctx.retried_streams, "gpu_launches": gpu_launches, "clocks": clocks,
+            "e2e": e2e, "decompress": decomp, "generate": generate, "retried_streams": ctx.retried_streams, "gpu_launches": gpu_launches, "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(min(size, 8192))

@@ -628,7 +628,17 @@ struct Ppmd {
   }
 
   // ConvertSQ :1192-1209 for one symbol: cum * freq / total (+1 for a symbol, the new cum for an escape)
-  GMX_DEV static uint32_t Scale(uint32_t cum, uint32_t freq, uint32_t total) { return (uint32_t)(((uint64_t)cum * freq) / total); }
+  // freq, total < 2^16 and freq <= total, so the 48-bit product divides in two 32-bit steps (schoolbook, base 2^16)
+  // instead of the software 64-bit division: hi < total always, every partial dividend stays below 2^32.
+  GMX_DEV static uint32_t Scale(uint32_t cum, uint32_t freq, uint32_t total) {
+    const uint64_t prod = (uint64_t)cum * freq;
+    const uint32_t hi = (uint32_t)(prod >> 32), lo = (uint32_t)prod;
+    if (total > 0xffffu || hi >= total) return (uint32_t)(prod / total);   // never taken (16-bit statistics); keeps the function total
+    uint32_t r = (hi << 16) | (lo >> 16);
+    const uint32_t q1 = r / total;
+    r = ((r - q1 * total) << 16) | (lo & 0xffffu);
+    return (q1 << 16) + r / total;
+  }
 
   // ppmd_PrepareByte :1322-1349 with the *_T walkers :1222-1297: full next-byte distribution.
   // (OrderFall is incremented and restored by the reference and read by nothing in between.)

@@ -152,8 +152,6 @@ struct StreamSmem {
   uint32_t ctx[C_COUNT + 2];
   alignas(16) float l0_out[NL0]; float l1_out[NL1], final_out, prob;   // l0_out | l1_out contiguous (final mixer input)
   alignas(16) float ppm[256], lprob[256];   // byte distributions of PPMd and LSTM
-  float node_ppm[256], node_lstm[256]; // Logit(p) of every node of the binary interval search
-  uint8_t nflag_ppm[256], nflag_lstm[256];  // bit0: denom != 0, bit1: p != 0.5
   uint8_t ring[32];            // last bytes (the reference keeps 1000, short-term-memory.h:23; only 10 are ever read)
   uint32_t ring_pos;
   int32_t new_bit, recent_bits, bb, first_prediction, analysis;
@@ -171,6 +169,7 @@ struct StreamSmem {
   uint32_t ind_base[NIND], ind_slot[NIND];   // ind_slot: dense slot, or position in the sparse map
   uint16_t ind_state[NIND + 1];
   uint8_t ind_found[NIND + 3];               // sparse tables: entry exists at ind_slot
+  float ind_pa[NIND], ind_pb[NIND];          // the two logit-map entries Learn will update, as read by Predict
   uint32_t sparse_used;
   uint32_t t_start_us;
   // match
@@ -788,7 +787,7 @@ GMX_DEV void LstmBptt(StreamSmem& s, const Arena& A, const StreamParams& P, int 
     const float2* e2 = (const float2*)(errh + (size_t)g * L_HORIZON * L_CELLS + 2 * ip);
     const float4* x4 = (const float4*)(lin + 4 * rg);
     float a[4][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}, {0.0f, 0.0f}, {0.0f, 0.0f}};
-#pragma unroll 2
+#pragma unroll 4
     for (int ep = L_HORIZON - 1; ep >= 0; --ep) {
       const float2 e = e2[ep * (L_CELLS / 2)];
       const float4 x = x4[ep * ((L_NIN + 1) / 4)];
@@ -843,28 +842,30 @@ GMX_DEV void LstmPerceive(StreamSmem& s, const Arena& A, const StreamParams& P, 
   GMX_PROF(10);
 }
 
-// Binary interval search node tables (ModPPMD::Predict mod_ppmd.cpp:1662-1681, LstmModel::Predict
-// lstm-model.cpp:36-47): node = recent_bits (1..255) covers [bot, top]; num = sum(mid+1..top) from
-// 0.0f ascending, denom continues from num over bot..mid. All 255 nodes are evaluated at the byte
-// boundary so the per-bit step is a lookup.
-static GMX_DEV GMX_NOINLINE void IntervalNode(const float* probs, int node, float* val, uint8_t* flag) {
-  int level = 31 - __clz(node);
+// One node of the binary interval search of a byte model (ModPPMD::Predict mod_ppmd.cpp:1662-1681, LstmModel::Predict
+// lstm-model.cpp:36-47): node = recent_bits (1..255) covers [bot, top]; num = sum(mid+1..top) from 0.0f ascending,
+// denom continues from num over bot..mid. Evaluated per bit by one lane per model while the Indirect lanes wait for
+// their table loads (256 sequential adds at the first bit of a byte, 2 at the last). Returns Logit(p); flag bit 0:
+// denom != 0, bit 1: p != 0.5.
+GMX_DEV inline float IntervalNode(const float* probs, int node, uint32_t* flag) {
+  const int level = 31 - __clz(node);
   const int width = 256 >> level;
   const int bot = (node - (1 << level)) * width;
   const int top = bot + width - 1;
   const int mid = bot + ((top - bot) / 2);
   float num = 0.0f;
+#pragma unroll 4
   for (int i = mid + 1; i <= top; ++i) num = f_add(num, probs[i]);
   float denom = num;
+#pragma unroll 4
   for (int i = bot; i <= mid; ++i) denom = f_add(denom, probs[i]);
   if (denom != 0.0f) {
     const float p = f_div(num, denom);
-    *val = Logit(p);
-    *flag = (uint8_t)(1 | (p == 0.5f ? 0 : 2));
-  } else {
-    *val = 0.0f;
-    *flag = 0;
+    *flag = 1u | (p == 0.5f ? 0u : 2u);
+    return Logit(p);
   }
+  *flag = 0u;
+  return 0.0f;
 }
 
 // L2 prefetch of the pool record a mixer's gate will select. which = 0: with the contexts as they are now
@@ -991,12 +992,6 @@ GMX_DEV void ByteBoundary(StreamSmem& s, const Arena& A, const StreamParams& P, 
     }
     if ((tid & 31) == 0) { s.l_red[4 + (tid >> 5)] = bv; s.l_err256[tid >> 5] = (float)bi; }
   }
-  // (4) interval-search node tables for both byte models
-  for (int n = tid + 1; n < 256; n += NT) {
-    IntervalNode(s.ppm, n, &s.node_ppm[n], &s.nflag_ppm[n]);
-    const int n2 = 256 - n;
-    IntervalNode(s.lprob, n2, &s.node_lstm[n2], &s.nflag_lstm[n2]);
-  }
   BlockSync();
   if (tid == 0) {
     float bv = 0.0f; int bi = 0;
@@ -1071,9 +1066,13 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     const uint32_t ns = e & 0xff, rm = e >> 8;
     const float* pr = A.at<float>(L.ind_pred) + k * 512;
     const int pi = s.T.ind[k].pred;
-    if (ns != 255) { const float p = pr[ns]; s.preds[pi] = p; s.act[pi] = p != 0.0f; }
+    // both entries are read unconditionally: Indirect::Learn updates exactly these two (a never-seen state learns as
+    // state 0, indirect.cpp:52-54) and takes them from shared memory instead of two more dependent global loads
+    const float pa = pr[ns == 255 ? 0 : ns], pb = pr[256 + rm];
+    s.ind_pa[k] = pa; s.ind_pb[k] = pb;
+    if (ns != 255) { s.preds[pi] = pa; s.act[pi] = pa != 0.0f; }
     else { s.act[pi] = 0; if (zero_inactive) s.preds[pi] = 0.0f; }
-    if (rm != 0) { const float p = pr[256 + rm]; s.preds[pi + 1] = p; s.act[pi + 1] = p != 0.0f; }
+    if (rm != 0) { s.preds[pi + 1] = pb; s.act[pi + 1] = pb != 0.0f; }
     else { s.act[pi + 1] = 0; if (zero_inactive) s.preds[pi + 1] = 0.0f; }
   } else if (tid >= 64 && tid < 64 + NMATCH) {  // Match::Predict match.cpp:25-74
     const int k = tid - 64;
@@ -1115,9 +1114,9 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     PrefetchRange(A.at<float>(L.l_wout) + (size_t)last * L_HID * L_NOUT, L_HID * L_NOUT * 4, tid - 98, NT - 98);
   } else if (tid == 96 || tid == 97) {  // per-bit part of ModPPMD / LstmModel::Predict
     const int which = tid - 96;
-    const int node = s.recent_bits;
-    const uint8_t fl = which ? s.nflag_lstm[node] : s.nflag_ppm[node];
-    if (fl & 1) { s.preds[which] = which ? s.node_lstm[node] : s.node_ppm[node]; s.act[which] = (fl >> 1) & 1; }
+    uint32_t fl;
+    const float val = IntervalNode(which ? s.lprob : s.ppm, s.recent_bits, &fl);
+    if (fl & 1) { s.preds[which] = val; s.act[which] = (fl >> 1) & 1; }
     else { s.act[which] = 0; if (zero_inactive) s.preds[which] = 0.0f; }
   }
   BlockSync();
@@ -1334,9 +1333,9 @@ GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int 
     uint32_t ns = e & 0xff;
     const uint32_t rm = e >> 8;
     if (ns == 255) ns = 0;
-    const float a = pr[ns];
+    const float a = s.ind_pa[k];
     pr[ns] = f_add(a, f_mul(f_sub(fbit, Logistic(a)), lr));
-    const float b = pr[256 + rm];
+    const float b = s.ind_pb[k];
     pr[256 + rm] = f_add(b, f_mul(f_sub(fbit, Logistic(b)), lr));
     // RunMap::Next run-map.cpp:3-21
     uint32_t nrm;
