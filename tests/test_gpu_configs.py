@@ -52,3 +52,29 @@ def test_incompressible_streams_take_the_roomy_retry_path(gpu_ctx, oracle):
     for s, c in zip(streams, comp):
         assert c == oracle.compress(s)
     assert gpu_ctx.decompress_batch(comp) == streams
+
+
+def test_config5_enwik_shaped_streams_sharded_with_checksums(gpu_ctx, oracle):
+    """configs[4] at reduced size: the enwik-shaped corpus cut into equal streams, sharded by byte-balanced index
+    ranges (gmix_b200/shard.py, as across GPUs), each shard compressed as one batch; per-stream {size, FNV-1a} match
+    the host function, a seeded sample matches the CPU oracle, every stream decodes losslessly."""
+    import torch
+    from gmix_b200 import shard, synth
+    n, size, world = 12, 20000, 4
+    corpus = synth.enwik_shaped_corpus(n * size)
+    streams = [corpus[i * size:(i + 1) * size] for i in range(n)]
+    ranges = shard.shard_ranges([len(s) for s in streams], world)
+    assert ranges[0][0] == 0 and ranges[-1][1] == n and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+    comp = []
+    for lo, hi in ranges:                                  # one "rank" after the other on the one GPU of the test box
+        comp += gpu_ctx.compress_batch(streams[lo:hi])
+    assert comp[5] == oracle.compress(streams[5])
+    dev = torch.device("cuda", 0)
+    flat = torch.frombuffer(bytearray(b"".join(comp)), dtype=torch.uint8).to(dev)
+    lens = torch.tensor([len(c) for c in comp], dtype=torch.int64, device=dev)
+    offs = torch.cumsum(lens, 0) - lens
+    sums = torch.zeros(n, dtype=torch.int64, device=dev)
+    gpu_ctx.checksum_device(flat.data_ptr(), offs.data_ptr(), lens.data_ptr(), n, sums.data_ptr())
+    torch.cuda.synchronize()
+    assert [x & 0xFFFFFFFFFFFFFFFF for x in sums.cpu().tolist()] == [shard.fnv1a64(c) for c in comp]
+    assert gpu_ctx.decompress_batch(comp) == streams
