@@ -624,8 +624,25 @@ int gmx_train_checkpoint(gmx_ctx* c, const gmx_model* from, const uint8_t* data,
   const uint32_t keep_resident = c->cfg_max_resident;
   rc = RunHost(c, gmx::MODE_COMPRESS, n ? data : &dummy, io, 1, out.data(), oo, &out_len, &status, nullptr, nullptr, o);
   (void)keep_resident;
-  if (rc) return rc;
+  bool roomy = false;
+  if (rc == GMX_E_STREAM && Retryable(status) && !from) {
+    // the text-sized arena overflowed (the parked state must come from the arena the stream ran in, so the batch
+    // calls' retry in a second arena class does not apply): run again in one worst-case-sized arena
+    FreeArenas(c);
+    c->layout = gmx::MakeLayout(n, true);
+    if (cudaMalloc(&c->d_arenas, c->layout.total) != cudaSuccess)
+      return Fail(c, GMX_E_NOMEM, "cannot allocate a worst-case arena of %llu MiB: %s", (unsigned long long)(c->layout.total >> 20),
+                  cudaGetErrorString(cudaGetLastError()));
+    GMX_CUDA(c, cudaMemcpy(c->d_layout, &c->layout, sizeof(c->layout), cudaMemcpyHostToDevice));
+    c->n_arenas = 1;
+    c->cfg_max_len = n;
+    roomy = true;
+    c->retried_streams += 1;
+    rc = RunHost(c, gmx::MODE_COMPRESS, n ? data : &dummy, io, 1, out.data(), oo, &out_len, &status, nullptr, nullptr, o);
+  }
+  if (rc) { if (roomy) FreeArenas(c); return rc; }
   rc = SerializeParked(c, c->layout, c->d_arenas, (const uint32_t*)c->b_final.p);   // one stream: it ran in arena 0
+  if (roomy) FreeArenas(c);   // the next batch call sizes its arenas afresh
   if (rc) return rc;
   *short_blob = c->ck_short.data(); *short_len = c->ck_short.size();
   *long_blob = c->ck_long.data(); *long_len = c->ck_long.size();
