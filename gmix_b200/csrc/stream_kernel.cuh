@@ -38,6 +38,7 @@ enum : uint32_t {
 // loads) and = 4 mod 32 banks, which makes lane-per-neuron float4 reads conflict free.
 enum : int { WSTRIDE0 = 132, WSTRIDE1 = 36, WTOTAL = 24 * WSTRIDE0 + 9 * WSTRIDE1 };
 enum : int { GMX_PROF_SLOTS = 24 };
+enum : int { NBITMIX = 4, CAND_Q = 68 };   // bit-gated mixers; float4s per staged candidate: (1 header + ceil(weights / 4)) summed over the four
 // Phase slots: 0 byte contexts+PPMd, 1 ppm normalise, 2 LSTM forward, 3 interval nodes, 4 indirect/match
 // lookups, 5 mixer set swap, 6 mixer predict, 7 coder, 8 learn scalars+indirect, 9 mixer weight update,
 // 10 LSTM output-layer step, 11 BPTT epochs, 12 BPTT weight grads+Adam, 13 stream init, 14 bit bookkeeping,
@@ -163,6 +164,9 @@ struct StreamSmem {
   uint32_t set_steps[NMIX], max_steps[NMIX], set_idx[NMIX], set_pool[NMIX];
   uint32_t swap_old[NMIX], swap_new[NMIX], nswap;   // queued set swaps of this bit
   uint8_t swap_m[NMIX + 3], shrink[NMIX + 3];
+  uint8_t swap_staged[NMIX + 3];             // queued swap takes its new set from cand_w (1 + candidate) instead of the pool
+  uint32_t cand_id[NBITMIX][2], cand_valid;  // pool ids of the staged candidates (0 = no set yet); valid for the next bit only
+  alignas(16) float cand_w[2 * CAND_Q * 4];  // [candidate bit][record images {steps,0,0,0 | weights} of the four mixers]
   float upd[NMIX];
   uint32_t pool_next;
   // indirect
@@ -266,6 +270,13 @@ GMX_DEV inline uint32_t RecentByte(const StreamSmem& s, int ago) {  // short-ter
 GMX_DEV inline int WOff(int m) { return m < NL0 ? m * WSTRIDE0 : NL0 * WSTRIDE0 + (m - NL0) * WSTRIDE1; }
 GMX_DEV inline int MixerNW(int m) { return m < NL0 ? NPRED + m : m < NL0 + NL1 ? NL0 + (m - NL0) + 1 : NL0 + NL1 + 1; }
 
+// The four mixers whose gate context contains bit_context select another weight set every bit. Both sets the next
+// bit can select are copied into shared memory one bit ahead (cand_w), so the swap on the per-bit critical path is a
+// shared-memory copy instead of two dependent global loads (directory entry, then record).
+GMX_DEV inline int BitMixer(int slot) { return slot == 0 ? 2 : slot == 1 ? 11 : slot == 2 ? NL0 + 2 : NL0 + 5; }   // gates: SLPR, LBPR, BIT_CONTEXT x2
+GMX_DEV inline int BitSlot(int m) { return m == 2 ? 0 : m == 11 ? 1 : m == NL0 + 2 ? 2 : m == NL0 + 5 ? 3 : -1; }
+GMX_DEV inline int CandOff(int slot) { return slot == 0 ? 0 : slot == 1 ? 24 : slot == 2 ? 51 : 59; }            // 24 + 27 + 8 + 9 = 68
+
 GMX_DEV inline void BlockSync() { __syncthreads(); }
 // 4-byte asynchronous global -> shared copy (LDGSTS): no register round trip, so many can be in flight.
 GMX_DEV inline void CpAsync4(void* smem_dst, const void* gmem_src) {
@@ -368,7 +379,7 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
     for (int i = kFirst + tid; i < kWords; i += NT) sw[i] = P.tmpl_state[i];
     BlockSync();
     if (tid == 0) {
-      s.error = 0; s.nswap = 0; s.x1 = 0; s.x2 = 0xffffffffu; s.x = 0;
+      s.error = 0; s.nswap = 0; s.cand_valid = 0; s.x1 = 0; s.x2 = 0xffffffffu; s.x = 0;
       for (int i = 0; i < GMX_PROF_SLOTS; ++i) s.prof[i] = 0;
       s.prof_t = GMX_CLOCK(); s.t_start_us = (uint32_t)(GlobalTimerNs() / 1000ull);
     }
@@ -429,7 +440,7 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
   for (int i = tid; i < L_HORIZON; i += NT) { s.l_hist[i] = 0; s.l_symin[i] = 0; }
   if (tid == 0) {
     s.final_out = 0; s.prob = 0.5f; s.ring_pos = 0; s.new_bit = 0; s.recent_bits = 1; s.bb = 0;
-    s.first_prediction = 1; s.error = 0; s.steps = 0; s.pool_next = 1; s.hist_len = 0; s.sparse_used = 0; s.nswap = 0;
+    s.first_prediction = 1; s.error = 0; s.steps = 0; s.pool_next = 1; s.hist_len = 0; s.sparse_used = 0; s.nswap = 0; s.cand_valid = 0;
     s.l_epoch = 0; s.l_update_steps = 0; s.l_old_input = 0; s.l_fused = 0;
     s.x1 = 0; s.x2 = 0xffffffffu; s.x = 0;
     for (int i = 0; i < GMX_PROF_SLOTS; ++i) s.prof[i] = 0;
@@ -1137,7 +1148,14 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
       const uint32_t q = atomicAdd(&s.nswap, 1u);
       s.swap_m[q] = (uint8_t)m;
       s.swap_old[q] = s.set_pool[m];
-      s.swap_new[q] = A.at<uint32_t>(L.mix_dir[m])[idx];
+      const int slot = BitSlot(m);
+      if (slot >= 0 && s.cand_valid) {   // staged one bit ago for both values of the bit that has just been perceived
+        s.swap_new[q] = s.cand_id[slot][s.new_bit];
+        s.swap_staged[q] = (uint8_t)(1 + s.new_bit);
+      } else {
+        s.swap_new[q] = A.at<uint32_t>(L.mix_dir[m])[idx];
+        s.swap_staged[q] = 0;
+      }
       s.set_idx[m] = idx;
     }
   } else if (tid == 40) {
@@ -1145,8 +1163,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     for (int k = 0; k < NMATCH; ++k) { const uint32_t v = s.m_len[k] >> 5; c = v > c ? v : c; }
     s.ctx[C_LONGEST] = c;
   } else if (tid >= 96 && tid < 128) {
-    // the weight sets the bit-level gates can select for the NEXT bit (both values of the bit)
-    for (int j = tid - 96; j < 2 * NMIX; j += 32) PrefetchMixerSet(s, A, j >> 1, 1 + (j & 1));
+    CpAsyncWaitAll();   // the candidate copies this warp issued during the previous bit's mixer phase have landed
   } else if (tid >= 64 && tid < 96) {
     // layer-0 input vector: the active predictions, inactive ones as +0 (Mixer::Predict sums the active ones
     // in index order; a +-0 product leaves the running sum unchanged, the sum itself is never -0)
@@ -1179,7 +1196,14 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     for (uint32_t r = tid >> 5; r < nswap; r += NT / 32) {   // asynchronous copies: all queued sets in flight together
       const int m = s.swap_m[r];
       const uint32_t nid = s.swap_new[r];
-      if (lane <= (MixerNW(m) + 3) / 4) {
+      const int staged = s.swap_staged[r];
+      if (staged && nid) {   // record image already in shared memory
+        if (lane <= (MixerNW(m) + 3) / 4) {
+          const float4* img = (const float4*)s.cand_w + (staged - 1) * CAND_Q + CandOff(BitSlot(m));
+          if (lane == 0) { s.set_steps[m] = f2u(img[0].x); s.set_pool[m] = nid; }
+          else ((float4*)(s.w + WOff(m)))[lane - 1] = img[lane];
+        }
+      } else if (lane <= (MixerNW(m) + 3) / 4) {
         const float4* rec = pool + (size_t)nid * stride4;
         if (lane == 0) {
           if (nid) CpAsync4(&s.set_steps[m], rec); else s.set_steps[m] = 0u;
@@ -1290,6 +1314,35 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
       s.prob = prob;
     }
     GMX_PROF(20);
+  } else if (tid >= NT - 32) {
+    // Meanwhile the last warp stages, for the four bit-gated mixers, the sets both values of this bit lead to: lanes
+    // 0..7 read the eight directory entries, then all lanes start the asynchronous copies of the record images. The
+    // copies are awaited by this warp in the next bit's gate-selection phase, a whole Learn step away.
+    const int lane = tid - (NT - 32);
+    const uint32_t bc = s.ctx[C_BIT_CONTEXT];
+    const bool ok = bc < 127;   // the next bit belongs to the same byte
+    if (lane == 0) s.cand_valid = ok;
+    if (ok) {
+      uint32_t nid = 0;
+      if (lane < 2 * NBITMIX) {
+        const int slot = lane >> 1, which = lane & 1, m = BitMixer(slot);
+        const uint32_t nbc = 2 * bc + 1 + which;   // bit_context after the next bit (basic-contexts.cpp:32-36)
+        const int cid = s.T.mixer[m].ctx;
+        const uint32_t c = cid == C_BIT_CONTEXT ? nbc : cid == C_LBPR ? (s.ctx[C_LAST_BYTE] << 8) + nbc : (s.ctx[C_RB1] << 8) + nbc;
+        nid = A.at<uint32_t>(L.mix_dir[m])[c & ((1u << s.T.mixer[m].log2) - 1)];
+        s.cand_id[slot][which] = nid;
+      }
+      const float4* pool = A.at<float4>(L.mix_pool);
+      const uint32_t stride4 = L.mix_set_stride / 4;
+#pragma unroll 1
+      for (int i0 = 0; i0 < 2 * CAND_Q; i0 += 32) {
+        const int i = i0 + lane;
+        const int which = i >= CAND_Q, o = i - which * CAND_Q;
+        const int slot = o < 24 ? 0 : o < 51 ? 1 : o < 59 ? 2 : 3;
+        const uint32_t id = __shfl_sync(0xffffffffu, nid, (2 * slot + which) & 31);
+        if (i < 2 * CAND_Q && id) CpAsync16((float4*)s.cand_w + i, pool + (size_t)id * stride4 + (o - CandOff(slot)));
+      }
+    }
   }
   BlockSync();
   GMX_PROF(6);
@@ -1699,6 +1752,7 @@ __global__ void __launch_bounds__(NT) StepKernel(StepParams Q) {
       LearnBit<NT, false>(s, A, Q.P, tid);
     }
   }
+  CpAsyncWaitAll();   // candidate weight sets staged by PredictBit must have landed before shared memory is parked
   BlockSync();
   for (int i = tid; i < kWords; i += NT) Q.state[i] = sw[i];
   if (tid == 0) *Q.status_out = s.error;
