@@ -14,7 +14,8 @@ class GmixError(RuntimeError):
 
 
 def library_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libgmix_b200.so")
+    # GMIX_B200_LIB: development only, an alternative build of the same library (kernel A/B measurements)
+    return os.environ.get("GMIX_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libgmix_b200.so")
 
 
 def load_library():

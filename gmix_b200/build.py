@@ -26,6 +26,27 @@ def _stale():
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
+def build_variant(name, defines):
+    """Development: the same library compiled with extra -D flags into lib/variants/<name>/ (kernel A/B measurements;
+    select it with GMIX_B200_LIB=<path>)."""
+    vdir = os.path.join(ROOT, "lib", "variants", name)
+    os.makedirs(vdir, exist_ok=True)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    procs, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(vdir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        procs.append(subprocess.Popen([nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-c", os.path.join(CSRC, src), "-o", obj],
+                                      stdout=subprocess.DEVNULL, stderr=subprocess.STDOUT))
+    if any(p.wait() != 0 for p in procs):
+        raise RuntimeError("nvcc failed")
+    out = os.path.join(vdir, "libgmix_b200.so")
+    subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs, check=True)
+    for o in objs:
+        os.remove(o)
+    return out
+
+
 def build_library(force=False, verbose=False):
     """Compile the CUDA library if it is missing or older than its sources. Returns the .so path."""
     if not force and not _stale():

@@ -579,6 +579,7 @@ inline bool ToArena(const Image& im, const ArenaLayout& L, uint8_t* arena, Strea
     P->found_state = im.found_state < im.sa_size ? (uint32_t)im.found_state : 0u;   // a null FoundState is written as -HeapStart
     P->max_context = (uint32_t)im.max_context; P->esc_count = im.esc_count; P->error = 0;
     memcpy(P->char_mask, im.char_mask, sizeof(P->char_mask));
+    for (int i = 0; i < 256; ++i) if (im.char_mask[i] == im.esc_count) s.p_masked[i >> 5] |= 1u << (i & 31);
     memcpy(P->bin_summ, im.bin_summ, sizeof(P->bin_summ));
     for (int i = 0; i < 23; ++i) for (int j = 0; j < 32; ++j) { P->see2[i][j].summ = im.see2[i][j].summ; P->see2[i][j].shift = im.see2[i][j].shift; P->see2[i][j].count = im.see2[i][j].count; }
     P->dummy_see2.summ = im.dummy_see2.summ; P->dummy_see2.shift = im.dummy_see2.shift; P->dummy_see2.count = im.dummy_see2.count;

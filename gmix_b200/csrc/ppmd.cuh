@@ -80,6 +80,13 @@ struct Ppmd {
   uint32_t text_cap, units_cap;
   uint32_t* sqp;  // out: 256 symbol pseudo-probabilities (:1187)
   int lane;       // lane of the calling thread in the PPMd warp (UpdateByte / PrepareByte are warp-collective)
+  // Shadow of the only question ever asked of CharMask (:449): "CharMask[sym] == EscCount?" as 256 bits in shared
+  // memory, cleared whenever EscCount changes. The array in the arena is still written (it is checkpoint state) but
+  // no longer read on the per-byte path.
+  uint32_t* masked;
+  GMX_DEV bool Masked(uint32_t sy) const { return (masked[sy >> 5] >> (sy & 31)) & 1u; }
+  GMX_DEV void Mask(uint32_t sy, uint32_t ec) const { S->char_mask[sy] = ec; atomicOr(&masked[sy >> 5], 1u << (sy & 31)); }
+  GMX_DEV void NextEscCount() const { S->esc_count++; for (int i = 0; i < 8; ++i) masked[i] = 0u; }   // called by one lane
 
   // ---- virtual heap -> backed memory -------------------------------------------------------
   GMX_DEV uint8_t* At(uint32_t v) const { return heap + (v & mask); }
@@ -198,6 +205,7 @@ struct Ppmd {
 #pragma unroll 1
     for (i = 0; i < 256; i++) S->char_mask[i] = 0;
     S->esc_count = 1;
+    for (i = 0; i < 8; i++) masked[i] = 0u;
     S->order_fall = PPMD_MAX_ORDER;
     for (i = 0; i <= (int)PPMD_N_INDEXES; i++) { S->bl_stamp[i] = 0; S->bl_next[i] = 0; }
     S->text_ptr = 0;
@@ -562,7 +570,7 @@ struct Ppmd {
           if (Freq(p) > PPMD_MAX_FREQ) S->found_state = Rescale(minc, S->order_fall, p));
       } else {
         const uint32_t ec = S->esc_count;
-        for (int k = lane; k <= cnum; k += 32) S->char_mask[Sym(p0 + 6 * k)] = ec;
+        for (int k = lane; k <= cnum; k += 32) Mask(Sym(p0 + 6 * k), ec);
         GMX_L0(S->prev_success = 0; S->num_masked = cnum; S->found_state = 0);
       }
     } else {  // processBinSymbol<0> :1023-1046
@@ -572,7 +580,7 @@ struct Ppmd {
         S->bsumm = *bs;
         *bs = (uint16_t)(*bs - ((S->bsumm + 64) >> PPMD_PERIOD_BITS));
         if (Sym(rs) != c) {
-          S->char_mask[Sym(rs)] = S->esc_count; S->num_masked = 0; S->prev_success = 0; S->found_state = 0;
+          Mask(Sym(rs), S->esc_count); S->num_masked = 0; S->prev_success = 0; S->found_state = 0;
         } else {
           *bs = (uint16_t)(*bs + PPMD_INTERVAL);
           SetFreq(rs, Freq(rs) + (Freq(rs) < 196));
@@ -593,8 +601,8 @@ struct Ppmd {
         bool hit = false;
         if (k <= cnum) {
           const uint32_t sy = Sym(p + 6 * k);
-          if (S->char_mask[sy] != ec) {
-            S->char_mask[sy] = ec;
+          if (!Masked(sy)) {
+            Mask(sy, ec);
             low += (int)Freq(p + 6 * k);
             hit = sy == c;
           }
@@ -616,7 +624,7 @@ struct Ppmd {
           SetFreq(ph, Freq(ph) + 4); SetSummFreq(minc, SummFreq(minc) + 4);
           if (Freq(ph) > PPMD_MAX_FREQ) S->found_state = Rescale(minc, S->order_fall, ph);
           S->run_length = S->init_rl;
-          S->esc_count++;
+          NextEscCount();
         } else {
           S->num_masked = cnum;
           see->summ = (uint16_t)(see->summ + (total - see_freq));
@@ -658,7 +666,7 @@ struct Ppmd {
         const uint32_t f = Freq(p + 6 * k), sy = Sym(p + 6 * k);
         sqp[sy] = Scale(cum, f, total) + 1;
         low += (int)f;
-        S->char_mask[sy] = ec;
+        Mask(sy, ec);
       }
       low = WarpSum(low);
       nm = cnum;
@@ -667,7 +675,7 @@ struct Ppmd {
       const uint32_t rs = OneState(minc);
       const int bsv = *BinSummFor(minc);
       const uint32_t sy = Sym(rs);
-      GMX_L0(S->bsumm = bsv; sqp[sy] = Scale(cum, (uint32_t)(bsv + bsv) & 0xffff, PPMD_SCALE) + 1; S->char_mask[sy] = ec);
+      GMX_L0(S->bsumm = bsv; sqp[sy] = Scale(cum, (uint32_t)(bsv + bsv) & 0xffff, PPMD_SCALE) + 1; Mask(sy, ec));
       cum = Scale(cum, (uint32_t)(PPMD_SCALE - bsv - bsv) & 0xffff, PPMD_SCALE);
       nm = 0;
     }
@@ -686,18 +694,18 @@ struct Ppmd {
       See2For(minc, cnum, nm, &see_freq);
       int low = 0;
       for (int k = lane; k <= cnum; k += 32)
-        if (S->char_mask[Sym(p + 6 * k)] != ec) low += (int)Freq(p + 6 * k);
+        if (!Masked(Sym(p + 6 * k))) low += (int)Freq(p + 6 * k);
       low = WarpSum(low);
       const uint32_t total = ((uint32_t)see_freq + (uint32_t)low) & 0xffff;
       for (int k = lane; k <= cnum; k += 32) {
         const uint32_t sy = Sym(p + 6 * k);
-        if (S->char_mask[sy] != ec) { sqp[sy] = Scale(cum, Freq(p + 6 * k), total) + 1; S->char_mask[sy] = ec; }
+        if (!Masked(sy)) { sqp[sy] = Scale(cum, Freq(p + 6 * k), total) + 1; Mask(sy, ec); }
       }
       cum = Scale(cum, (uint32_t)see_freq & 0xffff, total);
       nm = cnum;
       __syncwarp();
     }
-    GMX_L0(S->esc_count++; S->num_masked = 0);
+    GMX_L0(NextEscCount(); S->num_masked = 0);
   }
 #undef GMX_L0
 };

@@ -189,6 +189,7 @@ struct StreamSmem {
     uint32_t sqp[256];           //   PPMd symbol pseudo-probabilities (byte boundary, before the LSTM forward pass)
     float l_err256[256];         //   LSTM scratch (forward pass, Perceive, BPTT)
   };
+  uint32_t p_masked[8];          // PPMd: bit sym = CharMask[sym] == EscCount (ppmd.cuh)
   uint8_t l_hist[L_HORIZON], l_symin[L_HORIZON];
   uint32_t l_epoch, l_update_steps, l_old_input, l_fused;
   // coder
@@ -447,7 +448,7 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
   }
   BlockSync();
   if (tid == 0) {
-    Ppmd pm{A.at<PpmdState>(L.p_state), A.at<uint8_t>(L.p_heap), L.p_mask, L.p_text_cap, L.p_units_cap, s.sqp, 0};
+    Ppmd pm{A.at<PpmdState>(L.p_state), A.at<uint8_t>(L.p_heap), L.p_mask, L.p_text_cap, L.p_units_cap, s.sqp, 0, s.p_masked};
     pm.Init();
   }
   BlockSync();
@@ -664,7 +665,7 @@ GMX_DEV void LstmBptt(StreamSmem& s, const Arena& A, const StreamParams& P, int 
       float he = s.l_hidden_err[tid];
       const float4* wo4 = (const float4*)wo;
       const float4* er4 = (const float4*)s.l_err256;
-#pragma unroll 4
+#pragma unroll 8
       for (int i = 0; i < L_NOUT / 4; ++i) {
         const float4 w = LoadStream4(wo4 + i), e = er4[i];
         he = f_add(he, f_mul(w.x, e.x)); he = f_add(he, f_mul(w.y, e.y));
@@ -944,7 +945,7 @@ GMX_DEV void ByteBoundary(StreamSmem& s, const Arena& A, const StreamParams& P, 
     }
     s.ih_hash[k] = oh;
   } else if (tid >= NT - 32) {  // ModPPMD::Predict byte part, mod_ppmd.cpp:1651-1654 (the last warp, collectively)
-    Ppmd pm{A.at<PpmdState>(L.p_state), A.at<uint8_t>(L.p_heap), L.p_mask, L.p_text_cap, L.p_units_cap, s.sqp, tid - (NT - 32)};
+    Ppmd pm{A.at<PpmdState>(L.p_state), A.at<uint8_t>(L.p_heap), L.p_mask, L.p_text_cap, L.p_units_cap, s.sqp, tid - (NT - 32), s.p_masked};
     pm.UpdateByte(last_byte);
     if (!pm.S->error) pm.PrepareByte();
     if (pm.S->error) s.error = GMX_ERR_PPMD_ARENA;
@@ -1273,7 +1274,11 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     {
       const float4* x4 = (const float4*)s.l0_out;
       const float4* w4 = (const float4*)w1;
+#if defined(GMX_MIX_UNROLL)
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
       for (int q = 0; q < NL0 / 4; ++q) {
         const float4 x = x4[q], v = w4[q];
         acc = f_add(acc, f_mul(x.x, v.x)); acc = f_add(acc, f_mul(x.y, v.y));
@@ -1299,7 +1304,11 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
       float p = 0.0f;
       const float4* x4 = (const float4*)s.l0_out;   // l0_out[24] then l1_out[8]
       const float4* w4 = (const float4*)w2;
+#if defined(GMX_MIX_UNROLL)
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
       for (int q = 0; q < (NL0 + NL1) / 4; ++q) {
         const float4 x = x4[q], v = w4[q];
         p = f_add(p, f_mul(x.x, v.x)); p = f_add(p, f_mul(x.y, v.y));
