@@ -84,7 +84,11 @@ struct Ppmd {
   // memory, cleared whenever EscCount changes. The array in the arena is still written (it is checkpoint state) but
   // no longer read on the per-byte path.
   uint32_t* masked;
+#if defined(GMX_NO_MASK_SHADOW)
+  GMX_DEV bool Masked(uint32_t sy) const { return S->char_mask[sy] == S->esc_count; }
+#else
   GMX_DEV bool Masked(uint32_t sy) const { return (masked[sy >> 5] >> (sy & 31)) & 1u; }
+#endif
   GMX_DEV void Mask(uint32_t sy, uint32_t ec) const { S->char_mask[sy] = ec; atomicOr(&masked[sy >> 5], 1u << (sy & 31)); }
   GMX_DEV void NextEscCount() const { S->esc_count++; for (int i = 0; i < 8; ++i) masked[i] = 0u; }   // called by one lane
 

@@ -37,6 +37,29 @@ enum : uint32_t {
 // layer-1/final sets (<= 33 weights) at stride 36 words. Both strides are 16-byte multiples (float4
 // loads) and = 4 mod 32 banks, which makes lane-per-neuron float4 reads conflict free.
 enum : int { WSTRIDE0 = 132, WSTRIDE1 = 36, WTOTAL = 24 * WSTRIDE0 + 9 * WSTRIDE1 };
+#define GMX_PRAGMA_(x) _Pragma(#x)
+#define GMX_UNROLL(n) GMX_PRAGMA_(unroll n)
+#if defined(GMX_LSTM_STREAM)
+#define GMX_LSTM_LOAD(p) LoadStream4(p)   // gate weights as streaming (evict-first) traffic
+#else
+#define GMX_LSTM_LOAD(p) (*(p))
+#endif
+#ifndef GMX_BPTT_UNROLL
+#define GMX_BPTT_UNROLL 4
+#endif
+// L2 prefetches one step ahead (next-bit sparse slots, next-bit / next-byte weight sets, the output layer before
+// Perceive and between BPTT epochs) all LOSE 0.5-2.4 % each with 8 CTAs per SM (A/B in profiles/r01_s3_ab.md): the other
+// resident streams already cover the latency and the extra requests only queue in front of demand loads. They stay
+// available as GMX_PF_* build flags for low-occupancy use.
+#if !defined(GMX_CAND_STAGE)
+#define GMX_NO_CAND_STAGE 1   // staging both candidate weight sets one bit ahead wins 11 % at 1 CTA/SM and loses 2 % at 8 (A/B in profiles/)
+#endif
+#ifndef LSTM_STAGES
+#define LSTM_STAGES 5       // float4 pairs in flight per gate-row pair of the LSTM forward pass (ring in s.w: 5 x 2 x 75 x 16 B = 12 KB)
+#endif
+#ifndef GMX_LSTM_UNROLL
+#define GMX_LSTM_UNROLL 2   // quads in flight per gate row of the LSTM forward pass (register budget: 64)
+#endif
 enum : int { GMX_PROF_SLOTS = 24 };
 enum : int { NBITMIX = 4, CAND_Q = 68 };   // bit-gated mixers; float4s per staged candidate: (1 header + ceil(weights / 4)) summed over the four
 // Phase slots: 0 byte contexts+PPMd, 1 ppm normalise, 2 LSTM forward, 3 interval nodes, 4 indirect/match
@@ -296,6 +319,17 @@ GMX_DEV inline void CpAsync16(void* smem_dst, const void* gmem_src) {   // both 
   memcpy(smem_dst, gmem_src, 16);
 #endif
 }
+GMX_DEV inline void CpAsyncCommit() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+GMX_DEV inline void CpAsyncWaitGroup() {   // at most N of this thread's most recent groups still pending
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
 GMX_DEV inline void CpAsyncWaitAll() {
 #if defined(__CUDA_ARCH__)
   asm volatile("cp.async.wait_all;" ::: "memory");
@@ -500,10 +534,13 @@ GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, i
   // short enough that the lines are still in L2 when the dot products reach them).
   {
     const float* W = A.at<float>(L.l_w);
-#if !defined(GMX_NO_LSTM_PREFETCH)
+#if defined(GMX_PF_GATES)   // off by default: with the asynchronous ring below the extra L2 traffic costs more than it hides
     for (int g = 0; g < 3; ++g) PrefetchRangeKeep(W + LstmW(g, L_NOUT, 0), (L_ROWQ - L_NOUT / 4) * L_CELLS * 16, tid, NT);
+#endif
+#if !defined(GMX_NO_PF_WOUT)
     PrefetchRange(A.at<float>(L.l_wout) + (size_t)e * L_HID * L_NOUT, L_HID * L_NOUT * 4, tid, NT);
 #endif
+    (void)W;
   }
   // layer_input[e] = [ppm 256 | hidden 50 | 1]  (SetInput lstm.cpp:45-50, copy :94-96)
   for (int i = tid; i < L_NIN; i += NT) {
@@ -522,10 +559,50 @@ GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, i
     // quad q of this row = input columns 4q..4q+3 = one 16-byte load
     const float4* w0 = (const float4*)W + ((size_t)g0 * L_ROWQ + L_NOUT / 4) * L_CELLS + i0;
     const float4* w1 = (const float4*)W + ((size_t)g1 * L_ROWQ + L_NOUT / 4) * L_CELLS + i1;
+#if !defined(GMX_NO_LSTM_STAGE)
+    // The 77 quads of both rows stream through a private ring of LSTM_STAGES x 2 float4 slots in s.w (free at this
+    // point, ByteBoundary (0)): cp.async keeps 2 x LSTM_STAGES 16-byte copies in flight per thread without holding
+    // registers, 2.5x what register-staged loads reach under the 64-register cap. No barrier: a thread only ever
+    // touches its own slots.
+    constexpr int NQ = L_NOUT / 4 + L_CELLS / 4 + 1, HALF = 3 * L_CELLS / 2;
+    float4* ring = (float4*)s.w;
+    static_assert(LSTM_STAGES * 2 * HALF * 16 <= WTOTAL * 4, "ring does not fit the weight-set staging area");
+#pragma unroll
+    for (int q = 0; q < LSTM_STAGES; ++q) {
+      CpAsync16(ring + (q * 2 + 0) * HALF + tid, w0 + q * L_CELLS);
+      CpAsync16(ring + (q * 2 + 1) * HALF + tid, w1 + q * L_CELLS);
+      CpAsyncCommit();
+    }
+    int st = 0;
+#pragma unroll 1
+    for (int q = 0; q < NQ; ++q) {
+      CpAsyncWaitGroup<LSTM_STAGES - 1>();
+      const float4 a = ring[(st * 2 + 0) * HALF + tid], b = ring[(st * 2 + 1) * HALF + tid];
+      if (q + LSTM_STAGES < NQ) {
+        CpAsync16(ring + (st * 2 + 0) * HALF + tid, w0 + (q + LSTM_STAGES) * L_CELLS);
+        CpAsync16(ring + (st * 2 + 1) * HALF + tid, w1 + (q + LSTM_STAGES) * L_CELLS);
+      }
+      CpAsyncCommit();   // one group per iteration, empty at the tail, keeps the wait distance constant
+      st = st + 1 == LSTM_STAGES ? 0 : st + 1;
+      if (q < NQ - 1) {   // layer input = [ppm 256 | hidden 50 | 1]
+        const float4 x = q < L_NOUT / 4 ? ((const float4*)s.ppm)[q] : ((const float4*)s.l_hidden)[q - L_NOUT / 4];
+        f0 = f_add(f0, f_mul(x.x, a.x)); f1 = f_add(f1, f_mul(x.x, b.x));
+        f0 = f_add(f0, f_mul(x.y, a.y)); f1 = f_add(f1, f_mul(x.y, b.y));
+        f0 = f_add(f0, f_mul(x.z, a.z)); f1 = f_add(f1, f_mul(x.z, b.z));
+        f0 = f_add(f0, f_mul(x.w, a.w)); f1 = f_add(f1, f_mul(x.w, b.w));
+      } else {            // hidden 48, 49 and the bias input (1.0); the fourth column is padding
+        const float h48 = s.l_hidden[L_CELLS - 2], h49 = s.l_hidden[L_CELLS - 1];
+        f0 = f_add(f0, f_mul(h48, a.x)); f1 = f_add(f1, f_mul(h48, b.x));
+        f0 = f_add(f0, f_mul(h49, a.y)); f1 = f_add(f1, f_mul(h49, b.y));
+        f0 = f_add(f0, f_mul(1.0f, a.z)); f1 = f_add(f1, f_mul(1.0f, b.z));
+      }
+    }
+    CpAsyncWaitAll();
+#else
     const float4* x4 = (const float4*)s.ppm;
-#pragma unroll 2
+GMX_UNROLL(GMX_LSTM_UNROLL)
     for (int q = 0; q < L_NOUT / 4; ++q) {           // layer input = [ppm 256 | hidden 50 | 1]
-      const float4 x = x4[q], a = w0[q * L_CELLS], b = w1[q * L_CELLS];
+      const float4 x = x4[q], a = GMX_LSTM_LOAD(w0 + q * L_CELLS), b = GMX_LSTM_LOAD(w1 + q * L_CELLS);
       f0 = f_add(f0, f_mul(x.x, a.x)); f1 = f_add(f1, f_mul(x.x, b.x));
       f0 = f_add(f0, f_mul(x.y, a.y)); f1 = f_add(f1, f_mul(x.y, b.y));
       f0 = f_add(f0, f_mul(x.z, a.z)); f1 = f_add(f1, f_mul(x.z, b.z));
@@ -533,7 +610,7 @@ GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, i
     }
     w0 += (L_NOUT / 4) * L_CELLS; w1 += (L_NOUT / 4) * L_CELLS;
     x4 = (const float4*)s.l_hidden;
-#pragma unroll 2
+GMX_UNROLL(GMX_LSTM_UNROLL)
     for (int q = 0; q < L_CELLS / 4; ++q) {          // hidden 0..47
       const float4 x = x4[q], a = w0[q * L_CELLS], b = w1[q * L_CELLS];
       f0 = f_add(f0, f_mul(x.x, a.x)); f1 = f_add(f1, f_mul(x.x, b.x));
@@ -548,6 +625,7 @@ GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, i
       f0 = f_add(f0, f_mul(h49, a.y)); f1 = f_add(f1, f_mul(h49, b.y));
       f0 = f_add(f0, f_mul(1.0f, a.z)); f1 = f_add(f1, f_mul(1.0f, b.z));
     }
+#endif
     s.l_gate[g0][i0] = f0;
     s.l_gate[g1][i1] = f1;
   }
@@ -654,7 +732,9 @@ GMX_DEV void LstmBptt(StreamSmem& s, const Arena& A, const StreamParams& P, int 
   }
   BlockSync();
   for (int ep = L_HORIZON - 1; ep >= 0; --ep) {
+#if defined(GMX_PF_BPTT)
     if (ep > 0) PrefetchRange(A.at<float>(L.l_wout) + (size_t)(ep - 1) * L_HID * L_NOUT, L_HID * L_NOUT * 4, tid, NT);
+#endif
     const float* out_e = A.at<float>(L.l_out) + ep * L_NOUT;
     for (int i = tid; i < L_NOUT; i += NT)
       s.l_err256[i] = (uint32_t)i == s.l_hist[ep] ? f_sub(out_e[i], 1.0f) : out_e[i];
@@ -665,7 +745,7 @@ GMX_DEV void LstmBptt(StreamSmem& s, const Arena& A, const StreamParams& P, int 
       float he = s.l_hidden_err[tid];
       const float4* wo4 = (const float4*)wo;
       const float4* er4 = (const float4*)s.l_err256;
-#pragma unroll 8
+GMX_UNROLL(GMX_BPTT_UNROLL)
       for (int i = 0; i < L_NOUT / 4; ++i) {
         const float4 w = LoadStream4(wo4 + i), e = er4[i];
         he = f_add(he, f_mul(w.x, e.x)); he = f_add(he, f_mul(w.y, e.y));
@@ -910,6 +990,25 @@ template <int NT, bool PROF>
 GMX_DEV void ByteBoundary(StreamSmem& s, const Arena& A, const StreamParams& P, int known_byte, int tid) {
   const ArenaLayout& L = *A.L;
   const uint32_t last_byte = s.ctx[C_LAST_BYTE];
+#if !defined(GMX_NO_LSTM_STAGE)
+  // (0) Nearly every gate context changes with the byte, so all staged weight sets go back to the pool now instead of
+  // at the swap a moment later: until then s.w is free, and the LSTM forward pass uses it as the landing zone of its
+  // asynchronous gate-weight copies (LstmForward). Warps 0..2; the last warp starts PPMd right away.
+  if (tid < NT - 32) {
+    float4* pool = A.at<float4>(L.mix_pool);
+    const uint32_t stride4 = L.mix_set_stride / 4;
+    const int lane = tid & 31;
+#pragma unroll 1
+    for (int m = tid >> 5; m < NMIX; m += NT / 32 - 1) {
+      const uint32_t old = s.set_pool[m];
+      if (old && lane <= (MixerNW(m) + 3) / 4) {
+        float4* rec = pool + (size_t)old * stride4;
+        if (lane == 0) rec[0] = make_float4(u2f(s.set_steps[m]), 0.0f, 0.0f, 0.0f);
+        else rec[lane] = ((const float4*)(s.w + WOff(m)))[lane - 1];
+      }
+    }
+  }
+#endif
   // (1) contexts: intervals, hashed skip contexts, indirect-hash tables; PPMd on its own thread.
   if (tid < 9) {  // IntervalContext::Predict interval-context.cpp:17-23
     const IntervalSpec sp = s.T.interval[tid];
@@ -952,6 +1051,9 @@ GMX_DEV void ByteBoundary(StreamSmem& s, const Arena& A, const StreamParams& P, 
   }
   BlockSync();
   GMX_PROF(0);
+#if !defined(GMX_NO_LSTM_STAGE)
+  if (tid < NMIX) { s.set_idx[tid] = 0xFFFFFFFFu; s.set_pool[tid] = 0; }   // nothing is staged any more: the swap of this bit fetches all 33
+#endif
   // (2) ppm_predictions = max(sqp, 1) / sum, valarray::sum() ascending (mod_ppmd.cpp:1655-1661)
   for (int i = tid; i < 256; i += NT) { float v = (float)s.sqp[i]; if (v < 1.0f) v = 1.0f; s.ppm[i] = v; }
   // Indirect row bases ((ctx << 8) % M, so that slot = (base + bit_context) % M) and L2 prefetch of
@@ -969,7 +1071,11 @@ GMX_DEV void ByteBoundary(StreamSmem& s, const Arena& A, const StreamParams& P, 
     s.l_red[3] = acc;
   } else {
     // prefetch: 41 tables x 5 lines of 128 B cover the 510-byte row
+#if defined(GMX_NO_PF_IND_ROW)
+    for (int t = NIND * 5; t < NIND * 5; ++t) {
+#else
     for (int t = tid - 1; t < NIND * 5; t += NT - 1) {
+#endif
       const int k = t / 5, ln = t - k * 5;
       if (L.ind_sid[k]) {  // sparse: the probe start of the row's first slot (bit_context 0)
         if (ln == 0) PrefetchL2(A.map().tab + (SparseHash(SparseKey(L.ind_sid[k], s.ind_base[k])) & L.sparse_mask));
@@ -981,7 +1087,9 @@ GMX_DEV void ByteBoundary(StreamSmem& s, const Arena& A, const StreamParams& P, 
       PrefetchL2(A.at<uint16_t>(L.ind_tab[k]) + slot);
     }
     // weight sets the byte-level gates will select at this boundary: bring their pool records to L2
+#if defined(GMX_PF_MIX_BYTE)
     if (tid >= 64 && tid < 64 + NMIX) PrefetchMixerSet(s, A, tid - 64, 0);
+#endif
   }
   BlockSync();
   {
@@ -1067,7 +1175,11 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     }
     s.ind_slot[k] = slot;
     s.ind_state[k] = (uint16_t)e;
+#if !defined(GMX_PF_IND_NEXT)
+    if (false) {
+#else
     if (sid && bitctx < 127) {  // both slots the next bit can select: start their probes' sectors towards L2
+#endif
       uint32_t nslot = s.ind_base[k] + 2 * bitctx + 1;
       if (nslot >= M) nslot -= M;
       const SparseMap Mp = A.map();
@@ -1123,7 +1235,9 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
   } else if (tid >= 98 && s.recent_bits >= 128) {
     // last bit of the byte: Lstm::Perceive will copy + update the output layer of the epoch slot just used
     const uint32_t last = s.l_epoch == 0 ? L_HORIZON - 1 : s.l_epoch - 1;
+#if defined(GMX_PF_WOUT_LAST)
     PrefetchRange(A.at<float>(L.l_wout) + (size_t)last * L_HID * L_NOUT, L_HID * L_NOUT * 4, tid - 98, NT - 98);
+#endif
   } else if (tid == 96 || tid == 97) {  // per-bit part of ModPPMD / LstmModel::Predict
     const int which = tid - 96;
     uint32_t fl;
@@ -1164,7 +1278,14 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     for (int k = 0; k < NMATCH; ++k) { const uint32_t v = s.m_len[k] >> 5; c = v > c ? v : c; }
     s.ctx[C_LONGEST] = c;
   } else if (tid >= 96 && tid < 128) {
+#if defined(GMX_NO_CAND_STAGE)
+    // the weight sets the bit-level gates can select for the NEXT bit (both values of the bit): L2 prefetch only
+#if defined(GMX_PF_MIX_BIT)
+    for (int j = tid - 96; j < 2 * NMIX; j += 32) PrefetchMixerSet(s, A, j >> 1, 1 + (j & 1));
+#endif
+#else
     CpAsyncWaitAll();   // the candidate copies this warp issued during the previous bit's mixer phase have landed
+#endif
   } else if (tid >= 64 && tid < 96) {
     // layer-0 input vector: the active predictions, inactive ones as +0 (Mixer::Predict sums the active ones
     // in index order; a +-0 product leaves the running sum unchanged, the sum itself is never -0)
@@ -1323,7 +1444,9 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
       s.prob = prob;
     }
     GMX_PROF(20);
-  } else if (tid >= NT - 32) {
+  }
+#if !defined(GMX_NO_CAND_STAGE)
+  else if (tid >= NT - 32) {
     // Meanwhile the last warp stages, for the four bit-gated mixers, the sets both values of this bit lead to: lanes
     // 0..7 read the eight directory entries, then all lanes start the asynchronous copies of the record images. The
     // copies are awaited by this warp in the next bit's gate-selection phase, a whole Learn step away.
@@ -1353,6 +1476,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
       }
     }
   }
+#endif
   BlockSync();
   GMX_PROF(6);
 }
