@@ -198,6 +198,7 @@ struct StreamSmem {
   uint8_t ind_found[NIND + 3];               // sparse tables: entry exists at ind_slot
   float ind_pa[NIND], ind_pb[NIND];          // the two logit-map entries Learn will update, as read by Predict
   uint32_t sparse_used;
+  uint32_t tables_done;                      // LearnTables of this bit already ran during PredictBit (compress)
   uint32_t t_start_us;
   // match
   uint32_t m_cur[NMATCH]; uint8_t m_byte[NMATCH], m_bitpos[NMATCH], m_len[NMATCH];
@@ -414,7 +415,7 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
     for (int i = kFirst + tid; i < kWords; i += NT) sw[i] = P.tmpl_state[i];
     BlockSync();
     if (tid == 0) {
-      s.error = 0; s.nswap = 0; s.cand_valid = 0; s.x1 = 0; s.x2 = 0xffffffffu; s.x = 0;
+      s.error = 0; s.nswap = 0; s.cand_valid = 0; s.tables_done = 0; s.x1 = 0; s.x2 = 0xffffffffu; s.x = 0;
       for (int i = 0; i < GMX_PROF_SLOTS; ++i) s.prof[i] = 0;
       s.prof_t = GMX_CLOCK(); s.t_start_us = (uint32_t)(GlobalTimerNs() / 1000ull);
     }
@@ -475,7 +476,7 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
   for (int i = tid; i < L_HORIZON; i += NT) { s.l_hist[i] = 0; s.l_symin[i] = 0; }
   if (tid == 0) {
     s.final_out = 0; s.prob = 0.5f; s.ring_pos = 0; s.new_bit = 0; s.recent_bits = 1; s.bb = 0;
-    s.first_prediction = 1; s.error = 0; s.steps = 0; s.pool_next = 1; s.hist_len = 0; s.sparse_used = 0; s.nswap = 0; s.cand_valid = 0;
+    s.first_prediction = 1; s.error = 0; s.steps = 0; s.pool_next = 1; s.hist_len = 0; s.sparse_used = 0; s.nswap = 0; s.cand_valid = 0; s.tables_done = 0;
     s.l_epoch = 0; s.l_update_steps = 0; s.l_old_input = 0; s.l_fused = 0;
     s.x1 = 0; s.x2 = 0xffffffffu; s.x = 0;
     for (int i = 0; i < GMX_PROF_SLOTS; ++i) s.prof[i] = 0;
@@ -1127,6 +1128,72 @@ GMX_DEV void ByteBoundary(StreamSmem& s, const Arena& A, const StreamParams& P, 
   GMX_PROF(3);
 }
 
+// Indirect::Learn (x41), Match::Learn (x6) and the history append of BasicContexts::Learn for one bit, one model per lane
+// t = 0 .. NIND + NMATCH. They depend on the bit and on what the lookup phase left in shared memory, not on the mixer
+// outputs, so compress (which knows the bit before it is coded) runs them on the upper warps WHILE warp 0 evaluates the
+// mixer network (PredictBit); everything else runs them at the start of LearnBit.
+enum : int { LEARN_TABLE_LANES = NIND + NMATCH + 1 };
+#if defined(GMX_LT_NOINLINE)
+static GMX_DEV GMX_NOINLINE void LearnTables(StreamSmem& s, const Arena& A, int bit, int t) {
+#else
+GMX_DEV inline void LearnTables(StreamSmem& s, const Arena& A, int bit, int t) {
+#endif
+  const ArenaLayout& L = *A.L;
+  const float fbit = (float)bit;
+  const int cur = s.recent_bits * 2 + bit;
+  const bool byte_done = cur >= 256;
+  const uint32_t longest = s.ctx[C_LONGEST];
+  // history length after BasicContexts::Learn (basic-contexts.cpp:42-54)
+  const uint32_t hist_after = s.hist_len + ((byte_done && longest < 2) ? 1u : 0u);
+  if (t < NIND) {  // Indirect::Learn indirect.cpp:47-70
+    const int k = t;
+    const float lr = s.T.ind[k].slow_lr ? f_div(1.0f, 200.0f) : (float)0.02;
+    float* pr = A.at<float>(L.ind_pred) + k * 512;
+    const uint32_t e = s.ind_state[k];
+    uint32_t ns = e & 0xff;
+    const uint32_t rm = e >> 8;
+    if (ns == 255) ns = 0;
+    const float a = s.ind_pa[k];
+    pr[ns] = f_add(a, f_mul(f_sub(fbit, Logistic(a)), lr));
+    const float b = s.ind_pb[k];
+    pr[256 + rm] = f_add(b, f_mul(f_sub(fbit, Logistic(b)), lr));
+    // RunMap::Next run-map.cpp:3-21
+    uint32_t nrm;
+    if (bit == 0) nrm = rm < 127 ? rm + 1 : rm >= 128 ? 1 : rm;
+    else nrm = rm < 128 ? 128 : rm < 255 ? rm + 1 : rm;
+    const uint32_t nst = s.T.nonstationary[ns * 2 + bit] | (nrm << 8);
+    const uint32_t sid = L.ind_sid[k];
+    if (sid) {
+      uint32_t slot = s.ind_base[k] + s.ctx[C_BIT_CONTEXT];
+      if (slot >= L.ind_size[k]) slot -= L.ind_size[k];
+      SparsePut(A.map(), &s.sparse_used, L.sparse_limit, &s.error, SparseKey(sid, slot), s.ind_slot[k], s.ind_found[k] != 0, nst);
+    } else {
+      A.at<uint16_t>(L.ind_tab[k])[s.ind_slot[k]] = (uint16_t)nst;
+    }
+  } else if (t < NIND + NMATCH) {  // Match::Learn match.cpp:76-109
+    const int k = t - NIND;
+    const uint32_t len = s.m_len[k];
+    if (len > 2) {
+      const int hit = bit == ((s.m_byte[k] & s.m_bitpos[k]) != 0);
+      int* cnt = A.at<int>(L.match_cnt) + k * 256 + len;
+      float* mp = A.at<float>(L.match_pred) + k * 256 + len;
+      float rate = (float)(1.0 / 400);
+      const int c = *cnt;
+      if (c < 400) { *cnt = c + 1; rate = (float)d_div(1.0, (double)(c + 1)); }
+      const float v = *mp;
+      *mp = f_add(v, f_mul(f_sub((float)hit, v), rate));
+    }
+    if (s.recent_bits >= 128 && longest < 2) {
+      const uint32_t idx = s.ctx[s.T.match[k].ctx] & ((1u << s.T.match[k].log2) - 1);
+      if (L.match_sid[k]) SparseSet(A.map(), &s.sparse_used, L.sparse_limit, &s.error, SparseKey(L.match_sid[k], idx), hist_after - 1);
+      else A.at<uint32_t>(L.match_tab[k])[idx] = hist_after - 1;
+    }
+  } else if (t == NIND + NMATCH && byte_done && longest < 2) {
+    if (s.hist_len >= L.history_cap) s.error = GMX_ERR_HISTORY_CAP;
+    else A.at<uint8_t>(L.history)[s.hist_len] = (uint8_t)cur;
+  }
+}
+
 // ---- Predictor::Predict (predictor.cpp:360-376) --------------------------------------------------
 template <int NT, bool PROF>
 // known_byte: the byte whose bits are being predicted if the caller knows it (compress), else -1.
@@ -1445,6 +1512,14 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     }
     GMX_PROF(20);
   }
+#if defined(GMX_NO_CAND_STAGE) && defined(GMX_LEARN_OVERLAP)   // off: measured 2 % slower at 8 CTAs/SM (profiles/r01_s3_ab.md)
+  else if (known_byte >= 0 && tid >= 64 && tid < 64 + LEARN_TABLE_LANES) {
+    // compress: the bit about to be coded is known, so the table models learn it now, under the mixer network
+    const int pos = 31 - __clz(s.recent_bits);   // bits of this byte already perceived
+    LearnTables(s, A, (known_byte >> (7 - pos)) & 1, tid - 64);
+    if (tid == 64) s.tables_done = 1;
+  }
+#endif
 #if !defined(GMX_NO_CAND_STAGE)
   else if (tid >= NT - 32) {
     // Meanwhile the last warp stages, for the four bit-gated mixers, the sets both values of this bit lead to: lanes
@@ -1481,11 +1556,36 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
   GMX_PROF(6);
 }
 
+// ---- coder (encoder.cpp:8-34, decoder.cpp:3-39) ---------------------------------------------------
+GMX_DEV inline uint32_t Discretize(float p) { return (uint32_t)f_add(1.0f, f_mul(65534.0f, p)); }
+
+GMX_DEV inline void PutByte(StreamSmem& s, uint8_t* out, uint32_t b) {
+  if (s.out_pos < s.out_cap) out[s.out_pos] = (uint8_t)b; else s.error = GMX_ERR_OUTPUT_CAP;
+  s.out_pos++;
+}
+GMX_DEV inline uint32_t GetByte(StreamSmem& s, const uint8_t* in) {  // Decoder::ReadByte: 0 past the end
+  const uint32_t b = s.in_pos < s.in_len ? in[s.in_pos] : 0u;
+  s.in_pos++;
+  return b;
+}
+
+// One Encoder::Encode step (encoder.cpp:11-31) with the probability PredictBit left in s.prob.
+GMX_DEV inline void EncodeBit(StreamSmem& s, uint8_t* out, int bit) {
+  const uint32_t p16 = Discretize(s.prob);
+  const uint32_t r = s.x2 - s.x1;
+  const uint32_t xmid = s.x1 + (r >> 16) * p16 + (((r & 0xffff) * p16) >> 16);
+  if (bit) s.x2 = xmid; else s.x1 = xmid + 1;
+  while (((s.x1 ^ s.x2) & 0xff000000u) == 0) { PutByte(s, out, s.x2 >> 24); s.x1 <<= 8; s.x2 = (s.x2 << 8) + 255; }
+}
+
 // ---- Predictor::Learn (predictor.cpp:383-387) ----------------------------------------------------
 template <int NT, bool PROF>
-GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int tid) {
+// known_bit >= 0 (compress): the caller has not stored s.new_bit and not run the coder yet; both happen here, on lanes
+// that are otherwise idle in the first phase, which saves the barrier between coding and learning. code_out = the
+// stream's output slice.
+GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int tid, int known_bit = -1, uint8_t* code_out = nullptr) {
   const ArenaLayout& L = *A.L;
-  const int bit = s.new_bit;
+  const int bit = known_bit >= 0 ? known_bit : s.new_bit;
   const float fbit = (float)bit;
   const int cur = s.recent_bits * 2 + bit;
   const bool byte_done = cur >= 256;
@@ -1511,52 +1611,11 @@ GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int 
     s.set_steps[m] = nsteps;
     if (nsteps > mx) s.max_steps[m] = nsteps;
     s.shrink[m] = (nsteps & 1023u) == 0;
-  } else if (tid >= 64 && tid < 64 + NIND) {  // Indirect::Learn indirect.cpp:47-70
-    const int k = tid - 64;
-    const float lr = s.T.ind[k].slow_lr ? f_div(1.0f, 200.0f) : (float)0.02;
-    float* pr = A.at<float>(L.ind_pred) + k * 512;
-    const uint32_t e = s.ind_state[k];
-    uint32_t ns = e & 0xff;
-    const uint32_t rm = e >> 8;
-    if (ns == 255) ns = 0;
-    const float a = s.ind_pa[k];
-    pr[ns] = f_add(a, f_mul(f_sub(fbit, Logistic(a)), lr));
-    const float b = s.ind_pb[k];
-    pr[256 + rm] = f_add(b, f_mul(f_sub(fbit, Logistic(b)), lr));
-    // RunMap::Next run-map.cpp:3-21
-    uint32_t nrm;
-    if (bit == 0) nrm = rm < 127 ? rm + 1 : rm >= 128 ? 1 : rm;
-    else nrm = rm < 128 ? 128 : rm < 255 ? rm + 1 : rm;
-    const uint32_t nst = s.T.nonstationary[ns * 2 + bit] | (nrm << 8);
-    const uint32_t sid = L.ind_sid[k];
-    if (sid) {
-      uint32_t slot = s.ind_base[k] + s.ctx[C_BIT_CONTEXT];
-      if (slot >= L.ind_size[k]) slot -= L.ind_size[k];
-      SparsePut(A.map(), &s.sparse_used, L.sparse_limit, &s.error, SparseKey(sid, slot), s.ind_slot[k], s.ind_found[k] != 0, nst);
-    } else {
-      A.at<uint16_t>(L.ind_tab[k])[s.ind_slot[k]] = (uint16_t)nst;
-    }
-  } else if (tid >= 40 && tid < 40 + NMATCH) {  // Match::Learn match.cpp:76-109
-    const int k = tid - 40;
-    const uint32_t len = s.m_len[k];
-    if (len > 2) {
-      const int hit = bit == ((s.m_byte[k] & s.m_bitpos[k]) != 0);
-      int* cnt = A.at<int>(L.match_cnt) + k * 256 + len;
-      float* mp = A.at<float>(L.match_pred) + k * 256 + len;
-      float rate = (float)(1.0 / 400);
-      const int c = *cnt;
-      if (c < 400) { *cnt = c + 1; rate = (float)d_div(1.0, (double)(c + 1)); }
-      const float v = *mp;
-      *mp = f_add(v, f_mul(f_sub((float)hit, v), rate));
-    }
-    if (s.recent_bits >= 128 && longest < 2) {
-      const uint32_t idx = s.ctx[s.T.match[k].ctx] & ((1u << s.T.match[k].log2) - 1);
-      if (L.match_sid[k]) SparseSet(A.map(), &s.sparse_used, L.sparse_limit, &s.error, SparseKey(L.match_sid[k], idx), hist_after - 1);
-      else A.at<uint32_t>(L.match_tab[k])[idx] = hist_after - 1;
-    }
-  } else if (tid == 48 && byte_done && longest < 2) {
-    if (s.hist_len >= L.history_cap) s.error = GMX_ERR_HISTORY_CAP;
-    else A.at<uint8_t>(L.history)[s.hist_len] = (uint8_t)cur;
+  } else if (tid >= 64 && tid < 64 + LEARN_TABLE_LANES) {
+    if (!s.tables_done) LearnTables(s, A, bit, tid - 64);
+  } else if (tid == NT - 1 && known_bit >= 0) {   // Encoder::Encode encoder.cpp:8-34 (+ Perceive: predictor.cpp:378-381)
+    EncodeBit(s, code_out, bit);
+    s.new_bit = bit;
   }
   BlockSync();
   GMX_PROF(8);
@@ -1599,23 +1658,10 @@ GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int 
       }
     }
   }
-  if (tid == 0) { s.steps++; s.hist_len = hist_after; }
+  if (tid == 0) { s.steps++; s.hist_len = hist_after; s.tables_done = 0; }
   BlockSync();
   GMX_PROF(9);
   if (byte_done) LstmPerceive<NT, PROF>(s, A, P, (uint32_t)(cur - 256), tid);  // LstmModel::Learn lstm-model.cpp:50-59
-}
-
-// ---- coder (encoder.cpp:8-34, decoder.cpp:3-39) ---------------------------------------------------
-GMX_DEV inline uint32_t Discretize(float p) { return (uint32_t)f_add(1.0f, f_mul(65534.0f, p)); }
-
-GMX_DEV inline void PutByte(StreamSmem& s, uint8_t* out, uint32_t b) {
-  if (s.out_pos < s.out_cap) out[s.out_pos] = (uint8_t)b; else s.error = GMX_ERR_OUTPUT_CAP;
-  s.out_pos++;
-}
-GMX_DEV inline uint32_t GetByte(StreamSmem& s, const uint8_t* in) {  // Decoder::ReadByte: 0 past the end
-  const uint32_t b = s.in_pos < s.in_len ? in[s.in_pos] : 0u;
-  s.in_pos++;
-  return b;
 }
 
 static GMX_DEV GMX_NOINLINE void Trace(StreamSmem& s, const StreamParams& P, uint64_t bit_index) {
@@ -1676,18 +1722,12 @@ GMX_DEV void CompressStream(StreamSmem& s, const Arena& A, const StreamParams& P
     for (int j = 7; j >= 0; --j) {
       const int bit = (c >> j) & 1;
       PredictBit<NT, PROF>(s, A, P, (int)c, tid);
-      if (tid == 0) {
-        if (tracing) Trace(s, P, pos * 8 + (7 - j));
-        const uint32_t p16 = Discretize(s.prob);
-        const uint32_t r = s.x2 - s.x1;
-        const uint32_t xmid = s.x1 + (r >> 16) * p16 + (((r & 0xffff) * p16) >> 16);
-        if (bit) s.x2 = xmid; else s.x1 = xmid + 1;
-        while (((s.x1 ^ s.x2) & 0xff000000u) == 0) { PutByte(s, out, s.x2 >> 24); s.x1 <<= 8; s.x2 = (s.x2 << 8) + 255; }
-        s.new_bit = bit;
+      if (tracing && (P.bit_trace || P.pred_trace)) {   // debug/parity traces of stream 0 read the blackboard before Learn touches it
+        if (tid == 0) Trace(s, P, pos * 8 + (7 - j));
+        BlockSync();
       }
-      BlockSync();
       GMX_PROF(7);
-      LearnBit<NT, PROF>(s, A, P, tid);
+      LearnBit<NT, PROF>(s, A, P, tid, bit, out);   // codes the bit (lane NT-1) and learns it
       if (s.error) break;
     }
     if (s.error) break;
