@@ -250,6 +250,22 @@ GMX_DEV inline uint32_t Murmur64(uint64_t v) {
 }
 GMX_DEV inline uint32_t Murmur32(uint32_t v) { return MurmurFinal(MurmurMix(0xDEADBEEFu, v), 4); }
 
+// L2 eviction-priority hints (createpolicy): the gate weights of the resident streams alone are almost twice the L2, so
+// they are marked evict-first; what the per-bit path re-reads (logit maps, sparse-map lines) can be marked evict-last.
+GMX_DEV inline uint64_t PolicyEvictFirst() {
+#if defined(__CUDA_ARCH__)
+  uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+#else
+  return 0;
+#endif
+}
+GMX_DEV inline uint64_t PolicyEvictLast() {
+#if defined(__CUDA_ARCH__)
+  uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+#else
+  return 0;
+#endif
+}
 // ---- shared sparse map (exact: keyed by table id + full index, linear probing, never deletes) ----
 GMX_DEV inline uint32_t SparseKey(uint32_t sid, uint32_t index) { return (sid << 25) | index; }
 GMX_DEV inline uint32_t SparseHash(uint32_t k) {
@@ -260,7 +276,16 @@ GMX_DEV inline uint32_t SparseHash(uint32_t k) {
 GMX_DEV inline uint32_t SparseFind(const SparseMap& M, uint32_t key, unsigned long long* entry) {
   uint32_t pos = SparseHash(key) & M.mask;
   for (;;) {
+#if (defined(GMX_SPARSE_EVICT_LAST) || defined(GMX_SPARSE_EVICT_FIRST)) && defined(__CUDA_ARCH__)
+    unsigned long long e;
+#if defined(GMX_SPARSE_EVICT_LAST)
+    { const uint64_t pol = PolicyEvictLast(); asm volatile("ld.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(e) : "l"(M.tab + pos), "l"(pol) : "memory"); }
+#else
+    { const uint64_t pol = PolicyEvictFirst(); asm volatile("ld.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(e) : "l"(M.tab + pos), "l"(pol) : "memory"); }
+#endif
+#else
     const unsigned long long e = M.tab[pos];
+#endif
     if (e == 0ull || (uint32_t)(e >> 32) == key) { *entry = e; return pos; }
     pos = (pos + 1) & M.mask;
   }
@@ -318,6 +343,28 @@ GMX_DEV inline void CpAsync16(void* smem_dst, const void* gmem_src) {   // both 
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 #else
   memcpy(smem_dst, gmem_src, 16);
+#endif
+}
+GMX_DEV inline void CpAsync16Hint(void* smem_dst, const void* gmem_src, uint64_t policy) {
+#if defined(__CUDA_ARCH__)
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "l"(policy) : "memory");
+#else
+  (void)policy; memcpy(smem_dst, gmem_src, 16);
+#endif
+}
+GMX_DEV inline float LoadHint(const float* p, uint64_t policy) {
+#if defined(__CUDA_ARCH__)
+  float v; asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(policy) : "memory"); return v;
+#else
+  (void)policy; return *p;
+#endif
+}
+GMX_DEV inline void StoreHint(float* p, float v, uint64_t policy) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(policy) : "memory");
+#else
+  (void)policy; *p = v;
 #endif
 }
 GMX_DEV inline void CpAsyncCommit() {
@@ -514,10 +561,18 @@ GMX_DEV void LstmOutputStep(StreamSmem& s, const Arena& A, uint32_t last, uint32
 #pragma unroll 13
     for (int j = j0; j < j1; ++j) {
       const float h = s.l_hidden[j];
+#if defined(GMX_WOUT_PLAIN)
+      float4 w = wl4[j * (L_NOUT / 4)];
+#else
       float4 w = LoadStream4(wl4 + j * (L_NOUT / 4));
+#endif
       w.x = f_sub(w.x, f_mul(le[0], h)); w.y = f_sub(w.y, f_mul(le[1], h));
       w.z = f_sub(w.z, f_mul(le[2], h)); w.w = f_sub(w.w, f_mul(le[3], h));
+#if defined(GMX_WOUT_PLAIN)
+      wc4[j * (L_NOUT / 4)] = w;
+#else
       StoreStream4(wc4 + j * (L_NOUT / 4), w);
+#endif
     }
   }
 }
@@ -567,11 +622,17 @@ GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, i
     // touches its own slots.
     constexpr int NQ = L_NOUT / 4 + L_CELLS / 4 + 1, HALF = 3 * L_CELLS / 2;
     float4* ring = (float4*)s.w;
+#if !defined(GMX_NO_GATES_EVICT_FIRST)
+    const uint64_t pol = PolicyEvictFirst();
+#define GMX_RING_CP(dst, src) CpAsync16Hint(dst, src, pol)
+#else
+#define GMX_RING_CP(dst, src) CpAsync16(dst, src)
+#endif
     static_assert(LSTM_STAGES * 2 * HALF * 16 <= WTOTAL * 4, "ring does not fit the weight-set staging area");
 #pragma unroll
     for (int q = 0; q < LSTM_STAGES; ++q) {
-      CpAsync16(ring + (q * 2 + 0) * HALF + tid, w0 + q * L_CELLS);
-      CpAsync16(ring + (q * 2 + 1) * HALF + tid, w1 + q * L_CELLS);
+      GMX_RING_CP(ring + (q * 2 + 0) * HALF + tid, w0 + q * L_CELLS);
+      GMX_RING_CP(ring + (q * 2 + 1) * HALF + tid, w1 + q * L_CELLS);
       CpAsyncCommit();
     }
     int st = 0;
@@ -580,8 +641,8 @@ GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, i
       CpAsyncWaitGroup<LSTM_STAGES - 1>();
       const float4 a = ring[(st * 2 + 0) * HALF + tid], b = ring[(st * 2 + 1) * HALF + tid];
       if (q + LSTM_STAGES < NQ) {
-        CpAsync16(ring + (st * 2 + 0) * HALF + tid, w0 + (q + LSTM_STAGES) * L_CELLS);
-        CpAsync16(ring + (st * 2 + 1) * HALF + tid, w1 + (q + LSTM_STAGES) * L_CELLS);
+        GMX_RING_CP(ring + (st * 2 + 0) * HALF + tid, w0 + (q + LSTM_STAGES) * L_CELLS);
+        GMX_RING_CP(ring + (st * 2 + 1) * HALF + tid, w1 + (q + LSTM_STAGES) * L_CELLS);
       }
       CpAsyncCommit();   // one group per iteration, empty at the tail, keeps the wait distance constant
       st = st + 1 == LSTM_STAGES ? 0 : st + 1;
@@ -674,7 +735,11 @@ GMX_UNROLL(GMX_LSTM_UNROLL)
 #pragma unroll 17
     for (int j = 0; j < L_HID; ++j) {
       const float h = s.l_hidden[j];
+#if defined(GMX_WOUT_STREAM)
+      const float4 w = LoadStream4(wo4 + j * (L_NOUT / 4));
+#else
       const float4 w = wo4[j * (L_NOUT / 4)];
+#endif
       a0 = f_add(a0, f_mul(h, w.x)); a1 = f_add(a1, f_mul(h, w.y));
       a2 = f_add(a2, f_mul(h, w.z)); a3 = f_add(a3, f_mul(h, w.w));
     }
@@ -882,8 +947,13 @@ GMX_UNROLL(GMX_BPTT_UNROLL)
     float a[4][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}, {0.0f, 0.0f}, {0.0f, 0.0f}};
 #pragma unroll 4
     for (int ep = L_HORIZON - 1; ep >= 0; --ep) {
+#if defined(GMX_BPTT_STREAM) && defined(__CUDA_ARCH__)
+      const float2 e = __ldcs(e2 + ep * (L_CELLS / 2));
+      const float4 x = __ldcs(x4 + ep * ((L_NIN + 1) / 4));
+#else
       const float2 e = e2[ep * (L_CELLS / 2)];
       const float4 x = x4[ep * ((L_NIN + 1) / 4)];
+#endif
       a[0][0] = f_add(a[0][0], f_mul(e.x, x.x)); a[0][1] = f_add(a[0][1], f_mul(e.y, x.x));
       a[1][0] = f_add(a[1][0], f_mul(e.x, x.y)); a[1][1] = f_add(a[1][1], f_mul(e.y, x.y));
       a[2][0] = f_add(a[2][0], f_mul(e.x, x.z)); a[2][1] = f_add(a[2][1], f_mul(e.y, x.z));
@@ -893,10 +963,18 @@ GMX_UNROLL(GMX_BPTT_UNROLL)
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const size_t f4 = ((size_t)g * L_ROWQ + L_NOUT / 4 + rg) * L_CELLS + 2 * ip + c;
+#if defined(GMX_ADAM_STREAM)
+      float4 w = LoadStream4(W4 + f4), m = LoadStream4(M4 + f4), v = LoadStream4(V4 + f4);
+#else
       float4 w = W4[f4], m = M4[f4], v = V4[f4];
+#endif
       adam1(w.x, m.x, v.x, a[0][c]); adam1(w.y, m.y, v.y, a[1][c]); adam1(w.z, m.z, v.z, a[2][c]);
       if (!pad) adam1(w.w, m.w, v.w, a[3][c]);
+#if defined(GMX_ADAM_STREAM)
+      StoreStream4(W4 + f4, w); StoreStream4(M4 + f4, m); StoreStream4(V4 + f4, v);
+#else
       W4[f4] = w; M4[f4] = m; V4[f4] = v;
+#endif
     }
   }
   for (int t = tid; t < 2 * 3 * L_CELLS; t += NT) {  // gamma then beta (lstm-layer.cpp:349-352)
@@ -1154,9 +1232,16 @@ GMX_DEV inline void LearnTables(StreamSmem& s, const Arena& A, int bit, int t) {
     const uint32_t rm = e >> 8;
     if (ns == 255) ns = 0;
     const float a = s.ind_pa[k];
+#if !defined(GMX_NO_PRED_EVICT_LAST)
+    const uint64_t keep = PolicyEvictLast();
+    StoreHint(pr + ns, f_add(a, f_mul(f_sub(fbit, Logistic(a)), lr)), keep);
+    const float b = s.ind_pb[k];
+    StoreHint(pr + 256 + rm, f_add(b, f_mul(f_sub(fbit, Logistic(b)), lr)), keep);
+#else
     pr[ns] = f_add(a, f_mul(f_sub(fbit, Logistic(a)), lr));
     const float b = s.ind_pb[k];
     pr[256 + rm] = f_add(b, f_mul(f_sub(fbit, Logistic(b)), lr));
+#endif
     // RunMap::Next run-map.cpp:3-21
     uint32_t nrm;
     if (bit == 0) nrm = rm < 127 ? rm + 1 : rm >= 128 ? 1 : rm;
@@ -1259,7 +1344,12 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
     const int pi = s.T.ind[k].pred;
     // both entries are read unconditionally: Indirect::Learn updates exactly these two (a never-seen state learns as
     // state 0, indirect.cpp:52-54) and takes them from shared memory instead of two more dependent global loads
+#if !defined(GMX_NO_PRED_EVICT_LAST)
+    const uint64_t keep = PolicyEvictLast();
+    const float pa = LoadHint(pr + (ns == 255 ? 0 : ns), keep), pb = LoadHint(pr + 256 + rm, keep);
+#else
     const float pa = pr[ns == 255 ? 0 : ns], pb = pr[256 + rm];
+#endif
     s.ind_pa[k] = pa; s.ind_pb[k] = pb;
     if (ns != 255) { s.preds[pi] = pa; s.act[pi] = pa != 0.0f; }
     else { s.act[pi] = 0; if (zero_inactive) s.preds[pi] = 0.0f; }
@@ -1399,7 +1489,11 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
           s.set_pool[m] = nid;
         } else {
           float4* dst = (float4*)(s.w + WOff(m)) + (lane - 1);
+#if defined(GMX_MIX_EVICT_LAST)
+          if (nid) CpAsync16Hint(dst, rec + lane, PolicyEvictLast()); else *dst = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#else
           if (nid) CpAsync16(dst, rec + lane); else *dst = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#endif
         }
       }
     }
