@@ -40,3 +40,16 @@ def test_fixture_generation(work):
     subprocess.run([exe, "generate", str(d / "ckpt600"), os.path.join(GOLD, "ckpt600_prompt.txt"), str(d / "gen.out"), "40", "0.5"],
                    check=True, stderr=subprocess.DEVNULL)
     assert (d / "gen.out").read_bytes() == open(os.path.join(GOLD, "ckpt600_gen_40_0.5.out"), "rb").read()
+
+
+def test_malformed_checkpoints_are_rejected_not_crashed(work):
+    """Truncated or padded files fail Parse with a message (the C ABI turns that into GMX_E_ARG); nothing is read out of bounds."""
+    d, exe = work
+    short, long_ = (d / "ckpt600.short").read_bytes(), (d / "ckpt600.long").read_bytes()
+    cases = {"short_cut": (short[:len(short) // 2], long_), "long_cut": (short, long_[:1000]), "short_pad": (short + b"\0" * 7, long_),
+             "empty": (b"", b""), "long_garbage_count": (short, b"\xff\xff\xff\x7f" + long_[4:])}
+    for name, (s, l) in cases.items():
+        (d / (name + ".short")).write_bytes(s)
+        (d / (name + ".long")).write_bytes(l)
+        r = subprocess.run([exe, "recode", str(d / name), str(d / (name + "_out"))], capture_output=True, text=True)
+        assert r.returncode == 1 and "Parse:" in r.stderr, (name, r.returncode, r.stderr[-200:])

@@ -90,3 +90,28 @@ def test_predictor_facade_reads_and_writes_checkpoints(gpu_ctx, ckpt):
     # the facade ran with analysis on (inactive predictions are zeroed each Predict, predictor.cpp:362-365), the
     # training pass with analysis off (they keep their last value): ShortTermMemory::predictions legitimately differs
     assert set(ckpt_layout.differing_sections(sh, sh_ref)) <= ckpt_layout.SCRATCH | {"stm.predictions"}
+
+
+def test_training_on_incompressible_data_takes_the_worst_case_arena(gpu_ctx, tmp_path):
+    """Random bytes overflow the text-sized arena; gmx_train_checkpoint re-runs the stream in one worst-case arena and
+    the checkpoint still matches what the unmodified reference writes for the same bytes (oracle/_ref, when present)."""
+    import subprocess
+    import numpy as np
+    import gmix_b200
+    data = np.random.RandomState(11).randint(0, 256, 3000, dtype=np.uint8).tobytes()
+    before = gpu_ctx.retried_streams
+    sh, lo = gpu_ctx.train_checkpoint(data)
+    assert gpu_ctx.retried_streams == before + 1
+    m = gmix_b200.Model(gpu_ctx, sh, lo, max_new_bytes=600, roomy=True)      # loads back and continues
+    assert m.trained_bytes == 3000
+    comp = gpu_ctx.compress_batch_from(m, [data[:500]])
+    assert gpu_ctx.decompress_batch_from(m, comp) == [data[:500]]
+    m.close()
+    assert gpu_ctx.compress_batch([B]) == gpu_ctx.compress_batch([B])          # the context is back to from-scratch streams
+    ref = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "ref_driver")
+    if os.path.exists(ref):
+        (tmp_path / "r.in").write_bytes(data)
+        subprocess.run([ref, "train", str(tmp_path / "r.in"), str(tmp_path / "ref")], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        assert (tmp_path / "ref.long").read_bytes() == lo
+        diff = ckpt_layout.differing_sections(sh, (tmp_path / "ref.short").read_bytes())
+        assert set(diff) <= ckpt_layout.SCRATCH, diff
