@@ -22,7 +22,11 @@ def test_runner_help_and_argument_errors():
     r = subprocess.run([RUNNER], capture_output=True, text=True)
     assert r.returncode != 0 and "Compress" in r.stdout
     r = subprocess.run([RUNNER, "-g", "ckpt", "prompt", "out", "10", "1.0"], capture_output=True, text=True)
-    assert r.returncode != 0 and "not available" in r.stdout
+    assert r.returncode != 0 and "Can not open: prompt" in r.stdout          # reference wording, runner-utils.cpp:164
+    r = subprocess.run([RUNNER, "-g", "ckpt", "prompt", "out"], capture_output=True, text=True)
+    assert r.returncode != 0 and "Wrong number of arguments" in r.stdout     # runner.cpp:41
+    r = subprocess.run([RUNNER, "-t", "a", "b", "c", "d"], capture_output=True, text=True)
+    assert r.returncode != 0 and "Wrong number of arguments" in r.stdout
     r = subprocess.run([RUNNER, "-c", "/nonexistent/in", "/tmp/out"], capture_output=True, text=True)
     assert r.returncode != 0 and "Error opening" in r.stdout
 
