@@ -51,6 +51,17 @@ enum : int { WSTRIDE0 = 132, WSTRIDE1 = 36, WTOTAL = 24 * WSTRIDE0 + 9 * WSTRIDE
 // Perceive and between BPTT epochs) all LOSE 0.5-2.4 % each with 8 CTAs per SM (A/B in profiles/r01_s3_ab.md): the other
 // resident streams already cover the latency and the extra requests only queue in front of demand loads. They stay
 // available as GMX_PF_* build flags for low-occupancy use.
+// GMX_NEW_FRONT (experimental, OFF): gate selection and weight-set swaps on the last warp during the lookup phase
+// (MixerFrontEarly / MixerFrontLate). +1.3 % at 8 CTAs/SM and bit-exact under the CPU emulator and on the golden vectors
+// on the GPU, but tests/test_gpu_configs.py::test_config2 (300 x 8 KiB) diverges from the oracle on the GPU: an
+// ordering problem between the asynchronous set copies and another phase that the synchronous emulator cannot
+// show. Kept out of the product build until found.
+#if !defined(GMX_NEW_FRONT) && !defined(GMX_OLD_FRONT)
+#define GMX_OLD_FRONT 1
+#endif
+#if defined(GMX_CAND_STAGE) && !defined(GMX_OLD_FRONT)
+#define GMX_OLD_FRONT 1       // candidate staging belongs to the old gate-selection / swap phases
+#endif
 #if !defined(GMX_CAND_STAGE)
 #define GMX_NO_CAND_STAGE 1   // staging both candidate weight sets one bit ahead wins 11 % at 1 CTA/SM and loses 2 % at 8 (A/B in profiles/)
 #endif
@@ -1279,6 +1290,85 @@ GMX_DEV inline void LearnTables(StreamSmem& s, const Arena& A, int bit, int t) {
   }
 }
 
+// ---- mixer front end on the last warp ------------------------------------------------------------------------
+// Gate selection (mixer.cpp:29-37) and the weight-set swaps it triggers need nothing from this bit's table lookups,
+// except for the two mixers gated by longest_match (m = 6 and m = NL0 + 6, which wait for Match::Predict). The last
+// warp therefore runs them DURING the lookup phase: directory loads, write-backs and the asynchronous fetches of
+// the new sets overlap the sparse-map probes of the other warps, and the copies are only awaited after the barrier.
+GMX_DEV inline bool LongestGated(int m) { return m == 6 || m == NL0 + 6; }
+GMX_DEV inline int FrontMixer(int lane) { return lane < 6 ? lane : lane < 29 ? lane + 1 : lane + 2; }   // the 31 others, lane 0..30
+
+// One weight set, all 32 lanes with the same arguments: staged set -> its pool record `old` (0 = none), then record
+// `nid` (0 = no set yet: zeros) -> staging area, asynchronously.
+GMX_DEV inline void SwapSet(StreamSmem& s, const Arena& A, int m, uint32_t old, uint32_t nid, int lane) {
+  const ArenaLayout& L = *A.L;
+  float4* pool = A.at<float4>(L.mix_pool);
+  const uint32_t stride4 = L.mix_set_stride / 4;
+  float4* w4 = (float4*)(s.w + WOff(m));
+  if (lane <= (MixerNW(m) + 3) / 4) {
+    if (old) {
+      float4* rec = pool + (size_t)old * stride4;
+      if (lane == 0) rec[0] = make_float4(u2f(s.set_steps[m]), 0.0f, 0.0f, 0.0f);
+      else rec[lane] = w4[lane - 1];
+    }
+    const float4* rec = pool + (size_t)nid * stride4;
+    if (lane == 0) {
+      if (nid) CpAsync4(&s.set_steps[m], rec); else s.set_steps[m] = 0u;
+      s.set_pool[m] = nid;
+    } else {
+      if (nid) CpAsync16(w4 + (lane - 1), rec + lane); else w4[lane - 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+  }
+}
+
+// Lookup phase, last warp: the 31 mixers not gated by longest_match.
+GMX_DEV inline void MixerFrontEarly(StreamSmem& s, const Arena& A, int lane) {
+  const ArenaLayout& L = *A.L;
+  int m = 0;
+  uint32_t old = 0, nid = 0;
+  bool changed = false;
+  if (lane < NMIX - 2) {
+    m = FrontMixer(lane);
+    const uint32_t idx = s.ctx[s.T.mixer[m].ctx] & ((1u << s.T.mixer[m].log2) - 1);
+    changed = idx != s.set_idx[m];
+    if (changed) {
+      old = s.set_pool[m];
+      nid = A.at<uint32_t>(L.mix_dir[m])[idx];
+      s.set_idx[m] = idx;
+    }
+  }
+  unsigned todo = __ballot_sync(0xffffffffu, changed);
+  while (todo) {
+    const int src = __ffs((int)todo) - 1;
+    todo &= todo - 1;
+    SwapSet(s, A, __shfl_sync(0xffffffffu, m, src), __shfl_sync(0xffffffffu, old, src), __shfl_sync(0xffffffffu, nid, src), lane);
+  }
+}
+
+// After the lookup barrier, last warp: longest_match context, its two mixers, then wait for every copy of this bit.
+GMX_DEV inline void MixerFrontLate(StreamSmem& s, const Arena& A, int lane) {
+  const ArenaLayout& L = *A.L;
+  uint32_t c = 0;   // longest_match = max(match_length / 32) (match.cpp:71-73)
+#pragma unroll 1
+  for (int k = 0; k < NMATCH; ++k) { const uint32_t v = s.m_len[k] >> 5; c = v > c ? v : c; }
+#pragma unroll 1
+  for (int i = 0; i < 2; ++i) {
+    const int m = i ? NL0 + 6 : 6;
+    const uint32_t idx = c & ((1u << s.T.mixer[m].log2) - 1);
+    const bool changed = idx != s.set_idx[m];            // same answer on every lane
+    const uint32_t old = s.set_pool[m];
+    __syncwarp();
+    if (changed) {
+      const uint32_t nid = A.at<uint32_t>(L.mix_dir[m])[idx];
+      if (lane == 0) s.set_idx[m] = idx;
+      SwapSet(s, A, m, old, nid, lane);
+    }
+    __syncwarp();
+  }
+  if (lane == 0) s.ctx[C_LONGEST] = c;
+  CpAsyncWaitAll();
+}
+
 // ---- Predictor::Predict (predictor.cpp:360-376) --------------------------------------------------
 template <int NT, bool PROF>
 // known_byte: the byte whose bits are being predicted if the caller knows it (compress), else -1.
@@ -1389,14 +1479,16 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
       s.act[pi] = 0;
       if (zero_inactive) s.preds[pi] = 0.0f;
     }
-  } else if (tid >= 98 && s.recent_bits >= 128) {
-    // last bit of the byte: Lstm::Perceive will copy + update the output layer of the epoch slot just used
-    const uint32_t last = s.l_epoch == 0 ? L_HORIZON - 1 : s.l_epoch - 1;
-#if defined(GMX_PF_WOUT_LAST)
-    PrefetchRange(A.at<float>(L.l_wout) + (size_t)last * L_HID * L_NOUT, L_HID * L_NOUT * 4, tid - 98, NT - 98);
-#endif
-  } else if (tid == 96 || tid == 97) {  // per-bit part of ModPPMD / LstmModel::Predict
+  }
+#if !defined(GMX_OLD_FRONT)
+  else if (tid >= NT - 32) {
+    MixerFrontEarly(s, A, tid - (NT - 32));
+  } else if (tid == 70 || tid == 71) {  // per-bit part of ModPPMD / LstmModel::Predict
+    const int which = tid - 70;
+#else
+  else if (tid == 96 || tid == 97) {  // per-bit part of ModPPMD / LstmModel::Predict
     const int which = tid - 96;
+#endif
     uint32_t fl;
     const float val = IntervalNode(which ? s.lprob : s.ppm, s.recent_bits, &fl);
     if (fl & 1) { s.preds[which] = val; s.act[which] = (fl >> 1) & 1; }
@@ -1404,6 +1496,17 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
   }
   BlockSync();
   GMX_PROF(4);
+#if !defined(GMX_OLD_FRONT)
+  if (tid >= NT - 32) {
+    MixerFrontLate(s, A, tid - (NT - 32));
+  } else if (tid >= 64 && tid < 96) {
+    // layer-0 input vector: the active predictions, inactive ones as +0 (Mixer::Predict sums the active ones
+    // in index order; a +-0 product leaves the running sum unchanged, the sum itself is never -0)
+    for (int i = tid - 64; i < NPRED; i += 32) s.xe[i] = s.act[i] ? s.preds[i] : 0.0f;
+  }
+  BlockSync();
+  GMX_PROF(16);
+#else
   // Mixer gate selection (mixer.cpp:29-37): which weight set does each mixer need for this bit?
   if (tid < NMIX) {
     const int m = tid;
@@ -1501,6 +1604,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, in
   }
   BlockSync();
   GMX_PROF(5);
+#endif
   // Mixer::Predict (mixer.cpp:51-106): warp 0, one lane per neuron, sequential sums, the serial
   // same-layer chain is resolved by warp shuffles in neuron order.
   if (tid < 32) {
