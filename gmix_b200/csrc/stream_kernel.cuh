@@ -344,6 +344,8 @@ GMX_DEV inline void CpAsync4(void* smem_dst, const void* gmem_src) {
 #if defined(__CUDA_ARCH__)
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+#elif defined(GMX_EMU_DEFER_CP)
+  cuda_emu::CpAsyncIssue(smem_dst, gmem_src, 4);
 #else
   *(uint32_t*)smem_dst = *(const uint32_t*)gmem_src;
 #endif
@@ -352,6 +354,8 @@ GMX_DEV inline void CpAsync16(void* smem_dst, const void* gmem_src) {   // both 
 #if defined(__CUDA_ARCH__)
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+#elif defined(GMX_EMU_DEFER_CP)
+  cuda_emu::CpAsyncIssue(smem_dst, gmem_src, 16);
 #else
   memcpy(smem_dst, gmem_src, 16);
 #endif
@@ -360,6 +364,8 @@ GMX_DEV inline void CpAsync16Hint(void* smem_dst, const void* gmem_src, uint64_t
 #if defined(__CUDA_ARCH__)
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "l"(policy) : "memory");
+#elif defined(GMX_EMU_DEFER_CP)
+  (void)policy; cuda_emu::CpAsyncIssue(smem_dst, gmem_src, 16);
 #else
   (void)policy; memcpy(smem_dst, gmem_src, 16);
 #endif
@@ -381,17 +387,23 @@ GMX_DEV inline void StoreHint(float* p, float v, uint64_t policy) {
 GMX_DEV inline void CpAsyncCommit() {
 #if defined(__CUDA_ARCH__)
   asm volatile("cp.async.commit_group;" ::: "memory");
+#elif defined(GMX_EMU_DEFER_CP)
+  cuda_emu::CpAsyncCommitGroup();
 #endif
 }
 template <int N>
 GMX_DEV inline void CpAsyncWaitGroup() {   // at most N of this thread's most recent groups still pending
 #if defined(__CUDA_ARCH__)
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#elif defined(GMX_EMU_DEFER_CP)
+  cuda_emu::CpAsyncWaitGroupN(N);
 #endif
 }
 GMX_DEV inline void CpAsyncWaitAll() {
 #if defined(__CUDA_ARCH__)
   asm volatile("cp.async.wait_all;" ::: "memory");
+#elif defined(GMX_EMU_DEFER_CP)
+  cuda_emu::CpAsyncWaitEverything();
 #endif
 }
 GMX_DEV inline void PrefetchL2(const void* p) {

@@ -96,9 +96,18 @@ inline void RunBlock(unsigned nthreads, unsigned block_idx, unsigned grid_dim, s
   }
   Block* saved = B();
   B() = &blk;
+  // EMU_ORDER=reverse / EMU_ORDER=shuffle<seed>: other legal interleavings of the threads between two barriers
+  // (default: ascending thread id), to flush out races inside a phase.
+  const char* order = getenv("EMU_ORDER");
+  const bool reverse = order && order[0] == 'r';
+  uint64_t rng = order && order[0] == 's' ? 0x9E3779B97F4A7C15ull * (uint64_t)(atoi(order + 7) + 1) : 0;
+  std::vector<unsigned> perm(nthreads);
+  for (unsigned t = 0; t < nthreads; ++t) perm[t] = reverse ? nthreads - 1 - t : t;
   for (;;) {
     bool any = false;
-    for (unsigned t = 0; t < nthreads; ++t) {
+    if (rng) for (unsigned t = nthreads - 1; t > 0; --t) { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; std::swap(perm[t], perm[rng % (t + 1)]); }
+    for (unsigned k = 0; k < nthreads; ++k) {
+      const unsigned t = perm[k];
       Fiber& f = blk.fibers[t];
       if (f.done) continue;
       any = true;
@@ -138,6 +147,26 @@ inline T Shfl(T v, unsigned src_lane) {
   T out; memcpy(&out, &slots[src_lane % 32], sizeof(T));
   return out;
 }
+
+// cp.async emulation. Default: the copy happens at issue (earliest legal moment). With GMX_EMU_DEFER_CP the copy
+// happens when the issuing thread WAITS for it (latest legal moment) and reads global memory as it is then: code
+// that is only correct for one of the two timings has an ordering bug the synchronous emulation would hide.
+struct PendingCopy { void* dst; const void* src; unsigned bytes; unsigned group; };
+struct CpState { std::vector<PendingCopy> pending; unsigned open_group = 0; };
+inline CpState& Cp() { static std::vector<CpState> v(2048); return v[B()->cur->tid]; }
+inline void CpAsyncIssue(void* dst, const void* src, unsigned bytes) { CpState& c = Cp(); c.pending.push_back(PendingCopy{dst, src, bytes, c.open_group}); }
+inline void CpAsyncCommitGroup() { Cp().open_group++; }
+inline void CpAsyncComplete(unsigned first_pending_group) {   // runs every copy of a group < first_pending_group
+  CpState& c = Cp();
+  size_t keep = 0;
+  for (size_t i = 0; i < c.pending.size(); ++i) {
+    if (c.pending[i].group < first_pending_group) memcpy(c.pending[i].dst, c.pending[i].src, c.pending[i].bytes);
+    else c.pending[keep++] = c.pending[i];
+  }
+  c.pending.resize(keep);
+}
+inline void CpAsyncWaitGroupN(unsigned n) { CpState& c = Cp(); CpAsyncComplete(c.open_group > n ? c.open_group - n : 0); }
+inline void CpAsyncWaitEverything() { CpAsyncComplete(0xffffffffu); }
 
 struct ThreadIdxProxy { unsigned y = 0, z = 0; struct X { operator unsigned() const { return B()->cur->tid; } } x; };
 struct BlockIdxProxy { unsigned y = 0, z = 0; struct X { operator unsigned() const { return B()->block_idx; } } x; };

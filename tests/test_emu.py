@@ -27,3 +27,27 @@ def test_emulated_kernel_matches_reference_stream(emu, tmp_path, name):
     back = str(tmp_path / "back")
     subprocess.run([emu, "decompress", out, back], check=True)
     assert open(back, "rb").read() == open(os.path.join(GOLD, name + ".in"), "rb").read()
+
+
+@pytest.fixture(scope="module")
+def emu_deferred(tmp_path_factory):
+    """Same kernel source, cp.async emulated at its LATEST legal moment (the copy runs when the issuing thread waits
+    for it, tests/emu/cuda_emu.h) instead of the earliest: together with the default build this brackets the
+    timing freedom the hardware has."""
+    exe = str(tmp_path_factory.mktemp("emu_defer") / "emu_main")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-w", "-DGMX_EMU_DEFER_CP", "-o", exe, os.path.join(HERE, "emu", "emu_main.cpp")], check=True)
+    return exe
+
+
+@pytest.mark.parametrize("order", ["", "reverse", "shuffle5"])
+def test_kernel_is_insensitive_to_copy_timing_and_thread_interleaving(emu_deferred, tmp_path, order):
+    env = dict(os.environ)
+    if order:
+        env["EMU_ORDER"] = order     # threads between two barriers scheduled in another legal order
+    for name in ("text1k", "repetitive"):
+        out = str(tmp_path / (name + ".out"))
+        subprocess.run([emu_deferred, "compress", os.path.join(GOLD, name + ".in"), out], check=True, env=env, stderr=subprocess.DEVNULL)
+        assert open(out, "rb").read() == open(os.path.join(GOLD, name + ".gmix"), "rb").read(), (name, order)
+    back = str(tmp_path / "back")
+    subprocess.run([emu_deferred, "decompress", os.path.join(GOLD, "text1k.gmix"), back], check=True, env=env, stderr=subprocess.DEVNULL)
+    assert open(back, "rb").read() == open(os.path.join(GOLD, "text1k.in"), "rb").read()
