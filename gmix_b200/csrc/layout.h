@@ -26,7 +26,9 @@ struct Preload {
 // roomy = false: the shared sparse map and the mixer weight-set pool are sized for what text-like data
 // touches (a stream that needs more ends with GMX_ERR_SPARSE_FULL / GMX_ERR_MIXER_POOL and the host
 // re-runs it in a roomy arena); roomy = true: both are sized for the worst case of max_len bytes.
-inline ArenaLayout MakeLayout(uint64_t max_len, bool roomy = false, const Preload* pre = nullptr) {
+// force_dense: every table as a dense array whatever the stream length (what long streams get automatically); used by
+// tests to exercise that path on short inputs.
+inline ArenaLayout MakeLayout(uint64_t max_len, bool roomy = false, const Preload* pre = nullptr, bool force_dense = false) {
   const Preload none;
   if (!pre) pre = &none;
   static const IndirectSpec ind[NIND] = {GMX_INDIRECT_SPECS};
@@ -66,7 +68,7 @@ inline ArenaLayout MakeLayout(uint64_t max_len, bool roomy = false, const Preloa
   uint64_t cap = Pow2Ceil(roomy ? worst * 4 / 3 + 64 : (uint64_t)(typical * 4.0 / 3.0) + pre->sparse_entries * 4 / 3 + 64);
   const uint64_t cap_worst = Pow2Ceil(worst * 4 / 3 + 64);
   if (cap > cap_worst) cap = cap_worst;
-  if (cap * 8 >= dense_bytes || cap > (1ull << 31)) {  // long streams: the dense tables are smaller
+  if (force_dense || cap * 8 >= dense_bytes || cap > (1ull << 31)) {  // long streams: the dense tables are smaller
     for (int k = 0; k < NIND; ++k) L.ind_sid[k] = 0;
     for (int k = 0; k < NMATCH; ++k) L.match_sid[k] = 0;
     for (int k = 0; k < NIH; ++k) L.ih_sid[k] = 0;

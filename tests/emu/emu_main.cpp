@@ -52,7 +52,7 @@ static int Execute(Run& R, int mode, const gmx::ckpt::Image* ckpt, uint64_t new_
   gmx::Preload pre;
   if (ckpt) pre = gmx::ckpt::Count(*ckpt);
 retry:
-  R.L = gmx::MakeLayout(new_bytes, roomy, ckpt ? &pre : nullptr);
+  R.L = gmx::MakeLayout(new_bytes, roomy, ckpt ? &pre : nullptr, getenv("EMU_DENSE") != nullptr);
   R.arena.assign(R.L.total + 256, 0);
   gmx::FillDecayTable(R.decay, pre.steps + new_bytes * 8 + 16);
   gmx::FillAdamTable(R.adam);

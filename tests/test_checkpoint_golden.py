@@ -53,3 +53,18 @@ def test_malformed_checkpoints_are_rejected_not_crashed(work):
         (d / (name + ".long")).write_bytes(l)
         r = subprocess.run([exe, "recode", str(d / name), str(d / (name + "_out"))], capture_output=True, text=True)
         assert r.returncode == 1 and "Parse:" in r.stderr, (name, r.returncode, r.stderr[-200:])
+
+
+def test_dense_table_layout_with_checkpoints(work):
+    """Long streams get dense tables instead of the shared sparse map (layout.h); forced here on short inputs
+    (EMU_DENSE): compress from scratch, load a reference checkpoint, continue, and write one back."""
+    d, exe = work
+    env = dict(os.environ, EMU_DENSE="1")
+    subprocess.run([exe, "compress", os.path.join(GOLD, "short124.in"), str(d / "d.gmix")], check=True, env=env, stderr=subprocess.DEVNULL)
+    assert (d / "d.gmix").read_bytes() == open(os.path.join(GOLD, "short124.gmix"), "rb").read()
+    subprocess.run([exe, "resume", str(d / "ckpt600"), str(d / "b.in"), str(d / "bd.gmix")], check=True, env=env, stderr=subprocess.DEVNULL)
+    assert (d / "bd.gmix").read_bytes() == open(os.path.join(GOLD, "ckpt600_b.gmix"), "rb").read()
+    a = open(os.path.join(GOLD, "text1k.in"), "rb").read()[:600]
+    (d / "a.in").write_bytes(a)
+    subprocess.run([exe, "train", str(d / "a.in"), str(d / "dense_ck")], check=True, env=env, stderr=subprocess.DEVNULL)
+    assert (d / "dense_ck.long").read_bytes() == (d / "ckpt600.long").read_bytes()
