@@ -51,3 +51,21 @@ def test_kernel_is_insensitive_to_copy_timing_and_thread_interleaving(emu_deferr
     back = str(tmp_path / "back")
     subprocess.run([emu_deferred, "decompress", os.path.join(GOLD, "text1k.gmix"), back], check=True, env=env, stderr=subprocess.DEVNULL)
     assert open(back, "rb").read() == open(os.path.join(GOLD, "text1k.in"), "rb").read()
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_driver")), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("name", ["short124", "text1k"])     # analysis off (< 125 B) and on
+def test_full_blackboard_trace_matches_the_live_reference(emu, tmp_path, name):
+    """Per bit: Predict()'s probability, the coder's 16-bit probability, all 90 stretched predictions, the active-model
+    mask and the 24 + 8 + 1 mixer outputs of the product kernel are bit-identical to the unmodified reference's
+    (oracle/_ref/ref_driver trace level 2): this pins the model graph and the order of every model, not just the bytes."""
+    import numpy as np
+    src = os.path.join(GOLD, name + ".in")
+    subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_driver"), "trace", src, str(tmp_path / "ref.tr"), "2"], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.run([emu, "compress", src, str(tmp_path / "o"), str(tmp_path / "emu.tr"), str(tmp_path / "emu.ptr")], check=True, stderr=subprocess.DEVNULL)
+    ref = np.fromfile(str(tmp_path / "ref.tr"), dtype=np.uint32).reshape(-1, 128)
+    got = np.fromfile(str(tmp_path / "emu.tr"), dtype=np.uint32).reshape(-1, 128)
+    assert ref.shape == got.shape == (8 * os.path.getsize(src), 128)
+    bad = np.argwhere(ref != got)
+    assert bad.size == 0, f"first difference at bit {bad[0][0]}, word {bad[0][1]}"
