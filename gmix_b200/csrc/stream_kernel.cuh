@@ -1325,7 +1325,11 @@ GMX_DEV inline void SwapSet(StreamSmem& s, const Arena& A, int m, uint32_t old, 
     }
     const float4* rec = pool + (size_t)nid * stride4;
     if (lane == 0) {
+#if defined(GMX_NF_L2) && defined(__CUDA_ARCH__)
+      if (nid) s.set_steps[m] = __ldcg((const uint32_t*)rec); else s.set_steps[m] = 0u;   // experiment: header through L2, not L1
+#else
       if (nid) CpAsync4(&s.set_steps[m], rec); else s.set_steps[m] = 0u;
+#endif
       s.set_pool[m] = nid;
     } else {
       if (nid) CpAsync16(w4 + (lane - 1), rec + lane); else w4[lane - 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -1345,7 +1349,11 @@ GMX_DEV inline void MixerFrontEarly(StreamSmem& s, const Arena& A, int lane) {
     changed = idx != s.set_idx[m];
     if (changed) {
       old = s.set_pool[m];
+#if defined(GMX_NF_L2) && defined(__CUDA_ARCH__)
+      nid = __ldcg(A.at<uint32_t>(L.mix_dir[m]) + idx);
+#else
       nid = A.at<uint32_t>(L.mix_dir[m])[idx];
+#endif
       s.set_idx[m] = idx;
     }
   }

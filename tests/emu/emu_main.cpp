@@ -10,6 +10,7 @@
 #include "cuda_emu.h"
 
 #include <stdio.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -162,6 +163,33 @@ int main(int argc, char** argv) {
     return 0;
   }
 
+  if (mode == "compress2") {   // two streams through ONE persistent CTA and one arena: <in1> <in2> <out2> (what a batch larger than the arena count does)
+    std::vector<uint8_t> a = ReadAll(argv[2]), b = ReadAll(argv[3]);
+    std::vector<uint8_t> in(a); in.insert(in.end(), b.begin(), b.end());
+    const uint64_t cap = std::max(a.size(), b.size()) * 9 / 8 + 64;
+    std::vector<uint8_t> out(2 * cap);
+    uint64_t io[3] = {0, a.size(), a.size() + b.size()}, oo[3] = {0, cap, 2 * cap}, ol[2] = {0, 0};
+    uint32_t st2[2] = {0, 0};
+    P.in = in.data(); P.out = out.data(); P.in_off = io; P.out_off = oo; P.out_len = ol;
+    Run R2;
+    gmx::StreamParams Q = P;
+    // Execute() sets n_streams = 1 and its own status word: run it by hand for two streams
+    const uint64_t layout_len = getenv("EMU_LAYOUT_LEN") ? strtoull(getenv("EMU_LAYOUT_LEN"), nullptr, 10) : std::max(a.size(), b.size());
+    R2.L = gmx::MakeLayout(layout_len, getenv("EMU_ROOMY") != nullptr);   // EMU_LAYOUT_LEN: arenas configured for longer streams than these
+    R2.arena.assign(R2.L.total + 256, 0);
+    gmx::FillDecayTable(R2.decay, std::max(a.size(), b.size()) * 8 + 16);
+    gmx::FillAdamTable(R2.adam);
+    gmx::FillLstmInit(R2.linit);
+    static uint32_t queue2;
+    queue2 = 0;
+    Q.n_streams = 2; Q.queue = &queue2; Q.status = st2;
+    Q.arenas = (uint8_t*)(((uintptr_t)R2.arena.data() + 255) & ~(uintptr_t)255); Q.arena_stride = R2.L.total; Q.layout = &R2.L;
+    Q.lstm_init = R2.linit.data(); Q.decay = R2.decay.data(); Q.decay_len = (uint32_t)R2.decay.size(); Q.adam = R2.adam.data();
+    cuda_emu::RunBlock(EMU_NT, 0, 1, [&] { gmx::StreamKernel<EMU_NT, gmx::MODE_COMPRESS, 1, false>(Q); });
+    if (st2[0] || st2[1]) { fprintf(stderr, "status %u %u\n", st2[0], st2[1]); return 1; }
+    WriteAll(argv[4], out.data() + cap, ol[1]);
+    return 0;
+  }
   const bool resume = mode == "resume" || mode == "expand";
   gmx::ckpt::Image im;
   if (resume) { if (!LoadCkpt(argv[2], &im)) return 1; argv += 1; argc -= 1; }

@@ -69,3 +69,11 @@ def test_full_blackboard_trace_matches_the_live_reference(emu, tmp_path, name):
     assert ref.shape == got.shape == (8 * os.path.getsize(src), 128)
     bad = np.argwhere(ref != got)
     assert bad.size == 0, f"first difference at bit {bad[0][0]}, word {bad[0][1]}"
+
+
+def test_second_stream_of_a_persistent_cta_reuses_the_arena(emu, tmp_path):
+    """A batch with more streams than arenas makes a CTA compress a second stream in the arena and shared memory the
+    first one left behind: the second stream's bytes must not depend on that."""
+    out = str(tmp_path / "second.gmix")
+    subprocess.run([emu, "compress2", os.path.join(GOLD, "text_mid.in"), os.path.join(GOLD, "text1k.in"), out], check=True, stderr=subprocess.DEVNULL)
+    assert open(out, "rb").read() == open(os.path.join(GOLD, "text1k.gmix"), "rb").read()
