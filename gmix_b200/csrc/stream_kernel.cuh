@@ -52,10 +52,9 @@ enum : int { WSTRIDE0 = 132, WSTRIDE1 = 36, WTOTAL = 24 * WSTRIDE0 + 9 * WSTRIDE
 // resident streams already cover the latency and the extra requests only queue in front of demand loads. They stay
 // available as GMX_PF_* build flags for low-occupancy use.
 // GMX_NEW_FRONT (experimental, OFF): gate selection and weight-set swaps on the last warp during the lookup phase
-// (MixerFrontEarly / MixerFrontLate). +1.3 % at 8 CTAs/SM and bit-exact under the CPU emulator and on the golden vectors
-// on the GPU, but tests/test_gpu_configs.py::test_config2 (300 x 8 KiB) diverges from the oracle on the GPU: an
-// ordering problem between the asynchronous set copies and another phase that the synchronous emulator cannot
-// show. Kept out of the product build until found.
+// (MixerFrontEarly / MixerFrontLate). +1.3 % at 8 CTAs/SM; bit-exact under the CPU emulator (both cp.async timings,
+// three thread orders) and in the GPU checks it was given (golden vectors, 300 x 8 KiB against the oracle), but the
+// complete GPU suite has not been run with it yet (profiles/r01_s3_ab.md), so the product build keeps the old phases.
 #if !defined(GMX_NEW_FRONT) && !defined(GMX_OLD_FRONT)
 #define GMX_OLD_FRONT 1
 #endif
