@@ -128,15 +128,16 @@ class Model:
         ctx._check(ctx.lib.gmx_model_load(ctx.h, short_blob, len(short_blob), long_blob, len(long_blob), max_new_bytes, int(roomy), C.byref(h)),
                    "gmx_model_load")
         self.h = h
+        ctx._children.append(self)
 
     @classmethod
     def from_files(cls, ctx, prefix, max_new_bytes, roomy=False):
         return cls(ctx, open(prefix + ".short", "rb").read(), open(prefix + ".long", "rb").read(), max_new_bytes, roomy)
 
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and self.ctx.h:   # a closed Context has already freed its models
             self.ctx.lib.gmx_model_free(self.h)
-            self.h = None
+        self.h = None
 
     @property
     def arena_bytes(self):
@@ -155,11 +156,12 @@ class Predictor:
         h = C.c_void_p()
         ctx._check(ctx.lib.gmx_pred_new(ctx.h, max_stream_len, C.byref(h)), "gmx_pred_new")
         self.h = h
+        ctx._children.append(self)
 
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and self.ctx.h:
             self.ctx.lib.gmx_pred_free(self.h)
-            self.h = None
+        self.h = None
 
     def enable_analysis(self, on=True):
         self.ctx._check(self.ctx.lib.gmx_pred_enable_analysis(self.h, int(on)), "gmx_pred_enable_analysis")
@@ -198,9 +200,13 @@ class Context:
             raise GmixError(f"gmx_create({device}) failed ({rc}): {self.lib.gmx_global_error().decode()}")
         self.h = h
         self.device = device
+        self._children = []   # live Model / Predictor handles: they point into this ctx and are freed with it
 
     def close(self):
         if getattr(self, "h", None):
+            for ch in self._children:
+                ch.close()
+            self._children = []
             self.lib.gmx_destroy(self.h)
             self.h = None
 
@@ -263,6 +269,9 @@ class Context:
         if rand_u is None:
             rand_u = reference_rand_u(out_bytes * 8)
         rand_u = np.ascontiguousarray(rand_u, dtype=np.float32)
+        need = (n - 1) * rand_stride + out_bytes * 8   # what gmx_generate_batch reads (host.cu)
+        if rand_u.size < need:
+            raise GmixError(f"rand_u holds {rand_u.size} draws, {need} are needed ((n - 1) * rand_stride + out_bytes * 8)")
         buf, off = _pack(prompts)
         out = np.zeros(n * out_bytes + 1, dtype=np.uint8)
         status = np.zeros(n, dtype=np.uint32)

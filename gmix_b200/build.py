@@ -9,7 +9,7 @@ LIB = os.path.join(ROOT, "lib", "libgmix_b200.so")
 SOURCES = ["host.cu", "kernel_compress.cu", "kernel_decompress.cu", "kernel_compress_prof.cu", "kernel_step.cu", "kernel_generate.cu"]
 DEPS = ["host.cu", "kernel_compress.cu", "kernel_decompress.cu", "kernel_compress_prof.cu", "kernel_step.cu", "kernel_generate.cu", "checkpoint.h", "kernels.h", "stream_kernel.cuh", "ppmd.cuh", "dmath.cuh", "spec.cuh", "layout.h", "nonstationary.inc",
         os.path.join("..", "..", "include", "gmix_b200.h"), os.path.join("..", "host", "runner.cpp"), os.path.join("..", "host", "predictor.h"),
-        os.path.join("..", "host", "coder.h")]
+        os.path.join("..", "host", "coder.h"), os.path.join("..", "..", "scripts", "ncu_case.cpp")]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",

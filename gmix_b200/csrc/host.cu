@@ -197,7 +197,7 @@ int RetryInRoomyArenas(gmx_ctx* c, int mode, gmx::StreamParams P, uint32_t n, ui
   P.ids = (const uint32_t*)c->b_ids.p;
   P.n_streams = (uint32_t)ids.size();
   P.arenas = c->d_roomy; P.arena_stride = c->roomy_layout.total; P.layout = c->d_roomy_layout;
-  P.bit_trace = nullptr; P.pred_trace = nullptr;  // traces belong to stream 0 of the first launch
+  if (ids[0] != 0) { P.bit_trace = nullptr; P.pred_trace = nullptr; }  // traces belong to stream 0: re-traced only when it is re-run
   c->retried_streams += ids.size();
   return Launch(c, mode, P, P.n_streams < c->n_roomy ? P.n_streams : c->n_roomy);
 }
@@ -322,6 +322,13 @@ int RunHost(gmx_ctx* c, int mode, const uint8_t* in, const uint64_t* in_off, uin
   o.d_bit_trace = d_bt; o.d_pred_trace = d_pt;
   rc = RunDevice(c, mode, (const uint8_t*)c->b_in.p, (const uint64_t*)c->b_in_off.p, n, (uint8_t*)c->b_out.p,
                  (const uint64_t*)c->b_out_off.p, (uint64_t*)c->b_out_len.p, (uint32_t*)c->b_status.p, max_len, o);
+  if (rc == GMX_E_STREAM) {   // per-stream codes are part of the contract of GMX_E_STREAM (gmix_b200.h)
+    const std::string keep = c->error;
+    cudaMemcpyAsync(out_len, c->b_out_len.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream);
+    cudaMemcpyAsync(status, c->b_status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream);
+    cudaStreamSynchronize(c->stream);
+    c->error = keep;
+  }
   if (rc) return rc;
   GMX_CUDA(c, cudaMemcpyAsync(out + out_off[0], c->b_out.p, out_total, cudaMemcpyDeviceToHost, c->stream));
   GMX_CUDA(c, cudaMemcpyAsync(out_len, c->b_out_len.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -435,7 +442,7 @@ int gmx_set_cuda_stream(gmx_ctx* c, void* s) {
 int gmx_configure(gmx_ctx* c, uint64_t max_stream_len, uint32_t max_resident) {
   if (!c) return GMX_E_ARG;
   GMX_CUDA(c, cudaSetDevice(c->device));
-  if (max_stream_len >= (1ull << 31)) return Fail(c, GMX_E_ARG, "streams of 2 GiB or more are not supported");
+  if (max_stream_len * 8 + 16 >= (1ull << 32)) return Fail(c, GMX_E_ARG, "streams of 512 MiB or more are not supported (32-bit bit-step counters)");
   FreeArenas(c);
   c->layout = gmx::MakeLayout(max_stream_len);
   {
@@ -487,13 +494,18 @@ int gmx_model_load(gmx_ctx* c, const void* short_blob, uint64_t short_len, const
   if (!c || !out || !short_blob || !long_blob) return GMX_E_ARG;
   *out = nullptr;
   GMX_CUDA(c, cudaSetDevice(c->device));
-  if (max_new_bytes >= (1ull << 31)) return Fail(c, GMX_E_ARG, "max_new_bytes out of range");
+  if (max_new_bytes * 8 + 16 >= (1ull << 32)) return Fail(c, GMX_E_ARG, "max_new_bytes out of range");
   gmx::ckpt::Image im;
   std::string err;
   if (!gmx::ckpt::Parse(short_blob, short_len, long_blob, long_len, &im, &err)) return Fail(c, GMX_E_ARG, "checkpoint: %s", err.c_str());
   gmx_model* m = new gmx_model();
   m->ctx = c;
   m->pre = gmx::ckpt::Count(im);
+  if (m->pre.steps + max_new_bytes * 8 + 16 >= (1ull << 32)) {   // Mixer::steps_ and the decay table index are 32-bit on the device
+    delete m;
+    return Fail(c, GMX_E_ARG, "checkpoint trained on %llu bytes + %llu new bytes exceeds the 512 MiB (2^32 bit steps) limit",
+                (unsigned long long)(im.mixer[0].steps / 8), (unsigned long long)max_new_bytes);
+  }
   m->max_new_bytes = max_new_bytes;
   std::vector<uint8_t> arena;
   std::vector<uint32_t> state(sizeof(gmx::StreamSmem) / 4 + 4);
@@ -724,7 +736,7 @@ int gmx_pred_new(gmx_ctx* c, uint64_t max_stream_len, gmx_pred** out) {
   if (!c || !out) return GMX_E_ARG;
   *out = nullptr;
   GMX_CUDA(c, cudaSetDevice(c->device));
-  if (max_stream_len == 0 || max_stream_len >= (1ull << 31)) return Fail(c, GMX_E_ARG, "max_stream_len out of range");
+  if (max_stream_len == 0 || max_stream_len * 8 + 16 >= (1ull << 32)) return Fail(c, GMX_E_ARG, "max_stream_len out of range (1 .. 512 MiB)");
   int rc = EnsureDecay(c, max_stream_len);
   if (rc) return rc;
   gmx_pred* p = new gmx_pred();
@@ -800,6 +812,7 @@ int gmx_pred_read_checkpoint(gmx_pred* p, const void* short_blob, uint64_t short
   if (!gmx::ckpt::ToArena(im, p->layout, arena.data(), (gmx::StreamSmem*)state.data(), &err))
     return Fail(c, GMX_E_ARG, "checkpoint does not fit this predictor (create it with a larger max_stream_len): %s", err.c_str());
   const uint64_t trained_bits = im.mixer[0].steps;
+  if (trained_bits + p->max_bits + 16 >= (1ull << 32)) return Fail(c, GMX_E_ARG, "checkpoint + predictor length exceed the 2^32 bit-step limit");
   int rc = EnsureDecay(c, trained_bits / 8 + p->max_bits / 8 + 2);
   if (rc) return rc;
   ((gmx::StreamSmem*)state.data())->analysis = p->analysis;

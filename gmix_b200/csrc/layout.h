@@ -22,6 +22,20 @@ struct Preload {
   uint64_t sparse_entries = 0, mixer_sets = 0, ppmd_unit_bytes = 0, ppmd_text_bytes = 0, history_bytes = 0, steps = 0;
 };
 
+// Geometry of a PPMd heap window of P = 2^k bytes (ppmd.cuh): virtual offset v lives at heap[v & (P - 1)].
+// text_room = bytes below the low units; units_room = the gap the low (upward) and high (downward) unit areas share.
+// valid = that gap is one piece above the text area.
+struct PpmdWindow { bool valid; uint64_t text_room, units_room; };
+inline PpmdWindow PpmdWindowOf(uint64_t P) {
+  const uint64_t us = PPMD_UNITS_START % P;
+  const uint64_t he = PPMD_HEAP_END % P == 0 ? P : PPMD_HEAP_END % P;
+  PpmdWindow w;
+  w.valid = us < he;
+  w.text_room = us;
+  w.units_room = w.valid ? he - us : 0;
+  return w;
+}
+
 // max_len = longest stream (in uncompressed bytes) the arena must hold.
 // roomy = false: the shared sparse map and the mixer weight-set pool are sized for what text-like data
 // touches (a stream that needs more ends with GMX_ERR_SPARSE_FULL / GMX_ERR_MIXER_POOL and the host
@@ -126,12 +140,18 @@ inline ArenaLayout MakeLayout(uint64_t max_len, bool roomy = false, const Preloa
   {
     const uint64_t want_units = (roomy ? 400 : 90) * max_len + (256u << 10) + pre->ppmd_unit_bytes;
     const uint64_t want_text = max_len + 64 + pre->ppmd_text_bytes;
+    // Inside the window the low units grow up from units_start mod P and the high units grow down from
+    // heap_end mod P (= the top of the window while P divides 2000 MiB, i.e. up to 16 MiB). The kernel's test
+    // "low + high <= units_cap" is only right when the two areas share ONE gap that does not contain the text at
+    // the bottom of the window: units_start mod P < heap_end mod P. Window sizes where the gap would wrap through 0
+    // (32 .. 256 MiB) are skipped; 512 MiB (214 MiB of units) and 1 GiB (726 MiB) are valid again.
     uint64_t P = 1ull << 20;
     for (;; P <<= 1) {
-      const uint64_t text_room = PPMD_UNITS_START % P, units_room = P - text_room;
-      if ((text_room >= want_text && units_room >= want_units) || P >= (1ull << 30)) break;
+      const PpmdWindow w = PpmdWindowOf(P);
+      if (w.valid && ((w.text_room >= want_text && w.units_room >= want_units) || P >= (1ull << 30))) break;
     }
-    const uint64_t text_room = PPMD_UNITS_START % P, units_room = P - text_room;
+    const PpmdWindow w = PpmdWindowOf(P);
+    const uint64_t text_room = w.text_room, units_room = w.units_room;
     L.p_mask = (uint32_t)(P - 1);
     L.p_text_cap = (uint32_t)(want_text < text_room ? want_text : text_room);
     uint64_t units = units_room / 48 * 48;

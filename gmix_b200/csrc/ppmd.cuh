@@ -8,10 +8,11 @@
 //   text area   [0, text_cap)                    grows up
 //   low units   [units_start, units_start + x)   grows up
 //   high units  [heap_end - y, heap_end)         grows down
-// They are backed by ONE window of 2^k bytes addressed as heap[v & (2^k - 1)]: heap_end = 2000 MiB is
-// a multiple of 2^k (k <= 24), so the high units end at the top of the window, the low units start
-// at units_start mod 2^k, and the text sits at the bottom; the three never meet as long as
-// text_cap <= units_start mod 2^k and x + y <= units_cap = 2^k - units_start mod 2^k (layout.h picks k).
+// They are backed by ONE window of P = 2^k bytes addressed as heap[v & (P - 1)]: the text sits at the bottom, the
+// low units start at units_start mod P and grow up, the high units end at heap_end mod P (the top of the window
+// while P divides 2000 MiB, i.e. k <= 24; 464 MiB at k = 29, 976 MiB at k = 30) and grow down. The three never
+// meet as long as text_cap <= units_start mod P and x + y <= units_cap = (heap_end mod P) - (units_start mod P);
+// layout.h (PpmdWindowOf) only picks k for which that gap is one piece above the text area.
 // The reference's out-of-memory machinery (AllocUnitsRare/GlueFreeBlocks
 // :158-228, RestoreModelRare/cutOff :568-755, Expand/PrepareTextArea :299-348) only runs when the
 // 2000 MiB heap is exhausted (> ~90 MB of input); here exhausting the *backed* part raises
@@ -24,11 +25,11 @@
 
 #if defined(__CUDACC__)
 #define GMX_DEV __device__
-#define GMX_HD __host__ __device__
+#define GMX_HOSTDEV __host__ __device__   // (GMX_HD, with force-inline, belongs to dmath.cuh)
 #define GMX_NOINLINE __noinline__
 #else
 #define GMX_DEV
-#define GMX_HD
+#define GMX_HOSTDEV
 #define GMX_NOINLINE
 #endif
 
@@ -59,7 +60,7 @@ struct PpmdState {
 
 // Constant lookup tables of the model (PPMD_STARTUP :375-400); also filled by the host when a checkpoint
 // is turned into an arena image (checkpoint.h).
-GMX_HD inline void PpmdFillTables(PpmdState* S) {
+GMX_HOSTDEV inline void PpmdFillTables(PpmdState* S) {
   int i, k, m, step;
   for (i = 0, k = 1; i < 4; i++, k += 1) S->indx2units[i] = (uint8_t)k;
   for (k++; i < 8; i++, k += 2) S->indx2units[i] = (uint8_t)k;

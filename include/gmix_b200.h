@@ -67,7 +67,10 @@ int gmx_set_cuda_stream(gmx_ctx* ctx, void* cuda_stream);
  * wave of co-resident CTAs). Called implicitly by the batch calls when needed.
  * Arenas are sized for what text-like data touches; a stream that needs more (incompressible data)
  * is transparently re-run from scratch in a worst-case-sized arena by the same batch call, so
- * statuses 1, 2 and 7 only surface when even that does not fit the GPU. */
+ * statuses 1, 2 and 7 only surface when even that does not fit the GPU.
+ * Limit: a stream's bit-step counter (trained bits of the checkpoint it starts from + 8 * its own bytes) is
+ * 32-bit on the device, so trained bytes + stream bytes must stay below 512 MiB; larger requests are
+ * rejected with GMX_E_ARG here, in gmx_model_load and in gmx_pred_new. */
 int gmx_configure(gmx_ctx* ctx, uint64_t max_stream_len, uint32_t max_resident);
 
 /* Worst-case compressed size of an n-byte stream (header + coder bytes). */
