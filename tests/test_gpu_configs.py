@@ -42,6 +42,22 @@ def test_config2_synthetic_chunks_oracle_sample_and_roundtrip(gpu_ctx, oracle):
     assert gpu_ctx.retried_streams == retried_before      # text fits the normal arenas
 
 
+def test_config2_full_size_64_chunk_sample_against_the_reference(gpu_ctx):
+    """The benchmarked shape: a seeded sample of 64 full 64 KiB synthetic-text chunks of the
+    4096-chunk set. GPU bytes == the bytes the unmodified reference CLI writes (`oracle/_ref/gmix -c`, one process per
+    host core), and the GPU decompresses the REFERENCE's streams back to the inputs (configs[2])."""
+    import random
+    import ref_cli
+    from gmix_b200 import synth
+    ids = sorted(random.Random(0x676D6978).sample(range(4096), 64))
+    streams = [synth.synthetic_text_chunk(i, 65536) for i in ids]
+    want, _ = ref_cli.run_many("-c", streams)
+    got = gpu_ctx.compress_batch(streams)
+    diff = [ids[k] for k in range(len(ids)) if got[k] != want[k]]
+    assert not diff, f"chunks {diff[:8]} differ from the reference ({len(diff)} of {len(ids)})"
+    assert gpu_ctx.decompress_batch(want) == streams
+
+
 def test_incompressible_streams_take_the_roomy_retry_path(gpu_ctx, oracle):
     import numpy as np
     rng = np.random.RandomState(7)
