@@ -48,6 +48,8 @@ def load_library():
     lib.gmx_compress_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, u64p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gmx_resident_streams.argtypes = [C.c_void_p]
     lib.gmx_resident_streams.restype = C.c_uint32
+    lib.gmx_arena_count.argtypes = [C.c_void_p]
+    lib.gmx_arena_count.restype = C.c_uint32
     lib.gmx_arena_bytes.argtypes = [C.c_void_p]
     lib.gmx_arena_bytes.restype = C.c_uint64
     lib.gmx_retried_streams.argtypes = [C.c_void_p]
@@ -138,6 +140,10 @@ class Model:
         if getattr(self, "h", None) and self.ctx.h:   # a closed Context has already freed its models
             self.ctx.lib.gmx_model_free(self.h)
         self.h = None
+
+    @property
+    def max_resident_streams(self):
+        return int(self.lib.gmx_arena_count(self.h))
 
     @property
     def arena_bytes(self):

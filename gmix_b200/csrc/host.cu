@@ -824,6 +824,7 @@ int gmx_pred_read_checkpoint(gmx_pred* p, const void* short_blob, uint64_t short
 }
 
 uint32_t gmx_resident_streams(const gmx_ctx* c) { return c ? c->last_grid : 0; }
+uint32_t gmx_arena_count(const gmx_ctx* c) { return c ? c->n_arenas : 0; }
 uint64_t gmx_arena_bytes(const gmx_ctx* c) { return c ? c->layout.total : 0; }
 uint64_t gmx_retried_streams(const gmx_ctx* c) { return c ? c->retried_streams : 0; }
 uint64_t gmx_kernel_launches(const gmx_ctx* c) { return c ? c->launches : 0; }

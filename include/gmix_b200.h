@@ -167,6 +167,7 @@ int gmx_pred_read_checkpoint(gmx_pred* pred, const void* short_blob, uint64_t sh
 
 /* Introspection for benchmarks. */
 uint32_t gmx_resident_streams(const gmx_ctx* ctx);   /* CTAs (= arenas) the last launch used */
+uint32_t gmx_arena_count(const gmx_ctx* ctx);        /* stream arenas currently allocated (= most streams resident at once) */
 uint64_t gmx_arena_bytes(const gmx_ctx* ctx);        /* bytes of one stream arena */
 uint64_t gmx_retried_streams(const gmx_ctx* ctx);    /* streams re-run in a worst-case arena so far (see gmx_configure) */
 uint64_t gmx_kernel_launches(const gmx_ctx* ctx);    /* kernels launched by this ctx so far */
