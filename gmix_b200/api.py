@@ -48,6 +48,8 @@ def load_library():
     lib.gmx_compress_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, u64p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gmx_resident_streams.argtypes = [C.c_void_p]
     lib.gmx_resident_streams.restype = C.c_uint32
+    lib.gmx_set_kernel_config.argtypes = [C.c_void_p, C.c_int]
+    lib.gmx_kernel_config_info.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.gmx_arena_count.argtypes = [C.c_void_p]
     lib.gmx_arena_count.restype = C.c_uint32
     lib.gmx_arena_bytes.argtypes = [C.c_void_p]
@@ -327,6 +329,18 @@ class Context:
     def checksum_device(self, d_data, d_off, d_len, n, d_sum):
         self._check(self.lib.gmx_checksum_device(self.h, d_data, d_off, d_len, n, d_sum), "gmx_checksum_device")
 
+    def set_kernel_config(self, cfg):
+        self._check(self.lib.gmx_set_kernel_config(self.h, int(cfg)), "gmx_set_kernel_config")
+
+    def kernel_configs(self):
+        """[(bit warps, LSTM warps, CTAs per SM)] of every kernel configuration in the library."""
+        out = []
+        for k in range(self.lib.gmx_kernel_config_count()):
+            a, b, c = C.c_int(), C.c_int(), C.c_int()
+            self.lib.gmx_kernel_config_info(k, C.byref(a), C.byref(b), C.byref(c))
+            out.append((a.value, b.value, c.value))
+        return out
+
     # ---- introspection ----
     @property
     def resident_streams(self):
@@ -352,9 +366,12 @@ class Context:
     def sm_count(self):
         return int(self.lib.gmx_device_sm_count(self.h))
 
-    PROFILE_SLOTS = ("byte_ctx+ppmd", "ppm_norm", "lstm_fwd", "nodes", "lookups", "mix_swap", "mix_predict", "coder",
-                     "learn_scalars", "mix_update", "lstm_out_step", "bptt_epochs", "bptt_grads", "init", "bit_misc", "-",
-                     "gate_select", "l0_dot", "l0_chain", "l1", "final", "-", "-", "-")
+    # cycle counters of the PROF kernel variant, per role (stream_kernel.cuh): bit role 0-15, LSTM role 16-23, PPMd role 24-31
+    PROFILE_SLOTS = ("bit:bookkeeping", "bit:wait_packet", "bit:boundary_ctx", "bit:lookups", "bit:gate_select", "bit:set_swap", "bit:l0_dot",
+                     "bit:l0_chain", "bit:l1", "bit:final", "bit:predict_tail", "bit:learn_scalars+tables", "bit:weight_update", "bit:trace",
+                     "init", "-",
+                     "lstm:wait", "lstm:fwd_gates", "lstm:fwd_rest", "lstm:out_step", "lstm:bptt_epochs", "lstm:bptt_grads", "-", "-",
+                     "ppmd:wait", "ppmd:model", "ppmd:normalise+nodes", "-", "-", "-", "-", "-")
 
     def set_profile(self, on=True):
         self._check(self.lib.gmx_set_profile(self.h, int(on)), "gmx_set_profile")

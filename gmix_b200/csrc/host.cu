@@ -62,6 +62,7 @@ struct gmx_ctx {
   uint32_t prof_streams = 0;
   uint32_t usage_streams = 0;
   uint32_t last_grid = 0;
+  int kcfg = 0;            // kernel configuration (kernels.h) of the batch calls
   uint64_t launches = 0;
   double last_ms = 0;
 };
@@ -157,8 +158,8 @@ bool Retryable(uint32_t st) {
 int Launch(gmx_ctx* c, int mode, const gmx::StreamParams& P, uint32_t grid) {
   GMX_CUDA(c, cudaMemsetAsync(c->d_queue, 0, sizeof(uint32_t), c->stream));
   GMX_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-  GMX_CUDA(c, mode == gmx::MODE_COMPRESS ? (P.prof ? gmx::LaunchCompressProf(P, grid, c->stream) : gmx::LaunchCompress(P, grid, c->stream))
-              : mode == gmx::MODE_DECOMPRESS ? gmx::LaunchDecompress(P, grid, c->stream) : gmx::LaunchGenerate(P, grid, c->stream));
+  GMX_CUDA(c, mode == gmx::MODE_COMPRESS ? (P.prof ? gmx::LaunchCompressProf(c->kcfg, P, grid, c->stream) : gmx::LaunchCompress(c->kcfg, P, grid, c->stream))
+              : mode == gmx::MODE_DECOMPRESS ? gmx::LaunchDecompress(c->kcfg, P, grid, c->stream) : gmx::LaunchGenerate(c->kcfg, P, grid, c->stream));
   GMX_CUDA(c, cudaEventRecord(c->ev1, c->stream));
   GMX_CUDA(c, cudaStreamSynchronize(c->stream));
   float ms = 0;
@@ -211,7 +212,7 @@ int ConfigureForModel(gmx_ctx* c, const gmx_model* m) {
   int rc = EnsureDecay(c, m->pre.steps / 8 + m->max_new_bytes + 2);
   if (rc) return rc;
   int per_sm = 0;
-  GMX_CUDA(c, gmx::OccupancyCompress(&per_sm));
+  GMX_CUDA(c, gmx::OccupancyCompress(c->kcfg, &per_sm));
   if (per_sm < 1) per_sm = 1;
   uint64_t want = (uint64_t)per_sm * c->sm_count;
   if (max_resident && max_resident < want) want = max_resident;
@@ -399,6 +400,7 @@ int gmx_create(int device, gmx_ctx** out) {
     return GMX_E_CUDA;
   }
   c->stream = c->own_stream;
+  if (const char* e = getenv("GMIX_B200_KERNEL_CONFIG")) { const int k = atoi(e); if (k >= 0 && k < gmx::kNumKernelConfigs) c->kcfg = k; }
   std::vector<float> linit, adam;
   gmx::FillLstmInit(linit);
   gmx::FillAdamTable(adam);
@@ -433,6 +435,22 @@ void gmx_destroy(gmx_ctx* c) {
 
 const char* gmx_last_error(const gmx_ctx* c) { return c ? c->error.c_str() : g_global_error.c_str(); }
 
+int gmx_set_kernel_config(gmx_ctx* c, int cfg) {
+  if (!c) return GMX_E_ARG;
+  if (cfg < 0 || cfg >= gmx::kNumKernelConfigs) return Fail(c, GMX_E_ARG, "kernel configuration %d out of range (0 .. %d)", cfg, gmx::kNumKernelConfigs - 1);
+  if (cfg != c->kcfg) { c->kcfg = cfg; FreeArenas(c); }   // residency (arena count) depends on the configuration
+  return 0;
+}
+int gmx_kernel_config_count(void) { return gmx::kNumKernelConfigs; }
+int gmx_kernel_config_info(int cfg, int* bit_warps, int* lstm_warps, int* ctas_per_sm) {
+  if (cfg < 0 || cfg >= gmx::kNumKernelConfigs) return GMX_E_ARG;
+  const gmx::KernelConfigInfo k = gmx::KernelConfig(cfg);
+  if (bit_warps) *bit_warps = k.wb;
+  if (lstm_warps) *lstm_warps = k.wl;
+  if (ctas_per_sm) *ctas_per_sm = k.minb;
+  return 0;
+}
+
 int gmx_set_cuda_stream(gmx_ctx* c, void* s) {
   if (!c) return GMX_E_ARG;
   c->stream = s ? (cudaStream_t)s : c->own_stream;
@@ -450,7 +468,7 @@ int gmx_configure(gmx_ctx* c, uint64_t max_stream_len, uint32_t max_resident) {
     if (rc) return rc;
   }
   int per_sm = 0;
-  GMX_CUDA(c, gmx::OccupancyCompress(&per_sm));
+  GMX_CUDA(c, gmx::OccupancyCompress(c->kcfg, &per_sm));
   if (per_sm < 1) per_sm = 1;
   uint64_t want = (uint64_t)per_sm * c->sm_count;
   if (max_resident && max_resident < want) want = max_resident;

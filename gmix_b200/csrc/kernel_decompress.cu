@@ -1,14 +1,19 @@
 #include "kernels.h"
 namespace gmx {
-cudaError_t LaunchDecompress(const StreamParams& P, unsigned grid, cudaStream_t st) {
-  // all of the SM's unified L1/shared memory as shared memory, so that kStreamMinBlocks CTAs are co-resident
-  static const cudaError_t carve = cudaFuncSetAttribute(StreamKernel<kStreamThreads, MODE_DECOMPRESS, kStreamMinBlocks, false>,
-                                                        cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (carve != cudaSuccess) return carve;
-  StreamKernel<kStreamThreads, MODE_DECOMPRESS, kStreamMinBlocks, false><<<grid, kStreamThreads, 0, st>>>(P);
-  return cudaGetLastError();
+cudaError_t LaunchDecompress(int cfg, const StreamParams& P, unsigned grid, cudaStream_t st) {
+  switch (cfg) {
+#define X(id, wb, wl, minb) case id: return LaunchStreamKernel<wb, wl, MODE_DECOMPRESS, minb, false>(P, grid, st);
+    GMX_KERNEL_CONFIGS(X)
+#undef X
+    default: return cudaErrorInvalidValue;
+  }
 }
-cudaError_t OccupancyDecompress(int* n) {
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, StreamKernel<kStreamThreads, MODE_DECOMPRESS, kStreamMinBlocks, false>, kStreamThreads, 0);
+cudaError_t OccupancyDecompress(int cfg, int* n) {
+  switch (cfg) {
+#define X(id, wb, wl, minb) case id: return OccupancyStreamKernel<wb, wl, MODE_DECOMPRESS, minb, false>(n);
+    GMX_KERNEL_CONFIGS(X)
+#undef X
+    default: return cudaErrorInvalidValue;
+  }
 }
 }  // namespace gmx

@@ -2,11 +2,12 @@
 // clone of the loaded checkpoint.
 #include "kernels.h"
 namespace gmx {
-cudaError_t LaunchGenerate(const StreamParams& P, unsigned grid, cudaStream_t st) {
-  static const cudaError_t carve = cudaFuncSetAttribute(StreamKernel<kStreamThreads, MODE_GENERATE, kStreamMinBlocks, false>,
-                                                        cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (carve != cudaSuccess) return carve;
-  StreamKernel<kStreamThreads, MODE_GENERATE, kStreamMinBlocks, false><<<grid, kStreamThreads, 0, st>>>(P);
-  return cudaGetLastError();
+cudaError_t LaunchGenerate(int cfg, const StreamParams& P, unsigned grid, cudaStream_t st) {
+  switch (cfg) {
+#define X(id, wb, wl, minb) case id: return LaunchStreamKernel<wb, wl, MODE_GENERATE, minb, false>(P, grid, st);
+    GMX_KERNEL_CONFIGS(X)
+#undef X
+    default: return cudaErrorInvalidValue;
+  }
 }
 }  // namespace gmx

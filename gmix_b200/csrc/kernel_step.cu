@@ -2,7 +2,7 @@
 #include "kernels.h"
 namespace gmx {
 cudaError_t LaunchStep(const StepParams& Q, cudaStream_t st) {
-  StepKernel<kStreamThreads><<<1, kStreamThreads, 0, st>>>(Q);
+  StepKernel<kStepWB, kStepWL><<<1, 32 * (kStepWB + kStepWL + 1), 0, st>>>(Q);
   return cudaGetLastError();
 }
 unsigned StepStateBytes() { return (unsigned)sizeof(StreamSmem); }

@@ -58,6 +58,13 @@ int gmx_create(int device, gmx_ctx** out);
 void gmx_destroy(gmx_ctx* ctx);
 const char* gmx_last_error(const gmx_ctx* ctx);
 
+/* Kernel configuration = the role split of the stream CTA (warps of bit role / LSTM role + one PPMd warp, resident CTAs
+ * per SM). Every configuration produces the same bytes; they differ in throughput per workload shape. Default 0 (or the
+ * environment variable GMIX_B200_KERNEL_CONFIG). Changing it frees the arenas (the next call re-sizes them). */
+int gmx_set_kernel_config(gmx_ctx* ctx, int cfg);
+int gmx_kernel_config_count(void);
+int gmx_kernel_config_info(int cfg, int* bit_warps, int* lstm_warps, int* ctas_per_sm);
+
 /* Launch kernels on an existing CUDA stream (cudaStream_t passed as void*), e.g. torch's current
  * stream, so the caller can bracket calls with its own CUDA events. NULL = the ctx's own stream. */
 int gmx_set_cuda_stream(gmx_ctx* ctx, void* cuda_stream);
@@ -175,7 +182,7 @@ double gmx_last_kernel_ms(const gmx_ctx* ctx);       /* device time of the last 
 int gmx_device_sm_count(const gmx_ctx* ctx);
 
 /* Phase profiler: when on, every stream accumulates 24 cycle counters (slots documented in
- * gmix_b200/csrc/stream_kernel.cuh); gmx_get_profile copies up to max_streams x 24 counters of the
+ * gmix_b200/csrc/stream_kernel.cuh); gmx_get_profile copies up to max_streams x 32 counters of the
  * last launch and returns the number of streams copied. */
 int gmx_set_profile(gmx_ctx* ctx, int on);
 int gmx_get_profile(gmx_ctx* ctx, uint64_t* out, uint32_t max_streams);

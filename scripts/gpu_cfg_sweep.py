@@ -1,0 +1,31 @@
+"""Throughput of every kernel configuration (role split of the stream CTA) on one full wave of LEN-byte synthetic-text
+streams, after a byte-parity check of that configuration against the golden vectors.
+  python scripts/gpu_cfg_sweep.py LEN [cfg ...]"""
+import sys
+sys.path.insert(0, ".")
+import gmix_b200
+from gmix_b200 import synth
+size = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+c = gmix_b200.Context(0)
+cfgs = [int(x) for x in sys.argv[2:]] or list(range(len(c.kernel_configs())))
+names = ["text1k", "repetitive", "random1200", "text_mid", "synth_chunk0_4k"]
+ins = [open(f"tests/golden/{n}.in", "rb").read() for n in names]
+want = [open(f"tests/golden/{n}.gmix", "rb").read() for n in names]
+chunks = {}
+for k in cfgs:
+    wb, wl, minb = c.kernel_configs()[k]
+    c.set_kernel_config(k)
+    got = c.compress_batch(ins)
+    ok = got == want and c.decompress_batch(got) == ins
+    c.configure(size, 0)
+    n = c.max_resident_streams
+    for i in range(n):
+        if i not in chunks:
+            chunks[i] = synth.synthetic_text_chunk(i, size)
+    batch = [chunks[i] for i in range(n)]
+    comp = c.compress_batch(batch)
+    ms = c.last_kernel_ms
+    back = c.decompress_batch(comp)
+    dms = c.last_kernel_ms
+    print(f"cfg {k} (bit {wb}w, lstm {wl}w, {minb}/SM) parity {'OK' if ok else 'FAILED'} roundtrip {'OK' if back == batch else 'FAILED'}: "
+          f"{n} x {size}: compress {ms:.0f} ms -> {n*size/ms/1e3:.3f} MB/s, decompress {dms:.0f} ms -> {n*size/dms/1e3:.3f} MB/s", flush=True)

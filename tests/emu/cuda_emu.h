@@ -5,6 +5,7 @@
 // It exists to debug kernel *logic* against the oracle; it is never part of the shipped library.
 #ifndef GMIX_TESTS_CUDA_EMU_H_
 #define GMIX_TESTS_CUDA_EMU_H_
+#define GMX_EMU 1
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -31,6 +32,7 @@ struct Block {
   Fiber* cur = nullptr;
   unsigned nthreads = 0;
   unsigned bar_count = 0, bar_gen = 0;
+  unsigned nbar_count[16] = {0}, nbar_gen[16] = {0};   // named barriers (bar.sync id, count)
   std::vector<unsigned> wbar_count, wbar_gen;
   std::vector<uint64_t> shfl_slots;  // [warp][parity][lane]
   std::function<void()> body;
@@ -126,6 +128,12 @@ inline void BlockBarrier() {
   if (++b->bar_count == b->nthreads) { b->bar_count = 0; b->bar_gen++; }
   else while (b->bar_gen == gen) Yield();
 }
+inline void NamedBarrier(int id, unsigned count) {   // bar.sync id, count: `count` threads of the block meet here
+  Block* b = B();
+  const unsigned gen = b->nbar_gen[id];
+  if (++b->nbar_count[id] == count) { b->nbar_count[id] = 0; b->nbar_gen[id]++; }
+  else while (b->nbar_gen[id] == gen) Yield();
+}
 inline void WarpBarrier() {
   Block* b = B();
   const unsigned w = b->cur->tid / 32;
@@ -200,6 +208,8 @@ inline unsigned __ballot_sync(unsigned, int pred) {
   for (int l = 0; l < 32; ++l) m |= (cuda_emu::Shfl(pred ? 1u : 0u, (unsigned)l) & 1u) << l;
   return m;
 }
+inline void __threadfence_block() {}
+inline void __nanosleep(unsigned) { cuda_emu::Yield(); }
 inline int __ffs(int x) { return x == 0 ? 0 : __builtin_ctz((unsigned)x) + 1; }
 inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }

@@ -7,6 +7,8 @@
 //   emu_main expand   <ckpt_prefix> <in> <out>                   `gmix -d <ckpt> <in> <out>`
 //   emu_main generate <ckpt_prefix> <prompt> <out> <size> <temperature>   `gmix -g ...` (sampling draws from this host's rand())
 //   emu_main recode   <ckpt_prefix> <out_prefix>                 Parse then Serialize (must reproduce the files byte for byte)
+//   emu_main steps    <in> <out>                                 compress through the Predictor facade's StepKernel (one launch per
+//                                                                Predict / Learn, host coder), analysis as `gmix -c` sets it
 #include "cuda_emu.h"
 
 #include <stdio.h>
@@ -15,10 +17,17 @@
 #include <vector>
 
 #include "../../gmix_b200/csrc/checkpoint.h"
+#include "../../gmix_b200/host/coder.h"
 
-#ifndef EMU_NT
-#define EMU_NT 128
+// role split of the emulated CTA (warps of bit role / LSTM role; + one PPMd warp)
+#ifndef EMU_WB
+#define EMU_WB 2
 #endif
+#ifndef EMU_WL
+#define EMU_WL 1
+#endif
+#define EMU_NT (32 * (EMU_WB + EMU_WL + 1))
+namespace gmx { constexpr int kStepWB = 2, kStepWL = 1; }   // as kernels.h (which needs the CUDA runtime)
 
 static std::vector<uint8_t> ReadAll(const std::string& path) {
   FILE* f = fopen(path.c_str(), "rb");
@@ -81,9 +90,9 @@ retry:
   }
   if (want_final) { R.final_state.assign(sizeof(gmx::StreamSmem) / 4 + 4, 0); P.final_state = R.final_state.data(); }
   cuda_emu::RunBlock(EMU_NT, 0, 1, [&] {
-    if (mode == gmx::MODE_COMPRESS) gmx::StreamKernel<EMU_NT, gmx::MODE_COMPRESS, 1, false>(P);
-    else if (mode == gmx::MODE_DECOMPRESS) gmx::StreamKernel<EMU_NT, gmx::MODE_DECOMPRESS, 1, false>(P);
-    else gmx::StreamKernel<EMU_NT, gmx::MODE_GENERATE, 1, false>(P);
+    if (mode == gmx::MODE_COMPRESS) gmx::StreamKernel<EMU_WB, EMU_WL, gmx::MODE_COMPRESS, 1, false>(P);
+    else if (mode == gmx::MODE_DECOMPRESS) gmx::StreamKernel<EMU_WB, EMU_WL, gmx::MODE_DECOMPRESS, 1, false>(P);
+    else gmx::StreamKernel<EMU_WB, EMU_WL, gmx::MODE_GENERATE, 1, false>(P);
   });
   if (!roomy && (R.status == gmx::GMX_ERR_PPMD_ARENA || R.status == gmx::GMX_ERR_MIXER_POOL || R.status == gmx::GMX_ERR_SPARSE_FULL)) {
     fprintf(stderr, "status %u: retrying in a roomy arena (as the host library does)\n", R.status);
@@ -163,6 +172,43 @@ int main(int argc, char** argv) {
     return 0;
   }
 
+  if (mode == "steps") {   // what gmix_b200/host/predictor.h does over gmx_pred_*: STEP_INIT, then Predict / (Perceive) Learn per bit
+    std::vector<uint8_t> in = ReadAll(argv[2]);
+    Run R2;
+    R2.L = gmx::MakeLayout(in.size() + 1, true);
+    R2.arena.assign(R2.L.total + 256, 0);
+    gmx::FillDecayTable(R2.decay, in.size() * 8 + 16);
+    gmx::FillAdamTable(R2.adam);
+    gmx::FillLstmInit(R2.linit);
+    std::vector<uint32_t> state(sizeof(gmx::StreamSmem) / 4 + 4, 0);
+    float prob = 0; uint32_t status = 0;
+    gmx::StepParams Q;
+    memset(&Q, 0, sizeof(Q));
+    Q.P.arenas = (uint8_t*)(((uintptr_t)R2.arena.data() + 255) & ~(uintptr_t)255); Q.P.arena_stride = R2.L.total; Q.P.layout = &R2.L;
+    Q.P.lstm_init = R2.linit.data(); Q.P.decay = R2.decay.data(); Q.P.decay_len = (uint32_t)R2.decay.size(); Q.P.adam = R2.adam.data();
+    Q.state = state.data(); Q.prob_out = &prob; Q.status_out = &status;
+    const int analysis = (8 * in.size() / 1000) > 0;
+    constexpr int NTS = 32 * (gmx::kStepWB + gmx::kStepWL + 1);
+    auto step = [&](int op, int has_bit, int bit) {
+      Q.op = op; Q.has_bit = has_bit; Q.bit = bit; Q.analysis = analysis;
+      cuda_emu::RunBlock(NTS, 0, 1, [&] { gmx::StepKernel<gmx::kStepWB, gmx::kStepWL>(Q); });
+      if (status) { fprintf(stderr, "step status %u\n", status); exit(1); }
+    };
+    step(gmx::STEP_INIT, 0, 0);
+    std::vector<uint8_t> out;
+    for (int i = 4; i >= 0; --i) out.push_back((uint8_t)((uint64_t)in.size() >> (8 * i)));
+    gmixb::Encoder enc(&out);
+    for (size_t pos = 0; pos < in.size(); ++pos)
+      for (int j = 7; j >= 0; --j) {
+        const int bit = (in[pos] >> j) & 1;
+        step(gmx::STEP_PREDICT, 0, 0);
+        enc.Encode(bit, prob);
+        step(gmx::STEP_LEARN, 1, bit);
+      }
+    enc.Flush();
+    WriteAll(argv[3], out.data(), out.size());
+    return 0;
+  }
   if (mode == "compress2") {   // two streams through ONE persistent CTA and one arena: <in1> <in2> <out2> (what a batch larger than the arena count does)
     std::vector<uint8_t> a = ReadAll(argv[2]), b = ReadAll(argv[3]);
     std::vector<uint8_t> in(a); in.insert(in.end(), b.begin(), b.end());
@@ -185,7 +231,7 @@ int main(int argc, char** argv) {
     Q.n_streams = 2; Q.queue = &queue2; Q.status = st2;
     Q.arenas = (uint8_t*)(((uintptr_t)R2.arena.data() + 255) & ~(uintptr_t)255); Q.arena_stride = R2.L.total; Q.layout = &R2.L;
     Q.lstm_init = R2.linit.data(); Q.decay = R2.decay.data(); Q.decay_len = (uint32_t)R2.decay.size(); Q.adam = R2.adam.data();
-    cuda_emu::RunBlock(EMU_NT, 0, 1, [&] { gmx::StreamKernel<EMU_NT, gmx::MODE_COMPRESS, 1, false>(Q); });
+    cuda_emu::RunBlock(EMU_NT, 0, 1, [&] { gmx::StreamKernel<EMU_WB, EMU_WL, gmx::MODE_COMPRESS, 1, false>(Q); });
     if (st2[0] || st2[1]) { fprintf(stderr, "status %u %u\n", st2[0], st2[1]); return 1; }
     WriteAll(argv[4], out.data() + cap, ol[1]);
     return 0;

@@ -77,3 +77,29 @@ def test_second_stream_of_a_persistent_cta_reuses_the_arena(emu, tmp_path):
     out = str(tmp_path / "second.gmix")
     subprocess.run([emu, "compress2", os.path.join(GOLD, "text_mid.in"), os.path.join(GOLD, "text1k.in"), out], check=True, stderr=subprocess.DEVNULL)
     assert open(out, "rb").read() == open(os.path.join(GOLD, "text1k.gmix"), "rb").read()
+
+
+@pytest.mark.parametrize("name", ["short124", "text1k"])     # analysis off (< 125 B) and on
+def test_stepping_kernel_behind_the_predictor_facade(emu, tmp_path, name):
+    """StepKernel (one launch per Predictor::Predict / Learn, the three roles run one after the other) + the host coder
+    reproduce the reference's stream."""
+    out = str(tmp_path / "steps.gmix")
+    subprocess.run([emu, "steps", os.path.join(GOLD, name + ".in"), out], check=True, stderr=subprocess.DEVNULL)
+    assert open(out, "rb").read() == open(os.path.join(GOLD, name + ".gmix"), "rb").read()
+
+
+@pytest.mark.parametrize("roles", [(1, 2), (1, 1), (2, 2)])
+def test_other_role_splits_compute_the_same_bytes(tmp_path, roles):
+    """The kernel configurations of the library (kernels.h) differ only in how many warps the bit role and the LSTM role
+    get: every split must compute the reference's bytes, in both pipeline protocols (ahead: compress, lockstep: decompress)."""
+    wb, wl = roles
+    exe = str(tmp_path / "emu_main")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-w", f"-DEMU_WB={wb}", f"-DEMU_WL={wl}", "-o", exe,
+                    os.path.join(HERE, "emu", "emu_main.cpp")], check=True)
+    for name in ("text1k", "random1200"):
+        out = str(tmp_path / (name + ".out"))
+        subprocess.run([exe, "compress", os.path.join(GOLD, name + ".in"), out], check=True, stderr=subprocess.DEVNULL)
+        assert open(out, "rb").read() == open(os.path.join(GOLD, name + ".gmix"), "rb").read(), (roles, name)
+    back = str(tmp_path / "back")
+    subprocess.run([exe, "decompress", os.path.join(GOLD, "text1k.gmix"), back], check=True, stderr=subprocess.DEVNULL)
+    assert open(back, "rb").read() == open(os.path.join(GOLD, "text1k.in"), "rb").read()
