@@ -17,6 +17,18 @@ JSON line keys follow the driver contract; `value` is device-resident throughput
 HBM), `e2e` is the same metric through the host-pointer C-ABI call (pinned host buffers, H2D and D2H
 inside the timed region). `roofline` is the HBM roofline of the stream kernel with SURVEY.md 8(d)'s
 algorithmic bytes (4.29e5 B of model-state traffic per input byte).
+
+Further keys of the line (each a leg outside the timed region of `value`; `--no-legs` skips them all):
+  parity        streams of the TIMED batch compared byte for byte with the unmodified reference CLI (the same wave of
+                `gmix -c` processes that gives `cpu_baseline`)
+  decompress    configs[2]: the last step's streams decompressed on the GPU, every stream compared with its input
+  generate      configs[3] (reduced scale, stated): batched generation from a checkpoint written on the GPU
+  config1_4096  configs[1] as BASELINE.json words it: all 4096 chunks in ONE gmx_compress_batch call (several waves)
+  config0       configs[0]: dictionary/english.dic as a single stream, md5 of the output checked against the reference's
+  config4       configs[4]: the enwik-shaped corpus cut into equal streams, sharded over the N ranks (strong scaling: the
+                total is fixed), one NCCL all_gather of sizes + checksums
+The reference arm (`--impl reference`) times the unmodified reference CLI on the same configuration: every step is one
+wave of one FULL chunk per host core (a bounded sample of the step's chunk list, stated in cpu_baseline.sample).
 """
 import argparse
 import json
@@ -58,6 +70,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-decompress", action="store_true", help="skip the configs[2] leg (GPU decompress of the last step's streams)")
+    ap.add_argument("--no-legs", action="store_true", help="skip every leg outside the timed region (parity, decompress, generate, config0/1/4)")
+    ap.add_argument("--kernel-config", type=int, default=-1, help="kernel configuration (role split) of the timed steps; -1 = library default")
+    ap.add_argument("--c4-streams", type=int, default=100, help="config4 leg: number of streams")
+    ap.add_argument("--c4-bytes", type=int, default=131072, help="config4 leg: bytes per stream (BASELINE.json: 1000000; truncated to keep the run short, stated in the line)")
     ap.add_argument("--verify", type=int, default=1, help="streams per rank checked by a GPU decompress round trip after timing")
     ap.add_argument("--no-generate", action="store_true", help="skip the configs[3] leg (batched generation from a checkpoint)")
     ap.add_argument("--gen-train-bytes", type=int, default=65536, help="bytes of the enwik-shaped corpus the generation checkpoint is trained on")
@@ -67,6 +83,18 @@ def parse_args():
                     help="chunks = configs[1] (default, the metric's configuration); enwik = configs[4]: --chunks streams of --chunk-bytes "
                          "bytes cut from the enwik-shaped corpus (100 x 1000000 in BASELINE.json)")
     return ap.parse_args()
+
+
+def make_config(args, world):
+    """`config` of the JSON line; identical for both arms (the reference arm samples it, see cpu_baseline.sample)."""
+    if args.workload == "chunks":
+        wl = "configs[1]: independent 64 KiB synthetic-text chunks compressed from scratch, one CTA per stream"
+    else:
+        wl = "configs[4]: enwik-shaped corpus cut into independent streams, sharded over the GPUs, NCCL gather of sizes+checksums"
+    return {"workload": wl, "chunk_bytes": args.chunk_bytes, "chunks_per_step": args.chunks, "chunks_per_step_all_gpus": args.chunks * world,
+            "chunk_set": "step k of rank r compresses chunks r*4096 + (k*chunks_per_step + i) mod 4096 of the synthetic-text set (gmix_b200/synth.py)",
+            "l2": "256 MiB flush write between timed steps; per-stream arenas exceed L2",
+            "parallelism": f"streams sharded over {world} GPU(s), all_gather of sizes+checksums per step"}
 
 
 def peaks():
@@ -188,8 +216,9 @@ def reference_binary():
     return p2, "port"
 
 
-def cpu_wave(binary, chunks, workdir, cores):
-    """Compress `chunks` with one process per core (at most `cores` at a time); returns wall seconds."""
+def cpu_wave(binary, chunks, workdir, cores, keep_outputs=False):
+    """Compress `chunks` with one process per core (at most `cores` at a time); returns wall seconds (and the
+    compressed streams when keep_outputs)."""
     paths = []
     for i, c in enumerate(chunks):
         p = os.path.join(workdir, f"c{i}.in")
@@ -209,49 +238,71 @@ def cpu_wave(binary, chunks, workdir, cores):
                     raise RuntimeError(f"{binary} exited with {p.returncode}")
                 running.remove(p)
         time.sleep(0.005)
-    return time.perf_counter() - t0
+    dt = time.perf_counter() - t0
+    if keep_outputs:
+        return dt, [open(p + ".gmix", "rb").read() for p in paths]
+    return dt
 
 
-def cpu_baseline(sample_bytes, cores=None):
-    """Bounded sample: one wave of `cores` streams of `sample_bytes` (prefixes of configs[1] chunks)."""
+def first_diff_bit(a, b):
+    for i, (x, y) in enumerate(zip(a, b)):
+        if x != y:
+            return 8 * i + (7 - ((x ^ y).bit_length() - 1))
+    return 8 * min(len(a), len(b)) if len(a) != len(b) else None
+
+
+def cpu_baseline_and_parity(ids, size, gpu_streams, cores=None):
+    """One wave of the unmodified reference CLI over FULL chunks of the timed batch, one `gmix -c` process per host core:
+    the wall time is the CPU baseline, the bytes are the parity check of the GPU's streams for the same chunks."""
     binary, kind = reference_binary()
     cores = cores or os.cpu_count() or 1
-    chunks = make_chunks(list(range(cores)), sample_bytes)
+    k = min(cores, len(ids))
+    chunks = make_chunks(ids[:k], size)
     with tempfile.TemporaryDirectory(prefix="gmix_cpu_") as wd:
         os.makedirs(os.path.join(wd, "analysis"), exist_ok=True)
-        dt = cpu_wave(binary, chunks, wd, cores)
-    return {"value": cores * sample_bytes / dt / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"{cores} streams x first {sample_bytes} B of configs[1] chunks, one `gmix -c` process per core, "
-                      f"{dt:.1f} s wall incl. process start-up"}
+        dt, ref = cpu_wave(binary, chunks, wd, cores, keep_outputs=True)
+    base = {"value": k * size / dt / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{k} full {size}-byte chunks of the timed batch (chunk ids {ids[0]}..), one `gmix -c` process per core in one wave, "
+                      f"{dt:.1f} s wall incl. process start-up (0.7 s of ~{dt:.0f})"}
+    same = [g == r for g, r in zip(gpu_streams[:k], ref)]
+    fd = None
+    for g, r in zip(gpu_streams[:k], ref):
+        if g != r:
+            fd = first_diff_bit(g, r)
+            break
+    gb, rb = sum(len(g) for g in gpu_streams[:k]), sum(len(r) for r in ref)
+    parity = {"checked": k, "identical": sum(same), "bits_per_byte_delta": 8.0 * (gb - rb) / (k * size), "first_diff_bit": fd,
+              "against": f"oracle/_ref/gmix -c ({kind}) on the same chunks of the timed batch"}
+    return base, parity
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     binary, kind = reference_binary()
     cores = os.cpu_count() or 1
-    # a step = one wave of one stream per core; bounded sample: the first 16 KiB of each chunk
-    sample = min(args.chunk_bytes, 16384)
+    # a step = one wave of one FULL chunk per host core: the first `cores` chunks of the step's chunk list
+    size = args.chunk_bytes
     times = []
     with tempfile.TemporaryDirectory(prefix="gmix_ref_") as wd:
         os.makedirs(os.path.join(wd, "analysis"), exist_ok=True)
         for step in range(args.warmup + args.steps):
-            chunks = make_chunks(chunk_ids(0, step, cores), sample)
+            chunks = make_chunks(chunk_ids(0, step, args.chunks)[:cores], size)
             dt = cpu_wave(binary, chunks, wd, cores)
             if step >= args.warmup:
                 times.append(dt)
     total = sum(times)
-    value = args.steps * cores * sample / total / 1e6
+    value = args.steps * cores * size / total / 1e6
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32+u8 (bit-exact integer/fp32 model state)", "data": "synthetic",
-        "config": {"workload": "configs[1]: independent 64 KiB synthetic-text chunks compressed from scratch",
-                   "chunk_bytes": args.chunk_bytes, "chunks_per_step": cores,
-                   "sample": f"first {sample} B of each chunk, one stream per host core per step"},
+        "config": make_config(args, world),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": f"{cores} streams x first {sample} B per step, one `gmix -c` process per core (strict -O2 build)"},
+                         "sample": f"per step the first {cores} chunks of the step's {args.chunks}-chunk list, FULL {size}-byte chunks, one "
+                                   f"`gmix -c` process per host core in one wave (strict -O2 build), process start-up inside the timed region"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -286,6 +337,10 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     ctx = gmix_b200.Context(local)
+    if args.kernel_config >= 0:
+        ctx.set_kernel_config(args.kernel_config)
+    if args.no_legs:
+        args.no_decompress = args.no_generate = True
     stream = torch.cuda.current_stream()
     ctx.set_cuda_stream(stream.cuda_stream)
     n, size = args.chunks, args.chunk_bytes
@@ -353,6 +408,20 @@ def run_ours(args):
         raise SystemExit(f"bench.py: {bad} streams failed on rank {rank}: {d_status[d_status != 0][:8].tolist()}")
     comp_bytes = int(d_len.sum().item())
     value = world * n * size * args.steps / (ms_total / 1e3) / 1e6
+    resident, arena_mib = ctx.resident_streams, ctx.arena_bytes >> 20
+    kc = ctx.kernel_configs()[ctx.kernel_config]
+    kcfg_desc = f"config {ctx.kernel_config}: {kc[0]} bit-role warps + {kc[1]} LSTM-role warps + 1 PPMd warp per stream CTA, {kc[2]} CTAs/SM"
+    kernel_name = f"gmx::StreamKernel<{kc[0]}, {kc[1]}, MODE_COMPRESS, {kc[2]}, false>"
+
+    # ---- parity of the TIMED batch against the unmodified reference + CPU baseline (one wave of full chunks) --------
+    cpu_base, parity = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "chunks":
+        kpar = min(os.cpu_count() or 1, n)
+        lens = d_len[:kpar].cpu().tolist()
+        gpu_streams = [bytes(d_out[i * cap:i * cap + lens[i]].cpu().numpy()) for i in range(kpar)]
+        cpu_base, parity = cpu_baseline_and_parity(chunk_ids(rank, total_steps - 1, n, total_set), size, gpu_streams)
+        if parity["identical"] != parity["checked"]:
+            print(f"bench.py: WARNING parity {parity}", file=sys.stderr)
 
     # ---- parity spot check outside the timed region: GPU decompress of the last step's streams ------
     if args.verify:
@@ -430,6 +499,82 @@ def run_ours(args):
         model.close()
         ctx.set_cuda_stream(stream.cuda_stream)
 
+    # ---- configs[1] as worded: all 4096 chunks in ONE host-pointer call (several waves of resident streams) -----------
+    config1_4096 = None
+    if not args.no_legs and args.workload == "chunks":
+        ctx.set_cuda_stream(0)
+        n4 = 4096
+        big = make_chunks(chunk_ids(rank, 0, n4), size)
+        h_big = torch.frombuffer(bytearray(b"".join(big)), dtype=torch.uint8).pin_memory()
+        del big
+        big_in_off = (torch.arange(n4 + 1, dtype=torch.int64) * size).numpy()
+        big_out_off = (torch.arange(n4 + 1, dtype=torch.int64) * cap).numpy()
+        h_big_out = torch.zeros(n4 * cap + 16, dtype=torch.uint8).pin_memory()
+        h_big_len = torch.zeros(n4, dtype=torch.int64).pin_memory()
+        h_big_status = torch.zeros(n4, dtype=torch.int32).pin_memory()
+        barrier()
+        t0 = time.perf_counter()
+        rc = ctx.lib.gmx_compress_batch(ctx.h, h_big.data_ptr(), big_in_off.ctypes.data, n4, h_big_out.data_ptr(), big_out_off.ctypes.data,
+                                        h_big_len.data_ptr(), h_big_status.data_ptr())
+        ctx._check(rc, "gmx_compress_batch")
+        comp_total = int(h_big_len.sum().item())
+        barrier()
+        dt4 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        k4 = torch.tensor([ctx.last_kernel_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt4, op=dist.ReduceOp.MAX)
+            dist.all_reduce(k4, op=dist.ReduceOp.MAX)
+        config1_4096 = {"e2e": world * n4 * size / float(dt4.item()) / 1e6, "value": world * n4 * size / (float(k4.item()) / 1e3) / 1e6, "unit": UNIT,
+                        "chunks_per_gpu": n4, "waves": -(-n4 // ctx.resident_streams), "bits_per_byte": 8.0 * comp_total / (n4 * size),
+                        "workload": "configs[1]: 4096 independent 64 KiB chunks in one gmx_compress_batch call per GPU (host buffers; `value` = kernel time only)"}
+        del h_big, h_big_out
+        ctx.set_cuda_stream(stream.cuda_stream)
+
+    # ---- configs[0]: dictionary/english.dic as a single stream (rank 0), md5 against the reference's ----------------------
+    config0 = None
+    if not args.no_legs and rank == 0:
+        import hashlib
+        ctx.set_cuda_stream(0)
+        dic = open(os.path.join(ROOT, "tests", "data", "english.dic"), "rb").read()
+        known = json.load(open(os.path.join(ROOT, "tests", "golden", "known_answers.json")))["english_dic_full"]
+        t0 = time.perf_counter()
+        comp0 = ctx.compress_batch([dic])[0]
+        dt0 = time.perf_counter() - t0
+        config0 = {"value": len(dic) / dt0 / 1e6, "unit": UNIT, "seconds": dt0, "input_bytes": len(dic), "output_bytes": len(comp0),
+                   "md5_matches_reference": hashlib.md5(comp0).hexdigest() == known["md5"] and len(comp0) == known["output_bytes"],
+                   "workload": "configs[0]: dictionary/english.dic as ONE stream (one CTA: single-stream latency), host buffers"}
+        ctx.set_cuda_stream(stream.cuda_stream)
+
+    # ---- configs[4]: enwik-shaped corpus in equal streams sharded over the ranks (strong scaling), NCCL gather -----------
+    config4 = None
+    if not args.no_legs:
+        from gmix_b200 import shard, synth
+        ctx.set_cuda_stream(0)
+        ns4, sz4 = args.c4_streams, args.c4_bytes
+        corpus4 = synth.enwik_shaped_corpus(ns4 * sz4)
+        lo, hi = shard.shard_ranges([sz4] * ns4, world)[rank]
+        mine = [corpus4[i * sz4:(i + 1) * sz4] for i in range(lo, hi)]
+        barrier()
+        t0 = time.perf_counter()
+        comp4 = ctx.compress_batch(mine) if mine else []
+        rec = torch.zeros(2 * ns4, dtype=torch.int64, device=dev)
+        for j, cst in enumerate(comp4):
+            rec[2 * (lo + j)] = len(cst)
+            rec[2 * (lo + j) + 1] = shard.fnv1a64(cst) - (1 << 64) if shard.fnv1a64(cst) >= (1 << 63) else shard.fnv1a64(cst)
+        if world > 1:
+            dist.all_reduce(rec, op=dist.ReduceOp.SUM)      # disjoint slots: a gather of {size, checksum} per stream
+        barrier()
+        dt4s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt4s, op=dist.ReduceOp.MAX)
+        sizes = rec[0::2].cpu().tolist()
+        config4 = {"value": ns4 * sz4 / float(dt4s.item()) / 1e6, "unit": UNIT, "scaling": "strong", "streams": ns4, "stream_bytes": sz4,
+                   "streams_per_gpu": [b - a for a, b in shard.shard_ranges([sz4] * ns4, world)], "bits_per_byte": 8.0 * sum(sizes) / (ns4 * sz4),
+                   "all_streams_reported": all(x > 5 for x in sizes),
+                   "workload": f"configs[4]: {ns4} x {sz4} B of the enwik-shaped corpus (BASELINE.json: 100 x 1 000 000 B; truncated to bound the run), "
+                               f"contiguous stream ranges per rank, one NCCL reduction gathers sizes + FNV-1a checksums; host buffers"}
+        ctx.set_cuda_stream(stream.cuda_stream)
+
     # ---- end-to-end measurement through the host-pointer C ABI ---------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -467,23 +612,20 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32+u8 (bit-exact integer/fp32 model state)", "data": "synthetic",
-            "config": {"workload": "configs[1]: independent 64 KiB synthetic-text chunks compressed from scratch, one CTA per stream" if args.workload == "chunks"
-                       else "configs[4]: enwik-shaped corpus cut into independent streams, sharded over the GPUs, NCCL gather of sizes+checksums",
-                       "chunk_bytes": size, "chunks_per_step": n, "chunks_per_step_all_gpus": n * world,
-                       "resident_streams_per_gpu": ctx.resident_streams, "arena_mib_per_stream": ctx.arena_bytes >> 20,
-                       "l2": "256 MiB flush write between timed steps; per-stream arenas exceed L2",
-                       "parallelism": f"streams sharded over {world} GPU(s), all_gather of sizes+checksums per step"},
+            "config": make_config(args, world),
+            "runtime": {"resident_streams_per_gpu": resident, "arena_mib_per_stream": arena_mib, "kernel_config": kcfg_desc},
             "bits_per_byte": 8.0 * comp_bytes / (n * size),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / pk["hbm_gbs"], "traffic": tpb * n * size if tpb else None,
                          "traffic_source": f"{tpb:.0f} B of DRAM traffic per input byte in {tsrc}, scaled to this launch's input bytes" if tpb else None,
                          "peak_kind": pk_kind,
-                         "kernel": "gmx::StreamKernel<128, MODE_COMPRESS, 8, false>", "kernel_ms": kernel_ms_avg,
+                         "kernel": kernel_name, "kernel_ms": kernel_ms_avg,
                          "algorithmic_bytes_per_input_byte": ALGO_BYTES_PER_INPUT_BYTE},
-            "e2e": e2e, "decompress": decomp, "generate": generate, "retried_streams": ctx.retried_streams, "gpu_launches": gpu_launches, "clocks": clocks,
+            "e2e": e2e, "parity": parity, "decompress": decomp, "generate": generate, "config1_4096": config1_4096, "config0": config0,
+            "config4": config4, "retried_streams": ctx.retried_streams, "gpu_launches": gpu_launches, "clocks": clocks,
         }
-        if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(min(size, 8192))
+        if cpu_base:
+            line["cpu_baseline"] = cpu_base
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -49,6 +49,7 @@ def load_library():
     lib.gmx_resident_streams.argtypes = [C.c_void_p]
     lib.gmx_resident_streams.restype = C.c_uint32
     lib.gmx_set_kernel_config.argtypes = [C.c_void_p, C.c_int]
+    lib.gmx_get_kernel_config.argtypes = [C.c_void_p]
     lib.gmx_kernel_config_info.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.gmx_arena_count.argtypes = [C.c_void_p]
     lib.gmx_arena_count.restype = C.c_uint32
@@ -142,10 +143,6 @@ class Model:
         if getattr(self, "h", None) and self.ctx.h:   # a closed Context has already freed its models
             self.ctx.lib.gmx_model_free(self.h)
         self.h = None
-
-    @property
-    def max_resident_streams(self):
-        return int(self.lib.gmx_arena_count(self.h))
 
     @property
     def arena_bytes(self):
@@ -332,6 +329,10 @@ class Context:
     def set_kernel_config(self, cfg):
         self._check(self.lib.gmx_set_kernel_config(self.h, int(cfg)), "gmx_set_kernel_config")
 
+    @property
+    def kernel_config(self):
+        return int(self.lib.gmx_get_kernel_config(self.h))
+
     def kernel_configs(self):
         """[(bit warps, LSTM warps, CTAs per SM)] of every kernel configuration in the library."""
         out = []
@@ -345,6 +346,10 @@ class Context:
     @property
     def resident_streams(self):
         return int(self.lib.gmx_resident_streams(self.h))
+
+    @property
+    def max_resident_streams(self):
+        return int(self.lib.gmx_arena_count(self.h))
 
     @property
     def arena_bytes(self):

@@ -441,6 +441,7 @@ int gmx_set_kernel_config(gmx_ctx* c, int cfg) {
   if (cfg != c->kcfg) { c->kcfg = cfg; FreeArenas(c); }   // residency (arena count) depends on the configuration
   return 0;
 }
+int gmx_get_kernel_config(const gmx_ctx* c) { return c ? c->kcfg : -1; }
 int gmx_kernel_config_count(void) { return gmx::kNumKernelConfigs; }
 int gmx_kernel_config_info(int cfg, int* bit_warps, int* lstm_warps, int* ctas_per_sm) {
   if (cfg < 0 || cfg >= gmx::kNumKernelConfigs) return GMX_E_ARG;

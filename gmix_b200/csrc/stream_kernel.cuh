@@ -206,7 +206,7 @@ struct StreamSmem {
   alignas(16) float l_err256[256];         // LSTM role scratch (output pre-activations, BPTT error vector, symbol lists)
   alignas(16) float l_hidden[L_HID + 1]; float l_state[L_CELLS], l_state_err[L_CELLS], l_stored_err[L_CELLS], l_hidden_err[L_CELLS];
   float l_gate[3][L_CELLS], l_gerr[3][L_CELLS];
-  float l_red[16];
+  float l_red[24];               // 0..2 ivar, 3 sum, 4..11 / 12..19 per-warp partial results, 20..22 BPTT sums
   uint32_t p_masked[8];          // PPMd: bit sym = CharMask[sym] == EscCount (ppmd.cuh)
   uint8_t l_hist[L_HORIZON], l_symin[L_HORIZON];
   uint32_t l_epoch, l_update_steps, l_old_input, l_fused;
@@ -215,13 +215,11 @@ struct StreamSmem {
   uint64_t out_pos, out_cap, in_pos, in_len;
   // ---- role pipeline (reset at every stream start; not part of a checkpoint) ----
   BytePacket pkt[PKT_RING];
-  uint32_t n_known;        // bytes whose value is decided (compress: all of them from the start)
   uint32_t n_ppm;          // byte boundaries whose PPMd distribution has been published in ppm
   uint32_t n_ppm_used;     // byte boundaries whose distribution the LSTM role no longer reads
   uint32_t n_pkt;          // byte boundaries whose packet (and lprob) is published
   uint32_t n_done;         // bytes the bit role has finished (frees packet slots)
   uint32_t bit_stop, lstm_stop;   // role-uniform copies of `error != 0`, refreshed at role-defined points
-  uint8_t kbyte[4];        // lockstep modes: value of byte b at [b & 3]
   uint32_t byte0;          // byte in front of the stream (0 from scratch: the reference's phantom first byte)
 };
 
@@ -577,7 +575,7 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
   }
   __syncthreads();
   if (tid == 0) {   // role pipeline
-    s.n_known = 0; s.n_ppm = 0; s.n_ppm_used = 0; s.n_pkt = 0; s.n_done = 0; s.bit_stop = 0; s.lstm_stop = 0;
+    s.n_ppm = 0; s.n_ppm_used = 0; s.n_pkt = 0; s.n_done = 0; s.bit_stop = 0; s.lstm_stop = 0;
     // the byte in front of the stream: none from scratch (the reference's models see a phantom 0 at their first byte
     // boundary), the checkpoint's last byte otherwise (it is completed by the first BasicContexts::Predict)
     s.byte0 = s.first_prediction ? 0u : (uint32_t)(s.recent_bits * 2 + s.new_bit) & 0xffu;
@@ -599,29 +597,36 @@ GMX_DEV void LstmOutputStep(StreamSmem& s, const Arena& A, uint32_t last, uint32
   float* wc = A.at<float>(L.l_wout) + (size_t)cur * L_HID * L_NOUT;
   const float lr = (float)0.03;
   constexpr int NQ = L_NOUT / 4;                       // 64 quads of adjacent outputs
-  constexpr int H = NL >= NQ ? NL / NQ : 1;            // row ranges per quad
+  constexpr int H = NL >= NQ ? NL / NQ : 1;            // row ranges per quad (more threads than quads)
+  constexpr int QPT = NL >= NQ ? 1 : NQ / NL;          // quads per thread (fewer threads than quads), advanced together
   constexpr int ROWS = (L_HID + H - 1) / H;
-#pragma unroll 1
-  for (int item = ltid; item < NQ * H; item += NL) {
-    const int q = item & (NQ - 1), half = item / NQ;   // outputs 4q..4q+3, rows [half * ROWS, ...)
-    float le[4];
+  static_assert(NL >= NQ || NQ % NL == 0, "a role smaller than 64 threads must divide 64");
+  if (ltid >= NQ * H) return;
+  const int q0 = ltid & (NQ - 1), half = ltid / NQ;    // outputs 4q..4q+3 for q = q0 + k * NL, rows [half * ROWS, ...)
+  float le[QPT][4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t i = 4 * q + k;
+  for (int k = 0; k < QPT; ++k)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint32_t i = 4 * (q0 + k * NL) + c;
       const float err = i == byte ? f_sub(s.lprob[i], 1.0f) : s.lprob[i];
-      le[k] = f_mul(lr, err);
+      le[k][c] = f_mul(lr, err);
     }
-    const float4* wl4 = (const float4*)wl + q;
-    float4* wc4 = (float4*)wc + q;
-    const int j0 = half * ROWS;
-    const int j1 = j0 + ROWS < L_HID ? j0 + ROWS : L_HID;
-GMX_UNROLL(4)
-    for (int j = j0; j < j1; ++j) {
-      const float h = s.l_hidden[j];
-      float4 w = LoadStream4(wl4 + j * NQ);
-      w.x = f_sub(w.x, f_mul(le[0], h)); w.y = f_sub(w.y, f_mul(le[1], h));
-      w.z = f_sub(w.z, f_mul(le[2], h)); w.w = f_sub(w.w, f_mul(le[3], h));
-      StoreStream4(wc4 + j * NQ, w);
+  const float4* wl4 = (const float4*)wl + q0;
+  float4* wc4 = (float4*)wc + q0;
+  const int j0 = half * ROWS;
+  const int j1 = j0 + ROWS < L_HID ? j0 + ROWS : L_HID;
+GMX_UNROLL(QPT > 1 ? 2 : 4)
+  for (int j = j0; j < j1; ++j) {
+    const float h = s.l_hidden[j];
+    float4 w[QPT];
+#pragma unroll
+    for (int k = 0; k < QPT; ++k) w[k] = LoadStream4(wl4 + j * NQ + k * NL);
+#pragma unroll
+    for (int k = 0; k < QPT; ++k) {
+      w[k].x = f_sub(w[k].x, f_mul(le[k][0], h)); w[k].y = f_sub(w[k].y, f_mul(le[k][1], h));
+      w[k].z = f_sub(w[k].z, f_mul(le[k][2], h)); w[k].w = f_sub(w[k].w, f_mul(le[k][3], h));
+      StoreStream4(wc4 + j * NQ + k * NL, w[k]);
     }
   }
 }
@@ -667,53 +672,58 @@ GMX_DEV inline void PathNodes(BytePacket& pk, const float* probs, uint32_t byte,
 }
 
 // Gate pre-activations f = w[sym]; f += in[j] * w[256 + j], j ascending (lstm-layer.cpp:227-232) for the 150 gate rows:
-// R rows per thread as independent sequential sums (rows ltid, ltid + NL, ...), weights as 16-byte loads straight from
-// global memory (the four consecutive input columns of a cell are one float4, cells adjacent: a warp load is 512
-// contiguous bytes), marked evict-first in L2: the gate weights of all resident streams are 1.7 x the L2.
+// R rows per thread as independent sequential sums (rows t, t + NA, ... of the NA = ceil(150 / R) working threads),
+// weights as 16-byte loads straight from global memory (the four consecutive input columns of a cell are one float4,
+// cells adjacent: a warp load is 512 contiguous bytes), marked evict-first in L2: the gate weights of all resident
+// streams are 1.7 x the L2. The caller has started L2 prefetches of the whole 185 KB (LstmForward), and every row's
+// next quad is requested right after its current one is consumed, so R loads per thread are always in flight without
+// a second set of registers.
 template <int NL>
 GMX_DEV void LstmGateDots(StreamSmem& s, const float* W, uint32_t sym, int ltid) {
   constexpr int NROWS = 3 * L_CELLS;
   constexpr int R = (NROWS + NL - 1) / NL;
+  constexpr int NA = (NROWS + R - 1) / R;
   constexpr int NQ = L_NOUT / 4 + L_CELLS / 4 + 1;   // 64 quads of ppm, 12 of hidden 0..47, 1 of {h48, h49, bias, pad}
+  if (ltid >= NA) return;
   float f[R];
   const float4* w[R];
-#pragma unroll
-  for (int k = 0; k < R; ++k) {
-    const int r = ltid + k * NL < NROWS ? ltid + k * NL : 0;   // surplus slots recompute row 0 and drop it
-    const int g = r / L_CELLS, i = r - g * L_CELLS;
-    f[k] = W[LstmW(g, (int)sym, i)];
-    w[k] = (const float4*)W + ((size_t)g * L_ROWQ + L_NOUT / 4) * L_CELLS + i;
-  }
+  float4 a[R];
 #if defined(__CUDA_ARCH__)
   const uint64_t pol = PolicyEvictFirst();
 #define GMX_GATE_LD(p) LoadHint4(p, pol)
 #else
 #define GMX_GATE_LD(p) (*(p))
 #endif
-GMX_UNROLL(R <= 3 ? 2 : 1)
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const int r = ltid + k * NA < NROWS ? ltid + k * NA : 0;   // surplus slots (R * NA > 150) recompute row 0 and drop it
+    const int g = r / L_CELLS, i = r - g * L_CELLS;
+    w[k] = (const float4*)W + ((size_t)g * L_ROWQ + L_NOUT / 4) * L_CELLS + i;
+    a[k] = GMX_GATE_LD(w[k]);
+    f[k] = W[LstmW(g, (int)sym, i)];
+  }
+#pragma unroll 1
   for (int q = 0; q < NQ - 1; ++q) {
     const float4 x = q < L_NOUT / 4 ? ((const float4*)s.ppm)[q] : ((const float4*)s.l_hidden)[q - L_NOUT / 4];
-    float4 a[R];
-#pragma unroll
-    for (int k = 0; k < R; ++k) a[k] = GMX_GATE_LD(w[k] + q * L_CELLS);
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-      f[k] = f_add(f[k], f_mul(x.x, a[k].x)); f[k] = f_add(f[k], f_mul(x.y, a[k].y));
-      f[k] = f_add(f[k], f_mul(x.z, a[k].z)); f[k] = f_add(f[k], f_mul(x.w, a[k].w));
+      const float4 c = a[k];
+      a[k] = GMX_GATE_LD(w[k] + (q + 1) * L_CELLS);
+      f[k] = f_add(f[k], f_mul(x.x, c.x)); f[k] = f_add(f[k], f_mul(x.y, c.y));
+      f[k] = f_add(f[k], f_mul(x.z, c.z)); f[k] = f_add(f[k], f_mul(x.w, c.w));
     }
   }
   {   // hidden 48, 49 and the bias input (1.0); the fourth column is padding
     const float h48 = s.l_hidden[L_CELLS - 2], h49 = s.l_hidden[L_CELLS - 1];
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-      const float4 a = GMX_GATE_LD(w[k] + (NQ - 1) * L_CELLS);
-      f[k] = f_add(f[k], f_mul(h48, a.x)); f[k] = f_add(f[k], f_mul(h49, a.y)); f[k] = f_add(f[k], f_mul(1.0f, a.z));
+      f[k] = f_add(f[k], f_mul(h48, a[k].x)); f[k] = f_add(f[k], f_mul(h49, a[k].y)); f[k] = f_add(f[k], f_mul(1.0f, a[k].z));
     }
   }
 #undef GMX_GATE_LD
 #pragma unroll
   for (int k = 0; k < R; ++k) {
-    const int r = ltid + k * NL;
+    const int r = ltid + k * NA;
     if (r < NROWS) { const int g = r / L_CELLS; s.l_gate[g][r - g * L_CELLS] = f[k]; }
   }
 }
@@ -727,6 +737,14 @@ GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, u
   const ArenaLayout& L = *A.L;
   const uint32_t e = s.l_epoch;
   float* lin_e = A.at<float>(L.l_lin) + e * (L_NIN + 1);
+  // The pass streams 184.8 KB of gate weights and then the 52 KB output layer of this epoch slot. Ask L2 for all of it
+  // now: the role has few threads, so its own loads keep only a few KB in flight; the prefetches put the rest of the
+  // HBM latency behind them (the lines are consumed within this pass, long before L2 could evict them).
+  {
+    const float* W = A.at<float>(L.l_w);
+    for (int g = 0; g < 3; ++g) PrefetchRange(W + LstmW(g, L_NOUT, 0), (L_ROWQ - L_NOUT / 4) * L_CELLS * 16, ltid, NL);
+    PrefetchRange(A.at<float>(L.l_wout) + (size_t)e * L_HID * L_NOUT, L_HID * L_NOUT * 4, ltid, NL);
+  }
   // layer_input[e] = [ppm 256 | hidden 50 | 1]  (SetInput lstm.cpp:45-50, copy :94-96)
   for (int i = ltid; i < L_NIN; i += NL) lin_e[i] = i < 256 ? s.ppm[i] : i < 306 ? s.l_hidden[i - 256] : 1.0f;
   for (int i = ltid; i < L_CELLS; i += NL) A.at<float>(L.l_last)[e * L_CELLS + i] = s.l_state[i];  // last_state_[epoch] = state_
@@ -771,19 +789,32 @@ GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, u
   // per work item: one 16-byte load feeds 4 sequential sums
   const float* wo = A.at<float>(L.l_wout) + (size_t)e * L_HID * L_NOUT;
   float mx = 0.0f;
-#pragma unroll 1
-  for (int t = ltid; t < L_NOUT / 4; t += NL) {
-    const float4* wo4 = (const float4*)wo + t;
-    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-#pragma unroll 17
-    for (int j = 0; j < L_HID; ++j) {
-      const float h = s.l_hidden[j];
-      const float4 w = wo4[j * (L_NOUT / 4)];
-      a0 = f_add(a0, f_mul(h, w.x)); a1 = f_add(a1, f_mul(h, w.y));
-      a2 = f_add(a2, f_mul(h, w.z)); a3 = f_add(a3, f_mul(h, w.w));
+  {
+    constexpr int NQ = L_NOUT / 4;
+    constexpr int QPT = NL >= NQ ? 1 : NQ / NL;   // quads of adjacent outputs per thread, advanced together
+    if (ltid < NQ) {
+      const float4* wo4 = (const float4*)wo + ltid;
+      float acc[QPT][4];
+#pragma unroll
+      for (int k = 0; k < QPT; ++k) { acc[k][0] = 0.0f; acc[k][1] = 0.0f; acc[k][2] = 0.0f; acc[k][3] = 0.0f; }
+GMX_UNROLL(QPT > 1 ? 3 : 17)
+      for (int j = 0; j < L_HID; ++j) {
+        const float h = s.l_hidden[j];
+#pragma unroll
+        for (int k = 0; k < QPT; ++k) {
+          const float4 w = wo4[j * NQ + k * NL];
+          acc[k][0] = f_add(acc[k][0], f_mul(h, w.x)); acc[k][1] = f_add(acc[k][1], f_mul(h, w.y));
+          acc[k][2] = f_add(acc[k][2], f_mul(h, w.z)); acc[k][3] = f_add(acc[k][3], f_mul(h, w.w));
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < QPT; ++k)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          s.l_err256[4 * (ltid + k * NL) + c] = acc[k][c];
+          mx = acc[k][c] > mx ? acc[k][c] : mx;
+        }
     }
-    s.l_err256[4 * t + 0] = a0; s.l_err256[4 * t + 1] = a1; s.l_err256[4 * t + 2] = a2; s.l_err256[4 * t + 3] = a3;
-    mx = a0 > mx ? a0 : mx; mx = a1 > mx ? a1 : mx; mx = a2 > mx ? a2 : mx; mx = a3 > mx ? a3 : mx;
   }
   // max over all outputs, seeded with 0 (max is order independent)
   for (int o = 16; o > 0; o >>= 1) { const float v = __shfl_xor_sync(0xffffffffu, mx, o); mx = v > mx ? v : mx; }
@@ -814,14 +845,14 @@ GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, u
     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
     if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
   }
-  if ((ltid & 31) == 0) { s.l_red[4 + (ltid >> 5)] = bv; s.l_red[8 + (ltid >> 5)] = (float)bi; }
+  if ((ltid & 31) == 0) { s.l_red[4 + (ltid >> 5)] = bv; s.l_red[12 + (ltid >> 5)] = (float)bi; }
   GroupSync<NL>(BAR_LSTM);
   BytePacket& pk = s.pkt[b % PKT_RING];
   if (ltid < 32) {
     if (ltid == 0) {
       float v = 0.0f; int vi = 0;
       for (int wi = 0; wi < NL / 32; ++wi) {
-        const float ov = s.l_red[4 + wi]; const int oi = (int)s.l_red[8 + wi];
+        const float ov = s.l_red[4 + wi]; const int oi = (int)s.l_red[12 + wi];
         if (ov > v || (ov == v && ov > 0.0f && oi < vi)) { v = ov; vi = oi; }
       }
       pk.lstm_ctx = v > 0.0f ? (uint32_t)vi : 0u;
@@ -832,7 +863,7 @@ GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, u
     __syncwarp();
     if (ltid == 0) Publish(&s.n_pkt, b + 1);
   }
-  static_assert(NL / 32 <= 4, "l_red slots 4..7 / 8..11 hold one partial result per LSTM warp");
+  static_assert(NL / 32 <= 8, "l_red slots 4..11 / 12..19 hold one partial result per warp");
   lap.mark(18);
   // AHEAD knows the byte this distribution is about to code, so the output-layer step that Lstm::Perceive performs
   // after the byte (same operands: these probabilities, this hidden state, the layer of slot e) runs now, while slot e
@@ -864,8 +895,11 @@ GMX_DEV void LstmBptt(StreamSmem& s, const Arena& A, const StreamParams& P, int 
   }
   GroupSync<NL>(BAR_LSTM);
   constexpr int CPT = (L_CELLS + NL - 1) / NL;   // cells per thread in the cell-parallel phases (2 when the role is one warp)
+  PrefetchRange(A.at<float>(L.l_wout) + (size_t)(L_HORIZON - 1) * L_HID * L_NOUT, L_HID * L_NOUT * 4, ltid, NL);
 #pragma unroll 1
   for (int ep = L_HORIZON - 1; ep >= 0; --ep) {
+    // the output layer of the next (earlier) epoch: 52 KB this pass will stream one epoch from now
+    if (ep > 0) PrefetchRange(A.at<float>(L.l_wout) + (size_t)(ep - 1) * L_HID * L_NOUT, L_HID * L_NOUT * 4, ltid, NL);
     const float* out_e = A.at<float>(L.l_out) + ep * L_NOUT;
     for (int i = ltid; i < L_NOUT; i += NL)
       s.l_err256[i] = (uint32_t)i == s.l_hist[ep] ? f_sub(out_e[i], 1.0f) : out_e[i];
@@ -938,13 +972,13 @@ GMX_UNROLL(GMX_BPTT_UNROLL)
       float acc = f_mul(s.l_gerr[g][L_CELLS - 1], nrm[L_CELLS - 1]);
 #pragma unroll 7
       for (int k = L_CELLS - 2; k >= 0; --k) acc = f_add(acc, f_mul(s.l_gerr[g][k], nrm[k]));
-      s.l_red[12 + g] = f_div(acc, (float)L_CELLS);
+      s.l_red[20 + g] = f_div(acc, (float)L_CELLS);
     }
     GroupSync<NL>(BAR_LSTM);
     for (int t = ltid; t < 3 * L_CELLS; t += NL) {
       const int g = t / L_CELLS, i = t - g * L_CELLS;
       const float nrm = A.at<float>(L.l_norm)[((size_t)g * L_HORIZON + ep) * L_CELLS + i];
-      const float ne = f_sub(s.l_gerr[g][i], f_mul(s.l_red[12 + g], nrm));
+      const float ne = f_sub(s.l_gerr[g][i], f_mul(s.l_red[20 + g], nrm));
       s.l_gerr[g][i] = ne;
       errh[((size_t)g * L_HORIZON + ep) * L_CELLS + i] = ne;
     }
@@ -1016,32 +1050,44 @@ GMX_UNROLL(GMX_BPTT_UNROLL)
     W4[f4] = w; M4[f4] = m; V4[f4] = v;
   }
   // (b) dense rows: grad[r][i] = sum_ep err[ep][i] * in[ep][r] as a register-tiled product, 4 rows (one quad) x 2
-  // cells per thread (one 16-byte and one 8-byte load feed 8 multiply-adds), then two float4 Adam updates.
+  // cells per thread (one 16-byte and one 8-byte load feed 8 multiply-adds), then two float4 Adam updates. A small role
+  // (<= 64 threads) takes the three gates of a tile together: the layer-input quad is loaded once for all three and
+  // 24 independent sums are in flight per thread.
   constexpr int RG = (L_NIN + 3) / 4, IP = L_CELLS / 2;
+  constexpr int GPT = NL <= 64 ? 3 : 1;
 #pragma unroll 1
-  for (int id = ltid; id < 3 * RG * IP; id += NL) {
-    const int ip = id % IP, rg = (id / IP) % RG, g = id / (IP * RG);
-    const float2* e2 = (const float2*)(errh + (size_t)g * L_HORIZON * L_CELLS + 2 * ip);
+  for (int id = ltid; id < (3 / GPT) * RG * IP; id += NL) {
+    const int ip = id % IP, rg = (id / IP) % RG, g0 = id / (IP * RG);
+    const float2* e2 = (const float2*)(errh + (size_t)g0 * L_HORIZON * L_CELLS + 2 * ip);
     const float4* x4 = (const float4*)(lin + 4 * rg);
-    float a[4][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}, {0.0f, 0.0f}, {0.0f, 0.0f}};
-#pragma unroll 4
+    float a[GPT][4][2];
+#pragma unroll
+    for (int g = 0; g < GPT; ++g)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { a[g][r][0] = 0.0f; a[g][r][1] = 0.0f; }
+GMX_UNROLL(GPT > 1 ? 2 : 4)
     for (int ep = L_HORIZON - 1; ep >= 0; --ep) {
-      const float2 e = e2[ep * (L_CELLS / 2)];
       const float4 x = x4[ep * ((L_NIN + 1) / 4)];
-      a[0][0] = f_add(a[0][0], f_mul(e.x, x.x)); a[0][1] = f_add(a[0][1], f_mul(e.y, x.x));
-      a[1][0] = f_add(a[1][0], f_mul(e.x, x.y)); a[1][1] = f_add(a[1][1], f_mul(e.y, x.y));
-      a[2][0] = f_add(a[2][0], f_mul(e.x, x.z)); a[2][1] = f_add(a[2][1], f_mul(e.y, x.z));
-      a[3][0] = f_add(a[3][0], f_mul(e.x, x.w)); a[3][1] = f_add(a[3][1], f_mul(e.y, x.w));
+#pragma unroll
+      for (int g = 0; g < GPT; ++g) {
+        const float2 e = e2[(size_t)g * (L_HORIZON * L_CELLS / 2) + ep * (L_CELLS / 2)];
+        a[g][0][0] = f_add(a[g][0][0], f_mul(e.x, x.x)); a[g][0][1] = f_add(a[g][0][1], f_mul(e.y, x.x));
+        a[g][1][0] = f_add(a[g][1][0], f_mul(e.x, x.y)); a[g][1][1] = f_add(a[g][1][1], f_mul(e.y, x.y));
+        a[g][2][0] = f_add(a[g][2][0], f_mul(e.x, x.z)); a[g][2][1] = f_add(a[g][2][1], f_mul(e.y, x.z));
+        a[g][3][0] = f_add(a[g][3][0], f_mul(e.x, x.w)); a[g][3][1] = f_add(a[g][3][1], f_mul(e.y, x.w));
+      }
     }
     const bool pad = 4 * rg + 3 >= L_NIN;   // the last quad's fourth column does not exist (stays 0)
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const size_t f4 = ((size_t)g * L_ROWQ + L_NOUT / 4 + rg) * L_CELLS + 2 * ip + c;
-      float4 w = W4[f4], m = M4[f4], v = V4[f4];
-      adam1(w.x, m.x, v.x, a[0][c]); adam1(w.y, m.y, v.y, a[1][c]); adam1(w.z, m.z, v.z, a[2][c]);
-      if (!pad) adam1(w.w, m.w, v.w, a[3][c]);
-      W4[f4] = w; M4[f4] = m; V4[f4] = v;
-    }
+    for (int g = 0; g < GPT; ++g)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const size_t f4 = ((size_t)(g0 + g) * L_ROWQ + L_NOUT / 4 + rg) * L_CELLS + 2 * ip + c;
+        float4 w = W4[f4], m = M4[f4], v = V4[f4];
+        adam1(w.x, m.x, v.x, a[g][0][c]); adam1(w.y, m.y, v.y, a[g][1][c]); adam1(w.z, m.z, v.z, a[g][2][c]);
+        if (!pad) adam1(w.w, m.w, v.w, a[g][3][c]);
+        W4[f4] = w; M4[f4] = m; V4[f4] = v;
+      }
   }
   for (int t = ltid; t < 2 * 3 * L_CELLS; t += NL) {  // gamma then beta (lstm-layer.cpp:349-352)
     const int which = t / (3 * L_CELLS), k = t - which * 3 * L_CELLS;  // k = g*CELLS + i
@@ -1142,10 +1188,10 @@ GMX_DEV inline void Bookkeeping(StreamSmem& s) {
   s.bb = s.recent_bits == 1;
 }
 
-// Everything of the bit role that only happens when a new byte has been perceived (recent_bits == 1). The packet of
-// byte boundary b has been published (the caller waited for it).
+// Everything of the bit role that only happens when a new byte has been perceived (recent_bits == 1), in two parts:
+// A needs nothing from the byte models (it can run beside them), B needs the packet of byte boundary b.
 template <int NB>
-GMX_DEV void BitBoundary(StreamSmem& s, const Arena& A, uint32_t b, int btid) {
+GMX_DEV void BitBoundaryA(StreamSmem& s, const Arena& A, int btid) {
   const ArenaLayout& L = *A.L;
   const uint32_t last_byte = s.ctx[C_LAST_BYTE];
   // (0) Nearly every gate context changes with the byte: all staged weight sets go back to the pool at once and the
@@ -1164,9 +1210,9 @@ GMX_DEV void BitBoundary(StreamSmem& s, const Arena& A, uint32_t b, int btid) {
       }
     }
   }
-  // (1) contexts: 9 intervals, 20 hashed skip contexts, 9 indirect-hash tables, the LSTM's context from the packet
+  // (1) contexts: 9 intervals, 20 hashed skip contexts, 9 indirect-hash tables
 #pragma unroll 1
-  for (int t = btid; t < 9 + 20 + NIH + 1; t += NB) {
+  for (int t = btid; t < 9 + 20 + NIH; t += NB) {
     if (t < 9) {  // IntervalContext::Predict interval-context.cpp:17-23
       const IntervalSpec sp = s.T.interval[t];
       s.ctx[C_IV0 + t] = sp.mask & ((s.ctx[C_IV0 + t] << sp.shift) + (last_byte >> sp.div_log2));
@@ -1176,7 +1222,7 @@ GMX_DEV void BitBoundary(StreamSmem& s, const Arena& A, uint32_t b, int btid) {
       uint64_t c = 0;
       for (int k = 0; k < sp.n; ++k) c = (c << 8) + RecentByte(s, sp.b[k]);
       s.ctx[id < 5 ? C_H2 + id : C_SK0 + (id - 5)] = Murmur64(c);
-    } else if (t < 29 + NIH) {  // IndirectHash::Predict indirect-hash.cpp:16-31
+    } else {  // IndirectHash::Predict indirect-hash.cpp:16-31
       const int k = t - 29;
       const IHSpec sp = s.T.ih[k];
       const uint32_t mask = (1u << sp.log2) - 1;
@@ -1200,11 +1246,14 @@ GMX_DEV void BitBoundary(StreamSmem& s, const Arena& A, uint32_t b, int btid) {
         s.ctx[C_IH0 + k] = Murmur32(tab[oh & mask]);
       }
       s.ih_hash[k] = oh;
-    } else {
-      s.ctx[C_LSTM] = s.pkt[b % PKT_RING].lstm_ctx;
     }
   }
-  GroupSync<NB>(BAR_BIT);
+}
+template <int NB>
+GMX_DEV void BitBoundaryB(StreamSmem& s, const Arena& A, uint32_t b, int btid) {
+  const ArenaLayout& L = *A.L;
+  if (btid == 0) s.ctx[C_LSTM] = s.pkt[b % PKT_RING].lstm_ctx;
+  GroupSync<NB>(BAR_BIT);   // (also orders part A's shared-memory writes when the same threads ran it)
   // Indirect row bases ((ctx << 8) % M, so that slot = (base + bit_context) % M); nothing is staged any more
   for (int k = btid; k < NIND; k += NB) s.ind_base[k] = (s.ctx[s.T.ind[k].ctx] << 8) % L.ind_size[k];
   for (int m = btid; m < NMIX; m += NB) { s.set_idx[m] = 0xFFFFFFFFu; s.set_pool[m] = 0; }
@@ -1671,77 +1720,55 @@ GMX_DEV void ParkState(const StreamSmem& s, const StreamParams& P, uint32_t sid,
   for (int i = tid; i < kWords; i += NT) dst[i] = sw[i];
 }
 
-// ---- what a stream asks of the three roles ----------------------------------------------------------
+// ---- what a stream asks of the kernel ----------------------------------------------------------------
 enum : int { MODE_COMPRESS = 0, MODE_DECOMPRESS = 1, MODE_GENERATE = 2 };
 struct StreamJob {
   const uint8_t* in;       // compress: the stream; decompress: the coded bytes; generate: the prompt
   uint8_t* out;
   uint64_t n_in;
-  uint32_t n_bound;        // byte boundaries the stream runs through
-  uint32_t n_learn;        // bytes 0 .. n_learn-1 are learned (Learn after every bit, Lstm::Perceive after the byte)
-  uint32_t n_preset;       // generate: bytes 0 .. n_preset-1 come from the prompt
+  uint32_t n_bytes;        // compress / decompress: bytes of the stream; generate: bytes to sample
+  uint32_t n_preset;       // generate: bytes 0 .. n_preset-1 come from the prompt and are learned
 };
 
-// Value of byte i for the byte-model roles: straight from the input in compress (AHEAD), from the ring the bit role
-// fills as bytes get decided otherwise (the caller has waited for n_known > i).
-template <int MODE>
-GMX_DEV inline uint32_t ByteValue(const StreamSmem& s, const StreamJob& J, uint32_t i) {
-  if (MODE == MODE_COMPRESS) return J.in[i];
-  return *(const volatile uint8_t*)&s.kbyte[i & 3];
-}
-
-// PPMd role: byte boundaries 0 .. n_bound-1.
-template <int MODE, bool PROF>
+// ==== AHEAD pipeline (compress): three roles, each over all bytes of the stream =========================
+// PPMd role: byte boundaries 0 .. n-1.
+template <bool PROF>
 GMX_DEV void PpmdRole(StreamSmem& s, const Arena& A, const StreamJob& J, ProfSmem* prof, int lane) {
-  constexpr bool AHEAD = MODE == MODE_COMPRESS;
   Lap<PROF> lap;
   lap.start(prof, lane == 0);
 #pragma unroll 1
-  for (uint32_t b = 0; b < J.n_bound; ++b) {
+  for (uint32_t b = 0; b < J.n_bytes; ++b) {
     if (__shfl_sync(0xffffffffu, VolatileLoad(&s.error), 0)) break;   // warp-uniform stop check
-    if (!AHEAD && b) { WaitAtLeast(s, &s.n_known, b, 200); lap.mark(24); }
-    const uint32_t last = b ? ByteValue<MODE>(s, J, b - 1) : s.byte0;
-    PpmdStep<PROF>(s, A, b, last, AHEAD ? (int)J.in[b] : -1, AHEAD, lane, lap);
+    PpmdStep<PROF>(s, A, b, b ? J.in[b - 1] : s.byte0, (int)J.in[b], true, lane, lap);
   }
 }
 
-// LSTM role. AHEAD: forward(b), Perceive(byte b) back to back. Lockstep: Perceive(byte b-1) as soon as that byte is
-// known (while the PPMd role updates its model with it), then forward(b).
-template <int NL, int MODE, bool PROF>
+// LSTM role: forward(b), Perceive(byte b) back to back.
+template <int NL, bool PROF>
 GMX_DEV void LstmRole(StreamSmem& s, const Arena& A, const StreamParams& P, const StreamJob& J, ProfSmem* prof, int ltid) {
-  constexpr bool AHEAD = MODE == MODE_COMPRESS;
   Lap<PROF> lap;
   lap.start(prof, ltid == 0);
 #pragma unroll 1
-  for (uint32_t b = 0; b <= J.n_bound; ++b) {
+  for (uint32_t b = 0; b < J.n_bytes; ++b) {
     if (ltid == 0) s.lstm_stop = VolatileLoad(&s.error) != 0;
     GroupSync<NL>(BAR_LSTM);
     if (s.lstm_stop) break;
-    if (!AHEAD && b >= 1 && b - 1 < J.n_learn) {
-      WaitAtLeast(s, &s.n_known, b, 200);
-      lap.mark(16);
-      LstmPerceive<NL, PROF>(s, A, P, ByteValue<MODE>(s, J, b - 1), ltid, lap);
-    }
-    if (b == J.n_bound) break;
-    if (!AHEAD && b) WaitAtLeast(s, &s.n_known, b, 200);   // the bit role has stopped reading lprob (interval nodes of byte b-1)
     WaitAtLeast(s, &s.n_ppm, b + 1, 200);
     lap.mark(16);
-    const uint32_t sym = b ? ByteValue<MODE>(s, J, b - 1) : s.byte0;
-    LstmForward<NL, PROF>(s, A, P, b, sym, AHEAD ? (int)J.in[b] : -1, ltid, lap);
-    if (AHEAD) LstmPerceive<NL, PROF>(s, A, P, J.in[b], ltid, lap);
+    LstmForward<NL, PROF>(s, A, P, b, b ? J.in[b - 1] : s.byte0, (int)J.in[b], ltid, lap);
+    LstmPerceive<NL, PROF>(s, A, P, J.in[b], ltid, lap);
   }
 }
 
-// Bit role, one bit: Predict (+ byte boundary), then `decide` tells the bit (coder / prompt / sampler), then Learn when
-// the byte is one of the learned ones. Returns false when the stream has failed.
-// runner_utils::Compress (runner-utils.cpp:43-67) incl. the 5-byte header of RunCompression (:109).
+// Bit role: runner_utils::Compress (runner-utils.cpp:43-67); the 5-byte header of RunCompression (:109) is written by
+// the kernel entry.
 template <int NB, bool PROF>
 GMX_DEV void BitRoleCompress(StreamSmem& s, const Arena& A, const StreamParams& P, const StreamJob& J, uint32_t sid, ProfSmem* prof, int btid) {
   Lap<PROF> lap;
   lap.start(prof, btid == 0);
   const bool tracing = sid == 0 && (P.bit_trace || P.pred_trace);
 #pragma unroll 1
-  for (uint32_t pos = 0; pos < J.n_bound; ++pos) {
+  for (uint32_t pos = 0; pos < J.n_bytes; ++pos) {
     const uint32_t c = J.in[pos];
 #pragma unroll 1
     for (int j = 7; j >= 0; --j) {
@@ -1750,9 +1777,11 @@ GMX_DEV void BitRoleCompress(StreamSmem& s, const Arena& A, const StreamParams& 
       GroupSync<NB>(BAR_BIT);
       lap.mark(0);
       if (s.bb) {
+        BitBoundaryA<NB>(s, A, btid);
+        lap.mark(2);
         WaitAtLeast(s, &s.n_pkt, pos + 1, 100);
         lap.mark(1);
-        BitBoundary<NB>(s, A, pos, btid);
+        BitBoundaryB<NB>(s, A, pos, btid);
         lap.mark(2);
       }
       PredictBit<NB, PROF>(s, A, P, pos, 7 - j, btid, lap);
@@ -1768,23 +1797,47 @@ GMX_DEV void BitRoleCompress(StreamSmem& s, const Arena& A, const StreamParams& 
   }
 }
 
+// ==== LOCKSTEP (decompress, generation, the Predictor facade): a byte is only known when its last bit is decided, so
+// nothing can run ahead; the whole CTA (NT threads) walks the phases one after the other, every phase with all the
+// threads it can use, through the same step functions as the roles above. ===================================
+
+// Predictor::Predict of one bit.
+template <int NT, bool PROF>
+GMX_DEV void SerialPredict(StreamSmem& s, const Arena& A, const StreamParams& P, int tid, Lap<PROF>& lap) {
+  if (tid == 0) Bookkeeping(s);
+  __syncthreads();
+  lap.mark(0);
+  if (s.bb) {
+    const uint32_t last = s.ctx[C_LAST_BYTE];
+    // PPMd on the last warp while the other warps do the byte contexts (with b = 0 no wait inside can block)
+    if (tid >= NT - 32) PpmdStep<PROF>(s, A, 0, last, -1, false, tid - (NT - 32), lap);
+    else BitBoundaryA<NT - 32>(s, A, tid);
+    __syncthreads();
+    lap.mark(2);
+    LstmForward<NT, PROF>(s, A, P, 0, last, -1, tid, lap);
+    BitBoundaryB<NT>(s, A, 0, tid);
+  }
+  PredictBit<NT, PROF>(s, A, P, 0, -1, tid, lap);
+}
+// Predictor::Learn of one bit (s.new_bit).
+template <int NT, bool PROF>
+GMX_DEV void SerialLearn(StreamSmem& s, const Arena& A, const StreamParams& P, int tid, Lap<PROF>& lap) {
+  const int cur = s.recent_bits * 2 + s.new_bit;
+  LearnBit<NT, PROF>(s, A, P, tid, lap);
+  if (cur >= 256) LstmPerceive<NT, PROF>(s, A, P, (uint32_t)(cur - 256), tid, lap);   // LstmModel::Learn lstm-model.cpp:50-59
+}
+
 // runner_utils::Decompress (runner-utils.cpp:69-86); Decoder::Decode decoder.cpp:19-39. Analysis is never on.
-template <int NB, bool PROF>
-GMX_DEV void BitRoleDecompress(StreamSmem& s, const Arena& A, const StreamParams& P, const StreamJob& J, ProfSmem* prof, int btid) {
+template <int NT, bool PROF>
+GMX_DEV void SerialDecompress(StreamSmem& s, const Arena& A, const StreamParams& P, const StreamJob& J, ProfSmem* prof, int tid) {
   Lap<PROF> lap;
-  lap.start(prof, btid == 0);
+  lap.start(prof, tid == 0);
 #pragma unroll 1
-  for (uint32_t pos = 0; pos < J.n_bound; ++pos) {
+  for (uint32_t pos = 0; pos < J.n_bytes; ++pos) {
 #pragma unroll 1
     for (int j = 7; j >= 0; --j) {
-      if (btid == 0) Bookkeeping(s);
-      GroupSync<NB>(BAR_BIT);
-      if (s.bb) {
-        WaitAtLeast(s, &s.n_pkt, pos + 1, 100);
-        BitBoundary<NB>(s, A, pos, btid);
-      }
-      PredictBit<NB, PROF>(s, A, P, pos, -1, btid, lap);
-      if (btid == 0) {
+      SerialPredict<NT, PROF>(s, A, P, tid, lap);
+      if (tid == 0) {
         const uint32_t p16 = Discretize(s.prob);
         const uint32_t r = s.x2 - s.x1;
         const uint32_t xmid = s.x1 + (r >> 16) * p16 + (((r & 0xffff) * p16) >> 16);
@@ -1792,64 +1845,49 @@ GMX_DEV void BitRoleDecompress(StreamSmem& s, const Arena& A, const StreamParams
         if (s.x <= xmid) { bit = 1; s.x2 = xmid; } else s.x1 = xmid + 1;
         s.new_bit = bit;
         while (((s.x1 ^ s.x2) & 0xff000000u) == 0) { s.x1 <<= 8; s.x2 = (s.x2 << 8) + 255; s.x = (s.x << 8) + GetByte(s, J.in); }
-        if (j == 0) {   // the byte is decided: hand it to the byte-model roles before learning its last bit
-          const uint32_t byte = (uint32_t)(s.recent_bits * 2 + bit) & 0xffu;
-          J.out[pos] = (uint8_t)byte;
-          s.kbyte[pos & 3] = (uint8_t)byte;
-          Publish(&s.n_known, pos + 1);
-        }
+        if (j == 0) J.out[pos] = (uint8_t)((s.recent_bits * 2 + bit) & 0xff);
       }
-      GroupSync<NB>(BAR_BIT);
-      LearnBit<NB, PROF>(s, A, P, btid, lap);
+      __syncthreads();
+      SerialLearn<NT, PROF>(s, A, P, tid, lap);
       if (s.bit_stop) return;
     }
   }
 }
 
 // runner_utils::RunGeneration (runner-utils.cpp:158-221): the prompt (all but its last byte) is consumed WITH
-// learning, then gen_bytes bytes are sampled bit by bit without Learn: prob = Logistic(Logit(prob) / temperature),
-// bit = r < prob with r the next rand()/RAND_MAX draw, Perceive(bit), Predict(). The last Predict (after the last
-// sampled bit) still crosses a byte boundary: n_bound = n_preset + gen_bytes + 1.
-template <int NB, bool PROF>
-GMX_DEV void BitRoleGenerate(StreamSmem& s, const Arena& A, const StreamParams& P, const StreamJob& J, const float* ru, ProfSmem* prof, int btid) {
+// learning, then n_bytes bytes are sampled bit by bit without Learn: prob = Logistic(Logit(prob) / temperature),
+// bit = r < prob with r the next rand()/RAND_MAX draw, Perceive(bit), Predict().
+template <int NT, bool PROF>
+GMX_DEV void SerialGenerate(StreamSmem& s, const Arena& A, const StreamParams& P, const StreamJob& J, const float* ru, ProfSmem* prof, int tid) {
   Lap<PROF> lap;
-  lap.start(prof, btid == 0);
-  uint32_t draws = 0;
+  lap.start(prof, tid == 0);
 #pragma unroll 1
-  for (uint32_t pos = 0; pos < J.n_bound; ++pos) {
-    const bool preset = pos < J.n_preset;
-    const uint32_t c = preset ? J.in[pos] : 0u;
-    const int nbits = pos + 1 == J.n_bound ? 1 : 8;   // the final Predict only
+  for (uint32_t pos = 0; pos < J.n_preset; ++pos) {   // :187-194
+    const uint32_t c = J.in[pos];
 #pragma unroll 1
-    for (int j = 0; j < nbits; ++j) {
-      if (btid == 0) Bookkeeping(s);
-      GroupSync<NB>(BAR_BIT);
-      if (s.bb) {
-        WaitAtLeast(s, &s.n_pkt, pos + 1, 100);
-        BitBoundary<NB>(s, A, pos, btid);
+    for (int j = 7; j >= 0; --j) {
+      SerialPredict<NT, PROF>(s, A, P, tid, lap);
+      if (tid == 0) s.new_bit = (c >> j) & 1;
+      __syncthreads();
+      SerialLearn<NT, PROF>(s, A, P, tid, lap);
+      if (s.bit_stop) return;
+    }
+  }
+  SerialPredict<NT, PROF>(s, A, P, tid, lap);   // :198
+#pragma unroll 1
+  for (uint32_t i = 0; i < J.n_bytes; ++i) {
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+      if (tid == 0) {
+        const float r = ru[(size_t)i * 8 + j];
+        const float prob = Logistic(f_div(Logit(s.prob), P.temperature));
+        s.new_bit = r < prob ? 1 : 0;
+        if (j == 7) J.out[i] = (uint8_t)((s.recent_bits * 2 + s.new_bit) & 0xff);
+        s.bit_stop = VolatileLoad(&s.error) != 0;
       }
-      PredictBit<NB, PROF>(s, A, P, pos, -1, btid, lap);
-      if (pos + 1 == J.n_bound) break;
-      if (btid == 0) {
-        int bit;
-        if (preset) bit = (c >> (7 - j)) & 1;                                                     // :187-194
-        else { const float r = ru[draws]; bit = r < Logistic(f_div(Logit(s.prob), P.temperature)) ? 1 : 0; }   // :199-206
-        s.new_bit = bit;
-        if (j == 7) {
-          const uint32_t byte = (uint32_t)(s.recent_bits * 2 + bit) & 0xffu;
-          if (!preset) J.out[pos - J.n_preset] = (uint8_t)byte;
-          s.kbyte[pos & 3] = (uint8_t)byte;
-          Publish(&s.n_known, pos + 1);
-        }
-      }
-      if (!preset) ++draws;
-      GroupSync<NB>(BAR_BIT);
-      if (preset) { LearnBit<NB, PROF>(s, A, P, btid, lap); if (s.bit_stop) return; }
-      else {
-        if (btid == 0) s.bit_stop = VolatileLoad(&s.error) != 0;
-        GroupSync<NB>(BAR_BIT);
-        if (s.bit_stop) return;
-      }
+      __syncthreads();
+      if (s.bit_stop) return;
+      SerialPredict<NT, PROF>(s, A, P, tid, lap);
     }
   }
 }
@@ -1899,11 +1937,10 @@ __global__ void __launch_bounds__(32 * (WB + WL + 1), MINB) StreamKernel(StreamP
       job.in = in; job.n_in = n; job.n_preset = 0;
       if (MODE == MODE_COMPRESS) {
         uint8_t* out = P.out + P.out_off[sid];
-        job.out = out; job.n_bound = (uint32_t)n; job.n_learn = (uint32_t)n;
+        job.out = out; job.n_bytes = (uint32_t)n;
         s.out_pos = 0; s.out_cap = P.out_off[sid + 1] - P.out_off[sid];
         s.analysis = P.analysis >= 0 ? P.analysis : (8 * n / 1000) > 0;  // EnableAnalysis(8*n/1000) -> predictions zeroed every bit
         for (int i = 4; i >= 0; --i) PutByte(s, out, (uint32_t)(n >> (8 * i)) & 0xff);
-        s.n_known = (uint32_t)n;
       } else if (MODE == MODE_DECOMPRESS) {   // ReadHeader runner-utils.cpp:29-36, Decoder::Decoder decoder.cpp:3-9
         job.out = P.out + P.out_off[sid];
         s.in_pos = 0; s.in_len = n;
@@ -1914,10 +1951,10 @@ __global__ void __launch_bounds__(32 * (WB + WL + 1), MINB) StreamKernel(StreamP
         if (s.in_len < 5 || len > s.out_cap) { SetError(s, s.in_len < 5 ? GMX_ERR_BAD_HEADER : GMX_ERR_OUTPUT_CAP); len = 0; }
         s.out_cap = len;  // number of bytes to produce
         for (int i = 0; i < 4; ++i) s.x = (s.x << 8) + (GetByte(s, in) & 0xff);
-        job.n_bound = (uint32_t)len; job.n_learn = (uint32_t)len;
+        job.n_bytes = (uint32_t)len;
       } else {
         job.out = P.out + (size_t)sid * P.gen_bytes;
-        job.n_preset = n ? (uint32_t)n - 1 : 0; job.n_learn = job.n_preset; job.n_bound = job.n_preset + P.gen_bytes + 1;
+        job.n_preset = n ? (uint32_t)n - 1 : 0; job.n_bytes = P.gen_bytes;
         s.analysis = P.analysis >= 0 ? P.analysis : (8 * (uint64_t)P.gen_bytes / 1000) > 0;   // :177
       }
       if (PROF) prof->acc[14] += (unsigned long long)(GMX_CLOCK() - t_init);
@@ -1925,14 +1962,14 @@ __global__ void __launch_bounds__(32 * (WB + WL + 1), MINB) StreamKernel(StreamP
     __syncthreads();
     const bool failed_early = s.error != 0;
     if (!failed_early) {
-      if (tid < NB) {
-        if (MODE == MODE_COMPRESS) BitRoleCompress<NB, PROF>(s, A, P, job, sid, prof, tid);
-        else if (MODE == MODE_DECOMPRESS) BitRoleDecompress<NB, PROF>(s, A, P, job, prof, tid);
-        else BitRoleGenerate<NB, PROF>(s, A, P, job, P.rand_u + (size_t)sid * P.rand_stride, prof, tid);
-      } else if (tid < NB + NL) {
-        LstmRole<NL, MODE, PROF>(s, A, P, job, prof, tid - NB);
+      if (MODE == MODE_COMPRESS) {
+        if (tid < NB) BitRoleCompress<NB, PROF>(s, A, P, job, sid, prof, tid);
+        else if (tid < NB + NL) LstmRole<NL, PROF>(s, A, P, job, prof, tid - NB);
+        else PpmdRole<PROF>(s, A, job, prof, tid - NB - NL);
+      } else if (MODE == MODE_DECOMPRESS) {
+        SerialDecompress<NT, PROF>(s, A, P, job, prof, tid);
       } else {
-        PpmdRole<MODE, PROF>(s, A, job, prof, tid - NB - NL);
+        SerialGenerate<NT, PROF>(s, A, P, job, P.rand_u + (size_t)sid * P.rand_stride, prof, tid);
       }
     }
     __syncthreads();
@@ -1943,7 +1980,7 @@ __global__ void __launch_bounds__(32 * (WB + WL + 1), MINB) StreamKernel(StreamP
         PutByte(s, out, s.x2 >> 24);
         P.out_len[sid] = s.out_pos;
       } else if (MODE == MODE_DECOMPRESS) {
-        P.out_len[sid] = s.error ? 0 : job.n_bound;
+        P.out_len[sid] = s.error ? 0 : job.n_bytes;
       } else {
         P.out_len[sid] = s.error ? 0 : P.gen_bytes;
       }
@@ -1992,28 +2029,11 @@ __global__ void __launch_bounds__(32 * (WB + WL + 1)) StepKernel(StepParams Q) {
     if (tid == 0 && Q.analysis >= 0) s.analysis = Q.analysis;
     __syncthreads();
     if (Q.op == STEP_PREDICT) {
-      // the byte models' view of the byte in front of this boundary, before the bookkeeping consumes new_bit
-      const uint32_t last = s.first_prediction ? 0u : (uint32_t)(s.recent_bits * 2 + s.new_bit) & 0xffu;
-      __syncthreads();
-      if (tid == 0) Bookkeeping(s);
-      __syncthreads();
-      if (s.bb) {   // the counters make every wait inside the step functions fall through
-        if (tid == 0) { s.n_ppm_used = 0; s.n_ppm = 0; s.n_pkt = 0; }
-        __syncthreads();
-        if (tid >= NB + NL) PpmdStep<false>(s, A, 0, last, -1, false, tid - NB - NL, lap);
-        __syncthreads();
-        if (tid >= NB && tid < NB + NL) LstmForward<NL, false>(s, A, Q.P, 0, last, -1, tid - NB, lap);
-        __syncthreads();
-        if (tid < NB) BitBoundary<NB>(s, A, 0, tid);
-      }
-      if (tid < NB) PredictBit<NB, false>(s, A, Q.P, 0, -1, tid, lap);
+      SerialPredict<NT, false>(s, A, Q.P, tid, lap);
       __syncthreads();
       if (tid == 0) *Q.prob_out = s.prob;
     } else {
-      const int cur = s.recent_bits * 2 + s.new_bit;
-      if (tid < NB) LearnBit<NB, false>(s, A, Q.P, tid, lap);
-      __syncthreads();
-      if (cur >= 256 && tid >= NB && tid < NB + NL) LstmPerceive<NL, false>(s, A, Q.P, (uint32_t)(cur - 256), tid - NB, lap);   // LstmModel::Learn lstm-model.cpp:50-59
+      SerialLearn<NT, false>(s, A, Q.P, tid, lap);
     }
   }
   __syncthreads();

@@ -62,6 +62,7 @@ const char* gmx_last_error(const gmx_ctx* ctx);
  * per SM). Every configuration produces the same bytes; they differ in throughput per workload shape. Default 0 (or the
  * environment variable GMIX_B200_KERNEL_CONFIG). Changing it frees the arenas (the next call re-sizes them). */
 int gmx_set_kernel_config(gmx_ctx* ctx, int cfg);
+int gmx_get_kernel_config(const gmx_ctx* ctx);
 int gmx_kernel_config_count(void);
 int gmx_kernel_config_info(int cfg, int* bit_warps, int* lstm_warps, int* ctas_per_sm);
 
