@@ -213,6 +213,7 @@ int ConfigureForModel(gmx_ctx* c, const gmx_model* m) {
   if (rc) return rc;
   int per_sm = 0;
   GMX_CUDA(c, gmx::OccupancyCompress(c->kcfg, &per_sm));
+  if (per_sm > gmx::KernelConfig(c->kcfg).minb) per_sm = gmx::KernelConfig(c->kcfg).minb;   // a configuration is tuned for exactly this residency
   if (per_sm < 1) per_sm = 1;
   uint64_t want = (uint64_t)per_sm * c->sm_count;
   if (max_resident && max_resident < want) want = max_resident;
@@ -443,12 +444,13 @@ int gmx_set_kernel_config(gmx_ctx* c, int cfg) {
 }
 int gmx_get_kernel_config(const gmx_ctx* c) { return c ? c->kcfg : -1; }
 int gmx_kernel_config_count(void) { return gmx::kNumKernelConfigs; }
-int gmx_kernel_config_info(int cfg, int* bit_warps, int* lstm_warps, int* ctas_per_sm) {
+int gmx_kernel_config_info(int cfg, int* bit_warps, int* lstm_warps, int* ctas_per_sm, int* serial) {
   if (cfg < 0 || cfg >= gmx::kNumKernelConfigs) return GMX_E_ARG;
   const gmx::KernelConfigInfo k = gmx::KernelConfig(cfg);
   if (bit_warps) *bit_warps = k.wb;
   if (lstm_warps) *lstm_warps = k.wl;
   if (ctas_per_sm) *ctas_per_sm = k.minb;
+  if (serial) *serial = k.serial;
   return 0;
 }
 
@@ -470,6 +472,7 @@ int gmx_configure(gmx_ctx* c, uint64_t max_stream_len, uint32_t max_resident) {
   }
   int per_sm = 0;
   GMX_CUDA(c, gmx::OccupancyCompress(c->kcfg, &per_sm));
+  if (per_sm > gmx::KernelConfig(c->kcfg).minb) per_sm = gmx::KernelConfig(c->kcfg).minb;   // a configuration is tuned for exactly this residency
   if (per_sm < 1) per_sm = 1;
   uint64_t want = (uint64_t)per_sm * c->sm_count;
   if (max_resident && max_resident < want) want = max_resident;

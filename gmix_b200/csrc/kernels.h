@@ -10,16 +10,18 @@
 #include "stream_kernel.cuh"
 
 namespace gmx {
-//            id  WB WL MINB
+// SERIAL = 1: compress walks the phases with all threads (no role pipeline); decompress and generation always do.
+//            id  WB WL MINB SERIAL
 #define GMX_KERNEL_CONFIGS(X) \
-  X(0, 2, 1, 8)               \
-  X(1, 1, 2, 8)               \
-  X(2, 1, 1, 8)               \
-  X(3, 2, 2, 6)               \
-  X(4, 4, 2, 4)
-constexpr int kNumKernelConfigs = 5;
+  X(0, 2, 1, 8, 1)            \
+  X(1, 2, 1, 8, 0)            \
+  X(2, 1, 2, 8, 0)            \
+  X(3, 2, 2, 6, 0)            \
+  X(4, 4, 2, 4, 0)            \
+  X(5, 4, 2, 1, 0)
+constexpr int kNumKernelConfigs = 6;
 constexpr int kStepWB = 2, kStepWL = 1;   // role split of the single-stream stepping kernel
-struct KernelConfigInfo { int wb, wl, minb, threads; };
+struct KernelConfigInfo { int wb, wl, minb, threads, serial; };
 KernelConfigInfo KernelConfig(int cfg);
 cudaError_t LaunchCompress(int cfg, const StreamParams& P, unsigned grid, cudaStream_t st);
 cudaError_t LaunchCompressProf(int cfg, const StreamParams& P, unsigned grid, cudaStream_t st);
@@ -31,20 +33,20 @@ cudaError_t OccupancyCompress(int cfg, int* blocks_per_sm);
 cudaError_t OccupancyDecompress(int cfg, int* blocks_per_sm);
 
 // Shared body of the per-mode launchers.
-template <int WB, int WL, int MODE, int MINB, bool PROF>
+template <int WB, int WL, int MODE, int MINB, bool PROF, bool SERIAL>
 inline cudaError_t LaunchStreamKernel(const StreamParams& P, unsigned grid, cudaStream_t st) {
   // all of the SM's unified L1/shared memory as shared memory, so that MINB CTAs are co-resident
-  static const cudaError_t carve = cudaFuncSetAttribute(StreamKernel<WB, WL, MODE, MINB, PROF>, cudaFuncAttributePreferredSharedMemoryCarveout,
+  static const cudaError_t carve = cudaFuncSetAttribute(StreamKernel<WB, WL, MODE, MINB, PROF, SERIAL>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                                         cudaSharedmemCarveoutMaxShared);
   if (carve != cudaSuccess) return carve;
-  StreamKernel<WB, WL, MODE, MINB, PROF><<<grid, 32 * (WB + WL + 1), 0, st>>>(P);
+  StreamKernel<WB, WL, MODE, MINB, PROF, SERIAL><<<grid, 32 * (WB + WL + 1), 0, st>>>(P);
   return cudaGetLastError();
 }
-template <int WB, int WL, int MODE, int MINB, bool PROF>
+template <int WB, int WL, int MODE, int MINB, bool PROF, bool SERIAL>
 inline cudaError_t OccupancyStreamKernel(int* n) {
-  cudaError_t e = cudaFuncSetAttribute(StreamKernel<WB, WL, MODE, MINB, PROF>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaError_t e = cudaFuncSetAttribute(StreamKernel<WB, WL, MODE, MINB, PROF, SERIAL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, StreamKernel<WB, WL, MODE, MINB, PROF>, 32 * (WB + WL + 1), 0);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, StreamKernel<WB, WL, MODE, MINB, PROF, SERIAL>, 32 * (WB + WL + 1), 0);
 }
 }  // namespace gmx
 #endif

@@ -1801,30 +1801,55 @@ GMX_DEV void BitRoleCompress(StreamSmem& s, const Arena& A, const StreamParams& 
 // nothing can run ahead; the whole CTA (NT threads) walks the phases one after the other, every phase with all the
 // threads it can use, through the same step functions as the roles above. ===================================
 
-// Predictor::Predict of one bit.
+// Predictor::Predict of one bit. known_byte >= 0 (serial compress): the byte being coded; path_bit = index of this bit in
+// it. The byte models then leave their eight path nodes in packet 0 at the byte boundary.
 template <int NT, bool PROF>
-GMX_DEV void SerialPredict(StreamSmem& s, const Arena& A, const StreamParams& P, int tid, Lap<PROF>& lap) {
+GMX_DEV void SerialPredict(StreamSmem& s, const Arena& A, const StreamParams& P, int tid, Lap<PROF>& lap, int known_byte = -1, int path_bit = -1) {
   if (tid == 0) Bookkeeping(s);
   __syncthreads();
   lap.mark(0);
   if (s.bb) {
     const uint32_t last = s.ctx[C_LAST_BYTE];
     // PPMd on the last warp while the other warps do the byte contexts (with b = 0 no wait inside can block)
-    if (tid >= NT - 32) PpmdStep<PROF>(s, A, 0, last, -1, false, tid - (NT - 32), lap);
+    if (tid >= NT - 32) PpmdStep<PROF>(s, A, 0, last, known_byte, known_byte >= 0, tid - (NT - 32), lap);
     else BitBoundaryA<NT - 32>(s, A, tid);
     __syncthreads();
     lap.mark(2);
-    LstmForward<NT, PROF>(s, A, P, 0, last, -1, tid, lap);
+    LstmForward<NT, PROF>(s, A, P, 0, last, known_byte, tid, lap);
     BitBoundaryB<NT>(s, A, 0, tid);
   }
-  PredictBit<NT, PROF>(s, A, P, 0, -1, tid, lap);
+  PredictBit<NT, PROF>(s, A, P, 0, path_bit, tid, lap);
 }
-// Predictor::Learn of one bit (s.new_bit).
+// Predictor::Learn of one bit (s.new_bit, or known_bit which is then also coded into code_out first).
 template <int NT, bool PROF>
-GMX_DEV void SerialLearn(StreamSmem& s, const Arena& A, const StreamParams& P, int tid, Lap<PROF>& lap) {
-  const int cur = s.recent_bits * 2 + s.new_bit;
-  LearnBit<NT, PROF>(s, A, P, tid, lap);
+GMX_DEV void SerialLearn(StreamSmem& s, const Arena& A, const StreamParams& P, int tid, Lap<PROF>& lap, int known_bit = -1, uint8_t* code_out = nullptr) {
+  const int cur = s.recent_bits * 2 + (known_bit >= 0 ? known_bit : s.new_bit);
+  LearnBit<NT, PROF>(s, A, P, tid, lap, known_bit, code_out);
   if (cur >= 256) LstmPerceive<NT, PROF>(s, A, P, (uint32_t)(cur - 256), tid, lap);   // LstmModel::Learn lstm-model.cpp:50-59
+}
+
+// runner_utils::Compress (runner-utils.cpp:43-67) without the role pipeline: all phases with all threads. With a full
+// wave of resident streams per SM the other streams already hide this stream's latencies, and every phase having all
+// threads beats the pipeline's fixed split of them (kernels.h: configurations).
+template <int NT, bool PROF>
+GMX_DEV void SerialCompress(StreamSmem& s, const Arena& A, const StreamParams& P, const StreamJob& J, uint32_t sid, ProfSmem* prof, int tid) {
+  Lap<PROF> lap;
+  lap.start(prof, tid == 0);
+  const bool tracing = sid == 0 && (P.bit_trace || P.pred_trace);
+#pragma unroll 1
+  for (uint32_t pos = 0; pos < J.n_bytes; ++pos) {
+    const uint32_t c = J.in[pos];
+#pragma unroll 1
+    for (int j = 7; j >= 0; --j) {
+      SerialPredict<NT, PROF>(s, A, P, tid, lap, (int)c, 7 - j);
+      if (tracing) {
+        if (tid == 0) Trace(s, P, (uint64_t)pos * 8 + (7 - j));
+        __syncthreads();
+      }
+      SerialLearn<NT, PROF>(s, A, P, tid, lap, (c >> j) & 1, J.out);
+      if (s.bit_stop) return;
+    }
+  }
 }
 
 // runner_utils::Decompress (runner-utils.cpp:69-86); Decoder::Decode decoder.cpp:19-39. Analysis is never on.
@@ -1910,7 +1935,8 @@ GMX_DEV void StageTables(StreamSmem& s, const StreamParams& P, int tid) {
 
 // ---- kernel entry: persistent CTAs, one stream at a time, ids from an atomic queue ---------------
 // WB warps of bit role (threads 0 .. 32 WB - 1), WL warps of LSTM role, one PPMd warp.
-template <int WB, int WL, int MODE, int MINB, bool PROF>
+// SERIAL: compress without the role pipeline (the same NT threads walk the phases together, as the lockstep modes do).
+template <int WB, int WL, int MODE, int MINB, bool PROF, bool SERIAL = false>
 __global__ void __launch_bounds__(32 * (WB + WL + 1), MINB) StreamKernel(StreamParams P) {
   constexpr int NB = 32 * WB, NL = 32 * WL, NT = NB + NL + 32;
   __shared__ StreamSmem s;
@@ -1962,7 +1988,9 @@ __global__ void __launch_bounds__(32 * (WB + WL + 1), MINB) StreamKernel(StreamP
     __syncthreads();
     const bool failed_early = s.error != 0;
     if (!failed_early) {
-      if (MODE == MODE_COMPRESS) {
+      if (MODE == MODE_COMPRESS && SERIAL) {
+        SerialCompress<NT, PROF>(s, A, P, job, sid, prof, tid);
+      } else if (MODE == MODE_COMPRESS) {
         if (tid < NB) BitRoleCompress<NB, PROF>(s, A, P, job, sid, prof, tid);
         else if (tid < NB + NL) LstmRole<NL, PROF>(s, A, P, job, prof, tid - NB);
         else PpmdRole<PROF>(s, A, job, prof, tid - NB - NL);

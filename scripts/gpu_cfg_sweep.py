@@ -13,7 +13,7 @@ ins = [open(f"tests/golden/{n}.in", "rb").read() for n in names]
 want = [open(f"tests/golden/{n}.gmix", "rb").read() for n in names]
 chunks = {}
 for k in cfgs:
-    wb, wl, minb = c.kernel_configs()[k]
+    wb, wl, minb, serial = c.kernel_configs()[k]
     c.set_kernel_config(k)
     got = c.compress_batch(ins)
     ok = got == want and c.decompress_batch(got) == ins
@@ -27,5 +27,5 @@ for k in cfgs:
     ms = c.last_kernel_ms
     back = c.decompress_batch(comp)
     dms = c.last_kernel_ms
-    print(f"cfg {k} (bit {wb}w, lstm {wl}w, {minb}/SM) parity {'OK' if ok else 'FAILED'} roundtrip {'OK' if back == batch else 'FAILED'}: "
+    print(f"cfg {k} ({'serial' if serial else 'roles'} bit {wb}w, lstm {wl}w, {minb}/SM) parity {'OK' if ok else 'FAILED'} roundtrip {'OK' if back == batch else 'FAILED'}: "
           f"{n} x {size}: compress {ms:.0f} ms -> {n*size/ms/1e3:.3f} MB/s, decompress {dms:.0f} ms -> {n*size/dms/1e3:.3f} MB/s", flush=True)

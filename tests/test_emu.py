@@ -88,6 +88,17 @@ def test_stepping_kernel_behind_the_predictor_facade(emu, tmp_path, name):
     assert open(out, "rb").read() == open(os.path.join(GOLD, name + ".gmix"), "rb").read()
 
 
+def test_serial_compress_configuration(tmp_path):
+    """Configuration 0 of the library: compress without the role pipeline (all threads walk the phases together, the byte
+    models still hand their path nodes over through packet 0)."""
+    exe = str(tmp_path / "emu_main")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-w", "-DEMU_SERIAL=1", "-o", exe, os.path.join(HERE, "emu", "emu_main.cpp")], check=True)
+    for name in ("text1k", "random1200", "short124", "one_byte", "empty"):
+        out = str(tmp_path / (name + ".out"))
+        subprocess.run([exe, "compress", os.path.join(GOLD, name + ".in"), out], check=True, stderr=subprocess.DEVNULL)
+        assert open(out, "rb").read() == open(os.path.join(GOLD, name + ".gmix"), "rb").read(), name
+
+
 @pytest.mark.parametrize("roles", [(1, 2), (1, 1), (2, 2)])
 def test_other_role_splits_compute_the_same_bytes(tmp_path, roles):
     """The kernel configurations of the library (kernels.h) differ only in how many warps the bit role and the LSTM role
