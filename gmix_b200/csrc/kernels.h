@@ -18,8 +18,10 @@ namespace gmx {
   X(2, 1, 2, 8, 0)            \
   X(3, 2, 2, 6, 0)            \
   X(4, 4, 2, 4, 0)            \
-  X(5, 4, 2, 1, 0)
-constexpr int kNumKernelConfigs = 6;
+  X(5, 4, 2, 1, 0)            \
+  X(6, 3, 0, 8, 0)            \
+  X(7, 7, 0, 4, 0)
+constexpr int kNumKernelConfigs = 8;
 constexpr int kStepWB = 2, kStepWL = 1;   // role split of the single-stream stepping kernel
 struct KernelConfigInfo { int wb, wl, minb, threads, serial; };
 KernelConfigInfo KernelConfig(int cfg);

@@ -364,6 +364,7 @@ GMX_DEV inline void WaitAtLeast(const StreamSmem& s, const uint32_t* cnt, uint32
   while (VolatileLoad(cnt) < need) {
     if (VolatileLoad(&s.error)) break;
     Backoff(ns);
+    if (ns < 4000u) ns += ns;   // a role that is far ahead sleeps longer and longer: polling must not eat issue slots
   }
   FenceBlock();
 }
@@ -1797,6 +1798,47 @@ GMX_DEV void BitRoleCompress(StreamSmem& s, const Arena& A, const StreamParams& 
   }
 }
 
+// Two-role variant (WL = 0): the PPMd warp runs ahead, the other NB threads do the LSTM and the bit path one after the
+// other with all of them (forward(b), the 8 bits of byte b, Perceive(b)). PPMd is the one phase a single warp has to
+// itself in the serial order (its neighbours would idle at a barrier for ~16 % of the byte); everything else keeps the
+// full width.
+template <int NB, bool PROF>
+GMX_DEV void BitLstmRoleCompress(StreamSmem& s, const Arena& A, const StreamParams& P, const StreamJob& J, uint32_t sid, ProfSmem* prof, int btid) {
+  Lap<PROF> lap;
+  lap.start(prof, btid == 0);
+  const bool tracing = sid == 0 && (P.bit_trace || P.pred_trace);
+#pragma unroll 1
+  for (uint32_t pos = 0; pos < J.n_bytes; ++pos) {
+    const uint32_t c = J.in[pos];
+#pragma unroll 1
+    for (int j = 7; j >= 0; --j) {
+      const int bit = (c >> j) & 1;
+      if (btid == 0) Bookkeeping(s);
+      GroupSync<NB>(BAR_BIT);
+      lap.mark(0);
+      if (s.bb) {
+        BitBoundaryA<NB>(s, A, btid);
+        lap.mark(2);
+        WaitAtLeast(s, &s.n_ppm, pos + 1, 100);
+        lap.mark(1);
+        LstmForward<NB, PROF>(s, A, P, pos, pos ? J.in[pos - 1] : s.byte0, (int)c, btid, lap);
+        BitBoundaryB<NB>(s, A, pos, btid);
+        lap.mark(2);
+      }
+      PredictBit<NB, PROF>(s, A, P, pos, 7 - j, btid, lap);
+      if (tracing) {
+        if (btid == 0) Trace(s, P, (uint64_t)pos * 8 + (7 - j));
+        GroupSync<NB>(BAR_BIT);
+        lap.mark(13);
+      }
+      LearnBit<NB, PROF>(s, A, P, btid, lap, bit, J.out);
+      if (s.bit_stop) return;
+    }
+    LstmPerceive<NB, PROF>(s, A, P, c, btid, lap);
+    if (btid == 0) Publish(&s.n_done, pos + 1);
+  }
+}
+
 // ==== LOCKSTEP (decompress, generation, the Predictor facade): a byte is only known when its last bit is decided, so
 // nothing can run ahead; the whole CTA (NT threads) walks the phases one after the other, every phase with all the
 // threads it can use, through the same step functions as the roles above. ===================================
@@ -1990,9 +2032,12 @@ __global__ void __launch_bounds__(32 * (WB + WL + 1), MINB) StreamKernel(StreamP
     if (!failed_early) {
       if (MODE == MODE_COMPRESS && SERIAL) {
         SerialCompress<NT, PROF>(s, A, P, job, sid, prof, tid);
+      } else if (MODE == MODE_COMPRESS && WL == 0) {
+        if (tid < NB) BitLstmRoleCompress<NB, PROF>(s, A, P, job, sid, prof, tid);
+        else PpmdRole<PROF>(s, A, job, prof, tid - NB);
       } else if (MODE == MODE_COMPRESS) {
         if (tid < NB) BitRoleCompress<NB, PROF>(s, A, P, job, sid, prof, tid);
-        else if (tid < NB + NL) LstmRole<NL, PROF>(s, A, P, job, prof, tid - NB);
+        else if (tid < NB + NL) LstmRole<(NL > 0 ? NL : 32), PROF>(s, A, P, job, prof, tid - NB);
         else PpmdRole<PROF>(s, A, job, prof, tid - NB - NL);
       } else if (MODE == MODE_DECOMPRESS) {
         SerialDecompress<NT, PROF>(s, A, P, job, prof, tid);

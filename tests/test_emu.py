@@ -99,7 +99,7 @@ def test_serial_compress_configuration(tmp_path):
         assert open(out, "rb").read() == open(os.path.join(GOLD, name + ".gmix"), "rb").read(), name
 
 
-@pytest.mark.parametrize("roles", [(1, 2), (1, 1), (2, 2)])
+@pytest.mark.parametrize("roles", [(1, 2), (1, 1), (2, 2), (3, 0)])   # (3, 0): the two-role variant, PPMd ahead of everything else
 def test_other_role_splits_compute_the_same_bytes(tmp_path, roles):
     """The kernel configurations of the library (kernels.h) differ only in how many warps the bit role and the LSTM role
     get: every split must compute the reference's bytes, in both pipeline protocols (ahead: compress, lockstep: decompress)."""
