@@ -591,44 +591,45 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
 
 // Output layer of the next epoch slot: copy of the slot just used plus one SGD step (Lstm::Perceive
 // lstm.cpp:81-88). `byte` is the symbol that followed the forward pass of slot `last`.
+// One quad of adjacent outputs (4q .. 4q+3), rows j0 .. j1-1 of the output-layer step.
+template <int UNROLL>
+GMX_DEV inline void OutputStepRows(const StreamSmem& s, const float* wl, float* wc, int q, int j0, int j1, uint32_t byte) {
+  constexpr int NQ = L_NOUT / 4;
+  const float lr = (float)0.03;
+  float le[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t i = 4 * q + c;
+    const float err = i == byte ? f_sub(s.lprob[i], 1.0f) : s.lprob[i];
+    le[c] = f_mul(lr, err);
+  }
+  const float4* wl4 = (const float4*)wl + q;
+  float4* wc4 = (float4*)wc + q;
+GMX_UNROLL(UNROLL)
+  for (int j = j0; j < j1; ++j) {
+    const float h = s.l_hidden[j];
+    float4 w = LoadStream4(wl4 + j * NQ);
+    w.x = f_sub(w.x, f_mul(le[0], h)); w.y = f_sub(w.y, f_mul(le[1], h));
+    w.z = f_sub(w.z, f_mul(le[2], h)); w.w = f_sub(w.w, f_mul(le[3], h));
+    StoreStream4(wc4 + j * NQ, w);
+  }
+}
 template <int NL>
 GMX_DEV void LstmOutputStep(StreamSmem& s, const Arena& A, uint32_t last, uint32_t cur, uint32_t byte, int ltid) {
   const ArenaLayout& L = *A.L;
   const float* wl = A.at<float>(L.l_wout) + (size_t)last * L_HID * L_NOUT;
   float* wc = A.at<float>(L.l_wout) + (size_t)cur * L_HID * L_NOUT;
-  const float lr = (float)0.03;
-  constexpr int NQ = L_NOUT / 4;                       // 64 quads of adjacent outputs
-  constexpr int H = NL >= NQ ? NL / NQ : 1;            // row ranges per quad (more threads than quads)
-  constexpr int QPT = NL >= NQ ? 1 : NQ / NL;          // quads per thread (fewer threads than quads), advanced together
-  constexpr int ROWS = (L_HID + H - 1) / H;
-  static_assert(NL >= NQ || NQ % NL == 0, "a role smaller than 64 threads must divide 64");
-  if (ltid >= NQ * H) return;
-  const int q0 = ltid & (NQ - 1), half = ltid / NQ;    // outputs 4q..4q+3 for q = q0 + k * NL, rows [half * ROWS, ...)
-  float le[QPT][4];
-#pragma unroll
-  for (int k = 0; k < QPT; ++k)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const uint32_t i = 4 * (q0 + k * NL) + c;
-      const float err = i == byte ? f_sub(s.lprob[i], 1.0f) : s.lprob[i];
-      le[k][c] = f_mul(lr, err);
-    }
-  const float4* wl4 = (const float4*)wl + q0;
-  float4* wc4 = (float4*)wc + q0;
-  const int j0 = half * ROWS;
-  const int j1 = j0 + ROWS < L_HID ? j0 + ROWS : L_HID;
-GMX_UNROLL(QPT > 1 ? 2 : 4)
-  for (int j = j0; j < j1; ++j) {
-    const float h = s.l_hidden[j];
-    float4 w[QPT];
-#pragma unroll
-    for (int k = 0; k < QPT; ++k) w[k] = LoadStream4(wl4 + j * NQ + k * NL);
-#pragma unroll
-    for (int k = 0; k < QPT; ++k) {
-      w[k].x = f_sub(w[k].x, f_mul(le[k][0], h)); w[k].y = f_sub(w[k].y, f_mul(le[k][1], h));
-      w[k].z = f_sub(w[k].z, f_mul(le[k][2], h)); w[k].w = f_sub(w[k].w, f_mul(le[k][3], h));
-      StoreStream4(wc4 + j * NQ + k * NL, w[k]);
-    }
+  constexpr int NQ = L_NOUT / 4;   // 64 quads of adjacent outputs x 51 rows, split evenly over up to 128 threads
+  if (NL >= 2 * NQ) {              // two row halves per quad
+    if (ltid < 2 * NQ) { const int half = ltid / NQ; OutputStepRows<13>(s, wl, wc, ltid & (NQ - 1), half * 26, half ? L_HID : 26, byte); }
+  } else if (NL >= NQ + NQ / 2) {  // 96 threads: 64 take rows 0..33 of one quad, 32 take rows 34..50 of two quads
+    if (ltid < NQ) OutputStepRows<17>(s, wl, wc, ltid, 0, 34, byte);
+    else if (ltid < NQ + NQ / 2) { OutputStepRows<17>(s, wl, wc, 2 * (ltid - NQ), 34, L_HID, byte); OutputStepRows<17>(s, wl, wc, 2 * (ltid - NQ) + 1, 34, L_HID, byte); }
+  } else if (NL >= NQ) {
+    if (ltid < NQ) OutputStepRows<17>(s, wl, wc, ltid, 0, L_HID, byte);
+  } else {                         // fewer threads than quads
+    static_assert(NL >= NQ || NQ % NL == 0, "a role smaller than 64 threads must divide 64");
+    for (int q = ltid; q < NQ; q += NL) OutputStepRows<17>(s, wl, wc, q, 0, L_HID, byte);
   }
 }
 
@@ -679,6 +680,73 @@ GMX_DEV inline void PathNodes(BytePacket& pk, const float* probs, uint32_t byte,
 // streams are 1.7 x the L2. The caller has started L2 prefetches of the whole 185 KB (LstmForward), and every row's
 // next quad is requested right after its current one is consumed, so R loads per thread are always in flight without
 // a second set of registers.
+// RING: the weights travel through a private ring of LSTM_STAGES x R float4 slots per thread in s.w instead (cp.async
+// keeps R x LSTM_STAGES 16-byte copies in flight per thread without holding registers). Only legal when the bit path of
+// the same stream is not running (s.w is its weight-set staging area, empty at a byte boundary: BitBoundaryA).
+#ifndef LSTM_STAGES
+#define LSTM_STAGES 5
+#endif
+template <int NL>
+GMX_DEV void LstmGateDotsRing(StreamSmem& s, const float* W, uint32_t sym, int ltid) {
+  constexpr int NROWS = 3 * L_CELLS;
+  constexpr int R = (NROWS + NL - 1) / NL;
+  constexpr int NA = (NROWS + R - 1) / R;
+  constexpr int NQ = L_NOUT / 4 + L_CELLS / 4 + 1;
+  static_assert(LSTM_STAGES * R * NA * 16 <= WTOTAL * 4, "ring does not fit the weight-set staging area");
+  if (ltid >= NA) return;
+  float f[R];
+  const float4* w[R];
+  float4* ring = (float4*)s.w;
+  const uint64_t pol = PolicyEvictFirst();
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const int r = ltid + k * NA < NROWS ? ltid + k * NA : 0;
+    const int g = r / L_CELLS, i = r - g * L_CELLS;
+    w[k] = (const float4*)W + ((size_t)g * L_ROWQ + L_NOUT / 4) * L_CELLS + i;
+    f[k] = W[LstmW(g, (int)sym, i)];
+  }
+#pragma unroll
+  for (int q = 0; q < LSTM_STAGES; ++q) {
+#pragma unroll
+    for (int k = 0; k < R; ++k) CpAsync16Hint(ring + (q * R + k) * NA + ltid, w[k] + q * L_CELLS, pol);
+    CpAsyncCommit();
+  }
+  int st = 0;
+#pragma unroll 1
+  for (int q = 0; q < NQ; ++q) {
+    CpAsyncWaitGroup<LSTM_STAGES - 1>();
+    float4 a[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) a[k] = ring[(st * R + k) * NA + ltid];
+    if (q + LSTM_STAGES < NQ) {
+#pragma unroll
+      for (int k = 0; k < R; ++k) CpAsync16Hint(ring + (st * R + k) * NA + ltid, w[k] + (q + LSTM_STAGES) * L_CELLS, pol);
+    }
+    CpAsyncCommit();   // one group per iteration, empty at the tail, keeps the wait distance constant
+    st = st + 1 == LSTM_STAGES ? 0 : st + 1;
+    if (q < NQ - 1) {   // layer input = [ppm 256 | hidden 50 | 1]
+      const float4 x = q < L_NOUT / 4 ? ((const float4*)s.ppm)[q] : ((const float4*)s.l_hidden)[q - L_NOUT / 4];
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        f[k] = f_add(f[k], f_mul(x.x, a[k].x)); f[k] = f_add(f[k], f_mul(x.y, a[k].y));
+        f[k] = f_add(f[k], f_mul(x.z, a[k].z)); f[k] = f_add(f[k], f_mul(x.w, a[k].w));
+      }
+    } else {            // hidden 48, 49 and the bias input (1.0); the fourth column is padding
+      const float h48 = s.l_hidden[L_CELLS - 2], h49 = s.l_hidden[L_CELLS - 1];
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        f[k] = f_add(f[k], f_mul(h48, a[k].x)); f[k] = f_add(f[k], f_mul(h49, a[k].y)); f[k] = f_add(f[k], f_mul(1.0f, a[k].z));
+      }
+    }
+  }
+  CpAsyncWaitAll();
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const int r = ltid + k * NA;
+    if (r < NROWS) { const int g = r / L_CELLS; s.l_gate[g][r - g * L_CELLS] = f[k]; }
+  }
+}
+
 template <int NL>
 GMX_DEV void LstmGateDots(StreamSmem& s, const float* W, uint32_t sym, int ltid) {
   constexpr int NROWS = 3 * L_CELLS;
@@ -733,7 +801,7 @@ GMX_DEV void LstmGateDots(StreamSmem& s, const float* W, uint32_t sym, int ltid)
 // Precondition: s.ppm holds the normalised PPMd distribution of this byte. sym = the byte in front of it.
 // known_byte >= 0 (AHEAD): the byte this distribution is about to code; its path nodes go into the packet and the
 // output-layer step of Lstm::Perceive is fused (see below). Publishes n_ppm_used and n_pkt. ------------------------
-template <int NL, bool PROF>
+template <int NL, bool PROF, bool RING = false>
 GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, uint32_t b, uint32_t sym, int known_byte, int ltid, Lap<PROF>& lap) {
   const ArenaLayout& L = *A.L;
   const uint32_t e = s.l_epoch;
@@ -743,13 +811,14 @@ GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, u
   // HBM latency behind them (the lines are consumed within this pass, long before L2 could evict them).
   {
     const float* W = A.at<float>(L.l_w);
-    for (int g = 0; g < 3; ++g) PrefetchRange(W + LstmW(g, L_NOUT, 0), (L_ROWQ - L_NOUT / 4) * L_CELLS * 16, ltid, NL);
+    if (!RING) for (int g = 0; g < 3; ++g) PrefetchRange(W + LstmW(g, L_NOUT, 0), (L_ROWQ - L_NOUT / 4) * L_CELLS * 16, ltid, NL);
     PrefetchRange(A.at<float>(L.l_wout) + (size_t)e * L_HID * L_NOUT, L_HID * L_NOUT * 4, ltid, NL);
   }
   // layer_input[e] = [ppm 256 | hidden 50 | 1]  (SetInput lstm.cpp:45-50, copy :94-96)
   for (int i = ltid; i < L_NIN; i += NL) lin_e[i] = i < 256 ? s.ppm[i] : i < 306 ? s.l_hidden[i - 256] : 1.0f;
   for (int i = ltid; i < L_CELLS; i += NL) A.at<float>(L.l_last)[e * L_CELLS + i] = s.l_state[i];  // last_state_[epoch] = state_
-  LstmGateDots<NL>(s, A.at<float>(L.l_w), sym, ltid);
+  if (RING) LstmGateDotsRing<NL>(s, A.at<float>(L.l_w), sym, ltid);
+  else LstmGateDots<NL>(s, A.at<float>(L.l_w), sym, ltid);
   GroupSync<NL>(BAR_LSTM);
   if (ltid == 0) Publish(&s.n_ppm_used, b + 1);   // the PPMd role may overwrite ppm now
   lap.mark(17);
@@ -1323,17 +1392,38 @@ GMX_DEV inline void LearnTables(StreamSmem& s, const Arena& A, int bit, int t) {
   }
 }
 
+// Mixer gate selection (mixer.cpp:29-37) of mixer m whose gate context has the value c: if another weight set is needed,
+// queue the swap (the old set goes back to the pool, the new one - if it exists - is staged).
+GMX_DEV inline void GateSelect(StreamSmem& s, const Arena& A, int m, uint32_t c) {
+  const uint32_t idx = c & ((1u << s.T.mixer[m].log2) - 1);
+  if (idx != s.set_idx[m]) {
+    const uint32_t q = atomicAdd(&s.nswap, 1u);
+    s.swap_m[q] = (uint8_t)m;
+    s.swap_old[q] = s.set_pool[m];
+    s.swap_new[q] = A.at<uint32_t>(A.L->mix_dir[m])[idx];
+    s.set_idx[m] = idx;
+  }
+}
+
 // ---- Predictor::Predict (predictor.cpp:360-376), the part behind the bookkeeping and the byte boundary. ----------
 // path_bit >= 0 (AHEAD): index j of this bit inside its byte (0 = MSB); the byte models' predictions then come from
 // the packet of byte boundary b. Otherwise (lockstep) one work item per byte model evaluates its interval node.
+// learn_bit >= 0 (compress): the bit that is about to be coded; the table models then learn it on the threads that have
+// nothing to do while the first warp evaluates the mixer network (they depend on the bit and on the lookups, not on the
+// mixers), and the caller passes tables_done to LearnBit.
 template <int NB, bool PROF>
-GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, uint32_t b, int path_bit, int btid, Lap<PROF>& lap) {
+GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, uint32_t b, int path_bit, int btid, Lap<PROF>& lap, int learn_bit = -1) {
   const ArenaLayout& L = *A.L;
   const uint32_t bitctx = s.ctx[C_BIT_CONTEXT];
   const bool zero_inactive = s.analysis != 0;  // predictor.cpp:362-365
+  // Work items of the first phase: 41 Indirect + 6 Match lookups, the two byte models' nodes, and the gate selection of
+  // the 31 mixers whose gate context does not come out of this phase (their directory loads overlap the table probes).
 #pragma unroll 1
-  for (int t = btid; t < NIND + NMATCH + 2; t += NB) {
-    if (t < NIND) {  // Indirect::Predict indirect.cpp:28-45
+  for (int t = btid; t < NIND + NMATCH + 2 + NMIX; t += NB) {
+    if (t >= NIND + NMATCH + 2) {
+      const int m = t - (NIND + NMATCH + 2);
+      if (s.T.mixer[m].ctx != C_LONGEST) GateSelect(s, A, m, s.ctx[s.T.mixer[m].ctx]);
+    } else if (t < NIND) {  // Indirect::Predict indirect.cpp:28-45
       const int k = t;
       const uint32_t M = L.ind_size[k];
       uint32_t slot = s.ind_base[k] + bitctx;
@@ -1413,35 +1503,19 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, ui
   }
   GroupSync<NB>(BAR_BIT);
   lap.mark(3);
-  // Mixer gate selection (mixer.cpp:29-37): which weight set does each mixer need for this bit? + the layer-0 input
-  // vector: the active predictions, inactive ones as +0 (Mixer::Predict sums the active ones in index order; a +-0
-  // product leaves the running sum unchanged, the sum itself is never -0)
+  // longest_match = max(match_length / 32) (match.cpp:71-73) and the two mixers gated by it; the layer-0 input vector:
+  // the active predictions, inactive ones as +0 (Mixer::Predict sums the active ones in index order; a +-0 product leaves
+  // the running sum unchanged, the sum itself is never -0)
 #pragma unroll 1
-  for (int t = btid; t < NMIX + 1 + NPRED; t += NB) {
-    if (t < NMIX) {
-      const int m = t;
-      uint32_t c;
-      if (s.T.mixer[m].ctx == C_LONGEST) {  // longest_match = max(match_length / 32) (match.cpp:71-73)
-        c = 0;
-#pragma unroll 1
-        for (int k = 0; k < NMATCH; ++k) { const uint32_t v = s.m_len[k] >> 5; c = v > c ? v : c; }
-      } else {
-        c = s.ctx[s.T.mixer[m].ctx];
-      }
-      const uint32_t idx = c & ((1u << s.T.mixer[m].log2) - 1);
-      if (idx != s.set_idx[m]) {  // queue the swap: old set goes back to the pool, new one (if any) is staged
-        const uint32_t q = atomicAdd(&s.nswap, 1u);
-        s.swap_m[q] = (uint8_t)m;
-        s.swap_old[q] = s.set_pool[m];
-        s.swap_new[q] = A.at<uint32_t>(L.mix_dir[m])[idx];
-        s.set_idx[m] = idx;
-      }
-    } else if (t == NMIX) {
+  for (int t = btid; t < 3 + NPRED; t += NB) {
+    if (t < 3) {
       uint32_t c = 0;
+#pragma unroll 1
       for (int k = 0; k < NMATCH; ++k) { const uint32_t v = s.m_len[k] >> 5; c = v > c ? v : c; }
-      s.ctx[C_LONGEST] = c;
+      if (t == 0) s.ctx[C_LONGEST] = c;
+      else GateSelect(s, A, t == 1 ? 6 : NL0 + 6, c);
     } else {
-      const int i = t - (NMIX + 1);
+      const int i = t - 3;
       s.xe[i] = s.act[i] ? s.preds[i] : 0.0f;
     }
   }
@@ -1569,6 +1643,9 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, ui
       s.prob = prob;
     }
     lap.mark(9);
+  } else if (learn_bit >= 0) {
+#pragma unroll 1
+    for (int t = btid - 32; t < LEARN_TABLE_ITEMS; t += NB - 32) LearnTables(s, A, learn_bit, t);
   }
   GroupSync<NB>(BAR_BIT);
   lap.mark(10);
@@ -1601,7 +1678,8 @@ GMX_DEV inline void EncodeBit(StreamSmem& s, uint8_t* out, int bit) {
 // more work item of the first phase, which saves the barrier between coding and learning. code_out = the stream's
 // output slice. Returns with s.bit_stop refreshed (role-uniform).
 template <int NB, bool PROF>
-GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int btid, Lap<PROF>& lap, int known_bit = -1, uint8_t* code_out = nullptr) {
+GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int btid, Lap<PROF>& lap, int known_bit = -1, uint8_t* code_out = nullptr,
+                      bool tables_done = false) {
   const ArenaLayout& L = *A.L;
   const int bit = known_bit >= 0 ? known_bit : s.new_bit;
   const float fbit = (float)bit;
@@ -1632,7 +1710,7 @@ GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int 
       if (nsteps > mx) s.max_steps[m] = nsteps;
       s.shrink[m] = (nsteps & 1023u) == 0;
     } else if (t < NMIX + LEARN_TABLE_ITEMS) {
-      LearnTables(s, A, bit, t - NMIX);
+      if (!tables_done) LearnTables(s, A, bit, t - NMIX);
     } else if (known_bit >= 0) {   // Encoder::Encode encoder.cpp:8-34 (+ Perceive: predictor.cpp:378-381)
       EncodeBit(s, code_out, bit);
       s.new_bit = bit;
@@ -1785,13 +1863,13 @@ GMX_DEV void BitRoleCompress(StreamSmem& s, const Arena& A, const StreamParams& 
         BitBoundaryB<NB>(s, A, pos, btid);
         lap.mark(2);
       }
-      PredictBit<NB, PROF>(s, A, P, pos, 7 - j, btid, lap);
-      if (tracing) {   // debug/parity traces of stream 0 read the blackboard before Learn touches it
+      PredictBit<NB, PROF>(s, A, P, pos, 7 - j, btid, lap, NB > 32 ? bit : -1);
+      if (tracing) {   // debug/parity traces of stream 0 read the blackboard before the mixers learn
         if (btid == 0) Trace(s, P, (uint64_t)pos * 8 + (7 - j));
         GroupSync<NB>(BAR_BIT);
         lap.mark(13);
       }
-      LearnBit<NB, PROF>(s, A, P, btid, lap, bit, J.out);   // codes the bit and learns it
+      LearnBit<NB, PROF>(s, A, P, btid, lap, bit, J.out, NB > 32);   // codes the bit and learns it
       if (s.bit_stop) return;
     }
     if (btid == 0) Publish(&s.n_done, pos + 1);
@@ -1820,18 +1898,19 @@ GMX_DEV void BitLstmRoleCompress(StreamSmem& s, const Arena& A, const StreamPara
         BitBoundaryA<NB>(s, A, btid);
         lap.mark(2);
         WaitAtLeast(s, &s.n_ppm, pos + 1, 100);
+        GroupSync<NB>(BAR_BIT);   // every staged weight set is back in the pool: s.w is free for the forward pass's ring
         lap.mark(1);
-        LstmForward<NB, PROF>(s, A, P, pos, pos ? J.in[pos - 1] : s.byte0, (int)c, btid, lap);
+        LstmForward<NB, PROF, true>(s, A, P, pos, pos ? J.in[pos - 1] : s.byte0, (int)c, btid, lap);
         BitBoundaryB<NB>(s, A, pos, btid);
         lap.mark(2);
       }
-      PredictBit<NB, PROF>(s, A, P, pos, 7 - j, btid, lap);
+      PredictBit<NB, PROF>(s, A, P, pos, 7 - j, btid, lap, bit);
       if (tracing) {
         if (btid == 0) Trace(s, P, (uint64_t)pos * 8 + (7 - j));
         GroupSync<NB>(BAR_BIT);
         lap.mark(13);
       }
-      LearnBit<NB, PROF>(s, A, P, btid, lap, bit, J.out);
+      LearnBit<NB, PROF>(s, A, P, btid, lap, bit, J.out, true);
       if (s.bit_stop) return;
     }
     LstmPerceive<NB, PROF>(s, A, P, c, btid, lap);
@@ -1846,7 +1925,7 @@ GMX_DEV void BitLstmRoleCompress(StreamSmem& s, const Arena& A, const StreamPara
 // Predictor::Predict of one bit. known_byte >= 0 (serial compress): the byte being coded; path_bit = index of this bit in
 // it. The byte models then leave their eight path nodes in packet 0 at the byte boundary.
 template <int NT, bool PROF>
-GMX_DEV void SerialPredict(StreamSmem& s, const Arena& A, const StreamParams& P, int tid, Lap<PROF>& lap, int known_byte = -1, int path_bit = -1) {
+GMX_DEV void SerialPredict(StreamSmem& s, const Arena& A, const StreamParams& P, int tid, Lap<PROF>& lap, int known_byte = -1, int path_bit = -1, int learn_bit = -1) {
   if (tid == 0) Bookkeeping(s);
   __syncthreads();
   lap.mark(0);
@@ -1857,16 +1936,16 @@ GMX_DEV void SerialPredict(StreamSmem& s, const Arena& A, const StreamParams& P,
     else BitBoundaryA<NT - 32>(s, A, tid);
     __syncthreads();
     lap.mark(2);
-    LstmForward<NT, PROF>(s, A, P, 0, last, known_byte, tid, lap);
+    LstmForward<NT, PROF, true>(s, A, P, 0, last, known_byte, tid, lap);
     BitBoundaryB<NT>(s, A, 0, tid);
   }
-  PredictBit<NT, PROF>(s, A, P, 0, path_bit, tid, lap);
+  PredictBit<NT, PROF>(s, A, P, 0, path_bit, tid, lap, learn_bit);
 }
 // Predictor::Learn of one bit (s.new_bit, or known_bit which is then also coded into code_out first).
 template <int NT, bool PROF>
 GMX_DEV void SerialLearn(StreamSmem& s, const Arena& A, const StreamParams& P, int tid, Lap<PROF>& lap, int known_bit = -1, uint8_t* code_out = nullptr) {
   const int cur = s.recent_bits * 2 + (known_bit >= 0 ? known_bit : s.new_bit);
-  LearnBit<NT, PROF>(s, A, P, tid, lap, known_bit, code_out);
+  LearnBit<NT, PROF>(s, A, P, tid, lap, known_bit, code_out, known_bit >= 0);   // (SerialPredict ran the table models' Learn already when it knew the bit)
   if (cur >= 256) LstmPerceive<NT, PROF>(s, A, P, (uint32_t)(cur - 256), tid, lap);   // LstmModel::Learn lstm-model.cpp:50-59
 }
 
@@ -1883,7 +1962,7 @@ GMX_DEV void SerialCompress(StreamSmem& s, const Arena& A, const StreamParams& P
     const uint32_t c = J.in[pos];
 #pragma unroll 1
     for (int j = 7; j >= 0; --j) {
-      SerialPredict<NT, PROF>(s, A, P, tid, lap, (int)c, 7 - j);
+      SerialPredict<NT, PROF>(s, A, P, tid, lap, (int)c, 7 - j, (c >> j) & 1);
       if (tracing) {
         if (tid == 0) Trace(s, P, (uint64_t)pos * 8 + (7 - j));
         __syncthreads();
