@@ -50,7 +50,7 @@ def load_library():
     lib.gmx_resident_streams.restype = C.c_uint32
     lib.gmx_set_kernel_config.argtypes = [C.c_void_p, C.c_int]
     lib.gmx_get_kernel_config.argtypes = [C.c_void_p]
-    lib.gmx_kernel_config_info.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.gmx_kernel_config_info.argtypes = [C.c_int] + [C.POINTER(C.c_int)] * 5
     lib.gmx_arena_count.argtypes = [C.c_void_p]
     lib.gmx_arena_count.restype = C.c_uint32
     lib.gmx_arena_bytes.argtypes = [C.c_void_p]
@@ -334,12 +334,12 @@ class Context:
         return int(self.lib.gmx_get_kernel_config(self.h))
 
     def kernel_configs(self):
-        """[(bit warps, LSTM warps, CTAs per SM, serial compress)] of every kernel configuration in the library."""
+        """[(bit warps, LSTM warps, CTAs per SM, serial compress, resident gate weights)] of every kernel configuration."""
         out = []
         for k in range(self.lib.gmx_kernel_config_count()):
-            a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
-            self.lib.gmx_kernel_config_info(k, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
-            out.append((a.value, b.value, c.value, d.value))
+            v = [C.c_int() for _ in range(5)]
+            self.lib.gmx_kernel_config_info(k, *[C.byref(x) for x in v])
+            out.append(tuple(x.value for x in v))
         return out
 
     # ---- introspection ----

@@ -444,13 +444,14 @@ int gmx_set_kernel_config(gmx_ctx* c, int cfg) {
 }
 int gmx_get_kernel_config(const gmx_ctx* c) { return c ? c->kcfg : -1; }
 int gmx_kernel_config_count(void) { return gmx::kNumKernelConfigs; }
-int gmx_kernel_config_info(int cfg, int* bit_warps, int* lstm_warps, int* ctas_per_sm, int* serial) {
+int gmx_kernel_config_info(int cfg, int* bit_warps, int* lstm_warps, int* ctas_per_sm, int* serial, int* resident_weights) {
   if (cfg < 0 || cfg >= gmx::kNumKernelConfigs) return GMX_E_ARG;
   const gmx::KernelConfigInfo k = gmx::KernelConfig(cfg);
   if (bit_warps) *bit_warps = k.wb;
   if (lstm_warps) *lstm_warps = k.wl;
   if (ctas_per_sm) *ctas_per_sm = k.minb;
   if (serial) *serial = k.serial;
+  if (resident_weights) *resident_weights = k.ws;
   return 0;
 }
 

@@ -4,7 +4,7 @@
 namespace gmx {
 cudaError_t LaunchCompressProf(int cfg, const StreamParams& P, unsigned grid, cudaStream_t st) {
   switch (cfg) {
-#define X(id, wb, wl, minb, serial) case id: return LaunchStreamKernel<wb, wl, MODE_COMPRESS, minb, true, serial != 0>(P, grid, st);
+#define X(id, wb, wl, minb, serial, ws) case id: return LaunchStreamKernel<wb, wl, MODE_COMPRESS, minb, true, serial != 0, ws != 0>(P, grid, st);
     GMX_KERNEL_CONFIGS(X)
 #undef X
     default: return cudaErrorInvalidValue;

@@ -2,7 +2,7 @@
 namespace gmx {
 cudaError_t LaunchDecompress(int cfg, const StreamParams& P, unsigned grid, cudaStream_t st) {
   switch (cfg) {
-#define X(id, wb, wl, minb, serial) case id: return LaunchStreamKernel<wb, wl, MODE_DECOMPRESS, minb, false, false>(P, grid, st);
+#define X(id, wb, wl, minb, serial, ws) case id: return LaunchStreamKernel<wb, wl, MODE_DECOMPRESS, minb, false, false, ws != 0>(P, grid, st);
     GMX_KERNEL_CONFIGS(X)
 #undef X
     default: return cudaErrorInvalidValue;
@@ -10,7 +10,7 @@ cudaError_t LaunchDecompress(int cfg, const StreamParams& P, unsigned grid, cuda
 }
 cudaError_t OccupancyDecompress(int cfg, int* n) {
   switch (cfg) {
-#define X(id, wb, wl, minb, serial) case id: return OccupancyStreamKernel<wb, wl, MODE_DECOMPRESS, minb, false, false>(n);
+#define X(id, wb, wl, minb, serial, ws) case id: return OccupancyStreamKernel<wb, wl, MODE_DECOMPRESS, minb, false, false, ws != 0>(n);
     GMX_KERNEL_CONFIGS(X)
 #undef X
     default: return cudaErrorInvalidValue;

@@ -4,7 +4,7 @@
 namespace gmx {
 cudaError_t LaunchGenerate(int cfg, const StreamParams& P, unsigned grid, cudaStream_t st) {
   switch (cfg) {
-#define X(id, wb, wl, minb, serial) case id: return LaunchStreamKernel<wb, wl, MODE_GENERATE, minb, false, false>(P, grid, st);
+#define X(id, wb, wl, minb, serial, ws) case id: return LaunchStreamKernel<wb, wl, MODE_GENERATE, minb, false, false, ws != 0>(P, grid, st);
     GMX_KERNEL_CONFIGS(X)
 #undef X
     default: return cudaErrorInvalidValue;

@@ -11,19 +11,22 @@
 
 namespace gmx {
 // SERIAL = 1: compress walks the phases with all threads (no role pipeline); decompress and generation always do.
-//            id  WB WL MINB SERIAL
-#define GMX_KERNEL_CONFIGS(X) \
-  X(0, 2, 1, 8, 1)            \
-  X(1, 2, 1, 8, 0)            \
-  X(2, 1, 2, 8, 0)            \
-  X(3, 2, 2, 6, 0)            \
-  X(4, 4, 2, 4, 0)            \
-  X(5, 4, 2, 1, 0)            \
-  X(6, 3, 0, 8, 0)            \
-  X(7, 7, 0, 4, 0)
-constexpr int kNumKernelConfigs = 8;
+// WS = 1: the dense LSTM gate weights (184.8 KB) stay resident in shared memory (needs the whole SM: MINB = 1).
+//            id  WB WL MINB SERIAL WS
+#define GMX_KERNEL_CONFIGS(X)   \
+  X(0, 2, 1, 8, 1, 0)           \
+  X(1, 2, 1, 8, 0, 0)           \
+  X(2, 1, 2, 8, 0, 0)           \
+  X(3, 2, 2, 6, 0, 0)           \
+  X(4, 4, 2, 4, 0, 0)           \
+  X(5, 4, 2, 1, 0, 0)           \
+  X(6, 3, 0, 8, 0, 0)           \
+  X(7, 7, 0, 4, 0, 0)           \
+  X(8, 4, 8, 1, 0, 1)           \
+  X(9, 4, 4, 1, 0, 1)
+constexpr int kNumKernelConfigs = 10;
 constexpr int kStepWB = 2, kStepWL = 1;   // role split of the single-stream stepping kernel
-struct KernelConfigInfo { int wb, wl, minb, threads, serial; };
+struct KernelConfigInfo { int wb, wl, minb, threads, serial, ws; };
 KernelConfigInfo KernelConfig(int cfg);
 cudaError_t LaunchCompress(int cfg, const StreamParams& P, unsigned grid, cudaStream_t st);
 cudaError_t LaunchCompressProf(int cfg, const StreamParams& P, unsigned grid, cudaStream_t st);
@@ -35,20 +38,27 @@ cudaError_t OccupancyCompress(int cfg, int* blocks_per_sm);
 cudaError_t OccupancyDecompress(int cfg, int* blocks_per_sm);
 
 // Shared body of the per-mode launchers.
-template <int WB, int WL, int MODE, int MINB, bool PROF, bool SERIAL>
-inline cudaError_t LaunchStreamKernel(const StreamParams& P, unsigned grid, cudaStream_t st) {
+template <bool WS> constexpr size_t DynSmemBytes() { return WS ? (size_t)W_DENSE_BYTES + 16 : 0; }
+template <int WB, int WL, int MODE, int MINB, bool PROF, bool SERIAL, bool WS>
+inline cudaError_t PrepareStreamKernel() {
   // all of the SM's unified L1/shared memory as shared memory, so that MINB CTAs are co-resident
-  static const cudaError_t carve = cudaFuncSetAttribute(StreamKernel<WB, WL, MODE, MINB, PROF, SERIAL>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                        cudaSharedmemCarveoutMaxShared);
-  if (carve != cudaSuccess) return carve;
-  StreamKernel<WB, WL, MODE, MINB, PROF, SERIAL><<<grid, 32 * (WB + WL + 1), 0, st>>>(P);
+  cudaError_t e = cudaFuncSetAttribute(StreamKernel<WB, WL, MODE, MINB, PROF, SERIAL, WS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e == cudaSuccess && WS)
+    e = cudaFuncSetAttribute(StreamKernel<WB, WL, MODE, MINB, PROF, SERIAL, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DynSmemBytes<WS>());
+  return e;
+}
+template <int WB, int WL, int MODE, int MINB, bool PROF, bool SERIAL, bool WS>
+inline cudaError_t LaunchStreamKernel(const StreamParams& P, unsigned grid, cudaStream_t st) {
+  static const cudaError_t prep = PrepareStreamKernel<WB, WL, MODE, MINB, PROF, SERIAL, WS>();
+  if (prep != cudaSuccess) return prep;
+  StreamKernel<WB, WL, MODE, MINB, PROF, SERIAL, WS><<<grid, 32 * (WB + WL + 1), DynSmemBytes<WS>(), st>>>(P);
   return cudaGetLastError();
 }
-template <int WB, int WL, int MODE, int MINB, bool PROF, bool SERIAL>
+template <int WB, int WL, int MODE, int MINB, bool PROF, bool SERIAL, bool WS>
 inline cudaError_t OccupancyStreamKernel(int* n) {
-  cudaError_t e = cudaFuncSetAttribute(StreamKernel<WB, WL, MODE, MINB, PROF, SERIAL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaError_t e = PrepareStreamKernel<WB, WL, MODE, MINB, PROF, SERIAL, WS>();
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, StreamKernel<WB, WL, MODE, MINB, PROF, SERIAL>, 32 * (WB + WL + 1), 0);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, StreamKernel<WB, WL, MODE, MINB, PROF, SERIAL, WS>, 32 * (WB + WL + 1), DynSmemBytes<WS>());
 }
 }  // namespace gmx
 #endif

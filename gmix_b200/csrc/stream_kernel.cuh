@@ -206,7 +206,7 @@ struct StreamSmem {
   alignas(16) float l_err256[256];         // LSTM role scratch (output pre-activations, BPTT error vector, symbol lists)
   alignas(16) float l_hidden[L_HID + 1]; float l_state[L_CELLS], l_state_err[L_CELLS], l_stored_err[L_CELLS], l_hidden_err[L_CELLS];
   float l_gate[3][L_CELLS], l_gerr[3][L_CELLS];
-  float l_red[24];               // 0..2 ivar, 3 sum, 4..11 / 12..19 per-warp partial results, 20..22 BPTT sums
+  float l_red[40];               // 0..2 ivar, 3 sum, 4..19 / 20..35 per-warp partial results, 36..38 BPTT sums
   uint32_t p_masked[8];          // PPMd: bit sym = CharMask[sym] == EscCount (ppmd.cuh)
   uint8_t l_hist[L_HORIZON], l_symin[L_HORIZON];
   uint32_t l_epoch, l_update_steps, l_old_input, l_fused;
@@ -220,6 +220,7 @@ struct StreamSmem {
   uint32_t n_pkt;          // byte boundaries whose packet (and lprob) is published
   uint32_t n_done;         // bytes the bit role has finished (frees packet slots)
   uint32_t bit_stop, lstm_stop;   // role-uniform copies of `error != 0`, refreshed at role-defined points
+  uint32_t wphase;         // phase of the gate-weight mbarrier (latency configurations)
   uint32_t byte0;          // byte in front of the stream (0 from scratch: the reference's phantom first byte)
 };
 
@@ -490,6 +491,79 @@ GMX_DEV inline void PrefetchRange(const void* p, uint32_t bytes, int t, int nthr
 }
 
 
+// ---- TMA bulk copies (cp.async.bulk, 1-D, no tensor map) and their mbarrier --------------------------------
+GMX_DEV inline void MbarInit(uint64_t* mbar, uint32_t count) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(mbar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#else
+  *mbar = 0; (void)count;
+#endif
+}
+GMX_DEV inline void MbarExpectTx(uint64_t* mbar, uint32_t bytes) {   // one arrival + `bytes` of pending transactions
+#if defined(__CUDA_ARCH__)
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(mbar)), "r"(bytes) : "memory");
+#else
+  (void)mbar; (void)bytes;
+#endif
+}
+GMX_DEV inline void MbarWait(uint64_t* mbar, uint32_t parity) {
+#if defined(__CUDA_ARCH__)
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(mbar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  }
+#else
+  (void)mbar; (void)parity;
+#endif
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion is signalled on mbar
+GMX_DEV inline void BulkG2S(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* mbar) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(mbar)) : "memory");
+#else
+  (void)mbar; memcpy(smem_dst, gmem_src, bytes);
+#endif
+}
+// `bytes` (multiple of 16) at a 16-byte aligned global address -> L2, one instruction
+GMX_DEV inline void BulkPrefetchL2(const void* gmem_src, uint32_t bytes) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+#else
+  (void)gmem_src; (void)bytes;
+#endif
+}
+// orders this thread's earlier global/shared writes (generic proxy) before later bulk copies (async proxy)
+GMX_DEV inline void FenceProxyAsync() {
+#if defined(__CUDA_ARCH__)
+  __threadfence();
+  asm volatile("fence.proxy.async;" ::: "memory");
+#endif
+}
+
+// Gate weights resident in shared memory (latency configurations, one CTA per SM): the dense part of the three gate
+// matrices, [3][77 quads][50 cells] float4 = 184 800 B of dynamic shared memory, refreshed from the arena by three TMA
+// bulk copies after every Adam step (once per 100 bytes) instead of being streamed from HBM for every byte.
+enum : int { W_DENSE_Q = L_ROWQ - L_NOUT / 4, W_DENSE_F4 = 3 * W_DENSE_Q * L_CELLS, W_DENSE_BYTES = W_DENSE_F4 * 16 };
+struct WeightSmem { float4* w; uint64_t* mbar; };   // w == nullptr: not resident
+template <int NL>
+GMX_DEV void LoadGateWeights(StreamSmem& s, const Arena& A, const WeightSmem& ws, int ltid) {
+  FenceProxyAsync();            // Adam's (or InitStream's) stores of every thread of the group
+  GroupSync<NL>(BAR_LSTM);
+  const uint32_t parity = s.wphase & 1u;
+  if (ltid == 0) {
+    const float* W = A.at<float>(A.L->l_w);
+    MbarExpectTx(ws.mbar, (uint32_t)W_DENSE_BYTES);
+    for (int g = 0; g < 3; ++g) BulkG2S(ws.w + g * W_DENSE_Q * L_CELLS, W + LstmW(g, L_NOUT, 0), W_DENSE_Q * L_CELLS * 16, ws.mbar);
+  }
+  MbarWait(ws.mbar, parity);
+  GroupSync<NL>(BAR_LSTM);
+  if (ltid == 0) s.wphase = parity ^ 1u;
+}
+
 // ---- stream start ------------------------------------------------------------------------------
 template <int NT>
 GMX_DEV void FillWords(uint32_t* p, uint64_t nwords, uint32_t v, int tid) {
@@ -582,6 +656,7 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
     s.byte0 = s.first_prediction ? 0u : (uint32_t)(s.recent_bits * 2 + s.new_bit) & 0xffu;
     s.t_start_us = (uint32_t)(GlobalTimerNs() / 1000ull);
   }
+  FenceProxyAsync();   // the arena this thread has just written may be read by TMA bulk copies (resident gate weights)
   __syncthreads();
 }
 
@@ -747,6 +822,48 @@ GMX_DEV void LstmGateDotsRing(StreamSmem& s, const float* W, uint32_t sym, int l
   }
 }
 
+// Resident variant: the dense weights come from shared memory (WeightSmem), only the one-hot column from the arena.
+template <int NL>
+GMX_DEV void LstmGateDotsSmem(StreamSmem& s, const float* W, const float4* wd, uint32_t sym, int ltid) {
+  constexpr int NROWS = 3 * L_CELLS;
+  constexpr int R = (NROWS + NL - 1) / NL;
+  constexpr int NA = (NROWS + R - 1) / R;
+  constexpr int NQ = W_DENSE_Q;
+  if (ltid >= NA) return;
+  float f[R];
+  const float4* w[R];
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const int r = ltid + k * NA < NROWS ? ltid + k * NA : 0;
+    const int g = r / L_CELLS, i = r - g * L_CELLS;
+    w[k] = wd + (size_t)g * W_DENSE_Q * L_CELLS + i;
+    f[k] = W[LstmW(g, (int)sym, i)];
+  }
+#pragma unroll 4
+  for (int q = 0; q < NQ - 1; ++q) {
+    const float4 x = q < L_NOUT / 4 ? ((const float4*)s.ppm)[q] : ((const float4*)s.l_hidden)[q - L_NOUT / 4];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const float4 c = w[k][q * L_CELLS];
+      f[k] = f_add(f[k], f_mul(x.x, c.x)); f[k] = f_add(f[k], f_mul(x.y, c.y));
+      f[k] = f_add(f[k], f_mul(x.z, c.z)); f[k] = f_add(f[k], f_mul(x.w, c.w));
+    }
+  }
+  {
+    const float h48 = s.l_hidden[L_CELLS - 2], h49 = s.l_hidden[L_CELLS - 1];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const float4 c = w[k][(NQ - 1) * L_CELLS];
+      f[k] = f_add(f[k], f_mul(h48, c.x)); f[k] = f_add(f[k], f_mul(h49, c.y)); f[k] = f_add(f[k], f_mul(1.0f, c.z));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const int r = ltid + k * NA;
+    if (r < NROWS) { const int g = r / L_CELLS; s.l_gate[g][r - g * L_CELLS] = f[k]; }
+  }
+}
+
 template <int NL>
 GMX_DEV void LstmGateDots(StreamSmem& s, const float* W, uint32_t sym, int ltid) {
   constexpr int NROWS = 3 * L_CELLS;
@@ -802,7 +919,8 @@ GMX_DEV void LstmGateDots(StreamSmem& s, const float* W, uint32_t sym, int ltid)
 // known_byte >= 0 (AHEAD): the byte this distribution is about to code; its path nodes go into the packet and the
 // output-layer step of Lstm::Perceive is fused (see below). Publishes n_ppm_used and n_pkt. ------------------------
 template <int NL, bool PROF, bool RING = false>
-GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, uint32_t b, uint32_t sym, int known_byte, int ltid, Lap<PROF>& lap) {
+GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, uint32_t b, uint32_t sym, int known_byte, int ltid, Lap<PROF>& lap,
+                         const WeightSmem& ws = WeightSmem{nullptr, nullptr}) {
   const ArenaLayout& L = *A.L;
   const uint32_t e = s.l_epoch;
   float* lin_e = A.at<float>(L.l_lin) + e * (L_NIN + 1);
@@ -811,13 +929,16 @@ GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, u
   // HBM latency behind them (the lines are consumed within this pass, long before L2 could evict them).
   {
     const float* W = A.at<float>(L.l_w);
-    if (!RING) for (int g = 0; g < 3; ++g) PrefetchRange(W + LstmW(g, L_NOUT, 0), (L_ROWQ - L_NOUT / 4) * L_CELLS * 16, ltid, NL);
-    PrefetchRange(A.at<float>(L.l_wout) + (size_t)e * L_HID * L_NOUT, L_HID * L_NOUT * 4, ltid, NL);
+    if (ltid == 0) {   // one bulk prefetch instruction per contiguous range
+      if (!RING && !ws.w) for (int g = 0; g < 3; ++g) BulkPrefetchL2(W + LstmW(g, L_NOUT, 0), W_DENSE_Q * L_CELLS * 16);
+      BulkPrefetchL2(A.at<float>(L.l_wout) + (size_t)e * L_HID * L_NOUT, L_HID * L_NOUT * 4);
+    }
   }
   // layer_input[e] = [ppm 256 | hidden 50 | 1]  (SetInput lstm.cpp:45-50, copy :94-96)
   for (int i = ltid; i < L_NIN; i += NL) lin_e[i] = i < 256 ? s.ppm[i] : i < 306 ? s.l_hidden[i - 256] : 1.0f;
   for (int i = ltid; i < L_CELLS; i += NL) A.at<float>(L.l_last)[e * L_CELLS + i] = s.l_state[i];  // last_state_[epoch] = state_
-  if (RING) LstmGateDotsRing<NL>(s, A.at<float>(L.l_w), sym, ltid);
+  if (ws.w) LstmGateDotsSmem<NL>(s, A.at<float>(L.l_w), ws.w, sym, ltid);
+  else if (RING) LstmGateDotsRing<NL>(s, A.at<float>(L.l_w), sym, ltid);
   else LstmGateDots<NL>(s, A.at<float>(L.l_w), sym, ltid);
   GroupSync<NL>(BAR_LSTM);
   if (ltid == 0) Publish(&s.n_ppm_used, b + 1);   // the PPMd role may overwrite ppm now
@@ -915,14 +1036,14 @@ GMX_UNROLL(QPT > 1 ? 3 : 17)
     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
     if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
   }
-  if ((ltid & 31) == 0) { s.l_red[4 + (ltid >> 5)] = bv; s.l_red[12 + (ltid >> 5)] = (float)bi; }
+  if ((ltid & 31) == 0) { s.l_red[4 + (ltid >> 5)] = bv; s.l_red[20 + (ltid >> 5)] = (float)bi; }
   GroupSync<NL>(BAR_LSTM);
   BytePacket& pk = s.pkt[b % PKT_RING];
   if (ltid < 32) {
     if (ltid == 0) {
       float v = 0.0f; int vi = 0;
       for (int wi = 0; wi < NL / 32; ++wi) {
-        const float ov = s.l_red[4 + wi]; const int oi = (int)s.l_red[12 + wi];
+        const float ov = s.l_red[4 + wi]; const int oi = (int)s.l_red[20 + wi];
         if (ov > v || (ov == v && ov > 0.0f && oi < vi)) { v = ov; vi = oi; }
       }
       pk.lstm_ctx = v > 0.0f ? (uint32_t)vi : 0u;
@@ -933,7 +1054,7 @@ GMX_UNROLL(QPT > 1 ? 3 : 17)
     __syncwarp();
     if (ltid == 0) Publish(&s.n_pkt, b + 1);
   }
-  static_assert(NL / 32 <= 8, "l_red slots 4..11 / 12..19 hold one partial result per warp");
+  static_assert(NL / 32 <= 16, "l_red slots 4..19 / 20..35 hold one partial result per warp");
   lap.mark(18);
   // AHEAD knows the byte this distribution is about to code, so the output-layer step that Lstm::Perceive performs
   // after the byte (same operands: these probabilities, this hidden state, the layer of slot e) runs now, while slot e
@@ -950,7 +1071,7 @@ GMX_UNROLL(QPT > 1 ? 3 : 17)
 // LstmLayer::BackwardPass lstm-layer.cpp:252-354). Weight gradients are accumulated per weight in
 // the reference's epoch order (99 -> 0) by the thread that owns the weight, then Adam is applied.
 template <int NL, bool PROF>
-GMX_DEV void LstmBptt(StreamSmem& s, const Arena& A, const StreamParams& P, int ltid, Lap<PROF>& lap) {
+GMX_DEV void LstmBptt(StreamSmem& s, const Arena& A, const StreamParams& P, int ltid, Lap<PROF>& lap, const WeightSmem& ws) {
   const ArenaLayout& L = *A.L;
   float* gb = A.at<float>(L.l_gb);
   const float* W = A.at<float>(L.l_w);
@@ -965,11 +1086,11 @@ GMX_DEV void LstmBptt(StreamSmem& s, const Arena& A, const StreamParams& P, int 
   }
   GroupSync<NL>(BAR_LSTM);
   constexpr int CPT = (L_CELLS + NL - 1) / NL;   // cells per thread in the cell-parallel phases (2 when the role is one warp)
-  PrefetchRange(A.at<float>(L.l_wout) + (size_t)(L_HORIZON - 1) * L_HID * L_NOUT, L_HID * L_NOUT * 4, ltid, NL);
+  if (ltid == 0) BulkPrefetchL2(A.at<float>(L.l_wout) + (size_t)(L_HORIZON - 1) * L_HID * L_NOUT, L_HID * L_NOUT * 4);
 #pragma unroll 1
   for (int ep = L_HORIZON - 1; ep >= 0; --ep) {
     // the output layer of the next (earlier) epoch: 52 KB this pass will stream one epoch from now
-    if (ep > 0) PrefetchRange(A.at<float>(L.l_wout) + (size_t)(ep - 1) * L_HID * L_NOUT, L_HID * L_NOUT * 4, ltid, NL);
+    if (ep > 0 && ltid == 0) BulkPrefetchL2(A.at<float>(L.l_wout) + (size_t)(ep - 1) * L_HID * L_NOUT, L_HID * L_NOUT * 4);
     const float* out_e = A.at<float>(L.l_out) + ep * L_NOUT;
     for (int i = ltid; i < L_NOUT; i += NL)
       s.l_err256[i] = (uint32_t)i == s.l_hist[ep] ? f_sub(out_e[i], 1.0f) : out_e[i];
@@ -1042,13 +1163,13 @@ GMX_UNROLL(GMX_BPTT_UNROLL)
       float acc = f_mul(s.l_gerr[g][L_CELLS - 1], nrm[L_CELLS - 1]);
 #pragma unroll 7
       for (int k = L_CELLS - 2; k >= 0; --k) acc = f_add(acc, f_mul(s.l_gerr[g][k], nrm[k]));
-      s.l_red[20 + g] = f_div(acc, (float)L_CELLS);
+      s.l_red[36 + g] = f_div(acc, (float)L_CELLS);
     }
     GroupSync<NL>(BAR_LSTM);
     for (int t = ltid; t < 3 * L_CELLS; t += NL) {
       const int g = t / L_CELLS, i = t - g * L_CELLS;
       const float nrm = A.at<float>(L.l_norm)[((size_t)g * L_HORIZON + ep) * L_CELLS + i];
-      const float ne = f_sub(s.l_gerr[g][i], f_mul(s.l_red[20 + g], nrm));
+      const float ne = f_sub(s.l_gerr[g][i], f_mul(s.l_red[36 + g], nrm));
       s.l_gerr[g][i] = ne;
       errh[((size_t)g * L_HORIZON + ep) * L_CELLS + i] = ne;
     }
@@ -1173,12 +1294,14 @@ GMX_UNROLL(GPT > 1 ? 2 : 4)
     *w = f_sub(*w, f_mul(alpha, f_div(f_div(m, d1), f_sqrt(f_add(f_div(v, d2), eps)))));
   }
   GroupSync<NL>(BAR_LSTM);
+  if (ws.w) LoadGateWeights<NL>(s, A, ws, ltid);   // the resident copy follows the Adam step
   lap.mark(21);
 }
 
 // Lstm::Perceive (lstm.cpp:52-89) after the last bit of `byte`.
 template <int NL, bool PROF>
-GMX_DEV void LstmPerceive(StreamSmem& s, const Arena& A, const StreamParams& P, uint32_t byte, int ltid, Lap<PROF>& lap) {
+GMX_DEV void LstmPerceive(StreamSmem& s, const Arena& A, const StreamParams& P, uint32_t byte, int ltid, Lap<PROF>& lap,
+                          const WeightSmem& ws = WeightSmem{nullptr, nullptr}) {
   const uint32_t cur = s.l_epoch;
   const uint32_t last = cur == 0 ? L_HORIZON - 1 : cur - 1;
   if (ltid == 0) { s.l_old_input = s.l_hist[last]; s.l_hist[last] = (uint8_t)byte; }
@@ -1187,7 +1310,7 @@ GMX_DEV void LstmPerceive(StreamSmem& s, const Arena& A, const StreamParams& P, 
     // input symbol of epoch ep = byte perceived before it (lstm.cpp:71-74)
     for (int ep = ltid; ep < L_HORIZON; ep += NL) s.l_symin[ep] = ep == 0 ? (uint8_t)s.l_old_input : s.l_hist[ep - 1];
     GroupSync<NL>(BAR_LSTM);
-    LstmBptt<NL, PROF>(s, A, P, ltid, lap);
+    LstmBptt<NL, PROF>(s, A, P, ltid, lap, ws);
   }
   if (!s.l_fused) { LstmOutputStep<NL>(s, A, last, cur, byte, ltid); lap.mark(19); }
   GroupSync<NL>(BAR_LSTM);
@@ -1824,9 +1947,10 @@ GMX_DEV void PpmdRole(StreamSmem& s, const Arena& A, const StreamJob& J, ProfSme
 
 // LSTM role: forward(b), Perceive(byte b) back to back.
 template <int NL, bool PROF>
-GMX_DEV void LstmRole(StreamSmem& s, const Arena& A, const StreamParams& P, const StreamJob& J, ProfSmem* prof, int ltid) {
+GMX_DEV void LstmRole(StreamSmem& s, const Arena& A, const StreamParams& P, const StreamJob& J, ProfSmem* prof, int ltid, const WeightSmem& ws) {
   Lap<PROF> lap;
   lap.start(prof, ltid == 0);
+  if (ws.w) LoadGateWeights<NL>(s, A, ws, ltid);
 #pragma unroll 1
   for (uint32_t b = 0; b < J.n_bytes; ++b) {
     if (ltid == 0) s.lstm_stop = VolatileLoad(&s.error) != 0;
@@ -1834,8 +1958,8 @@ GMX_DEV void LstmRole(StreamSmem& s, const Arena& A, const StreamParams& P, cons
     if (s.lstm_stop) break;
     WaitAtLeast(s, &s.n_ppm, b + 1, 200);
     lap.mark(16);
-    LstmForward<NL, PROF>(s, A, P, b, b ? J.in[b - 1] : s.byte0, (int)J.in[b], ltid, lap);
-    LstmPerceive<NL, PROF>(s, A, P, J.in[b], ltid, lap);
+    LstmForward<NL, PROF>(s, A, P, b, b ? J.in[b - 1] : s.byte0, (int)J.in[b], ltid, lap, ws);
+    LstmPerceive<NL, PROF>(s, A, P, J.in[b], ltid, lap, ws);
   }
 }
 
@@ -1881,9 +2005,11 @@ GMX_DEV void BitRoleCompress(StreamSmem& s, const Arena& A, const StreamParams& 
 // itself in the serial order (its neighbours would idle at a barrier for ~16 % of the byte); everything else keeps the
 // full width.
 template <int NB, bool PROF>
-GMX_DEV void BitLstmRoleCompress(StreamSmem& s, const Arena& A, const StreamParams& P, const StreamJob& J, uint32_t sid, ProfSmem* prof, int btid) {
+GMX_DEV void BitLstmRoleCompress(StreamSmem& s, const Arena& A, const StreamParams& P, const StreamJob& J, uint32_t sid, ProfSmem* prof, int btid,
+                                 const WeightSmem& ws) {
   Lap<PROF> lap;
   lap.start(prof, btid == 0);
+  if (ws.w) LoadGateWeights<NB>(s, A, ws, btid);
   const bool tracing = sid == 0 && (P.bit_trace || P.pred_trace);
 #pragma unroll 1
   for (uint32_t pos = 0; pos < J.n_bytes; ++pos) {
@@ -1900,7 +2026,7 @@ GMX_DEV void BitLstmRoleCompress(StreamSmem& s, const Arena& A, const StreamPara
         WaitAtLeast(s, &s.n_ppm, pos + 1, 100);
         GroupSync<NB>(BAR_BIT);   // every staged weight set is back in the pool: s.w is free for the forward pass's ring
         lap.mark(1);
-        LstmForward<NB, PROF, true>(s, A, P, pos, pos ? J.in[pos - 1] : s.byte0, (int)c, btid, lap);
+        LstmForward<NB, PROF, true>(s, A, P, pos, pos ? J.in[pos - 1] : s.byte0, (int)c, btid, lap, ws);
         BitBoundaryB<NB>(s, A, pos, btid);
         lap.mark(2);
       }
@@ -1913,7 +2039,7 @@ GMX_DEV void BitLstmRoleCompress(StreamSmem& s, const Arena& A, const StreamPara
       LearnBit<NB, PROF>(s, A, P, btid, lap, bit, J.out, true);
       if (s.bit_stop) return;
     }
-    LstmPerceive<NB, PROF>(s, A, P, c, btid, lap);
+    LstmPerceive<NB, PROF>(s, A, P, c, btid, lap, ws);
     if (btid == 0) Publish(&s.n_done, pos + 1);
   }
 }
@@ -1925,7 +2051,8 @@ GMX_DEV void BitLstmRoleCompress(StreamSmem& s, const Arena& A, const StreamPara
 // Predictor::Predict of one bit. known_byte >= 0 (serial compress): the byte being coded; path_bit = index of this bit in
 // it. The byte models then leave their eight path nodes in packet 0 at the byte boundary.
 template <int NT, bool PROF>
-GMX_DEV void SerialPredict(StreamSmem& s, const Arena& A, const StreamParams& P, int tid, Lap<PROF>& lap, int known_byte = -1, int path_bit = -1, int learn_bit = -1) {
+GMX_DEV void SerialPredict(StreamSmem& s, const Arena& A, const StreamParams& P, int tid, Lap<PROF>& lap, const WeightSmem& ws, int known_byte = -1,
+                           int path_bit = -1, int learn_bit = -1) {
   if (tid == 0) Bookkeeping(s);
   __syncthreads();
   lap.mark(0);
@@ -1936,38 +2063,41 @@ GMX_DEV void SerialPredict(StreamSmem& s, const Arena& A, const StreamParams& P,
     else BitBoundaryA<NT - 32>(s, A, tid);
     __syncthreads();
     lap.mark(2);
-    LstmForward<NT, PROF, true>(s, A, P, 0, last, known_byte, tid, lap);
+    LstmForward<NT, PROF, true>(s, A, P, 0, last, known_byte, tid, lap, ws);
     BitBoundaryB<NT>(s, A, 0, tid);
   }
   PredictBit<NT, PROF>(s, A, P, 0, path_bit, tid, lap, learn_bit);
 }
 // Predictor::Learn of one bit (s.new_bit, or known_bit which is then also coded into code_out first).
 template <int NT, bool PROF>
-GMX_DEV void SerialLearn(StreamSmem& s, const Arena& A, const StreamParams& P, int tid, Lap<PROF>& lap, int known_bit = -1, uint8_t* code_out = nullptr) {
+GMX_DEV void SerialLearn(StreamSmem& s, const Arena& A, const StreamParams& P, int tid, Lap<PROF>& lap, const WeightSmem& ws, int known_bit = -1,
+                         uint8_t* code_out = nullptr) {
   const int cur = s.recent_bits * 2 + (known_bit >= 0 ? known_bit : s.new_bit);
   LearnBit<NT, PROF>(s, A, P, tid, lap, known_bit, code_out, known_bit >= 0);   // (SerialPredict ran the table models' Learn already when it knew the bit)
-  if (cur >= 256) LstmPerceive<NT, PROF>(s, A, P, (uint32_t)(cur - 256), tid, lap);   // LstmModel::Learn lstm-model.cpp:50-59
+  if (cur >= 256) LstmPerceive<NT, PROF>(s, A, P, (uint32_t)(cur - 256), tid, lap, ws);   // LstmModel::Learn lstm-model.cpp:50-59
 }
 
 // runner_utils::Compress (runner-utils.cpp:43-67) without the role pipeline: all phases with all threads. With a full
 // wave of resident streams per SM the other streams already hide this stream's latencies, and every phase having all
 // threads beats the pipeline's fixed split of them (kernels.h: configurations).
 template <int NT, bool PROF>
-GMX_DEV void SerialCompress(StreamSmem& s, const Arena& A, const StreamParams& P, const StreamJob& J, uint32_t sid, ProfSmem* prof, int tid) {
+GMX_DEV void SerialCompress(StreamSmem& s, const Arena& A, const StreamParams& P, const StreamJob& J, uint32_t sid, ProfSmem* prof, int tid,
+                            const WeightSmem& ws) {
   Lap<PROF> lap;
   lap.start(prof, tid == 0);
+  if (ws.w) LoadGateWeights<NT>(s, A, ws, tid);
   const bool tracing = sid == 0 && (P.bit_trace || P.pred_trace);
 #pragma unroll 1
   for (uint32_t pos = 0; pos < J.n_bytes; ++pos) {
     const uint32_t c = J.in[pos];
 #pragma unroll 1
     for (int j = 7; j >= 0; --j) {
-      SerialPredict<NT, PROF>(s, A, P, tid, lap, (int)c, 7 - j, (c >> j) & 1);
+      SerialPredict<NT, PROF>(s, A, P, tid, lap, ws, (int)c, 7 - j, (c >> j) & 1);
       if (tracing) {
         if (tid == 0) Trace(s, P, (uint64_t)pos * 8 + (7 - j));
         __syncthreads();
       }
-      SerialLearn<NT, PROF>(s, A, P, tid, lap, (c >> j) & 1, J.out);
+      SerialLearn<NT, PROF>(s, A, P, tid, lap, ws, (c >> j) & 1, J.out);
       if (s.bit_stop) return;
     }
   }
@@ -1975,14 +2105,15 @@ GMX_DEV void SerialCompress(StreamSmem& s, const Arena& A, const StreamParams& P
 
 // runner_utils::Decompress (runner-utils.cpp:69-86); Decoder::Decode decoder.cpp:19-39. Analysis is never on.
 template <int NT, bool PROF>
-GMX_DEV void SerialDecompress(StreamSmem& s, const Arena& A, const StreamParams& P, const StreamJob& J, ProfSmem* prof, int tid) {
+GMX_DEV void SerialDecompress(StreamSmem& s, const Arena& A, const StreamParams& P, const StreamJob& J, ProfSmem* prof, int tid, const WeightSmem& ws) {
   Lap<PROF> lap;
   lap.start(prof, tid == 0);
+  if (ws.w) LoadGateWeights<NT>(s, A, ws, tid);
 #pragma unroll 1
   for (uint32_t pos = 0; pos < J.n_bytes; ++pos) {
 #pragma unroll 1
     for (int j = 7; j >= 0; --j) {
-      SerialPredict<NT, PROF>(s, A, P, tid, lap);
+      SerialPredict<NT, PROF>(s, A, P, tid, lap, ws);
       if (tid == 0) {
         const uint32_t p16 = Discretize(s.prob);
         const uint32_t r = s.x2 - s.x1;
@@ -1994,7 +2125,7 @@ GMX_DEV void SerialDecompress(StreamSmem& s, const Arena& A, const StreamParams&
         if (j == 0) J.out[pos] = (uint8_t)((s.recent_bits * 2 + bit) & 0xff);
       }
       __syncthreads();
-      SerialLearn<NT, PROF>(s, A, P, tid, lap);
+      SerialLearn<NT, PROF>(s, A, P, tid, lap, ws);
       if (s.bit_stop) return;
     }
   }
@@ -2004,22 +2135,24 @@ GMX_DEV void SerialDecompress(StreamSmem& s, const Arena& A, const StreamParams&
 // learning, then n_bytes bytes are sampled bit by bit without Learn: prob = Logistic(Logit(prob) / temperature),
 // bit = r < prob with r the next rand()/RAND_MAX draw, Perceive(bit), Predict().
 template <int NT, bool PROF>
-GMX_DEV void SerialGenerate(StreamSmem& s, const Arena& A, const StreamParams& P, const StreamJob& J, const float* ru, ProfSmem* prof, int tid) {
+GMX_DEV void SerialGenerate(StreamSmem& s, const Arena& A, const StreamParams& P, const StreamJob& J, const float* ru, ProfSmem* prof, int tid,
+                            const WeightSmem& ws) {
   Lap<PROF> lap;
   lap.start(prof, tid == 0);
+  if (ws.w) LoadGateWeights<NT>(s, A, ws, tid);
 #pragma unroll 1
   for (uint32_t pos = 0; pos < J.n_preset; ++pos) {   // :187-194
     const uint32_t c = J.in[pos];
 #pragma unroll 1
     for (int j = 7; j >= 0; --j) {
-      SerialPredict<NT, PROF>(s, A, P, tid, lap);
+      SerialPredict<NT, PROF>(s, A, P, tid, lap, ws);
       if (tid == 0) s.new_bit = (c >> j) & 1;
       __syncthreads();
-      SerialLearn<NT, PROF>(s, A, P, tid, lap);
+      SerialLearn<NT, PROF>(s, A, P, tid, lap, ws);
       if (s.bit_stop) return;
     }
   }
-  SerialPredict<NT, PROF>(s, A, P, tid, lap);   // :198
+  SerialPredict<NT, PROF>(s, A, P, tid, lap, ws);   // :198
 #pragma unroll 1
   for (uint32_t i = 0; i < J.n_bytes; ++i) {
 #pragma unroll 1
@@ -2033,7 +2166,7 @@ GMX_DEV void SerialGenerate(StreamSmem& s, const Arena& A, const StreamParams& P
       }
       __syncthreads();
       if (s.bit_stop) return;
-      SerialPredict<NT, PROF>(s, A, P, tid, lap);
+      SerialPredict<NT, PROF>(s, A, P, tid, lap, ws);
     }
   }
 }
@@ -2057,15 +2190,23 @@ GMX_DEV void StageTables(StreamSmem& s, const StreamParams& P, int tid) {
 // ---- kernel entry: persistent CTAs, one stream at a time, ids from an atomic queue ---------------
 // WB warps of bit role (threads 0 .. 32 WB - 1), WL warps of LSTM role, one PPMd warp.
 // SERIAL: compress without the role pipeline (the same NT threads walk the phases together, as the lockstep modes do).
-template <int WB, int WL, int MODE, int MINB, bool PROF, bool SERIAL = false>
+// WS: the dense gate weights are resident in W_DENSE_BYTES + 16 bytes of dynamic shared memory (one CTA per SM).
+template <int WB, int WL, int MODE, int MINB, bool PROF, bool SERIAL = false, bool WS = false>
 __global__ void __launch_bounds__(32 * (WB + WL + 1), MINB) StreamKernel(StreamParams P) {
   constexpr int NB = 32 * WB, NL = 32 * WL, NT = NB + NL + 32;
   __shared__ StreamSmem s;
+#if defined(__CUDACC__)
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+#else
+  static unsigned char dyn_smem[WS ? W_DENSE_BYTES + 16 : 16] __attribute__((aligned(128)));
+#endif
+  WeightSmem ws{WS ? (float4*)dyn_smem : nullptr, WS ? (uint64_t*)(dyn_smem + W_DENSE_BYTES) : nullptr};
   __shared__ ProfHolder<PROF> prof_mem;
   __shared__ uint32_t next_stream;
   __shared__ StreamJob job;
   const int tid = (int)threadIdx.x;
   ProfSmem* prof = prof_mem.get();
+  if (WS && tid == 0) { MbarInit(ws.mbar, 1); s.wphase = 0; }
   StageTables<NT>(s, P, tid);
   Arena A{P.arenas + (uint64_t)blockIdx.x * P.arena_stride, &s.T.L};
   for (;;) {
@@ -2110,18 +2251,18 @@ __global__ void __launch_bounds__(32 * (WB + WL + 1), MINB) StreamKernel(StreamP
     const bool failed_early = s.error != 0;
     if (!failed_early) {
       if (MODE == MODE_COMPRESS && SERIAL) {
-        SerialCompress<NT, PROF>(s, A, P, job, sid, prof, tid);
+        SerialCompress<NT, PROF>(s, A, P, job, sid, prof, tid, ws);
       } else if (MODE == MODE_COMPRESS && WL == 0) {
-        if (tid < NB) BitLstmRoleCompress<NB, PROF>(s, A, P, job, sid, prof, tid);
+        if (tid < NB) BitLstmRoleCompress<NB, PROF>(s, A, P, job, sid, prof, tid, ws);
         else PpmdRole<PROF>(s, A, job, prof, tid - NB);
       } else if (MODE == MODE_COMPRESS) {
         if (tid < NB) BitRoleCompress<NB, PROF>(s, A, P, job, sid, prof, tid);
-        else if (tid < NB + NL) LstmRole<(NL > 0 ? NL : 32), PROF>(s, A, P, job, prof, tid - NB);
+        else if (tid < NB + NL) LstmRole<(NL > 0 ? NL : 32), PROF>(s, A, P, job, prof, tid - NB, ws);
         else PpmdRole<PROF>(s, A, job, prof, tid - NB - NL);
       } else if (MODE == MODE_DECOMPRESS) {
-        SerialDecompress<NT, PROF>(s, A, P, job, prof, tid);
+        SerialDecompress<NT, PROF>(s, A, P, job, prof, tid, ws);
       } else {
-        SerialGenerate<NT, PROF>(s, A, P, job, P.rand_u + (size_t)sid * P.rand_stride, prof, tid);
+        SerialGenerate<NT, PROF>(s, A, P, job, P.rand_u + (size_t)sid * P.rand_stride, prof, tid, ws);
       }
     }
     __syncthreads();
@@ -2181,11 +2322,11 @@ __global__ void __launch_bounds__(32 * (WB + WL + 1)) StepKernel(StepParams Q) {
     if (tid == 0 && Q.analysis >= 0) s.analysis = Q.analysis;
     __syncthreads();
     if (Q.op == STEP_PREDICT) {
-      SerialPredict<NT, false>(s, A, Q.P, tid, lap);
+      SerialPredict<NT, false>(s, A, Q.P, tid, lap, WeightSmem{nullptr, nullptr});
       __syncthreads();
       if (tid == 0) *Q.prob_out = s.prob;
     } else {
-      SerialLearn<NT, false>(s, A, Q.P, tid, lap);
+      SerialLearn<NT, false>(s, A, Q.P, tid, lap, WeightSmem{nullptr, nullptr});
     }
   }
   __syncthreads();

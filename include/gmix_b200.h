@@ -64,7 +64,7 @@ const char* gmx_last_error(const gmx_ctx* ctx);
 int gmx_set_kernel_config(gmx_ctx* ctx, int cfg);
 int gmx_get_kernel_config(const gmx_ctx* ctx);
 int gmx_kernel_config_count(void);
-int gmx_kernel_config_info(int cfg, int* bit_warps, int* lstm_warps, int* ctas_per_sm, int* serial);
+int gmx_kernel_config_info(int cfg, int* bit_warps, int* lstm_warps, int* ctas_per_sm, int* serial, int* resident_weights);
 
 /* Launch kernels on an existing CUDA stream (cudaStream_t passed as void*), e.g. torch's current
  * stream, so the caller can bracket calls with its own CUDA events. NULL = the ctx's own stream. */
