@@ -62,7 +62,8 @@ struct gmx_ctx {
   uint32_t prof_streams = 0;
   uint32_t usage_streams = 0;
   uint32_t last_grid = 0;
-  int kcfg = 0;            // kernel configuration (kernels.h) of the batch calls
+  int kcfg = 0;            // kernel configuration (kernels.h) the arenas are currently sized for
+  int kcfg_user = -1;      // -1: chosen per call from the batch shape (AutoConfig), else pinned by gmx_set_kernel_config
   uint64_t launches = 0;
   double last_ms = 0;
 };
@@ -237,6 +238,13 @@ int RunDevice(gmx_ctx* c, int mode, const uint8_t* d_in, const uint64_t* d_in_of
   if (n == 0) return 0;
   if (!d_in || !d_in_off || !d_out || !d_out_len || !d_status || (mode != gmx::MODE_GENERATE && !d_out_off)) return Fail(c, GMX_E_ARG, "null pointer argument");
   GMX_CUDA(c, cudaSetDevice(c->device));
+  {
+    // Few streams (at most one per SM): the latency configuration (one CTA per SM, pipelined roles, gate weights resident in
+    // shared memory) runs each stream ~1.8x faster; a full wave of streams is served best by the phase-serial configuration
+    // at 8 CTAs per SM (measurements: profiles/r02_*). A pinned configuration (gmx_set_kernel_config) is left alone.
+    const int want = c->kcfg_user >= 0 ? c->kcfg_user : (n <= (uint32_t)c->sm_count ? gmx::kLatencyConfig : gmx::kThroughputConfig);
+    if (want != c->kcfg) { c->kcfg = want; FreeArenas(c); }
+  }
   if (o.model) {
     if (o.model->ctx != c) return Fail(c, GMX_E_ARG, "model belongs to another context");
     if (max_len > o.model->max_new_bytes) return Fail(c, GMX_E_ARG, "stream of %llu bytes exceeds the max_new_bytes (%llu) the model was loaded with",
@@ -401,7 +409,7 @@ int gmx_create(int device, gmx_ctx** out) {
     return GMX_E_CUDA;
   }
   c->stream = c->own_stream;
-  if (const char* e = getenv("GMIX_B200_KERNEL_CONFIG")) { const int k = atoi(e); if (k >= 0 && k < gmx::kNumKernelConfigs) c->kcfg = k; }
+  if (const char* e = getenv("GMIX_B200_KERNEL_CONFIG")) { const int k = atoi(e); if (k >= 0 && k < gmx::kNumKernelConfigs) { c->kcfg = k; c->kcfg_user = k; } }
   std::vector<float> linit, adam;
   gmx::FillLstmInit(linit);
   gmx::FillAdamTable(adam);
@@ -438,8 +446,9 @@ const char* gmx_last_error(const gmx_ctx* c) { return c ? c->error.c_str() : g_g
 
 int gmx_set_kernel_config(gmx_ctx* c, int cfg) {
   if (!c) return GMX_E_ARG;
-  if (cfg < 0 || cfg >= gmx::kNumKernelConfigs) return Fail(c, GMX_E_ARG, "kernel configuration %d out of range (0 .. %d)", cfg, gmx::kNumKernelConfigs - 1);
-  if (cfg != c->kcfg) { c->kcfg = cfg; FreeArenas(c); }   // residency (arena count) depends on the configuration
+  if (cfg < -1 || cfg >= gmx::kNumKernelConfigs) return Fail(c, GMX_E_ARG, "kernel configuration %d out of range (-1 = automatic, 0 .. %d)", cfg, gmx::kNumKernelConfigs - 1);
+  c->kcfg_user = cfg;
+  if (cfg >= 0 && cfg != c->kcfg) { c->kcfg = cfg; FreeArenas(c); }   // residency (arena count) depends on the configuration
   return 0;
 }
 int gmx_get_kernel_config(const gmx_ctx* c) { return c ? c->kcfg : -1; }

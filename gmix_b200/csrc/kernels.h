@@ -25,6 +25,7 @@ namespace gmx {
   X(8, 4, 8, 1, 0, 1)           \
   X(9, 4, 4, 1, 0, 1)
 constexpr int kNumKernelConfigs = 10;
+constexpr int kThroughputConfig = 0, kLatencyConfig = 9;   // what the host picks for a full wave of streams / for at most one stream per SM
 constexpr int kStepWB = 2, kStepWL = 1;   // role split of the single-stream stepping kernel
 struct KernelConfigInfo { int wb, wl, minb, threads, serial, ws; };
 KernelConfigInfo KernelConfig(int cfg);

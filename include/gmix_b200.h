@@ -59,8 +59,10 @@ void gmx_destroy(gmx_ctx* ctx);
 const char* gmx_last_error(const gmx_ctx* ctx);
 
 /* Kernel configuration = the role split of the stream CTA (warps of bit role / LSTM role + one PPMd warp, resident CTAs
- * per SM). Every configuration produces the same bytes; they differ in throughput per workload shape. Default 0 (or the
- * environment variable GMIX_B200_KERNEL_CONFIG). Changing it frees the arenas (the next call re-sizes them). */
+ * per SM). Every configuration produces the same bytes; they differ in throughput per workload shape. Default -1: chosen
+ * per call (at most one stream per SM -> the latency configuration: pipelined roles, LSTM gate weights resident in shared
+ * memory, one CTA per SM; more streams -> the throughput configuration: 8 CTAs per SM). A value >= 0 (or the environment
+ * variable GMIX_B200_KERNEL_CONFIG) pins one. Changing it frees the arenas (the next call re-sizes them). */
 int gmx_set_kernel_config(gmx_ctx* ctx, int cfg);
 int gmx_get_kernel_config(const gmx_ctx* ctx);
 int gmx_kernel_config_count(void);
