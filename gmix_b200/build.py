@@ -9,7 +9,8 @@ LIB = os.path.join(ROOT, "lib", "libgmix_b200.so")
 SOURCES = ["host.cu", "kernel_compress.cu", "kernel_decompress.cu", "kernel_compress_prof.cu", "kernel_step.cu", "kernel_generate.cu"]
 DEPS = ["host.cu", "kernel_compress.cu", "kernel_decompress.cu", "kernel_compress_prof.cu", "kernel_step.cu", "kernel_generate.cu", "checkpoint.h", "kernels.h", "stream_kernel.cuh", "ppmd.cuh", "dmath.cuh", "spec.cuh", "layout.h", "nonstationary.inc",
         os.path.join("..", "..", "include", "gmix_b200.h"), os.path.join("..", "host", "runner.cpp"), os.path.join("..", "host", "predictor.h"),
-        os.path.join("..", "host", "coder.h"), os.path.join("..", "..", "scripts", "ncu_case.cpp")]
+        os.path.join("..", "host", "coder.h"), os.path.join("..", "host", "multi_gpu.h"), os.path.join("..", "host", "shard.h"),
+        os.path.join("..", "..", "scripts", "ncu_case.cpp")]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
@@ -90,6 +91,8 @@ def build_host_tools():
     cxx = os.environ.get("CXX", "g++")
     for src, exe in ((os.path.join(ROOT, "host", "runner.cpp"), "gmixb200"), (os.path.join(ROOT, "..", "scripts", "ncu_case.cpp"), "ncu_case")):
         cmd = [cxx, "-std=c++17", "-O2", "-ffp-contract=off", "-o", os.path.join(libdir, exe), src, "-L" + libdir, "-lgmix_b200", "-Wl,-rpath,$ORIGIN"]
+        if exe == "gmixb200":   # the multi-GPU host (host/multi_gpu.h) talks to the CUDA runtime and NCCL directly
+            cmd += ["-I/usr/local/cuda/include", "-L/usr/local/cuda/lib64", "-lcudart", "-lnccl", "-pthread", "-Wl,-rpath,/usr/local/cuda/lib64"]
         print("[gmix_b200] " + " ".join(cmd), file=sys.stderr)
         subprocess.run(cmd, check=True)
 

@@ -7,9 +7,11 @@
 //   gmixb200 -t [ckpt] train test     Predict/Perceive/Learn over `train`, write data/trained_checkpoint.{short,long}
 //                                     (the reference's format) and report the cross entropy of `test` under the trained
 //                                     model (runner-utils.cpp:223-322 without the periodic test passes)
-//   gmixb200 -C bytes input output  split input into chunks of `bytes`, compress them as independent
-//                                   streams in one GPU batch (container: "GMXB", u32 count, u64 sizes[], streams)
-//   gmixb200 -D input output        inverse of -C
+//   gmixb200 -C bytes input output  split input into chunks of `bytes` and compress them as independent streams on ALL
+//                                   visible GPUs (GMIXB200_GPUS=k limits them): one context + host thread per GPU, contiguous
+//                                   byte-balanced stream ranges, one ncclAllGather of {size, FNV-1a 64} per stream
+//                                   (host/multi_gpu.h). Container: "GMXB", u32 count, u64 sizes[], streams
+//   gmixb200 -D input output        inverse of -C (same sharding)
 //   gmixb200 -p input output        compress one stream through the Predictor facade + host coder
 //                                   (Predict/Perceive/Learn per bit; slow, for checking the drop-in interface)
 // `ckpt` is a checkpoint prefix: <ckpt>.short + <ckpt>.long, written by the reference or by this program.
@@ -26,6 +28,7 @@
 
 #include "../../include/gmix_b200.h"
 #include "coder.h"
+#include "multi_gpu.h"
 #include "predictor.h"
 
 namespace {
@@ -229,12 +232,36 @@ int main(int argc, char* argv[]) {
         src = &payload;
       }
       Batch b;
+      const uint32_t n = (uint32_t)in_off.size() - 1;
+      if (mode == 'C' || mode == 'D') {   // all visible GPUs
+        int ng = 0;
+        if (cudaGetDeviceCount(&ng) != cudaSuccess || ng < 1) { printf("no CUDA device\n"); return -1; }
+        if (const char* e = getenv("GMIXB200_GPUS")) { const int k = atoi(e); if (k >= 1 && k < ng) ng = k; }
+        std::vector<int> devs;
+        for (int d = 0; d < ng; ++d) devs.push_back(d);
+        gmixb::MultiGpu mg(devs);
+        if (!mg.ok()) { printf("%s\n", mg.error().c_str()); return -1; }
+        b.out_off.assign(n + 1, 0);
+        for (uint32_t i = 0; i < n; ++i) {
+          uint64_t cap;
+          if (mode == 'C') cap = gmx_compress_bound(in_off[i + 1] - in_off[i]);
+          else { cap = 0; for (uint64_t k = 0; k < 5 && in_off[i] + k < in_off[i + 1]; ++k) cap = (cap << 8) + (*src)[in_off[i] + k]; cap += 8; }
+          b.out_off[i + 1] = b.out_off[i] + cap;
+        }
+        b.out.assign(b.out_off[n] + 1, 0);
+        std::vector<gmixb::StreamRecord> table;
+        static const uint8_t kNone = 0;
+        if (!mg.Run(mode == 'C', src->empty() ? &kNone : src->data(), in_off, b.out.data(), b.out_off, &b.out_len, &table)) { printf("%s\n", mg.error().c_str()); return -1; }
+        printf("%u streams on %d GPU(s):", n, mg.world());
+        for (int r = 0; r < mg.world(); ++r) printf(" [%u, %u)", mg.ranges()[r].first, mg.ranges()[r].second);
+        printf("; {size, checksum} of every stream gathered on every GPU (ncclAllGather) and verified\n");
+      } else {
       gmx_model* model = nullptr;
       if (with_ckpt && !(model = LoadModel(gpu.ctx(), checkpoint_path, mode == 'c' ? in.size() : HeaderLength(in)))) return -1;
       const bool ok = RunBatch(gpu.ctx(), mode == 'c' || mode == 'C', *src, in_off, &b, model);
       if (model) gmx_model_free(model);
       if (!ok) return -1;
-      const uint32_t n = (uint32_t)in_off.size() - 1;
+      }
       if (mode == 'C') {
         result.assign({'G', 'M', 'X', 'B'});
         result.resize(8 + 8ull * n);

@@ -110,3 +110,32 @@ def test_runner_checkpoint_generate_and_train_cli(tmp_path):
     assert (d / "data" / "trained_checkpoint.long").read_bytes() == long_ref
     diff = ckpt_layout.differing_sections((d / "data" / "trained_checkpoint.short").read_bytes(), short_ref)
     assert set(diff) <= ckpt_layout.SCRATCH, diff
+
+
+def test_runner_chunked_mode_shards_over_all_visible_gpus(tmp_path, gpu_ctx):
+    """`gmixb200 -C` = the C++ multi-GPU host (host/multi_gpu.h): one context + host thread per visible GPU, byte-balanced
+    contiguous stream ranges, one ncclAllGather of {size, FNV-1a 64} per stream (verified by the runner itself). The
+    container must hold exactly the streams the single-GPU batch call writes, whatever the number of GPUs."""
+    import struct
+    import torch
+    from gmix_b200 import synth
+    corpus = synth.enwik_shaped_corpus(9 * 3000 + 1234)           # 10 streams, the last one short
+    src = tmp_path / "corpus.in"
+    src.write_bytes(corpus)
+    cont, back = str(tmp_path / "c.gmxb"), str(tmp_path / "c.back")
+    r = subprocess.run([RUNNER, "-C", "3000", str(src), cont], check=True, capture_output=True, text=True)
+    ngpu = torch.cuda.device_count()
+    assert f"10 streams on {ngpu} GPU(s)" in r.stdout and "ncclAllGather" in r.stdout, r.stdout
+    chunks = [corpus[i:i + 3000] for i in range(0, len(corpus), 3000)]
+    want = gpu_ctx.compress_batch(chunks)
+    blob = open(cont, "rb").read()
+    assert blob[:4] == b"GMXB" and struct.unpack("<I", blob[4:8])[0] == len(chunks)
+    sizes = struct.unpack(f"<{len(chunks)}Q", blob[8:8 + 8 * len(chunks)])
+    assert list(sizes) == [len(w) for w in want]
+    assert blob[8 + 8 * len(chunks):] == b"".join(want)
+    subprocess.run([RUNNER, "-D", cont, back], check=True)
+    assert open(back, "rb").read() == corpus
+    if ngpu > 1:                                                    # and the same bytes when limited to one GPU
+        env = dict(os.environ, GMIXB200_GPUS="1")
+        subprocess.run([RUNNER, "-C", "3000", str(src), cont + "1"], check=True, env=env)
+        assert open(cont + "1", "rb").read() == blob

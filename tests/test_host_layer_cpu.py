@@ -73,3 +73,38 @@ int main() {
     subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-o", str(exe), str(harness)], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout
+
+
+def test_cxx_partitioner_matches_the_python_one(tmp_path):
+    """gmix_b200/host/shard.h (what `gmixb200 -C` shards its streams over the GPUs with) against gmix_b200/shard.py (what the
+    torch.distributed harness uses), on random length lists incl. empty streams, all-empty lists and more ranks than streams."""
+    import random
+    from gmix_b200 import shard
+    harness = tmp_path / "shard_check.cpp"
+    harness.write_text(r'''
+#include <stdio.h>
+#include <stdlib.h>
+#include "%s/gmix_b200/host/shard.h"
+int main(int argc, char** argv) {   // world n len0 len1 ... -> "lo hi" per rank
+  const int world = atoi(argv[1]);
+  std::vector<uint64_t> len;
+  for (int i = 3; i < argc; ++i) len.push_back(strtoull(argv[i], nullptr, 10));
+  for (auto& r : gmixb::ShardRanges(len, world)) printf("%%u %%u\n", r.first, r.second);
+  const unsigned char abc[3] = {'a', 'b', 'c'};
+  printf("%%llu\n", (unsigned long long)gmixb::Fnv1a64(abc, 3));
+  return 0;
+}
+''' % ROOT)
+    exe = tmp_path / "shard_check"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-o", str(exe), str(harness)], check=True)
+    rng = random.Random(5)
+    cases = [([], 4), ([0, 0, 0], 2), ([5], 8), ([1000000] * 100, 8), ([1000000] * 100, 3)]
+    for _ in range(40):
+        n = rng.randint(1, 60)
+        cases.append(([rng.choice([0, 1, 7, 4096, 65536, rng.randint(0, 10 ** 6)]) for _ in range(n)], rng.randint(1, 9)))
+    for lengths, world in cases:
+        r = subprocess.run([str(exe), str(world), str(len(lengths))] + [str(x) for x in lengths], capture_output=True, text=True, check=True)
+        lines = r.stdout.split("\n")
+        got = [tuple(int(x) for x in l.split()) for l in lines[:world]]
+        assert got == [tuple(x) for x in shard.shard_ranges(lengths, world)], (lengths, world)
+        assert int(lines[world]) == shard.fnv1a64(b"abc")
