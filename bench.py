@@ -479,7 +479,7 @@ def run_ours(args):
         model = gmix_b200.Model(ctx, ck_short, ck_long, max_new_bytes=64 + G)
         prompts = [corpus[T + 4096 * k:T + 4096 * k + 64] for k in range(npr)]
         prompts[1] = prompts[0]                                          # same prompt, same draws -> must give the same bytes
-        ctx.generate_batch(model, prompts[:8], 16)                       # warm-up (allocates the model-sized arenas)
+        ctx.generate_batch(model, prompts, 1)                            # warm-up with the same batch shape (allocates the model-sized arenas)
         barrier()
         t0 = time.perf_counter()
         out = ctx.generate_batch(model, prompts, G, 1.0)
