@@ -92,7 +92,15 @@ def build_host_tools():
     for src, exe in ((os.path.join(ROOT, "host", "runner.cpp"), "gmixb200"), (os.path.join(ROOT, "..", "scripts", "ncu_case.cpp"), "ncu_case")):
         cmd = [cxx, "-std=c++17", "-O2", "-ffp-contract=off", "-o", os.path.join(libdir, exe), src, "-L" + libdir, "-lgmix_b200", "-Wl,-rpath,$ORIGIN"]
         if exe == "gmixb200":   # the multi-GPU host (host/multi_gpu.h) talks to the CUDA runtime and NCCL directly
-            cmd += ["-I/usr/local/cuda/include", "-L/usr/local/cuda/lib64", "-lcudart", "-lnccl", "-pthread", "-Wl,-rpath,/usr/local/cuda/lib64"]
+            # NCCL: the library PyTorch ships (the one bench.py's process group runs on) when present, else the system's
+            import importlib.util
+            spec = importlib.util.find_spec("nvidia.nccl")
+            nccl_dir = os.path.join(list(spec.submodule_search_locations)[0], "lib") if spec and spec.submodule_search_locations else None
+            cmd += ["-I/usr/local/cuda/include", "-L/usr/local/cuda/lib64", "-lcudart", "-pthread", "-Wl,-rpath,/usr/local/cuda/lib64"]
+            if nccl_dir and os.path.exists(os.path.join(nccl_dir, "libnccl.so.2")):
+                cmd += [os.path.join(nccl_dir, "libnccl.so.2"), "-Wl,-rpath," + nccl_dir]
+            else:
+                cmd += ["-lnccl"]
         print("[gmix_b200] " + " ".join(cmd), file=sys.stderr)
         subprocess.run(cmd, check=True)
 

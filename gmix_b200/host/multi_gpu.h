@@ -10,8 +10,12 @@
 #include <cuda_runtime_api.h>
 #include <nccl.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -23,12 +27,29 @@ namespace gmixb {
 
 struct StreamRecord { uint64_t len, fnv1a64; };
 
+// The host threads of the GPUs meet here. cudaMalloc / cudaFree synchronise devices implicitly and can deadlock against a
+// collective kernel that is spinning for its peers, so every allocation happens before the first rank launches the
+// gather and every release after the last rank has finished it.
+class HostBarrier {
+ public:
+  explicit HostBarrier(int n) : n_(n) {}
+  void Wait() {
+    std::unique_lock<std::mutex> lk(m_);
+    const unsigned gen = gen_;
+    if (++count_ == n_) { count_ = 0; ++gen_; cv_.notify_all(); }
+    else cv_.wait(lk, [&] { return gen_ != gen; });
+  }
+ private:
+  std::mutex m_; std::condition_variable cv_; int n_, count_ = 0; unsigned gen_ = 0;
+};
+
 class MultiGpu {
  public:
   // devices: CUDA device ordinals, one rank each. Throws nothing: ok() tells, error() explains.
-  explicit MultiGpu(const std::vector<int>& devices) : dev_(devices), ctx_(devices.size(), nullptr), comm_(devices.size(), nullptr) {
+  explicit MultiGpu(const std::vector<int>& devices) : dev_(devices), ctx_(devices.size(), nullptr), comm_(devices.size(), nullptr), buf_(devices.size()) {
     for (size_t r = 0; r < dev_.size(); ++r)
       if (gmx_create(dev_[r], &ctx_[r]) != 0) { err_ = std::string("gmx_create: ") + gmx_global_error(); return; }
+    if (getenv("GMIXB200_VERBOSE")) fprintf(stderr, "[gmixb200] %zu contexts created, ncclCommInitAll ...\n", dev_.size());
     const ncclResult_t rc = ncclCommInitAll(comm_.data(), (int)dev_.size(), dev_.data());
     if (rc != ncclSuccess) { err_ = std::string("ncclCommInitAll: ") + ncclGetErrorString(rc); return; }
     ok_ = true;
@@ -59,8 +80,10 @@ class MultiGpu {
     std::vector<std::string> errs((size_t)world());
     std::vector<std::vector<uint64_t>> gathered((size_t)world());
     std::vector<std::thread> th;
+    HostBarrier bar(world());
+    std::atomic<int> failed{0};
     for (int r = 0; r < world(); ++r)
-      th.emplace_back([&, r] { errs[r] = Rank(r, compress, in, in_off, out, out_off, out_len->data(), width, &gathered[r]); });
+      th.emplace_back([&, r] { errs[r] = Rank(r, compress, in, in_off, out, out_off, out_len->data(), width, &gathered[r], &bar, &failed); });
     for (auto& t : th) t.join();
     for (int r = 0; r < world(); ++r) if (!errs[r].empty()) { err_ = "GPU " + std::to_string(dev_[r]) + ": " + errs[r]; return false; }
     // every GPU holds the whole table: [rank][2][width]
@@ -82,16 +105,40 @@ class MultiGpu {
 #define GMIXB_NCCL(expr) do { ncclResult_t e_ = (expr); if (e_ != ncclSuccess) return std::string(#expr) + ": " + ncclGetErrorString(e_); } while (0)
   // Everything GPU r does, on its own host thread. Returns an error text or "".
   std::string Rank(int r, bool compress, const uint8_t* in, const std::vector<uint64_t>& in_off, uint8_t* out, const std::vector<uint64_t>& out_off,
-                   uint64_t* out_len, uint32_t width, std::vector<uint64_t>* gathered) {
-    const uint32_t lo = ranges_[r].first, hi = ranges_[r].second, m = hi - lo;
-    GMIXB_CUDA(cudaSetDevice(dev_[r]));
-    cudaStream_t st;
-    GMIXB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    gmx_set_cuda_stream(ctx_[r], st);
-    const uint64_t in_bytes = in_off[hi] - in_off[lo], out_bytes = out_off[hi] - out_off[lo];
+                   uint64_t* out_len, uint32_t width, std::vector<uint64_t>* gathered, HostBarrier* bar, std::atomic<int>* failed) {
+    // compute (allocates), then - all ranks together - the gather; a rank that fails still walks through the barriers and
+    // nobody enters the collective without it
+    const bool verbose = getenv("GMIXB200_VERBOSE") != nullptr;
+    std::string err = Compute(r, compress, in, in_off, out_off, width);
+    if (verbose) fprintf(stderr, "[gmixb200] GPU %d: streams [%u, %u) done%s%s\n", dev_[r], ranges_[r].first, ranges_[r].second, err.empty() ? "" : ": ", err.c_str());
+    if (!err.empty()) failed->store(1);
+    bar->Wait();
+    if (!failed->load()) err = Gather(r, out, out_off, out_len, width, gathered);
+    else if (err.empty()) err = "another GPU failed";
+    if (verbose) fprintf(stderr, "[gmixb200] GPU %d: gather done%s%s\n", dev_[r], err.empty() ? "" : ": ", err.c_str());
+    bar->Wait();
+    Release(r);
+    return err;
+  }
+
+  struct RankBuffers {
+    cudaStream_t st = nullptr;
     uint8_t *d_in = nullptr, *d_out = nullptr;
     uint64_t *d_io = nullptr, *d_oo = nullptr, *d_send = nullptr, *d_recv = nullptr;
     uint32_t* d_status = nullptr;
+  };
+
+  std::string Compute(int r, bool compress, const uint8_t* in, const std::vector<uint64_t>& in_off, const std::vector<uint64_t>& out_off, uint32_t width) {
+    RankBuffers& B = buf_[r];
+    cudaStream_t& st = B.st;
+    uint8_t*& d_in = B.d_in; uint8_t*& d_out = B.d_out;
+    uint64_t*& d_io = B.d_io; uint64_t*& d_oo = B.d_oo; uint64_t*& d_send = B.d_send; uint64_t*& d_recv = B.d_recv;
+    uint32_t*& d_status = B.d_status;
+    const uint32_t lo = ranges_[r].first, hi = ranges_[r].second, m = hi - lo;
+    GMIXB_CUDA(cudaSetDevice(dev_[r]));
+    GMIXB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    gmx_set_cuda_stream(ctx_[r], st);
+    const uint64_t in_bytes = in_off[hi] - in_off[lo], out_bytes = out_off[hi] - out_off[lo];
     GMIXB_CUDA(cudaMalloc(&d_in, in_bytes + 16));
     GMIXB_CUDA(cudaMalloc(&d_out, out_bytes + 16));
     GMIXB_CUDA(cudaMalloc(&d_io, (m + 1) * 8));
@@ -116,6 +163,17 @@ class MultiGpu {
       if (rc != 0) return gmx_last_error(ctx_[r]);
       if (gmx_checksum_device(ctx_[r], d_out, d_oo, d_send, m, d_send + width) != 0) return gmx_last_error(ctx_[r]);
     }
+    GMIXB_CUDA(cudaStreamSynchronize(st));
+    return "";
+  }
+
+  std::string Gather(int r, uint8_t* out, const std::vector<uint64_t>& out_off, uint64_t* out_len, uint32_t width, std::vector<uint64_t>* gathered) {
+    RankBuffers& B = buf_[r];
+    cudaStream_t st = B.st;
+    uint8_t* d_out = B.d_out; uint64_t* d_send = B.d_send; uint64_t* d_recv = B.d_recv; uint32_t* d_status = B.d_status;
+    const uint32_t lo = ranges_[r].first, hi = ranges_[r].second, m = hi - lo;
+    const uint64_t out_bytes = out_off[hi] - out_off[lo];
+    GMIXB_CUDA(cudaSetDevice(dev_[r]));
     // the one collective: sizes + checksums of every stream to every GPU
     GMIXB_NCCL(ncclAllGather(d_send, d_recv, 2ull * width, ncclUint64, comm_[r], st));
     gathered->resize(2ull * width * world());
@@ -127,11 +185,17 @@ class MultiGpu {
       GMIXB_CUDA(cudaMemcpyAsync(status.data(), d_status, m * 4ull, cudaMemcpyDeviceToHost, st));
     }
     GMIXB_CUDA(cudaStreamSynchronize(st));
-    gmx_set_cuda_stream(ctx_[r], nullptr);
-    for (void* p : {(void*)d_in, (void*)d_out, (void*)d_io, (void*)d_oo, (void*)d_send, (void*)d_recv, (void*)d_status}) cudaFree(p);
-    cudaStreamDestroy(st);
     for (uint32_t i = 0; i < m; ++i) if (status[i]) return "stream " + std::to_string(lo + i) + " failed with status " + std::to_string(status[i]);
     return "";
+  }
+
+  void Release(int r) {
+    RankBuffers& B = buf_[r];
+    cudaSetDevice(dev_[r]);
+    gmx_set_cuda_stream(ctx_[r], nullptr);
+    for (void* p : {(void*)B.d_in, (void*)B.d_out, (void*)B.d_io, (void*)B.d_oo, (void*)B.d_send, (void*)B.d_recv, (void*)B.d_status}) if (p) cudaFree(p);
+    if (B.st) cudaStreamDestroy(B.st);
+    B = RankBuffers();
   }
 #undef GMIXB_CUDA
 #undef GMIXB_NCCL
@@ -139,6 +203,7 @@ class MultiGpu {
   std::vector<int> dev_;
   std::vector<gmx_ctx*> ctx_;
   std::vector<ncclComm_t> comm_;
+  std::vector<RankBuffers> buf_;
   std::vector<std::pair<uint32_t, uint32_t>> ranges_;
   bool ok_ = false;
   std::string err_;

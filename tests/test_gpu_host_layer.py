@@ -123,7 +123,8 @@ def test_runner_chunked_mode_shards_over_all_visible_gpus(tmp_path, gpu_ctx):
     src = tmp_path / "corpus.in"
     src.write_bytes(corpus)
     cont, back = str(tmp_path / "c.gmxb"), str(tmp_path / "c.back")
-    r = subprocess.run([RUNNER, "-C", "3000", str(src), cont], check=True, capture_output=True, text=True)
+    r = subprocess.run([RUNNER, "-C", "3000", str(src), cont], capture_output=True, text=True, timeout=240, env=dict(os.environ, GMIXB200_VERBOSE="1"))
+    assert r.returncode == 0, r.stdout + r.stderr
     ngpu = torch.cuda.device_count()
     assert f"10 streams on {ngpu} GPU(s)" in r.stdout and "ncclAllGather" in r.stdout, r.stdout
     chunks = [corpus[i:i + 3000] for i in range(0, len(corpus), 3000)]
@@ -133,7 +134,7 @@ def test_runner_chunked_mode_shards_over_all_visible_gpus(tmp_path, gpu_ctx):
     sizes = struct.unpack(f"<{len(chunks)}Q", blob[8:8 + 8 * len(chunks)])
     assert list(sizes) == [len(w) for w in want]
     assert blob[8 + 8 * len(chunks):] == b"".join(want)
-    subprocess.run([RUNNER, "-D", cont, back], check=True)
+    subprocess.run([RUNNER, "-D", cont, back], check=True, timeout=240)
     assert open(back, "rb").read() == corpus
     if ngpu > 1:                                                    # and the same bytes when limited to one GPU
         env = dict(os.environ, GMIXB200_GPUS="1")
