@@ -50,7 +50,9 @@ inline cudaError_t PrepareStreamKernel() {
 }
 template <int WB, int WL, int MODE, int MINB, bool PROF, bool SERIAL, bool WS>
 inline cudaError_t LaunchStreamKernel(const StreamParams& P, unsigned grid, cudaStream_t st) {
-  static const cudaError_t prep = PrepareStreamKernel<WB, WL, MODE, MINB, PROF, SERIAL, WS>();
+  // function attributes are per device (the multi-GPU host launches the same kernel from one thread per GPU): set them
+  // for the calling thread's device on every launch, it costs microseconds against kernels that run for seconds
+  const cudaError_t prep = PrepareStreamKernel<WB, WL, MODE, MINB, PROF, SERIAL, WS>();
   if (prep != cudaSuccess) return prep;
   StreamKernel<WB, WL, MODE, MINB, PROF, SERIAL, WS><<<grid, 32 * (WB + WL + 1), DynSmemBytes<WS>(), st>>>(P);
   return cudaGetLastError();
