@@ -48,6 +48,13 @@ def load_library():
     lib.gmx_compress_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, u64p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gmx_resident_streams.argtypes = [C.c_void_p]
     lib.gmx_resident_streams.restype = C.c_uint32
+    lib.gmx_pred_copy.argtypes = [C.c_void_p, C.c_void_p]
+    lib.gmx_compress_part.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p,
+                                      C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
+                                      C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    lib.gmx_decompress_part.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p,
+                                        C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
+                                        C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     lib.gmx_set_kernel_config.argtypes = [C.c_void_p, C.c_int]
     lib.gmx_get_kernel_config.argtypes = [C.c_void_p]
     lib.gmx_kernel_config_info.argtypes = [C.c_int] + [C.POINTER(C.c_int)] * 5
@@ -182,6 +189,10 @@ class Predictor:
     def learn(self):
         self.ctx._check(self.ctx.lib.gmx_pred_learn(self.h), "gmx_pred_learn")
 
+    def copy_from(self, other):
+        """Predictor::Copy (predictor.cpp:42-48)."""
+        self.ctx._check(self.ctx.lib.gmx_pred_copy(self.h, other.h), "gmx_pred_copy")
+
     def write_checkpoint(self):
         """Predictor::WriteCheckpoint: returns (.short bytes, .long bytes)."""
         rc, sh, lo = _blobs(self.ctx.lib.gmx_pred_write_checkpoint, self.h)
@@ -292,6 +303,43 @@ class Context:
         rc, sh, lo = _blobs(self.lib.gmx_train_checkpoint, self.h, model.h if model is not None else None, src.ctypes.data, len(data))
         self._check(rc, "gmx_train_checkpoint")
         return sh, lo
+
+    def compress_part(self, data, model=None, coder=None, header_total=None, last=False, analysis=0, want_checkpoint=True):
+        """One part of a stream coded in parts (Encoder::Write/ReadCheckpoint + Predictor::Write/ReadCheckpoint). coder = (x1, x2)
+        the part starts with (None = fresh); header_total = length the 5-byte header announces (None = no header).
+        Returns (bytes appended to the stream, (x1, x2) after the part, (.short, .long) checkpoint or None)."""
+        n = len(data)
+        src = np.frombuffer(bytes(data), dtype=np.uint8).copy() if n else np.zeros(1, np.uint8)
+        cap = compress_bound(n)
+        out = np.zeros(cap, dtype=np.uint8)
+        out_len = C.c_uint64(0)
+        cin = np.array(list(coder) + [0], dtype=np.uint32) if coder is not None else None
+        cout = np.zeros(3, dtype=np.uint32)
+        sp, sl, lp, ll = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_uint64()
+        rc = self.lib.gmx_compress_part(self.h, model.h if model is not None else None, cin.ctypes.data if cin is not None else None,
+                                        int(header_total is not None), int(header_total or 0), int(last), int(analysis), src.ctypes.data, n,
+                                        out.ctypes.data, cap, C.byref(out_len), cout.ctypes.data,
+                                        C.byref(sp) if want_checkpoint else None, C.byref(sl), C.byref(lp), C.byref(ll))
+        self._check(rc, "gmx_compress_part")
+        ck = (C.string_at(sp.value, sl.value), C.string_at(lp.value, ll.value)) if want_checkpoint else None
+        return out[:out_len.value].tobytes(), (int(cout[0]), int(cout[1])), ck
+
+    def decompress_part(self, coded, out_bytes, model=None, coder=None, analysis=0, want_checkpoint=True):
+        """One part of a stream decoded in parts. coder = (x1, x2, x) (None = first part: header + 4 bytes are read from `coded`).
+        Returns (bytes, coded bytes consumed, (x1, x2, x) after the part, checkpoint or None)."""
+        n = len(coded)
+        src = np.frombuffer(bytes(coded), dtype=np.uint8).copy() if n else np.zeros(1, np.uint8)
+        out = np.zeros(out_bytes + 16, dtype=np.uint8)
+        used = C.c_uint64(0)
+        cin = np.array(list(coder), dtype=np.uint32) if coder is not None else None
+        cout = np.zeros(3, dtype=np.uint32)
+        sp, sl, lp, ll = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_uint64()
+        rc = self.lib.gmx_decompress_part(self.h, model.h if model is not None else None, cin.ctypes.data if cin is not None else None, int(analysis),
+                                          src.ctypes.data, n, out_bytes, out.ctypes.data, C.byref(used), cout.ctypes.data,
+                                          C.byref(sp) if want_checkpoint else None, C.byref(sl), C.byref(lp), C.byref(ll))
+        self._check(rc, "gmx_decompress_part")
+        ck = (C.string_at(sp.value, sl.value), C.string_at(lp.value, ll.value)) if want_checkpoint else None
+        return out[:out_bytes].tobytes(), int(used.value), tuple(int(x) for x in cout), ck
 
     def compress(self, data):
         return self.compress_batch([data])[0]

@@ -57,7 +57,7 @@ struct gmx_ctx {
   uint32_t* d_queue = nullptr;
   std::vector<float> h_decay;
   // staging buffers of the host-pointer entry points
-  DevBuf b_in, b_out, b_in_off, b_out_off, b_out_len, b_status, b_trace, b_ptrace, b_prof, b_ids, b_usage, b_rand, b_final;
+  DevBuf b_in, b_out, b_in_off, b_out_off, b_out_len, b_status, b_trace, b_ptrace, b_prof, b_ids, b_usage, b_rand, b_final, b_coder;
   bool profile = false;
   uint32_t prof_streams = 0;
   uint32_t usage_streams = 0;
@@ -86,6 +86,9 @@ struct RunOpts {
   uint32_t* d_final_state = nullptr;
   uint32_t gen_bytes = 0; float temperature = 1.0f; const float* d_rand_u = nullptr; uint64_t rand_stride = 0;
   uint64_t* d_bit_trace = nullptr; float* d_pred_trace = nullptr;
+  // one stream coded in parts (gmx_compress_part / gmx_decompress_part)
+  uint32_t part = 0, part_header = 0, part_last = 0; uint64_t part_total = 0;
+  const uint32_t* d_coder_in = nullptr; uint32_t* d_coder_out = nullptr;
 };
 
 // One stream stepped bit by bit (the Predictor facade). Owns a worst-case-sized arena.
@@ -264,6 +267,7 @@ int RunDevice(gmx_ctx* c, int mode, const uint8_t* d_in, const uint64_t* d_in_of
   P.bit_trace = o.d_bit_trace; P.pred_trace = o.d_pred_trace;
   P.analysis = o.analysis; P.final_state = o.d_final_state;
   P.gen_bytes = o.gen_bytes; P.temperature = o.temperature; P.rand_u = o.d_rand_u; P.rand_stride = o.rand_stride;
+  P.part = o.part; P.part_header = o.part_header; P.part_last = o.part_last; P.part_total = o.part_total; P.coder_in = o.d_coder_in; P.coder_out = o.d_coder_out;
   if (o.model) { P.tmpl_arena = o.model->d_arena; P.tmpl_state = o.model->d_state; }
   const uint32_t grid = n < c->n_arenas ? n : c->n_arenas;
   {
@@ -428,7 +432,7 @@ void gmx_destroy(gmx_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   FreeArenas(c);
-  for (DevBuf* b : {&c->b_in, &c->b_out, &c->b_in_off, &c->b_out_off, &c->b_out_len, &c->b_status, &c->b_trace, &c->b_ptrace, &c->b_prof, &c->b_ids, &c->b_usage, &c->b_rand, &c->b_final})
+  for (DevBuf* b : {&c->b_in, &c->b_out, &c->b_in_off, &c->b_out_off, &c->b_out_len, &c->b_status, &c->b_trace, &c->b_ptrace, &c->b_prof, &c->b_ids, &c->b_usage, &c->b_rand, &c->b_final, &c->b_coder})
     if (b->p) cudaFree(b->p);
   if (c->d_layout) cudaFree(c->d_layout);
   if (c->d_roomy_layout) cudaFree(c->d_roomy_layout);
@@ -693,6 +697,76 @@ int gmx_train_checkpoint(gmx_ctx* c, const gmx_model* from, const uint8_t* data,
   return 0;
 }
 
+namespace {
+// One stream, one part, parked afterwards and serialised as the reference's checkpoint files. `from` == null: the part
+// starts a stream from scratch.
+int RunPart(gmx_ctx* c, int mode, const gmx_model* from, const gmx_coder_state* coder_in, RunOpts o, const uint8_t* in, uint64_t n_in, uint8_t* out,
+            uint64_t cap, uint64_t* out_len, gmx_coder_state* coder_out, uint64_t* in_consumed, const void** short_blob, uint64_t* short_len,
+            const void** long_blob, uint64_t* long_len) {
+  GMX_CUDA(c, cudaSetDevice(c->device));
+  int rc;
+  if ((rc = Reserve(c, c->b_final, sizeof(gmx::StreamSmem)))) return rc;
+  if ((rc = Reserve(c, c->b_coder, 64))) return rc;
+  uint32_t h[8] = {0, 0xffffffffu, 0, 0, 0, 0, 0, 0};
+  if (coder_in) { h[0] = coder_in->x1; h[1] = coder_in->x2; h[2] = coder_in->x; }
+  GMX_CUDA(c, cudaMemcpy(c->b_coder.p, h, 32, cudaMemcpyHostToDevice));
+  o.model = from; o.d_final_state = (uint32_t*)c->b_final.p; o.part = 1;
+  o.d_coder_in = coder_in ? (const uint32_t*)c->b_coder.p : nullptr; o.d_coder_out = (uint32_t*)c->b_coder.p + 4;
+  const uint64_t io[2] = {0, n_in}, oo[2] = {0, cap};
+  uint32_t status = 0;
+  const uint8_t dummy = 0;
+  rc = RunHost(c, mode, n_in ? in : &dummy, io, 1, out, oo, out_len, &status, nullptr, nullptr, o);
+  bool roomy = false;
+  if (rc == GMX_E_STREAM && Retryable(status) && !from) {   // as gmx_train_checkpoint: once more in one worst-case-sized arena
+    const uint64_t len = mode == gmx::MODE_COMPRESS ? n_in : cap;
+    FreeArenas(c);
+    c->layout = gmx::MakeLayout(len, true);
+    if (cudaMalloc(&c->d_arenas, c->layout.total) != cudaSuccess)
+      return Fail(c, GMX_E_NOMEM, "cannot allocate a worst-case arena of %llu MiB: %s", (unsigned long long)(c->layout.total >> 20),
+                  cudaGetErrorString(cudaGetLastError()));
+    GMX_CUDA(c, cudaMemcpy(c->d_layout, &c->layout, sizeof(c->layout), cudaMemcpyHostToDevice));
+    c->n_arenas = 1;
+    c->cfg_max_len = len;
+    roomy = true;
+    c->retried_streams += 1;
+    rc = RunHost(c, mode, n_in ? in : &dummy, io, 1, out, oo, out_len, &status, nullptr, nullptr, o);
+  }
+  if (rc) { if (roomy) FreeArenas(c); return rc; }
+  GMX_CUDA(c, cudaMemcpy(h, (uint32_t*)c->b_coder.p + 4, 16, cudaMemcpyDeviceToHost));
+  if (coder_out) { coder_out->x1 = h[0]; coder_out->x2 = h[1]; coder_out->x = h[2]; }
+  if (in_consumed) *in_consumed = h[3];
+  if (short_blob) {
+    rc = SerializeParked(c, c->layout, c->d_arenas, (const uint32_t*)c->b_final.p);   // one stream: it ran in arena 0
+    if (roomy) FreeArenas(c);
+    if (rc) return rc;
+    *short_blob = c->ck_short.data(); *short_len = c->ck_short.size();
+    *long_blob = c->ck_long.data(); *long_len = c->ck_long.size();
+  } else if (roomy) {
+    FreeArenas(c);
+  }
+  return 0;
+}
+}  // namespace
+
+int gmx_compress_part(gmx_ctx* c, const gmx_model* from, const gmx_coder_state* coder_in, int write_header, uint64_t total_len, int last, int analysis,
+                      const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_len, gmx_coder_state* coder_out,
+                      const void** short_blob, uint64_t* short_len, const void** long_blob, uint64_t* long_len) {
+  if (!c || !out || !out_len || (!in && n) || (short_blob && (!short_len || !long_blob || !long_len))) return GMX_E_ARG;
+  RunOpts o;
+  o.analysis = analysis; o.part_header = write_header != 0; o.part_last = last != 0; o.part_total = total_len;
+  return RunPart(c, gmx::MODE_COMPRESS, from, coder_in, o, in, n, out, cap, out_len, coder_out, nullptr, short_blob, short_len, long_blob, long_len);
+}
+
+int gmx_decompress_part(gmx_ctx* c, const gmx_model* from, const gmx_coder_state* coder_in, int analysis, const uint8_t* in, uint64_t n_in,
+                        uint64_t out_bytes, uint8_t* out, uint64_t* in_consumed, gmx_coder_state* coder_out,
+                        const void** short_blob, uint64_t* short_len, const void** long_blob, uint64_t* long_len) {
+  if (!c || !out || (!in && n_in) || (short_blob && (!short_len || !long_blob || !long_len))) return GMX_E_ARG;
+  RunOpts o;
+  o.analysis = analysis; o.part_header = coder_in == nullptr; o.part_total = out_bytes;
+  uint64_t out_len = 0;
+  return RunPart(c, gmx::MODE_DECOMPRESS, from, coder_in, o, in, n_in, out, out_bytes + 8, &out_len, coder_out, in_consumed, short_blob, short_len, long_blob, long_len);
+}
+
 int gmx_checksum_device(gmx_ctx* c, const uint8_t* d_data, const uint64_t* d_off, const uint64_t* d_len, uint32_t n, uint64_t* d_sum) {
   if (!c) return GMX_E_ARG;
   if (n == 0) return 0;
@@ -815,6 +889,20 @@ int gmx_pred_perceive(gmx_pred* p, int bit) {
 int gmx_pred_learn(gmx_pred* p) {
   if (!p) return GMX_E_ARG;
   return PredStep(p, gmx::STEP_LEARN, nullptr);
+}
+
+// Predictor::Copy (predictor.cpp:42-48): dst becomes a deep copy of src (device-to-device: arena + parked state).
+int gmx_pred_copy(gmx_pred* dst, const gmx_pred* src) {
+  if (!dst || !src) return GMX_E_ARG;
+  gmx_ctx* c = dst->ctx;
+  if (src->ctx != c) return Fail(c, GMX_E_ARG, "predictors belong to different contexts");
+  if (memcmp(&dst->layout, &src->layout, sizeof(gmx::ArenaLayout)) != 0) return Fail(c, GMX_E_ARG, "predictors were created with different max_stream_len");
+  GMX_CUDA(c, cudaSetDevice(c->device));
+  GMX_CUDA(c, cudaMemcpyAsync(dst->d_arena, src->d_arena, src->layout.total, cudaMemcpyDeviceToDevice, c->stream));
+  GMX_CUDA(c, cudaMemcpyAsync(dst->d_state, src->d_state, gmx::StepStateBytes(), cudaMemcpyDeviceToDevice, c->stream));
+  GMX_CUDA(c, cudaStreamSynchronize(c->stream));
+  dst->pending_bit = src->pending_bit; dst->analysis = src->analysis; dst->bits = src->bits;
+  return 0;
 }
 
 int gmx_pred_write_checkpoint(gmx_pred* p, const void** short_blob, uint64_t* short_len, const void** long_blob, uint64_t* long_len) {

@@ -130,6 +130,13 @@ struct StreamParams {
   // generation (runner_utils::RunGeneration runner-utils.cpp:158-221): `in` holds the prompts, out[sid * gen_bytes ..] the samples
   uint32_t gen_bytes; float temperature;
   const float* rand_u; uint64_t rand_stride;   // rand()/RAND_MAX draws, one per generated bit; stream sid reads rand_u[sid * rand_stride + k]
+  // One stream coded in PARTS (Encoder/Decoder::WriteCheckpoint + ReadCheckpoint, encoder.cpp:36-51, decoder.cpp:41-57):
+  // single-stream launches only. part != 0 switches the framing off: no header is written / read unless part_header,
+  // the coder starts from coder_in {x1, x2, x} when given, ends without Encoder::Flush unless part_last, and leaves its
+  // state in coder_out {x1, x2, x, coded bytes consumed by the decoder}.
+  uint32_t part, part_header, part_last;
+  uint64_t part_total;         // compress: length the header announces; decompress: bytes this part produces
+  const uint32_t* coder_in; uint32_t* coder_out;
 };
 
 // ---- device constant tables --------------------------------------------------------------------
@@ -2227,8 +2234,18 @@ __global__ void __launch_bounds__(32 * (WB + WL + 1), MINB) StreamKernel(StreamP
         uint8_t* out = P.out + P.out_off[sid];
         job.out = out; job.n_bytes = (uint32_t)n;
         s.out_pos = 0; s.out_cap = P.out_off[sid + 1] - P.out_off[sid];
-        s.analysis = P.analysis >= 0 ? P.analysis : (8 * n / 1000) > 0;  // EnableAnalysis(8*n/1000) -> predictions zeroed every bit
-        for (int i = 4; i >= 0; --i) PutByte(s, out, (uint32_t)(n >> (8 * i)) & 0xff);
+        const uint64_t announced = P.part ? P.part_total : n;
+        s.analysis = P.analysis >= 0 ? P.analysis : (8 * announced / 1000) > 0;  // EnableAnalysis(8*n/1000) -> predictions zeroed every bit
+        if (!P.part || P.part_header) for (int i = 4; i >= 0; --i) PutByte(s, out, (uint32_t)(announced >> (8 * i)) & 0xff);
+        if (P.part && P.coder_in) { s.x1 = P.coder_in[0]; s.x2 = P.coder_in[1]; }
+      } else if (MODE == MODE_DECOMPRESS && P.part && !P.part_header) {   // a later part of a stream: the decoder continues
+        job.out = P.out + P.out_off[sid];
+        s.in_pos = 0; s.in_len = n;
+        s.out_pos = 0; s.out_cap = P.part_total;
+        s.analysis = P.analysis >= 0 ? P.analysis : 0;
+        if (P.part_total > P.out_off[sid + 1] - P.out_off[sid]) SetError(s, GMX_ERR_OUTPUT_CAP);
+        if (P.coder_in) { s.x1 = P.coder_in[0]; s.x2 = P.coder_in[1]; s.x = P.coder_in[2]; }
+        job.n_bytes = (uint32_t)P.part_total;
       } else if (MODE == MODE_DECOMPRESS) {   // ReadHeader runner-utils.cpp:29-36, Decoder::Decoder decoder.cpp:3-9
         job.out = P.out + P.out_off[sid];
         s.in_pos = 0; s.in_len = n;
@@ -2236,6 +2253,7 @@ __global__ void __launch_bounds__(32 * (WB + WL + 1), MINB) StreamKernel(StreamP
         s.analysis = P.analysis >= 0 ? P.analysis : 0;
         uint64_t len = 0;
         for (int i = 0; i <= 4; ++i) len = (len << 8) + GetByte(s, in);
+        if (P.part && P.part_total <= len) len = P.part_total;   // first part of a stream coded in parts: only this many bytes now
         if (s.in_len < 5 || len > s.out_cap) { SetError(s, s.in_len < 5 ? GMX_ERR_BAD_HEADER : GMX_ERR_OUTPUT_CAP); len = 0; }
         s.out_cap = len;  // number of bytes to produce
         for (int i = 0; i < 4; ++i) s.x = (s.x << 8) + (GetByte(s, in) & 0xff);
@@ -2267,10 +2285,13 @@ __global__ void __launch_bounds__(32 * (WB + WL + 1), MINB) StreamKernel(StreamP
     }
     __syncthreads();
     if (tid == 0) {
+      if (P.part && P.coder_out) { P.coder_out[0] = s.x1; P.coder_out[1] = s.x2; P.coder_out[2] = s.x; P.coder_out[3] = (uint32_t)s.in_pos; }
       if (MODE == MODE_COMPRESS) {   // Encoder::Flush encoder.cpp:27-34
         uint8_t* out = job.out;
-        while (((s.x1 ^ s.x2) & 0xff000000u) == 0) { PutByte(s, out, s.x2 >> 24); s.x1 <<= 8; s.x2 = (s.x2 << 8) + 255; }
-        PutByte(s, out, s.x2 >> 24);
+        if (!P.part || P.part_last) {
+          while (((s.x1 ^ s.x2) & 0xff000000u) == 0) { PutByte(s, out, s.x2 >> 24); s.x1 <<= 8; s.x2 = (s.x2 << 8) + 255; }
+          PutByte(s, out, s.x2 >> 24);
+        }
         P.out_len[sid] = s.out_pos;
       } else if (MODE == MODE_DECOMPRESS) {
         P.out_len[sid] = s.error ? 0 : job.n_bytes;

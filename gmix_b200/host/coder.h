@@ -5,7 +5,10 @@
 #ifndef GMIX_B200_HOST_CODER_H_
 #define GMIX_B200_HOST_CODER_H_
 #include <stdint.h>
+#include <string.h>
 
+#include <fstream>
+#include <string>
 #include <vector>
 
 namespace gmixb {
@@ -29,6 +32,20 @@ class Encoder {
     Normalize();
   }
   void Flush() { Normalize(); out_->push_back((uint8_t)(x2_ >> 24)); }  // encoder.cpp:27-34
+  // encoder.cpp:36-51: the file holds x1, x2 as raw little-endian u32 (a file that cannot be opened is silently ignored)
+  void WriteCheckpoint(const std::string& path) const {
+    std::ofstream f(path, std::ios::out | std::ios::binary);
+    if (!f.is_open()) return;
+    f.write((const char*)&x1_, 4); f.write((const char*)&x2_, 4);
+  }
+  void ReadCheckpoint(const std::string& path) {
+    std::ifstream f(path, std::ios::in | std::ios::binary);
+    if (!f.is_open()) return;
+    f.read((char*)&x1_, 4); f.read((char*)&x2_, 4);
+  }
+  uint32_t x1() const { return x1_; }
+  uint32_t x2() const { return x2_; }
+  void Set(uint32_t x1, uint32_t x2) { x1_ = x1; x2_ = x2; }
 
  private:
   void Normalize() {
@@ -50,6 +67,20 @@ class Decoder {
     while (((x1_ ^ x2_) & 0xff000000u) == 0) { x1_ <<= 8; x2_ = (x2_ << 8) + 255; x_ = (x_ << 8) + Next(); }
     return bit;
   }
+  // decoder.cpp:41-57: x1, x2, x as raw little-endian u32. The read position of the coded stream is the caller's
+  // business, as in the reference (its decoder reads from a std::ifstream that simply keeps its position).
+  void WriteCheckpoint(const std::string& path) const {
+    std::ofstream f(path, std::ios::out | std::ios::binary);
+    if (!f.is_open()) return;
+    f.write((const char*)&x1_, 4); f.write((const char*)&x2_, 4); f.write((const char*)&x_, 4);
+  }
+  void ReadCheckpoint(const std::string& path) {
+    std::ifstream f(path, std::ios::in | std::ios::binary);
+    if (!f.is_open()) return;
+    f.read((char*)&x1_, 4); f.read((char*)&x2_, 4); f.read((char*)&x_, 4);
+  }
+  uint64_t position() const { return pos_; }       // coded bytes consumed so far
+  void Seek(uint64_t pos) { pos_ = pos; }
 
  private:
   uint32_t Next() { return pos_ < n_ ? in_[pos_++] : (pos_++, 0u); }  // reads as 0 past the end

@@ -46,6 +46,7 @@ class Predictor {
   }
   void Perceive(int bit) { Check(gmx_pred_perceive(p_, bit)); }   // predictor.cpp:378-381
   void Learn() { Check(gmx_pred_learn(p_)); }                       // predictor.cpp:383-387
+  void Copy(const Predictor& p) { Check(gmx_pred_copy(p_, p.p_)); } // predictor.cpp:42-48 (same Gpu, same max_stream_len)
   // Only the path-visible effect of EnableAnalysis (predictions zeroed each Predict, predictor.cpp:362-365).
   void EnableAnalysis(int sample_frequency) { Check(gmx_pred_enable_analysis(p_, sample_frequency > 0)); }
   // `path`.short + `path`.long in the reference's format (predictor.cpp:389-420); like the reference, a file that

@@ -14,6 +14,10 @@
 //   gmixb200 -D input output        inverse of -C (same sharding)
 //   gmixb200 -p input output        compress one stream through the Predictor facade + host coder
 //                                   (Predict/Perceive/Learn per bit; slow, for checking the drop-in interface)
+//   gmixb200 -T input workdir       the reference's own test-suite (runner/tester.cpp:323-378) re-run against this build
+//                                   through the Predictor facade + host coder: compression, compression with restart
+//                                   (predictor + coder checkpoints), with Copy restart, decompression with restart,
+//                                   generation leaves the long-term memory unchanged. Prints "Tests passed." like it.
 // `ckpt` is a checkpoint prefix: <ckpt>.short + <ckpt>.long, written by the reference or by this program.
 #include <stdio.h>
 #include <stdlib.h>
@@ -40,7 +44,8 @@ int Help() {
          "Generate:    gmixb200 -g checkpoint_path prompt output output_size temperature\n"
          "Train:       gmixb200 -t [checkpoint_path] training_file test_file\n"
          "Chunked:     gmixb200 -C chunk_bytes input output   /   gmixb200 -D input output\n"
-         "Via facade:  gmixb200 -p input output\n");
+         "Via facade:  gmixb200 -p input output\n"
+         "Self test:   gmixb200 -T input workdir   (the reference's tester.cpp against this build)\n");
   return -1;
 }
 
@@ -184,12 +189,128 @@ int Train(int argc, char* argv[]) {
   return 0;
 }
 
+// ---- the reference's tests (runner/tester.cpp) against the facade ------------------------------------------------
+bool FilesEqual(const std::string& a, const std::string& b) {
+  std::vector<uint8_t> x, y;
+  return ReadFile(a, &x) && ReadFile(b, &y) && x == y;
+}
+void CodeByte(gmixb::Predictor& p, gmixb::Encoder& e, uint8_t c) {   // runner-utils.cpp:50-58
+  for (int j = 7; j >= 0; --j) { const int bit = (c >> j) & 1; e.Encode(bit, p.Predict()); p.Perceive(bit); p.Learn(); }
+}
+int DecodeByte(gmixb::Predictor& p, gmixb::Decoder& d) {             // runner-utils.cpp:75-78 + decoder.cpp:19-39
+  int byte = 1;
+  while (byte < 256) { const int bit = d.Decode(p.Predict()); p.Perceive(bit); p.Learn(); byte += byte + bit; }
+  return byte - 256;
+}
+void Header(uint64_t n, std::vector<uint8_t>* out) { for (int i = 4; i >= 0; --i) out->push_back((uint8_t)(n >> (8 * i))); }
+
+int SelfTest(const std::string& input_path, const std::string& dir) {
+  std::vector<uint8_t> in;
+  if (!ReadFile(input_path, &in) || in.size() < 4) { printf("Error opening: %s\n", input_path.c_str()); return -1; }
+  std::filesystem::create_directories(dir);
+  const uint64_t n = in.size(), half = n / 2;
+  gmixb::Gpu gpu(0);
+  // TestCompression (tester.cpp:323-327): the batch kernel's stream is the expected one (analysis off, as in tester.cpp)
+  std::vector<uint8_t> test1;
+  {
+    gmixb::Predictor p(gpu, n + 1);
+    Header(n, &test1);
+    gmixb::Encoder e(&test1);
+    for (uint64_t pos = 0; pos < n; ++pos) CodeByte(p, e, in[pos]);
+    e.Flush();
+  }
+  printf("compression: %llu -> %zu bytes\n", (unsigned long long)n, test1.size());
+  // TestCompressionWithRestart (:329-337, CompressFirstHalf/SecondHalf :24-88): checkpoint after byte n/2
+  {
+    std::vector<uint8_t> out;
+    Header(n, &out);
+    {
+      gmixb::Predictor p(gpu, n + 1);
+      gmixb::Encoder e(&out);
+      for (uint64_t pos = 0; pos <= half; ++pos) CodeByte(p, e, in[pos]);
+      p.WriteCheckpoint(dir + "/checkpoint");
+      e.WriteCheckpoint(dir + "/checkpoint.coder");
+    }
+    gmixb::Predictor p(gpu, n + 1);
+    p.ReadCheckpoint(dir + "/checkpoint");
+    gmixb::Encoder e(&out);
+    e.ReadCheckpoint(dir + "/checkpoint.coder");
+    p.WriteCheckpoint(dir + "/checkpoint2");
+    for (uint64_t pos = half + 1; pos < n; ++pos) CodeByte(p, e, in[pos]);
+    e.Flush();
+    if (out != test1) { printf("compression with restart: output differs\n"); return -1; }
+    if (!FilesEqual(dir + "/checkpoint.long", dir + "/checkpoint2.long") || !FilesEqual(dir + "/checkpoint.short", dir + "/checkpoint2.short")) {
+      printf("compression with restart: a checkpoint read back and written again differs\n");
+      return -1;
+    }
+  }
+  printf("compression with restart: ok\n");
+  // TestCompressionWithCopyRestart (:339-348, :112-180)
+  {
+    std::vector<uint8_t> out;
+    Header(n, &out);
+    gmixb::Predictor p(gpu, n + 1);
+    gmixb::Encoder e(&out);
+    for (uint64_t pos = 0; pos <= half; ++pos) CodeByte(p, e, in[pos]);
+    e.WriteCheckpoint(dir + "/checkpoint.coder");
+    gmixb::Predictor p2(gpu, n + 1);
+    p2.Copy(p);
+    gmixb::Encoder e2(&out);
+    e2.ReadCheckpoint(dir + "/checkpoint.coder");
+    p2.WriteCheckpoint(dir + "/checkpoint2");
+    for (uint64_t pos = half + 1; pos < n; ++pos) CodeByte(p2, e2, in[pos]);
+    e2.Flush();
+    if (out != test1) { printf("compression with Copy restart: output differs\n"); return -1; }
+    if (!FilesEqual(dir + "/checkpoint.long", dir + "/checkpoint2.long") || !FilesEqual(dir + "/checkpoint.short", dir + "/checkpoint2.short")) {
+      printf("compression with Copy restart: the copy's checkpoint differs from the original's\n");
+      return -1;
+    }
+  }
+  printf("compression with Copy restart: ok\n");
+  // TestDecompressionWithRestart (:350-356, :182-321)
+  {
+    std::vector<uint8_t> back;
+    uint64_t coded_pos;
+    {
+      gmixb::Predictor p(gpu, n + 1);
+      gmixb::Decoder d(test1.data() + 5, test1.size() - 5);
+      for (uint64_t pos = 0; pos <= half; ++pos) back.push_back((uint8_t)DecodeByte(p, d));
+      p.WriteCheckpoint(dir + "/checkpoint");
+      d.WriteCheckpoint(dir + "/checkpoint.coder");
+      coded_pos = d.position();
+    }
+    gmixb::Predictor p(gpu, n + 1);
+    p.ReadCheckpoint(dir + "/checkpoint");
+    gmixb::Decoder d(test1.data() + 5, test1.size() - 5);
+    d.ReadCheckpoint(dir + "/checkpoint.coder");
+    d.Seek(coded_pos);
+    for (uint64_t pos = half + 1; pos < n; ++pos) back.push_back((uint8_t)DecodeByte(p, d));
+    if (back != in) { printf("decompression with restart: output differs from the original\n"); return -1; }
+  }
+  printf("decompression with restart: ok\n");
+  // TestGeneration (:358-366): Predict/Perceive without Learn leaves `.long` unchanged and changes `.short`
+  {
+    gmixb::Predictor p(gpu, n + 64);
+    for (uint64_t pos = 0; pos < n; ++pos)
+      for (int j = 7; j >= 0; --j) { p.Predict(); p.Perceive((in[pos] >> j) & 1); p.Learn(); }
+    p.WriteCheckpoint(dir + "/checkpoint");
+    unsigned x = 12345;
+    for (int i = 0; i < 8 * 32; ++i) { const float pr = p.Predict(); x = x * 1103515245u + 12345u; p.Perceive(((x >> 16) & 0xffff) < pr * 65536.0f); }
+    p.WriteCheckpoint(dir + "/checkpoint2");
+    if (!FilesEqual(dir + "/checkpoint.long", dir + "/checkpoint2.long")) { printf("generation changed the long-term memory\n"); return -1; }
+    if (FilesEqual(dir + "/checkpoint.short", dir + "/checkpoint2.short")) { printf("generation did not change the short-term memory\n"); return -1; }
+  }
+  printf("generation: ok\nTests passed.\n");
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char* argv[]) {
   if (argc < 4 || strlen(argv[1]) != 2 || argv[1][0] != '-') return Help();
   const char mode = argv[1][1];
   try {
+    if (mode == 'T') { if (argc != 4) return Help(); return SelfTest(argv[2], argv[3]); }
     if (mode == 'g') return Generate(argc, argv);
     if (mode == 't') return Train(argc, argv);
   } catch (const std::exception& e) {

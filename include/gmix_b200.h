@@ -156,6 +156,25 @@ int gmx_checksum_device(gmx_ctx* ctx, const uint8_t* d_data, const uint64_t* d_o
 int gmx_compress_trace(gmx_ctx* ctx, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_len,
                        float* probs, uint32_t* p16, float* blackboard);
 
+/* ---- One stream coded in parts: Encoder/Decoder::WriteCheckpoint + ReadCheckpoint (coder/encoder.cpp:36-51,
+ * coder/decoder.cpp:41-57) together with Predictor::Write/ReadCheckpoint, i.e. what the reference's restart tests do
+ * (runner/tester.cpp:24-110, 182-321) at batch speed. A part is a whole number of bytes. `from` = the model the part
+ * starts from (NULL = a fresh Predictor; load it with max_new_bytes >= the part's bytes + 8); coder_in = the coder state
+ * the part starts with (NULL = a fresh Encoder / a Decoder that reads the 5-byte header and its first 4 bytes from `in`).
+ * After the part: coder_out = what Encoder/Decoder::WriteCheckpoint would write, and - when short_blob != NULL - the
+ * predictor checkpoint (valid until the next checkpoint-producing call on the ctx). analysis: -1 = as the runner would
+ * for a stream of total_len bytes, 0 / 1 = forced (the reference's tester never enables it).
+ * gmx_compress_part: write_header != 0 puts the 5-byte header of a total_len-byte stream first; last != 0 ends with
+ * Encoder::Flush. gmx_decompress_part: produces exactly out_bytes bytes; in_consumed = coded bytes the decoder has
+ * taken from `in` (the next part's `in` starts there). */
+typedef struct { uint32_t x1, x2, x; } gmx_coder_state;
+int gmx_compress_part(gmx_ctx* ctx, const gmx_model* from, const gmx_coder_state* coder_in, int write_header, uint64_t total_len, int last,
+                      int analysis, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_len, gmx_coder_state* coder_out,
+                      const void** short_blob, uint64_t* short_len, const void** long_blob, uint64_t* long_len);
+int gmx_decompress_part(gmx_ctx* ctx, const gmx_model* from, const gmx_coder_state* coder_in, int analysis, const uint8_t* in, uint64_t n_in,
+                        uint64_t out_bytes, uint8_t* out, uint64_t* in_consumed, gmx_coder_state* coder_out,
+                        const void** short_blob, uint64_t* short_len, const void** long_blob, uint64_t* long_len);
+
 /* ---- Predictor facade: one stream stepped bit by bit -------------------------------------------
  * Mirrors `class Predictor` (reference src/predictor.h:20-38): Predict() -> Perceive(bit) -> Learn(), Learn
  * optional (generation). Every Predict/Learn is one kernel launch plus a device->host read, so this is
@@ -170,6 +189,8 @@ int gmx_pred_enable_analysis(gmx_pred* pred, int on);
 int gmx_pred_predict(gmx_pred* pred, float* prob);
 int gmx_pred_perceive(gmx_pred* pred, int bit);
 int gmx_pred_learn(gmx_pred* pred);
+/* Predictor::Copy (predictor.cpp:42-48): dst becomes a deep copy of src (same ctx, same max_stream_len). */
+int gmx_pred_copy(gmx_pred* dst, const gmx_pred* src);
 
 /* Predictor::WriteCheckpoint / ReadCheckpoint (predictor.cpp:389-420) of the stepped stream, at a byte boundary. */
 int gmx_pred_write_checkpoint(gmx_pred* pred, const void** short_blob, uint64_t* short_len, const void** long_blob, uint64_t* long_len);

@@ -7,6 +7,10 @@
 //   emu_main expand   <ckpt_prefix> <in> <out>                   `gmix -d <ckpt> <in> <out>`
 //   emu_main generate <ckpt_prefix> <prompt> <out> <size> <temperature>   `gmix -g ...` (sampling draws from this host's rand())
 //   emu_main recode   <ckpt_prefix> <out_prefix>                 Parse then Serialize (must reproduce the files byte for byte)
+//   emu_main parts    <in> <out> <split>                         compress <in> as ONE stream in two parts: bytes [0, split) with the
+//                                                                header and no flush, a predictor + coder checkpoint (through the
+//                                                                reference's file format), then the rest from that checkpoint
+//   emu_main unparts  <in.gmix> <out> <split>                    decompress likewise: `split` bytes, checkpoint, the rest
 //   emu_main steps    <in> <out>                                 compress through the Predictor facade's StepKernel (one launch per
 //                                                                Predict / Learn, host coder), analysis as `gmix -c` sets it
 #include "cuda_emu.h"
@@ -178,6 +182,43 @@ int main(int argc, char** argv) {
     return 0;
   }
 
+  if (mode == "parts" || mode == "unparts") {
+    const bool comp = mode == "parts";
+    std::vector<uint8_t> in = ReadAll(argv[2]);
+    uint64_t total = in.size();
+    if (!comp) { total = 0; for (int i = 0; i < 5; ++i) total = (total << 8) + in[i]; }
+    const uint64_t split = strtoull(argv[4], nullptr, 10);
+    if (split > total) return 2;
+    std::vector<uint8_t> out(total + total / 8 + 64), result;
+    uint32_t coder[8] = {0};
+    // part 1 (from scratch)
+    in_off[0] = 0; in_off[1] = comp ? split : in.size(); out_off[0] = 0; out_off[1] = out.size();
+    P.in = in.data(); P.out = out.data(); P.analysis = 0;
+    P.part = 1; P.part_header = 1; P.part_last = 0; P.part_total = comp ? total : split; P.coder_in = nullptr; P.coder_out = coder;
+    if (Execute(R, comp ? gmx::MODE_COMPRESS : gmx::MODE_DECOMPRESS, nullptr, total, P, true)) return 1;
+    result.assign(out.begin(), out.begin() + out_len[0]);
+    const uint64_t consumed = coder[3];
+    gmx::ckpt::Image im, im2;
+    std::string err;
+    if (!gmx::ckpt::FromArena(R.L, P.arenas, *(const gmx::StreamSmem*)R.final_state.data(), &im, &err)) { fprintf(stderr, "FromArena: %s\n", err.c_str()); return 1; }
+    std::vector<uint8_t> sh, lo;
+    gmx::ckpt::Serialize(im, &sh, &lo);
+    if (!gmx::ckpt::Parse(sh.data(), sh.size(), lo.data(), lo.size(), &im2, &err)) { fprintf(stderr, "Parse: %s\n", err.c_str()); return 1; }
+    // part 2 (from the checkpoint, coder state from part 1)
+    Run R2;
+    gmx::StreamParams Q;
+    memset(&Q, 0, sizeof(Q));
+    uint64_t io2[2], oo2[2] = {0, out.size()}, ol2[1] = {0};
+    uint32_t coder_in[4] = {coder[0], coder[1], coder[2], 0}, coder2[8] = {0};
+    Q.in_off = io2; Q.out_off = oo2; Q.out_len = ol2; Q.out = out.data(); Q.analysis = 0;
+    if (comp) { Q.in = in.data() + split; io2[0] = 0; io2[1] = total - split; }
+    else { Q.in = in.data() + consumed; io2[0] = 0; io2[1] = in.size() - consumed; }
+    Q.part = 1; Q.part_header = 0; Q.part_last = 1; Q.part_total = comp ? total : total - split; Q.coder_in = coder_in; Q.coder_out = coder2;
+    if (Execute(R2, comp ? gmx::MODE_COMPRESS : gmx::MODE_DECOMPRESS, &im2, total - split, Q, false)) return 1;
+    result.insert(result.end(), out.begin(), out.begin() + ol2[0]);
+    WriteAll(argv[3], result.data(), result.size());
+    return 0;
+  }
   if (mode == "steps") {   // what gmix_b200/host/predictor.h does over gmx_pred_*: STEP_INIT, then Predict / (Perceive) Learn per bit
     std::vector<uint8_t> in = ReadAll(argv[2]);
     Run R2;

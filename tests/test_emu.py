@@ -114,3 +114,16 @@ def test_other_role_splits_compute_the_same_bytes(tmp_path, roles):
     back = str(tmp_path / "back")
     subprocess.run([exe, "decompress", os.path.join(GOLD, "text1k.gmix"), back], check=True, stderr=subprocess.DEVNULL)
     assert open(back, "rb").read() == open(os.path.join(GOLD, "text1k.in"), "rb").read()
+
+
+def test_stream_coded_in_two_parts_with_checkpoints(emu, tmp_path):
+    """Encoder/Decoder::Write/ReadCheckpoint + Predictor::Write/ReadCheckpoint mid-stream (the reference's restart tests,
+    tester.cpp:329-356) at kernel level: part 1 without flush, the stream's state through the reference's file format,
+    part 2 from it with the saved coder state; the concatenation is the whole-stream output."""
+    for name, split in (("text1k", 517), ("random1200", 1), ("random1200", 1199)):
+        out = str(tmp_path / "p.out")
+        subprocess.run([emu, "parts", os.path.join(GOLD, name + ".in"), out, str(split)], check=True, stderr=subprocess.DEVNULL)
+        assert open(out, "rb").read() == open(os.path.join(GOLD, name + ".gmix"), "rb").read(), (name, split)
+    back = str(tmp_path / "u.out")
+    subprocess.run([emu, "unparts", os.path.join(GOLD, "text1k.gmix"), back, "333"], check=True, stderr=subprocess.DEVNULL)
+    assert open(back, "rb").read() == open(os.path.join(GOLD, "text1k.in"), "rb").read()
