@@ -51,7 +51,7 @@ def load_library():
     lib.gmx_pred_copy.argtypes = [C.c_void_p, C.c_void_p]
     lib.gmx_compress_part.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p,
                                       C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
-                                      C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+                                      C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_void_p]
     lib.gmx_decompress_part.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p,
                                         C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
                                         C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
@@ -319,7 +319,7 @@ class Context:
         rc = self.lib.gmx_compress_part(self.h, model.h if model is not None else None, cin.ctypes.data if cin is not None else None,
                                         int(header_total is not None), int(header_total or 0), int(last), int(analysis), src.ctypes.data, n,
                                         out.ctypes.data, cap, C.byref(out_len), cout.ctypes.data,
-                                        C.byref(sp) if want_checkpoint else None, C.byref(sl), C.byref(lp), C.byref(ll))
+                                        C.byref(sp) if want_checkpoint else None, C.byref(sl), C.byref(lp), C.byref(ll), None)
         self._check(rc, "gmx_compress_part")
         ck = (C.string_at(sp.value, sl.value), C.string_at(lp.value, ll.value)) if want_checkpoint else None
         return out[:out_len.value].tobytes(), (int(cout[0]), int(cout[1])), ck

@@ -702,7 +702,7 @@ namespace {
 // starts a stream from scratch.
 int RunPart(gmx_ctx* c, int mode, const gmx_model* from, const gmx_coder_state* coder_in, RunOpts o, const uint8_t* in, uint64_t n_in, uint8_t* out,
             uint64_t cap, uint64_t* out_len, gmx_coder_state* coder_out, uint64_t* in_consumed, const void** short_blob, uint64_t* short_len,
-            const void** long_blob, uint64_t* long_len) {
+            const void** long_blob, uint64_t* long_len, float* probs = nullptr) {
   GMX_CUDA(c, cudaSetDevice(c->device));
   int rc;
   if ((rc = Reserve(c, c->b_final, sizeof(gmx::StreamSmem)))) return rc;
@@ -715,7 +715,9 @@ int RunPart(gmx_ctx* c, int mode, const gmx_model* from, const gmx_coder_state* 
   const uint64_t io[2] = {0, n_in}, oo[2] = {0, cap};
   uint32_t status = 0;
   const uint8_t dummy = 0;
-  rc = RunHost(c, mode, n_in ? in : &dummy, io, 1, out, oo, out_len, &status, nullptr, nullptr, o);
+  std::vector<uint64_t> bt(probs ? n_in * 8 + 1 : 0);
+  uint64_t* trace = probs ? bt.data() : nullptr;
+  rc = RunHost(c, mode, n_in ? in : &dummy, io, 1, out, oo, out_len, &status, trace, nullptr, o);
   bool roomy = false;
   if (rc == GMX_E_STREAM && Retryable(status) && !from) {   // as gmx_train_checkpoint: once more in one worst-case-sized arena
     const uint64_t len = mode == gmx::MODE_COMPRESS ? n_in : cap;
@@ -729,9 +731,10 @@ int RunPart(gmx_ctx* c, int mode, const gmx_model* from, const gmx_coder_state* 
     c->cfg_max_len = len;
     roomy = true;
     c->retried_streams += 1;
-    rc = RunHost(c, mode, n_in ? in : &dummy, io, 1, out, oo, out_len, &status, nullptr, nullptr, o);
+    rc = RunHost(c, mode, n_in ? in : &dummy, io, 1, out, oo, out_len, &status, trace, nullptr, o);
   }
   if (rc) { if (roomy) FreeArenas(c); return rc; }
+  for (uint64_t i = 0; probs && i < n_in * 8; ++i) { const uint32_t lo = (uint32_t)bt[i]; memcpy(&probs[i], &lo, 4); }
   GMX_CUDA(c, cudaMemcpy(h, (uint32_t*)c->b_coder.p + 4, 16, cudaMemcpyDeviceToHost));
   if (coder_out) { coder_out->x1 = h[0]; coder_out->x2 = h[1]; coder_out->x = h[2]; }
   if (in_consumed) *in_consumed = h[3];
@@ -750,11 +753,11 @@ int RunPart(gmx_ctx* c, int mode, const gmx_model* from, const gmx_coder_state* 
 
 int gmx_compress_part(gmx_ctx* c, const gmx_model* from, const gmx_coder_state* coder_in, int write_header, uint64_t total_len, int last, int analysis,
                       const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_len, gmx_coder_state* coder_out,
-                      const void** short_blob, uint64_t* short_len, const void** long_blob, uint64_t* long_len) {
+                      const void** short_blob, uint64_t* short_len, const void** long_blob, uint64_t* long_len, float* probs) {
   if (!c || !out || !out_len || (!in && n) || (short_blob && (!short_len || !long_blob || !long_len))) return GMX_E_ARG;
   RunOpts o;
   o.analysis = analysis; o.part_header = write_header != 0; o.part_last = last != 0; o.part_total = total_len;
-  return RunPart(c, gmx::MODE_COMPRESS, from, coder_in, o, in, n, out, cap, out_len, coder_out, nullptr, short_blob, short_len, long_blob, long_len);
+  return RunPart(c, gmx::MODE_COMPRESS, from, coder_in, o, in, n, out, cap, out_len, coder_out, nullptr, short_blob, short_len, long_blob, long_len, probs);
 }
 
 int gmx_decompress_part(gmx_ctx* c, const gmx_model* from, const gmx_coder_state* coder_in, int analysis, const uint8_t* in, uint64_t n_in,

@@ -4,9 +4,9 @@
 //   gmixb200 -c [ckpt] input output   compress, one stream; bytes identical to `gmix -c` (strict build)
 //   gmixb200 -d [ckpt] input output   decompress a stream written by either program
 //   gmixb200 -g ckpt prompt output size temperature    generate, bytes identical to `gmix -g` (runner-utils.cpp:158-221)
-//   gmixb200 -t [ckpt] train test     Predict/Perceive/Learn over `train`, write data/trained_checkpoint.{short,long}
-//                                     (the reference's format) and report the cross entropy of `test` under the trained
-//                                     model (runner-utils.cpp:223-322 without the periodic test passes)
+//   gmixb200 -t [ckpt] train test     RunTraining (runner-utils.cpp:223-322): Predict/Perceive/Learn over `train`, after every
+//                                     2 % the test file is scored on a copy of the predictor (analysis/training.tsv), the
+//                                     coded training stream goes to data/tmp, data/trained_checkpoint.{short,long} at the end
 //   gmixb200 -C bytes input output  split input into chunks of `bytes` and compress them as independent streams on ALL
 //                                   visible GPUs (GMIXB200_GPUS=k limits them): one context + host thread per GPU, contiguous
 //                                   byte-balanced stream ranges, one ncclAllGather of {size, FNV-1a 64} per stream
@@ -24,8 +24,12 @@
 #include <string.h>
 #include <time.h>
 
+#include <math.h>
+
+#include <algorithm>
 #include <filesystem>
 #include <fstream>
+#include <iomanip>
 #include <iterator>
 #include <string>
 #include <vector>
@@ -156,7 +160,20 @@ int Generate(int argc, char* argv[]) {
   return 0;
 }
 
-// RunTraining (runner-utils.cpp:223-322): learn the training file, write data/trained_checkpoint, score the test file.
+// RunTraining (runner-utils.cpp:223-322) at batch speed: the training file is one stream coded in parts that end where
+// the reference scores the test file (after every 2 % of the training bytes: pos % percent == 0, pos / percent even);
+// at each of those positions the stream's checkpoint is loaded as a model (= Predictor::Copy, :291-292) and the test
+// file runs from it, learning as it goes, like p2 does. Same outputs: analysis/training.tsv (bytes, train_entropy,
+// test_entropy, computed from the per-bit probabilities exactly as :284-309 does), data/tmp, data/trained_checkpoint.
+double SumLog2(const std::vector<uint8_t>& data, const std::vector<float>& probs) {
+  double e = 0;
+  for (size_t i = 0; i < data.size(); ++i)
+    for (int j = 7; j >= 0; --j) {
+      const float prob = probs[i * 8 + (7 - j)];
+      if ((data[i] >> j) & 1) e += log2(prob); else e += log2(1 - prob);
+    }
+  return e;
+}
 int Train(int argc, char* argv[]) {
   if (argc != 4 && argc != 5) { printf("Wrong number of arguments.\n"); return Help(); }
   const std::string ckpt = argc == 5 ? argv[2] : "", train_path = argv[argc - 2], test_path = argv[argc - 1];
@@ -165,27 +182,62 @@ int Train(int argc, char* argv[]) {
   if (!ReadFile(test_path, &test)) { printf("Can not open: %s\n", test_path.c_str()); return Help(); }
   const clock_t start = clock();
   gmixb::Gpu gpu(0);
-  gmx_model* from = nullptr;
-  if (!ckpt.empty() && !(from = LoadModel(gpu.ctx(), ckpt, train.size()))) return -1;
-  const void *sp, *lp;
-  uint64_t sl, ll;
-  int rc = gmx_train_checkpoint(gpu.ctx(), from, train.data(), train.size(), &sp, &sl, &lp, &ll);
-  if (from) gmx_model_free(from);
-  if (rc != 0) { printf("%s\n", gmx_last_error(gpu.ctx())); return -1; }
+  gmx_ctx* ctx = gpu.ctx();
+  const uint64_t n = train.size(), percent = 1 + n / 100;
+  std::vector<uint64_t> cuts;   // part k covers bytes [cuts[k-1], cuts[k])
+  for (uint64_t pos = 1; pos < n; ++pos) if (pos % percent == 0 && (pos / percent) % 2 == 0) cuts.push_back(pos + 1);
+  if (cuts.empty() || cuts.back() != n) cuts.push_back(n);
+  std::filesystem::create_directory("analysis");
   std::filesystem::create_directory("data");
-  if (!WriteFile("data/trained_checkpoint.short", (const uint8_t*)sp, sl) || !WriteFile("data/trained_checkpoint.long", (const uint8_t*)lp, ll)) {
+  std::ofstream metrics("analysis/training.tsv", std::ios::out);
+  metrics << "bytes\ttrain_entropy\ttest_entropy" << std::endl;
+  std::vector<uint8_t> tmp, part_out(gmx_compress_bound(n) + 16), test_out(gmx_compress_bound(test.size()) + 16), sh, lo;
+  gmx_model* cur = nullptr;
+  const uint64_t longest_new = std::max<uint64_t>(n, test.size()) + 16;
+  if (!ckpt.empty() && !(cur = LoadModel(ctx, ckpt, longest_new))) return -1;
+  gmx_coder_state coder{0, 0xffffffffu, 0};
+  double train_entropy = 0;
+  uint64_t begin = 0;
+  const int analysis = (8 * n / 1000) > 0;   // p.EnableAnalysis(8 * input_bytes / 1000), :268
+  for (size_t k = 0; k < cuts.size(); ++k) {
+    const uint64_t end = cuts[k], len = end - begin;
+    std::vector<uint8_t> piece(train.begin() + begin, train.begin() + end);
+    std::vector<float> probs(len * 8 + 1);
+    const void *sp, *lp;
+    uint64_t sl, ll, out_len = 0;
+    gmx_coder_state next;
+    const int rc = gmx_compress_part(ctx, cur, k == 0 ? nullptr : &coder, k == 0, n, end == n, analysis, piece.data(), len, part_out.data(), part_out.size(),
+                                     &out_len, &next, &sp, &sl, &lp, &ll, probs.data());
+    if (rc != 0) { printf("%s\n", gmx_last_error(ctx)); return -1; }
+    coder = next;
+    tmp.insert(tmp.end(), part_out.begin(), part_out.begin() + out_len);
+    train_entropy += SumLog2(piece, probs);
+    sh.assign((const uint8_t*)sp, (const uint8_t*)sp + sl);
+    lo.assign((const uint8_t*)lp, (const uint8_t*)lp + ll);
+    if (cur) gmx_model_free(cur);
+    cur = nullptr;
+    if (gmx_model_load(ctx, sh.data(), sh.size(), lo.data(), lo.size(), longest_new, 0, &cur) != 0) { printf("%s\n", gmx_last_error(ctx)); return -1; }
+    const uint64_t pos = end - 1;
+    printf("\rtraining: %lld%%", (long long)(pos / percent));
+    fflush(stdout);
+    if (pos % percent == 0 && (pos / percent) % 2 == 0 && pos != 0) {   // score the test file on a copy (:288-311)
+      std::vector<float> tprobs(test.size() * 8 + 1);
+      uint64_t tl = 0;
+      if (gmx_compress_part(ctx, cur, nullptr, 0, test.size(), 1, 0, test.data(), test.size(), test_out.data(), test_out.size(), &tl, nullptr,
+                            nullptr, nullptr, nullptr, nullptr, tprobs.data()) != 0) { printf("%s\n", gmx_last_error(ctx)); return -1; }
+      const double test_entropy = SumLog2(test, tprobs);
+      metrics << std::fixed << std::setprecision(5) << pos << "\t" << -train_entropy / pos << "\t" << -test_entropy / test.size() << std::endl;
+    }
+    begin = end;
+  }
+  if (cur) gmx_model_free(cur);
+  printf("\rtraining cross entropy: %.4f\n", n ? -train_entropy / n : 0.0);
+  if (!WriteFile("data/tmp", tmp.data(), tmp.size()) || !WriteFile("data/trained_checkpoint.short", sh.data(), sh.size()) ||
+      !WriteFile("data/trained_checkpoint.long", lo.data(), lo.size())) {
     printf("Can not write data/trained_checkpoint\n");
     return -1;
   }
-  gmx_model* trained = nullptr;
-  if (gmx_model_load(gpu.ctx(), sp, sl, lp, ll, test.size(), 0, &trained) != 0) { printf("%s\n", gmx_last_error(gpu.ctx())); return -1; }
-  Batch b;
-  const bool ok = RunBatch(gpu.ctx(), true, test, {0, test.size()}, &b, trained);
-  gmx_model_free(trained);
-  if (!ok) return -1;
-  printf("trained on %zu bytes -> data/trained_checkpoint (.short %llu B, .long %llu B)\n", train.size(), (unsigned long long)sl, (unsigned long long)ll);
-  printf("test cross entropy: %.4f\n", test.empty() ? 0.0 : 8.0 * (double)(b.out_len[0] - 5) / test.size());
-  printf("%1.2f s.\n", ((double)clock() - start) / CLOCKS_PER_SEC);
+  printf("%zu bytes -> %zu bytes in %1.2f s.\n", train.size(), tmp.size(), ((double)clock() - start) / CLOCKS_PER_SEC);
   return 0;
 }
 

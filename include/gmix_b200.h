@@ -170,7 +170,8 @@ int gmx_compress_trace(gmx_ctx* ctx, const uint8_t* in, uint64_t n, uint8_t* out
 typedef struct { uint32_t x1, x2, x; } gmx_coder_state;
 int gmx_compress_part(gmx_ctx* ctx, const gmx_model* from, const gmx_coder_state* coder_in, int write_header, uint64_t total_len, int last,
                       int analysis, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_len, gmx_coder_state* coder_out,
-                      const void** short_blob, uint64_t* short_len, const void** long_blob, uint64_t* long_len);
+                      const void** short_blob, uint64_t* short_len, const void** long_blob, uint64_t* long_len,
+                      float* probs /* optional: 8 * n values, what Predictor::Predict returned for every bit of the part */);
 int gmx_decompress_part(gmx_ctx* ctx, const gmx_model* from, const gmx_coder_state* coder_in, int analysis, const uint8_t* in, uint64_t n_in,
                         uint64_t out_bytes, uint8_t* out, uint64_t* in_consumed, gmx_coder_state* coder_out,
                         const void** short_blob, uint64_t* short_len, const void** long_blob, uint64_t* long_len);

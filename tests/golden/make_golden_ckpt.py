@@ -41,3 +41,18 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def make_training_golden():
+    """`gmix -t text1k.in short124.in` (RunTraining runner-utils.cpp:223-322, ~200 s): analysis/training.tsv, data/tmp and
+    the md5 of data/trained_checkpoint.long -> train_text1k_short124.*"""
+    import hashlib
+    import json
+    with tempfile.TemporaryDirectory() as d:
+        subprocess.run([REF_GMIX, "-t", os.path.join(HERE, "text1k.in"), os.path.join(HERE, "short124.in")], cwd=d, check=True, capture_output=True)
+        shutil.copy(os.path.join(d, "analysis", "training.tsv"), os.path.join(HERE, "train_text1k_short124.training.tsv"))
+        shutil.copy(os.path.join(d, "data", "tmp"), os.path.join(HERE, "train_text1k_short124.tmp"))
+        blob = open(os.path.join(d, "data", "trained_checkpoint.long"), "rb").read()
+        json.dump({"long_md5": hashlib.md5(blob).hexdigest(), "long_bytes": len(blob),
+                   "made_by": "oracle/_ref/gmix -t tests/golden/text1k.in tests/golden/short124.in (unmodified reference, strict build)"},
+                  open(os.path.join(HERE, "train_text1k_short124.json"), "w"), indent=1)

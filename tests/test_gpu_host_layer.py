@@ -140,3 +140,19 @@ def test_runner_chunked_mode_shards_over_all_visible_gpus(tmp_path, gpu_ctx):
         env = dict(os.environ, GMIXB200_GPUS="1")
         subprocess.run([RUNNER, "-C", "3000", str(src), cont + "1"], check=True, env=env)
         assert open(cont + "1", "rb").read() == blob
+
+
+def test_training_mode_reproduces_the_reference_metrics(tmp_path):
+    """`gmixb200 -t train test` against `gmix -t` of the unmodified reference (fixtures: tests/golden/make_golden_ckpt.py
+    make_training_golden): the periodic test-file scores on a copy of the predictor (analysis/training.tsv, every number),
+    the coded training stream (data/tmp) and the final long-term memory."""
+    import hashlib
+    import json
+    want = json.load(open(os.path.join(GOLD, "train_text1k_short124.json")))
+    r = subprocess.run([RUNNER, "-t", os.path.join(GOLD, "text1k.in"), os.path.join(GOLD, "short124.in")], cwd=str(tmp_path), capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert (tmp_path / "analysis" / "training.tsv").read_text() == open(os.path.join(GOLD, "train_text1k_short124.training.tsv")).read()
+    assert (tmp_path / "data" / "tmp").read_bytes() == open(os.path.join(GOLD, "train_text1k_short124.tmp"), "rb").read()
+    blob = (tmp_path / "data" / "trained_checkpoint.long").read_bytes()
+    assert len(blob) == want["long_bytes"] and hashlib.md5(blob).hexdigest() == want["long_md5"]
