@@ -77,7 +77,7 @@ def parse_args():
     ap.add_argument("--verify", type=int, default=1, help="streams per rank checked by a GPU decompress round trip after timing")
     ap.add_argument("--no-generate", action="store_true", help="skip the configs[3] leg (batched generation from a checkpoint)")
     ap.add_argument("--gen-train-bytes", type=int, default=65536, help="bytes of the enwik-shaped corpus the generation checkpoint is trained on")
-    ap.add_argument("--gen-prompts", type=int, default=0, help="prompts per GPU for the generation leg (0 = one wave of resident streams)")
+    ap.add_argument("--gen-prompts", type=int, default=8192, help="prompts per GPU for the generation leg (BASELINE.json configs[3]: 8192; 0 = one wave of resident streams)")
     ap.add_argument("--gen-bytes", type=int, default=1024)
     ap.add_argument("--workload", default="chunks", choices=["chunks", "enwik"],
                     help="chunks = configs[1] (default, the metric's configuration); enwik = configs[4]: --chunks streams of --chunk-bytes "
@@ -495,8 +495,10 @@ def run_ours(args):
                     "checkpoint": f"written on the GPU after {T} B of the enwik-shaped corpus ({train_s:.1f} s), reference format "
                                   f"(.short {len(ck_short)} B, .long {len(ck_long)} B), loaded back through gmx_model_load",
                     "arena_mib_per_stream": model.arena_bytes >> 20,
-                    "workload": "configs[3] at reduced scale: one wave of prompts, checkpoint trained on 64 KiB instead of 1 MB; host buffers, "
-                                "H2D of prompts + draws and D2H of samples inside the timed region"}
+                    "resident_prompts": ctx.resident_streams,
+                    "workload": f"configs[3]: {npr} prompts x {G} B per GPU from a checkpoint trained on {T} B (BASELINE.json: 1 MB; stated reduction), every "
+                                "stream an overlay of the shared model (no clone of its tables); host buffers, H2D of prompts + draws and D2H of samples "
+                                "inside the timed region"}
         model.close()
         ctx.set_cuda_stream(stream.cuda_stream)
 

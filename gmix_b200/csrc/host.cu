@@ -40,6 +40,7 @@ struct gmx_ctx {
   uint64_t cfg_max_len = 0;
   uint32_t cfg_max_resident = 0;
   const gmx_model* cfg_model = nullptr;   // arenas currently use this model's layout (streams start from its checkpoint)
+  uint64_t cfg_ov_learn = 0, cfg_ov_new = 0;   // != 0: ... in overlay mode, sized for this many learned / new bytes per stream
   std::vector<uint8_t> ck_short, ck_long; // last checkpoint written through this ctx (gmx_train_checkpoint, gmx_pred_write_checkpoint)
   uint32_t n_arenas = 0;
   gmx::ArenaLayout layout;
@@ -77,6 +78,7 @@ struct gmx_model {
   uint64_t max_new_bytes = 0;
   uint8_t* d_arena = nullptr;
   uint32_t* d_state = nullptr;
+  gmx::ArenaLayout* d_layout = nullptr;   // the model's layout on the device (overlay-mode streams read the model's arena through it)
 };
 
 // Per-call options of RunDevice beyond the stream slices.
@@ -85,6 +87,7 @@ struct RunOpts {
   int analysis = -1;
   uint32_t* d_final_state = nullptr;
   uint32_t gen_bytes = 0; float temperature = 1.0f; const float* d_rand_u = nullptr; uint64_t rand_stride = 0;
+  uint64_t overlay_learn = 0;   // generation: longest prompt (the bytes a stream learns)
   uint64_t* d_bit_trace = nullptr; float* d_pred_trace = nullptr;
   // one stream coded in parts (gmx_compress_part / gmx_decompress_part)
   uint32_t part = 0, part_header = 0, part_last = 0; uint64_t part_total = 0;
@@ -153,6 +156,7 @@ void FreeArenas(gmx_ctx* c) {
   c->n_roomy = 0;
   c->cfg_max_len = 0;
   c->cfg_model = nullptr;
+  c->cfg_ov_learn = c->cfg_ov_new = 0;
 }
 
 bool Retryable(uint32_t st) {
@@ -207,12 +211,14 @@ int RetryInRoomyArenas(gmx_ctx* c, int mode, gmx::StreamParams P, uint32_t n, ui
   return Launch(c, mode, P, P.n_streams < c->n_roomy ? P.n_streams : c->n_roomy);
 }
 
-// Arenas sized by a loaded model's layout (every stream is a clone of the model's parked stream).
-int ConfigureForModel(gmx_ctx* c, const gmx_model* m) {
-  if (c->cfg_model == m && c->n_arenas) return 0;
+// Arenas sized by a loaded model's layout (every stream is a clone of the model's parked stream), or - ov_new != 0 - overlay
+// arenas on top of the model's arena (MakeOverlayLayout: the model's tables are shared, a stream keeps its changes only).
+int ConfigureForModel(gmx_ctx* c, const gmx_model* m, uint64_t ov_learn = 0, uint64_t ov_new = 0) {
+  if (c->cfg_model == m && c->n_arenas && ((ov_new == 0 && c->cfg_ov_new == 0) || (ov_new != 0 && c->cfg_ov_learn >= ov_learn && c->cfg_ov_new >= ov_new))) return 0;
   const uint32_t max_resident = c->cfg_max_resident;
   FreeArenas(c);
-  c->layout = m->layout;
+  c->layout = ov_new ? gmx::MakeOverlayLayout(m->layout, m->pre, ov_learn, ov_new) : m->layout;
+  c->cfg_ov_learn = ov_learn; c->cfg_ov_new = ov_new;
   int rc = EnsureDecay(c, m->pre.steps / 8 + m->max_new_bytes + 2);
   if (rc) return rc;
   int per_sm = 0;
@@ -252,7 +258,9 @@ int RunDevice(gmx_ctx* c, int mode, const uint8_t* d_in, const uint64_t* d_in_of
     if (o.model->ctx != c) return Fail(c, GMX_E_ARG, "model belongs to another context");
     if (max_len > o.model->max_new_bytes) return Fail(c, GMX_E_ARG, "stream of %llu bytes exceeds the max_new_bytes (%llu) the model was loaded with",
                                                        (unsigned long long)max_len, (unsigned long long)o.model->max_new_bytes);
-    int rc = ConfigureForModel(c, o.model);
+    // generation never writes a checkpoint of its streams: they run as overlays of the shared model
+    const bool overlay = mode == gmx::MODE_GENERATE && !o.d_final_state;
+    int rc = overlay ? ConfigureForModel(c, o.model, o.overlay_learn ? o.overlay_learn : max_len, max_len) : ConfigureForModel(c, o.model);
     if (rc) return rc;
   } else if (max_len > c->cfg_max_len || c->n_arenas == 0 || c->cfg_model) {
     int rc = gmx_configure(c, max_len > c->cfg_max_len || c->cfg_model ? max_len : c->cfg_max_len, c->cfg_max_resident);
@@ -268,7 +276,7 @@ int RunDevice(gmx_ctx* c, int mode, const uint8_t* d_in, const uint64_t* d_in_of
   P.analysis = o.analysis; P.final_state = o.d_final_state;
   P.gen_bytes = o.gen_bytes; P.temperature = o.temperature; P.rand_u = o.d_rand_u; P.rand_stride = o.rand_stride;
   P.part = o.part; P.part_header = o.part_header; P.part_last = o.part_last; P.part_total = o.part_total; P.coder_in = o.d_coder_in; P.coder_out = o.d_coder_out;
-  if (o.model) { P.tmpl_arena = o.model->d_arena; P.tmpl_state = o.model->d_state; }
+  if (o.model) { P.tmpl_arena = o.model->d_arena; P.tmpl_state = o.model->d_state; P.tmpl_layout = c->layout.ov ? o.model->d_layout : nullptr; }
   const uint32_t grid = n < c->n_arenas ? n : c->n_arenas;
   {
     int rc = Reserve(c, c->b_usage, (size_t)n * 32);
@@ -553,6 +561,8 @@ int gmx_model_load(gmx_ctx* c, const void* short_blob, uint64_t short_len, const
   }
   if (!ok) { delete m; return Fail(c, GMX_E_ARG, "checkpoint: %s", err.c_str()); }
   if (cudaMalloc(&m->d_arena, m->layout.total) != cudaSuccess || cudaMalloc(&m->d_state, sizeof(gmx::StreamSmem)) != cudaSuccess ||
+      cudaMalloc(&m->d_layout, sizeof(gmx::ArenaLayout)) != cudaSuccess ||
+      cudaMemcpy(m->d_layout, &m->layout, sizeof(gmx::ArenaLayout), cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(m->d_arena, arena.data(), m->layout.total, cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(m->d_state, state.data(), sizeof(gmx::StreamSmem), cudaMemcpyHostToDevice) != cudaSuccess) {
     const char* what = cudaGetErrorString(cudaGetLastError());
@@ -569,6 +579,7 @@ void gmx_model_free(gmx_model* m) {
   if (m->ctx->cfg_model == m) FreeArenas(m->ctx);
   if (m->d_arena) cudaFree(m->d_arena);
   if (m->d_state) cudaFree(m->d_state);
+  if (m->d_layout) cudaFree(m->d_layout);
   delete m;
 }
 
@@ -591,7 +602,7 @@ int gmx_generate_batch_device(gmx_ctx* c, const gmx_model* model, const uint8_t*
                               uint64_t* d_out_len, uint32_t* d_status, uint64_t max_prompt_len) {
   if (!c || !model) return GMX_E_ARG;
   if (!d_rand_u) return Fail(c, GMX_E_ARG, "null pointer argument");
-  RunOpts o; o.model = model; o.gen_bytes = out_bytes; o.d_rand_u = d_rand_u; o.rand_stride = rand_stride;
+  RunOpts o; o.model = model; o.gen_bytes = out_bytes; o.d_rand_u = d_rand_u; o.rand_stride = rand_stride; o.overlay_learn = max_prompt_len;
   o.temperature = temperature < (float)0.001 ? (float)0.001 : temperature;   // runner-utils.cpp:170
   return RunDevice(c, gmx::MODE_GENERATE, d_prompts, d_prompt_off, n, d_out, nullptr, d_out_len, d_status, max_prompt_len + out_bytes, o);
 }

@@ -164,6 +164,59 @@ inline ArenaLayout MakeLayout(uint64_t max_len, bool roomy = false, const Preloa
   return L;
 }
 
+// Arena of a stream that starts from a loaded model in OVERLAY mode (ArenaLayout::ov, stream_kernel.cuh): the model's
+// tables, weight-set pool and history are shared read-only; this arena holds the overlay map, the local pool / history and
+// private copies of the densely updated state. base = the model's layout, pre = what the model holds, learn_bytes = bytes
+// the stream learns at most (the prompt), new_bytes = bytes it adds in total (prompt + samples). Sized for the worst case:
+// overlay entries = every table write (41 Indirect states per learned bit, 6 Match pointers per learned byte, one
+// IndirectHash update per table and byte, one directory entry per new or changed weight set); weight sets = at most 27
+// byte-gated + 6 x 8 bit-gated or longest-match-gated ones change per learned byte.
+inline ArenaLayout MakeOverlayLayout(const ArenaLayout& base, const Preload& pre, uint64_t learn_bytes, uint64_t new_bytes) {
+  ArenaLayout L;
+  memset(&L, 0, sizeof(L));
+  uint64_t off = 0;
+  auto take = [&](uint64_t bytes) { uint64_t o = off; off = AlignUp(off + bytes, 256); return o; };
+  L.ov = 1;
+  for (int k = 0; k < NIND; ++k) { L.ind_size[k] = base.ind_size[k]; L.ind_sid[k] = (uint8_t)(OV_SID_IND + k); }
+  for (int k = 0; k < NMATCH; ++k) L.match_sid[k] = (uint8_t)(OV_SID_MATCH + k);
+  for (int k = 0; k < NIH; ++k) L.ih_sid[k] = (uint8_t)(OV_SID_IH + k);
+  const uint64_t sets = 75 * learn_bytes + 64;
+  const uint64_t entries = learn_bytes * (8 * NIND + NMATCH) + new_bytes * NIH + sets + 64;
+  const uint64_t cap = Pow2Ceil(entries * 4 / 3 + 64);
+  L.sparse_mask = (uint32_t)(cap - 1);
+  L.sparse_limit = (uint32_t)(cap / 4 * 3);
+  L.sparse = take(cap * 8);
+  L.ind_pred = take((uint64_t)NIND * 512 * 4);
+  L.match_pred = take(NMATCH * 256 * 4);
+  L.match_cnt = take(NMATCH * 256 * 4);
+  L.base_hist = (uint32_t)pre.history_bytes;
+  L.history_cap = pre.history_bytes + learn_bytes + 8;
+  L.history = take(learn_bytes + 8);
+  L.base_sets = (uint32_t)(pre.mixer_sets + 1);
+  L.mix_pool_sets = (uint32_t)(L.base_sets + sets);
+  L.mix_set_stride = base.mix_set_stride;
+  L.mix_pool = take(sets * L.mix_set_stride * 4);
+  const uint64_t wsz = (uint64_t)L_WSIZE * 4;
+  L.l_w = take(wsz); L.l_m = take(wsz); L.l_v = take(wsz);
+  L.l_gb = take(8 * 3 * L_CELLS * 4);
+  L.l_wout = take((uint64_t)L_HORIZON * L_HID * L_NOUT * 4);
+  L.l_lin = take((uint64_t)L_HORIZON * (L_NIN + 1) * 4);
+  L.l_out = take((uint64_t)L_HORIZON * L_NOUT * 4);
+  L.l_gstate = take(3ull * L_HORIZON * L_CELLS * 4);
+  L.l_norm = take(3ull * L_HORIZON * L_CELLS * 4);
+  L.l_ivar = take(3ull * L_HORIZON * 4);
+  L.l_tanh = take((uint64_t)L_HORIZON * L_CELLS * 4);
+  L.l_ig = take((uint64_t)L_HORIZON * L_CELLS * 4);
+  L.l_last = take((uint64_t)L_HORIZON * L_CELLS * 4);
+  L.l_errh = take(3ull * L_HORIZON * L_CELLS * 4);
+  L.l_wt = take(3ull * L_CELLS * L_CELLS * 4);
+  L.p_state = take(sizeof(PpmdState));
+  L.p_mask = base.p_mask; L.p_text_cap = base.p_text_cap; L.p_units_cap = base.p_units_cap;   // the model's window geometry (sized for max_new_bytes more)
+  L.p_heap = take((uint64_t)L.p_mask + 1);
+  L.total = off;
+  return L;
+}
+
 // decay[s] = (float)(0.9 / pow(0.0000001 * s + 0.8, 0.8)) — mixer.cpp:111, a function of the mixer's
 // global step counter only; evaluated with the HOST libm exactly as the reference does.
 inline void FillDecayTable(std::vector<float>& t, uint64_t n) {

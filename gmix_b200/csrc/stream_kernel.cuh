@@ -103,7 +103,16 @@ struct ArenaLayout {
   // PPMd
   uint64_t p_state; uint64_t p_heap; uint32_t p_mask; uint32_t p_text_cap; uint32_t p_units_cap;  // see ppmd.cuh
   uint64_t total;             // arena bytes
+  // Overlay mode (ov != 0; streams that start from a loaded model WITHOUT cloning its tables: batched generation). The
+  // big tables then stay in the model's arena, read-only and shared by every stream; this arena holds what the stream
+  // changes: every table (all of them have a sid here, mixer directories use sid OV_SID_MIX + m) is written to the
+  // shared sparse map of THIS arena and looked up there first, weight sets the stream creates or changes live in a
+  // local pool (ids >= base_sets), history bytes it appends behind base_hist. Small / dense-updated state (logit maps,
+  // Match predictions, LSTM, PPMd) is a private copy made at stream start.
+  uint32_t ov, base_sets, base_hist, ov_pad;
 };
+enum : uint32_t { OV_SID_IND = 1, OV_SID_MATCH = OV_SID_IND + NIND, OV_SID_IH = OV_SID_MATCH + NMATCH, OV_SID_MIX = OV_SID_IH + NIH };
+static_assert(OV_SID_MIX + NMIX <= 128, "overlay table ids must fit the 7 bits above the 25-bit index of a sparse key");
 
 struct StreamParams {
   const uint8_t* in; const uint64_t* in_off;     // n_streams + 1 offsets
@@ -125,6 +134,7 @@ struct StreamParams {
   // Start every stream from a parked stream (a loaded checkpoint: Predictor::ReadCheckpoint predictor.cpp:406-420)
   // instead of from scratch: arena image of layout->total bytes + StreamSmem image. null = from scratch.
   const uint8_t* tmpl_arena; const uint32_t* tmpl_state;
+  const ArenaLayout* tmpl_layout;   // layout of tmpl_arena when it differs from `layout` (overlay mode, ArenaLayout::ov), else null
   uint32_t* final_state;     // optional: the stream's StreamSmem is parked here at its end (n_streams x sizeof(StreamSmem)), or null
   int32_t analysis;          // -1: what the reference runner does for this mode; 0/1: forced (Predictor::EnableAnalysis)
   // generation (runner_utils::RunGeneration runner-utils.cpp:158-221): `in` holds the prompts, out[sid * gen_bytes ..] the samples
@@ -190,8 +200,9 @@ struct StreamSmem {
   alignas(16) float w[WTOTAL];
   alignas(16) float xe[NPRED + NL0 + 2];    // layer-0 input vector: predictions (inactive ones zeroed) | layer-0 outputs
   uint32_t set_steps[NMIX], max_steps[NMIX], set_idx[NMIX], set_pool[NMIX];
-  uint32_t swap_old[NMIX], swap_new[NMIX], nswap;   // queued set swaps of this bit
+  uint32_t swap_old[NMIX], swap_new[NMIX], swap_oldidx[NMIX], nswap;   // queued set swaps of this bit
   uint8_t swap_m[NMIX + 3], shrink[NMIX + 3];
+  uint8_t set_dirty[NMIX + 3];               // the staged set has learned since it was staged (its pool record is stale)
   float upd[NMIX];
   uint32_t pool_next;
   // indirect -- bit role
@@ -250,6 +261,8 @@ struct SparseMap { unsigned long long* tab; uint32_t mask; };
 struct Arena {
   uint8_t* base;
   const ArenaLayout* L;
+  const uint8_t* base0 = nullptr;       // overlay mode: the model's arena and its layout (global memory, read-only)
+  const ArenaLayout* BL = nullptr;
   template <typename T> GMX_DEV T* at(uint64_t off) const { return (T*)(base + off); }
   GMX_DEV SparseMap map() const { return SparseMap{(unsigned long long*)(base + L->sparse), L->sparse_mask}; }
 };
@@ -333,6 +346,76 @@ GMX_DEV inline int WOff(int m) { return m < NL0 ? m * WSTRIDE0 : NL0 * WSTRIDE0 
 GMX_DEV inline int MixerNW(int m) { return m < NL0 ? NPRED + m : m < NL0 + NL1 ? NL0 + (m - NL0) + 1 : NL0 + NL1 + 1; }
 
 
+GMX_DEV inline void SetError(StreamSmem& s, uint32_t code) { atomicCAS(&s.error, 0u, code); }
+
+// ---- overlay mode: what the model's arena (base) holds for a table entry this stream has not written -------------
+GMX_DEV inline uint32_t BaseInd(const Arena& A, int k, uint32_t slot) {   // Indirect state {ns | rm << 8}; never written = {255, 0}
+  const ArenaLayout& B = *A.BL;
+  if (B.ind_sid[k]) {
+    unsigned long long e;
+    SparseFind(SparseMap{(unsigned long long*)(A.base0 + B.sparse), B.sparse_mask}, SparseKey(B.ind_sid[k], slot), &e);
+    return e ? (uint32_t)e & 0xffffu : 0x00ffu;
+  }
+  return ((const uint16_t*)(A.base0 + B.ind_tab[k]))[slot];
+}
+GMX_DEV inline uint32_t BaseMatch(const Arena& A, int k, uint32_t idx) {
+  const ArenaLayout& B = *A.BL;
+  if (B.match_sid[k]) return SparseGet(SparseMap{(unsigned long long*)(A.base0 + B.sparse), B.sparse_mask}, SparseKey(B.match_sid[k], idx));
+  return ((const uint32_t*)(A.base0 + B.match_tab[k]))[idx];
+}
+GMX_DEV inline uint32_t BaseIH(const Arena& A, int k, uint32_t idx) {
+  const ArenaLayout& B = *A.BL;
+  if (B.ih_sid[k]) return SparseGet(SparseMap{(unsigned long long*)(A.base0 + B.sparse), B.sparse_mask}, SparseKey(B.ih_sid[k], idx));
+  return ((const uint32_t*)(A.base0 + B.ih_tab[k]))[idx];
+}
+// Mixer directory: pool id of the weight set of mixer m's gate context idx (0 = none yet)
+GMX_DEV inline uint32_t DirGet(const Arena& A, int m, uint32_t idx) {
+  const ArenaLayout& L = *A.L;
+  if (!L.ov) return A.at<uint32_t>(L.mix_dir[m])[idx];
+  unsigned long long e;
+  SparseFind(A.map(), SparseKey(OV_SID_MIX + m, idx), &e);
+  return e ? (uint32_t)e : ((const uint32_t*)(A.base0 + A.BL->mix_dir[m]))[idx];
+}
+GMX_DEV inline void DirSet(StreamSmem& s, const Arena& A, int m, uint32_t idx, uint32_t id) {
+  const ArenaLayout& L = *A.L;
+  if (!L.ov) A.at<uint32_t>(L.mix_dir[m])[idx] = id;
+  else SparseSet(A.map(), &s.sparse_used, L.sparse_limit, &s.error, SparseKey(OV_SID_MIX + m, idx), id);
+}
+// Pool record of weight set `id` (float4 units): the model's pool below base_sets in overlay mode (read-only)
+GMX_DEV inline float4* PoolRec(const Arena& A, uint32_t id) {
+  const ArenaLayout& L = *A.L;
+  const uint32_t stride4 = L.mix_set_stride / 4;
+  if (L.ov && id < L.base_sets) return (float4*)(A.base0 + A.BL->mix_pool) + (size_t)id * stride4;
+  return A.at<float4>(L.mix_pool) + (size_t)(id - (L.ov ? L.base_sets : 0u)) * stride4;
+}
+GMX_DEV inline uint32_t HistByte(const Arena& A, uint32_t pos) {
+  const ArenaLayout& L = *A.L;
+  if (L.ov) return pos < L.base_hist ? (A.base0 + A.BL->history)[pos] : A.at<uint8_t>(L.history)[pos - L.base_hist];
+  return A.at<uint8_t>(L.history)[pos];
+}
+// One staged weight set goes back to its pool record; all 32 lanes with the same arguments. `idx` = the gate context it
+// belongs to. A set that has not learned since it was staged is skipped (its record is current). Overlay mode: a changed
+// set of the model moves to a fresh local record and the overlay directory follows.
+GMX_DEV inline void WriteBackSet(StreamSmem& s, const Arena& A, int m, uint32_t old, uint32_t idx, int lane) {
+  if (!old || !s.set_dirty[m]) return;
+  const ArenaLayout& L = *A.L;
+  uint32_t id = old;
+  if (L.ov && old < L.base_sets) {
+    if (lane == 0) {
+      id = atomicAdd(&s.pool_next, 1u);
+      if (id >= L.mix_pool_sets) { SetError(s, GMX_ERR_MIXER_POOL); id = 0; }
+      else DirSet(s, A, m, idx, id);
+    }
+    id = __shfl_sync(0xffffffffu, id, 0);
+    if (!id) return;
+  }
+  if (lane <= (MixerNW(m) + 3) / 4) {
+    float4* rec = PoolRec(A, id);
+    if (lane == 0) rec[0] = make_float4(u2f(s.set_steps[m]), 0.0f, 0.0f, 0.0f);
+    else rec[lane] = ((const float4*)(s.w + WOff(m)))[lane - 1];
+  }
+}
+
 // ---- role groups -----------------------------------------------------------------------------------
 // A role is N consecutive threads (a multiple of 32); `id` is its named barrier (0 is left to __syncthreads).
 template <int N>
@@ -348,7 +431,6 @@ GMX_DEV inline void GroupSync(int id) {
 }
 enum : int { BAR_BIT = 1, BAR_LSTM = 2 };
 
-GMX_DEV inline void SetError(StreamSmem& s, uint32_t code) { atomicCAS(&s.error, 0u, code); }
 GMX_DEV inline uint32_t VolatileLoad(const uint32_t* p) { return *(const volatile uint32_t*)p; }
 GMX_DEV inline void FenceBlock() {
 #if defined(__CUDA_ARCH__)
@@ -582,15 +664,41 @@ template <int NT>
 GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, int tid) {
   const ArenaLayout& L = *A.L;
   if (P.tmpl_arena) {   // clone of a parked stream: arena image, then everything of StreamSmem behind the launch tables
-    const uint4* src = (const uint4*)P.tmpl_arena;
-    uint4* dst = (uint4*)A.base;
-    const uint64_t n16 = L.total / 16;
-    for (uint64_t i = tid; i < n16; i += NT) dst[i] = src[i];
+    if (L.ov) {
+      // overlay mode: only the state the stream updates densely is copied (every region is a 256-byte multiple apart from
+      // its tail, all offsets are 256-byte aligned: 16-byte copies); the overlay map starts empty
+      const ArenaLayout& B = *P.tmpl_layout;
+      auto copy = [&](uint64_t dst_off, uint64_t src_off, uint64_t bytes) {
+        const uint4* src = (const uint4*)(P.tmpl_arena + src_off);
+        uint4* dst = (uint4*)(A.base + dst_off);
+        for (uint64_t i = tid; i < (bytes + 15) / 16; i += NT) dst[i] = src[i];
+      };
+      copy(L.ind_pred, B.ind_pred, (uint64_t)NIND * 512 * 4);
+      copy(L.match_pred, B.match_pred, NMATCH * 256 * 4); copy(L.match_cnt, B.match_cnt, NMATCH * 256 * 4);
+      copy(L.l_w, B.l_w, (uint64_t)L_WSIZE * 4); copy(L.l_m, B.l_m, (uint64_t)L_WSIZE * 4); copy(L.l_v, B.l_v, (uint64_t)L_WSIZE * 4);
+      copy(L.l_gb, B.l_gb, 8 * 3 * L_CELLS * 4);
+      copy(L.l_wout, B.l_wout, (uint64_t)L_HORIZON * L_HID * L_NOUT * 4);
+      copy(L.l_lin, B.l_lin, (uint64_t)L_HORIZON * (L_NIN + 1) * 4); copy(L.l_out, B.l_out, (uint64_t)L_HORIZON * L_NOUT * 4);
+      copy(L.l_gstate, B.l_gstate, 3ull * L_HORIZON * L_CELLS * 4); copy(L.l_norm, B.l_norm, 3ull * L_HORIZON * L_CELLS * 4);
+      copy(L.l_ivar, B.l_ivar, 3ull * L_HORIZON * 4);
+      copy(L.l_tanh, B.l_tanh, (uint64_t)L_HORIZON * L_CELLS * 4); copy(L.l_ig, B.l_ig, (uint64_t)L_HORIZON * L_CELLS * 4);
+      copy(L.l_last, B.l_last, (uint64_t)L_HORIZON * L_CELLS * 4);
+      copy(L.p_state, B.p_state, sizeof(PpmdState));
+      copy(L.p_heap, B.p_heap, (uint64_t)L.p_mask + 1);
+      uint4* z = A.at<uint4>(L.sparse);
+      const uint64_t n16 = ((uint64_t)L.sparse_mask + 1) / 2;
+      for (uint64_t i = tid; i < n16; i += NT) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+      const uint4* src = (const uint4*)P.tmpl_arena;
+      uint4* dst = (uint4*)A.base;
+      const uint64_t n16 = L.total / 16;
+      for (uint64_t i = tid; i < n16; i += NT) dst[i] = src[i];
+    }
     constexpr int kFirst = (int)(sizeof(StreamTables) / 4), kWords = (int)(offsetof(StreamSmem, pkt) / 4);
     uint32_t* sw = (uint32_t*)&s;
     for (int i = kFirst + tid; i < kWords; i += NT) sw[i] = P.tmpl_state[i];
     __syncthreads();
-    if (tid == 0) { s.error = 0; s.nswap = 0; s.x1 = 0; s.x2 = 0xffffffffu; s.x = 0; }
+    if (tid == 0) { s.error = 0; s.nswap = 0; s.x1 = 0; s.x2 = 0xffffffffu; s.x = 0; if (L.ov) s.sparse_used = 0; }
   } else {
     for (int k = 0; k < NIND; ++k)
       if (!L.ind_sid[k]) FillWords<NT>(A.at<uint32_t>(L.ind_tab[k]), ((uint64_t)L.ind_size[k] + 1) / 2, 0x00FF00FFu, tid);
@@ -1397,18 +1505,9 @@ GMX_DEV void BitBoundaryA(StreamSmem& s, const Arena& A, int btid) {
   // (0) Nearly every gate context changes with the byte: all staged weight sets go back to the pool at once and the
   // swap phase of this bit fetches all 33 (one warp per set, one float4 per lane).
   {
-    float4* pool = A.at<float4>(L.mix_pool);
-    const uint32_t stride4 = L.mix_set_stride / 4;
     const int lane = btid & 31;
 #pragma unroll 1
-    for (int m = btid >> 5; m < NMIX; m += NB / 32) {
-      const uint32_t old = s.set_pool[m];
-      if (old && lane <= (MixerNW(m) + 3) / 4) {
-        float4* rec = pool + (size_t)old * stride4;
-        if (lane == 0) rec[0] = make_float4(u2f(s.set_steps[m]), 0.0f, 0.0f, 0.0f);
-        else rec[lane] = ((const float4*)(s.w + WOff(m)))[lane - 1];
-      }
-    }
+    for (int m = btid >> 5; m < NMIX; m += NB / 32) WriteBackSet(s, A, m, s.set_pool[m], s.set_idx[m], lane);
   }
   // (1) contexts: 9 intervals, 20 hashed skip contexts, 9 indirect-hash tables
 #pragma unroll 1
@@ -1436,9 +1535,11 @@ GMX_DEV void BitBoundaryA(StreamSmem& s, const Arena& A, int btid) {
         const uint32_t key = SparseKey(sid, s.ih_hash[k] & mask);
         unsigned long long e;
         const uint32_t pos = SparseFind(M, key, &e);
-        SparsePut(M, &s.sparse_used, L.sparse_limit, &s.error, key, pos, e != 0ull,
-                  (uint32_t)((((uint64_t)(uint32_t)e % inner_mod) << 8) + last_byte));
-        s.ctx[C_IH0 + k] = Murmur32(SparseGet(M, SparseKey(sid, oh & mask)));
+        const uint32_t cur = e ? (uint32_t)e : L.ov ? BaseIH(A, k, s.ih_hash[k] & mask) : 0u;
+        SparsePut(M, &s.sparse_used, L.sparse_limit, &s.error, key, pos, e != 0ull, (uint32_t)((((uint64_t)cur % inner_mod) << 8) + last_byte));
+        unsigned long long e2;
+        SparseFind(M, SparseKey(sid, oh & mask), &e2);
+        s.ctx[C_IH0 + k] = Murmur32(e2 ? (uint32_t)e2 : L.ov ? BaseIH(A, k, oh & mask) : 0u);
       } else {
         uint32_t* tab = A.at<uint32_t>(L.ih_tab[k]);
         uint32_t* slot = tab + (s.ih_hash[k] & mask);
@@ -1456,7 +1557,7 @@ GMX_DEV void BitBoundaryB(StreamSmem& s, const Arena& A, uint32_t b, int btid) {
   GroupSync<NB>(BAR_BIT);   // (also orders part A's shared-memory writes when the same threads ran it)
   // Indirect row bases ((ctx << 8) % M, so that slot = (base + bit_context) % M); nothing is staged any more
   for (int k = btid; k < NIND; k += NB) s.ind_base[k] = (s.ctx[s.T.ind[k].ctx] << 8) % L.ind_size[k];
-  for (int m = btid; m < NMIX; m += NB) { s.set_idx[m] = 0xFFFFFFFFu; s.set_pool[m] = 0; }
+  for (int m = btid; m < NMIX; m += NB) { s.set_idx[m] = 0xFFFFFFFFu; s.set_pool[m] = 0; s.set_dirty[m] = 0; }
   GroupSync<NB>(BAR_BIT);
 }
 
@@ -1518,7 +1619,7 @@ GMX_DEV inline void LearnTables(StreamSmem& s, const Arena& A, int bit, int t) {
     }
   } else if (t == NIND + NMATCH && byte_done && longest < 2) {
     if (s.hist_len >= L.history_cap) SetError(s, GMX_ERR_HISTORY_CAP);
-    else A.at<uint8_t>(L.history)[s.hist_len] = (uint8_t)cur;
+    else A.at<uint8_t>(L.history)[s.hist_len - (L.ov ? L.base_hist : 0u)] = (uint8_t)cur;
   }
 }
 
@@ -1530,7 +1631,8 @@ GMX_DEV inline void GateSelect(StreamSmem& s, const Arena& A, int m, uint32_t c)
     const uint32_t q = atomicAdd(&s.nswap, 1u);
     s.swap_m[q] = (uint8_t)m;
     s.swap_old[q] = s.set_pool[m];
-    s.swap_new[q] = A.at<uint32_t>(A.L->mix_dir[m])[idx];
+    s.swap_oldidx[q] = s.set_idx[m];
+    s.swap_new[q] = DirGet(A, m, idx);
     s.set_idx[m] = idx;
   }
 }
@@ -1560,10 +1662,11 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, ui
       if (slot >= M) slot -= M;
       uint32_t e;
       const uint32_t sid = L.ind_sid[k];
-      if (sid) {  // absent == never written == {ns 255, rm 0}
+      if (sid) {  // absent == never written == {ns 255, rm 0} (overlay mode: == what the model's table holds)
         unsigned long long ent;
+        const uint32_t index = slot;
         slot = SparseFind(A.map(), SparseKey(sid, slot), &ent);
-        e = ent ? (uint32_t)ent & 0xffffu : 0x00ffu;
+        e = ent ? (uint32_t)ent & 0xffffu : L.ov ? BaseInd(A, k, index) : 0x00ffu;
         s.ind_found[k] = ent != 0ull;
       } else {
         e = A.at<uint16_t>(L.ind_tab[k])[slot];
@@ -1596,11 +1699,17 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, ui
         if (s.hist_len != 0 && cm == s.hist_len - 1) len = 0;
         if (len < 8) {
           const uint32_t idx = s.ctx[s.T.match[k].ctx] & ((1u << s.T.match[k].log2) - 1);
-          cm = L.match_sid[k] ? SparseGet(A.map(), SparseKey(L.match_sid[k], idx)) : A.at<uint32_t>(L.match_tab[k])[idx];
+          if (L.match_sid[k]) {
+            unsigned long long ent;
+            SparseFind(A.map(), SparseKey(L.match_sid[k], idx), &ent);
+            cm = ent ? (uint32_t)ent : L.ov ? BaseMatch(A, k, idx) : 0u;
+          } else {
+            cm = A.at<uint32_t>(L.match_tab[k])[idx];
+          }
         } else ++cm;
         if (s.hist_len != 0) {
           if (cm >= s.hist_len) { SetError(s, GMX_ERR_MATCH_RANGE); cm = 0; }
-          cbyte = A.at<uint8_t>(L.history)[cm];
+          cbyte = HistByte(A, cm);
         }
         s.m_cur[k] = cm;
         bp = 128;
@@ -1656,29 +1765,20 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, ui
   // +0, exactly the reference's "data == nullptr" output). Pool record = {steps, 0, 0, 0 | weights...}.
   {
     const uint32_t nswap = s.nswap;
-    float4* pool = A.at<float4>(L.mix_pool);
-    const uint32_t stride4 = L.mix_set_stride / 4;
     const int lane = btid & 31;
 #pragma unroll 1
-    for (uint32_t r = btid >> 5; r < nswap; r += NB / 32) {
-      const int m = s.swap_m[r];
-      const uint32_t old = s.swap_old[r];
-      if (old && lane <= (MixerNW(m) + 3) / 4) {
-        float4* rec = pool + (size_t)old * stride4;
-        if (lane == 0) rec[0] = make_float4(u2f(s.set_steps[m]), 0.0f, 0.0f, 0.0f);
-        else rec[lane] = ((const float4*)(s.w + WOff(m)))[lane - 1];
-      }
-    }
+    for (uint32_t r = btid >> 5; r < nswap; r += NB / 32) WriteBackSet(s, A, s.swap_m[r], s.swap_old[r], s.swap_oldidx[r], lane);
     __syncwarp();   // the same warp re-reads swap_* and overwrites the staged sets below
 #pragma unroll 1
     for (uint32_t r = btid >> 5; r < nswap; r += NB / 32) {
       const int m = s.swap_m[r];
       const uint32_t nid = s.swap_new[r];
       if (lane <= (MixerNW(m) + 3) / 4) {
-        const float4* rec = pool + (size_t)nid * stride4;
+        const float4* rec = nid ? PoolRec(A, nid) : nullptr;
         if (lane == 0) {
           if (nid) CpAsync4(&s.set_steps[m], rec); else s.set_steps[m] = 0u;
           s.set_pool[m] = nid;
+          s.set_dirty[m] = 0;
         } else {
           float4* dst = (float4*)(s.w + WOff(m)) + (lane - 1);
           if (nid) CpAsync16(dst, rec + lane); else *dst = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -1825,7 +1925,7 @@ GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int 
       if (s.set_pool[m] == 0) {  // FindOrCreateMixerData mixer.cpp:39-49
         const uint32_t id = atomicAdd(&s.pool_next, 1u);
         if (id >= L.mix_pool_sets) { SetError(s, GMX_ERR_MIXER_POOL); }
-        else { s.set_pool[m] = id; A.at<uint32_t>(L.mix_dir[m])[s.set_idx[m]] = id; }
+        else { s.set_pool[m] = id; DirSet(s, A, m, s.set_idx[m], id); }
       }
       const uint32_t st = s.steps < P.decay_len ? s.steps : P.decay_len - 1;
       float decay = P.decay[st];
@@ -1858,6 +1958,7 @@ GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int 
     const bool shrink = s.shrink[m] != 0;
     const float keep = f_sub(1.0f, 3.0e-6f);
     float* w = s.w + WOff(m);
+    if (lane == 0) s.set_dirty[m] = 1;
     if (m < NL0) {
       // Layer 0: inputs = [90 predictions | outputs of the earlier layer-0 neurons] = s.xe[0 .. nw) (inactive
       // predictions are +0 there and are skipped through the `use` bytes); one float4 per lane covers them all.
@@ -2215,7 +2316,7 @@ __global__ void __launch_bounds__(32 * (WB + WL + 1), MINB) StreamKernel(StreamP
   ProfSmem* prof = prof_mem.get();
   if (WS && tid == 0) { MbarInit(ws.mbar, 1); s.wphase = 0; }
   StageTables<NT>(s, P, tid);
-  Arena A{P.arenas + (uint64_t)blockIdx.x * P.arena_stride, &s.T.L};
+  Arena A{P.arenas + (uint64_t)blockIdx.x * P.arena_stride, &s.T.L, P.tmpl_arena, P.tmpl_layout};
   for (;;) {
     if (tid == 0) next_stream = atomicAdd(P.queue, 1u);
     __syncthreads();

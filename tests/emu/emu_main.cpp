@@ -66,7 +66,9 @@ struct Run {
 };
 
 // mode: gmx::MODE_*; ckpt: optional parsed checkpoint to start from; new_bytes: bytes the stream will add.
-static int Execute(Run& R, int mode, const gmx::ckpt::Image* ckpt, uint64_t new_bytes, gmx::StreamParams& P, bool want_final) {
+// overlay_learn > 0: the stream runs in overlay mode on top of the checkpoint (what gmx_generate_batch does): the checkpoint's
+// arena stays read-only, the stream arena is a MakeOverlayLayout sized for overlay_learn learned bytes.
+static int Execute(Run& R, int mode, const gmx::ckpt::Image* ckpt, uint64_t new_bytes, gmx::StreamParams& P, bool want_final, uint64_t overlay_learn = 0) {
   const bool force_roomy = getenv("EMU_ROOMY") != nullptr;
   bool roomy = force_roomy;
   gmx::Preload pre;
@@ -97,6 +99,15 @@ retry:
       return 1;
     }
     P.tmpl_arena = ta; P.tmpl_state = R.tmpl_state.data();
+    if (overlay_learn) {
+      static gmx::ArenaLayout base;
+      base = R.L;
+      R.L = gmx::MakeOverlayLayout(base, pre, overlay_learn, new_bytes);
+      R.arena.assign(R.L.total + 256, 0xCD);   // nothing in the overlay arena may be assumed zero
+      P.arenas = (uint8_t*)(((uintptr_t)R.arena.data() + 255) & ~(uintptr_t)255); P.arena_stride = R.L.total; P.layout = &R.L;
+      P.tmpl_layout = &base;
+      fprintf(stderr, "overlay arena %llu KiB on top of a %llu KiB model\n", (unsigned long long)(R.L.total >> 10), (unsigned long long)(base.total >> 10));
+    }
   }
   if (want_final) { R.final_state.assign(sizeof(gmx::StreamSmem) / 4 + 4, 0); P.final_state = R.final_state.data(); }
   cuda_emu::RunBlock(EMU_NT, 0, 1, [&] {
@@ -177,7 +188,7 @@ int main(int argc, char** argv) {
     std::vector<uint8_t> out(size + 8);
     in_off[0] = 0; in_off[1] = prompt.size(); out_off[0] = 0; out_off[1] = out.size();
     P.in = prompt.data(); P.out = out.data(); P.gen_bytes = size; P.temperature = temperature; P.rand_u = ru.data(); P.rand_stride = 0;
-    if (Execute(R, gmx::MODE_GENERATE, &im, prompt.size() + size, P, false)) return 1;
+    if (Execute(R, gmx::MODE_GENERATE, &im, prompt.size() + size, P, false, getenv("EMU_OVERLAY") ? prompt.size() : 0)) return 1;
     WriteAll(argv[4], out.data(), size);
     return 0;
   }

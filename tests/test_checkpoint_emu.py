@@ -102,3 +102,9 @@ def test_generation_samples_the_reference_bytes(work, size, temp):
     emu(exe, "generate", d / "ref_a", d / "prompt.txt", d / f"emu_gen_{size}.out", size, temp)
     got, want = (d / f"emu_gen_{size}.out").read_bytes(), (d / f"ref_gen_{size}.out").read_bytes()
     assert len(want) == size and got == want
+    # and in overlay mode (what the batched generation call runs): the model's tables stay read-only and shared, the
+    # stream keeps its changes in an overlay map / local pool / private copies of the small state
+    env = dict(os.environ, EMU_OVERLAY="1")
+    subprocess.run([exe, "generate", str(d / "ref_a"), str(d / "prompt.txt"), str(d / f"ov_gen_{size}.out"), str(size), temp], check=True,
+                   stderr=subprocess.DEVNULL, env=env)
+    assert (d / f"ov_gen_{size}.out").read_bytes() == want
