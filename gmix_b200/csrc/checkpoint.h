@@ -433,6 +433,7 @@ inline Preload Count(const Image& im) {
   for (int k = 0; k < NIH; ++k) if (IHSpecs()[k].log2 >= 24) p.sparse_entries += im.ih[k].e.size();
   for (int m = 0; m < NMIX; ++m) p.mixer_sets += im.mix[m].ctx.size();
   p.ppmd_unit_bytes = im.heap_lo.size() + im.heap_hi.size();
+  p.ppmd_lo_bytes = im.heap_lo.size(); p.ppmd_hi_bytes = im.heap_hi.size();
   p.ppmd_text_bytes = im.heap_text.size();
   p.history_bytes = im.history.size();
   p.steps = im.mixer[0].steps;

@@ -20,6 +20,7 @@ inline uint64_t Pow2Ceil(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; re
 // max_len new bytes can need.
 struct Preload {
   uint64_t sparse_entries = 0, mixer_sets = 0, ppmd_unit_bytes = 0, ppmd_text_bytes = 0, history_bytes = 0, steps = 0;
+  uint64_t ppmd_lo_bytes = 0, ppmd_hi_bytes = 0;   // the two unit areas separately (their sum is ppmd_unit_bytes)
 };
 
 // Geometry of a PPMd heap window of P = 2^k bytes (ppmd.cuh): virtual offset v lives at heap[v & (P - 1)].
@@ -211,8 +212,18 @@ inline ArenaLayout MakeOverlayLayout(const ArenaLayout& base, const Preload& pre
   L.l_errh = take(3ull * L_HORIZON * L_CELLS * 4);
   L.l_wt = take(3ull * L_CELLS * L_CELLS * 4);
   L.p_state = take(sizeof(PpmdState));
-  L.p_mask = base.p_mask; L.p_text_cap = base.p_text_cap; L.p_units_cap = base.p_units_cap;   // the model's window geometry (sized for max_new_bytes more)
-  L.p_heap = take((uint64_t)L.p_mask + 1);
+  // PPMd: segmented private backing (ppmd.cuh): what the model uses of each area + room for new_bytes more
+  // (one text byte per input byte; units: the same worst-case allowance MakeLayout's roomy class uses, per area)
+  {
+    const uint64_t grow = 400 * new_bytes + (64u << 10);
+    L.p_mask = 0;
+    L.p_text_cap = (uint32_t)AlignUp(pre.ppmd_text_bytes + new_bytes + 64, 16);
+    L.p_seg_lo = L.p_text_cap;
+    L.p_lo_cap = (uint32_t)AlignUp(pre.ppmd_lo_bytes + grow, 48);
+    L.p_hi_cap = (uint32_t)AlignUp(pre.ppmd_hi_bytes + grow, 48);
+    L.p_units_cap = L.p_lo_cap + L.p_hi_cap;
+    L.p_heap = take((uint64_t)L.p_seg_lo + L.p_lo_cap + L.p_hi_cap + 64);
+  }
   L.total = off;
   return L;
 }

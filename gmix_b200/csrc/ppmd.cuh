@@ -85,6 +85,11 @@ struct Ppmd {
   // memory, cleared whenever EscCount changes. The array in the arena is still written (it is checkpoint state) but
   // no longer read on the per-byte path.
   uint32_t* masked;
+  // Segmented backing (mask == 0; overlay arenas of batched generation, layout.h MakeOverlayLayout): the three live
+  // areas sit back to back in private memory instead of in a power-of-two window: text [0, text_cap) at heap + 0, low
+  // units [units_start, units_start + lo_cap) at heap + seg_lo, high units [heap_end - hi_cap, heap_end) at heap +
+  // seg_lo + lo_cap. A model trained on 1 MB would otherwise drag a 512 MiB window into every stream.
+  uint32_t seg_lo = 0, lo_cap = 0, hi_cap = 0;
 #if defined(GMX_NO_MASK_SHADOW)
   GMX_DEV bool Masked(uint32_t sy) const { return S->char_mask[sy] == S->esc_count; }
 #else
@@ -94,7 +99,11 @@ struct Ppmd {
   GMX_DEV void NextEscCount() const { S->esc_count++; for (int i = 0; i < 8; ++i) masked[i] = 0u; }   // called by one lane
 
   // ---- virtual heap -> backed memory -------------------------------------------------------
-  GMX_DEV uint8_t* At(uint32_t v) const { return heap + (v & mask); }
+  GMX_DEV uint8_t* At(uint32_t v) const {
+    if (mask) return heap + (v & mask);
+    const uint32_t hi_base = PPMD_HEAP_END - hi_cap;
+    return heap + (v < PPMD_UNITS_START ? v : v < hi_base ? seg_lo + (v - PPMD_UNITS_START) : seg_lo + lo_cap + (v - hi_base));
+  }
   GMX_DEV uint32_t R8(uint32_t v) const { return *At(v); }
   GMX_DEV void W8(uint32_t v, uint32_t x) const { *At(v) = (uint8_t)x; }
   GMX_DEV uint32_t R16(uint32_t v) const { return *(const uint16_t*)At(v); }
@@ -150,6 +159,7 @@ struct Ppmd {
     return blk;
   }
   GMX_DEV bool Backed() const {  // do the low and high unit areas still fit the backed memory?
+    if (!mask) return S->lo_unit - PPMD_UNITS_START <= lo_cap && PPMD_HEAP_END - S->hi_unit <= hi_cap;
     return (uint64_t)(S->lo_unit - PPMD_UNITS_START) + (PPMD_HEAP_END - S->hi_unit) <= units_cap;
   }
   GMX_DEV void SplitBlock(uint32_t blk, uint32_t old_i, uint32_t new_i) const {  // :197-208

@@ -102,6 +102,7 @@ struct ArenaLayout {
   uint64_t l_wt;              // float [3][L_CELLS][L_CELLS] transposed recurrent weights (BPTT scratch)
   // PPMd
   uint64_t p_state; uint64_t p_heap; uint32_t p_mask; uint32_t p_text_cap; uint32_t p_units_cap;  // see ppmd.cuh
+  uint32_t p_seg_lo, p_lo_cap, p_hi_cap;   // p_mask == 0: segmented backing (ppmd.cuh), overlay arenas only
   uint64_t total;             // arena bytes
   // Overlay mode (ov != 0; streams that start from a loaded model WITHOUT cloning its tables: batched generation). The
   // big tables then stay in the model's arena, read-only and shared by every stream; this arena holds what the stream
@@ -684,7 +685,21 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
       copy(L.l_tanh, B.l_tanh, (uint64_t)L_HORIZON * L_CELLS * 4); copy(L.l_ig, B.l_ig, (uint64_t)L_HORIZON * L_CELLS * 4);
       copy(L.l_last, B.l_last, (uint64_t)L_HORIZON * L_CELLS * 4);
       copy(L.p_state, B.p_state, sizeof(PpmdState));
-      copy(L.p_heap, B.p_heap, (uint64_t)L.p_mask + 1);
+      {   // the three live areas of the model's PPMd heap (a power-of-two window there) into the segmented private backing
+        const PpmdState* bs = (const PpmdState*)(P.tmpl_arena + B.p_state);
+        const uint8_t* bh = P.tmpl_arena + B.p_heap;
+        uint8_t* h = A.at<uint8_t>(L.p_heap);
+        const uint32_t text = bs->text_ptr, lo = bs->lo_unit - PPMD_UNITS_START, hi = PPMD_HEAP_END - bs->hi_unit;
+        const uint32_t hi_base = PPMD_HEAP_END - L.p_hi_cap;
+        // 4-byte words: every area starts 4-byte aligned in both backings (units are 12 bytes, caps multiples of 16)
+        for (uint32_t i = tid * 4u; i < text; i += NT * 4u) *(uint32_t*)(h + i) = *(const uint32_t*)(bh + (i & B.p_mask));
+        for (uint32_t i = tid * 4u; i < lo; i += NT * 4u) *(uint32_t*)(h + L.p_seg_lo + i) = *(const uint32_t*)(bh + ((PPMD_UNITS_START + i) & B.p_mask));
+        for (uint32_t i = tid * 4u; i < hi; i += NT * 4u)
+          *(uint32_t*)(h + L.p_seg_lo + L.p_lo_cap + (bs->hi_unit - hi_base) + i) = *(const uint32_t*)(bh + ((bs->hi_unit + i) & B.p_mask));
+        // what the model never used must read as zero (mod_ppmd.cpp relies on fresh pages): text tail, units beyond lo, below hi
+        for (uint32_t i = ((text + 3u) & ~3u) + tid * 4u; i < L.p_seg_lo; i += NT * 4u) *(uint32_t*)(h + i) = 0u;
+        for (uint32_t i = ((lo + 3u) & ~3u) + tid * 4u; i < L.p_lo_cap + (bs->hi_unit - hi_base); i += NT * 4u) *(uint32_t*)(h + L.p_seg_lo + i) = 0u;
+      }
       uint4* z = A.at<uint4>(L.sparse);
       const uint64_t n16 = ((uint64_t)L.sparse_mask + 1) / 2;
       for (uint64_t i = tid; i < n16; i += NT) z[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -759,7 +774,7 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
     }
     __syncthreads();
     if (tid == 0) {
-      Ppmd pm{A.at<PpmdState>(L.p_state), A.at<uint8_t>(L.p_heap), L.p_mask, L.p_text_cap, L.p_units_cap, s.sqp, 0, s.p_masked};
+      Ppmd pm{A.at<PpmdState>(L.p_state), A.at<uint8_t>(L.p_heap), L.p_mask, L.p_text_cap, L.p_units_cap, s.sqp, 0, s.p_masked, L.p_seg_lo, L.p_lo_cap, L.p_hi_cap};
       pm.Init();
     }
   }
@@ -1438,7 +1453,7 @@ GMX_DEV void LstmPerceive(StreamSmem& s, const Arena& A, const StreamParams& P, 
 template <bool PROF>
 GMX_DEV void PpmdStep(StreamSmem& s, const Arena& A, uint32_t b, uint32_t last_byte, int known_byte, bool ahead, int lane, Lap<PROF>& lap) {
   const ArenaLayout& L = *A.L;
-  Ppmd pm{A.at<PpmdState>(L.p_state), A.at<uint8_t>(L.p_heap), L.p_mask, L.p_text_cap, L.p_units_cap, s.sqp, lane, s.p_masked};
+  Ppmd pm{A.at<PpmdState>(L.p_state), A.at<uint8_t>(L.p_heap), L.p_mask, L.p_text_cap, L.p_units_cap, s.sqp, lane, s.p_masked, L.p_seg_lo, L.p_lo_cap, L.p_hi_cap};
   pm.UpdateByte(last_byte);
   // sqp/ppm is one buffer: the LSTM role must be done with the previous distribution (and, in lockstep modes, the bit
   // role with its interval nodes: guaranteed by the caller having waited for byte b-1 to be known)
