@@ -1565,14 +1565,55 @@ GMX_DEV void BitBoundaryA(StreamSmem& s, const Arena& A, int btid) {
     }
   }
 }
+// known_byte >= 0 (compress): the byte about to be coded. Every table slot and every weight set its 8 bits will touch is
+// then already determined (bit_context of bit j = (1 << j) - 1 + (byte >> (8 - j))): their lines are requested from L2
+// now, so that the per-bit lookups and weight-set swaps of this byte find them there instead of waiting for HBM. These
+// are not extra requests, only earlier ones (the round-1 prefetches guessed both values of the next bit).
 template <int NB>
-GMX_DEV void BitBoundaryB(StreamSmem& s, const Arena& A, uint32_t b, int btid) {
+GMX_DEV void BitBoundaryB(StreamSmem& s, const Arena& A, uint32_t b, int btid, int known_byte = -1) {
   const ArenaLayout& L = *A.L;
   if (btid == 0) s.ctx[C_LSTM] = s.pkt[b % PKT_RING].lstm_ctx;
   GroupSync<NB>(BAR_BIT);   // (also orders part A's shared-memory writes when the same threads ran it)
   // Indirect row bases ((ctx << 8) % M, so that slot = (base + bit_context) % M); nothing is staged any more
-  for (int k = btid; k < NIND; k += NB) s.ind_base[k] = (s.ctx[s.T.ind[k].ctx] << 8) % L.ind_size[k];
+  for (int k = btid; k < NIND; k += NB) {
+    const uint32_t M = L.ind_size[k];
+    const uint32_t base = (s.ctx[s.T.ind[k].ctx] << 8) % M;
+    s.ind_base[k] = base;
+#if !defined(GMX_NO_BYTE_PREFETCH)
+    if (known_byte >= 0) {
+      const uint32_t sid = L.ind_sid[k];
+#pragma unroll 1
+      for (int j = 0; j < 8; ++j) {
+        uint32_t slot = base + ((1u << j) - 1u + ((uint32_t)known_byte >> (8 - j)));
+        if (slot >= M) slot -= M;
+        if (sid) PrefetchL2(A.map().tab + (SparseHash(SparseKey(sid, slot)) & L.sparse_mask));
+        else if (j == 0 || j == 6) PrefetchL2(A.at<uint16_t>(L.ind_tab[k]) + slot);   // a dense row is 510 bytes: bits 0-5 share a line
+      }
+    }
+#endif
+  }
   for (int m = btid; m < NMIX; m += NB) { s.set_idx[m] = 0xFFFFFFFFu; s.set_pool[m] = 0; s.set_dirty[m] = 0; }
+#if !defined(GMX_NO_BYTE_PREFETCH)
+  if (known_byte >= 0 && !L.ov) {
+    // weight sets: the 27 byte-gated mixers' one set, the 4 bit-gated mixers' eight (the two longest-match gates depend on
+    // the lookups): directory entry, then the record's lines. Work items = (mixer, bit).
+#pragma unroll 1
+    for (int t = btid; t < NMIX * 8; t += NB) {
+      const int m = t >> 3, j = t & 7;
+      const int cid = s.T.mixer[m].ctx;
+      const bool bit_level = cid == C_SLPR || cid == C_LBPR || cid == C_BIT_CONTEXT;
+      if (cid == C_LONGEST || (!bit_level && j)) continue;
+      const uint32_t bc = (1u << j) - 1u + ((uint32_t)known_byte >> (8 - j));
+      const uint32_t c = cid == C_BIT_CONTEXT ? bc : cid == C_LBPR ? (s.ctx[C_LAST_BYTE] << 8) + bc : cid == C_SLPR ? (s.ctx[C_RB1] << 8) + bc : s.ctx[cid];
+      const uint32_t nid = A.at<uint32_t>(L.mix_dir[m])[c & ((1u << s.T.mixer[m].log2) - 1)];
+      if (nid) {
+        const char* rec = (const char*)(A.at<float4>(L.mix_pool) + (size_t)nid * (L.mix_set_stride / 4));
+        const int bytes = (MixerNW(m) + 4) * 4;
+        for (int o = 0; o < bytes; o += 128) PrefetchL2(rec + o);
+      }
+    }
+  }
+#endif
   GroupSync<NB>(BAR_BIT);
 }
 
@@ -2107,7 +2148,7 @@ GMX_DEV void BitRoleCompress(StreamSmem& s, const Arena& A, const StreamParams& 
         lap.mark(2);
         WaitAtLeast(s, &s.n_pkt, pos + 1, 100);
         lap.mark(1);
-        BitBoundaryB<NB>(s, A, pos, btid);
+        BitBoundaryB<NB>(s, A, pos, btid, (int)c);
         lap.mark(2);
       }
       PredictBit<NB, PROF>(s, A, P, pos, 7 - j, btid, lap, NB > 32 ? bit : -1);
@@ -2150,7 +2191,7 @@ GMX_DEV void BitLstmRoleCompress(StreamSmem& s, const Arena& A, const StreamPara
         GroupSync<NB>(BAR_BIT);   // every staged weight set is back in the pool: s.w is free for the forward pass's ring
         lap.mark(1);
         LstmForward<NB, PROF, true>(s, A, P, pos, pos ? J.in[pos - 1] : s.byte0, (int)c, btid, lap, ws);
-        BitBoundaryB<NB>(s, A, pos, btid);
+        BitBoundaryB<NB>(s, A, pos, btid, (int)c);
         lap.mark(2);
       }
       PredictBit<NB, PROF>(s, A, P, pos, 7 - j, btid, lap, bit);
@@ -2187,7 +2228,7 @@ GMX_DEV void SerialPredict(StreamSmem& s, const Arena& A, const StreamParams& P,
     __syncthreads();
     lap.mark(2);
     LstmForward<NT, PROF, true>(s, A, P, 0, last, known_byte, tid, lap, ws);
-    BitBoundaryB<NT>(s, A, 0, tid);
+    BitBoundaryB<NT>(s, A, 0, tid, known_byte);
   }
   PredictBit<NT, PROF>(s, A, P, 0, path_bit, tid, lap, learn_bit);
 }
