@@ -1,5 +1,6 @@
 // Batched generation (runner_utils::RunGeneration runner-utils.cpp:158-221): one CTA per prompt, every stream a
 // clone of the loaded checkpoint.
+#define GMX_OVERLAY 1   // streams of a generation batch are overlays of the shared model (stream_kernel.cuh)
 #include "kernels.h"
 namespace gmx {
 cudaError_t LaunchGenerate(int cfg, const StreamParams& P, unsigned grid, cudaStream_t st) {

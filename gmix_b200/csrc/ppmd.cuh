@@ -100,6 +100,9 @@ struct Ppmd {
 
   // ---- virtual heap -> backed memory -------------------------------------------------------
   GMX_DEV uint8_t* At(uint32_t v) const {
+#if !defined(GMX_OVERLAY) || !GMX_OVERLAY
+    return heap + (v & mask);   // (kernels without overlay mode: no second translation, see stream_kernel.cuh GMX_OVERLAY)
+#endif
     if (mask) return heap + (v & mask);
     const uint32_t hi_base = PPMD_HEAP_END - hi_cap;
     return heap + (v < PPMD_UNITS_START ? v : v < hi_base ? seg_lo + (v - PPMD_UNITS_START) : seg_lo + lo_cap + (v - hi_base));
@@ -159,7 +162,9 @@ struct Ppmd {
     return blk;
   }
   GMX_DEV bool Backed() const {  // do the low and high unit areas still fit the backed memory?
+#if defined(GMX_OVERLAY) && GMX_OVERLAY
     if (!mask) return S->lo_unit - PPMD_UNITS_START <= lo_cap && PPMD_HEAP_END - S->hi_unit <= hi_cap;
+#endif
     return (uint64_t)(S->lo_unit - PPMD_UNITS_START) + (PPMD_HEAP_END - S->hi_unit) <= units_cap;
   }
   GMX_DEV void SplitBlock(uint32_t blk, uint32_t old_i, uint32_t new_i) const {  // :197-208

@@ -112,6 +112,13 @@ struct ArenaLayout {
   // Match predictions, LSTM, PPMd) is a private copy made at stream start.
   uint32_t ov, base_sets, base_hist, ov_pad;
 };
+// Overlay mode exists in the generation kernels only (kernel_generate.cu defines GMX_OVERLAY 1 before this header; the
+// CPU emulator too): everywhere else the checks below are compile-time false, so that the compress / decompress kernels
+// carry neither the branches nor the code behind them (their per-bit path is instruction-cache and register bound).
+#ifndef GMX_OVERLAY
+#define GMX_OVERLAY 0
+#endif
+#define GMX_IS_OV(L) (GMX_OVERLAY && (L).ov)
 enum : uint32_t { OV_SID_IND = 1, OV_SID_MATCH = OV_SID_IND + NIND, OV_SID_IH = OV_SID_MATCH + NMATCH, OV_SID_MIX = OV_SID_IH + NIH };
 static_assert(OV_SID_MIX + NMIX <= 128, "overlay table ids must fit the 7 bits above the 25-bit index of a sparse key");
 
@@ -372,26 +379,26 @@ GMX_DEV inline uint32_t BaseIH(const Arena& A, int k, uint32_t idx) {
 // Mixer directory: pool id of the weight set of mixer m's gate context idx (0 = none yet)
 GMX_DEV inline uint32_t DirGet(const Arena& A, int m, uint32_t idx) {
   const ArenaLayout& L = *A.L;
-  if (!L.ov) return A.at<uint32_t>(L.mix_dir[m])[idx];
+  if (!GMX_IS_OV(L)) return A.at<uint32_t>(L.mix_dir[m])[idx];
   unsigned long long e;
   SparseFind(A.map(), SparseKey(OV_SID_MIX + m, idx), &e);
   return e ? (uint32_t)e : ((const uint32_t*)(A.base0 + A.BL->mix_dir[m]))[idx];
 }
 GMX_DEV inline void DirSet(StreamSmem& s, const Arena& A, int m, uint32_t idx, uint32_t id) {
   const ArenaLayout& L = *A.L;
-  if (!L.ov) A.at<uint32_t>(L.mix_dir[m])[idx] = id;
+  if (!GMX_IS_OV(L)) A.at<uint32_t>(L.mix_dir[m])[idx] = id;
   else SparseSet(A.map(), &s.sparse_used, L.sparse_limit, &s.error, SparseKey(OV_SID_MIX + m, idx), id);
 }
 // Pool record of weight set `id` (float4 units): the model's pool below base_sets in overlay mode (read-only)
 GMX_DEV inline float4* PoolRec(const Arena& A, uint32_t id) {
   const ArenaLayout& L = *A.L;
   const uint32_t stride4 = L.mix_set_stride / 4;
-  if (L.ov && id < L.base_sets) return (float4*)(A.base0 + A.BL->mix_pool) + (size_t)id * stride4;
-  return A.at<float4>(L.mix_pool) + (size_t)(id - (L.ov ? L.base_sets : 0u)) * stride4;
+  if (GMX_IS_OV(L) && id < L.base_sets) return (float4*)(A.base0 + A.BL->mix_pool) + (size_t)id * stride4;
+  return A.at<float4>(L.mix_pool) + (size_t)(id - (GMX_IS_OV(L) ? L.base_sets : 0u)) * stride4;
 }
 GMX_DEV inline uint32_t HistByte(const Arena& A, uint32_t pos) {
   const ArenaLayout& L = *A.L;
-  if (L.ov) return pos < L.base_hist ? (A.base0 + A.BL->history)[pos] : A.at<uint8_t>(L.history)[pos - L.base_hist];
+  if (GMX_IS_OV(L)) return pos < L.base_hist ? (A.base0 + A.BL->history)[pos] : A.at<uint8_t>(L.history)[pos - L.base_hist];
   return A.at<uint8_t>(L.history)[pos];
 }
 // One staged weight set goes back to its pool record; all 32 lanes with the same arguments. `idx` = the gate context it
@@ -401,7 +408,7 @@ GMX_DEV inline void WriteBackSet(StreamSmem& s, const Arena& A, int m, uint32_t 
   if (!old || !s.set_dirty[m]) return;
   const ArenaLayout& L = *A.L;
   uint32_t id = old;
-  if (L.ov && old < L.base_sets) {
+  if (GMX_IS_OV(L) && old < L.base_sets) {
     if (lane == 0) {
       id = atomicAdd(&s.pool_next, 1u);
       if (id >= L.mix_pool_sets) { SetError(s, GMX_ERR_MIXER_POOL); id = 0; }
@@ -665,7 +672,7 @@ template <int NT>
 GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, int tid) {
   const ArenaLayout& L = *A.L;
   if (P.tmpl_arena) {   // clone of a parked stream: arena image, then everything of StreamSmem behind the launch tables
-    if (L.ov) {
+    if (GMX_IS_OV(L)) {
       // overlay mode: only the state the stream updates densely is copied (every region is a 256-byte multiple apart from
       // its tail, all offsets are 256-byte aligned: 16-byte copies); the overlay map starts empty
       const ArenaLayout& B = *P.tmpl_layout;
@@ -713,7 +720,7 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
     uint32_t* sw = (uint32_t*)&s;
     for (int i = kFirst + tid; i < kWords; i += NT) sw[i] = P.tmpl_state[i];
     __syncthreads();
-    if (tid == 0) { s.error = 0; s.nswap = 0; s.x1 = 0; s.x2 = 0xffffffffu; s.x = 0; if (L.ov) s.sparse_used = 0; }
+    if (tid == 0) { s.error = 0; s.nswap = 0; s.x1 = 0; s.x2 = 0xffffffffu; s.x = 0; if (GMX_IS_OV(L)) s.sparse_used = 0; }
   } else {
     for (int k = 0; k < NIND; ++k)
       if (!L.ind_sid[k]) FillWords<NT>(A.at<uint32_t>(L.ind_tab[k]), ((uint64_t)L.ind_size[k] + 1) / 2, 0x00FF00FFu, tid);
@@ -1550,11 +1557,11 @@ GMX_DEV void BitBoundaryA(StreamSmem& s, const Arena& A, int btid) {
         const uint32_t key = SparseKey(sid, s.ih_hash[k] & mask);
         unsigned long long e;
         const uint32_t pos = SparseFind(M, key, &e);
-        const uint32_t cur = e ? (uint32_t)e : L.ov ? BaseIH(A, k, s.ih_hash[k] & mask) : 0u;
+        const uint32_t cur = e ? (uint32_t)e : GMX_IS_OV(L) ? BaseIH(A, k, s.ih_hash[k] & mask) : 0u;
         SparsePut(M, &s.sparse_used, L.sparse_limit, &s.error, key, pos, e != 0ull, (uint32_t)((((uint64_t)cur % inner_mod) << 8) + last_byte));
         unsigned long long e2;
         SparseFind(M, SparseKey(sid, oh & mask), &e2);
-        s.ctx[C_IH0 + k] = Murmur32(e2 ? (uint32_t)e2 : L.ov ? BaseIH(A, k, oh & mask) : 0u);
+        s.ctx[C_IH0 + k] = Murmur32(e2 ? (uint32_t)e2 : GMX_IS_OV(L) ? BaseIH(A, k, oh & mask) : 0u);
       } else {
         uint32_t* tab = A.at<uint32_t>(L.ih_tab[k]);
         uint32_t* slot = tab + (s.ih_hash[k] & mask);
@@ -1594,7 +1601,7 @@ GMX_DEV void BitBoundaryB(StreamSmem& s, const Arena& A, uint32_t b, int btid, i
   }
   for (int m = btid; m < NMIX; m += NB) { s.set_idx[m] = 0xFFFFFFFFu; s.set_pool[m] = 0; s.set_dirty[m] = 0; }
 #if !defined(GMX_NO_BYTE_PREFETCH)
-  if (known_byte >= 0 && !L.ov) {
+  if (known_byte >= 0 && !GMX_IS_OV(L)) {
     // weight sets: the 27 byte-gated mixers' one set, the 4 bit-gated mixers' eight (the two longest-match gates depend on
     // the lookups): directory entry, then the record's lines. Work items = (mixer, bit).
 #pragma unroll 1
@@ -1675,7 +1682,7 @@ GMX_DEV inline void LearnTables(StreamSmem& s, const Arena& A, int bit, int t) {
     }
   } else if (t == NIND + NMATCH && byte_done && longest < 2) {
     if (s.hist_len >= L.history_cap) SetError(s, GMX_ERR_HISTORY_CAP);
-    else A.at<uint8_t>(L.history)[s.hist_len - (L.ov ? L.base_hist : 0u)] = (uint8_t)cur;
+    else A.at<uint8_t>(L.history)[s.hist_len - (GMX_IS_OV(L) ? L.base_hist : 0u)] = (uint8_t)cur;
   }
 }
 
@@ -1722,7 +1729,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, ui
         unsigned long long ent;
         const uint32_t index = slot;
         slot = SparseFind(A.map(), SparseKey(sid, slot), &ent);
-        e = ent ? (uint32_t)ent & 0xffffu : L.ov ? BaseInd(A, k, index) : 0x00ffu;
+        e = ent ? (uint32_t)ent & 0xffffu : GMX_IS_OV(L) ? BaseInd(A, k, index) : 0x00ffu;
         s.ind_found[k] = ent != 0ull;
       } else {
         e = A.at<uint16_t>(L.ind_tab[k])[slot];
@@ -1758,7 +1765,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, ui
           if (L.match_sid[k]) {
             unsigned long long ent;
             SparseFind(A.map(), SparseKey(L.match_sid[k], idx), &ent);
-            cm = ent ? (uint32_t)ent : L.ov ? BaseMatch(A, k, idx) : 0u;
+            cm = ent ? (uint32_t)ent : GMX_IS_OV(L) ? BaseMatch(A, k, idx) : 0u;
           } else {
             cm = A.at<uint32_t>(L.match_tab[k])[idx];
           }

@@ -6,6 +6,7 @@
 #ifndef GMIX_TESTS_CUDA_EMU_H_
 #define GMIX_TESTS_CUDA_EMU_H_
 #define GMX_EMU 1
+#define GMX_OVERLAY 1   // the emulator build carries the overlay mode of the generation kernels
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
