@@ -155,6 +155,10 @@ struct StreamParams {
   uint32_t part, part_header, part_last;
   uint64_t part_total;         // compress: length the header announces; decompress: bytes this part produces
   const uint32_t* coder_in; uint32_t* coder_out;
+  // compress: request the table slots and weight sets of a byte's 8 bits from L2 at its byte boundary (BitBoundaryB). Wins
+  // when a stream has its SM to itself (+1 %), loses when other resident streams already hide the latency (-2 % at 8
+  // CTAs/SM, profiles/r02_ab_byte_prefetch.txt): the host switches it on for the one-CTA-per-SM configurations only.
+  uint32_t byte_prefetch;
 };
 
 // ---- device constant tables --------------------------------------------------------------------
@@ -2155,7 +2159,7 @@ GMX_DEV void BitRoleCompress(StreamSmem& s, const Arena& A, const StreamParams& 
         lap.mark(2);
         WaitAtLeast(s, &s.n_pkt, pos + 1, 100);
         lap.mark(1);
-        BitBoundaryB<NB>(s, A, pos, btid, (int)c);
+        BitBoundaryB<NB>(s, A, pos, btid, P.byte_prefetch ? (int)c : -1);
         lap.mark(2);
       }
       PredictBit<NB, PROF>(s, A, P, pos, 7 - j, btid, lap, NB > 32 ? bit : -1);
@@ -2198,7 +2202,7 @@ GMX_DEV void BitLstmRoleCompress(StreamSmem& s, const Arena& A, const StreamPara
         GroupSync<NB>(BAR_BIT);   // every staged weight set is back in the pool: s.w is free for the forward pass's ring
         lap.mark(1);
         LstmForward<NB, PROF, true>(s, A, P, pos, pos ? J.in[pos - 1] : s.byte0, (int)c, btid, lap, ws);
-        BitBoundaryB<NB>(s, A, pos, btid, (int)c);
+        BitBoundaryB<NB>(s, A, pos, btid, P.byte_prefetch ? (int)c : -1);
         lap.mark(2);
       }
       PredictBit<NB, PROF>(s, A, P, pos, 7 - j, btid, lap, bit);
@@ -2235,7 +2239,7 @@ GMX_DEV void SerialPredict(StreamSmem& s, const Arena& A, const StreamParams& P,
     __syncthreads();
     lap.mark(2);
     LstmForward<NT, PROF, true>(s, A, P, 0, last, known_byte, tid, lap, ws);
-    BitBoundaryB<NT>(s, A, 0, tid, known_byte);
+    BitBoundaryB<NT>(s, A, 0, tid, P.byte_prefetch ? known_byte : -1);
   }
   PredictBit<NT, PROF>(s, A, P, 0, path_bit, tid, lap, learn_bit);
 }
