@@ -1710,7 +1710,7 @@ GMX_DEV inline void GateSelect(StreamSmem& s, const Arena& A, int m, uint32_t c)
 // learn_bit >= 0 (compress): the bit that is about to be coded; the table models then learn it on the threads that have
 // nothing to do while the first warp evaluates the mixer network (they depend on the bit and on the lookups, not on the
 // mixers), and the caller passes tables_done to LearnBit.
-template <int NB, bool PROF>
+template <int NB, bool PROF, bool LAT = false>
 GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, uint32_t b, int path_bit, int btid, Lap<PROF>& lap, int learn_bit = -1) {
   const ArenaLayout& L = *A.L;
   const uint32_t bitctx = s.ctx[C_BIT_CONTEXT];
@@ -1866,7 +1866,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, ui
     {
       const float4* x4 = (const float4*)s.xe;
       const float4* w4 = (const float4*)w;
-#pragma unroll 2
+GMX_UNROLL(LAT ? NPRED / 4 : 2)   // a stream alone on its SM (LAT) is not instruction-cache bound: straight-line code there
       for (int q = 0; q < NPRED / 4; ++q) {
         const float4 x = x4[q], v = w4[q];
         acc = f_add(acc, f_mul(x.x, v.x)); acc = f_add(acc, f_mul(x.y, v.y));
@@ -1881,13 +1881,24 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, ui
       // serial chain of the layer: neuron j's finished output feeds every later neuron (mixer.cpp:60-70). Rolled (a
       // handful of instructions that stay in the instruction cache); the chain weight of the next step is loaded from
       // shared memory while the current step's shuffle is in flight.
-      float c = w[NPRED];
+      if (LAT) {   // the 23 chain weights in registers: one step is shuffle -> mul -> add
+        float cw[NL0 - 1];
+#pragma unroll
+        for (int j = 0; j < NL0 - 1; ++j) cw[j] = w[NPRED + j];
+#pragma unroll
+        for (int j = 0; j < NL0 - 1; ++j) {
+          const float oj = __shfl_sync(0xffffffffu, acc, j);
+          if (lane > j && lane < NL0) acc = f_add(acc, f_mul(oj, cw[j]));
+        }
+      } else {
+        float c = w[NPRED];
 #pragma unroll 1
-      for (int j = 0; j < NL0 - 1; ++j) {
-        const float cn = w[NPRED + j + 1];   // j = 22 reads the pad word behind the set: never used
-        const float oj = __shfl_sync(0xffffffffu, acc, j);
-        if (lane > j && lane < NL0) acc = f_add(acc, f_mul(oj, c));
-        c = cn;
+        for (int j = 0; j < NL0 - 1; ++j) {
+          const float cn = w[NPRED + j + 1];   // j = 22 reads the pad word behind the set: never used
+          const float oj = __shfl_sync(0xffffffffu, acc, j);
+          if (lane > j && lane < NL0) acc = f_add(acc, f_mul(oj, c));
+          c = cn;
+        }
       }
     }
     if (lane < NL0) { s.l0_out[lane] = acc; s.xe[NPRED + lane] = acc; }
@@ -1899,7 +1910,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, ui
     {
       const float4* x4 = (const float4*)s.l0_out;
       const float4* w4 = (const float4*)w1;
-#pragma unroll 1
+GMX_UNROLL(LAT ? NL0 / 4 : 1)
       for (int q = 0; q < NL0 / 4; ++q) {
         const float4 x = x4[q], v = w4[q];
         acc = f_add(acc, f_mul(x.x, v.x)); acc = f_add(acc, f_mul(x.y, v.y));
@@ -1909,7 +1920,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, ui
     __syncwarp();
     // a layer-1 output is complete (skip connection added last, weights[num_layer0 + output_index],
     // mixer.cpp:77-83) before the next layer-1 neuron reads it
-#pragma unroll 1
+GMX_UNROLL(LAT ? NL1 : 1)
     for (int j = 0; j < NL1; ++j) {
       if (lane == j) acc = f_add(acc, f_mul(skip, w1[NL0 + j]));
       if (j < NL1 - 1) {
@@ -1925,7 +1936,7 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, ui
       float p = 0.0f;
       const float4* x4 = (const float4*)s.l0_out;   // l0_out[24] then l1_out[8]
       const float4* w4 = (const float4*)w2;
-#pragma unroll 1
+GMX_UNROLL(LAT ? (NL0 + NL1) / 4 : 1)
       for (int q = 0; q < (NL0 + NL1) / 4; ++q) {
         const float4 x = x4[q], v = w4[q];
         p = f_add(p, f_mul(x.x, v.x)); p = f_add(p, f_mul(x.y, v.y));
@@ -1974,7 +1985,7 @@ GMX_DEV inline void EncodeBit(StreamSmem& s, uint8_t* out, int bit) {
 // known_bit >= 0 (compress): the caller has not stored s.new_bit and not run the coder yet; both happen here, as one
 // more work item of the first phase, which saves the barrier between coding and learning. code_out = the stream's
 // output slice. Returns with s.bit_stop refreshed (role-uniform).
-template <int NB, bool PROF>
+template <int NB, bool PROF, bool LAT = false>
 GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int btid, Lap<PROF>& lap, int known_bit = -1, uint8_t* code_out = nullptr,
                       bool tables_done = false) {
   const ArenaLayout& L = *A.L;
@@ -2017,7 +2028,7 @@ GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int 
   lap.mark(11);
   // Mixer weight updates (mixer.cpp:128-175): w -= update * x over exactly the inputs used by
   // Predict, then the (1 - 3e-6) shrink every 1024 steps of the set.
-#pragma unroll 1
+GMX_UNROLL(LAT ? 3 : 1)
   for (int m = btid >> 5; m < NMIX; m += NB / 32) {
     const int lane = btid & 31;
     const int nw = MixerNW(m);
@@ -2140,7 +2151,7 @@ GMX_DEV void LstmRole(StreamSmem& s, const Arena& A, const StreamParams& P, cons
 
 // Bit role: runner_utils::Compress (runner-utils.cpp:43-67); the 5-byte header of RunCompression (:109) is written by
 // the kernel entry.
-template <int NB, bool PROF>
+template <int NB, bool PROF, bool LAT = false>
 GMX_DEV void BitRoleCompress(StreamSmem& s, const Arena& A, const StreamParams& P, const StreamJob& J, uint32_t sid, ProfSmem* prof, int btid) {
   Lap<PROF> lap;
   lap.start(prof, btid == 0);
@@ -2162,13 +2173,13 @@ GMX_DEV void BitRoleCompress(StreamSmem& s, const Arena& A, const StreamParams& 
         BitBoundaryB<NB>(s, A, pos, btid, P.byte_prefetch ? (int)c : -1);
         lap.mark(2);
       }
-      PredictBit<NB, PROF>(s, A, P, pos, 7 - j, btid, lap, NB > 32 ? bit : -1);
+      PredictBit<NB, PROF, LAT>(s, A, P, pos, 7 - j, btid, lap, NB > 32 ? bit : -1);
       if (tracing) {   // debug/parity traces of stream 0 read the blackboard before the mixers learn
         if (btid == 0) Trace(s, P, (uint64_t)pos * 8 + (7 - j));
         GroupSync<NB>(BAR_BIT);
         lap.mark(13);
       }
-      LearnBit<NB, PROF>(s, A, P, btid, lap, bit, J.out, NB > 32);   // codes the bit and learns it
+      LearnBit<NB, PROF, LAT>(s, A, P, btid, lap, bit, J.out, NB > 32);   // codes the bit and learns it
       if (s.bit_stop) return;
     }
     if (btid == 0) Publish(&s.n_done, pos + 1);
@@ -2179,7 +2190,7 @@ GMX_DEV void BitRoleCompress(StreamSmem& s, const Arena& A, const StreamParams& 
 // other with all of them (forward(b), the 8 bits of byte b, Perceive(b)). PPMd is the one phase a single warp has to
 // itself in the serial order (its neighbours would idle at a barrier for ~16 % of the byte); everything else keeps the
 // full width.
-template <int NB, bool PROF>
+template <int NB, bool PROF, bool LAT = false>
 GMX_DEV void BitLstmRoleCompress(StreamSmem& s, const Arena& A, const StreamParams& P, const StreamJob& J, uint32_t sid, ProfSmem* prof, int btid,
                                  const WeightSmem& ws) {
   Lap<PROF> lap;
@@ -2205,13 +2216,13 @@ GMX_DEV void BitLstmRoleCompress(StreamSmem& s, const Arena& A, const StreamPara
         BitBoundaryB<NB>(s, A, pos, btid, P.byte_prefetch ? (int)c : -1);
         lap.mark(2);
       }
-      PredictBit<NB, PROF>(s, A, P, pos, 7 - j, btid, lap, bit);
+      PredictBit<NB, PROF, LAT>(s, A, P, pos, 7 - j, btid, lap, bit);
       if (tracing) {
         if (btid == 0) Trace(s, P, (uint64_t)pos * 8 + (7 - j));
         GroupSync<NB>(BAR_BIT);
         lap.mark(13);
       }
-      LearnBit<NB, PROF>(s, A, P, btid, lap, bit, J.out, true);
+      LearnBit<NB, PROF, LAT>(s, A, P, btid, lap, bit, J.out, true);
       if (s.bit_stop) return;
     }
     LstmPerceive<NB, PROF>(s, A, P, c, btid, lap, ws);
@@ -2225,7 +2236,7 @@ GMX_DEV void BitLstmRoleCompress(StreamSmem& s, const Arena& A, const StreamPara
 
 // Predictor::Predict of one bit. known_byte >= 0 (serial compress): the byte being coded; path_bit = index of this bit in
 // it. The byte models then leave their eight path nodes in packet 0 at the byte boundary.
-template <int NT, bool PROF>
+template <int NT, bool PROF, bool LAT = false>
 GMX_DEV void SerialPredict(StreamSmem& s, const Arena& A, const StreamParams& P, int tid, Lap<PROF>& lap, const WeightSmem& ws, int known_byte = -1,
                            int path_bit = -1, int learn_bit = -1) {
   if (tid == 0) Bookkeeping(s);
@@ -2241,21 +2252,21 @@ GMX_DEV void SerialPredict(StreamSmem& s, const Arena& A, const StreamParams& P,
     LstmForward<NT, PROF, true>(s, A, P, 0, last, known_byte, tid, lap, ws);
     BitBoundaryB<NT>(s, A, 0, tid, P.byte_prefetch ? known_byte : -1);
   }
-  PredictBit<NT, PROF>(s, A, P, 0, path_bit, tid, lap, learn_bit);
+  PredictBit<NT, PROF, LAT>(s, A, P, 0, path_bit, tid, lap, learn_bit);
 }
 // Predictor::Learn of one bit (s.new_bit, or known_bit which is then also coded into code_out first).
-template <int NT, bool PROF>
+template <int NT, bool PROF, bool LAT = false>
 GMX_DEV void SerialLearn(StreamSmem& s, const Arena& A, const StreamParams& P, int tid, Lap<PROF>& lap, const WeightSmem& ws, int known_bit = -1,
                          uint8_t* code_out = nullptr) {
   const int cur = s.recent_bits * 2 + (known_bit >= 0 ? known_bit : s.new_bit);
-  LearnBit<NT, PROF>(s, A, P, tid, lap, known_bit, code_out, known_bit >= 0);   // (SerialPredict ran the table models' Learn already when it knew the bit)
+  LearnBit<NT, PROF, LAT>(s, A, P, tid, lap, known_bit, code_out, known_bit >= 0);   // (SerialPredict ran the table models' Learn already when it knew the bit)
   if (cur >= 256) LstmPerceive<NT, PROF>(s, A, P, (uint32_t)(cur - 256), tid, lap, ws);   // LstmModel::Learn lstm-model.cpp:50-59
 }
 
 // runner_utils::Compress (runner-utils.cpp:43-67) without the role pipeline: all phases with all threads. With a full
 // wave of resident streams per SM the other streams already hide this stream's latencies, and every phase having all
 // threads beats the pipeline's fixed split of them (kernels.h: configurations).
-template <int NT, bool PROF>
+template <int NT, bool PROF, bool LAT = false>
 GMX_DEV void SerialCompress(StreamSmem& s, const Arena& A, const StreamParams& P, const StreamJob& J, uint32_t sid, ProfSmem* prof, int tid,
                             const WeightSmem& ws) {
   Lap<PROF> lap;
@@ -2267,19 +2278,19 @@ GMX_DEV void SerialCompress(StreamSmem& s, const Arena& A, const StreamParams& P
     const uint32_t c = J.in[pos];
 #pragma unroll 1
     for (int j = 7; j >= 0; --j) {
-      SerialPredict<NT, PROF>(s, A, P, tid, lap, ws, (int)c, 7 - j, (c >> j) & 1);
+      SerialPredict<NT, PROF, LAT>(s, A, P, tid, lap, ws, (int)c, 7 - j, (c >> j) & 1);
       if (tracing) {
         if (tid == 0) Trace(s, P, (uint64_t)pos * 8 + (7 - j));
         __syncthreads();
       }
-      SerialLearn<NT, PROF>(s, A, P, tid, lap, ws, (c >> j) & 1, J.out);
+      SerialLearn<NT, PROF, LAT>(s, A, P, tid, lap, ws, (c >> j) & 1, J.out);
       if (s.bit_stop) return;
     }
   }
 }
 
 // runner_utils::Decompress (runner-utils.cpp:69-86); Decoder::Decode decoder.cpp:19-39. Analysis is never on.
-template <int NT, bool PROF>
+template <int NT, bool PROF, bool LAT = false>
 GMX_DEV void SerialDecompress(StreamSmem& s, const Arena& A, const StreamParams& P, const StreamJob& J, ProfSmem* prof, int tid, const WeightSmem& ws) {
   Lap<PROF> lap;
   lap.start(prof, tid == 0);
@@ -2288,7 +2299,7 @@ GMX_DEV void SerialDecompress(StreamSmem& s, const Arena& A, const StreamParams&
   for (uint32_t pos = 0; pos < J.n_bytes; ++pos) {
 #pragma unroll 1
     for (int j = 7; j >= 0; --j) {
-      SerialPredict<NT, PROF>(s, A, P, tid, lap, ws);
+      SerialPredict<NT, PROF, LAT>(s, A, P, tid, lap, ws);
       if (tid == 0) {
         const uint32_t p16 = Discretize(s.prob);
         const uint32_t r = s.x2 - s.x1;
@@ -2300,7 +2311,7 @@ GMX_DEV void SerialDecompress(StreamSmem& s, const Arena& A, const StreamParams&
         if (j == 0) J.out[pos] = (uint8_t)((s.recent_bits * 2 + bit) & 0xff);
       }
       __syncthreads();
-      SerialLearn<NT, PROF>(s, A, P, tid, lap, ws);
+      SerialLearn<NT, PROF, LAT>(s, A, P, tid, lap, ws);
       if (s.bit_stop) return;
     }
   }
@@ -2309,7 +2320,7 @@ GMX_DEV void SerialDecompress(StreamSmem& s, const Arena& A, const StreamParams&
 // runner_utils::RunGeneration (runner-utils.cpp:158-221): the prompt (all but its last byte) is consumed WITH
 // learning, then n_bytes bytes are sampled bit by bit without Learn: prob = Logistic(Logit(prob) / temperature),
 // bit = r < prob with r the next rand()/RAND_MAX draw, Perceive(bit), Predict().
-template <int NT, bool PROF>
+template <int NT, bool PROF, bool LAT = false>
 GMX_DEV void SerialGenerate(StreamSmem& s, const Arena& A, const StreamParams& P, const StreamJob& J, const float* ru, ProfSmem* prof, int tid,
                             const WeightSmem& ws) {
   Lap<PROF> lap;
@@ -2320,14 +2331,14 @@ GMX_DEV void SerialGenerate(StreamSmem& s, const Arena& A, const StreamParams& P
     const uint32_t c = J.in[pos];
 #pragma unroll 1
     for (int j = 7; j >= 0; --j) {
-      SerialPredict<NT, PROF>(s, A, P, tid, lap, ws);
+      SerialPredict<NT, PROF, LAT>(s, A, P, tid, lap, ws);
       if (tid == 0) s.new_bit = (c >> j) & 1;
       __syncthreads();
-      SerialLearn<NT, PROF>(s, A, P, tid, lap, ws);
+      SerialLearn<NT, PROF, LAT>(s, A, P, tid, lap, ws);
       if (s.bit_stop) return;
     }
   }
-  SerialPredict<NT, PROF>(s, A, P, tid, lap, ws);   // :198
+  SerialPredict<NT, PROF, LAT>(s, A, P, tid, lap, ws);   // :198
 #pragma unroll 1
   for (uint32_t i = 0; i < J.n_bytes; ++i) {
 #pragma unroll 1
@@ -2341,7 +2352,7 @@ GMX_DEV void SerialGenerate(StreamSmem& s, const Arena& A, const StreamParams& P
       }
       __syncthreads();
       if (s.bit_stop) return;
-      SerialPredict<NT, PROF>(s, A, P, tid, lap, ws);
+      SerialPredict<NT, PROF, LAT>(s, A, P, tid, lap, ws);
     }
   }
 }
@@ -2437,18 +2448,18 @@ __global__ void __launch_bounds__(32 * (WB + WL + 1), MINB) StreamKernel(StreamP
     const bool failed_early = s.error != 0;
     if (!failed_early) {
       if (MODE == MODE_COMPRESS && SERIAL) {
-        SerialCompress<NT, PROF>(s, A, P, job, sid, prof, tid, ws);
+        SerialCompress<NT, PROF, MINB == 1>(s, A, P, job, sid, prof, tid, ws);
       } else if (MODE == MODE_COMPRESS && WL == 0) {
-        if (tid < NB) BitLstmRoleCompress<NB, PROF>(s, A, P, job, sid, prof, tid, ws);
+        if (tid < NB) BitLstmRoleCompress<NB, PROF, MINB == 1>(s, A, P, job, sid, prof, tid, ws);
         else PpmdRole<PROF>(s, A, job, prof, tid - NB);
       } else if (MODE == MODE_COMPRESS) {
-        if (tid < NB) BitRoleCompress<NB, PROF>(s, A, P, job, sid, prof, tid);
+        if (tid < NB) BitRoleCompress<NB, PROF, MINB == 1>(s, A, P, job, sid, prof, tid);
         else if (tid < NB + NL) LstmRole<(NL > 0 ? NL : 32), PROF>(s, A, P, job, prof, tid - NB, ws);
         else PpmdRole<PROF>(s, A, job, prof, tid - NB - NL);
       } else if (MODE == MODE_DECOMPRESS) {
-        SerialDecompress<NT, PROF>(s, A, P, job, prof, tid, ws);
+        SerialDecompress<NT, PROF, MINB == 1>(s, A, P, job, prof, tid, ws);
       } else {
-        SerialGenerate<NT, PROF>(s, A, P, job, P.rand_u + (size_t)sid * P.rand_stride, prof, tid, ws);
+        SerialGenerate<NT, PROF, MINB == 1>(s, A, P, job, P.rand_u + (size_t)sid * P.rand_stride, prof, tid, ws);
       }
     }
     __syncthreads();

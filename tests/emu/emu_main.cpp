@@ -33,6 +33,9 @@
 #ifndef EMU_SERIAL
 #define EMU_SERIAL 0      // 1: compress without the role pipeline (kernels.h configuration 0)
 #endif
+#ifndef EMU_MINB
+#define EMU_MINB 8        // resident CTAs per SM the configuration is built for; 1 selects the latency code paths (LAT)
+#endif
 #ifndef EMU_WS
 #define EMU_WS 0          // 1: dense gate weights resident in (emulated) shared memory, refreshed by bulk copies after Adam
 #endif
@@ -111,9 +114,9 @@ retry:
   }
   if (want_final) { R.final_state.assign(sizeof(gmx::StreamSmem) / 4 + 4, 0); P.final_state = R.final_state.data(); }
   cuda_emu::RunBlock(EMU_NT, 0, 1, [&] {
-    if (mode == gmx::MODE_COMPRESS) gmx::StreamKernel<EMU_WB, EMU_WL, gmx::MODE_COMPRESS, 1, false, EMU_SERIAL != 0, EMU_WS != 0>(P);
-    else if (mode == gmx::MODE_DECOMPRESS) gmx::StreamKernel<EMU_WB, EMU_WL, gmx::MODE_DECOMPRESS, 1, false, false, EMU_WS != 0>(P);
-    else gmx::StreamKernel<EMU_WB, EMU_WL, gmx::MODE_GENERATE, 1, false, false, EMU_WS != 0>(P);
+    if (mode == gmx::MODE_COMPRESS) gmx::StreamKernel<EMU_WB, EMU_WL, gmx::MODE_COMPRESS, EMU_MINB, false, EMU_SERIAL != 0, EMU_WS != 0>(P);
+    else if (mode == gmx::MODE_DECOMPRESS) gmx::StreamKernel<EMU_WB, EMU_WL, gmx::MODE_DECOMPRESS, EMU_MINB, false, false, EMU_WS != 0>(P);
+    else gmx::StreamKernel<EMU_WB, EMU_WL, gmx::MODE_GENERATE, EMU_MINB, false, false, EMU_WS != 0>(P);
   });
   if (!roomy && (R.status == gmx::GMX_ERR_PPMD_ARENA || R.status == gmx::GMX_ERR_MIXER_POOL || R.status == gmx::GMX_ERR_SPARSE_FULL)) {
     fprintf(stderr, "status %u: retrying in a roomy arena (as the host library does)\n", R.status);
@@ -289,7 +292,7 @@ int main(int argc, char** argv) {
     Q.n_streams = 2; Q.queue = &queue2; Q.status = st2;
     Q.arenas = (uint8_t*)(((uintptr_t)R2.arena.data() + 255) & ~(uintptr_t)255); Q.arena_stride = R2.L.total; Q.layout = &R2.L;
     Q.lstm_init = R2.linit.data(); Q.decay = R2.decay.data(); Q.decay_len = (uint32_t)R2.decay.size(); Q.adam = R2.adam.data();
-    cuda_emu::RunBlock(EMU_NT, 0, 1, [&] { gmx::StreamKernel<EMU_WB, EMU_WL, gmx::MODE_COMPRESS, 1, false, EMU_SERIAL != 0, EMU_WS != 0>(Q); });
+    cuda_emu::RunBlock(EMU_NT, 0, 1, [&] { gmx::StreamKernel<EMU_WB, EMU_WL, gmx::MODE_COMPRESS, EMU_MINB, false, EMU_SERIAL != 0, EMU_WS != 0>(Q); });
     if (st2[0] || st2[1]) { fprintf(stderr, "status %u %u\n", st2[0], st2[1]); return 1; }
     WriteAll(argv[4], out.data() + cap, ol[1]);
     return 0;

@@ -99,6 +99,21 @@ def test_serial_compress_configuration(tmp_path):
         assert open(out, "rb").read() == open(os.path.join(GOLD, name + ".gmix"), "rb").read(), name
 
 
+def test_latency_configuration(tmp_path):
+    """Configuration 9 of the library: one CTA per SM, roles 4 / 4 / 1, the dense gate weights resident in (emulated) shared
+    memory and refreshed by bulk copies after every Adam step, straight-line mixer network (LAT), whole-byte prefetch."""
+    exe = str(tmp_path / "emu_main")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-w", "-DEMU_WB=4", "-DEMU_WL=4", "-DEMU_WS=1", "-DEMU_MINB=1", "-o", exe,
+                    os.path.join(HERE, "emu", "emu_main.cpp")], check=True)
+    for name in ("text1k", "random1200", "repetitive"):
+        out = str(tmp_path / (name + ".out"))
+        subprocess.run([exe, "compress", os.path.join(GOLD, name + ".in"), out], check=True, stderr=subprocess.DEVNULL)
+        assert open(out, "rb").read() == open(os.path.join(GOLD, name + ".gmix"), "rb").read(), name
+    back = str(tmp_path / "back")
+    subprocess.run([exe, "decompress", os.path.join(GOLD, "text1k.gmix"), back], check=True, stderr=subprocess.DEVNULL)
+    assert open(back, "rb").read() == open(os.path.join(GOLD, "text1k.in"), "rb").read()
+
+
 @pytest.mark.parametrize("roles", [(1, 2), (1, 1), (2, 2), (3, 0)])   # (3, 0): the two-role variant, PPMd ahead of everything else
 def test_other_role_splits_compute_the_same_bytes(tmp_path, roles):
     """The kernel configurations of the library (kernels.h) differ only in how many warps the bit role and the LSTM role
