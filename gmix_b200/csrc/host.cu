@@ -275,7 +275,6 @@ int RunDevice(gmx_ctx* c, int mode, const uint8_t* d_in, const uint64_t* d_in_of
   P.bit_trace = o.d_bit_trace; P.pred_trace = o.d_pred_trace;
   P.analysis = o.analysis; P.final_state = o.d_final_state;
   P.gen_bytes = o.gen_bytes; P.temperature = o.temperature; P.rand_u = o.d_rand_u; P.rand_stride = o.rand_stride;
-  P.byte_prefetch = gmx::KernelConfig(c->kcfg).minb == 1;
   P.part = o.part; P.part_header = o.part_header; P.part_last = o.part_last; P.part_total = o.part_total; P.coder_in = o.d_coder_in; P.coder_out = o.d_coder_out;
   if (o.model) { P.tmpl_arena = o.model->d_arena; P.tmpl_state = o.model->d_state; P.tmpl_layout = c->layout.ov ? o.model->d_layout : nullptr; }
   const uint32_t grid = n < c->n_arenas ? n : c->n_arenas;

@@ -155,10 +155,6 @@ struct StreamParams {
   uint32_t part, part_header, part_last;
   uint64_t part_total;         // compress: length the header announces; decompress: bytes this part produces
   const uint32_t* coder_in; uint32_t* coder_out;
-  // compress: request the table slots and weight sets of a byte's 8 bits from L2 at its byte boundary (BitBoundaryB). Wins
-  // when a stream has its SM to itself (+1 %), loses when other resident streams already hide the latency (-2 % at 8
-  // CTAs/SM, profiles/r02_ab_byte_prefetch.txt): the host switches it on for the one-CTA-per-SM configurations only.
-  uint32_t byte_prefetch;
 };
 
 // ---- device constant tables --------------------------------------------------------------------
@@ -1579,8 +1575,10 @@ GMX_DEV void BitBoundaryA(StreamSmem& s, const Arena& A, int btid) {
 // known_byte >= 0 (compress): the byte about to be coded. Every table slot and every weight set its 8 bits will touch is
 // then already determined (bit_context of bit j = (1 << j) - 1 + (byte >> (8 - j))): their lines are requested from L2
 // now, so that the per-bit lookups and weight-set swaps of this byte find them there instead of waiting for HBM. These
-// are not extra requests, only earlier ones (the round-1 prefetches guessed both values of the next bit).
-template <int NB>
+// are not extra requests, only earlier ones (the round-1 prefetches guessed both values of the next bit). Wins when a
+// stream has its SM to itself (+1 %), loses when other resident streams already hide the latency (-2 % at 8 CTAs/SM):
+// LAT kernels only.
+template <int NB, bool LAT = false>
 GMX_DEV void BitBoundaryB(StreamSmem& s, const Arena& A, uint32_t b, int btid, int known_byte = -1) {
   const ArenaLayout& L = *A.L;
   if (btid == 0) s.ctx[C_LSTM] = s.pkt[b % PKT_RING].lstm_ctx;
@@ -1591,7 +1589,7 @@ GMX_DEV void BitBoundaryB(StreamSmem& s, const Arena& A, uint32_t b, int btid, i
     const uint32_t base = (s.ctx[s.T.ind[k].ctx] << 8) % M;
     s.ind_base[k] = base;
 #if !defined(GMX_NO_BYTE_PREFETCH)
-    if (known_byte >= 0) {
+    if (LAT && known_byte >= 0) {   // (compiled into the one-CTA-per-SM kernels only: A/B in profiles/r02_ab_byte_prefetch.txt)
       const uint32_t sid = L.ind_sid[k];
 #pragma unroll 1
       for (int j = 0; j < 8; ++j) {
@@ -1605,7 +1603,7 @@ GMX_DEV void BitBoundaryB(StreamSmem& s, const Arena& A, uint32_t b, int btid, i
   }
   for (int m = btid; m < NMIX; m += NB) { s.set_idx[m] = 0xFFFFFFFFu; s.set_pool[m] = 0; s.set_dirty[m] = 0; }
 #if !defined(GMX_NO_BYTE_PREFETCH)
-  if (known_byte >= 0 && !GMX_IS_OV(L)) {
+  if (LAT && known_byte >= 0 && !GMX_IS_OV(L)) {
     // weight sets: the 27 byte-gated mixers' one set, the 4 bit-gated mixers' eight (the two longest-match gates depend on
     // the lookups): directory entry, then the record's lines. Work items = (mixer, bit).
 #pragma unroll 1
@@ -2170,7 +2168,7 @@ GMX_DEV void BitRoleCompress(StreamSmem& s, const Arena& A, const StreamParams& 
         lap.mark(2);
         WaitAtLeast(s, &s.n_pkt, pos + 1, 100);
         lap.mark(1);
-        BitBoundaryB<NB>(s, A, pos, btid, P.byte_prefetch ? (int)c : -1);
+        BitBoundaryB<NB, LAT>(s, A, pos, btid, (int)c);
         lap.mark(2);
       }
       PredictBit<NB, PROF, LAT>(s, A, P, pos, 7 - j, btid, lap, NB > 32 ? bit : -1);
@@ -2213,7 +2211,7 @@ GMX_DEV void BitLstmRoleCompress(StreamSmem& s, const Arena& A, const StreamPara
         GroupSync<NB>(BAR_BIT);   // every staged weight set is back in the pool: s.w is free for the forward pass's ring
         lap.mark(1);
         LstmForward<NB, PROF, true>(s, A, P, pos, pos ? J.in[pos - 1] : s.byte0, (int)c, btid, lap, ws);
-        BitBoundaryB<NB>(s, A, pos, btid, P.byte_prefetch ? (int)c : -1);
+        BitBoundaryB<NB, LAT>(s, A, pos, btid, (int)c);
         lap.mark(2);
       }
       PredictBit<NB, PROF, LAT>(s, A, P, pos, 7 - j, btid, lap, bit);
@@ -2250,7 +2248,7 @@ GMX_DEV void SerialPredict(StreamSmem& s, const Arena& A, const StreamParams& P,
     __syncthreads();
     lap.mark(2);
     LstmForward<NT, PROF, true>(s, A, P, 0, last, known_byte, tid, lap, ws);
-    BitBoundaryB<NT>(s, A, 0, tid, P.byte_prefetch ? known_byte : -1);
+    BitBoundaryB<NT, LAT>(s, A, 0, tid, known_byte);
   }
   PredictBit<NT, PROF, LAT>(s, A, P, 0, path_bit, tid, lap, learn_bit);
 }

@@ -84,7 +84,7 @@ retry:
   gmx::FillLstmInit(R.linit);
   static uint32_t queue;
   queue = 0;
-  P.n_streams = 1; P.queue = &queue; P.byte_prefetch = 1;   // (exercises the address arithmetic of the whole-byte prefetch)
+  P.n_streams = 1; P.queue = &queue;
   P.arenas = (uint8_t*)(((uintptr_t)R.arena.data() + 255) & ~(uintptr_t)255); P.arena_stride = R.L.total; P.layout = &R.L;
   P.lstm_init = R.linit.data(); P.decay = R.decay.data(); P.decay_len = (uint32_t)R.decay.size(); P.adam = R.adam.data();
   memset(R.usage, 0, sizeof(R.usage));
