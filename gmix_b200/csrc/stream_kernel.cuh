@@ -405,7 +405,11 @@ GMX_DEV inline uint32_t HistByte(const Arena& A, uint32_t pos) {
 // belongs to. A set that has not learned since it was staged is skipped (its record is current). Overlay mode: a changed
 // set of the model moves to a fresh local record and the overlay directory follows.
 GMX_DEV inline void WriteBackSet(StreamSmem& s, const Arena& A, int m, uint32_t old, uint32_t idx, int lane) {
+#if GMX_OVERLAY
   if (!old || !s.set_dirty[m]) return;
+#else
+  if (!old) return;   // (compress / decompress learn every bit: a staged set is always dirty, no bookkeeping there)
+#endif
   const ArenaLayout& L = *A.L;
   uint32_t id = old;
   if (GMX_IS_OV(L) && old < L.base_sets) {
@@ -1066,9 +1070,13 @@ GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, u
   // HBM latency behind them (the lines are consumed within this pass, long before L2 could evict them).
   {
     const float* W = A.at<float>(L.l_w);
-    if (ltid == 0) {   // one bulk prefetch instruction per contiguous range
-      if (!RING && !ws.w) for (int g = 0; g < 3; ++g) BulkPrefetchL2(W + LstmW(g, L_NOUT, 0), W_DENSE_Q * L_CELLS * 16);
-      BulkPrefetchL2(A.at<float>(L.l_wout) + (size_t)e * L_HID * L_NOUT, L_HID * L_NOUT * 4);
+    // (measured at 8 CTAs/SM: per-thread prefetch instructions beat one bulk prefetch by 1 %; the bulk form serves the
+    // resident-weight configurations, whose roles have better things to do than issue 400 prefetches)
+    if (ws.w) {
+      if (ltid == 0) BulkPrefetchL2(A.at<float>(L.l_wout) + (size_t)e * L_HID * L_NOUT, L_HID * L_NOUT * 4);
+    } else {
+      if (!RING) for (int g = 0; g < 3; ++g) PrefetchRange(W + LstmW(g, L_NOUT, 0), W_DENSE_Q * L_CELLS * 16, ltid, NL);
+      PrefetchRange(A.at<float>(L.l_wout) + (size_t)e * L_HID * L_NOUT, L_HID * L_NOUT * 4, ltid, NL);
     }
   }
   // layer_input[e] = [ppm 256 | hidden 50 | 1]  (SetInput lstm.cpp:45-50, copy :94-96)
@@ -1223,11 +1231,15 @@ GMX_DEV void LstmBptt(StreamSmem& s, const Arena& A, const StreamParams& P, int 
   }
   GroupSync<NL>(BAR_LSTM);
   constexpr int CPT = (L_CELLS + NL - 1) / NL;   // cells per thread in the cell-parallel phases (2 when the role is one warp)
-  if (ltid == 0) BulkPrefetchL2(A.at<float>(L.l_wout) + (size_t)(L_HORIZON - 1) * L_HID * L_NOUT, L_HID * L_NOUT * 4);
+  if (!ws.w) PrefetchRange(A.at<float>(L.l_wout) + (size_t)(L_HORIZON - 1) * L_HID * L_NOUT, L_HID * L_NOUT * 4, ltid, NL);
+  else if (ltid == 0) BulkPrefetchL2(A.at<float>(L.l_wout) + (size_t)(L_HORIZON - 1) * L_HID * L_NOUT, L_HID * L_NOUT * 4);
 #pragma unroll 1
   for (int ep = L_HORIZON - 1; ep >= 0; --ep) {
     // the output layer of the next (earlier) epoch: 52 KB this pass will stream one epoch from now
-    if (ep > 0 && ltid == 0) BulkPrefetchL2(A.at<float>(L.l_wout) + (size_t)(ep - 1) * L_HID * L_NOUT, L_HID * L_NOUT * 4);
+    if (ep > 0) {
+      if (!ws.w) PrefetchRange(A.at<float>(L.l_wout) + (size_t)(ep - 1) * L_HID * L_NOUT, L_HID * L_NOUT * 4, ltid, NL);
+      else if (ltid == 0) BulkPrefetchL2(A.at<float>(L.l_wout) + (size_t)(ep - 1) * L_HID * L_NOUT, L_HID * L_NOUT * 4);
+    }
     const float* out_e = A.at<float>(L.l_out) + ep * L_NOUT;
     for (int i = ltid; i < L_NOUT; i += NL)
       s.l_err256[i] = (uint32_t)i == s.l_hist[ep] ? f_sub(out_e[i], 1.0f) : out_e[i];
@@ -2034,7 +2046,9 @@ GMX_UNROLL(LAT ? 3 : 1)
     const bool shrink = s.shrink[m] != 0;
     const float keep = f_sub(1.0f, 3.0e-6f);
     float* w = s.w + WOff(m);
+#if GMX_OVERLAY
     if (lane == 0) s.set_dirty[m] = 1;
+#endif
     if (m < NL0) {
       // Layer 0: inputs = [90 predictions | outputs of the earlier layer-0 neurons] = s.xe[0 .. nw) (inactive
       // predictions are +0 there and are skipped through the `use` bytes); one float4 per lane covers them all.
