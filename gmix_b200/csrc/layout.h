@@ -172,7 +172,7 @@ inline ArenaLayout MakeLayout(uint64_t max_len, bool roomy = false, const Preloa
 // overlay entries = every table write (41 Indirect states per learned bit, 6 Match pointers per learned byte, one
 // IndirectHash update per table and byte, one directory entry per new or changed weight set); weight sets = at most 27
 // byte-gated + 6 x 8 bit-gated or longest-match-gated ones change per learned byte.
-inline ArenaLayout MakeOverlayLayout(const ArenaLayout& base, const Preload& pre, uint64_t learn_bytes, uint64_t new_bytes) {
+inline ArenaLayout MakeOverlayLayout(const ArenaLayout& base, const Preload& pre, uint64_t learn_bytes, uint64_t new_bytes, bool force_segmented = false) {
   ArenaLayout L;
   memset(&L, 0, sizeof(L));
   uint64_t off = 0;
@@ -212,9 +212,14 @@ inline ArenaLayout MakeOverlayLayout(const ArenaLayout& base, const Preload& pre
   L.l_errh = take(3ull * L_HORIZON * L_CELLS * 4);
   L.l_wt = take(3ull * L_CELLS * L_CELLS * 4);
   L.p_state = take(sizeof(PpmdState));
-  // PPMd: segmented private backing (ppmd.cuh): what the model uses of each area + room for new_bytes more
-  // (one text byte per input byte; units: the same worst-case allowance MakeLayout's roomy class uses, per area)
-  {
+  // PPMd: the model's power-of-two window copied whole while it is small (one AND per heap access); beyond 32 MiB a
+  // segmented private backing (ppmd.cuh; two compares per access, measured 25 % slower generation on a small model): what
+  // the model uses of each area + room for new_bytes more (one text byte per input byte; units: the same worst-case
+  // allowance MakeLayout's roomy class uses, per area)
+  if (!force_segmented && (uint64_t)base.p_mask + 1 <= (32ull << 20)) {
+    L.p_mask = base.p_mask; L.p_text_cap = base.p_text_cap; L.p_units_cap = base.p_units_cap;
+    L.p_heap = take((uint64_t)L.p_mask + 1);
+  } else {
     const uint64_t grow = 400 * new_bytes + (64u << 10);
     L.p_mask = 0;
     L.p_text_cap = (uint32_t)AlignUp(pre.ppmd_text_bytes + new_bytes + 64, 16);

@@ -696,7 +696,9 @@ GMX_DEV void InitStream(StreamSmem& s, const Arena& A, const StreamParams& P, in
       copy(L.l_tanh, B.l_tanh, (uint64_t)L_HORIZON * L_CELLS * 4); copy(L.l_ig, B.l_ig, (uint64_t)L_HORIZON * L_CELLS * 4);
       copy(L.l_last, B.l_last, (uint64_t)L_HORIZON * L_CELLS * 4);
       copy(L.p_state, B.p_state, sizeof(PpmdState));
-      {   // the three live areas of the model's PPMd heap (a power-of-two window there) into the segmented private backing
+      if (L.p_mask) {   // small model: its whole power-of-two window
+        copy(L.p_heap, B.p_heap, (uint64_t)L.p_mask + 1);
+      } else {   // the three live areas of the model's PPMd heap (a power-of-two window there) into the segmented private backing
         const PpmdState* bs = (const PpmdState*)(P.tmpl_arena + B.p_state);
         const uint8_t* bh = P.tmpl_arena + B.p_heap;
         uint8_t* h = A.at<uint8_t>(L.p_heap);

@@ -105,7 +105,7 @@ retry:
     if (overlay_learn) {
       static gmx::ArenaLayout base;
       base = R.L;
-      R.L = gmx::MakeOverlayLayout(base, pre, overlay_learn, new_bytes);
+      R.L = gmx::MakeOverlayLayout(base, pre, overlay_learn, new_bytes, getenv("EMU_SEGMENTED") != nullptr);
       R.arena.assign(R.L.total + 256, 0xCD);   // nothing in the overlay arena may be assumed zero
       P.arenas = (uint8_t*)(((uintptr_t)R.arena.data() + 255) & ~(uintptr_t)255); P.arena_stride = R.L.total; P.layout = &R.L;
       P.tmpl_layout = &base;
