@@ -499,6 +499,28 @@ def run_ours(args):
                     "workload": f"configs[3]: {npr} prompts x {G} B per GPU from a checkpoint trained on {T} B (BASELINE.json: 1 MB; stated reduction), every "
                                 "stream an overlay of the shared model (no clone of its tables); host buffers, H2D of prompts + draws and D2H of samples "
                                 "inside the timed region"}
+        # the same batch in the two LOCK-STEP modes (gmix_b200.h GMX_GEN_*): all streams advance one sampled byte per launch and
+        # the LSTM gate products of a byte step are one batched kernel - with the reference's arithmetic (same bytes), or on the
+        # tensor cores (tcgen05 kind::tf32, 3xTF32; summation order differs, so the divergence from the exact samples is reported)
+        for mode, key in ((ctx.GEN_LOCKSTEP_EXACT, "lockstep_exact"), (ctx.GEN_LOCKSTEP_TENSOR, "lockstep_tensor")):
+            ctx.set_generation_mode(mode)
+            ctx.generate_batch(model, prompts, 1)
+            barrier()
+            t0 = time.perf_counter()
+            out2 = ctx.generate_batch(model, prompts, G, 1.0)
+            barrier()
+            s2 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(s2, op=dist.ReduceOp.MAX)
+            ran = ctx.last_generation_mode
+            same = sum(a == b for a, b in zip(out, out2))
+            firsts = [next(i for i in range(G) if a[i] != b[i]) for a, b in zip(out, out2) if a != b]
+            generate[key] = {"value": world * npr * G / float(s2.item()), "unit": "generated bytes/s", "kernel_ms": ctx.last_kernel_ms, "mode_ran": ran,
+                             "streams_identical_to_per_stream": same, "streams": npr,
+                             "mean_first_differing_byte": (sum(firsts) / len(firsts)) if firsts else None}
+            if mode == ctx.GEN_LOCKSTEP_EXACT and ran == mode and same != npr:
+                raise SystemExit("bench.py: lock-step generation with the exact gate product differs from per-stream generation")
+        ctx.set_generation_mode(ctx.GEN_PER_STREAM)
         model.close()
         ctx.set_cuda_stream(stream.cuda_stream)
 

@@ -97,6 +97,9 @@ def load_library():
     lib.gmx_pred_write_checkpoint.argtypes = [C.c_void_p] + blobs
     lib.gmx_pred_read_checkpoint.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
     lib.gmx_selftest_math.argtypes = [C.c_void_p, C.c_uint32, u64p, u32p]
+    lib.gmx_set_generation_mode.argtypes = [C.c_void_p, C.c_int]
+    lib.gmx_last_generation_mode.argtypes = [C.c_void_p]
+    lib.gmx_selftest_gate.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, u64p, C.POINTER(C.c_double)]
     _LIB = lib
     return lib
 
@@ -444,6 +447,25 @@ class Context:
         if n < 0:
             self._check(n, "gmx_get_usage")
         return buf[:n]
+
+    GEN_PER_STREAM, GEN_LOCKSTEP_EXACT, GEN_LOCKSTEP_TENSOR = 0, 1, 2
+
+    def set_generation_mode(self, mode):
+        """How generate_batch runs the sampling phase (gmix_b200.h: GMX_GEN_*): per stream, lock-step with the exact batched
+        gate product, or lock-step with the tensor-core (tcgen05) gate product."""
+        self._check(self.lib.gmx_set_generation_mode(self.h, int(mode)), "gmx_set_generation_mode")
+
+    @property
+    def last_generation_mode(self):
+        return int(self.lib.gmx_last_generation_mode(self.h))
+
+    def selftest_gate(self, n_slots=300, seed=1):
+        """Batched gate product kernels on seeded random operands: (entries of the exact kernel that differ bitwise from the
+        host loop in the reference's order, max |tensor-core - fp64|, max |sequential fp32 - fp64|, max |value|)."""
+        bad = C.c_uint64(0)
+        err = (C.c_double * 3)()
+        self._check(self.lib.gmx_selftest_gate(self.h, n_slots, seed, C.byref(bad), err), "gmx_selftest_gate")
+        return int(bad.value), float(err[0]), float(err[1]), float(err[2])
 
     def selftest_math(self, stride=1):
         mism = (C.c_uint64 * 3)()

@@ -6,8 +6,8 @@ import sys
 ROOT = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(ROOT, "csrc")
 LIB = os.path.join(ROOT, "lib", "libgmix_b200.so")
-SOURCES = ["host.cu", "kernel_compress.cu", "kernel_decompress.cu", "kernel_compress_prof.cu", "kernel_step.cu", "kernel_generate.cu"]
-DEPS = ["host.cu", "kernel_compress.cu", "kernel_decompress.cu", "kernel_compress_prof.cu", "kernel_step.cu", "kernel_generate.cu", "checkpoint.h", "kernels.h", "stream_kernel.cuh", "ppmd.cuh", "dmath.cuh", "spec.cuh", "layout.h", "nonstationary.inc",
+SOURCES = ["host.cu", "kernel_compress.cu", "kernel_decompress.cu", "kernel_compress_prof.cu", "kernel_step.cu", "kernel_generate.cu", "kernel_genstep.cu", "kernel_gate.cu"]
+DEPS = ["host.cu", "kernel_compress.cu", "kernel_decompress.cu", "kernel_compress_prof.cu", "kernel_step.cu", "kernel_generate.cu", "kernel_genstep.cu", "kernel_gate.cu", "gate_gemm.cuh", "checkpoint.h", "kernels.h", "stream_kernel.cuh", "ppmd.cuh", "dmath.cuh", "spec.cuh", "layout.h", "nonstationary.inc",
         os.path.join("..", "..", "include", "gmix_b200.h"), os.path.join("..", "host", "runner.cpp"), os.path.join("..", "host", "predictor.h"),
         os.path.join("..", "host", "coder.h"), os.path.join("..", "host", "multi_gpu.h"), os.path.join("..", "host", "shard.h"),
         os.path.join("..", "..", "scripts", "ncu_case.cpp")]

@@ -59,6 +59,14 @@ struct gmx_ctx {
   std::vector<float> h_decay;
   // staging buffers of the host-pointer entry points
   DevBuf b_in, b_out, b_in_off, b_out_off, b_out_len, b_status, b_trace, b_ptrace, b_prof, b_ids, b_usage, b_rand, b_final, b_coder;
+  // lock-step batched generation (gate_gemm.cuh): parked stream states, operand planes / byte in front / pre-activations of the
+  // batched gate product, the model's tiled weight planes
+  DevBuf b_park, b_gx, b_gsym, b_gg, b_wt;
+  enum { kGroups = 4 };
+  cudaStream_t gen_stream[kGroups] = {nullptr, nullptr, nullptr, nullptr};   // one per group of lock-step streams
+  cudaEvent_t gen_done[kGroups] = {nullptr, nullptr, nullptr, nullptr}, gen_fork = nullptr;
+  int gen_mode = 0;        // GMX_GEN_* requested by gmx_set_generation_mode
+  int last_gen_mode = 0;   // what the last generation call actually ran
   bool profile = false;
   uint32_t prof_streams = 0;
   uint32_t usage_streams = 0;
@@ -76,6 +84,7 @@ struct gmx_model {
   gmx::ArenaLayout layout;
   gmx::Preload pre;
   uint64_t max_new_bytes = 0;
+  uint32_t l_epoch = 0;      // LSTM epoch slot of the parked stream: bytes learned since the model's last BPTT pass (lstm.cpp:57-79)
   uint8_t* d_arena = nullptr;
   uint32_t* d_state = nullptr;
   gmx::ArenaLayout* d_layout = nullptr;   // the model's layout on the device (overlay-mode streams read the model's arena through it)
@@ -440,7 +449,8 @@ void gmx_destroy(gmx_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   FreeArenas(c);
-  for (DevBuf* b : {&c->b_in, &c->b_out, &c->b_in_off, &c->b_out_off, &c->b_out_len, &c->b_status, &c->b_trace, &c->b_ptrace, &c->b_prof, &c->b_ids, &c->b_usage, &c->b_rand, &c->b_final, &c->b_coder})
+  for (DevBuf* b : {&c->b_in, &c->b_out, &c->b_in_off, &c->b_out_off, &c->b_out_len, &c->b_status, &c->b_trace, &c->b_ptrace, &c->b_prof, &c->b_ids, &c->b_usage, &c->b_rand, &c->b_final, &c->b_coder,
+                     &c->b_park, &c->b_gx, &c->b_gsym, &c->b_gg, &c->b_wt})
     if (b->p) cudaFree(b->p);
   if (c->d_layout) cudaFree(c->d_layout);
   if (c->d_roomy_layout) cudaFree(c->d_roomy_layout);
@@ -448,6 +458,11 @@ void gmx_destroy(gmx_ctx* c) {
   if (c->d_adam) cudaFree(c->d_adam);
   if (c->d_decay) cudaFree(c->d_decay);
   if (c->d_queue) cudaFree(c->d_queue);
+  for (int g = 0; g < gmx_ctx::kGroups; ++g) {
+    if (c->gen_stream[g]) cudaStreamDestroy(c->gen_stream[g]);
+    if (c->gen_done[g]) cudaEventDestroy(c->gen_done[g]);
+  }
+  if (c->gen_fork) cudaEventDestroy(c->gen_fork);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -560,6 +575,7 @@ int gmx_model_load(gmx_ctx* c, const void* short_blob, uint64_t short_len, const
     ok = gmx::ckpt::ToArena(im, m->layout, arena.data(), (gmx::StreamSmem*)state.data(), &err);
   }
   if (!ok) { delete m; return Fail(c, GMX_E_ARG, "checkpoint: %s", err.c_str()); }
+  m->l_epoch = ((const gmx::StreamSmem*)state.data())->l_epoch;
   if (cudaMalloc(&m->d_arena, m->layout.total) != cudaSuccess || cudaMalloc(&m->d_state, sizeof(gmx::StreamSmem)) != cudaSuccess ||
       cudaMalloc(&m->d_layout, sizeof(gmx::ArenaLayout)) != cudaSuccess ||
       cudaMemcpy(m->d_layout, &m->layout, sizeof(gmx::ArenaLayout), cudaMemcpyHostToDevice) != cudaSuccess ||
@@ -597,13 +613,129 @@ int gmx_decompress_batch_from(gmx_ctx* c, const gmx_model* model, const uint8_t*
   return RunHost(c, gmx::MODE_DECOMPRESS, in, in_off, n, out, out_off, out_len, status, nullptr, nullptr, o);
 }
 
+namespace {
+// Lock-step batched generation (stream_kernel.cuh: StreamParams::lockstep, GenStepKernel; gate_gemm.cuh). Waves of at most n_arenas
+// streams: one launch consumes the prompts (with learning, per stream), then every sampled byte is one batched gate product
+// (exact SIMT or tcgen05) + one GenStepKernel launch over all streams of the wave.
+constexpr int kGenGroups = gmx_ctx::kGroups;
+int RunLockstepGenerate(gmx_ctx* c, const gmx_model* model, const uint8_t* d_prompts, const uint64_t* d_prompt_off, uint32_t n, uint32_t out_bytes,
+                        float temperature, const float* d_rand_u, uint64_t rand_stride, uint8_t* d_out, uint64_t* d_out_len, uint32_t* d_status,
+                        uint64_t max_prompt_len, bool tensor) {
+  GMX_CUDA(c, cudaSetDevice(c->device));
+  if (model->ctx != c) return Fail(c, GMX_E_ARG, "model belongs to another context");
+  const uint64_t max_len = max_prompt_len + out_bytes;
+  if (max_len > model->max_new_bytes) return Fail(c, GMX_E_ARG, "stream of %llu bytes exceeds the max_new_bytes (%llu) the model was loaded with",
+                                                  (unsigned long long)max_len, (unsigned long long)model->max_new_bytes);
+  if (c->kcfg != gmx::kThroughputConfig) { c->kcfg = gmx::kThroughputConfig; FreeArenas(c); }   // GenStepKernel is that configuration's CTA
+  int rc = ConfigureForModel(c, model, max_prompt_len ? max_prompt_len : max_len, max_len);
+  if (rc) return rc;
+  const uint32_t cap = c->n_arenas;
+  // The arenas are split into up to kGenGroups GROUPS that advance independently, each in its own CUDA stream: a byte step is a
+  // barrier over the streams of ONE group only, and while one group waits for its slowest stream or runs its (small) gate product
+  // the other groups' step kernels keep the SMs busy.
+  const uint32_t ng = cap >= 4 * gmx::GG_M ? (uint32_t)kGenGroups : 1u;
+  const uint32_t gs = (cap + ng - 1) / ng;                                   // arena slots per group
+  const size_t state_bytes = sizeof(gmx::StreamSmem);
+  const size_t gx_floats = gmx::GateXFloats(gs), gsym_words = (size_t)gs + 128, gg_floats = ((size_t)gs + gmx::GG_M) * gmx::GG_N;
+  if ((rc = Reserve(c, c->b_park, (size_t)cap * state_bytes))) return rc;
+  if ((rc = Reserve(c, c->b_gx, ng * gx_floats * 4))) return rc;
+  if ((rc = Reserve(c, c->b_gsym, ng * gsym_words * 4))) return rc;
+  if ((rc = Reserve(c, c->b_gg, ng * gg_floats * 4))) return rc;
+  if ((rc = Reserve(c, c->b_wt, (size_t)gmx::GateWtFloats() * 4))) return rc;
+  if ((rc = Reserve(c, c->b_usage, (size_t)n * 32))) return rc;
+  c->usage_streams = n;
+  for (uint32_t g = 0; g < ng; ++g) {
+    if (!c->gen_stream[g]) GMX_CUDA(c, cudaStreamCreateWithFlags(&c->gen_stream[g], cudaStreamNonBlocking));
+    if (!c->gen_done[g]) GMX_CUDA(c, cudaEventCreateWithFlags(&c->gen_done[g], cudaEventDisableTiming));
+  }
+  if (!c->gen_fork) GMX_CUDA(c, cudaEventCreateWithFlags(&c->gen_fork, cudaEventDisableTiming));
+  GMX_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+  GMX_CUDA(c, cudaMemsetAsync(c->b_gx.p, 0, ng * gx_floats * 4, c->stream));    // rows of a partial last tile stay finite
+  GMX_CUDA(c, cudaMemsetAsync(c->b_gsym.p, 0, ng * gsym_words * 4, c->stream));
+  const float* d_w = (const float*)(model->d_arena + model->layout.l_w);
+  if (tensor) GMX_CUDA(c, gmx::LaunchGateWeightPrep(d_w, (float*)c->b_wt.p, c->stream));
+  GMX_CUDA(c, cudaEventRecord(c->gen_fork, c->stream));
+  gmx::StreamParams P;
+  memset(&P, 0, sizeof(P));
+  P.in = d_prompts; P.in_off = d_prompt_off; P.out = d_out; P.out_len = d_out_len; P.status = d_status;
+  P.n_streams = n; P.queue = c->d_queue;
+  P.arena_stride = c->layout.total; P.layout = c->d_layout;
+  P.lstm_init = c->d_lstm_init; P.decay = c->d_decay; P.decay_len = c->decay_len; P.adam = c->d_adam;
+  P.analysis = -1; P.usage = (uint32_t*)c->b_usage.p;
+  P.gen_bytes = out_bytes; P.temperature = temperature; P.rand_u = d_rand_u; P.rand_stride = rand_stride;
+  P.tmpl_arena = model->d_arena; P.tmpl_state = model->d_state; P.tmpl_layout = c->layout.ov ? model->d_layout : nullptr;
+  P.lockstep = 1;
+  c->last_ms = 0;
+  c->last_grid = n < cap ? n : cap;
+  gmx::GenStepParams Q[kGenGroups];
+  for (uint32_t g = 0; g < ng; ++g) {   // block b of a group's launches = arena slot g * gs + b
+    gmx::StreamParams& G = Q[g].P;
+    G = P;
+    G.arenas = c->d_arenas + (uint64_t)g * gs * c->layout.total;
+    G.park = (uint32_t*)c->b_park.p + (size_t)g * gs * (state_bytes / 4);
+    G.final_state = G.park;
+    G.gate_x = (float*)c->b_gx.p + g * gx_floats; G.gate_sym = (uint32_t*)c->b_gsym.p + g * gsym_words; G.gate_g = (const float*)c->b_gg.p + g * gg_floats;
+    GMX_CUDA(c, cudaStreamWaitEvent(c->gen_stream[g], c->gen_fork, 0));
+  }
+  for (uint32_t base = 0; base < n;) {   // rounds: every group takes the next range of streams that fits its slots
+    uint32_t active = 0;
+    for (uint32_t g = 0; g < ng && base < n; ++g) {
+      const uint32_t room = std::min<uint32_t>(gs, cap - g * gs);
+      Q[g].n_slots = std::min<uint32_t>(room, n - base);
+      Q[g].P.stream_base = base;
+      base += Q[g].n_slots;
+      active = g + 1;
+      GMX_CUDA(c, gmx::LaunchGenerate(c->kcfg, Q[g].P, Q[g].n_slots, c->gen_stream[g]));
+      c->launches += 1;
+    }
+    for (uint32_t i = 0; i < out_bytes; ++i)
+      for (uint32_t g = 0; g < active; ++g) {
+        const gmx::StreamParams& G = Q[g].P;
+        if (tensor) GMX_CUDA(c, gmx::LaunchGateTc(G.gate_x, (const float*)c->b_wt.p, d_w, G.gate_sym, (float*)G.gate_g, Q[g].n_slots, c->gen_stream[g]));
+        else GMX_CUDA(c, gmx::LaunchGateExact(d_w, G.gate_x, G.gate_sym, (float*)G.gate_g, Q[g].n_slots, (unsigned)c->sm_count, c->gen_stream[g]));
+        Q[g].byte_index = i; Q[g].last = i + 1 == out_bytes;
+        GMX_CUDA(c, gmx::LaunchGenStep(Q[g], Q[g].n_slots, c->gen_stream[g]));
+        c->launches += 2;
+      }
+  }
+  for (uint32_t g = 0; g < ng; ++g) {
+    GMX_CUDA(c, cudaEventRecord(c->gen_done[g], c->gen_stream[g]));
+    GMX_CUDA(c, cudaStreamWaitEvent(c->stream, c->gen_done[g], 0));
+  }
+  GMX_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+  GMX_CUDA(c, cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  GMX_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->last_ms = ms;
+  return 0;
+}
+}  // namespace
+
+int gmx_set_generation_mode(gmx_ctx* c, int mode) {
+  if (!c) return GMX_E_ARG;
+  if (mode < GMX_GEN_PER_STREAM || mode > GMX_GEN_LOCKSTEP_TENSOR) return Fail(c, GMX_E_ARG, "generation mode %d out of range", mode);
+  c->gen_mode = mode;
+  return 0;
+}
+int gmx_last_generation_mode(const gmx_ctx* c) { return c ? c->last_gen_mode : -1; }
+
 int gmx_generate_batch_device(gmx_ctx* c, const gmx_model* model, const uint8_t* d_prompts, const uint64_t* d_prompt_off, uint32_t n,
                               uint32_t out_bytes, float temperature, const float* d_rand_u, uint64_t rand_stride, uint8_t* d_out,
                               uint64_t* d_out_len, uint32_t* d_status, uint64_t max_prompt_len) {
   if (!c || !model) return GMX_E_ARG;
   if (!d_rand_u) return Fail(c, GMX_E_ARG, "null pointer argument");
+  const float temp = temperature < (float)0.001 ? (float)0.001 : temperature;   // runner-utils.cpp:170
+  // The batched gate product needs the gate matrix to be the model's in every stream: no stream may reach a BPTT pass while it
+  // learns its prompt (all but the prompt's last byte are learned; a pass runs when the epoch slot wraps at L_HORIZON).
+  const bool shared_gates = max_prompt_len >= 1 && model->l_epoch + (max_prompt_len - 1) < (uint64_t)gmx::L_HORIZON;
+  if (c->gen_mode != GMX_GEN_PER_STREAM && shared_gates && n && out_bytes) {
+    c->last_gen_mode = c->gen_mode;
+    return RunLockstepGenerate(c, model, d_prompts, d_prompt_off, n, out_bytes, temp, d_rand_u, rand_stride, d_out, d_out_len, d_status, max_prompt_len,
+                               c->gen_mode == GMX_GEN_LOCKSTEP_TENSOR);
+  }
+  c->last_gen_mode = GMX_GEN_PER_STREAM;
   RunOpts o; o.model = model; o.gen_bytes = out_bytes; o.d_rand_u = d_rand_u; o.rand_stride = rand_stride; o.overlay_learn = max_prompt_len;
-  o.temperature = temperature < (float)0.001 ? (float)0.001 : temperature;   // runner-utils.cpp:170
+  o.temperature = temp;
   return RunDevice(c, gmx::MODE_GENERATE, d_prompts, d_prompt_off, n, d_out, nullptr, d_out_len, d_status, max_prompt_len + out_bytes, o);
 }
 
@@ -964,6 +1096,68 @@ uint64_t gmx_retried_streams(const gmx_ctx* c) { return c ? c->retried_streams :
 uint64_t gmx_kernel_launches(const gmx_ctx* c) { return c ? c->launches : 0; }
 double gmx_last_kernel_ms(const gmx_ctx* c) { return c ? c->last_ms : 0; }
 int gmx_device_sm_count(const gmx_ctx* c) { return c ? c->sm_count : 0; }
+
+int gmx_selftest_gate(gmx_ctx* c, uint32_t n_slots, uint32_t seed, uint64_t* exact_mismatches, double err[3]) {
+  if (!c || !exact_mismatches || !err || n_slots == 0 || n_slots > 65536) return GMX_E_ARG;
+  GMX_CUDA(c, cudaSetDevice(c->device));
+  uint64_t rs = seed * 2654435761ull + 88172645463325252ull;
+  auto rnd = [&]() { rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17; return (float)((rs >> 40) & 0xffffff) / 16777216.0f; };   // [0, 1)
+  std::vector<float> W(gmx::L_WSIZE), X(gmx::GateXFloats(n_slots), 0.0f), xv((size_t)n_slots * gmx::GG_K, 0.0f);
+  std::vector<uint32_t> sym(n_slots);
+  for (auto& w : W) w = (rnd() - 0.5f) * 0.6f;
+  for (uint32_t s = 0; s < n_slots; ++s) {
+    float sum = 0;
+    for (int k = 0; k < 256; ++k) { const float r = rnd(); xv[(size_t)s * gmx::GG_K + k] = r * r * r * r; sum += r * r * r * r; }
+    for (int k = 0; k < 256; ++k) xv[(size_t)s * gmx::GG_K + k] /= sum;
+    for (int k = 256; k < 306; ++k) xv[(size_t)s * gmx::GG_K + k] = rnd() * 2.0f - 1.0f;
+    xv[(size_t)s * gmx::GG_K + 306] = 1.0f;
+    sym[s] = (uint32_t)(rnd() * 256.0f) & 0xffu;
+    for (int k = 0; k < gmx::GG_K; ++k) {
+      const float v = xv[(size_t)s * gmx::GG_K + k], hi = gmx::Tf32Hi(v);
+      X[gmx::GateXIndex(s, k, 0)] = hi; X[gmx::GateXIndex(s, k, 1)] = v - hi;
+    }
+  }
+  float *dW = nullptr, *dX = nullptr, *dWt = nullptr, *dG = nullptr, *dG2 = nullptr; uint32_t* dS = nullptr;
+  const size_t g_bytes = ((size_t)n_slots + gmx::GG_M) * gmx::GG_N * 4;
+  GMX_CUDA(c, cudaMalloc(&dW, W.size() * 4)); GMX_CUDA(c, cudaMalloc(&dX, X.size() * 4)); GMX_CUDA(c, cudaMalloc(&dWt, (size_t)gmx::GateWtFloats() * 4));
+  GMX_CUDA(c, cudaMalloc(&dG, g_bytes)); GMX_CUDA(c, cudaMalloc(&dG2, g_bytes)); GMX_CUDA(c, cudaMalloc(&dS, (size_t)n_slots * 4 + 512));
+  GMX_CUDA(c, cudaMemcpy(dW, W.data(), W.size() * 4, cudaMemcpyHostToDevice));
+  GMX_CUDA(c, cudaMemcpy(dX, X.data(), X.size() * 4, cudaMemcpyHostToDevice));
+  GMX_CUDA(c, cudaMemset(dS, 0, (size_t)n_slots * 4 + 512));
+  GMX_CUDA(c, cudaMemcpy(dS, sym.data(), (size_t)n_slots * 4, cudaMemcpyHostToDevice));
+  GMX_CUDA(c, cudaMemset(dG, 0, g_bytes)); GMX_CUDA(c, cudaMemset(dG2, 0, g_bytes));
+  GMX_CUDA(c, gmx::LaunchGateWeightPrep(dW, dWt, c->stream));
+  GMX_CUDA(c, gmx::LaunchGateExact(dW, dX, dS, dG, n_slots, (unsigned)c->sm_count, c->stream));
+  GMX_CUDA(c, gmx::LaunchGateTc(dX, dWt, dW, dS, dG2, n_slots, c->stream));
+  c->launches += 3;
+  GMX_CUDA(c, cudaStreamSynchronize(c->stream));
+  std::vector<float> G((size_t)n_slots * gmx::GG_N), G2((size_t)n_slots * gmx::GG_N);
+  GMX_CUDA(c, cudaMemcpy(G.data(), dG, G.size() * 4, cudaMemcpyDeviceToHost));
+  GMX_CUDA(c, cudaMemcpy(G2.data(), dG2, G2.size() * 4, cudaMemcpyDeviceToHost));
+  cudaFree(dW); cudaFree(dX); cudaFree(dWt); cudaFree(dG); cudaFree(dG2); cudaFree(dS);
+  uint64_t bad = 0;
+  double e_tc = 0, e_seq = 0, mag = 0;
+  for (uint32_t s = 0; s < n_slots; ++s)
+    for (int r = 0; r < gmx::GG_ROWS; ++r) {
+      const int g = r / gmx::L_CELLS, i = r - g * gmx::L_CELLS;
+      volatile float f = W[gmx::LstmW(g, (int)sym[s], i)];
+      double d = (double)f;
+      for (int k = 0; k < gmx::GG_KUSED; ++k) {
+        const float x = xv[(size_t)s * gmx::GG_K + k], w = W[gmx::LstmW(g, gmx::L_NOUT + k, i)];
+        volatile float pr = x * w;
+        f = f + pr;
+        d += (double)x * (double)w;
+      }
+      const float fe = f;
+      if (!SameFloat(fe, G[(size_t)s * gmx::GG_N + r])) ++bad;
+      e_tc = std::max(e_tc, fabs((double)G2[(size_t)s * gmx::GG_N + r] - d));
+      e_seq = std::max(e_seq, fabs((double)fe - d));
+      mag = std::max(mag, fabs(d));
+    }
+  *exact_mismatches = bad;
+  err[0] = e_tc; err[1] = e_seq; err[2] = mag;
+  return 0;
+}
 
 int gmx_selftest_math(gmx_ctx* c, uint32_t stride, uint64_t mismatches[3], uint32_t first_bad[3]) {
   if (!c || !mismatches || !first_bad || stride == 0) return GMX_E_ARG;

@@ -34,6 +34,12 @@ cudaError_t LaunchCompressProf(int cfg, const StreamParams& P, unsigned grid, cu
 cudaError_t LaunchDecompress(int cfg, const StreamParams& P, unsigned grid, cudaStream_t st);
 cudaError_t LaunchGenerate(int cfg, const StreamParams& P, unsigned grid, cudaStream_t st);
 cudaError_t LaunchStep(const StepParams& Q, cudaStream_t st);
+// lock-step batched generation (gate_gemm.cuh, GenStepKernel)
+cudaError_t LaunchGenStep(const GenStepParams& Q, unsigned grid, cudaStream_t st);
+cudaError_t LaunchGateExact(const float* W, const float* X, const uint32_t* sym, float* G, uint32_t n_slots, unsigned max_grid, cudaStream_t st);
+cudaError_t LaunchGateWeightPrep(const float* W, float* Wt, cudaStream_t st);
+cudaError_t LaunchGateTc(const float* Xt, const float* Wt, const float* Wfull, const uint32_t* sym, float* G, uint32_t n_slots, cudaStream_t st);
+unsigned GateWtFloats();
 unsigned StepStateBytes();
 cudaError_t OccupancyCompress(int cfg, int* blocks_per_sm);
 cudaError_t OccupancyDecompress(int cfg, int* blocks_per_sm);

@@ -42,6 +42,7 @@ enum : uint32_t {
   GMX_ERR_HISTORY_CAP = 5,
   GMX_ERR_BAD_HEADER = 6,
   GMX_ERR_SPARSE_FULL = 7,   // shared sparse table over its load limit (host retries with a roomier arena)
+  GMX_ERR_INTERNAL = 8,      // a hand-over between kernels of the lock-step generation happened off a byte boundary
 };
 
 // Shared-memory staging of the 33 selected weight sets: layer-0 sets (<= 113 weights) at stride 132 words,
@@ -155,7 +156,39 @@ struct StreamParams {
   uint32_t part, part_header, part_last;
   uint64_t part_total;         // compress: length the header announces; decompress: bytes this part produces
   const uint32_t* coder_in; uint32_t* coder_out;
+  // LOCK-STEP batched generation (gate_gemm.cuh; host.cu RunLockstepGenerate). While no stream of a batch has reached a BPTT pass,
+  // the 3 x 50 x 563 LSTM gate matrix is the loaded model's for ALL streams (lstm.cpp:57-79 changes it once per 100 learned
+  // bytes), so the gate products of one byte step of all streams are ONE dense contraction [streams x 307] . [307 x 150].
+  // lockstep != 0: MODE_GENERATE runs stream stream_base + blockIdx.x in arena blockIdx.x, consumes the prompt, stops in front
+  // of the first sampled byte's gate product (input vector in gate_x, byte in front in gate_sym) and parks its state in `park`;
+  // GenStepKernel then advances every stream by one sampled byte per launch, reading the gate pre-activations the batched
+  // kernel left in gate_g.
+  uint32_t lockstep, stream_base;
+  float* gate_x;               // GateXIndex(slot, k, plane): tf32-truncated value / exact residual planes, tiled for the MMA
+  uint32_t* gate_sym;          // [slots] byte in front of the boundary (the one-hot column of the gate matrices)
+  const float* gate_g;         // [slots][GG_N] gate pre-activations of this byte step
+  uint32_t* park;              // [slots][sizeof(StreamSmem) / 4]
 };
+
+// ---- layouts of the batched gate product (gate_gemm.cuh) --------------------------------------------------------------
+// M = 128 streams per tile, N = 160 (150 gate rows, padded), K = 320 (256 PPMd probabilities, 50 hidden, bias, padded) in chunks
+// of 32. Both operands are K-major and stored in global memory as the shared-memory image tcgen05.mma reads without swizzle:
+// 8-row x 16-byte core matrices (128 contiguous bytes), row groups adjacent (SBO = 128 B), the eight 4-float k-slices of a chunk
+// behind each other (LBO = rows / 8 * 128 B). One (tile, chunk, plane) block is therefore one contiguous TMA bulk copy.
+enum : int { GG_M = 128, GG_N = 160, GG_K = 320, GG_KC = 32, GG_NCHUNK = GG_K / GG_KC, GG_ROWS = 3 * L_CELLS, GG_KUSED = L_NIN };
+enum : int { GG_A_FLOATS = GG_M * GG_KC, GG_B_FLOATS = GG_N * GG_KC };
+GMX_HD size_t GateXIndex(uint32_t slot, int k, int plane) {
+  const uint32_t tile = slot / GG_M, r = slot % GG_M;
+  const int chunk = k / GG_KC, kk = k % GG_KC;
+  return (((size_t)tile * GG_NCHUNK + chunk) * 2 + plane) * GG_A_FLOATS + (size_t)(((kk >> 2) * (GG_M / 8) + (r >> 3)) * 32 + (r & 7) * 4 + (kk & 3));
+}
+GMX_HD size_t GateWIndex(int row, int k, int plane) {
+  const int chunk = k / GG_KC, kk = k % GG_KC;
+  return ((size_t)chunk * 2 + plane) * GG_B_FLOATS + (size_t)(((kk >> 2) * (GG_N / 8) + (row >> 3)) * 32 + (row & 7) * 4 + (kk & 3));
+}
+GMX_HD size_t GateXFloats(uint32_t slots) { return (size_t)((slots + GG_M - 1) / GG_M) * GG_NCHUNK * 2 * GG_A_FLOATS; }
+// tf32 keeps the top 19 bits of an fp32 word; the residual v - hi is exact in fp32
+GMX_HD float Tf32Hi(float v) { uint32_t u; memcpy(&u, &v, 4); u &= 0xffffe000u; float r; memcpy(&r, &u, 4); return r; }
 
 // ---- device constant tables --------------------------------------------------------------------
 #if defined(__CUDACC__)
@@ -1063,10 +1096,30 @@ GMX_DEV void LstmGateDots(StreamSmem& s, const float* W, uint32_t sym, int ltid)
 // output-layer step of Lstm::Perceive is fused (see below). Publishes n_ppm_used and n_pkt. ------------------------
 template <int NL, bool PROF, bool RING = false>
 GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, uint32_t b, uint32_t sym, int known_byte, int ltid, Lap<PROF>& lap,
-                         const WeightSmem& ws = WeightSmem{nullptr, nullptr}) {
+                         const WeightSmem& ws = WeightSmem{nullptr, nullptr}, int part = 0) {
   const ArenaLayout& L = *A.L;
   const uint32_t e = s.l_epoch;
   float* lin_e = A.at<float>(L.l_lin) + e * (L_NIN + 1);
+  // Lock-step generation splits the pass around the gate products: part 1 ends after the input vector (which also goes to the
+  // batched product's operand planes), part 2 starts from the pre-activations the batched kernel computed for this stream.
+  if (part == 1) {
+    PrefetchRange(A.at<float>(L.l_wout) + (size_t)e * L_HID * L_NOUT, L_HID * L_NOUT * 4, ltid, NL);
+    for (int i = ltid; i < L_NIN; i += NL) lin_e[i] = i < 256 ? s.ppm[i] : i < 306 ? s.l_hidden[i - 256] : 1.0f;
+    for (int i = ltid; i < L_CELLS; i += NL) A.at<float>(L.l_last)[e * L_CELLS + i] = s.l_state[i];
+    const uint32_t slot = blockIdx.x;
+    for (int k = ltid; k < GG_K; k += NL) {
+      const float v = k < 256 ? s.ppm[k] : k < 306 ? s.l_hidden[k - 256] : k == 306 ? 1.0f : 0.0f;
+      const float hi = Tf32Hi(v);
+      P.gate_x[GateXIndex(slot, k, 0)] = hi;
+      P.gate_x[GateXIndex(slot, k, 1)] = f_sub(v, hi);
+    }
+    if (ltid == 0) P.gate_sym[slot] = sym;
+    return;
+  }
+  if (part == 2) {
+    const float* g = P.gate_g + (size_t)blockIdx.x * GG_N;
+    for (int t = ltid; t < 3 * L_CELLS; t += NL) s.l_gate[t / L_CELLS][t % L_CELLS] = g[t];
+  } else {
   // The pass streams 184.8 KB of gate weights and then the 52 KB output layer of this epoch slot. Ask L2 for all of it
   // now: the role has few threads, so its own loads keep only a few KB in flight; the prefetches put the rest of the
   // HBM latency behind them (the lines are consumed within this pass, long before L2 could evict them).
@@ -1087,6 +1140,7 @@ GMX_DEV void LstmForward(StreamSmem& s, const Arena& A, const StreamParams& P, u
   if (ws.w) LstmGateDotsSmem<NL>(s, A.at<float>(L.l_w), ws.w, sym, ltid);
   else if (RING) LstmGateDotsRing<NL>(s, A.at<float>(L.l_w), sym, ltid);
   else LstmGateDots<NL>(s, A.at<float>(L.l_w), sym, ltid);
+  }
   GroupSync<NL>(BAR_LSTM);
   if (ltid == 0) Publish(&s.n_ppm_used, b + 1);   // the PPMd role may overwrite ppm now
   lap.mark(17);
@@ -2251,20 +2305,29 @@ GMX_DEV void BitLstmRoleCompress(StreamSmem& s, const Arena& A, const StreamPara
 // Predictor::Predict of one bit. known_byte >= 0 (serial compress): the byte being coded; path_bit = index of this bit in
 // it. The byte models then leave their eight path nodes in packet 0 at the byte boundary.
 template <int NT, bool PROF, bool LAT = false>
+// part (lock-step generation, always at a byte boundary): 1 = up to the LSTM input vector, 2 = from the gate pre-activations on.
 GMX_DEV void SerialPredict(StreamSmem& s, const Arena& A, const StreamParams& P, int tid, Lap<PROF>& lap, const WeightSmem& ws, int known_byte = -1,
-                           int path_bit = -1, int learn_bit = -1) {
-  if (tid == 0) Bookkeeping(s);
-  __syncthreads();
-  lap.mark(0);
-  if (s.bb) {
-    const uint32_t last = s.ctx[C_LAST_BYTE];
-    // PPMd on the last warp while the other warps do the byte contexts (with b = 0 no wait inside can block)
-    if (tid >= NT - 32) PpmdStep<PROF>(s, A, 0, last, known_byte, known_byte >= 0, tid - (NT - 32), lap);
-    else BitBoundaryA<NT - 32>(s, A, tid);
+                           int path_bit = -1, int learn_bit = -1, int part = 0) {
+  if (part != 2) {
+    if (tid == 0) Bookkeeping(s);
     __syncthreads();
-    lap.mark(2);
-    LstmForward<NT, PROF, true>(s, A, P, 0, last, known_byte, tid, lap, ws);
+    lap.mark(0);
+  }
+  if (part == 2 || s.bb) {
+    const uint32_t last = s.ctx[C_LAST_BYTE];
+    if (part != 2) {
+      // PPMd on the last warp while the other warps do the byte contexts (with b = 0 no wait inside can block)
+      if (tid >= NT - 32) PpmdStep<PROF>(s, A, 0, last, known_byte, known_byte >= 0, tid - (NT - 32), lap);
+      else BitBoundaryA<NT - 32>(s, A, tid);
+      __syncthreads();
+      lap.mark(2);
+    }
+    LstmForward<NT, PROF, true>(s, A, P, 0, last, known_byte, tid, lap, ws, part);
+    if (part == 1) return;
     BitBoundaryB<NT, LAT>(s, A, 0, tid, known_byte);
+  } else if (part == 1) {
+    if (tid == 0) SetError(s, GMX_ERR_INTERNAL);   // lock-step hand-over off a byte boundary
+    return;
   }
   PredictBit<NT, PROF, LAT>(s, A, P, 0, path_bit, tid, lap, learn_bit);
 }
@@ -2352,6 +2415,10 @@ GMX_DEV void SerialGenerate(StreamSmem& s, const Arena& A, const StreamParams& P
       if (s.bit_stop) return;
     }
   }
+  if (P.lockstep) {   // the sampling phase belongs to GenStepKernel + the batched gate product
+    SerialPredict<NT, PROF, LAT>(s, A, P, tid, lap, ws, -1, -1, -1, 1);
+    return;
+  }
   SerialPredict<NT, PROF, LAT>(s, A, P, tid, lap, ws);   // :198
 #pragma unroll 1
   for (uint32_t i = 0; i < J.n_bytes; ++i) {
@@ -2409,10 +2476,11 @@ __global__ void __launch_bounds__(32 * (WB + WL + 1), MINB) StreamKernel(StreamP
   if (WS && tid == 0) { MbarInit(ws.mbar, 1); s.wphase = 0; }
   StageTables<NT>(s, P, tid);
   Arena A{P.arenas + (uint64_t)blockIdx.x * P.arena_stride, &s.T.L, P.tmpl_arena, P.tmpl_layout};
-  for (;;) {
-    if (tid == 0) next_stream = atomicAdd(P.queue, 1u);
+  for (uint32_t round = 0;; ++round) {
+    const bool lockstep = MODE == MODE_GENERATE && P.lockstep;   // block b runs stream stream_base + b in arena b, once
+    if (!lockstep && tid == 0) next_stream = atomicAdd(P.queue, 1u);
     __syncthreads();
-    const uint32_t q = next_stream;
+    const uint32_t q = lockstep ? (round == 0 ? P.stream_base + blockIdx.x : P.n_streams) : next_stream;
     __syncthreads();
     if (q >= P.n_streams) break;
     const uint32_t sid = P.ids ? P.ids[q] : q;
@@ -2496,8 +2564,64 @@ __global__ void __launch_bounds__(32 * (WB + WL + 1), MINB) StreamKernel(StreamP
       if (PROF && P.prof) for (int i = 0; i < GMX_PROF_SLOTS; ++i) P.prof[(size_t)sid * GMX_PROF_SLOTS + i] = prof->acc[i];
     }
     __syncthreads();
-    ParkState<NT>(s, P, sid, tid);
+    ParkState<NT>(s, P, lockstep ? blockIdx.x : sid, tid);
     __syncthreads();
+  }
+}
+
+// ---- lock-step generation: one sampled byte of every stream per launch ----------------------------------------------------
+// Block b = stream stream_base + b in arena b, state parked in P.park between launches. A launch starts where the previous one
+// (or the prompt launch of StreamKernel<MODE_GENERATE> with P.lockstep) stopped: the byte models have run for byte
+// `byte_index`, the batched kernel has left this stream's 150 gate pre-activations in P.gate_g. It finishes the LSTM forward
+// pass and the byte boundary, samples the byte's eight bits exactly as SerialGenerate does (runner-utils.cpp:198-215) and -
+// unless this was the last byte - runs the byte models for the next byte up to the next gate product.
+struct GenStepParams {
+  StreamParams P;
+  uint32_t n_slots, byte_index, last;
+};
+template <int WB, int WL, int MINB>
+__global__ void __launch_bounds__(32 * (WB + WL + 1), MINB) GenStepKernel(GenStepParams Q) {
+  constexpr int NB = 32 * WB, NL = 32 * WL, NT = NB + NL + 32;
+  constexpr int kWords = (int)(sizeof(StreamSmem) / 4);
+  __shared__ StreamSmem s;
+  const StreamParams& P = Q.P;
+  const int tid = (int)threadIdx.x;
+  const uint32_t slot = blockIdx.x;
+  if (slot >= Q.n_slots) return;
+  const uint32_t sid = P.stream_base + slot;
+  uint32_t* sw = (uint32_t*)&s;
+  uint32_t* parked = P.park + (size_t)slot * kWords;
+  for (int i = tid; i < kWords; i += NT) sw[i] = parked[i];
+  __syncthreads();
+  Arena A{P.arenas + (uint64_t)slot * P.arena_stride, &s.T.L, P.tmpl_arena, P.tmpl_layout};
+  Lap<false> lap;
+  lap.start(nullptr, false);
+  const WeightSmem ws{nullptr, nullptr};
+  if (s.error == 0) {
+    SerialPredict<NT, false>(s, A, P, tid, lap, ws, -1, -1, -1, 2);
+    const float* ru = P.rand_u + (size_t)sid * P.rand_stride + (size_t)Q.byte_index * 8;
+    uint8_t* out = P.out + (size_t)sid * P.gen_bytes;
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+      if (tid == 0) {
+        const float r = ru[j];
+        const float prob = Logistic(f_div(Logit(s.prob), P.temperature));
+        s.new_bit = r < prob ? 1 : 0;
+        if (j == 7) out[Q.byte_index] = (uint8_t)((s.recent_bits * 2 + s.new_bit) & 0xff);
+        s.bit_stop = VolatileLoad(&s.error) != 0;
+      }
+      __syncthreads();
+      if (s.bit_stop) break;
+      if (j < 7) SerialPredict<NT, false>(s, A, P, tid, lap, ws);
+      else if (!Q.last) SerialPredict<NT, false>(s, A, P, tid, lap, ws, -1, -1, -1, 1);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < kWords; i += NT) parked[i] = sw[i];
+  if (tid == 0) {
+    P.status[sid] = s.error;
+    P.out_len[sid] = s.error ? 0 : P.gen_bytes;
+    if (Q.last) WriteUsage(s, A, P, sid);
   }
 }
 

@@ -47,7 +47,7 @@ enum {
 /* Per-stream status codes written to status[] (0 = ok). */
 enum {
   GMX_S_OK = 0, GMX_S_PPMD_ARENA = 1, GMX_S_MIXER_POOL = 2, GMX_S_OUTPUT_CAP = 3,
-  GMX_S_MATCH_RANGE = 4, GMX_S_HISTORY_CAP = 5, GMX_S_BAD_HEADER = 6, GMX_S_SPARSE_FULL = 7
+  GMX_S_MATCH_RANGE = 4, GMX_S_HISTORY_CAP = 5, GMX_S_BAD_HEADER = 6, GMX_S_SPARSE_FULL = 7, GMX_S_INTERNAL = 8
 };
 
 const char* gmx_version(void);
@@ -133,6 +133,20 @@ int gmx_generate_batch(gmx_ctx* ctx, const gmx_model* model, const uint8_t* prom
 int gmx_generate_batch_device(gmx_ctx* ctx, const gmx_model* model, const uint8_t* d_prompts, const uint64_t* d_prompt_off, uint32_t n,
                               uint32_t out_bytes, float temperature, const float* d_rand_u, uint64_t rand_stride, uint8_t* d_out,
                               uint64_t* d_out_len, uint32_t* d_status, uint64_t max_prompt_len);
+/* How gmx_generate_batch[_device] runs the sampling phase.
+ *   GMX_GEN_PER_STREAM      (default) one persistent CTA per prompt does everything (RunGeneration as written, per stream).
+ *   GMX_GEN_LOCKSTEP_EXACT  all streams advance one sampled byte per launch; the LSTM gate products of a byte step
+ *                           (LstmLayer::ForwardPass lstm-layer.cpp:198-204) are ONE batched kernel over all streams with the
+ *                           reference's arithmetic - the same bytes as GMX_GEN_PER_STREAM and as `gmix -g`.
+ *   GMX_GEN_LOCKSTEP_TENSOR the batched product runs on the tensor cores (tcgen05.mma kind::tf32, 3xTF32 split, TMEM
+ *                           accumulators, TMA bulk operand loads): fp32-accurate but not the reference's summation order, so
+ *                           sampled bytes can differ from `gmix -g` (opt-in; divergence reported by bench.py / the tests).
+ * The lock-step modes need the gate matrix to be shared by all streams, i.e. no stream may reach an LSTM BPTT pass while it
+ * learns its prompt: (bytes the model learned since its last pass) + longest prompt - 1 < 100 (lstm.cpp:57-79). Otherwise
+ * the call runs GMX_GEN_PER_STREAM; gmx_last_generation_mode tells which mode the last call used. */
+enum { GMX_GEN_PER_STREAM = 0, GMX_GEN_LOCKSTEP_EXACT = 1, GMX_GEN_LOCKSTEP_TENSOR = 2 };
+int gmx_set_generation_mode(gmx_ctx* ctx, int mode);
+int gmx_last_generation_mode(const gmx_ctx* ctx);
 /* The draws one `gmix -g` process makes for sampling: srand(0xDEADBEEF) (predictor.cpp:18), 84450 draws consumed by
  * the LSTM initialisation (lstm-layer.cpp:176-195), then n x rand()/RAND_MAX. Uses and reseeds the host libc rand(). */
 void gmx_reference_rand_u(float* out, uint64_t n);
@@ -221,6 +235,11 @@ int gmx_get_usage(gmx_ctx* ctx, uint32_t* out, uint32_t max_streams);
  * patterns 0, stride, 2*stride, ... < 2^32 (logf: positive normals only). mismatches[3] and
  * first_bad[3] are indexed expf, logf, tanhf. */
 int gmx_selftest_math(gmx_ctx* ctx, uint32_t stride, uint64_t mismatches[3], uint32_t first_bad[3]);
+/* Self test of the batched gate product kernels on seeded random operands (n_slots streams): exact_mismatches = entries of
+ * the exact kernel that differ bitwise from a host loop in the reference's order; err[0] = largest |tensor-core result - fp64
+ * sum|, err[1] = largest |sequential fp32 - fp64 sum| (the reference arithmetic's own rounding, for scale), err[2] = largest
+ * |result|. */
+int gmx_selftest_gate(gmx_ctx* ctx, uint32_t n_slots, uint32_t seed, uint64_t* exact_mismatches, double err[3]);
 
 #ifdef __cplusplus
 }

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "../../gmix_b200/csrc/checkpoint.h"
+#include "../../gmix_b200/csrc/gate_gemm.cuh"
 #include "../../gmix_b200/host/coder.h"
 
 // role split of the emulated CTA (warps of bit role / LSTM role; + one PPMd warp)
@@ -191,6 +192,27 @@ int main(int argc, char** argv) {
     std::vector<uint8_t> out(size + 8);
     in_off[0] = 0; in_off[1] = prompt.size(); out_off[0] = 0; out_off[1] = out.size();
     P.in = prompt.data(); P.out = out.data(); P.gen_bytes = size; P.temperature = temperature; P.rand_u = ru.data(); P.rand_stride = 0;
+    if (getenv("EMU_LOCKSTEP")) {
+      // what host.cu RunLockstepGenerate does: the prompt launch stops in front of the first gate product, then one exact batched
+      // gate product + one GenStepKernel launch per sampled byte (one stream = one slot here)
+      std::vector<uint32_t> park(sizeof(gmx::StreamSmem) / 4 + 4, 0), gsym(64, 0);
+      std::vector<float> gx(gmx::GateXFloats(1), 0.0f), gg(gmx::GG_N * 2, 0.0f);
+      P.lockstep = 1; P.stream_base = 0;
+      P.gate_x = gx.data(); P.gate_sym = gsym.data(); P.gate_g = gg.data(); P.park = park.data();
+      if (Execute(R, gmx::MODE_GENERATE, &im, prompt.size() + size, P, true, getenv("EMU_OVERLAY") ? prompt.size() : 0)) return 1;
+      memcpy(park.data(), R.final_state.data(), sizeof(gmx::StreamSmem));
+      const float* W = (const float*)(P.tmpl_arena + (P.tmpl_layout ? P.tmpl_layout->l_w : R.L.l_w));
+      gmx::GenStepParams Q;
+      Q.P = P; Q.n_slots = 1;
+      for (uint32_t i = 0; i < size; ++i) {
+        cuda_emu::RunBlock(gmx::GX_THREADS, 0, 1, [&] { gmx::GateDotsExactKernel(W, gx.data(), gsym.data(), gg.data(), 1); });
+        Q.byte_index = i; Q.last = i + 1 == size;
+        cuda_emu::RunBlock(EMU_NT, 0, 1, [&] { gmx::GenStepKernel<EMU_WB, EMU_WL, EMU_MINB>(Q); });
+        if (R.status) { fprintf(stderr, "stream status %u at byte %u\n", R.status, i); return 1; }
+      }
+      WriteAll(argv[4], out.data(), size);
+      return 0;
+    }
     if (Execute(R, gmx::MODE_GENERATE, &im, prompt.size() + size, P, false, getenv("EMU_OVERLAY") ? prompt.size() : 0)) return 1;
     WriteAll(argv[4], out.data(), size);
     return 0;

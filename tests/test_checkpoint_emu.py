@@ -105,7 +105,9 @@ def test_generation_samples_the_reference_bytes(work, size, temp):
     # and in overlay mode (what the batched generation call runs): the model's tables stay read-only and shared, the
     # stream keeps its changes in an overlay map / local pool / private copies of the small state
     # (both PPMd backings of an overlay arena: the model's window copied whole, and the segmented one big models get)
-    for extra in ({}, {"EMU_SEGMENTED": "1"}):
+    # ... and as LOCK-STEP generation (host.cu RunLockstepGenerate): the prompt launch stops in front of the first sampled byte's
+    # gate product, then one exact batched gate product (gate_gemm.cuh GateDotsExactKernel) + one GenStepKernel launch per byte
+    for extra in ({}, {"EMU_SEGMENTED": "1"}, {"EMU_LOCKSTEP": "1"}, {"EMU_LOCKSTEP": "1", "EMU_SEGMENTED": "1"}):
         env = dict(os.environ, EMU_OVERLAY="1", **extra)
         subprocess.run([exe, "generate", str(d / "ref_a"), str(d / "prompt.txt"), str(d / f"ov_gen_{size}.out"), str(size), temp], check=True,
                        stderr=subprocess.DEVNULL, env=env)

@@ -55,6 +55,63 @@ def test_batched_generation_samples_the_reference_bytes(gpu_ctx, model, size, te
     assert gpu_ctx.generate_batch(model, prompts[:2], size, temp) == out[:2]
 
 
+@pytest.mark.parametrize("size,temp", [(48, 1.0), (40, 0.5)])
+def test_lockstep_generation_with_the_exact_batched_gate_product_samples_the_reference_bytes(gpu_ctx, model, size, temp):
+    """GMX_GEN_LOCKSTEP_EXACT: prompt launch, then one batched gate product (reference arithmetic, all streams at once) + one
+    GenStepKernel launch per sampled byte - the same bytes as `gmix -g` and as the per-stream kernel."""
+    want = open(os.path.join(GOLD, f"ckpt600_gen_{size}_{temp}.out"), "rb").read()
+    prompts = [PROMPT] * 5 + [PROMPT[:9] + b"\n"] + [PROMPT] * 140     # 146 streams: two 128-stream tiles, 19 exact-kernel groups
+    per_stream = gpu_ctx.generate_batch(model, prompts, size, temp)
+    gpu_ctx.set_generation_mode(gpu_ctx.GEN_LOCKSTEP_EXACT)
+    try:
+        out = gpu_ctx.generate_batch(model, prompts, size, temp)
+        assert gpu_ctx.last_generation_mode == gpu_ctx.GEN_LOCKSTEP_EXACT
+    finally:
+        gpu_ctx.set_generation_mode(gpu_ctx.GEN_PER_STREAM)
+    assert out == per_stream
+    assert all(o == want for o in out[:5]) and out[5] != want and out[-1] == want
+
+
+def test_batched_gate_product_kernels(gpu_ctx):
+    """gate_gemm.cuh on seeded random operands: the exact kernel is bit-identical to a host loop in the reference's order; the
+    tcgen05 kernel (3xTF32, fp32 accumulation in TMEM) is within the stated tolerance of the fp64 sum - 8x the rounding error the
+    reference's own sequential fp32 arithmetic shows on the same operands, and 1e-5 of the largest value."""
+    for n_slots, seed in ((300, 3), (128, 4), (1, 5)):
+        bad, e_tc, e_seq, mag = gpu_ctx.selftest_gate(n_slots, seed)
+        assert bad == 0
+        assert e_tc <= max(8 * e_seq, 1e-5 * mag), (n_slots, e_tc, e_seq, mag)
+
+
+def test_tensor_core_generation_follows_the_exact_samples(gpu_ctx, model):
+    """GMX_GEN_LOCKSTEP_TENSOR is opt-in and not bit-exact (summation order): its samples must be valid, reproducible, and stay
+    with the exact samples except where a draw falls within rounding distance of a probability."""
+    prompts = [PROMPT] * 3 + [PROMPT[:9] + b"\n", PROMPT[:20]]
+    exact = gpu_ctx.generate_batch(model, prompts, 48, 1.0)
+    gpu_ctx.set_generation_mode(gpu_ctx.GEN_LOCKSTEP_TENSOR)
+    try:
+        out = gpu_ctx.generate_batch(model, prompts, 48, 1.0)
+        assert gpu_ctx.last_generation_mode == gpu_ctx.GEN_LOCKSTEP_TENSOR
+        again = gpu_ctx.generate_batch(model, prompts, 48, 1.0)
+    finally:
+        gpu_ctx.set_generation_mode(gpu_ctx.GEN_PER_STREAM)
+    assert [len(o) for o in out] == [48] * len(prompts) and out == again
+    assert out[0] == out[1] == out[2]
+    assert sum(o == e for o, e in zip(out, exact)) >= 3, (out, exact)
+
+
+def test_lockstep_modes_fall_back_to_per_stream_when_a_prompt_reaches_a_bptt_pass(gpu_ctx, model):
+    """The gate matrix is only shared while no stream runs BPTT: a 120-byte prompt crosses the 100-byte horizon."""
+    long_prompt = (PROMPT * 8)[:120]
+    per_stream = gpu_ctx.generate_batch(model, [long_prompt], 16, 1.0)
+    gpu_ctx.set_generation_mode(gpu_ctx.GEN_LOCKSTEP_EXACT)
+    try:
+        out = gpu_ctx.generate_batch(model, [long_prompt], 16, 1.0)
+        assert gpu_ctx.last_generation_mode == gpu_ctx.GEN_PER_STREAM
+    finally:
+        gpu_ctx.set_generation_mode(gpu_ctx.GEN_PER_STREAM)
+    assert out == per_stream
+
+
 def test_written_checkpoint_matches_the_reference_files(gpu_ctx, ckpt):
     sh, lo = gpu_ctx.train_checkpoint(A)
     assert lo == ckpt[1]
