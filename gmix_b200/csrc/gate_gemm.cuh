@@ -8,7 +8,7 @@
 //                         dense weights (184.8 KB) are loaded into shared memory ONCE per CTA instead of once per stream and byte.
 //   GateGemmTcKernel      opt-in: the same contraction on the 5th-generation tensor cores. tcgen05.mma kind::tf32 with M = 128
 //                         streams, N = 160, K = 8 per instruction, accumulators in TMEM; both operands arrive as TMA bulk copies
-//                         (cp.async.bulk + mbarrier) of pre-tiled K-major core-matrix images, two stages deep. fp32 accuracy is
+//                         (cp.async.bulk + mbarrier) of pre-tiled K-major core-matrix images, three stages deep. fp32 accuracy is
 //                         recovered with the 3xTF32 split (x = hi + lo, w = hi + lo; hi.hi + hi.lo + lo.hi accumulate in fp32):
 //                         relative error ~2^-21 per product, but NOT the reference's summation order - sampled bytes can differ
 //                         from `gmix -g`, which is why it is opt-in and its divergence is measured (bench.py, tests).
@@ -94,7 +94,7 @@ __global__ void GateWeightPrepKernel(const float* W, float* Wt) {
 
 #if defined(__CUDACC__)
 // ---- tensor cores --------------------------------------------------------------------------------------------------------
-enum : int { GT_STAGES = 2, GT_STAGE_BYTES = 2 * GG_A_FLOATS * 4 + 2 * GG_B_FLOATS * 4, GT_SMEM_BYTES = GT_STAGES * GT_STAGE_BYTES, GT_TMEM_COLS = 256 };
+enum : int { GT_STAGES = 3, GT_STAGE_BYTES = 2 * GG_A_FLOATS * 4 + 2 * GG_B_FLOATS * 4, GT_SMEM_BYTES = GT_STAGES * GT_STAGE_BYTES, GT_TMEM_COLS = 256 };
 
 // shared-memory matrix descriptor, K-major, no swizzle (layout type 0), descriptor version 1 (sm_100):
 // bits 0-13 start address >> 4, 16-29 leading byte offset >> 4 (between the two 16-byte k-slices of one MMA),
@@ -143,13 +143,14 @@ __global__ void __launch_bounds__(128) GateGemmTcKernel(const float* Xt, const f
       BulkG2S(dst, xa + (size_t)chunk * 2 * GG_A_FLOATS, 2 * GG_A_FLOATS * 4, &full[st]);
       BulkG2S(dst + 2 * GG_A_FLOATS * 4, Wt + (size_t)chunk * 2 * GG_B_FLOATS, 2 * GG_B_FLOATS * 4, &full[st]);
     };
-    if (lane == 0) load(0);
+    if (lane == 0) for (int c = 0; c < GT_STAGES - 1; ++c) load(c);
 #pragma unroll 1
     for (int c = 0; c < GG_NCHUNK; ++c) {
       const int st = c % GT_STAGES;
-      if (c + 1 < GG_NCHUNK) {
-        if (c + 1 >= GT_STAGES) MbarWait(&freed[(c + 1) % GT_STAGES], (uint32_t)(((c + 1) / GT_STAGES - 1) & 1));   // its previous MMAs are done
-        if (lane == 0) load(c + 1);
+      const int nx = c + GT_STAGES - 1;   // the chunk that goes into the stage chunk c - 1 used
+      if (nx < GG_NCHUNK) {
+        if (nx >= GT_STAGES) MbarWait(&freed[nx % GT_STAGES], (uint32_t)((nx / GT_STAGES - 1) & 1));   // that stage's previous MMAs are done
+        if (lane == 0) load(nx);
       }
       MbarWait(&full[st], (uint32_t)((c / GT_STAGES) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

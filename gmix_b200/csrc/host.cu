@@ -40,6 +40,7 @@ struct gmx_ctx {
   uint64_t cfg_max_len = 0;
   uint32_t cfg_max_resident = 0;
   const gmx_model* cfg_model = nullptr;   // arenas currently use this model's layout (streams start from its checkpoint)
+  uint32_t cfg_factor = 1;                // arenas per resident CTA slot (ConfigureForModel)
   uint64_t cfg_ov_learn = 0, cfg_ov_new = 0;   // != 0: ... in overlay mode, sized for this many learned / new bytes per stream
   std::vector<uint8_t> ck_short, ck_long; // last checkpoint written through this ctx (gmx_train_checkpoint, gmx_pred_write_checkpoint)
   uint32_t n_arenas = 0;
@@ -62,9 +63,9 @@ struct gmx_ctx {
   // lock-step batched generation (gate_gemm.cuh): parked stream states, operand planes / byte in front / pre-activations of the
   // batched gate product, the model's tiled weight planes
   DevBuf b_park, b_gx, b_gsym, b_gg, b_wt;
-  enum { kGroups = 4 };
-  cudaStream_t gen_stream[kGroups] = {nullptr, nullptr, nullptr, nullptr};   // one per group of lock-step streams
-  cudaEvent_t gen_done[kGroups] = {nullptr, nullptr, nullptr, nullptr}, gen_fork = nullptr;
+  enum { kGroups = 16 };
+  cudaStream_t gen_stream[kGroups] = {};   // one per group of lock-step streams
+  cudaEvent_t gen_done[kGroups] = {}, gen_fork = nullptr;
   int gen_mode = 0;        // GMX_GEN_* requested by gmx_set_generation_mode
   int last_gen_mode = 0;   // what the last generation call actually ran
   bool profile = false;
@@ -166,6 +167,7 @@ void FreeArenas(gmx_ctx* c) {
   c->cfg_max_len = 0;
   c->cfg_model = nullptr;
   c->cfg_ov_learn = c->cfg_ov_new = 0;
+  c->cfg_factor = 1;
 }
 
 bool Retryable(uint32_t st) {
@@ -222,10 +224,13 @@ int RetryInRoomyArenas(gmx_ctx* c, int mode, gmx::StreamParams P, uint32_t n, ui
 
 // Arenas sized by a loaded model's layout (every stream is a clone of the model's parked stream), or - ov_new != 0 - overlay
 // arenas on top of the model's arena (MakeOverlayLayout: the model's tables are shared, a stream keeps its changes only).
-int ConfigureForModel(gmx_ctx* c, const gmx_model* m, uint64_t ov_learn = 0, uint64_t ov_new = 0) {
-  if (c->cfg_model == m && c->n_arenas && ((ov_new == 0 && c->cfg_ov_new == 0) || (ov_new != 0 && c->cfg_ov_learn >= ov_learn && c->cfg_ov_new >= ov_new))) return 0;
+// factor: arenas per resident CTA slot (lock-step generation keeps more streams in flight than CTAs fit the SMs).
+int ConfigureForModel(gmx_ctx* c, const gmx_model* m, uint64_t ov_learn = 0, uint64_t ov_new = 0, uint32_t factor = 1) {
+  if (c->cfg_model == m && c->n_arenas && c->cfg_factor == factor &&
+      ((ov_new == 0 && c->cfg_ov_new == 0) || (ov_new != 0 && c->cfg_ov_learn >= ov_learn && c->cfg_ov_new >= ov_new))) return 0;
   const uint32_t max_resident = c->cfg_max_resident;
   FreeArenas(c);
+  c->cfg_factor = factor;
   c->layout = ov_new ? gmx::MakeOverlayLayout(m->layout, m->pre, ov_learn, ov_new) : m->layout;
   c->cfg_ov_learn = ov_learn; c->cfg_ov_new = ov_new;
   int rc = EnsureDecay(c, m->pre.steps / 8 + m->max_new_bytes + 2);
@@ -236,6 +241,7 @@ int ConfigureForModel(gmx_ctx* c, const gmx_model* m, uint64_t ov_learn = 0, uin
   if (per_sm < 1) per_sm = 1;
   uint64_t want = (uint64_t)per_sm * c->sm_count;
   if (max_resident && max_resident < want) want = max_resident;
+  want *= factor;
   size_t free_b = 0, total_b = 0;
   GMX_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
   const uint64_t usable = free_b > (2ull << 30) ? free_b - (2ull << 30) : 0;
@@ -618,6 +624,7 @@ namespace {
 // streams: one launch consumes the prompts (with learning, per stream), then every sampled byte is one batched gate product
 // (exact SIMT or tcgen05) + one GenStepKernel launch over all streams of the wave.
 constexpr int kGenGroups = gmx_ctx::kGroups;
+constexpr uint32_t kGenOversubscribe = 2;
 int RunLockstepGenerate(gmx_ctx* c, const gmx_model* model, const uint8_t* d_prompts, const uint64_t* d_prompt_off, uint32_t n, uint32_t out_bytes,
                         float temperature, const float* d_rand_u, uint64_t rand_stride, uint8_t* d_out, uint64_t* d_out_len, uint32_t* d_status,
                         uint64_t max_prompt_len, bool tensor) {
@@ -627,13 +634,17 @@ int RunLockstepGenerate(gmx_ctx* c, const gmx_model* model, const uint8_t* d_pro
   if (max_len > model->max_new_bytes) return Fail(c, GMX_E_ARG, "stream of %llu bytes exceeds the max_new_bytes (%llu) the model was loaded with",
                                                   (unsigned long long)max_len, (unsigned long long)model->max_new_bytes);
   if (c->kcfg != gmx::kThroughputConfig) { c->kcfg = gmx::kThroughputConfig; FreeArenas(c); }   // GenStepKernel is that configuration's CTA
-  int rc = ConfigureForModel(c, model, max_prompt_len ? max_prompt_len : max_len, max_len);
+  // Streams in flight = kGenOversubscribe x the CTAs that fit the SMs, in GROUPS of two streams per SM that advance independently,
+  // each in its own CUDA stream: a byte step is a barrier over the streams of ONE group only, and while a group waits for its
+  // slowest stream, runs its (small) gate product or sits between two launches, the step kernels of the other groups keep every
+  // CTA slot of the SMs busy.
+  uint32_t oversub = kGenOversubscribe, group_streams = 2u * (uint32_t)c->sm_count;   // measured: profiles/r02_lockstep_generation.md
+  if (const char* e = getenv("GMX_GEN_OVERSUB")) oversub = (uint32_t)std::max(1, atoi(e));        // development: A/B of the two knobs
+  if (const char* e = getenv("GMX_GEN_GROUP")) group_streams = (uint32_t)std::max(1, atoi(e));
+  int rc = ConfigureForModel(c, model, max_prompt_len ? max_prompt_len : max_len, max_len, oversub);
   if (rc) return rc;
   const uint32_t cap = c->n_arenas;
-  // The arenas are split into up to kGenGroups GROUPS that advance independently, each in its own CUDA stream: a byte step is a
-  // barrier over the streams of ONE group only, and while one group waits for its slowest stream or runs its (small) gate product
-  // the other groups' step kernels keep the SMs busy.
-  const uint32_t ng = cap >= 4 * gmx::GG_M ? (uint32_t)kGenGroups : 1u;
+  const uint32_t ng = std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)kGenGroups, (cap + group_streams - 1) / group_streams));
   const uint32_t gs = (cap + ng - 1) / ng;                                   // arena slots per group
   const size_t state_bytes = sizeof(gmx::StreamSmem);
   const size_t gx_floats = gmx::GateXFloats(gs), gsym_words = (size_t)gs + 128, gg_floats = ((size_t)gs + gmx::GG_M) * gmx::GG_N;

@@ -2589,9 +2589,10 @@ __global__ void __launch_bounds__(32 * (WB + WL + 1), MINB) GenStepKernel(GenSte
   const uint32_t slot = blockIdx.x;
   if (slot >= Q.n_slots) return;
   const uint32_t sid = P.stream_base + slot;
-  uint32_t* sw = (uint32_t*)&s;
-  uint32_t* parked = P.park + (size_t)slot * kWords;
-  for (int i = tid; i < kWords; i += NT) sw[i] = parked[i];
+  static_assert(sizeof(StreamSmem) % 16 == 0, "the parked state moves as 16-byte words");
+  uint4* sw = (uint4*)&s;
+  uint4* parked = (uint4*)(P.park + (size_t)slot * kWords);
+  for (int i = tid; i < kWords / 4; i += NT) sw[i] = parked[i];
   __syncthreads();
   Arena A{P.arenas + (uint64_t)slot * P.arena_stride, &s.T.L, P.tmpl_arena, P.tmpl_layout};
   Lap<false> lap;
@@ -2617,7 +2618,7 @@ __global__ void __launch_bounds__(32 * (WB + WL + 1), MINB) GenStepKernel(GenSte
     }
   }
   __syncthreads();
-  for (int i = tid; i < kWords; i += NT) parked[i] = sw[i];
+  for (int i = tid; i < kWords / 4; i += NT) parked[i] = sw[i];
   if (tid == 0) {
     P.status[sid] = s.error;
     P.out_len[sid] = s.error ? 0 : P.gen_bytes;
