@@ -4,6 +4,7 @@
 //   gmixb200 -c [ckpt] input output   compress, one stream; bytes identical to `gmix -c` (strict build)
 //   gmixb200 -d [ckpt] input output   decompress a stream written by either program
 //   gmixb200 -g ckpt prompt output size temperature    generate, bytes identical to `gmix -g` (runner-utils.cpp:158-221)
+//   gmixb200 -G ckpt prompts output size temperature [stream|exact|tensor]   one prompt per line, batched (lock-step) generation
 //   gmixb200 -t [ckpt] train test     RunTraining (runner-utils.cpp:223-322): Predict/Perceive/Learn over `train`, after every
 //                                     2 % the test file is scored on a copy of the predictor (analysis/training.tsv), the
 //                                     coded training stream goes to data/tmp, data/trained_checkpoint.{short,long} at the end
@@ -46,6 +47,7 @@ int Help() {
          "Compress:    gmixb200 -c [checkpoint_path] input output\n"
          "Decompress:  gmixb200 -d [checkpoint_path] input output\n"
          "Generate:    gmixb200 -g checkpoint_path prompt output output_size temperature\n"
+         "Batched:     gmixb200 -G checkpoint_path prompts(one per line) output output_size temperature [stream|exact|tensor]\n"
          "Train:       gmixb200 -t [checkpoint_path] training_file test_file\n"
          "Chunked:     gmixb200 -C chunk_bytes input output   /   gmixb200 -D input output\n"
          "Via facade:  gmixb200 -p input output\n"
@@ -157,6 +159,44 @@ int Generate(int argc, char* argv[]) {
   if (rc != 0) return -1;
   if (!WriteFile(argv[4], out.data(), (size_t)size)) { printf("Can not open: %s\n", argv[4]); return Help(); }
   printf("generation: 100%%\n%1.2f s.\n", ((double)clock() - start) / CLOCKS_PER_SEC);
+  return 0;
+}
+
+// RunGeneration for MANY prompts at once (BASELINE configs[3]): one prompt per line of the prompt file (the line break is part
+// of the prompt, as it is when `gmix -g` reads a one-line file), every prompt sampled with the reference's draw sequence - the
+// output file is what n separate `gmix -g` processes write, concatenated. mode: "stream" (one CTA per prompt does everything),
+// "exact" (lock-step, batched gate product with the reference's arithmetic: same bytes) or "tensor" (lock-step, the gate product
+// on the tensor cores: opt-in, not bit-exact). gmix_b200.h: GMX_GEN_*.
+int GenerateBatch(int argc, char* argv[]) {
+  if (argc != 7 && argc != 8) { printf("Wrong number of arguments.\n"); return Help(); }
+  std::vector<uint8_t> file;
+  if (!ReadFile(argv[3], &file) || file.empty()) { printf("Can not open: %s\n", argv[3]); return Help(); }
+  const int size = std::stoi(argv[5]);
+  const float temperature = std::stof(argv[6]);
+  const std::string mode = argc == 8 ? argv[7] : "exact";
+  if (size <= 0 || (mode != "stream" && mode != "exact" && mode != "tensor")) return Help();
+  std::vector<uint64_t> off(1, 0);
+  uint64_t longest = 0;
+  for (size_t i = 0; i < file.size(); ++i)
+    if (file[i] == '\n' || i + 1 == file.size()) { longest = std::max<uint64_t>(longest, i + 1 - off.back()); off.push_back(i + 1); }
+  const uint32_t n = (uint32_t)off.size() - 1;
+  const clock_t start = clock();
+  gmixb::Gpu gpu(0);
+  gmx_model* m = LoadModel(gpu.ctx(), argv[2], longest + (uint64_t)size);
+  if (!m) return -1;
+  std::vector<float> rand_u((size_t)size * 8 + 1);
+  gmx_reference_rand_u(rand_u.data(), (uint64_t)size * 8);
+  std::vector<uint8_t> out((size_t)n * size + 1);
+  std::vector<uint32_t> status(n, 0);
+  gmx_set_generation_mode(gpu.ctx(), mode == "stream" ? GMX_GEN_PER_STREAM : mode == "exact" ? GMX_GEN_LOCKSTEP_EXACT : GMX_GEN_LOCKSTEP_TENSOR);
+  const int rc = gmx_generate_batch(gpu.ctx(), m, file.data(), off.data(), n, (uint32_t)size, temperature, rand_u.data(), 0, out.data(), status.data());
+  if (rc != 0) printf("%s\n", gmx_last_error(gpu.ctx()));
+  const int ran = gmx_last_generation_mode(gpu.ctx());
+  gmx_model_free(m);
+  if (rc != 0) return -1;
+  if (!WriteFile(argv[4], out.data(), (size_t)n * size)) { printf("Can not open: %s\n", argv[4]); return Help(); }
+  printf("generation: %u prompts x %d bytes, mode %s\n%1.2f s.\n", n, size, ran == GMX_GEN_PER_STREAM ? "stream" : ran == GMX_GEN_LOCKSTEP_EXACT ? "exact" : "tensor",
+         ((double)clock() - start) / CLOCKS_PER_SEC);
   return 0;
 }
 
@@ -364,6 +404,7 @@ int main(int argc, char* argv[]) {
   try {
     if (mode == 'T') { if (argc != 4) return Help(); return SelfTest(argv[2], argv[3]); }
     if (mode == 'g') return Generate(argc, argv);
+    if (mode == 'G') return GenerateBatch(argc, argv);
     if (mode == 't') return Train(argc, argv);
   } catch (const std::exception& e) {
     printf("%s\n", e.what());

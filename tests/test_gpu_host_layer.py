@@ -106,6 +106,19 @@ def test_runner_checkpoint_generate_and_train_cli(tmp_path):
     assert (d / "b.back").read_bytes() == text[600:]
     subprocess.run([RUNNER, "-g", ck, os.path.join(GOLD, "ckpt600_prompt.txt"), str(d / "gen.out"), "48", "1.0"], check=True)
     assert (d / "gen.out").read_bytes() == open(os.path.join(GOLD, "ckpt600_gen_48_1.0.out"), "rb").read()
+    # batched generation from the C++ host: one prompt per line, every sample is what its own `gmix -g` process writes;
+    # "exact" = lock-step with the batched gate product in the reference's arithmetic, "stream" = one CTA per prompt
+    prompt = open(os.path.join(GOLD, "ckpt600_prompt.txt"), "rb").read()
+    want = open(os.path.join(GOLD, "ckpt600_gen_48_1.0.out"), "rb").read()
+    if prompt.endswith(b"\n") and prompt.count(b"\n") == 1:
+        (d / "prompts.txt").write_bytes(prompt * 3)
+        for mode in ("exact", "stream", "tensor"):
+            r = subprocess.run([RUNNER, "-G", ck, str(d / "prompts.txt"), str(d / f"gen3_{mode}.out"), "48", "1.0", mode], check=True, capture_output=True, text=True)
+            assert f"mode {mode}" in r.stdout, r.stdout
+            got = (d / f"gen3_{mode}.out").read_bytes()
+            assert len(got) == 3 * 48 and got[:48] == got[48:96] == got[96:]
+            if mode != "tensor":
+                assert got == want * 3, mode
     subprocess.run([RUNNER, "-t", str(d / "a.in"), str(d / "b.in")], check=True, cwd=str(d))
     assert (d / "data" / "trained_checkpoint.long").read_bytes() == long_ref
     diff = ckpt_layout.differing_sections((d / "data" / "trained_checkpoint.short").read_bytes(), short_ref)
