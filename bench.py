@@ -411,7 +411,9 @@ def run_ours(args):
     resident, arena_mib = ctx.resident_streams, ctx.arena_bytes >> 20
     kc = ctx.kernel_configs()[ctx.kernel_config]
     kcfg_desc = (f"config {ctx.kernel_config}: {32 * (kc[0] + kc[1] + 1)} threads per stream CTA, {kc[2]} CTAs/SM, " +
-                 ("all threads walk the phases together" if kc[3] else f"pipelined roles: {kc[0]} bit warps + {kc[1]} LSTM warps + 1 PPMd warp"))
+                 ("hybrid order: all threads run the LSTM phases, the PPMd warp prepares the next byte under this byte's bit path"
+                  if kc[3] and kc[1] == 0 else "all threads walk the phases together" if kc[3]
+                  else f"pipelined roles: {kc[0]} bit warps + {kc[1]} LSTM warps + 1 PPMd warp"))
     kernel_name = f"gmx::StreamKernel<{kc[0]}, {kc[1]}, MODE_COMPRESS, {kc[2]}, false, {'true' if kc[3] else 'false'}>"
 
     # ---- parity of the TIMED batch against the unmodified reference + CPU baseline (one wave of full chunks) --------

@@ -72,7 +72,7 @@ struct gmx_ctx {
   uint32_t prof_streams = 0;
   uint32_t usage_streams = 0;
   uint32_t last_grid = 0;
-  int kcfg = 0;            // kernel configuration (kernels.h) the arenas are currently sized for
+  int kcfg = gmx::kThroughputConfig;   // kernel configuration (kernels.h) the arenas are currently sized for
   int kcfg_user = -1;      // -1: chosen per call from the batch shape (AutoConfig), else pinned by gmx_set_kernel_config
   uint64_t launches = 0;
   double last_ms = 0;

@@ -11,6 +11,7 @@
 
 namespace gmx {
 // SERIAL = 1: compress walks the phases with all threads (no role pipeline); decompress and generation always do.
+// SERIAL = 1 with WL = 0 (configuration 10): the hybrid order - PPMd warp one byte ahead under the bit path, LSTM phases with all threads.
 // WS = 1: the dense LSTM gate weights (184.8 KB) stay resident in shared memory (needs the whole SM: MINB = 1).
 //            id  WB WL MINB SERIAL WS
 #define GMX_KERNEL_CONFIGS(X)   \
@@ -23,9 +24,10 @@ namespace gmx {
   X(6, 3, 0, 8, 0, 0)           \
   X(7, 7, 0, 4, 0, 0)           \
   X(8, 4, 8, 1, 0, 1)           \
-  X(9, 4, 4, 1, 0, 1)
-constexpr int kNumKernelConfigs = 10;
-constexpr int kThroughputConfig = 0, kLatencyConfig = 9;   // what the host picks for a full wave of streams / for at most one stream per SM
+  X(9, 4, 4, 1, 0, 1)           \
+  X(10, 3, 0, 8, 1, 0)
+constexpr int kNumKernelConfigs = 11;
+constexpr int kThroughputConfig = 10, kLatencyConfig = 9;   // what the host picks for a full wave of streams / for at most one stream per SM
 constexpr int kStepWB = 2, kStepWL = 1;   // role split of the single-stream stepping kernel
 struct KernelConfigInfo { int wb, wl, minb, threads, serial, ws; };
 KernelConfigInfo KernelConfig(int cfg);

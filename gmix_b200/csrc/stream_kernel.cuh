@@ -60,6 +60,7 @@ enum : int { WSTRIDE0 = 132, WSTRIDE1 = 36, WTOTAL = 24 * WSTRIDE0 + 9 * WSTRIDE
 #define GMX_PKT_RING 32
 #endif
 enum : int { PKT_RING = GMX_PKT_RING };
+
 // Cycle-counter slots of the PROF kernel variant. Bit role: 0 bookkeeping, 1 wait for the byte packet, 2 byte-boundary
 // contexts, 3 lookups, 4 gate selection, 5 weight-set swap, 6 layer-0 dot products, 7 layer-0 chain, 8 layer 1, 9 final
 // neuron, 10 rest of predict (barrier), 11 learn scalars + tables + coder, 12 weight update, 13 trace, 14 stream init.
@@ -2298,14 +2299,82 @@ GMX_DEV void BitLstmRoleCompress(StreamSmem& s, const Arena& A, const StreamPara
   }
 }
 
+// Hybrid order (SERIAL with WL = 0): the PPMd warp is ahead by ONE byte and is not lost to the LSTM. Per byte: all NT threads
+// run the LSTM forward pass; then the PPMd warp prepares the NEXT byte (UpdateByte with this byte, PrepareByte, normalisation,
+// path nodes - the phase that is one warp wide by nature) while the other NT - 32 threads run this byte's eight bit steps (whose
+// phases have at most 47 work items or are serial chains); then all NT threads run Lstm::Perceive. Against the phase-serial
+// order this hides PPMd behind the bit path; against the two-role variant the LSTM phases, whose time is inversely proportional
+// to their threads, keep the full CTA. Hand-overs: two CTA barriers per byte (forward: the distribution and the freed weight-set
+// staging area; Perceive: the byte is done), packets of consecutive bytes alternate ring slots.
+template <int NT, bool PROF, bool LAT = false>
+GMX_DEV void HybridCompress(StreamSmem& s, const Arena& A, const StreamParams& P, const StreamJob& J, uint32_t sid, ProfSmem* prof, int tid,
+                            const WeightSmem& ws) {
+  constexpr int NB = NT - 32;
+  const bool bitw = tid < NB;
+  const int lane = tid - NB;
+  Lap<PROF> lap, plap;
+  lap.start(prof, tid == 0);        // bit + LSTM slots
+  plap.start(prof, tid == NB);      // PPMd slots (24..26); the PPMd warp's share of the LSTM phases is not counted twice
+  Lap<PROF> nolap;
+  nolap.start(prof, false);
+  if (ws.w) LoadGateWeights<NT>(s, A, ws, tid);
+  const bool tracing = sid == 0 && (P.bit_trace || P.pred_trace);
+  if (!bitw && J.n_bytes) PpmdStep<PROF>(s, A, 0, s.byte0, (int)J.in[0], true, lane, plap);
+#pragma unroll 1
+  for (uint32_t pos = 0; pos < J.n_bytes; ++pos) {
+    const uint32_t c = J.in[pos];
+    if (bitw) {
+      if (tid == 0) Bookkeeping(s);
+      GroupSync<NB>(BAR_BIT);
+      lap.mark(0);
+      BitBoundaryA<NB>(s, A, tid);   // (the first bit of a byte: s.bb is set)
+      lap.mark(2);
+    }
+    __syncthreads();   // the distribution of this byte is published; every staged weight set is back in the pool (s.w = the forward pass's ring)
+    if (bitw) lap.mark(1);
+    LstmForward<NT, PROF, true>(s, A, P, pos, pos ? J.in[pos - 1] : s.byte0, (int)c, tid, bitw ? lap : nolap, ws);
+    // (Measured and not kept, profiles/r02_hybrid_compress.md: the next byte's gate products on the PPMd warp - one warp needs
+    // longer for them than the bit path lasts, 3.64 instead of 4.58 MB/s; the fused output-layer step on the PPMd warp - no change.)
+    if (!bitw) {
+      if (pos + 1 < J.n_bytes && !__shfl_sync(0xffffffffu, VolatileLoad(&s.error), 0))
+        PpmdStep<PROF>(s, A, pos + 1, c, (int)J.in[pos + 1], true, lane, plap);
+    } else {
+      BitBoundaryB<NB, LAT>(s, A, pos, tid, (int)c);
+      lap.mark(2);
+#pragma unroll 1
+      for (int j = 7; j >= 0; --j) {
+        const int bit = (c >> j) & 1;
+        if (j != 7) {
+          if (tid == 0) Bookkeeping(s);
+          GroupSync<NB>(BAR_BIT);
+          lap.mark(0);
+        }
+        PredictBit<NB, PROF, LAT>(s, A, P, pos, 7 - j, tid, lap, bit);
+        if (tracing) {
+          if (tid == 0) Trace(s, P, (uint64_t)pos * 8 + (7 - j));
+          GroupSync<NB>(BAR_BIT);
+          lap.mark(13);
+        }
+        LearnBit<NB, PROF, LAT>(s, A, P, tid, lap, bit, J.out, true);
+        if (s.bit_stop) break;
+      }
+    }
+    __syncthreads();
+    if (VolatileLoad(&s.error) != 0) return;   // uniform: nothing between the barrier and Perceive's first barrier sets it
+    if (bitw) lap.mark(1);
+    LstmPerceive<NT, PROF>(s, A, P, c, tid, bitw ? lap : nolap, ws);
+    if (tid == 0) Publish(&s.n_done, pos + 1);
+  }
+}
+
 // ==== LOCKSTEP (decompress, generation, the Predictor facade): a byte is only known when its last bit is decided, so
 // nothing can run ahead; the whole CTA (NT threads) walks the phases one after the other, every phase with all the
 // threads it can use, through the same step functions as the roles above. ===================================
 
 // Predictor::Predict of one bit. known_byte >= 0 (serial compress): the byte being coded; path_bit = index of this bit in
 // it. The byte models then leave their eight path nodes in packet 0 at the byte boundary.
-template <int NT, bool PROF, bool LAT = false>
 // part (lock-step generation, always at a byte boundary): 1 = up to the LSTM input vector, 2 = from the gate pre-activations on.
+template <int NT, bool PROF, bool LAT = false>
 GMX_DEV void SerialPredict(StreamSmem& s, const Arena& A, const StreamParams& P, int tid, Lap<PROF>& lap, const WeightSmem& ws, int known_byte = -1,
                            int path_bit = -1, int learn_bit = -1, int part = 0) {
   if (part != 2) {
@@ -2529,7 +2598,9 @@ __global__ void __launch_bounds__(32 * (WB + WL + 1), MINB) StreamKernel(StreamP
     __syncthreads();
     const bool failed_early = s.error != 0;
     if (!failed_early) {
-      if (MODE == MODE_COMPRESS && SERIAL) {
+      if (MODE == MODE_COMPRESS && SERIAL && WL == 0) {
+        HybridCompress<NT, PROF, MINB == 1>(s, A, P, job, sid, prof, tid, ws);
+      } else if (MODE == MODE_COMPRESS && SERIAL) {
         SerialCompress<NT, PROF, MINB == 1>(s, A, P, job, sid, prof, tid, ws);
       } else if (MODE == MODE_COMPRESS && WL == 0) {
         if (tid < NB) BitLstmRoleCompress<NB, PROF, MINB == 1>(s, A, P, job, sid, prof, tid, ws);

@@ -99,6 +99,26 @@ def test_serial_compress_configuration(tmp_path):
         assert open(out, "rb").read() == open(os.path.join(GOLD, name + ".gmix"), "rb").read(), name
 
 
+def test_hybrid_compress_configuration(tmp_path):
+    """Configuration 10 of the library: the PPMd warp prepares the next byte under the bit path of this one, the LSTM phases run
+    with all threads (HybridCompress) - same bytes in every legal interleaving of the two sides (thread order between barriers,
+    cp.async at its latest legal moment), and through the parts / resume protocols that start mid-stream."""
+    exe = str(tmp_path / "emu_main")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-w", "-DEMU_WB=3", "-DEMU_WL=0", "-DEMU_SERIAL=1", "-DGMX_EMU_DEFER_CP", "-o", exe,
+                    os.path.join(HERE, "emu", "emu_main.cpp")], check=True)
+    for order in ("", "reverse", "shuffle5"):
+        env = dict(os.environ)
+        if order:
+            env["EMU_ORDER"] = order
+        for name in ("text1k", "random1200", "short124", "one_byte", "empty") if not order else ("text1k", "repetitive"):
+            out = str(tmp_path / (name + ".out"))
+            subprocess.run([exe, "compress", os.path.join(GOLD, name + ".in"), out], check=True, stderr=subprocess.DEVNULL, env=env)
+            assert open(out, "rb").read() == open(os.path.join(GOLD, name + ".gmix"), "rb").read(), (name, order)
+    out = str(tmp_path / "p.out")
+    subprocess.run([exe, "parts", os.path.join(GOLD, "text1k.in"), out, "517"], check=True, stderr=subprocess.DEVNULL)
+    assert open(out, "rb").read() == open(os.path.join(GOLD, "text1k.gmix"), "rb").read()
+
+
 def test_latency_configuration(tmp_path):
     """Configuration 9 of the library: one CTA per SM, roles 4 / 4 / 1, the dense gate weights resident in (emulated) shared
     memory and refreshed by bulk copies after every Adam step, straight-line mixer network (LAT), whole-byte prefetch."""
