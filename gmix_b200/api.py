@@ -98,6 +98,7 @@ def load_library():
     lib.gmx_pred_read_checkpoint.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
     lib.gmx_selftest_math.argtypes = [C.c_void_p, C.c_uint32, u64p, u32p]
     lib.gmx_set_generation_mode.argtypes = [C.c_void_p, C.c_int]
+    lib.gmx_compress_analysis.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, u64p, C.c_uint32, C.c_void_p, C.c_uint32, u32p]
     lib.gmx_last_generation_mode.argtypes = [C.c_void_p]
     lib.gmx_selftest_gate.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, u64p, C.POINTER(C.c_double)]
     _LIB = lib
@@ -447,6 +448,25 @@ class Context:
         if n < 0:
             self._check(n, "gmx_get_usage")
         return buf[:n]
+
+    ANALYSIS_ROW = np.dtype([("bits_seen", np.uint64), ("neg_entropy", np.float64, (33,)), ("ppmd_used", np.uint64), ("history", np.uint64)])
+
+    def compress_analysis(self, data, sample_frequency=None):
+        """One stream compressed with the reference's analysis output (Predictor::EnableAnalysis / RunAnalysis): returns
+        (compressed bytes, rows) with one ANALYSIS_ROW per sample_frequency bits (default: 8 * len / 1000 as `gmix -c` uses)."""
+        data = bytes(data)
+        freq = int(sample_frequency if sample_frequency is not None else 8 * len(data) // 1000)
+        if freq <= 0:
+            raise GmixError("sample_frequency must be positive (the reference enables analysis from 125 input bytes on)")
+        cap = compress_bound(len(data))
+        out = np.zeros(cap + 1, dtype=np.uint8)
+        src = np.frombuffer(data, dtype=np.uint8) if data else np.zeros(1, dtype=np.uint8)
+        max_rows = (8 * len(data)) // freq + 1
+        rows = np.zeros(max_rows, dtype=self.ANALYSIS_ROW)
+        n_out, n_rows = C.c_uint64(0), C.c_uint32(0)
+        self._check(self.lib.gmx_compress_analysis(self.h, src.ctypes.data, len(data), out.ctypes.data, cap, C.byref(n_out), freq, rows.ctypes.data,
+                                                   max_rows, C.byref(n_rows)), "gmx_compress_analysis")
+        return out[:n_out.value].tobytes(), rows[:n_rows.value]
 
     GEN_PER_STREAM, GEN_LOCKSTEP_EXACT, GEN_LOCKSTEP_TENSOR = 0, 1, 2
 

@@ -62,7 +62,7 @@ struct gmx_ctx {
   DevBuf b_in, b_out, b_in_off, b_out_off, b_out_len, b_status, b_trace, b_ptrace, b_prof, b_ids, b_usage, b_rand, b_final, b_coder;
   // lock-step batched generation (gate_gemm.cuh): parked stream states, operand planes / byte in front / pre-activations of the
   // batched gate product, the model's tiled weight planes
-  DevBuf b_park, b_gx, b_gsym, b_gg, b_wt;
+  DevBuf b_park, b_gx, b_gsym, b_gg, b_wt, b_an;
   enum { kGroups = 16 };
   cudaStream_t gen_stream[kGroups] = {};   // one per group of lock-step streams
   cudaEvent_t gen_done[kGroups] = {}, gen_fork = nullptr;
@@ -102,6 +102,8 @@ struct RunOpts {
   // one stream coded in parts (gmx_compress_part / gmx_decompress_part)
   uint32_t part = 0, part_header = 0, part_last = 0; uint64_t part_total = 0;
   const uint32_t* d_coder_in = nullptr; uint32_t* d_coder_out = nullptr;
+  // analysis output of a single stream (gmx_compress_analysis)
+  double* d_an_entropy = nullptr; gmx::AnalysisRow* d_an_rows = nullptr; uint32_t an_freq = 0, an_max_rows = 0;
 };
 
 // One stream stepped bit by bit (the Predictor facade). Owns a worst-case-sized arena.
@@ -291,6 +293,7 @@ int RunDevice(gmx_ctx* c, int mode, const uint8_t* d_in, const uint64_t* d_in_of
   P.analysis = o.analysis; P.final_state = o.d_final_state;
   P.gen_bytes = o.gen_bytes; P.temperature = o.temperature; P.rand_u = o.d_rand_u; P.rand_stride = o.rand_stride;
   P.part = o.part; P.part_header = o.part_header; P.part_last = o.part_last; P.part_total = o.part_total; P.coder_in = o.d_coder_in; P.coder_out = o.d_coder_out;
+  P.an_entropy = o.d_an_entropy; P.an_rows = o.d_an_rows; P.an_freq = o.an_freq; P.an_max_rows = o.an_max_rows;
   if (o.model) { P.tmpl_arena = o.model->d_arena; P.tmpl_state = o.model->d_state; P.tmpl_layout = c->layout.ov ? o.model->d_layout : nullptr; }
   const uint32_t grid = n < c->n_arenas ? n : c->n_arenas;
   {
@@ -456,7 +459,7 @@ void gmx_destroy(gmx_ctx* c) {
   cudaSetDevice(c->device);
   FreeArenas(c);
   for (DevBuf* b : {&c->b_in, &c->b_out, &c->b_in_off, &c->b_out_off, &c->b_out_len, &c->b_status, &c->b_trace, &c->b_ptrace, &c->b_prof, &c->b_ids, &c->b_usage, &c->b_rand, &c->b_final, &c->b_coder,
-                     &c->b_park, &c->b_gx, &c->b_gsym, &c->b_gg, &c->b_wt})
+                     &c->b_park, &c->b_gx, &c->b_gsym, &c->b_gg, &c->b_wt, &c->b_an})
     if (b->p) cudaFree(b->p);
   if (c->d_layout) cudaFree(c->d_layout);
   if (c->d_roomy_layout) cudaFree(c->d_roomy_layout);
@@ -932,6 +935,36 @@ int gmx_checksum_device(gmx_ctx* c, const uint8_t* d_data, const uint64_t* d_off
   ChecksumKernel<<<(n + 63) / 64, 64, 0, c->stream>>>(d_data, d_off, d_len, n, d_sum);
   GMX_CUDA(c, cudaGetLastError());
   c->launches += 1;
+  return 0;
+}
+
+int gmx_compress_analysis(gmx_ctx* c, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_len, uint32_t sample_frequency,
+                          gmx_analysis_row* rows, uint32_t max_rows, uint32_t* n_rows) {
+  static_assert(sizeof(gmx_analysis_row) == sizeof(gmx::AnalysisRow) && GMX_ANALYSIS_COLUMNS == gmx::AN_COLS, "gmix_b200.h mirrors stream_kernel.cuh");
+  if (!c || !in || !out || !out_len || !rows || !n_rows || sample_frequency == 0) return GMX_E_ARG;
+  GMX_CUDA(c, cudaSetDevice(c->device));
+  *n_rows = 0;
+  const uint64_t want = n ? (8 * n - 1) / sample_frequency : 0;   // samples at bits_seen = f, 2f, ... <= 8n - 1
+  const uint32_t nr = (uint32_t)std::min<uint64_t>(want, max_rows);
+  int rc = Reserve(c, c->b_an, gmx::AN_COLS * 8 + (size_t)(nr + 1) * sizeof(gmx::AnalysisRow));
+  if (rc) return rc;
+  double init[gmx::AN_COLS];
+  for (double& e : init) e = -1;   // predictor.cpp:37-38
+  GMX_CUDA(c, cudaMemcpyAsync(c->b_an.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+  GMX_CUDA(c, cudaMemsetAsync((char*)c->b_an.p + sizeof(init), 0, (size_t)(nr + 1) * sizeof(gmx::AnalysisRow), c->stream));
+  RunOpts o;
+  o.analysis = 1;
+  o.d_an_entropy = (double*)c->b_an.p; o.d_an_rows = (gmx::AnalysisRow*)((char*)c->b_an.p + sizeof(init));
+  o.an_freq = sample_frequency; o.an_max_rows = nr;
+  const uint64_t in_off[2] = {0, n}, out_off[2] = {0, cap};
+  uint32_t status = 0;
+  const int keep = c->kcfg_user;
+  c->kcfg_user = 0;   // the analysis step lives in the phase-serial order (SerialCompress)
+  rc = RunHost(c, gmx::MODE_COMPRESS, in, in_off, 1, out, out_off, out_len, &status, nullptr, nullptr, o);
+  c->kcfg_user = keep;
+  if (rc) return rc;
+  GMX_CUDA(c, cudaMemcpy(rows, o.d_an_rows, (size_t)nr * sizeof(gmx::AnalysisRow), cudaMemcpyDeviceToHost));
+  *n_rows = nr;
   return 0;
 }
 

@@ -124,6 +124,11 @@ struct ArenaLayout {
 enum : uint32_t { OV_SID_IND = 1, OV_SID_MATCH = OV_SID_IND + NIND, OV_SID_IH = OV_SID_MATCH + NMATCH, OV_SID_MIX = OV_SID_IH + NIH };
 static_assert(OV_SID_MIX + NMIX <= 128, "overlay table ids must fit the 7 bits above the 25-bit index of a sparse key");
 
+// One sample of analysis/entropy.tsv + analysis/memory.tsv (predictor.cpp:476-503): the columns are mod_ppmd(20), LSTM, the 15
+// skip-context Indirect models' two predictions each, the final mixer (the models constructed with enable_analysis = true,
+// predictor.cpp:28-29,124,353); the memory figures that change over a stream are PPMd's GetUsedMemory and the match history.
+enum : int { AN_COLS = 33 };
+struct AnalysisRow { uint64_t bits_seen; double neg_entropy[AN_COLS]; uint64_t ppmd_used, history; };
 struct StreamParams {
   const uint8_t* in; const uint64_t* in_off;     // n_streams + 1 offsets
   uint8_t* out; const uint64_t* out_off;         // n_streams + 1 offsets (capacity slices)
@@ -157,6 +162,11 @@ struct StreamParams {
   uint32_t part, part_header, part_last;
   uint64_t part_total;         // compress: length the header announces; decompress: bytes this part produces
   const uint32_t* coder_in; uint32_t* coder_out;
+  // Analysis output (Predictor::EnableAnalysis / RunAnalysis predictor.cpp:422-504) of a single compress stream run in the
+  // phase-serial order: cross-entropy accumulators of the 33 models the reference enables analysis for (an_entropy, start
+  // value -1) and one AnalysisRow per an_freq bits. null = off (only the reference's side effect on the inactive predictions,
+  // StreamSmem::analysis, is mirrored).
+  double* an_entropy; struct AnalysisRow* an_rows; uint32_t an_freq, an_max_rows;
   // LOCK-STEP batched generation (gate_gemm.cuh; host.cu RunLockstepGenerate). While no stream of a batch has reached a BPTT pass,
   // the 3 x 50 x 563 LSTM gate matrix is the loaded model's for ALL streams (lstm.cpp:57-79 changes it once per 100 learned
   // bytes), so the gate products of one byte step of all streams are ONE dense contraction [streams x 307] . [307 x 150].
@@ -2409,6 +2419,35 @@ GMX_DEV void SerialLearn(StreamSmem& s, const Arena& A, const StreamParams& P, i
   if (cur >= 256) LstmPerceive<NT, PROF>(s, A, P, (uint32_t)(cur - 256), tid, lap, ws);   // LstmModel::Learn lstm-model.cpp:50-59
 }
 
+// Predictor::RunAnalysis(bit) (predictor.cpp:471-504) with UpdateEntropy (:437-469), between Predict and Learn of a bit: the
+// blackboard holds this bit's predictions (inactive ones zeroed: analysis is on), s.steps == bits_seen. One thread per column.
+// log2 is the one operation here that is not bit-pinned to the host libm (CUDA's is within 1 ulp); the reference rounds its
+// result to float before it enters the double accumulator, which absorbs that.
+static GMX_DEV GMX_NOINLINE void AnalysisStep(StreamSmem& s, const Arena& A, const StreamParams& P, int bit, int tid) {
+  if (tid < AN_COLS) {
+    const float v = tid < 2 ? s.preds[tid] : tid < AN_COLS - 1 ? s.preds[P_IND0 + 2 * 17 + (tid - 2)] : s.final_out;
+    float prob = Logistic(v);
+    const float eps = (float)0.01, hi = f_sub(1.0f, eps);
+    if (prob < eps) prob = eps; else if (prob > hi) prob = hi;
+    const float e = (float)log2((double)(bit ? prob : f_sub(1.0f, prob)));
+    const double alpha = 0.00001;
+    const double acc = d_add(d_mul(d_sub(1.0, alpha), P.an_entropy[tid]), d_mul(alpha, (double)e));
+    P.an_entropy[tid] = acc;
+    const uint64_t bits_seen = s.steps;
+    if (bits_seen > 0 && bits_seen % P.an_freq == 0 && bits_seen / P.an_freq <= P.an_max_rows) {
+      AnalysisRow& row = P.an_rows[bits_seen / P.an_freq - 1];
+      row.neg_entropy[tid] = -acc;
+      if (tid == 0) {
+        const PpmdState* ps = A.at<PpmdState>(A.L->p_state);
+        uint64_t used = (uint64_t)PPMD_HEAP_END - (ps->hi_unit - ps->lo_unit) - (ps->units_start - ps->text_ptr);   // GetUsedMemory mod_ppmd.cpp:142-149
+        for (uint32_t i = 0; i < PPMD_N_INDEXES; ++i) used -= (uint64_t)ps->indx2units[i] * ps->bl_stamp[i] * 12u;
+        row.bits_seen = bits_seen; row.ppmd_used = used; row.history = s.hist_len;
+      }
+    }
+  }
+  __syncthreads();
+}
+
 // runner_utils::Compress (runner-utils.cpp:43-67) without the role pipeline: all phases with all threads. With a full
 // wave of resident streams per SM the other streams already hide this stream's latencies, and every phase having all
 // threads beats the pipeline's fixed split of them (kernels.h: configurations).
@@ -2425,6 +2464,7 @@ GMX_DEV void SerialCompress(StreamSmem& s, const Arena& A, const StreamParams& P
 #pragma unroll 1
     for (int j = 7; j >= 0; --j) {
       SerialPredict<NT, PROF, LAT>(s, A, P, tid, lap, ws, (int)c, 7 - j, (c >> j) & 1);
+      if (P.an_rows) AnalysisStep(s, A, P, (c >> j) & 1, tid);
       if (tracing) {
         if (tid == 0) Trace(s, P, (uint64_t)pos * 8 + (7 - j));
         __syncthreads();

@@ -111,6 +111,45 @@ bool RunBatch(gmx_ctx* ctx, bool compress, const std::vector<uint8_t>& in, const
   return true;
 }
 
+// runner_utils::Compress with the analysis output the reference writes whenever 8 * n / 1000 > 0 (runner-utils.cpp:47,
+// Predictor::EnableAnalysis / RunAnalysis predictor.cpp:422-504): analysis/entropy.tsv and analysis/memory.tsv in the working
+// directory, one row per sample_frequency bits. The changing figures come from the GPU (gmx_compress_analysis); the other
+// memory.tsv columns are constants of the model graph: LstmModel::GetMemoryUsage (lstm-model.cpp:86-99) = 7 017 924, an Indirect
+// model with a 2^16-context table (indirect.cpp:72-79) = 12 + 2048 + 2 * (2^16 * 256 + 1), the final mixer after its first Learn
+// (mixer.cpp:197-206) = 29 + (33 * 4 + 12) + 8.
+bool CompressWithAnalysis(gmx_ctx* ctx, const std::vector<uint8_t>& in, Batch* b) {
+  const uint32_t freq = (uint32_t)(8 * in.size() / 1000);
+  const uint64_t cap = gmx_compress_bound(in.size());
+  b->out.assign(cap + 1, 0);
+  b->out_off = {0, cap};
+  b->out_len.assign(1, 0);
+  std::vector<gmx_analysis_row> rows(4096);
+  uint32_t nr = 0;
+  if (gmx_compress_analysis(ctx, in.data(), in.size(), b->out.data(), cap, &b->out_len[0], freq, rows.data(), (uint32_t)rows.size(), &nr) != 0) {
+    printf("%s\n", gmx_last_error(ctx));
+    return false;
+  }
+  static const char* kSkip[15] = {"1_2", "1_2_3", "0_2", "0_2_3", "1_2_3_4", "0_3", "0_4", "0_5", "0_2_3_4", "0_3_4", "0_6", "0_7", "0_1_3_4", "0_4_5", "0_1_2_4"};
+  std::filesystem::create_directory("analysis");
+  std::ofstream entropy("analysis/entropy.tsv", std::ios::out), memory("analysis/memory.tsv", std::ios::out);
+  std::string header = "bits seen\tmod_ppmd(20)\tLSTM";
+  for (const char* k : kSkip) header += std::string("\tIndirect(skip_") + k + ")-indirect\tIndirect(skip_" + k + ")-run_map";
+  header += "\tMixer(final layer)";
+  entropy << header << std::endl;
+  memory << header << "\tmatch history" << std::endl;
+  for (uint32_t r = 0; r < nr; ++r) {
+    entropy << rows[r].bits_seen;
+    memory << rows[r].bits_seen;
+    for (int i = 0; i < GMX_ANALYSIS_COLUMNS; ++i) entropy << std::fixed << std::setprecision(5) << "\t" << rows[r].neg_entropy[i];
+    memory << "\t" << 16 + rows[r].ppmd_used << "\t" << 7017924ull;
+    for (int i = 0; i < 30; ++i) memory << "\t" << 12 + 256 * 4 * 2 + 2 * ((1ull << 16) * 256 + 1);
+    memory << "\t" << 29 + (33 * 4 + 12) + 8 << "\t" << rows[r].history;
+    entropy << std::endl;
+    memory << std::endl;
+  }
+  return true;
+}
+
 bool CompressViaPredictor(const std::vector<uint8_t>& in, std::vector<uint8_t>* out) {
   gmixb::Gpu gpu(0);
   gmixb::Predictor p(gpu, in.size() + 1);
@@ -472,7 +511,11 @@ int main(int argc, char* argv[]) {
       } else {
       gmx_model* model = nullptr;
       if (with_ckpt && !(model = LoadModel(gpu.ctx(), checkpoint_path, mode == 'c' ? in.size() : HeaderLength(in)))) return -1;
-      const bool ok = RunBatch(gpu.ctx(), mode == 'c' || mode == 'C', *src, in_off, &b, model);
+      // `gmix -c` from scratch writes analysis/*.tsv whenever the input has at least 125 bytes; GMIXB200_ANALYSIS=0 skips it
+      // (the analysis step runs in the phase-serial kernel configuration, a single stream is ~1.7x faster without)
+      const char* an_env = getenv("GMIXB200_ANALYSIS");
+      const bool analysis = mode == 'c' && !model && 8 * in.size() / 1000 > 0 && !(an_env && an_env[0] == '0');
+      const bool ok = analysis ? CompressWithAnalysis(gpu.ctx(), in, &b) : RunBatch(gpu.ctx(), mode == 'c' || mode == 'C', *src, in_off, &b, model);
       if (model) gmx_model_free(model);
       if (!ok) return -1;
       }

@@ -133,6 +133,18 @@ int gmx_generate_batch(gmx_ctx* ctx, const gmx_model* model, const uint8_t* prom
 int gmx_generate_batch_device(gmx_ctx* ctx, const gmx_model* model, const uint8_t* d_prompts, const uint64_t* d_prompt_off, uint32_t n,
                               uint32_t out_bytes, float temperature, const float* d_rand_u, uint64_t rand_stride, uint8_t* d_out,
                               uint64_t* d_out_len, uint32_t* d_status, uint64_t max_prompt_len);
+/* Predictor::EnableAnalysis(sample_frequency) + RunAnalysis (predictor.cpp:422-504) for ONE compressed stream: the stream is
+ * compressed as gmx_compress_batch does (analysis on: inactive predictions read as 0.5, predictor.cpp:362-365) and every
+ * sample_frequency bits one row is recorded - what the reference appends to analysis/entropy.tsv and analysis/memory.tsv.
+ * Columns: mod_ppmd(20), LSTM, the 15 skip-context Indirect models' "-indirect" and "-run_map" predictions, Mixer(final layer)
+ * (the models the reference constructs with enable_analysis = true). neg_entropy = the value the reference prints
+ * (-entropy, exponential average with alpha 1e-5 from a start value of -1); ppmd_used = ppmd_Model::GetUsedMemory(); history =
+ * LongTermMemory::history.size(). The other memory.tsv columns are constants of the model graph (gmixb200 -c writes both files). */
+enum { GMX_ANALYSIS_COLUMNS = 33 };
+typedef struct gmx_analysis_row { uint64_t bits_seen; double neg_entropy[GMX_ANALYSIS_COLUMNS]; uint64_t ppmd_used, history; } gmx_analysis_row;
+int gmx_compress_analysis(gmx_ctx* ctx, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_len,
+                          uint32_t sample_frequency, gmx_analysis_row* rows, uint32_t max_rows, uint32_t* n_rows);
+
 /* How gmx_generate_batch[_device] runs the sampling phase.
  *   GMX_GEN_PER_STREAM      (default) one persistent CTA per prompt does everything (RunGeneration as written, per stream).
  *   GMX_GEN_LOCKSTEP_EXACT  all streams advance one sampled byte per launch; the LSTM gate products of a byte step

@@ -171,3 +171,37 @@ def test_training_mode_reproduces_the_reference_metrics(tmp_path):
     assert (tmp_path / "data" / "tmp").read_bytes() == open(os.path.join(GOLD, "train_text1k_short124.tmp"), "rb").read()
     blob = (tmp_path / "data" / "trained_checkpoint.long").read_bytes()
     assert len(blob) == want["long_bytes"] and hashlib.md5(blob).hexdigest() == want["long_md5"]
+
+
+def test_runner_writes_the_reference_analysis_files(tmp_path):
+    """`gmixb200 -c` from scratch writes analysis/entropy.tsv and analysis/memory.tsv as `gmix -c` does (Predictor::EnableAnalysis /
+    RunAnalysis, predictor.cpp:422-504), checked against the unmodified reference run on the same input: memory.tsv byte for byte
+    (PPMd's used memory and the match history change per row), entropy.tsv field by field - identical text, except that a field
+    may differ by one unit of its last printed digit (1e-5): log2 is CUDA's (<= 1 ulp) where the reference calls glibc's."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "gmix")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref not built")
+    src = os.path.join(GOLD, "text1k.in")
+    ours, theirs = tmp_path / "ours", tmp_path / "ref"
+    ours.mkdir(), theirs.mkdir()
+    subprocess.run([RUNNER, "-c", src, "out.gmix"], check=True, cwd=str(ours), stdout=subprocess.DEVNULL)
+    subprocess.run([ref, "-c", src, "out.gmix"], check=True, cwd=str(theirs), stdout=subprocess.DEVNULL)
+    assert (ours / "out.gmix").read_bytes() == (theirs / "out.gmix").read_bytes()
+    assert (ours / "analysis" / "memory.tsv").read_bytes() == (theirs / "analysis" / "memory.tsv").read_bytes()
+    a = (ours / "analysis" / "entropy.tsv").read_text().split("\n")
+    b = (theirs / "analysis" / "entropy.tsv").read_text().split("\n")
+    assert a[0] == b[0] and len(a) == len(b) and len(a) > 1000
+    off = 0
+    for la, lb in zip(a[1:], b[1:]):
+        fa, fb = la.split("\t"), lb.split("\t")
+        assert len(fa) == len(fb) and fa[0] == fb[0]
+        for x, y in zip(fa[1:], fb[1:]):
+            if x != y:
+                off += 1
+                assert abs(float(x) - float(y)) < 1.5e-5, (fa[0], x, y)
+    assert off <= 5, off
+    # GMIXB200_ANALYSIS=0: same stream, no files
+    quiet = tmp_path / "quiet"
+    quiet.mkdir()
+    subprocess.run([RUNNER, "-c", src, "out.gmix"], check=True, cwd=str(quiet), stdout=subprocess.DEVNULL, env=dict(os.environ, GMIXB200_ANALYSIS="0"))
+    assert (quiet / "out.gmix").read_bytes() == (theirs / "out.gmix").read_bytes() and not (quiet / "analysis").exists()
