@@ -42,20 +42,37 @@ def test_config2_synthetic_chunks_oracle_sample_and_roundtrip(gpu_ctx, oracle):
     assert gpu_ctx.retried_streams == retried_before      # text fits the normal arenas
 
 
-def test_config2_full_size_64_chunk_sample_against_the_reference(gpu_ctx):
-    """The benchmarked shape: a seeded sample of 64 full 64 KiB synthetic-text chunks of the
-    4096-chunk set. GPU bytes == the bytes the unmodified reference CLI writes (`oracle/_ref/gmix -c`, one process per
-    host core), and the GPU decompresses the REFERENCE's streams back to the inputs (configs[2])."""
+@pytest.fixture(scope="module")
+def ref64():
+    """A seeded sample of 64 full 64 KiB synthetic-text chunks of the 4096-chunk set and the bytes the unmodified reference CLI
+    writes for them (`oracle/_ref/gmix -c`, one process per host core)."""
     import random
     import ref_cli
     from gmix_b200 import synth
     ids = sorted(random.Random(0x676D6978).sample(range(4096), 64))
     streams = [synth.synthetic_text_chunk(i, 65536) for i in ids]
     want, _ = ref_cli.run_many("-c", streams)
-    got = gpu_ctx.compress_batch(streams)
-    diff = [ids[k] for k in range(len(ids)) if got[k] != want[k]]
-    assert not diff, f"chunks {diff[:8]} differ from the reference ({len(diff)} of {len(ids)})"
-    assert gpu_ctx.decompress_batch(want) == streams
+    return ids, streams, want
+
+
+@pytest.mark.parametrize("pin", [None, "throughput"])
+def test_config2_full_size_64_chunk_sample_against_the_reference(gpu_ctx, ref64, pin):
+    """The benchmarked shape: GPU bytes == the reference's bytes for every chunk of the sample, and
+    the GPU decompresses the REFERENCE's streams back to the inputs (configs[2]). 64 streams alone select the latency
+    configuration (one stream per SM); pinned, the same streams run through the throughput configuration bench.py times
+    (the hybrid order, kernels.h configuration 10)."""
+    ids, streams, want = ref64
+    if pin:
+        cfg = max(k for k, c in enumerate(gpu_ctx.kernel_configs()) if c[3] and c[1] == 0)   # serial with no LSTM warps = hybrid
+        gpu_ctx.set_kernel_config(cfg)
+    try:
+        got = gpu_ctx.compress_batch(streams)
+        diff = [ids[k] for k in range(len(ids)) if got[k] != want[k]]
+        assert not diff, f"chunks {diff[:8]} differ from the reference ({len(diff)} of {len(ids)})"
+        if not pin:
+            assert gpu_ctx.decompress_batch(want) == streams
+    finally:
+        gpu_ctx.set_kernel_config(-1)
 
 
 def test_incompressible_streams_take_the_roomy_retry_path(gpu_ctx, oracle):
