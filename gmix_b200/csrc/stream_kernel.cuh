@@ -2063,8 +2063,11 @@ GMX_DEV inline void EncodeBit(StreamSmem& s, uint8_t* out, int bit) {
 // more work item of the first phase, which saves the barrier between coding and learning. code_out = the stream's
 // output slice. Returns with s.bit_stop refreshed (role-uniform).
 template <int NB, bool PROF, bool LAT = false>
+// next_bookkeeping: BasicContexts::Predict of the NEXT bit (Bookkeeping) runs here, on the thread that closes this bit, instead of
+// as a one-thread phase with its own barrier in front of the next PredictBit (the hybrid compress order; never after the last
+// bit of a stream - the parked state is the one before the next Predict).
 GMX_DEV void LearnBit(StreamSmem& s, const Arena& A, const StreamParams& P, int btid, Lap<PROF>& lap, int known_bit = -1, uint8_t* code_out = nullptr,
-                      bool tables_done = false) {
+                      bool tables_done = false, bool next_bookkeeping = false) {
   const ArenaLayout& L = *A.L;
   const int bit = known_bit >= 0 ? known_bit : s.new_bit;
   const float fbit = (float)bit;
@@ -2145,7 +2148,10 @@ GMX_UNROLL(LAT ? 3 : 1)
       }
     }
   }
-  if (btid == 0) { s.steps++; s.hist_len = hist_after; s.bit_stop = VolatileLoad(&s.error) != 0; }
+  if (btid == 0) {
+    s.steps++; s.hist_len = hist_after; s.bit_stop = VolatileLoad(&s.error) != 0;
+    if (next_bookkeeping) Bookkeeping(s);   // (nothing in the weight update reads the contexts it advances)
+  }
   GroupSync<NB>(BAR_BIT);
   lap.mark(12);
 }
@@ -2334,8 +2340,10 @@ GMX_DEV void HybridCompress(StreamSmem& s, const Arena& A, const StreamParams& P
   for (uint32_t pos = 0; pos < J.n_bytes; ++pos) {
     const uint32_t c = J.in[pos];
     if (bitw) {
-      if (tid == 0) Bookkeeping(s);
-      GroupSync<NB>(BAR_BIT);
+      if (pos == 0 || tracing) {   // later bits: folded into the previous bit's LearnBit
+        if (tid == 0) Bookkeeping(s);
+        GroupSync<NB>(BAR_BIT);
+      }
       lap.mark(0);
       BitBoundaryA<NB>(s, A, tid);   // (the first bit of a byte: s.bb is set)
       lap.mark(2);
@@ -2354,7 +2362,7 @@ GMX_DEV void HybridCompress(StreamSmem& s, const Arena& A, const StreamParams& P
 #pragma unroll 1
       for (int j = 7; j >= 0; --j) {
         const int bit = (c >> j) & 1;
-        if (j != 7) {
+        if (j != 7 && tracing) {
           if (tid == 0) Bookkeeping(s);
           GroupSync<NB>(BAR_BIT);
           lap.mark(0);
@@ -2365,7 +2373,7 @@ GMX_DEV void HybridCompress(StreamSmem& s, const Arena& A, const StreamParams& P
           GroupSync<NB>(BAR_BIT);
           lap.mark(13);
         }
-        LearnBit<NB, PROF, LAT>(s, A, P, tid, lap, bit, J.out, true);
+        LearnBit<NB, PROF, LAT>(s, A, P, tid, lap, bit, J.out, true, !tracing && !(j == 0 && pos + 1 == J.n_bytes));
         if (s.bit_stop) break;
       }
     }
