@@ -1787,8 +1787,98 @@ GMX_DEV inline void GateSelect(StreamSmem& s, const Arena& A, int m, uint32_t c)
 // learn_bit >= 0 (compress): the bit that is about to be coded; the table models then learn it on the threads that have
 // nothing to do while the first warp evaluates the mixer network (they depend on the bit and on the lookups, not on the
 // mixers), and the caller passes tables_done to LearnBit.
-template <int NB, bool PROF, bool LAT = false>
-GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, uint32_t b, int path_bit, int btid, Lap<PROF>& lap, int learn_bit = -1) {
+#if defined(__CUDACC__)
+#define GMX_DEV_INLINE __device__ __forceinline__
+#else
+#define GMX_DEV_INLINE inline
+#endif
+// ahead: the weight update of the CURRENT bit still reads the active flags (bit 0 of the act bytes), so the flags of the next bit
+// go to bit 1 and PredictBit shifts them down when that bit starts.
+GMX_DEV inline void SetAct(StreamSmem& s, int pi, bool v, bool ahead) {
+  s.act[pi] = ahead ? (uint8_t)((s.act[pi] & 1u) | (v ? 2u : 0u)) : (uint8_t)v;
+}
+// The table lookups of one bit (41 x Indirect::Predict, 6 x Match::Predict), work item t = model. bitctx / new_bit / bb are those of
+// the bit being predicted: PredictBit passes the stream's current ones; in compress (hybrid order), where the byte is known, the
+// lookups of the NEXT bit run under this bit's mixer network with the values Bookkeeping is going to produce.
+GMX_DEV_INLINE void TableLookup(StreamSmem& s, const Arena& A, int t, uint32_t bitctx, int new_bit, bool bb, bool zero_inactive, bool ahead) {
+  const ArenaLayout& L = *A.L;
+  if (t < NIND) {  // Indirect::Predict indirect.cpp:28-45
+    const int k = t;
+    const uint32_t M = L.ind_size[k];
+    uint32_t slot = s.ind_base[k] + bitctx;
+    if (slot >= M) slot -= M;
+    uint32_t e;
+    const uint32_t sid = L.ind_sid[k];
+    if (sid) {  // absent == never written == {ns 255, rm 0} (overlay mode: == what the model's table holds)
+      unsigned long long ent;
+      const uint32_t index = slot;
+      slot = SparseFind(A.map(), SparseKey(sid, slot), &ent);
+      e = ent ? (uint32_t)ent & 0xffffu : GMX_IS_OV(L) ? BaseInd(A, k, index) : 0x00ffu;
+      s.ind_found[k] = ent != 0ull;
+    } else {
+      e = A.at<uint16_t>(L.ind_tab[k])[slot];
+    }
+    s.ind_slot[k] = slot;
+    s.ind_state[k] = (uint16_t)e;
+    const uint32_t ns = e & 0xff, rm = e >> 8;
+    const float* pr = A.at<float>(L.ind_pred) + k * 512;
+    const int pi = s.T.ind[k].pred;
+    // both entries are read unconditionally: Indirect::Learn updates exactly these two (a never-seen state learns as
+    // state 0, indirect.cpp:52-54) and takes them from shared memory instead of two more dependent global loads
+    const uint64_t keep = PolicyEvictLast();
+    const float pa = LoadHint(pr + (ns == 255 ? 0 : ns), keep), pb = LoadHint(pr + 256 + rm, keep);
+    s.ind_pa[k] = pa; s.ind_pb[k] = pb;
+    if (ns != 255) { s.preds[pi] = pa; SetAct(s, pi, pa != 0.0f, ahead); }
+    else { SetAct(s, pi, false, ahead); if (zero_inactive) s.preds[pi] = 0.0f; }
+    if (rm != 0) { s.preds[pi + 1] = pb; SetAct(s, pi + 1, pb != 0.0f, ahead); }
+    else { SetAct(s, pi + 1, false, ahead); if (zero_inactive) s.preds[pi + 1] = 0.0f; }
+  } else {  // Match::Predict match.cpp:25-74
+    const int k = t - NIND;
+    uint32_t len = s.m_len[k];
+    const uint32_t cb = s.m_byte[k];
+    uint32_t bp = s.m_bitpos[k];
+    const int hit = new_bit == ((cb & bp) != 0);
+    if (hit) { if (len < 255) ++len; } else len = 0;
+    bp >>= 1;
+    uint32_t cbyte = cb;
+    if (bb) {
+      uint32_t cm = s.m_cur[k];
+      if (s.hist_len != 0 && cm == s.hist_len - 1) len = 0;
+      if (len < 8) {
+        const uint32_t idx = s.ctx[s.T.match[k].ctx] & ((1u << s.T.match[k].log2) - 1);
+        if (L.match_sid[k]) {
+          unsigned long long ent;
+          SparseFind(A.map(), SparseKey(L.match_sid[k], idx), &ent);
+          cm = ent ? (uint32_t)ent : GMX_IS_OV(L) ? BaseMatch(A, k, idx) : 0u;
+        } else {
+          cm = A.at<uint32_t>(L.match_tab[k])[idx];
+        }
+      } else ++cm;
+      if (s.hist_len != 0) {
+        if (cm >= s.hist_len) { SetError(s, GMX_ERR_MATCH_RANGE); cm = 0; }
+        cbyte = HistByte(A, cm);
+      }
+      s.m_cur[k] = cm;
+      bp = 128;
+    }
+    s.m_len[k] = (uint8_t)len; s.m_byte[k] = (uint8_t)cbyte; s.m_bitpos[k] = (uint8_t)bp;
+    const int pi = P_MATCH0 + k;
+    if (len > 2) {
+      const float mp = A.at<float>(L.match_pred)[k * 256 + len];
+      const float p = (cbyte & bp) ? mp : f_sub(1.0f, mp);
+      s.preds[pi] = Logit(p);
+      SetAct(s, pi, p != 0.5f, ahead);
+    } else {
+      SetAct(s, pi, false, ahead);
+      if (zero_inactive) s.preds[pi] = 0.0f;
+    }
+  }
+}
+
+enum : int { BAR_LOOK = 3 };
+// look (LOOK only): bit 0 = this bit's table lookups were already done under the previous bit's network, bit 1 = do the next bit's.
+template <int NB, bool PROF, bool LAT = false, bool LOOK = false>
+GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, uint32_t b, int path_bit, int btid, Lap<PROF>& lap, int learn_bit = -1, int look = 0) {
   const ArenaLayout& L = *A.L;
   const uint32_t bitctx = s.ctx[C_BIT_CONTEXT];
   const bool zero_inactive = s.analysis != 0;  // predictor.cpp:362-365
@@ -1799,76 +1889,10 @@ GMX_DEV void PredictBit(StreamSmem& s, const Arena& A, const StreamParams& P, ui
     if (t >= NIND + NMATCH + 2) {
       const int m = t - (NIND + NMATCH + 2);
       if (s.T.mixer[m].ctx != C_LONGEST) GateSelect(s, A, m, s.ctx[s.T.mixer[m].ctx]);
-    } else if (t < NIND) {  // Indirect::Predict indirect.cpp:28-45
-      const int k = t;
-      const uint32_t M = L.ind_size[k];
-      uint32_t slot = s.ind_base[k] + bitctx;
-      if (slot >= M) slot -= M;
-      uint32_t e;
-      const uint32_t sid = L.ind_sid[k];
-      if (sid) {  // absent == never written == {ns 255, rm 0} (overlay mode: == what the model's table holds)
-        unsigned long long ent;
-        const uint32_t index = slot;
-        slot = SparseFind(A.map(), SparseKey(sid, slot), &ent);
-        e = ent ? (uint32_t)ent & 0xffffu : GMX_IS_OV(L) ? BaseInd(A, k, index) : 0x00ffu;
-        s.ind_found[k] = ent != 0ull;
-      } else {
-        e = A.at<uint16_t>(L.ind_tab[k])[slot];
-      }
-      s.ind_slot[k] = slot;
-      s.ind_state[k] = (uint16_t)e;
-      const uint32_t ns = e & 0xff, rm = e >> 8;
-      const float* pr = A.at<float>(L.ind_pred) + k * 512;
-      const int pi = s.T.ind[k].pred;
-      // both entries are read unconditionally: Indirect::Learn updates exactly these two (a never-seen state learns as
-      // state 0, indirect.cpp:52-54) and takes them from shared memory instead of two more dependent global loads
-      const uint64_t keep = PolicyEvictLast();
-      const float pa = LoadHint(pr + (ns == 255 ? 0 : ns), keep), pb = LoadHint(pr + 256 + rm, keep);
-      s.ind_pa[k] = pa; s.ind_pb[k] = pb;
-      if (ns != 255) { s.preds[pi] = pa; s.act[pi] = pa != 0.0f; }
-      else { s.act[pi] = 0; if (zero_inactive) s.preds[pi] = 0.0f; }
-      if (rm != 0) { s.preds[pi + 1] = pb; s.act[pi + 1] = pb != 0.0f; }
-      else { s.act[pi + 1] = 0; if (zero_inactive) s.preds[pi + 1] = 0.0f; }
-    } else if (t < NIND + NMATCH) {  // Match::Predict match.cpp:25-74
-      const int k = t - NIND;
-      uint32_t len = s.m_len[k];
-      const uint32_t cb = s.m_byte[k];
-      uint32_t bp = s.m_bitpos[k];
-      const int hit = s.new_bit == ((cb & bp) != 0);
-      if (hit) { if (len < 255) ++len; } else len = 0;
-      bp >>= 1;
-      uint32_t cbyte = cb;
-      if (s.bb) {
-        uint32_t cm = s.m_cur[k];
-        if (s.hist_len != 0 && cm == s.hist_len - 1) len = 0;
-        if (len < 8) {
-          const uint32_t idx = s.ctx[s.T.match[k].ctx] & ((1u << s.T.match[k].log2) - 1);
-          if (L.match_sid[k]) {
-            unsigned long long ent;
-            SparseFind(A.map(), SparseKey(L.match_sid[k], idx), &ent);
-            cm = ent ? (uint32_t)ent : GMX_IS_OV(L) ? BaseMatch(A, k, idx) : 0u;
-          } else {
-            cm = A.at<uint32_t>(L.match_tab[k])[idx];
-          }
-        } else ++cm;
-        if (s.hist_len != 0) {
-          if (cm >= s.hist_len) { SetError(s, GMX_ERR_MATCH_RANGE); cm = 0; }
-          cbyte = HistByte(A, cm);
-        }
-        s.m_cur[k] = cm;
-        bp = 128;
-      }
-      s.m_len[k] = (uint8_t)len; s.m_byte[k] = (uint8_t)cbyte; s.m_bitpos[k] = (uint8_t)bp;
-      const int pi = P_MATCH0 + k;
-      if (len > 2) {
-        const float mp = A.at<float>(L.match_pred)[k * 256 + len];
-        const float p = (cbyte & bp) ? mp : f_sub(1.0f, mp);
-        s.preds[pi] = Logit(p);
-        s.act[pi] = p != 0.5f;
-      } else {
-        s.act[pi] = 0;
-        if (zero_inactive) s.preds[pi] = 0.0f;
-      }
+    } else if (t < NIND + NMATCH) {
+      if (!(look & 1)) TableLookup(s, A, t, bitctx, s.new_bit, s.bb != 0, zero_inactive, false);
+      else if (t < NIND) { const int pi = s.T.ind[t].pred; s.act[pi] >>= 1; s.act[pi + 1] >>= 1; }   // looked up one bit ahead
+      else s.act[P_MATCH0 + t - NIND] >>= 1;
     } else {  // per-bit part of ModPPMD / LstmModel::Predict (mod_ppmd.cpp:1662-1681, lstm-model.cpp:36-47)
       const int which = t - (NIND + NMATCH);
       uint32_t fl;
@@ -2031,6 +2055,15 @@ GMX_UNROLL(LAT ? (NL0 + NL1) / 4 : 1)
   } else if (learn_bit >= 0) {
 #pragma unroll 1
     for (int t = btid - 32; t < LEARN_TABLE_ITEMS; t += NB - 32) LearnTables(s, A, learn_bit, t);
+    if (LOOK && (look & 2)) {
+      // every table model has learned this bit (the barrier also orders their sparse-map insertions); nothing later in this bit
+      // reads the lookup state or the table models' predictions (the network and the weight update read xe and bit 0 of act), so
+      // the next bit's lookups - memory round trips - run now, beside the first warp's serial mixer network
+      GroupSync<NB - 32>(BAR_LOOK);
+      const uint32_t next_bitctx = (uint32_t)(s.recent_bits * 2 + learn_bit) - 1u;
+#pragma unroll 1
+      for (int t = btid - 32; t < NIND + NMATCH; t += NB - 32) TableLookup(s, A, t, next_bitctx, learn_bit, false, zero_inactive, true);
+    }
   }
   GroupSync<NB>(BAR_BIT);
   lap.mark(10);
@@ -2128,10 +2161,11 @@ GMX_UNROLL(LAT ? 3 : 1)
         const float4 x = ((const float4*)s.xe)[lane];
         uint32_t on = ((const uint32_t*)s.act)[lane];
         if (left < 4) on &= 0x00ffffffu >> (8 * (3 - left));
-        if (on & 0x000000ffu) v.x = f_sub(v.x, f_mul(upd, x.x));
-        if (on & 0x0000ff00u) v.y = f_sub(v.y, f_mul(upd, x.y));
-        if (on & 0x00ff0000u) v.z = f_sub(v.z, f_mul(upd, x.z));
-        if (on & 0xff000000u) v.w = f_sub(v.w, f_mul(upd, x.w));
+        // (bit 0 of an act byte: bit 1 may already hold the next bit's flag, TableLookup ahead)
+        if (on & 0x00000001u) v.x = f_sub(v.x, f_mul(upd, x.x));
+        if (on & 0x00000100u) v.y = f_sub(v.y, f_mul(upd, x.y));
+        if (on & 0x00010000u) v.z = f_sub(v.z, f_mul(upd, x.z));
+        if (on & 0x01000000u) v.w = f_sub(v.w, f_mul(upd, x.w));
         if (shrink) {   // applies to every weight of the set (mixer.cpp:170-174), used or not; pad lanes hold 0
           v.x = f_mul(v.x, keep); v.y = f_mul(v.y, keep); v.z = f_mul(v.z, keep); v.w = f_mul(v.w, keep);
         }
@@ -2367,7 +2401,8 @@ GMX_DEV void HybridCompress(StreamSmem& s, const Arena& A, const StreamParams& P
           GroupSync<NB>(BAR_BIT);
           lap.mark(0);
         }
-        PredictBit<NB, PROF, LAT>(s, A, P, pos, 7 - j, tid, lap, bit);
+        const int look = tracing ? 0 : ((j != 7 ? 1 : 0) | (j != 0 ? 2 : 0));   // table lookups of bits 1..7 run one bit ahead
+        PredictBit<NB, PROF, LAT, true>(s, A, P, pos, 7 - j, tid, lap, bit, look);
         if (tracing) {
           if (tid == 0) Trace(s, P, (uint64_t)pos * 8 + (7 - j));
           GroupSync<NB>(BAR_BIT);
