@@ -9,7 +9,7 @@ LIB = os.path.join(ROOT, "lib", "libgmix_b200.so")
 SOURCES = ["host.cu", "kernel_compress.cu", "kernel_decompress.cu", "kernel_compress_prof.cu", "kernel_step.cu", "kernel_generate.cu", "kernel_genstep.cu", "kernel_gate.cu"]
 DEPS = ["host.cu", "kernel_compress.cu", "kernel_decompress.cu", "kernel_compress_prof.cu", "kernel_step.cu", "kernel_generate.cu", "kernel_genstep.cu", "kernel_gate.cu", "gate_gemm.cuh", "checkpoint.h", "kernels.h", "stream_kernel.cuh", "ppmd.cuh", "dmath.cuh", "spec.cuh", "layout.h", "nonstationary.inc",
         os.path.join("..", "..", "include", "gmix_b200.h"), os.path.join("..", "host", "runner.cpp"), os.path.join("..", "host", "predictor.h"),
-        os.path.join("..", "host", "coder.h"), os.path.join("..", "host", "multi_gpu.h"), os.path.join("..", "host", "shard.h"),
+        os.path.join("..", "host", "coder.h"), os.path.join("..", "host", "dictionary.h"), os.path.join("..", "host", "dictionary_prep.cpp"), os.path.join("..", "host", "multi_gpu.h"), os.path.join("..", "host", "shard.h"),
         os.path.join("..", "..", "scripts", "ncu_case.cpp")]
 
 NVCC_FLAGS = [
@@ -89,6 +89,10 @@ def build_host_tools():
     """C++ host layer above the C ABI: the gmixb200 runner (reference CLI mirror) and the profiler driver."""
     libdir = os.path.dirname(LIB)
     cxx = os.environ.get("CXX", "g++")
+    # host-only tool: the reference's dictionary preprocessing (host/dictionary.h), no GPU library behind it
+    cmd = [cxx, "-std=c++17", "-O2", "-o", os.path.join(libdir, "dictionary-prep"), os.path.join(ROOT, "host", "dictionary_prep.cpp")]
+    print("[gmix_b200] " + " ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
     for src, exe in ((os.path.join(ROOT, "host", "runner.cpp"), "gmixb200"), (os.path.join(ROOT, "..", "scripts", "ncu_case.cpp"), "ncu_case")):
         cmd = [cxx, "-std=c++17", "-O2", "-ffp-contract=off", "-o", os.path.join(libdir, exe), src, "-L" + libdir, "-lgmix_b200", "-Wl,-rpath,$ORIGIN"]
         if exe == "gmixb200":   # the multi-GPU host (host/multi_gpu.h) talks to the CUDA runtime and NCCL directly
