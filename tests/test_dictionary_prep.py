@@ -78,7 +78,7 @@ def test_round_trip(tool, tmp_path, name):
 
 
 def test_committed_vectors(tool, tmp_path):
-    data = open(os.path.join(GOLD, "dict_prep_crafted.in"), "rb").read()
+    data = open(os.path.join(GOLD, "dict_prep_crafted.txt"), "rb").read()
     want = open(os.path.join(GOLD, "dict_prep_crafted.enc"), "rb").read()
     assert run(tool, "-e", data, tmp_path) == want
     assert run(tool, "-d", want, tmp_path) == data
